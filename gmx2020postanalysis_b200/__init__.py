@@ -1,0 +1,9 @@
+"""B200-native per-frame trajectory analysis (centres -> density -> RDF) behind the itp::GmxHandle surface.
+
+The product is the C-ABI library ``libb2a.so`` (CUDA, sm_100a; ``include/b2a.h``) and the C++ drop-in
+header ``include/itp/gmx``.  This Python package is the thin host-side mirror used by tests and
+``bench.py``: ctypes bindings, the synthetic trajectory generator and file writers.
+"""
+from . import synth, trajio  # noqa: F401
+
+__all__ = ["synth", "trajio"]

@@ -1,0 +1,162 @@
+"""Synthetic systems: SPC/E water boxes and a 25+7-site ionic liquid.
+
+Thin ctypes wrapper over ``libb2a_synth.so`` (include/b2a_synth.h) plus the system definitions
+(templates, masses, charges, molecule/residue tables, index groups) that the reference would read
+from a .tpr/.ndx (reference include/itp/gmx_bits/gmx_handle.ipp:23-34, 419-468).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "libb2a_synth.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(path)
+        lib.b2a_synth_species.restype = ctypes.c_int
+        lib.b2a_synth_species.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        lib.b2a_synth_hash.restype = ctypes.c_uint64
+        lib.b2a_synth_hash.argtypes = [ctypes.c_uint64] * 5
+        _lib = lib
+    return _lib
+
+
+def synth_hash(seed, frame, species, mol, lane) -> int:
+    return int(_load().b2a_synth_hash(seed, frame, species, mol, lane))
+
+
+@dataclass
+class Species:
+    name: str
+    nmol: int
+    tmpl: np.ndarray            # [napm, 3] float32, nm
+    mass: np.ndarray            # [napm] float32 (GROMACS t_atom.m is `real`)
+    charge: np.ndarray          # [napm] float32
+    atomnames: list
+    split_atoms: bool = False   # topology lists every atom as its own molecule/residue (O-O RDF)
+
+    @property
+    def napm(self) -> int:
+        return int(self.tmpl.shape[0])
+
+
+@dataclass
+class System:
+    species: list
+    L: np.ndarray               # [3] float32 box lengths
+    seed: int = 20200101
+    groups: dict = field(default_factory=dict)   # name -> int32 atom indices (0-based)
+
+    @property
+    def natoms(self) -> int:
+        return sum(s.nmol * s.napm for s in self.species)
+
+    def offsets(self):
+        off, out = 0, []
+        for s in self.species:
+            out.append(off)
+            off += s.nmol * s.napm
+        return out
+
+    def frame(self, f: int, out: np.ndarray | None = None) -> np.ndarray:
+        lib = _load()
+        if out is None:
+            out = np.empty((self.natoms, 3), dtype=np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.natoms, 3)
+        L = np.ascontiguousarray(self.L, dtype=np.float32)
+        for sid, (s, off) in enumerate(zip(self.species, self.offsets())):
+            tm = np.ascontiguousarray(s.tmpl, dtype=np.float32)
+            view = out[off:off + s.nmol * s.napm]
+            rc = lib.b2a_synth_species(self.seed, f, sid, s.nmol, s.napm, tm.ctypes.data, L.ctypes.data,
+                                       view.ctypes.data)
+            if rc != 0:
+                raise RuntimeError("b2a_synth_species failed")
+        return out
+
+    def frames(self, f0: int, n: int, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((n, self.natoms, 3), dtype=np.float32)
+        for k in range(n):
+            self.frame(f0 + k, out[k])
+        return out
+
+    def box9(self) -> np.ndarray:
+        b = np.zeros(9, dtype=np.float32)
+        b[0], b[4], b[8] = self.L
+        return b
+
+    # ---- per-atom topology tables (what read_tpx_top would deliver) -------------------------------
+    def atom_tables(self):
+        m, q, resind, typ, names, mols = [], [], [], [], [], [0]
+        res = 0
+        for sid, s in enumerate(self.species):
+            for _ in range(s.nmol):
+                for j in range(s.napm):
+                    m.append(s.mass[j]); q.append(s.charge[j]); typ.append(sid); names.append(s.atomnames[j])
+                    if s.split_atoms:
+                        resind.append(res); res += 1
+                        mols.append(mols[-1] + 1)
+                    else:
+                        resind.append(res)
+                if not s.split_atoms:
+                    res += 1
+                    mols.append(mols[-1] + s.napm)
+        return (np.asarray(m, np.float32), np.asarray(q, np.float32), np.asarray(resind, np.int32),
+                np.asarray(typ, np.int32), names, np.asarray(mols, np.int32))
+
+
+# SPC/E: O-H 0.1 nm, H-O-H 109.47 deg
+_SPCE_TMPL = np.array([[0.0, 0.0, 0.0],
+                       [0.08164904, 0.05773596, 0.0],
+                       [-0.08164904, 0.05773596, 0.0]], dtype=np.float32)
+_SPCE_MASS = np.array([15.9994, 1.008, 1.008], dtype=np.float32)
+_SPCE_Q = np.array([-0.8476, 0.4238, 0.4238], dtype=np.float32)
+
+
+def water_box(nmol: int, L: float, seed: int = 20200101, split_atoms: bool = False) -> System:
+    """SPC/E box.  Groups: SOL (all atoms), OW (oxygens).  ``split_atoms`` gives the topology in which every
+    atom is its own molecule so an O-only group passes GmxHandle::init(true) (option 1)."""
+    sp = Species("SOL", nmol, _SPCE_TMPL, _SPCE_MASS, _SPCE_Q, ["OW", "HW1", "HW2"], split_atoms)
+    sysm = System([sp], np.array([L, L, L], np.float32), seed)
+    n = 3 * nmol
+    sysm.groups = {"SOL": np.arange(n, dtype=np.int32), "OW": np.arange(0, n, 3, dtype=np.int32)}
+    return sysm
+
+
+def _blob_template(napm: int, radius: float, key: int) -> np.ndarray:
+    """Deterministic rigid template: napm sites inside a sphere of the given radius (extent <= 2*radius)."""
+    pts, lane = [], 0
+    while len(pts) < napm:
+        p = np.array([2.0 * ((synth_hash(key, 0, 0, len(pts), lane + a) >> 40) / 16777216.0) - 1.0 for a in range(3)])
+        lane += 3
+        if p @ p <= 1.0:
+            pts.append(p * radius)
+    return np.asarray(pts, dtype=np.float32)
+
+
+def ionic_liquid(npairs: int, L: float, seed: int = 20200103) -> System:
+    """31 250 x (25-site cation + 7-site anion) = 1M atoms at npairs=31250.
+    Cation total charge +0.8, anion -0.8, molecular extent <= 0.6 nm."""
+    cm = np.array(([12.011, 1.008, 1.008, 14.007, 12.011] * 5), dtype=np.float32)
+    cq = np.full(25, 0.8 / 25, dtype=np.float32)
+    cq[::5] += 0.05; cq[1::5] -= 0.05          # non-uniform but still +0.8 overall (to float rounding)
+    am = np.array([10.811, 18.998, 18.998, 18.998, 18.998, 12.011, 14.007], dtype=np.float32)
+    aq = np.array([0.9, -0.45, -0.45, -0.45, -0.45, 0.2, -0.1], dtype=np.float32)
+    cat = Species("CAT", npairs, _blob_template(25, 0.3, 7001), cm, cq, [f"C{j}" for j in range(25)])
+    ani = Species("ANI", npairs, _blob_template(7, 0.2, 7002), am, aq, [f"A{j}" for j in range(7)])
+    sysm = System([cat, ani], np.array([L, L, L], np.float32), seed)
+    nc = 25 * npairs
+    sysm.groups = {"CAT": np.arange(nc, dtype=np.int32), "ANI": np.arange(nc, nc + 7 * npairs, dtype=np.int32),
+                   "System": np.arange(nc + 7 * npairs, dtype=np.int32)}
+    return sysm

@@ -1,0 +1,627 @@
+/*
+ * gmxstub.cpp -- implementation of the libgromacs stand-in declared in
+ * include/gromacs/gmxstub_api.h.  See gmxstub/README.md for the file formats.
+ *
+ * This is NOT GROMACS code: it implements, from scratch, just enough behaviour behind
+ * the GROMACS entry-point names for itp::GmxHandle-style programs to run in an image
+ * that has no libgromacs (command-line parsing of t_pargs / t_filenm tables, a binary
+ * topology reader, an .ndx reader with stdin group selection, and a raw float trajectory
+ * reader with -b/-e/-dt time selection).
+ */
+#include "gromacs/gmxstub_api.h"
+
+#include <cctype>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <sstream>
+
+struct gmx_output_env_t
+{
+    std::string program;
+};
+
+namespace
+{
+struct TimeSel
+{
+    bool   has_b = false, has_e = false, has_dt = false;
+    double b = 0, e = 0, dt = 0;
+} g_time;
+
+std::string g_program = "gmxstub";
+
+const char* default_ext(int ftp)
+{
+    switch (ftp)
+    {
+        case efTRX: case efTRO: case efXTC: case efCOMPRESSED: return ".xtc";
+        case efTRR: case efTRN: return ".trr";
+        case efTPR: case efTPS: return ".tpr";
+        case efNDX: return ".ndx";
+        case efXVG: return ".xvg";
+        case efDAT: return ".dat";
+        case efLOG: return ".log";
+        case efOUT: return ".out";
+        case efGRO: case efSTX: case efSTO: return ".gro";
+        case efPDB: return ".pdb";
+        case efTOP: return ".top";
+        case efCSV: return ".csv";
+        default: return ".dat";
+    }
+}
+
+const char* default_base(int ftp)
+{
+    switch (ftp)
+    {
+        case efTRX: case efTRO: case efXTC: case efCOMPRESSED: case efTRR: case efTRN: return "traj";
+        case efTPR: case efTPS: return "topol";
+        case efNDX: return "index";
+        default: return "out";
+    }
+}
+
+bool has_extension(const std::string& s)
+{
+    size_t slash = s.find_last_of('/');
+    size_t dot   = s.find_last_of('.');
+    return dot != std::string::npos && (slash == std::string::npos || dot > slash) && dot + 1 < s.size();
+}
+
+std::string with_ext(const std::string& name, int ftp)
+{
+    return has_extension(name) ? name : name + default_ext(ftp);
+}
+
+void print_help(int nfile, t_filenm fnm[], int npargs, t_pargs* pa, int ndesc, const char** desc)
+{
+    std::printf("SYNOPSIS\n\n%s", g_program.c_str());
+    for (int i = 0; i < nfile; ++i) std::printf(" [%s <file>]", fnm[i].opt);
+    for (int i = 0; i < npargs; ++i) std::printf(" [%s ...]", pa[i].option);
+    std::printf("\n\nDESCRIPTION\n\n");
+    for (int i = 0; i < ndesc; ++i) std::printf("%s\n", desc[i]);
+    std::printf("\nOPTIONS\n\n");
+    for (int i = 0; i < nfile; ++i)
+        std::printf(" %-8s %-20s %s\n", fnm[i].opt, fnm[i].filenames.empty() ? "" : fnm[i].filenames[0].c_str(),
+                    (fnm[i].flag & ffOPT) ? "(Opt.)" : "");
+    for (int i = 0; i < npargs; ++i) std::printf(" %-12s %s\n", pa[i].option, pa[i].desc ? pa[i].desc : "");
+    std::printf(" %-12s %s\n %-12s %s\n %-12s %s\n", "-b", "first frame time (ps)", "-e", "last frame time (ps)", "-dt",
+                "only use frames with t MOD dt == first time (ps)");
+}
+
+[[noreturn]] void usage_error(const char* what, const char* arg)
+{
+    std::fprintf(stderr, "\nError in user input:\n%s '%s'\n", what, arg);
+    std::exit(1);
+}
+
+double to_double(const char* opt, const char* s)
+{
+    char*  end = nullptr;
+    double v   = std::strtod(s, &end);
+    if (end == s || *end != '\0') usage_error("Invalid value for option", opt);
+    return v;
+}
+} // namespace
+
+gmx_bool parse_common_args(int* argc, char* argv[], unsigned long Flags, int nfile, t_filenm fnm[], int npargs,
+                           t_pargs* pa, int ndesc, const char** desc, int /*nbugs*/, const char** /*bugs*/,
+                           gmx_output_env_t** oenv)
+{
+    if (*argc > 0 && argv[0]) g_program = argv[0];
+    /* defaults for file options */
+    for (int i = 0; i < nfile; ++i)
+    {
+        fnm[i].filenames.clear();
+        std::string base = fnm[i].fn ? fnm[i].fn : default_base(fnm[i].ftp);
+        fnm[i].filenames.push_back(with_ext(base, fnm[i].ftp));
+        fnm[i].flag &= ~static_cast<unsigned long>(ffSET);
+    }
+    bool want_help = false;
+    for (int a = 1; a < *argc; ++a)
+    {
+        const char* arg = argv[a];
+        if (!std::strcmp(arg, "-h") || !std::strcmp(arg, "-help") || !std::strcmp(arg, "--help"))
+        {
+            want_help = true;
+            continue;
+        }
+        bool matched = false;
+        for (int i = 0; i < nfile && !matched; ++i)
+        {
+            if (!std::strcmp(arg, fnm[i].opt))
+            {
+                matched = true;
+                fnm[i].flag |= ffSET;
+                if (a + 1 < *argc && argv[a + 1][0] != '-')
+                {
+                    fnm[i].filenames[0] = with_ext(argv[++a], fnm[i].ftp);
+                }
+            }
+        }
+        for (int i = 0; i < npargs && !matched; ++i)
+        {
+            t_pargs& p = pa[i];
+            if (p.type == etBOOL)
+            {
+                if (!std::strcmp(arg, p.option)) { *p.u.b = TRUE; p.bSet = TRUE; matched = true; }
+                else if (!std::strncmp(arg, "-no", 3) && !std::strcmp(arg + 3, p.option + 1)) { *p.u.b = FALSE; p.bSet = TRUE; matched = true; }
+                continue;
+            }
+            if (std::strcmp(arg, p.option)) continue;
+            matched = true;
+            p.bSet  = TRUE;
+            int need = (p.type == etRVEC) ? 3 : 1;
+            if (a + need >= *argc + 0 && a + need > *argc - 1 + 0)
+            {
+                if (a + need > *argc - 1) usage_error("Missing value for option", arg);
+            }
+            switch (p.type)
+            {
+                case etINT: *p.u.i = static_cast<int>(std::lround(to_double(arg, argv[++a]))); break;
+                case etINT64: *p.u.is = static_cast<int64_t>(std::llround(to_double(arg, argv[++a]))); break;
+                case etREAL:
+                case etTIME: *p.u.r = static_cast<real>(to_double(arg, argv[++a])); break;
+                case etSTR: *p.u.c = argv[++a]; break;
+                case etENUM: p.u.c[0] = argv[++a]; break;
+                case etRVEC:
+                    for (int k = 0; k < 3; ++k) (*p.u.rv)[k] = static_cast<real>(to_double(arg, argv[++a]));
+                    break;
+                default: usage_error("Unsupported option type for", arg);
+            }
+        }
+        if (!matched && (Flags & PCA_CAN_TIME))
+        {
+            if (!std::strcmp(arg, "-b") && a + 1 < *argc) { g_time.has_b = true; g_time.b = to_double(arg, argv[++a]); matched = true; }
+            else if (!std::strcmp(arg, "-e") && a + 1 < *argc) { g_time.has_e = true; g_time.e = to_double(arg, argv[++a]); matched = true; }
+            else if (!std::strcmp(arg, "-dt") && a + 1 < *argc) { g_time.has_dt = true; g_time.dt = to_double(arg, argv[++a]); matched = true; }
+        }
+        if (!matched) usage_error("Unknown command-line option", arg);
+    }
+    if (want_help)
+    {
+        print_help(nfile, fnm, npargs, pa, ndesc, desc);
+        return FALSE;
+    }
+    /* required input files must exist */
+    for (int i = 0; i < nfile; ++i)
+    {
+        if ((fnm[i].flag & ffREAD) && (!(fnm[i].flag & ffOPT) || (fnm[i].flag & ffSET)))
+        {
+            FILE* fp = std::fopen(fnm[i].filenames[0].c_str(), "rb");
+            if (!fp) usage_error("Input file does not exist or is not accessible:", fnm[i].filenames[0].c_str());
+            std::fclose(fp);
+        }
+    }
+    if (oenv)
+    {
+        *oenv            = new gmx_output_env_t;
+        (*oenv)->program = g_program;
+    }
+    return TRUE;
+}
+
+static const t_filenm* find_opt(const char* opt, int nfile, const t_filenm fnm[])
+{
+    for (int i = 0; i < nfile; ++i)
+        if (!std::strcmp(opt, fnm[i].opt)) return &fnm[i];
+    return nullptr;
+}
+static const t_filenm* find_ftp(int ftp, int nfile, const t_filenm fnm[])
+{
+    for (int i = 0; i < nfile; ++i)
+        if (fnm[i].ftp == ftp) return &fnm[i];
+    return nullptr;
+}
+static bool is_active(const t_filenm* f) { return f && (!(f->flag & ffOPT) || (f->flag & ffSET)); }
+
+const char* opt2fn(const char* opt, int nfile, const t_filenm fnm[])
+{
+    const t_filenm* f = find_opt(opt, nfile, fnm);
+    if (!f || f->filenames.empty()) gmx_fatal(FARGS, "opt2fn: no file for option %s", opt);
+    return f->filenames[0].c_str();
+}
+const char* opt2fn_null(const char* opt, int nfile, const t_filenm fnm[])
+{
+    const t_filenm* f = find_opt(opt, nfile, fnm);
+    return (is_active(f) && !f->filenames.empty()) ? f->filenames[0].c_str() : nullptr;
+}
+const char* ftp2fn(int ftp, int nfile, const t_filenm fnm[])
+{
+    const t_filenm* f = find_ftp(ftp, nfile, fnm);
+    if (!f || f->filenames.empty()) gmx_fatal(FARGS, "ftp2fn: no file of type %d", ftp);
+    return f->filenames[0].c_str();
+}
+const char* ftp2fn_null(int ftp, int nfile, const t_filenm fnm[])
+{
+    const t_filenm* f = find_ftp(ftp, nfile, fnm);
+    return (is_active(f) && !f->filenames.empty()) ? f->filenames[0].c_str() : nullptr;
+}
+gmx_bool opt2bSet(const char* opt, int nfile, const t_filenm fnm[])
+{
+    const t_filenm* f = find_opt(opt, nfile, fnm);
+    return (f && (f->flag & ffSET)) ? TRUE : FALSE;
+}
+gmx_bool opt2parg_bSet(const char* opt, int nargs, const t_pargs pa[])
+{
+    for (int i = 0; i < nargs; ++i)
+        if (!std::strcmp(opt, pa[i].option)) return pa[i].bSet;
+    return FALSE;
+}
+
+int gmx_run_cmain(int argc, char* argv[], int (*mainFunction)(int, char*[])) { return mainFunction(argc, argv); }
+
+void gmx_fatal(int /*fatal_errno*/, const char* file, int line, const char* fmt, ...)
+{
+    std::fflush(stdout);
+    std::fprintf(stderr, "\n-------------------------------------------------------\nProgram:     %s\nSource file: %s (line %d)\n\nFatal error:\n",
+                 g_program.c_str(), file, line);
+    va_list ap;
+    va_start(ap, fmt);
+    std::vfprintf(stderr, fmt, ap);
+    va_end(ap);
+    std::fprintf(stderr, "\n-------------------------------------------------------\n");
+    std::exit(1);
+}
+
+FILE* gmx_ffopen(const char* file, const char* mode)
+{
+    FILE* fp = std::fopen(file, mode);
+    if (!fp) gmx_fatal(FARGS, "Cannot open file %s (mode %s)", file, mode);
+    return fp;
+}
+int gmx_ffclose(FILE* fp) { return std::fclose(fp); }
+
+/* ---- topology (.b2p) ---------------------------------------------------------------- */
+namespace
+{
+struct TopHeader
+{
+    char    magic[8];
+    int32_t natoms, nmols, ntypes, reserved;
+};
+struct TopAtom
+{
+    float   m, q;
+    int32_t resind, type;
+    char    name[8];
+};
+template <typename T>
+void read_exact(FILE* fp, T* dst, size_t n, const char* fn)
+{
+    if (n && std::fread(dst, sizeof(T), n, fp) != n) gmx_fatal(FARGS, "Unexpected end of file in %s", fn);
+}
+} // namespace
+
+int read_tpx_top(const char* fn, t_inputrec* ir, matrix box, int* natoms, rvec* /*x*/, rvec* /*v*/, t_topology* top)
+{
+    FILE*     fp = gmx_ffopen(fn, "rb");
+    TopHeader h;
+    read_exact(fp, &h, 1, fn);
+    if (std::memcmp(h.magic, "B2ATOP01", 8) != 0) gmx_fatal(FARGS, "%s is not a gmxstub topology (bad magic)", fn);
+    std::vector<TopAtom> at(h.natoms);
+    read_exact(fp, at.data(), at.size(), fn);
+    std::memset(top, 0, sizeof(*top));
+    top->atoms.nr = h.natoms;
+    snew(top->atoms.atom, h.natoms);
+    snew(top->atoms.atomname, h.natoms);
+    int nres = 0;
+    for (int i = 0; i < h.natoms; ++i)
+    {
+        t_atom& a = top->atoms.atom[i];
+        a.m = a.mB = at[i].m;
+        a.q = a.qB = at[i].q;
+        a.type = a.typeB = static_cast<unsigned short>(at[i].type);
+        a.resind         = at[i].resind;
+        if (a.resind + 1 > nres) nres = a.resind + 1;
+        char** slot = nullptr;
+        snew(slot, 1);
+        char* nm = nullptr;
+        snew(nm, 9);
+        std::memcpy(nm, at[i].name, 8);
+        *slot                  = nm;
+        top->atoms.atomname[i] = slot;
+    }
+    top->atoms.nres      = nres;
+    top->atoms.haveMass  = TRUE;
+    top->atoms.haveCharge = TRUE;
+    top->atoms.haveType  = TRUE;
+    top->mols.nr         = h.nmols;
+    snew(top->mols.index, h.nmols + 1);
+    {
+        std::vector<int32_t> mi(h.nmols + 1);
+        read_exact(fp, mi.data(), mi.size(), fn);
+        for (int i = 0; i <= h.nmols; ++i) top->mols.index[i] = mi[i];
+    }
+    top->mols.nalloc_index = h.nmols + 1;
+    top->atomtypes.nr      = h.ntypes;
+    top->idef.ntypes       = h.ntypes * h.ntypes;
+    top->idef.atnr         = h.ntypes;
+    snew(top->idef.iparams, static_cast<size_t>(h.ntypes) * h.ntypes);
+    {
+        std::vector<float> lj(static_cast<size_t>(h.ntypes) * h.ntypes * 2);
+        read_exact(fp, lj.data(), lj.size(), fn);
+        for (size_t i = 0; i < lj.size() / 2; ++i)
+        {
+            top->idef.iparams[i].lj.c6  = lj[2 * i];
+            top->idef.iparams[i].lj.c12 = lj[2 * i + 1];
+        }
+    }
+    std::fclose(fp);
+    if (natoms) *natoms = h.natoms;
+    if (ir) { std::memset(ir, 0, sizeof(*ir)); ir->ePBC = 0; }
+    if (box) std::memset(box, 0, sizeof(matrix));
+    return 0; /* epbcXYZ */
+}
+
+/* ---- index groups (.ndx) ------------------------------------------------------------ */
+namespace
+{
+struct NdxGroup
+{
+    std::string      name;
+    std::vector<int> atoms;
+};
+
+std::vector<NdxGroup> load_ndx(const char* fn)
+{
+    std::vector<NdxGroup> groups;
+    FILE*                 fp = gmx_ffopen(fn, "r");
+    std::string           text;
+    char                  buf[1 << 16];
+    size_t                n;
+    while ((n = std::fread(buf, 1, sizeof(buf), fp)) > 0) text.append(buf, n);
+    std::fclose(fp);
+    const char* p   = text.c_str();
+    const char* end = p + text.size();
+    while (p < end)
+    {
+        while (p < end && std::isspace(static_cast<unsigned char>(*p))) ++p;
+        if (p >= end) break;
+        if (*p == '[')
+        {
+            const char* q = p + 1;
+            while (q < end && *q != ']') ++q;
+            std::string name(p + 1, q);
+            size_t      a = name.find_first_not_of(" \t");
+            size_t      b = name.find_last_not_of(" \t");
+            groups.push_back({ a == std::string::npos ? std::string() : name.substr(a, b - a + 1), {} });
+            p = (q < end) ? q + 1 : end;
+        }
+        else if (*p == ';')
+        {
+            while (p < end && *p != '\n') ++p;
+        }
+        else
+        {
+            char* e = nullptr;
+            long  v = std::strtol(p, &e, 10);
+            if (e == p) gmx_fatal(FARGS, "Invalid token in index file %s", fn);
+            if (groups.empty()) gmx_fatal(FARGS, "Index file %s: atom number before first group header", fn);
+            groups.back().atoms.push_back(static_cast<int>(v - 1)); /* .ndx is 1-based */
+            p = e;
+        }
+    }
+    return groups;
+}
+
+void select_groups(const std::vector<NdxGroup>& groups, int ngrps, int isize[], int* index[], char* grpnames[])
+{
+    for (size_t g = 0; g < groups.size(); ++g)
+        std::printf("Group %5zu (%15s) has %5zu elements\n", g, groups[g].name.c_str(), groups[g].atoms.size());
+    for (int s = 0; s < ngrps; ++s)
+    {
+        int choice = -1;
+        if (groups.size() == 1) choice = 0;
+        else
+        {
+            std::printf("Select a group: ");
+            std::fflush(stdout);
+            char tok[256];
+            if (std::scanf("%255s", tok) == 1)
+            {
+                char* e = nullptr;
+                long  v = std::strtol(tok, &e, 10);
+                if (e != tok && *e == '\0') choice = static_cast<int>(v);
+                else
+                    for (size_t g = 0; g < groups.size(); ++g)
+                        if (groups[g].name == tok) choice = static_cast<int>(g);
+            }
+            else
+            {
+                choice = s; /* no stdin: take groups in file order */
+            }
+        }
+        if (choice < 0 || choice >= static_cast<int>(groups.size())) gmx_fatal(FARGS, "Invalid group selection");
+        const NdxGroup& G = groups[choice];
+        std::printf("Selected %d: '%s'\n", choice, G.name.c_str());
+        isize[s] = static_cast<int>(G.atoms.size());
+        snew(index[s], G.atoms.size());
+        for (size_t i = 0; i < G.atoms.size(); ++i) index[s][i] = G.atoms[i];
+        char* nm = nullptr;
+        snew(nm, G.name.size() + 1);
+        std::memcpy(nm, G.name.c_str(), G.name.size());
+        grpnames[s] = nm;
+    }
+}
+} // namespace
+
+void rd_index(const char* statfile, int ngrps, int isize[], int* index[], char* grpnames[])
+{
+    if (!statfile) gmx_fatal(FARGS, "No index file specified");
+    select_groups(load_ndx(statfile), ngrps, isize, index, grpnames);
+}
+
+void get_index(const t_atoms* atoms, const char* fnm, int ngrps, int isize[], int* index[], char* grpnames[])
+{
+    if (fnm)
+    {
+        rd_index(fnm, ngrps, isize, index, grpnames);
+        return;
+    }
+    /* default groups when no index file is given: the whole system only */
+    std::vector<NdxGroup> groups(1);
+    groups[0].name = "System";
+    groups[0].atoms.resize(atoms ? atoms->nr : 0);
+    for (size_t i = 0; i < groups[0].atoms.size(); ++i) groups[0].atoms[i] = static_cast<int>(i);
+    select_groups(groups, ngrps, isize, index, grpnames);
+}
+
+/* ---- trajectory (.b2t) -------------------------------------------------------------- */
+struct t_trxstatus
+{
+    FILE*   fp      = nullptr;
+    int     natoms  = 0;
+    int     nframes = 0;
+    int     fflags  = 0; /* bit0 x, bit1 v, bit2 f as stored in the file */
+    int     next    = 0; /* next frame index in file */
+    int     nread   = 0;
+    int     want    = 0; /* TRX_* flags requested */
+    bool    have_t0 = false;
+    double  t0      = 0;
+    std::string fn;
+    std::vector<float> scratch;
+};
+
+namespace
+{
+struct TrjHeader
+{
+    char    magic[8];
+    int32_t natoms, nframes, flags, reserved;
+};
+
+size_t frame_floats(const t_trxstatus* st)
+{
+    size_t per = 0;
+    if (st->fflags & 1) per += 3;
+    if (st->fflags & 2) per += 3;
+    if (st->fflags & 4) per += 3;
+    return 10 + per * static_cast<size_t>(st->natoms);
+}
+
+bool time_selected(t_trxstatus* st, double t, bool* past_end)
+{
+    *past_end = false;
+    if (g_time.has_e && t > g_time.e + 1e-9) { *past_end = true; return false; }
+    if (g_time.has_b && t < g_time.b - 1e-9) return false;
+    if (g_time.has_dt && g_time.dt > 0)
+    {
+        if (!st->have_t0) return true;
+        double k = (t - st->t0) / g_time.dt;
+        if (std::fabs(k - std::round(k)) > 1e-6) return false;
+    }
+    return true;
+}
+
+/* Reads the next selected frame header (time, box) into hdr[10]; leaves the file positioned at x. */
+bool next_selected(t_trxstatus* st, float hdr[10])
+{
+    while (st->next < st->nframes)
+    {
+        if (std::fread(hdr, sizeof(float), 10, st->fp) != 10) return false;
+        bool past = false;
+        bool sel  = time_selected(st, hdr[0], &past);
+        if (past) return false;
+        st->next++;
+        if (sel)
+        {
+            if (!st->have_t0) { st->have_t0 = true; st->t0 = hdr[0]; }
+            return true;
+        }
+        std::fseek(st->fp, static_cast<long>((frame_floats(st) - 10) * sizeof(float)), SEEK_CUR);
+    }
+    return false;
+}
+
+t_trxstatus* open_trx(const char* fn)
+{
+    t_trxstatus* st = new t_trxstatus;
+    st->fp          = gmx_ffopen(fn, "rb");
+    st->fn          = fn;
+    std::setvbuf(st->fp, nullptr, _IOFBF, 8 << 20);
+    TrjHeader h;
+    read_exact(st->fp, &h, 1, fn);
+    if (std::memcmp(h.magic, "B2ATRJ01", 8) != 0) gmx_fatal(FARGS, "%s is not a gmxstub trajectory (bad magic)", fn);
+    st->natoms  = h.natoms;
+    st->nframes = h.nframes;
+    st->fflags  = h.flags;
+    return st;
+}
+
+bool deliver(t_trxstatus* st, t_trxframe* fr)
+{
+    float hdr[10];
+    if (!next_selected(st, hdr)) return false;
+    fr->time  = hdr[0];
+    fr->bTime = TRUE;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) fr->box[a][b] = hdr[1 + 3 * a + b];
+    fr->bBox    = TRUE;
+    fr->natoms  = st->natoms;
+    fr->step    = st->next - 1;
+    fr->bStep   = TRUE;
+    const size_t n3 = static_cast<size_t>(st->natoms) * 3;
+    auto         rd = [&](int bit, int want_bit, rvec* dst, gmx_bool* have) {
+        if (!(st->fflags & bit)) { *have = FALSE; return; }
+        if ((st->want & want_bit) && dst) { read_exact(st->fp, &dst[0][0], n3, st->fn.c_str()); *have = TRUE; }
+        else { std::fseek(st->fp, static_cast<long>(n3 * sizeof(float)), SEEK_CUR); *have = FALSE; }
+    };
+    rd(1, TRX_READ_X | TRX_NEED_X, fr->x, &fr->bX);
+    rd(2, TRX_READ_V | TRX_NEED_V, fr->v, &fr->bV);
+    rd(4, TRX_READ_F | TRX_NEED_F, fr->f, &fr->bF);
+    st->nread++;
+    return true;
+}
+} // namespace
+
+bool read_first_frame(const gmx_output_env_t* /*oenv*/, t_trxstatus** status, const char* fn, t_trxframe* fr, int flags)
+{
+    t_trxstatus* st = open_trx(fn);
+    st->want        = flags;
+    *status         = st;
+    rvec* keep_x = fr->x; rvec* keep_v = fr->v; rvec* keep_f = fr->f;
+    std::memset(fr, 0, sizeof(*fr));
+    fr->x = keep_x; fr->v = keep_v; fr->f = keep_f;
+    if ((flags & (TRX_READ_X | TRX_NEED_X)) && (st->fflags & 1)) { if (fr->x) sfree(fr->x); snew(fr->x, st->natoms); }
+    if ((flags & (TRX_READ_V | TRX_NEED_V)) && (st->fflags & 2)) { if (fr->v) sfree(fr->v); snew(fr->v, st->natoms); }
+    if ((flags & (TRX_READ_F | TRX_NEED_F)) && (st->fflags & 4)) { if (fr->f) sfree(fr->f); snew(fr->f, st->natoms); }
+    if ((flags & TRX_NEED_X) && !(st->fflags & 1)) gmx_fatal(FARGS, "Trajectory %s has no coordinates", fn);
+    if ((flags & TRX_NEED_V) && !(st->fflags & 2)) gmx_fatal(FARGS, "Trajectory %s has no velocities", fn);
+    if ((flags & TRX_NEED_F) && !(st->fflags & 4)) gmx_fatal(FARGS, "Trajectory %s has no forces", fn);
+    return deliver(st, fr);
+}
+
+bool read_next_frame(const gmx_output_env_t* /*oenv*/, t_trxstatus* status, t_trxframe* fr) { return deliver(status, fr); }
+
+void close_trx(t_trxstatus* status)
+{
+    if (!status) return;
+    if (status->fp) std::fclose(status->fp);
+    delete status;
+}
+
+int nframes_read(t_trxstatus* status) { return status ? status->nread : 0; }
+
+int gmxstub_natoms(const t_trxstatus* status) { return status ? status->natoms : 0; }
+
+int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* box_out, float* time_out)
+{
+    if (!st || !(st->fflags & 1)) return 0;
+    const size_t n3   = static_cast<size_t>(st->natoms) * 3;
+    const size_t rest = frame_floats(st) - 10 - n3;
+    int          got  = 0;
+    while (got < max_frames)
+    {
+        float hdr[10];
+        if (!next_selected(st, hdr)) break;
+        time_out[got] = hdr[0];
+        std::memcpy(box_out + 9 * static_cast<size_t>(got), hdr + 1, 9 * sizeof(float));
+        read_exact(st->fp, x_out + n3 * got, n3, st->fn.c_str());
+        if (rest) std::fseek(st->fp, static_cast<long>(rest * sizeof(float)), SEEK_CUR);
+        st->nread++;
+        ++got;
+    }
+    return got;
+}

@@ -1,0 +1,108 @@
+/*
+ * ref_handle_shim.cpp -- TEST INFRASTRUCTURE.  extern "C" access to the reference's own
+ * itp::GmxHandle loaders, compiled from the headers where they lie under /root/reference/include
+ * (never copied).  Built into oracle/_ref/libref_handle.so by oracle/Makefile; used only by tests/
+ * and tools/make_golden.py to pin oracle/port/oracle.c and to generate tests/golden fixtures.
+ *
+ * The handle's data members are public (reference include/itp/gmx_bits/gmx_handle.hpp:162-184), so
+ * instead of going through init()/read_first_frame() the shim fills them directly from caller arrays
+ * and then calls the unmodified loadPosition / loadPositionCenter / periodicity
+ * (gmx_handle.ipp:115-148, 150-199, 410-417).
+ */
+#include <itp/gmx>
+
+#include <cstring>
+
+namespace
+{
+struct Shim
+{
+    itp::GmxHandle hd{ 0, nullptr };
+    std::vector<std::vector<int>> idx;
+};
+} // namespace
+
+extern "C" {
+
+void* refshim_new(int ngrps)
+{
+    Shim* s      = new Shim;
+    s->hd.ngrps  = ngrps;
+    s->idx.resize(ngrps);
+    s->hd.napm.resize(ngrps);
+    s->hd.nmol.resize(ngrps);
+    s->hd.mass.resize(ngrps);
+    s->hd.charge.resize(ngrps);
+    snew(s->hd.index, ngrps);
+    snew(s->hd.ngx, ngrps);
+    snew(s->hd.fr, 1);
+    return s;
+}
+
+void refshim_free(void* h) { delete static_cast<Shim*>(h); }
+
+void refshim_set_group(void* h, int grp, const int* index, int ngx, int napm, const double* mass, const double* charge)
+{
+    Shim* s = static_cast<Shim*>(h);
+    s->idx[grp].assign(index, index + ngx);
+    s->hd.index[grp] = s->idx[grp].data();
+    s->hd.ngx[grp]   = ngx;
+    s->hd.napm[grp]  = napm;
+    s->hd.nmol[grp]  = ngx / napm;
+    s->hd.mass[grp].resize(napm);
+    s->hd.charge[grp].resize(napm);
+    for (int j = 0; j < napm; ++j)
+    {
+        s->hd.mass[grp][j]   = mass[j];
+        s->hd.charge[grp][j] = charge[j];
+    }
+}
+
+/* x: [natoms][3] float, box: float[9] row-major; Lbox taken from the diagonal as readFirstFrame does (ipp:72-74) */
+void refshim_set_frame(void* h, float* x, const float* box9)
+{
+    Shim* s    = static_cast<Shim*>(h);
+    s->hd.fr->x = reinterpret_cast<rvec*>(x);
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) s->hd.fr->box[a][b] = box9[3 * a + b];
+    s->hd.Lbox[XX] = s->hd.fr->box[XX][XX];
+    s->hd.Lbox[YY] = s->hd.fr->box[YY][YY];
+    s->hd.Lbox[ZZ] = s->hd.fr->box[ZZ][ZZ];
+}
+
+/* out: nmol*napm*3 doubles in boxd memory order: element (i,j) at ((i + j*nmol)*3 + k) */
+void refshim_load_position(void* h, int grp, double* out)
+{
+    Shim*     s   = static_cast<Shim*>(h);
+    itp::boxd pos = s->hd.initPos(grp);
+    s->hd.loadPosition(pos, grp);
+    std::memcpy(out, pos.data(), sizeof(double) * 3 * pos.size());
+}
+
+/* out: nmol*3 doubles, column-major (i + k*nmol) */
+void refshim_load_position_center(void* h, int grp, int com, double* out)
+{
+    Shim*     s    = static_cast<Shim*>(h);
+    itp::matd posc = s->hd.initPosc(grp);
+    s->hd.loadPositionCenter(posc, grp, com);
+    std::memcpy(out, posc.data(), sizeof(double) * posc.size());
+}
+
+double refshim_periodicity(double dx, double box) { return itp::GmxHandle::periodicity(dx, box); }
+
+/* atomCenter.sum() exactly as ipp:195 evaluates it (Eigen 3.3.9 vectorised redux) */
+double refshim_eigen_sum(const double* w, int n)
+{
+    itp::vecd v(n);
+    for (int i = 0; i < n; ++i) v[i] = w[i];
+    return v.sum();
+}
+
+/* rowwise mean of the last ncols columns of a (rows x cols) column-major matrix, as calc_rdf_region.cpp:113 */
+void refshim_rightcols_rowmean(const double* m, int rows, int cols, int ncols, double* out)
+{
+    Eigen::Map<const itp::matd> M(m, rows, cols);
+    itp::vecd                   mean = M.rightCols(ncols).rowwise().mean();
+    for (int i = 0; i < rows; ++i) out[i] = mean[i];
+}
+}
