@@ -1,0 +1,739 @@
+// libb2a.so -- C ABI (include/b2a.h) over the sm_100a kernels.  No CPU fallback: without a CUDA device
+// b2a_create fails with B2A_ERR_CUDA.
+#include "b2a.h"
+
+#include "b2a_kernels_center.cuh"
+#include "b2a_kernels_orient.cuh"
+#include "b2a_kernels_rdf.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace b2a;
+
+namespace
+{
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...)
+{
+    char    buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                               \
+    do {                                                                                                       \
+        cudaError_t e_ = (call);                                                                               \
+        if (e_ != cudaSuccess) return fail(B2A_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// Sum in the order Eigen 3.3.9's vectorised Array<double>::sum() uses on SSE2 (two packet accumulators of
+// two doubles, then the scalar tail) -- this is what `atomCenter.sum()` evaluates in the reference
+// (include/itp/gmx_bits/gmx_handle.ipp:195), and for napm > 3 it differs from a sequential sum in the last bit.
+double eigen_order_sum(const double* w, int n)
+{
+    const int a2 = (n / 4) * 4, a1 = (n / 2) * 2;
+    if (!a1)
+    {
+        double r = w[0];
+        for (int i = 1; i < n; ++i) r += w[i];
+        return r;
+    }
+    double p00 = w[0], p01 = w[1];
+    if (a1 > 2)
+    {
+        double p10 = w[2], p11 = w[3];
+        for (int i = 4; i < a2; i += 4) { p00 += w[i]; p01 += w[i + 1]; p10 += w[i + 2]; p11 += w[i + 3]; }
+        p00 += p10; p01 += p11;
+        if (a1 > a2) { p00 += w[a2]; p01 += w[a2 + 1]; }
+    }
+    double r = p00 + p01;
+    for (int i = a1; i < n; ++i) r += w[i];
+    return r;
+}
+
+struct Group
+{
+    int     ngx = 0, napm = 0, nmol = 0;
+    int*    d_index = nullptr;
+    double* d_w[4]  = { nullptr, nullptr, nullptr, nullptr };   // mass, ones, charge, charge(dipole)
+    double  wsum[4] = { 0, 0, 0, 0 };
+    // centre cache per com for the current batch
+    double*  d_cen[4]   = { nullptr, nullptr, nullptr, nullptr };
+    int4*    d_fix[4]   = { nullptr, nullptr, nullptr, nullptr };
+    uint64_t valid[4]   = { 0, 0, 0, 0 };   // batch serial the cache belongs to
+};
+
+enum AccKind { ACC_DENSITY, ACC_RDF, ACC_ORIENT };
+
+struct Acc
+{
+    AccKind            kind;
+    b2a_density_spec   den{};
+    b2a_rdf_spec       rdf{};
+    b2a_orient_spec    ori{};
+    size_t             ncounters = 0;       // public counters (reference layout size)
+    size_t             ndev      = 0;       // device u64 words before the stats block
+    unsigned long long* d_hist   = nullptr; // [ndev + NSLOTS]
+    // rdf scratch
+    int*      d_slab_id = nullptr;
+    unsigned* d_slab_cnt = nullptr;   // [maxK][nslab] counts then [maxK][nslab] cursors
+    int4*     d_sortedA = nullptr;
+    RdfFrame* d_frames = nullptr;
+    RdfFrame* h_frames = nullptr;     // pinned
+    int       symmetric = 0, paranoid = 0;
+    int       ipt = 0, threads = 0;   // 0 = auto
+    // orient
+    double* d_cosedge = nullptr;
+    int     nbin1 = 0;
+};
+} // namespace
+
+struct b2a_ctx
+{
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    int          natoms = 0, maxK = 0;
+    float*       d_x    = nullptr;
+    FrameGeom*   d_geom = nullptr;
+    FrameGeom*   h_geom = nullptr;   // pinned
+    std::vector<float> h_box;        // [K][9]
+    int          nframes = 0;
+    uint64_t     serial  = 0;
+    int          sm_count = 148;
+    std::map<int, Group> groups;
+    std::vector<std::unique_ptr<Acc>> accs;
+    double*      d_pos_scratch = nullptr;
+    size_t       pos_scratch_n = 0;
+};
+
+extern "C" const char* b2a_last_error(void) { return g_err.c_str(); }
+extern "C" const char* b2a_version(void) { return "b2a 0.1 (sm_100a)"; }
+
+extern "C" int b2a_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
+{
+    if (!out || natoms <= 0 || max_frames <= 0) return fail(B2A_ERR_ARG, "b2a_create: natoms and max_frames must be positive");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    {
+        cudaGetLastError();
+        return fail(B2A_ERR_CUDA, "b2a_create: no CUDA device visible; libb2a has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(B2A_ERR_ARG, "b2a_create: device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    std::unique_ptr<b2a_ctx> c(new b2a_ctx);
+    c->device = device;
+    c->natoms = natoms;
+    c->maxK   = max_frames;
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->d_x, (size_t)natoms * 3 * sizeof(float) * max_frames));
+    CU(cudaMalloc(&c->d_geom, sizeof(FrameGeom) * max_frames));
+    CU(cudaMallocHost(&c->h_geom, sizeof(FrameGeom) * max_frames));
+    c->h_box.assign((size_t)max_frames * 9, 0.f);
+    *out = c.release();
+    return B2A_OK;
+}
+
+static void free_group(Group& g)
+{
+    cudaFree(g.d_index);
+    for (int k = 0; k < 4; ++k) { cudaFree(g.d_w[k]); cudaFree(g.d_cen[k]); cudaFree(g.d_fix[k]); }
+    g = Group();
+}
+
+static void free_acc(Acc& a)
+{
+    cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
+    cudaFree(a.d_cosedge);
+    if (a.h_frames) cudaFreeHost(a.h_frames);
+}
+
+extern "C" void b2a_destroy(b2a_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->groups) free_group(kv.second);
+    for (auto& a : c->accs) if (a) free_acc(*a);
+    cudaFree(c->d_x); cudaFree(c->d_geom); cudaFree(c->d_pos_scratch);
+    if (c->h_geom) cudaFreeHost(c->h_geom);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int b2a_sync(b2a_ctx* c)
+{
+    if (!c) return fail(B2A_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
+extern "C" void* b2a_stream(b2a_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" void* b2a_pinned_alloc(size_t n)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, n) != cudaSuccess) { cudaGetLastError(); g_err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+extern "C" void b2a_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+// ---- groups --------------------------------------------------------------------------------------------------
+extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int napm, const double* mass, const double* charge)
+{
+    if (!c || !index || !mass || !charge) return fail(B2A_ERR_ARG, "b2a_set_group: null argument");
+    if (grp < 0) return fail(B2A_ERR_ARG, "grp(%d) should not be negative", grp);
+    if (napm <= 0 || ngx <= 0 || ngx % napm != 0)
+        return fail(B2A_ERR_ARG, "The index group does not consist of whole molecules");   // ipp:432
+    const int nmol = ngx / napm;
+    for (int i = 0; i < nmol; ++i)
+    {
+        const int m = index[(size_t)i * napm];
+        if (m < 0 || m + napm > c->natoms) return fail(B2A_ERR_ARG, "b2a_set_group: atom index out of range in molecule %d", i);
+    }
+    for (int n = 0; n < ngx; ++n)
+        if (index[n] < 0 || index[n] >= c->natoms) return fail(B2A_ERR_ARG, "b2a_set_group: atom index %d out of range", index[n]);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    Group& g = c->groups[grp];
+    free_group(g);
+    g.ngx = ngx; g.napm = napm; g.nmol = nmol;
+    CU(cudaMalloc(&g.d_index, sizeof(int) * ngx));
+    CU(cudaMemcpy(g.d_index, index, sizeof(int) * ngx, cudaMemcpyHostToDevice));
+    std::vector<double> ones(napm, 1.0);
+    const double*       src[4] = { mass, ones.data(), charge, charge };
+    for (int k = 0; k < 4; ++k)
+    {
+        CU(cudaMalloc(&g.d_w[k], sizeof(double) * napm));
+        CU(cudaMemcpy(g.d_w[k], src[k], sizeof(double) * napm, cudaMemcpyHostToDevice));
+    }
+    g.wsum[0] = eigen_order_sum(mass, napm);
+    g.wsum[1] = eigen_order_sum(ones.data(), napm);
+    g.wsum[2] = eigen_order_sum(charge, napm);
+    double s = 0.0;   // general/9g_dist_bin_1803.cpp:217-221: sequential sum, |sum| < 1e-6 -> 1
+    for (int j = 0; j < napm; ++j) s += charge[j];
+    g.wsum[3] = (std::fabs(s) < 1e-6) ? 1.0 : s;
+    return B2A_OK;
+}
+
+static int get_group(b2a_ctx* c, int grp, Group** out)
+{
+    auto it = c->groups.find(grp);
+    if (it == c->groups.end()) return fail(B2A_ERR_ARG, "grp(%d) should less than ngrps(%d)!", grp, (int)c->groups.size());   // ipp:101
+    *out = &it->second;
+    return B2A_OK;
+}
+
+extern "C" int b2a_set_group_wsum(b2a_ctx* c, int grp, int com, double wsum)
+{
+    if (!c || com < 0 || com > 3) return fail(B2A_ERR_ARG, "b2a_set_group_wsum: bad argument");
+    Group* g;
+    if (int rc = get_group(c, grp, &g)) return rc;
+    g->wsum[com]  = wsum;
+    g->valid[com] = 0;
+    return B2A_OK;
+}
+
+extern "C" int b2a_group_nmol(b2a_ctx* c, int grp)
+{
+    if (!c) return -1;
+    auto it = c->groups.find(grp);
+    return it == c->groups.end() ? -1 : it->second.nmol;
+}
+
+// ---- frames --------------------------------------------------------------------------------------------------
+extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const float* box9)
+{
+    if (!c || !x || !box9) return fail(B2A_ERR_ARG, "b2a_submit_batch: null argument");
+    if (nframes <= 0 || nframes > c->maxK) return fail(B2A_ERR_ARG, "b2a_submit_batch: nframes %d outside 1..%d", nframes, c->maxK);
+    CU(cudaSetDevice(c->device));
+    // h_geom is reused: make sure the previous upload has left the pinned buffer
+    CU(cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < nframes; ++f)
+    {
+        FrameGeom& g = c->h_geom[f];
+        for (int k = 0; k < 3; ++k)
+        {
+            const float bk = box9[(size_t)f * 9 + 4 * k];
+            if (!(bk > 0.f)) return fail(B2A_ERR_ARG, "b2a_submit_batch: frame %d has non-positive box length", f);
+            g.L[k]        = (double)bk;            // ipp:72-74
+            g.half[k]     = g.L[k] / 2;            // ipp:128
+            g.inv_unit[k] = 4294967296.0 / g.L[k];
+        }
+    }
+    std::memcpy(c->h_box.data(), box9, sizeof(float) * 9 * (size_t)nframes);
+    CU(cudaMemcpyAsync(c->d_x, x, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_geom, c->h_geom, sizeof(FrameGeom) * nframes, cudaMemcpyHostToDevice, c->stream));
+    c->nframes = nframes;
+    c->serial++;
+    return B2A_OK;
+}
+
+extern "C" int b2a_batch_frames(b2a_ctx* c) { return c ? c->nframes : -1; }
+
+// ---- K1 launch + cache -----------------------------------------------------------------------------------------
+static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
+{
+    if (com < 0 || com > 3) return fail(B2A_ERR_ARG, "com(%d) must be 0 (mass), 1 (geometry), 2 (charge) or 3 (dipole)", com);
+    if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
+    if (!g.d_cen[com]) CU(cudaMalloc(&g.d_cen[com], sizeof(double) * 3 * (size_t)g.nmol * c->maxK));
+    if (!g.d_fix[com]) CU(cudaMalloc(&g.d_fix[com], sizeof(int4) * (size_t)g.nmol * c->maxK));
+    (void)need_fix;
+    if (g.valid[com] == c->serial) return B2A_OK;
+    const int threads = 128;
+    dim3      grid((g.nmol + threads - 1) / threads, c->nframes);
+    k1_centers<4><<<grid, threads, sizeof(double) * g.napm, c->stream>>>(
+        c->d_x, (size_t)c->natoms * 3, c->nframes, g.d_index, g.nmol, g.napm, g.d_w[com], g.wsum[com], c->d_geom,
+        g.d_cen[com], g.d_fix[com]);
+    CU(cudaGetLastError());
+    g.valid[com] = c->serial;
+    return B2A_OK;
+}
+
+extern "C" int b2a_centers(b2a_ctx* c, int grp, int com, int frame, double* out)
+{
+    if (!c || !out) return fail(B2A_ERR_ARG, "b2a_centers: null argument");
+    Group* g;
+    if (int rc = get_group(c, grp, &g)) return rc;
+    if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_centers: frame %d outside batch of %d", frame, c->nframes);
+    CU(cudaSetDevice(c->device));
+    if (int rc = ensure_centers(c, *g, com, false)) return rc;
+    CU(cudaMemcpyAsync(out, g->d_cen[com] + (size_t)frame * 3 * g->nmol, sizeof(double) * 3 * g->nmol, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
+extern "C" int b2a_centers_batch(b2a_ctx* c, int grp, int com, double* out)
+{
+    if (!c || !out) return fail(B2A_ERR_ARG, "b2a_centers_batch: null argument");
+    Group* g;
+    if (int rc = get_group(c, grp, &g)) return rc;
+    CU(cudaSetDevice(c->device));
+    if (int rc = ensure_centers(c, *g, com, false)) return rc;
+    CU(cudaMemcpyAsync(out, g->d_cen[com], sizeof(double) * 3 * g->nmol * c->nframes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
+extern "C" int b2a_positions(b2a_ctx* c, int grp, int frame, double* out)
+{
+    if (!c || !out) return fail(B2A_ERR_ARG, "b2a_positions: null argument");
+    Group* g;
+    if (int rc = get_group(c, grp, &g)) return rc;
+    if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
+    if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_positions: frame %d outside batch of %d", frame, c->nframes);
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)g->nmol * g->napm;
+    if (c->pos_scratch_n < n)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_pos_scratch);
+        c->d_pos_scratch = nullptr;
+        CU(cudaMalloc(&c->d_pos_scratch, sizeof(double) * 3 * n));
+        c->pos_scratch_n = n;
+    }
+    const int threads = 256;
+    k1b_positions<<<(unsigned)((n + threads - 1) / threads), threads, 0, c->stream>>>(
+        c->d_x + (size_t)frame * c->natoms * 3, g->d_index, g->nmol, g->napm, c->h_geom[frame], c->d_pos_scratch);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->d_pos_scratch, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
+// ---- accumulators ----------------------------------------------------------------------------------------------
+static int new_acc(b2a_ctx* c, std::unique_ptr<Acc> a, int* id)
+{
+    CU(cudaMalloc(&a->d_hist, sizeof(unsigned long long) * (a->ndev + B2A_STAT_NSLOTS)));
+    CU(cudaMemsetAsync(a->d_hist, 0, sizeof(unsigned long long) * (a->ndev + B2A_STAT_NSLOTS), c->stream));
+    c->accs.push_back(std::move(a));
+    *id = (int)c->accs.size() - 1;
+    return B2A_OK;
+}
+
+static int get_acc(b2a_ctx* c, int id, Acc** out)
+{
+    if (!c) return fail(B2A_ERR_ARG, "null context");
+    if (id < 0 || id >= (int)c->accs.size() || !c->accs[id]) return fail(B2A_ERR_ARG, "unknown accumulator %d", id);
+    *out = c->accs[id].get();
+    return B2A_OK;
+}
+
+extern "C" int b2a_density_create(b2a_ctx* c, const b2a_density_spec* s, int* id)
+{
+    if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_density_create: null argument");
+    Group* g;
+    if (int rc = get_group(c, s->grp, &g)) return rc;
+    if (s->nbin <= 0 || s->dim < 0 || s->dim > 2 || s->dim2 > 2 || !(s->dbin > 0)) return fail(B2A_ERR_ARG, "b2a_density_create: bad spec");
+    if (s->com < 0 || s->com > 3) return fail(B2A_ERR_ARG, "com(%d) out of range", s->com);
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<Acc> a(new Acc);
+    a->kind = ACC_DENSITY;
+    a->den  = *s;
+    a->ncounters = a->ndev = (size_t)s->nbin;
+    return new_acc(c, std::move(a), id);
+}
+
+extern "C" int b2a_rdf_create(b2a_ctx* c, const b2a_rdf_spec* s, int* id)
+{
+    if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_rdf_create: null argument");
+    Group *g0, *g1;
+    if (int rc = get_group(c, s->grp0, &g0)) return rc;
+    if (int rc = get_group(c, s->grp1, &g1)) return rc;
+    if (s->nbin <= 0 || s->Rbin <= 0 || !(s->Rm > 0.f) || s->dim < 0 || s->dim > 2 || s->dim2 < 0 || s->dim2 > 2)
+        return fail(B2A_ERR_ARG, "b2a_rdf_create: bad spec (nbin=%d Rbin=%d Rm=%g dim=%d dim2=%d)", s->nbin, s->Rbin, (double)s->Rm, s->dim, s->dim2);
+    if (s->com0 < 0 || s->com0 > 3 || s->com1 < 0 || s->com1 > 3) return fail(B2A_ERR_ARG, "com out of range");
+    if (s->nbin > 4096) return fail(B2A_ERR_UNSUPPORTED, "b2a_rdf_create: nbin > 4096 slabs not supported");
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<Acc> a(new Acc);
+    a->kind      = ACC_RDF;
+    a->rdf       = *s;
+    a->ncounters = (size_t)s->nbin * s->Rbin;
+    a->ndev      = (size_t)(s->nbin + 1) * s->Rbin;   // + slab nbin: i whose meZ == nbin (out of bounds in the reference)
+    const int nslab = s->nbin + 1;
+    CU(cudaMalloc(&a->d_slab_id, sizeof(int) * (size_t)g0->nmol * c->maxK));
+    CU(cudaMalloc(&a->d_slab_cnt, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK));
+    CU(cudaMalloc(&a->d_sortedA, sizeof(int4) * (size_t)g0->nmol * c->maxK));
+    CU(cudaMalloc(&a->d_frames, sizeof(RdfFrame) * c->maxK));
+    CU(cudaMallocHost(&a->h_frames, sizeof(RdfFrame) * c->maxK));
+    return new_acc(c, std::move(a), id);
+}
+
+extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (a->kind != ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF", id);
+    a->symmetric = symmetric;
+    a->paranoid  = paranoid;
+    return B2A_OK;
+}
+
+static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
+static float next_up(float v) { return std::nextafterf(v, INFINITY); }
+
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID>
+static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, int max_tiles)
+{
+    auto kern = k3_rdf<IPT, THREADS, CLAMP, CUBIC, PARANOID>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(max_tiles, p.jsplit, c->nframes);
+    kern<<<grid, THREADS, smem, c->stream>>>(a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
+                                            a.d_slab_cnt, a.d_frames, p, a.d_hist, a.d_hist + a.ndev);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
+static int accumulate_rdf(b2a_ctx* c, Acc& a)
+{
+    const b2a_rdf_spec& s = a.rdf;
+    Group *g0, *g1;
+    if (int rc = get_group(c, s.grp0, &g0)) return rc;
+    if (int rc = get_group(c, s.grp1, &g1)) return rc;
+    if (int rc = ensure_centers(c, *g0, s.com0, true)) return rc;
+    if (int rc = ensure_centers(c, *g1, s.com1, true)) return rc;
+
+    RdfDev p{};
+    p.n0 = g0->nmol; p.n1 = g1->nmol; p.nbin = s.nbin; p.nslab = s.nbin + 1; p.Rbin = s.Rbin;
+    p.dim = s.dim; p.dim2 = s.dim2;
+    p.low = (double)s.low; p.up = (double)s.up; p.low2 = (double)s.low2; p.up2 = (double)s.up2;
+    p.width  = (double)(float)(s.up - s.low);          // float subtraction, calc_rdf_region.cpp:77
+    p.rm2    = (double)(float)(s.Rm * s.Rm);           // float product, :88
+    p.Rm     = (double)s.Rm;
+    p.Rbin_d = (double)s.Rbin;
+    p.rbin_bits = kMagicBits + (unsigned)s.Rbin;
+
+    // per-frame fast-path constants and the largest reachable bin
+    bool   cubic = true;
+    double tmax  = 0.0;
+    // K3 error bound: relative error of the FP32 distance <= 4.5 * 2^-24 (cubic), 6.5 * 2^-24 otherwise
+    CU(cudaStreamSynchronize(c->stream));   // h_frames reuse
+    for (int f = 0; f < c->nframes; ++f)
+    {
+        const FrameGeom& g = c->h_geom[f];
+        if (g.L[0] != g.L[1] || g.L[0] != g.L[2]) cubic = false;
+    }
+    const double eps_true = (cubic ? 4.5 : 6.5) * std::ldexp(1.0, -24);
+    const double eps      = eps_true + 1.3e-7;
+    for (int f = 0; f < c->nframes; ++f)
+    {
+        const FrameGeom& g    = c->h_geom[f];
+        RdfFrame&        fr   = a.h_frames[f];
+        const double     unit = g.L[0] / 4294967296.0;         // nm per x fixed unit
+        const double     sc   = unit * (double)s.Rbin / (double)s.Rm;   // bins per unit
+        float lo = (float)(sc * (1.0 - eps)), hi = (float)(sc * (1.0 + eps));
+        if ((double)lo > sc * (1.0 - eps)) lo = next_down(lo);
+        if ((double)hi < sc * (1.0 + eps)) hi = next_up(hi);
+        fr.s_lo = lo; fr.s_hi = hi;
+        fr.ay = (float)(g.L[1] / g.L[0]);
+        fr.az = (float)(g.L[2] / g.L[0]);
+        // absolute error: coordinates are rounded to the fixed grid (<= 1 unit per component of the difference)
+        const double delta_bins = std::sqrt(3.0) * 1.0001 * sc * std::max(1.0, std::max((double)fr.ay, (double)fr.az));
+        const unsigned lowk     = (unsigned)std::ceil(delta_bins / (eps - eps_true)) + 2;
+        fr.lowk_bits = kMagicBits + lowk;
+        fr.pad = 0;
+        for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
+        const double rmax_units = 2147483648.0 * std::sqrt(1.0 + (double)fr.ay * fr.ay + (double)fr.az * fr.az) * 1.000001;
+        tmax = std::max(tmax, rmax_units * (double)hi);
+    }
+    CU(cudaMemcpyAsync(a.d_frames, a.h_frames, sizeof(RdfFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
+
+    // shared histogram: every reachable bin if it fits comfortably, else clamp to Rbin (+1 FMNMX pair per pair)
+    const size_t fixed_smem = kTileJ * sizeof(int4) + kQueueCap * sizeof(unsigned long long) + 16;
+    const unsigned full_stride = (unsigned)std::ceil(tmax) + 4;
+    bool clamp = ((size_t)full_stride * 4 + fixed_smem > 56 * 1024);
+    p.kstride  = clamp ? (unsigned)s.Rbin + 3 : full_stride;
+    p.clamp    = clamp;
+    const size_t smem = fixed_smem + (size_t)p.kstride * 4;
+    if (smem > 200 * 1024) return fail(B2A_ERR_UNSUPPORTED, "rdf: Rbin=%d needs %zu bytes of shared memory per block", s.Rbin, smem);
+
+    // prep: slab ids, counts, scatter
+    const int nslab = p.nslab;
+    CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, c->stream));
+    {
+        dim3 grid((p.n0 + 255) / 256, c->nframes);
+        k3_slab_count<<<grid, 256, 0, c->stream>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
+        CU(cudaGetLastError());
+        k3_slab_scatter<<<grid, 256, sizeof(unsigned) * nslab, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
+                                                                         a.d_slab_cnt, a.d_slab_cnt + (size_t)nslab * c->maxK, a.d_sortedA);
+        CU(cudaGetLastError());
+    }
+
+    // tiling: TI molecules of one slab per block, j split so that the grid covers the machine several times
+    const int IPT = 8, THREADS = 128, TI = IPT * THREADS;
+    const int max_tiles = (p.n0 + TI - 1) / TI + std::min(nslab, p.n0);
+    const int itiles    = std::max(1, (p.n0 + TI - 1) / TI);
+    int       jsplit    = std::max(1, (c->sm_count * 16 + itiles * c->nframes - 1) / (itiles * c->nframes));
+    jsplit              = std::min(jsplit, std::max(1, (p.n1 + 511) / 512));
+    p.jsplit            = jsplit;
+    p.jchunk            = (p.n1 + jsplit - 1) / jsplit;
+
+#define B2A_LAUNCH(CL, CB, PA) launch_rdf<8, 128, CL, CB, PA>(c, a, *g0, *g1, p, smem, max_tiles)
+    int rc;
+    if (a.paranoid) rc = clamp ? (cubic ? B2A_LAUNCH(true, true, true) : B2A_LAUNCH(true, false, true))
+                               : (cubic ? B2A_LAUNCH(false, true, true) : B2A_LAUNCH(false, false, true));
+    else rc = clamp ? (cubic ? B2A_LAUNCH(true, true, false) : B2A_LAUNCH(true, false, false))
+                    : (cubic ? B2A_LAUNCH(false, true, false) : B2A_LAUNCH(false, false, false));
+#undef B2A_LAUNCH
+    return rc;
+}
+
+static int accumulate_density(b2a_ctx* c, Acc& a)
+{
+    const b2a_density_spec& s = a.den;
+    Group* g;
+    if (int rc = get_group(c, s.grp, &g)) return rc;
+    if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
+    DensityDev d{};
+    d.dim = s.dim; d.dim2 = s.dim2; d.nbin = s.nbin; d.upper_inclusive = s.upper_inclusive;
+    d.low = (double)s.low; d.up = (double)s.up; d.low2 = (double)s.low2; d.up2 = (double)s.up2; d.dbin = s.dbin;
+    const int    threads   = 256;
+    const int    smem_bins = s.nbin <= 40000 ? s.nbin : 0;
+    const size_t smem      = sizeof(double) * g->napm + sizeof(unsigned) * smem_bins;
+    CU(cudaFuncSetAttribute(k2_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long total  = (long long)g->nmol * c->nframes;
+    const int       blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)c->sm_count * 8);
+    k2_density<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->nmol, g->napm,
+                                                     g->d_w[s.com], g->wsum[s.com], c->d_geom, d, a.d_hist, a.d_hist + a.ndev, smem_bins);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
+static int accumulate_orient(b2a_ctx* c, Acc& a);
+
+__global__ void k_add_frames(unsigned long long* stats, unsigned long long n) { stats[0] += n; }
+
+extern "C" int b2a_accumulate(b2a_ctx* c, int id)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    CU(cudaSetDevice(c->device));
+    if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
+    int rc = B2A_OK;
+    switch (a->kind)
+    {
+        case ACC_DENSITY: rc = accumulate_density(c, *a); break;
+        case ACC_RDF: rc = accumulate_rdf(c, *a); break;
+        case ACC_ORIENT: rc = accumulate_orient(c, *a); break;
+    }
+    if (rc) return rc;
+    k_add_frames<<<1, 1, 0, c->stream>>>(a->d_hist + a->ndev, (unsigned long long)c->nframes);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
+extern "C" int b2a_acc_reset(b2a_ctx* c, int id)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(a->d_hist, 0, sizeof(unsigned long long) * (a->ndev + B2A_STAT_NSLOTS), c->stream));
+    return B2A_OK;
+}
+
+extern "C" int b2a_acc_size(b2a_ctx* c, int id, size_t* n)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (!n) return fail(B2A_ERR_ARG, "null argument");
+    *n = a->ndev;   // device words before the stats block; the merge covers ndev + B2A_STAT_NSLOTS
+    return B2A_OK;
+}
+
+extern "C" int b2a_acc_device_ptr(b2a_ctx* c, int id, void** p)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (!p) return fail(B2A_ERR_ARG, "null argument");
+    *p = a->d_hist;
+    return B2A_OK;
+}
+
+extern "C" int b2a_acc_read(b2a_ctx* c, int id, uint64_t* counts, uint64_t* stats)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (!counts) return fail(B2A_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    std::vector<unsigned long long> h(a->ndev + B2A_STAT_NSLOTS);
+    CU(cudaMemcpyAsync(h.data(), a->d_hist, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long* st = h.data() + a->ndev;
+    if (a->kind == ACC_RDF)
+    {
+        const int nbin = a->rdf.nbin, Rbin = a->rdf.Rbin;
+        // device layout [slab][meR] -> reference layout meZ + meR*nbin (itp::matd(nbin, Rbin), column-major)
+        for (int z = 0; z < nbin; ++z)
+            for (int r = 0; r < Rbin; ++r) counts[(size_t)z + (size_t)r * nbin] = h[(size_t)z * Rbin + r];
+        unsigned long long oob = 0;   // pairs of i whose slab index == nbin: out-of-bounds writes in the reference
+        for (int r = 0; r < Rbin; ++r) oob += h[(size_t)nbin * Rbin + r];
+        st[B2A_STAT_DROPPED] += oob;
+    }
+    else
+    {
+        for (size_t i = 0; i < a->ncounters; ++i) counts[i] = h[i];
+    }
+    if (stats) for (int i = 0; i < B2A_STAT_NSLOTS; ++i) stats[i] = st[i];
+    return B2A_OK;
+}
+
+extern "C" int b2a_rdf_normalise(const uint64_t* counts, int nbin, int Rbin, double* g)
+{
+    if (!counts || !g || nbin <= 0 || Rbin <= 0) return fail(B2A_ERR_ARG, "b2a_rdf_normalise: bad argument");
+    // calc_rdf_region.cpp:100-109: shell "volumes" from 0.002-wide shells (NOT Rm/Rbin), :111 divide
+    for (int r = 0; r < Rbin; ++r)
+    {
+        double v = std::pow(0.002 * (r + 1), 3);
+        if (r > 0) v = v - std::pow(0.002 * r, 3);
+        for (int z = 0; z < nbin; ++z) g[(size_t)z + (size_t)r * nbin] = (double)counts[(size_t)z + (size_t)r * nbin] / v;
+    }
+    // :113-115: each slab divided by the mean of its last int(Rbin*0.1) bins (0/0 -> NaN rows, as the reference prints)
+    const int tail = (int)(Rbin * 0.1);
+    for (int z = 0; z < nbin; ++z)
+    {
+        double s = 0.0;
+        for (int r = Rbin - tail; r < Rbin; ++r) s += g[(size_t)z + (size_t)r * nbin];
+        const double mean = s / tail;
+        for (int r = 0; r < Rbin; ++r) g[(size_t)z + (size_t)r * nbin] /= mean;
+    }
+    return B2A_OK;
+}
+
+// ---- orientation -------------------------------------------------------------------------------------------------
+extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
+{
+    if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_orient_create: null argument");
+    Group* g;
+    if (int rc = get_group(c, s->grp, &g)) return rc;
+    if (s->DIMN < 0 || s->DIMN > 2 || s->DIMNOrient < 0 || s->DIMNOrient > 2) return fail(B2A_ERR_ARG, "orient: dim out of range");
+    if (s->tp1 < 1 || s->tp2 < 1 || s->tp3 < 1 || s->tp1 > g->napm || s->tp2 > g->napm || s->tp3 > g->napm)
+        return fail(B2A_ERR_ARG, "orient: tp1..3 must lie in 1..napm(%d)", g->napm);
+    if (s->nAngle <= 0 || s->nAngle > 180) return fail(B2A_ERR_ARG, "orient: nAngle must be 1..180 (dAngle = 180 / nAngle is integer division)");
+    if (s->method != 1 && s->method != 2) return fail(B2A_ERR_ARG, "orient: method must be 1 or 2");
+    if (s->com < 0 || s->com > 3) return fail(B2A_ERR_ARG, "com out of range");
+    const int nbin1 = (int)((s->CR - s->Cr) / s->dr);   // float arithmetic, calc_orient_mof.cpp:133
+    if (nbin1 <= 0) return fail(B2A_ERR_ARG, "orient: (CR - Cr) / dr gives no radial bins");
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<Acc> a(new Acc);
+    a->kind  = ACC_ORIENT;
+    a->ori   = *s;
+    a->nbin1 = nbin1;
+    a->ncounters = a->ndev = (size_t)nbin1 * s->nAngle + nbin1;
+    // Angle-bin edges as thresholds on cos(angle): the reference evaluates
+    //   angle = acos(c) / pi(long double) * 180 ; meA = int(angle / dAngle)        (calc_orient_mof.cpp:41-47, 193-194)
+    // with the HOST libm.  acos is monotone, so bin(c) = #{k >= 1 : c <= edge[k]} where edge[k] is the largest
+    // double c whose reference bin is >= k.  The table is found here by bisection with the host's own acos and
+    // long double arithmetic, and the device only compares -- it never evaluates a transcendental.
+    const int          nA     = s->nAngle;
+    const double       dAngle = (double)(180 / nA);
+    std::vector<double> edge(nA + 1);
+    auto bin_of = [&](double cv) -> int {
+        const long double pi = 3.14159265358979323846264338327950288L;
+        const double      ang = (double)(std::acos(cv) / pi * 180);
+        return (int)(ang / dAngle);
+    };
+    for (int k = 1; k <= nA; ++k)
+    {
+        // largest c in [-1, 1] with bin_of(c) >= k  (bin_of is non-increasing in c)
+        if (bin_of(-1.0) < k) { edge[k] = -2.0; continue; }   // never reached
+        double lo = -1.0, hi = 1.0;                            // invariant: bin_of(lo) >= k
+        if (bin_of(hi) >= k) { edge[k] = 1.0; continue; }
+        for (;;)
+        {
+            const double mid = lo + (hi - lo) / 2;
+            if (mid <= lo || mid >= hi) break;
+            if (bin_of(mid) >= k) lo = mid; else hi = mid;
+        }
+        // lo and hi are now adjacent doubles
+        edge[k] = lo;
+    }
+    edge[0] = 2.0;
+    CU(cudaMalloc(&a->d_cosedge, sizeof(double) * (nA + 1)));
+    CU(cudaMemcpy(a->d_cosedge, edge.data(), sizeof(double) * (nA + 1), cudaMemcpyHostToDevice));
+    return new_acc(c, std::move(a), id);
+}
+
+static int accumulate_orient(b2a_ctx* c, Acc& a)
+{
+    const b2a_orient_spec& s = a.ori;
+    Group* g;
+    if (int rc = get_group(c, s.grp, &g)) return rc;
+    OrientDev d{};
+    d.DIMN = s.DIMN; d.nAngle = s.nAngle; d.nbin1 = a.nbin1; d.tp1 = s.tp1 - 1; d.tp2 = s.tp2 - 1; d.tp3 = s.tp3 - 1;
+    d.DIMNOrient = s.DIMNOrient; d.method = s.method;
+    d.low = (double)s.low; d.up = (double)s.up; d.c1 = (double)s.c1; d.c2 = (double)s.c2;
+    d.dr = (double)s.dr; d.CR = (double)s.CR; d.Cr = (double)s.Cr;
+    const int    threads = 256;
+    const size_t hist_words = (size_t)a.nbin1 * s.nAngle + a.nbin1;
+    const int    smem_bins  = hist_words <= 40000 ? (int)hist_words : 0;
+    const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1) + sizeof(unsigned) * smem_bins;
+    CU(cudaFuncSetAttribute(k4_orient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long total  = (long long)g->nmol * c->nframes;
+    const int       blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)c->sm_count * 8);
+    k4_orient<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->nmol, g->napm,
+                                                    g->d_w[s.com], g->wsum[s.com], c->d_geom, d, a.d_cosedge, a.d_hist,
+                                                    a.d_hist + a.ndev, smem_bins);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}

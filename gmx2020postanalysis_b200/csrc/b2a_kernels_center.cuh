@@ -1,0 +1,183 @@
+// K1 (centres), K1b (unwrapped positions) and K2 (fused centre -> density histogram) for sm_100a.
+//
+// All three are HBM-bound streams over the float rvec array (12 B/atom).  The arithmetic
+// is the reference's, operation for operation, in FP64 with FMA contraction disabled
+// (__dmul_rn/__dadd_rn/__ddiv_rn): the reference binary is baseline x86-64 (no FMA), so
+// `tmpCenter += tmpPos * w` rounds twice (reference include/itp/gmx_bits/gmx_handle.ipp:193) and the
+// result here is bit-identical, not merely within tolerance.  The j-summation order per (molecule, k) is
+// the reference's sequential order, which is why this is a thread-per-molecule loop and not a shuffle tree.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b2a
+{
+
+struct FrameGeom   // per frame; filled on the host at submit time from the float box diagonal (ipp:72-74)
+{
+    double L[3];         // Lbox[k] = double(fr->box[k][k])
+    double half[3];      // Lbox[k] / 2  (ipp:128, 176)
+    double inv_unit[3];  // 2^32 / Lbox[k]: box-fraction fixed point used by the RDF fast path
+};
+
+__device__ __forceinline__ double unwrap(double t, double ref, double L, double half)
+{
+    // ipp:139-142 / 188-191: repeated +-L until within half a box of the molecule's first atom
+    while (__dsub_rn(t, ref) > half) t = __dsub_rn(t, L);
+    while (__dsub_rn(t, ref) < -half) t = __dadd_rn(t, L);
+    return t;
+}
+
+__device__ __forceinline__ int to_fixed(double c, double inv_unit)
+{
+    // nearest multiple of L/2^32, wrapped mod 2^32: integer differences are then minimum-image for free
+    return (int)(unsigned)(unsigned long long)__double2ll_rn(c * inv_unit);
+}
+
+// ---- K1: per-molecule centre, GmxHandle::loadPositionCenter (ipp:150-199) -----------------------------------
+// cen: [frame][k][i] doubles (= itp::matd column-major per frame); fix: [frame][i] int4 {x,y,z fixed, i}
+template <int UNROLL>
+__global__ void __launch_bounds__(256) k1_centers(const float* __restrict__ x, size_t frame_stride, int nframes,
+                                                  const int* __restrict__ index, int nmol, int napm,
+                                                  const double* __restrict__ w, double wsum,
+                                                  const FrameGeom* __restrict__ geom, double* __restrict__ cen,
+                                                  int4* __restrict__ fix)
+{
+    extern __shared__ double sw[];
+    for (int j = threadIdx.x; j < napm; j += blockDim.x) sw[j] = w[j];
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmol || f >= nframes) return;
+    const FrameGeom g   = geom[f];
+    const int       mol = __ldg(index + (size_t)i * napm);
+    const float*    p   = x + (size_t)f * frame_stride + (size_t)mol * 3;
+    const double r0 = (double)__ldg(p), r1 = (double)__ldg(p + 1), r2 = (double)__ldg(p + 2);
+    double       c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    int          j  = 0;
+    for (; j + UNROLL <= napm; j += UNROLL)
+    {
+        float v[UNROLL][3];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+        {
+            v[u][0] = __ldg(p + 3 * (j + u));
+            v[u][1] = __ldg(p + 3 * (j + u) + 1);
+            v[u][2] = __ldg(p + 3 * (j + u) + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+        {
+            const double wj = sw[j + u];
+            c0 = __dadd_rn(c0, __dmul_rn(unwrap((double)v[u][0], r0, g.L[0], g.half[0]), wj));
+            c1 = __dadd_rn(c1, __dmul_rn(unwrap((double)v[u][1], r1, g.L[1], g.half[1]), wj));
+            c2 = __dadd_rn(c2, __dmul_rn(unwrap((double)v[u][2], r2, g.L[2], g.half[2]), wj));
+        }
+    }
+    for (; j < napm; ++j)
+    {
+        const double wj = sw[j];
+        c0 = __dadd_rn(c0, __dmul_rn(unwrap((double)__ldg(p + 3 * j), r0, g.L[0], g.half[0]), wj));
+        c1 = __dadd_rn(c1, __dmul_rn(unwrap((double)__ldg(p + 3 * j + 1), r1, g.L[1], g.half[1]), wj));
+        c2 = __dadd_rn(c2, __dmul_rn(unwrap((double)__ldg(p + 3 * j + 2), r2, g.L[2], g.half[2]), wj));
+    }
+    c0 = __ddiv_rn(c0, wsum);
+    c1 = __ddiv_rn(c1, wsum);
+    c2 = __ddiv_rn(c2, wsum);
+    double* o = cen + (size_t)f * 3 * nmol;
+    o[i]                    = c0;
+    o[(size_t)nmol + i]     = c1;
+    o[2 * (size_t)nmol + i] = c2;
+    if (fix) fix[(size_t)f * nmol + i] = make_int4(to_fixed(c0, g.inv_unit[0]), to_fixed(c1, g.inv_unit[1]), to_fixed(c2, g.inv_unit[2]), i);
+}
+
+// ---- K1b: unwrapped per-atom positions, GmxHandle::loadPosition (ipp:115-148) --------------------------------
+// one frame; pos in itp::boxd memory order: element (i,j)[k] at (i + j*nmol)*3 + k
+__global__ void __launch_bounds__(256) k1b_positions(const float* __restrict__ xf, const int* __restrict__ index,
+                                                     int nmol, int napm, FrameGeom g, double* __restrict__ pos)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long long)nmol * napm) return;
+    // thread n handles output slot n = i + j*nmol so the 24-byte stores of a warp are contiguous
+    const int    i   = (int)(n % nmol), j = (int)(n / nmol);
+    const int    mol = __ldg(index + (size_t)i * napm);
+    const int    at  = __ldg(index + (size_t)i * napm + j);   // ipp:137 reads index[grp][n], not molN + j
+    const float* pr  = xf + (size_t)mol * 3;
+    const float* pa  = xf + (size_t)at * 3;
+    double*      o   = pos + (size_t)n * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = unwrap((double)__ldg(pa + k), (double)__ldg(pr + k), g.L[k], g.half[k]);
+}
+
+// ---- K2: centre of the needed dimension(s) -> 1-D histogram, never materialising the centres ----------------
+// README.md:143-150, general/calc_density_region.cpp:59-71, general/density_slit_jhl.cpp:59-77
+struct DensityDev
+{
+    int    dim, dim2, nbin, upper_inclusive;
+    double low, up, low2, up2;   // the program's float `real` bounds widened (comparison is done in double)
+    double dbin;
+};
+
+__device__ __forceinline__ double center_component(const float* __restrict__ p, int k, int napm, const double* sw,
+                                                   double wsum, double L, double half)
+{
+    const double ref = (double)__ldg(p + k);
+    double       c   = 0.0;
+    for (int j = 0; j < napm; ++j) c = __dadd_rn(c, __dmul_rn(unwrap((double)__ldg(p + 3 * j + k), ref, L, half), sw[j]));
+    return __ddiv_rn(c, wsum);
+}
+
+__global__ void __launch_bounds__(256) k2_density(const float* __restrict__ x, size_t frame_stride, int nframes,
+                                                  const int* __restrict__ index, int nmol, int napm,
+                                                  const double* __restrict__ w, double wsum,
+                                                  const FrameGeom* __restrict__ geom, DensityDev d,
+                                                  unsigned long long* __restrict__ hist,
+                                                  unsigned long long* __restrict__ stats, int smem_bins)
+{
+    extern __shared__ double sm2[];
+    double*   sw    = sm2;
+    unsigned* shist = reinterpret_cast<unsigned*>(sm2 + napm);
+    for (int j = threadIdx.x; j < napm; j += blockDim.x) sw[j] = w[j];
+    for (int b = threadIdx.x; b < smem_bins; b += blockDim.x) shist[b] = 0;
+    __syncthreads();
+    const bool use_smem = smem_bins >= d.nbin;
+    unsigned   ndrop = 0, nsel = 0;
+    // grid-stride over (frame, molecule) so one block folds many samples into its private histogram
+    const long long total = (long long)nframes * nmol;
+    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < total; n += (long long)gridDim.x * blockDim.x)
+    {
+        const int       f = (int)(n / nmol), i = (int)(n % nmol);
+        const FrameGeom g = geom[f];
+        const float*    p = x + (size_t)f * frame_stride + (size_t)__ldg(index + (size_t)i * napm) * 3;
+        const double    c = center_component(p, d.dim, napm, sw, wsum, g.L[d.dim], g.half[d.dim]);
+        bool            ok = (d.low <= c) && (d.upper_inclusive ? (c <= d.up) : (c < d.up));
+        if (ok && d.dim2 >= 0)
+        {
+            const double c2 = center_component(p, d.dim2, napm, sw, wsum, g.L[d.dim2], g.half[d.dim2]);
+            ok              = (d.low2 <= c2) && (d.upper_inclusive ? (c2 <= d.up2) : (c2 < d.up2));
+        }
+        if (!ok) continue;
+        nsel++;
+        const int me = __double2int_rz(__ddiv_rn(__dsub_rn(c, d.low), d.dbin));
+        if (me < 0 || me >= d.nbin) { ndrop++; continue; }
+        if (use_smem) atomicAdd(&shist[me], 1u);
+        else atomicAdd(&hist[me], 1ull);
+    }
+    __syncthreads();
+    if (use_smem)
+        for (int b = threadIdx.x; b < d.nbin; b += blockDim.x)
+            if (shist[b]) atomicAdd(&hist[b], (unsigned long long)shist[b]);
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        ndrop += __shfl_xor_sync(0xffffffffu, ndrop, o);
+        nsel += __shfl_xor_sync(0xffffffffu, nsel, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (ndrop) atomicAdd(&stats[1], (unsigned long long)ndrop);
+        if (nsel) atomicAdd(&stats[4], (unsigned long long)nsel);
+    }
+}
+
+} // namespace b2a

@@ -1,0 +1,252 @@
+"""ctypes binding of libb2a.so (include/b2a.h).  Fails loudly when the CUDA library is missing or no GPU is
+visible: there is no CPU fallback anywhere in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2a.so")
+_lib = None
+_P = C.c_void_p
+
+STAT_FRAMES, STAT_DROPPED, STAT_EXACT, STAT_MOVED, STAT_SELECTED, STAT_PAIRS, STAT_OVERFLOW = range(7)
+STAT_NSLOTS = 8
+COM_MASS, COM_GEOMETRY, COM_CHARGE, COM_DIPOLE = range(4)
+
+# every symbol include/b2a.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "b2a_last_error", "b2a_version", "b2a_device_count", "b2a_create", "b2a_destroy", "b2a_sync", "b2a_stream",
+    "b2a_pinned_alloc", "b2a_pinned_free", "b2a_set_group", "b2a_set_group_wsum", "b2a_group_nmol",
+    "b2a_submit_batch", "b2a_batch_frames", "b2a_centers", "b2a_centers_batch", "b2a_positions",
+    "b2a_density_create", "b2a_rdf_create", "b2a_orient_create", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
+    "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune",
+]
+
+
+class DensitySpec(C.Structure):
+    _fields_ = [("grp", C.c_int), ("com", C.c_int), ("dim", C.c_int), ("low", C.c_float), ("up", C.c_float),
+                ("dbin", C.c_double), ("nbin", C.c_int), ("upper_inclusive", C.c_int), ("dim2", C.c_int),
+                ("low2", C.c_float), ("up2", C.c_float)]
+
+
+class RdfSpec(C.Structure):
+    _fields_ = [("grp0", C.c_int), ("grp1", C.c_int), ("com0", C.c_int), ("com1", C.c_int), ("nbin", C.c_int),
+                ("low", C.c_float), ("up", C.c_float), ("dim", C.c_int), ("dim2", C.c_int), ("low2", C.c_float),
+                ("up2", C.c_float), ("Rm", C.c_float), ("Rbin", C.c_int)]
+
+
+class OrientSpec(C.Structure):
+    _fields_ = [("grp", C.c_int), ("com", C.c_int), ("DIMN", C.c_int), ("low", C.c_float), ("up", C.c_float),
+                ("c1", C.c_float), ("c2", C.c_float), ("dr", C.c_float), ("CR", C.c_float), ("Cr", C.c_float),
+                ("nAngle", C.c_int), ("tp1", C.c_int), ("tp2", C.c_int), ("tp3", C.c_int), ("DIMNOrient", C.c_int),
+                ("method", C.c_int)]
+
+
+class B2AError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libb2a error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing -- build it with __graft_entry__.build(); "
+                               "the B200 path has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.b2a_last_error.restype = C.c_char_p
+        L.b2a_version.restype = C.c_char_p
+        L.b2a_device_count.restype = C.c_int
+        L.b2a_create.argtypes = [C.POINTER(_P), C.c_int, C.c_int, C.c_int]
+        L.b2a_destroy.argtypes = [_P]
+        L.b2a_destroy.restype = None
+        L.b2a_sync.argtypes = [_P]
+        L.b2a_stream.argtypes = [_P]
+        L.b2a_stream.restype = _P
+        L.b2a_pinned_alloc.argtypes = [C.c_size_t]
+        L.b2a_pinned_alloc.restype = _P
+        L.b2a_pinned_free.argtypes = [_P]
+        L.b2a_pinned_free.restype = None
+        L.b2a_set_group.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P]
+        L.b2a_set_group_wsum.argtypes = [_P, C.c_int, C.c_int, C.c_double]
+        L.b2a_group_nmol.argtypes = [_P, C.c_int]
+        L.b2a_submit_batch.argtypes = [_P, C.c_int, _P, _P]
+        L.b2a_batch_frames.argtypes = [_P]
+        L.b2a_centers.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
+        L.b2a_centers_batch.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.b2a_positions.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.b2a_density_create.argtypes = [_P, C.POINTER(DensitySpec), C.POINTER(C.c_int)]
+        L.b2a_rdf_create.argtypes = [_P, C.POINTER(RdfSpec), C.POINTER(C.c_int)]
+        L.b2a_orient_create.argtypes = [_P, C.POINTER(OrientSpec), C.POINTER(C.c_int)]
+        L.b2a_accumulate.argtypes = [_P, C.c_int]
+        L.b2a_acc_reset.argtypes = [_P, C.c_int]
+        L.b2a_acc_size.argtypes = [_P, C.c_int, C.POINTER(C.c_size_t)]
+        L.b2a_acc_device_ptr.argtypes = [_P, C.c_int, C.POINTER(_P)]
+        L.b2a_acc_read.argtypes = [_P, C.c_int, _P, _P]
+        L.b2a_rdf_normalise.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.b2a_rdf_tune.argtypes = [_P, C.c_int, C.c_int, C.c_int]
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise B2AError(rc, load().b2a_last_error().decode())
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over cudaMallocHost memory (freed when the array's base object dies)."""
+    L = load()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = L.b2a_pinned_alloc(max(n, 1))
+    if not p:
+        raise B2AError(2, L.b2a_last_error().decode())
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                L.b2a_pinned_free(self.ptr)
+            except Exception:
+                pass
+
+    owner = _Owner(p)
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    arr._b2a_owner = owner if hasattr(arr, "__dict__") else None
+    _PINNED_KEEPALIVE[id(buf)] = (owner, buf)
+    return arr
+
+
+_PINNED_KEEPALIVE = {}
+
+
+class Context:
+    """One GPU, one stream: owner of the device-resident frame batch, group tables and accumulators."""
+
+    def __init__(self, natoms: int, max_frames: int, device: int = 0):
+        self.L = load()
+        self._h = _P()
+        check(self.L.b2a_create(C.byref(self._h), device, natoms, max_frames))
+        self.natoms, self.max_frames, self.device = natoms, max_frames, device
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self.L.b2a_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return int(self.L.b2a_stream(self._h) or 0)
+
+    def sync(self):
+        check(self.L.b2a_sync(self._h))
+
+    def set_group(self, grp, index, napm, mass, charge):
+        idx = np.ascontiguousarray(index, dtype=np.int32)
+        m = np.ascontiguousarray(mass, dtype=np.float64)
+        q = np.ascontiguousarray(charge, dtype=np.float64)
+        check(self.L.b2a_set_group(self._h, grp, idx.ctypes.data, len(idx), napm, m.ctypes.data, q.ctypes.data))
+
+    def set_group_wsum(self, grp, com, wsum):
+        check(self.L.b2a_set_group_wsum(self._h, grp, com, wsum))
+
+    def nmol(self, grp):
+        return self.L.b2a_group_nmol(self._h, grp)
+
+    def submit(self, x, box9):
+        """x: [K, natoms, 3] float32 (C-contiguous), box9: [9] or [K, 9] float32."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim == 2:
+            x = x[None]
+        K = x.shape[0]
+        b = np.ascontiguousarray(box9, dtype=np.float32).reshape(-1, 9)
+        if b.shape[0] == 1 and K > 1:
+            b = np.ascontiguousarray(np.repeat(b, K, axis=0))
+        assert x.shape[1:] == (self.natoms, 3) and b.shape[0] == K
+        self._keep = [x, b]
+        check(self.L.b2a_submit_batch(self._h, K, x.ctypes.data, b.ctypes.data))
+        return K
+
+    def centers(self, grp, com=0, frame=0):
+        n = self.nmol(grp)
+        out = np.empty((3, n), dtype=np.float64)
+        check(self.L.b2a_centers(self._h, grp, com, frame, out.ctypes.data))
+        return out.T            # [nmol, 3], column-major memory like itp::matd
+
+    def centers_batch(self, grp, com=0):
+        n, K = self.nmol(grp), self.L.b2a_batch_frames(self._h)
+        out = np.empty((K, 3, n), dtype=np.float64)
+        check(self.L.b2a_centers_batch(self._h, grp, com, out.ctypes.data))
+        return out.transpose(0, 2, 1)
+
+    def positions(self, grp, napm, frame=0):
+        n = self.nmol(grp)
+        out = np.empty((napm, n, 3), dtype=np.float64)
+        check(self.L.b2a_positions(self._h, grp, frame, out.ctypes.data))
+        return out.transpose(1, 0, 2)   # [nmol, napm, 3]
+
+    # ---- accumulators ----------------------------------------------------------------------------------
+    def density_create(self, **kw):
+        s = DensitySpec(**kw)
+        a = C.c_int()
+        check(self.L.b2a_density_create(self._h, C.byref(s), C.byref(a)))
+        return a.value
+
+    def rdf_create(self, **kw):
+        s = RdfSpec(**kw)
+        a = C.c_int()
+        check(self.L.b2a_rdf_create(self._h, C.byref(s), C.byref(a)))
+        return a.value
+
+    def orient_create(self, **kw):
+        s = OrientSpec(**kw)
+        a = C.c_int()
+        check(self.L.b2a_orient_create(self._h, C.byref(s), C.byref(a)))
+        return a.value
+
+    def rdf_tune(self, acc, symmetric=0, paranoid=0):
+        check(self.L.b2a_rdf_tune(self._h, acc, symmetric, paranoid))
+
+    def accumulate(self, acc):
+        check(self.L.b2a_accumulate(self._h, acc))
+
+    def reset(self, acc):
+        check(self.L.b2a_acc_reset(self._h, acc))
+
+    def acc_size(self, acc):
+        n = C.c_size_t()
+        check(self.L.b2a_acc_size(self._h, acc, C.byref(n)))
+        return n.value
+
+    def acc_device_ptr(self, acc):
+        p = _P()
+        check(self.L.b2a_acc_device_ptr(self._h, acc, C.byref(p)))
+        return int(p.value)
+
+    def read(self, acc, ncounters):
+        counts = np.zeros(ncounters, dtype=np.uint64)
+        stats = np.zeros(STAT_NSLOTS, dtype=np.uint64)
+        check(self.L.b2a_acc_read(self._h, acc, counts.ctypes.data, stats.ctypes.data))
+        return counts, stats
+
+
+def rdf_normalise(counts, nbin, Rbin):
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    g = np.empty(nbin * Rbin, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        check(load().b2a_rdf_normalise(counts.ctypes.data, nbin, Rbin, g.ctypes.data))
+    return g.reshape(Rbin, nbin)

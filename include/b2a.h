@@ -1,0 +1,174 @@
+/*
+ * b2a.h -- C ABI of libb2a.so: the B200-native per-frame analysis path behind itp::GmxHandle.
+ *
+ * The reference has no FFI layer: its boundary is the C++ class itp::GmxHandle
+ * (reference include/itp/gmx_bits/gmx_handle.hpp:7-192) plus the per-frame loops that analysis
+ * programs write by hand on the arrays it returns.  This header is the boundary inserted INSIDE that
+ * class: include/itp/gmx forwards the loaders to it, and ported programs /
+ * bench.py call the fused accumulators.  Everything is extern "C", plain pointers and sizes, status
+ * codes instead of gmx_fatal (the C++ wrapper turns them back into gmx_fatal with the reference's
+ * messages).  One context = one GPU = one host control thread; calls on a context are not thread-safe,
+ * distinct contexts are independent.  All device work is queued on the context's stream; calls that
+ * return data to host memory synchronise that stream, everything else is asynchronous.
+ *
+ * Reference interface replaced by each entry point (paths relative to /root/reference):
+ *   b2a_set_group      <- GmxHandle::init: get_natom_per_mol / get_mass / get_charge results
+ *                         (include/itp/gmx_bits/gmx_handle.ipp:36-65, 419-468)
+ *   b2a_submit_batch   <- readFirstFrame / readNextFrame: fr->x, fr->box for K frames (ipp:68-95)
+ *   b2a_positions      <- GmxHandle::loadPosition          (ipp:115-148)
+ *   b2a_centers        <- GmxHandle::loadPositionCenter    (ipp:150-199), com 0/1/2; com 3 = dipole
+ *                         numerator with the neutral-molecule guard of
+ *                         src/general/9g_dist_bin_1803.cpp:215-222
+ *   b2a_density_*      <- README.md:129-154 template loop; src/general/calc_density_region.cpp:59-71;
+ *                         src/general/density_slit_jhl.cpp:59-77
+ *   b2a_rdf_*          <- src/general/calc_rdf_region.cpp:52-64 (setup), 73-95 (pair loop),
+ *                         100-115 (normalisation); GmxHandle::periodicity (ipp:410-417)
+ *   b2a_orient_*       <- src/mofs/calc_orient_mof.cpp:14-63, 120-200
+ */
+#ifndef B2A_H
+#define B2A_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2a_ctx b2a_ctx;
+
+enum {
+    B2A_OK              = 0,
+    B2A_ERR_ARG         = 1, /* bad argument (message says which; mirrors the reference's gmx_fatal checks) */
+    B2A_ERR_CUDA        = 2, /* CUDA runtime failure, or no usable device: there is NO CPU fallback */
+    B2A_ERR_STATE       = 3, /* call out of order (e.g. loader before any batch was submitted) */
+    B2A_ERR_NOMEM       = 4,
+    B2A_ERR_UNSUPPORTED = 5
+};
+
+/* centre kinds: the reference's `com` argument (ipp:161-174) plus the guarded dipole */
+enum { B2A_COM_MASS = 0, B2A_COM_GEOMETRY = 1, B2A_COM_CHARGE = 2, B2A_COM_DIPOLE = 3 };
+
+/* ---- context ------------------------------------------------------------------------------------ */
+const char* b2a_last_error(void);      /* thread-local text of the last failure */
+const char* b2a_version(void);
+int         b2a_device_count(void);    /* 0 if no CUDA device is visible */
+
+/* natoms = atoms per frame; max_frames = largest batch that will be submitted (device buffers are
+ * sized once: 12 B x natoms x max_frames for coordinates).                                        */
+int  b2a_create(b2a_ctx** ctx, int device, int natoms, int max_frames);
+void b2a_destroy(b2a_ctx* ctx);
+int  b2a_sync(b2a_ctx* ctx);
+void* b2a_stream(b2a_ctx* ctx);        /* the cudaStream_t all work is queued on */
+
+/* pinned host staging for async H2D (optional; pageable memory also works, synchronously) */
+void* b2a_pinned_alloc(size_t nbytes);
+void  b2a_pinned_free(void* p);
+
+/* ---- index groups (A2) ------------------------------------------------------------------------- */
+/* index[ngx] atom ids; napm atoms per molecule; molecules are the consecutive napm-runs of index, and
+ * atoms of a molecule are taken as index[i*napm] + j exactly as the reference does (ipp:187).
+ * mass/charge: napm doubles (template = first molecule, ipp:450-468).  Sum of weights is evaluated in
+ * the order Eigen's vectorised Array::sum() uses (what ipp:195 calls); b2a_set_group_wsum overrides it
+ * with the caller's own value (the C++ wrapper passes atomCenter.sum() itself).                     */
+int b2a_set_group(b2a_ctx* ctx, int grp, const int* index, int ngx, int napm, const double* mass, const double* charge);
+int b2a_set_group_wsum(b2a_ctx* ctx, int grp, int com, double wsum);
+int b2a_group_nmol(b2a_ctx* ctx, int grp);
+
+/* ---- frames (A1) ------------------------------------------------------------------------------- */
+/* x: [nframes][natoms][3] float (rvec layout), box9: [nframes][9] float row-major matrix; only the
+ * diagonal is used, as in the reference (ipp:72-74).  Replaces the current batch; cached centres of
+ * the previous batch are invalidated.                                                             */
+int b2a_submit_batch(b2a_ctx* ctx, int nframes, const float* x, const float* box9);
+int b2a_batch_frames(b2a_ctx* ctx);
+
+/* ---- compatibility loaders (A3, A4): results in the reference's Eigen memory layouts ------------ */
+/* out: nmol x 3 doubles, column-major (itp::matd): element (i,k) at i + k*nmol */
+int b2a_centers(b2a_ctx* ctx, int grp, int com, int frame, double* out);
+/* all frames of the batch at once: out[frame][k][i] */
+int b2a_centers_batch(b2a_ctx* ctx, int grp, int com, double* out);
+/* out: nmol x napm x 3 doubles in itp::boxd memory order: element (i,j)[k] at (i + j*nmol)*3 + k */
+int b2a_positions(b2a_ctx* ctx, int grp, int frame, double* out);
+
+/* ---- fused accumulators: process every frame of the current batch on the device ---------------- */
+typedef struct b2a_density_spec
+{
+    int    grp, com;
+    int    dim;              /* 0,1,2 */
+    float  low, up;          /* `real` in the reference programs */
+    double dbin;             /* bin width as the program computes it (README.md:127) */
+    int    nbin;
+    int    upper_inclusive;  /* 0: low <= p < up (README.md:145); 1: low <= p <= up (density_slit_jhl.cpp:62) */
+    int    dim2;             /* second filter dimension, or -1 (calc_density_region.cpp:64) */
+    float  low2, up2;
+} b2a_density_spec;
+
+typedef struct b2a_rdf_spec
+{
+    int   grp0, grp1;        /* i runs over grp0, j over grp1 (calc_rdf_region.cpp:73,79) */
+    int   com0, com1;        /* centre kind for each (the program uses mass for both, :70-71) */
+    int   nbin;              /* slabs along dim (:23) */
+    float low, up;           /* strict: low < p < up (:75) */
+    int   dim, dim2;
+    float low2, up2;
+    float Rm;                /* cut-off, already defaulted by the caller (:52-57) */
+    int   Rbin;              /* int(Rm / 0.002) (:58) */
+} b2a_rdf_spec;
+
+typedef struct b2a_orient_spec
+{
+    int   grp, com;          /* NCM (:153) */
+    int   DIMN;              /* axis of the cylinder / slab filter (:156-172) */
+    float low, up;           /* inclusive both ends (:158) */
+    float c1, c2;            /* cylinder centre */
+    float dr, CR, Cr;        /* radial bins: nbin1 = int((CR - Cr) / dr) in float (:133) */
+    int   nAngle;            /* dAngle = 180 / nAngle in INTEGER arithmetic (:143) */
+    int   tp1, tp2, tp3;     /* 1-based atoms in molecule (:14-29) */
+    int   DIMNOrient;        /* wall vector axis (:144) */
+    int   method;            /* 1 sum, 2 cross product (:184-191) */
+} b2a_orient_spec;
+
+/* stats slots common to all accumulators (u64 each) */
+enum {
+    B2A_STAT_FRAMES   = 0,  /* frames accumulated */
+    B2A_STAT_DROPPED  = 1,  /* samples whose bin lies outside the array (memory corruption in the reference) */
+    B2A_STAT_EXACT    = 2,  /* rdf: pairs re-evaluated in FP64 because FP32 could not decide the bin */
+    B2A_STAT_MOVED    = 3,  /* rdf: of those, pairs whose bin changed */
+    B2A_STAT_SELECTED = 4,  /* molecules passing the region filter (summed over frames) */
+    B2A_STAT_PAIRS    = 5,  /* rdf: pair distances physically evaluated */
+    B2A_STAT_OVERFLOW = 6,  /* rdf: exact-queue overflows handled inline */
+    B2A_STAT_NSLOTS   = 8
+};
+
+int b2a_density_create(b2a_ctx* ctx, const b2a_density_spec* spec, int* acc);
+int b2a_rdf_create(b2a_ctx* ctx, const b2a_rdf_spec* spec, int* acc);
+int b2a_orient_create(b2a_ctx* ctx, const b2a_orient_spec* spec, int* acc);
+
+/* queue the accumulation of the whole current batch (asynchronous) */
+int b2a_accumulate(b2a_ctx* ctx, int acc);
+int b2a_acc_reset(b2a_ctx* ctx, int acc);
+
+/* number of u64 counters (histogram cells) and their device address, for the frame-sharded merge:
+ * one all-reduce (sum, 64-bit integer) over [dptr, dptr + ncounters + B2A_STAT_NSLOTS) per accumulator. */
+int b2a_acc_size(b2a_ctx* ctx, int acc, size_t* ncounters);
+int b2a_acc_device_ptr(b2a_ctx* ctx, int acc, void** dptr);
+
+/* synchronise and copy out.  counts layouts are the reference's:
+ *   density: counts[me]                         (itp::vecd)
+ *   rdf:     counts[meZ + meR*nbin]             (itp::matd(nbin, Rbin), column-major)
+ *   orient:  counts[meZ + meA*nbin1], then ncm[nbin1] appended (orient matd + NCMDens)
+ * stats: B2A_STAT_NSLOTS values (may be NULL).                                                    */
+int b2a_acc_read(b2a_ctx* ctx, int acc, uint64_t* counts, uint64_t* stats);
+
+/* host post-processing exactly as calc_rdf_region.cpp:100-115 (shell volumes with 0.002, tail mean) */
+int b2a_rdf_normalise(const uint64_t* counts, int nbin, int Rbin, double* g);
+
+/* rdf tuning: 0 = auto.  symmetric=1 lets grp0==grp1 evaluate i<j only when every molecule passes the
+ * region filter into one slab (counts are identical); paranoid=1 re-evaluates EVERY pair in FP64
+ * (validation of the FP32 error bound; slow).                                                      */
+int b2a_rdf_tune(b2a_ctx* ctx, int acc, int symmetric, int paranoid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2A_H */
