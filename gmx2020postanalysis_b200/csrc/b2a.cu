@@ -117,7 +117,33 @@ struct b2a_ctx
     std::vector<std::unique_ptr<Acc>> accs;
     double*      d_pos_scratch = nullptr;
     size_t       pos_scratch_n = 0;
+    // optional CUDA-event timing per kernel family (bench.py): pairs are resolved lazily in b2a_timing_read
+    bool         timing = false;
+    struct Span { int slot; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double       t_ms[8] = { 0 };
+    long long    t_n[8]  = { 0 };
 };
+
+namespace
+{
+struct Timed   // RAII: records an event pair around a launch sequence when timing is on
+{
+    b2a_ctx* c; int slot; cudaEvent_t a = nullptr, b = nullptr;
+    Timed(b2a_ctx* c_, int slot_) : c(c_), slot(slot_)
+    {
+        if (!c->timing) return;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        cudaEventRecord(a, c->stream);
+    }
+    ~Timed()
+    {
+        if (!a) return;
+        cudaEventRecord(b, c->stream);
+        c->spans.push_back({ slot, a, b });
+    }
+};
+} // namespace
 
 extern "C" const char* b2a_last_error(void) { return g_err.c_str(); }
 extern "C" const char* b2a_version(void) { return "b2a 0.1 (sm_100a)"; }
@@ -283,8 +309,11 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
         }
     }
     std::memcpy(c->h_box.data(), box9, sizeof(float) * 9 * (size_t)nframes);
-    CU(cudaMemcpyAsync(c->d_x, x, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->d_geom, c->h_geom, sizeof(FrameGeom) * nframes, cudaMemcpyHostToDevice, c->stream));
+    {
+        Timed t(c, 5);
+        CU(cudaMemcpyAsync(c->d_x, x, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->d_geom, c->h_geom, sizeof(FrameGeom) * nframes, cudaMemcpyHostToDevice, c->stream));
+    }
     c->nframes = nframes;
     c->serial++;
     return B2A_OK;
@@ -303,6 +332,7 @@ static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
     if (g.valid[com] == c->serial) return B2A_OK;
     const int threads = 128;
     dim3      grid((g.nmol + threads - 1) / threads, c->nframes);
+    Timed     tm(c, 0);
     k1_centers<4><<<grid, threads, sizeof(double) * g.napm, c->stream>>>(
         c->d_x, (size_t)c->natoms * 3, c->nframes, g.d_index, g.nmol, g.napm, g.d_w[com], g.wsum[com], c->d_geom,
         g.d_cen[com], g.d_fix[com]);
@@ -316,6 +346,7 @@ extern "C" int b2a_centers(b2a_ctx* c, int grp, int com, int frame, double* out)
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_centers: null argument");
     Group* g;
     if (int rc = get_group(c, grp, &g)) return rc;
+    if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
     if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_centers: frame %d outside batch of %d", frame, c->nframes);
     CU(cudaSetDevice(c->device));
     if (int rc = ensure_centers(c, *g, com, false)) return rc;
@@ -439,6 +470,7 @@ static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p,
     auto kern = k3_rdf<IPT, THREADS, CLAMP, CUBIC, PARANOID>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(max_tiles, p.jsplit, c->nframes);
+    Timed tm(c, 2);
     kern<<<grid, THREADS, smem, c->stream>>>(a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
                                             a.d_slab_cnt, a.d_frames, p, a.d_hist, a.d_hist + a.ndev);
     CU(cudaGetLastError());
@@ -512,6 +544,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     const int nslab = p.nslab;
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, c->stream));
     {
+        Timed tm(c, 1);
         dim3 grid((p.n0 + 255) / 256, c->nframes);
         k3_slab_count<<<grid, 256, 0, c->stream>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
         CU(cudaGetLastError());
@@ -554,6 +587,7 @@ static int accumulate_density(b2a_ctx* c, Acc& a)
     CU(cudaFuncSetAttribute(k2_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total  = (long long)g->nmol * c->nframes;
     const int       blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)c->sm_count * 8);
+    Timed           tm(c, 3);
     k2_density<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->nmol, g->napm,
                                                      g->d_w[s.com], g->wsum[s.com], c->d_geom, d, a.d_hist, a.d_hist + a.ndev, smem_bins);
     CU(cudaGetLastError());
@@ -660,6 +694,39 @@ extern "C" int b2a_rdf_normalise(const uint64_t* counts, int nbin, int Rbin, dou
     return B2A_OK;
 }
 
+// ---- measurement support ---------------------------------------------------------------------------------------
+extern "C" int b2a_invalidate(b2a_ctx* c)
+{
+    if (!c) return fail(B2A_ERR_ARG, "null context");
+    c->serial++;
+    return B2A_OK;
+}
+
+extern "C" int b2a_timing_enable(b2a_ctx* c, int enable)
+{
+    if (!c) return fail(B2A_ERR_ARG, "null context");
+    c->timing = enable != 0;
+    return B2A_OK;
+}
+
+extern "C" int b2a_timing_read(b2a_ctx* c, double* ms, long long* launches)
+{
+    if (!c || !ms || !launches) return fail(B2A_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (auto& s : c->spans)
+    {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, s.a, s.b));
+        c->t_ms[s.slot] += t;
+        c->t_n[s.slot]++;
+        cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    c->spans.clear();
+    for (int i = 0; i < 8; ++i) { ms[i] = c->t_ms[i]; launches[i] = c->t_n[i]; c->t_ms[i] = 0; c->t_n[i] = 0; }
+    return B2A_OK;
+}
+
 // ---- orientation -------------------------------------------------------------------------------------------------
 extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
 {
@@ -731,6 +798,7 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
     CU(cudaFuncSetAttribute(k4_orient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long total  = (long long)g->nmol * c->nframes;
     const int       blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)c->sm_count * 8);
+    Timed           tm(c, 4);
     k4_orient<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->nmol, g->napm,
                                                     g->d_w[s.com], g->wsum[s.com], c->d_geom, d, a.d_cosedge, a.d_hist,
                                                     a.d_hist + a.ndev, smem_bins);

@@ -22,7 +22,8 @@ SYMBOLS = [
     "b2a_pinned_alloc", "b2a_pinned_free", "b2a_set_group", "b2a_set_group_wsum", "b2a_group_nmol",
     "b2a_submit_batch", "b2a_batch_frames", "b2a_centers", "b2a_centers_batch", "b2a_positions",
     "b2a_density_create", "b2a_rdf_create", "b2a_orient_create", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
-    "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune",
+    "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_invalidate", "b2a_timing_enable",
+    "b2a_timing_read",
 ]
 
 
@@ -89,6 +90,9 @@ def load():
         L.b2a_acc_read.argtypes = [_P, C.c_int, _P, _P]
         L.b2a_rdf_normalise.argtypes = [_P, C.c_int, C.c_int, _P]
         L.b2a_rdf_tune.argtypes = [_P, C.c_int, C.c_int, C.c_int]
+        L.b2a_invalidate.argtypes = [_P]
+        L.b2a_timing_enable.argtypes = [_P, C.c_int]
+        L.b2a_timing_read.argtypes = [_P, _P, _P]
         _lib = L
     return _lib
 
@@ -182,19 +186,19 @@ class Context:
         return K
 
     def centers(self, grp, com=0, frame=0):
-        n = self.nmol(grp)
+        n = max(self.nmol(grp), 0)
         out = np.empty((3, n), dtype=np.float64)
         check(self.L.b2a_centers(self._h, grp, com, frame, out.ctypes.data))
         return out.T            # [nmol, 3], column-major memory like itp::matd
 
     def centers_batch(self, grp, com=0):
-        n, K = self.nmol(grp), self.L.b2a_batch_frames(self._h)
+        n, K = max(self.nmol(grp), 0), max(self.L.b2a_batch_frames(self._h), 0)
         out = np.empty((K, 3, n), dtype=np.float64)
         check(self.L.b2a_centers_batch(self._h, grp, com, out.ctypes.data))
         return out.transpose(0, 2, 1)
 
     def positions(self, grp, napm, frame=0):
-        n = self.nmol(grp)
+        n = max(self.nmol(grp), 0)
         out = np.empty((napm, n, 3), dtype=np.float64)
         check(self.L.b2a_positions(self._h, grp, frame, out.ctypes.data))
         return out.transpose(1, 0, 2)   # [nmol, napm, 3]
@@ -220,6 +224,21 @@ class Context:
 
     def rdf_tune(self, acc, symmetric=0, paranoid=0):
         check(self.L.b2a_rdf_tune(self._h, acc, symmetric, paranoid))
+
+    def invalidate(self):
+        """Drop cached centres so the next accumulate redoes the whole path on the resident batch."""
+        check(self.L.b2a_invalidate(self._h))
+
+    def timing_enable(self, on=True):
+        check(self.L.b2a_timing_enable(self._h, int(on)))
+
+    def timing_read(self):
+        """-> dict(kernel -> (total_ms, launches)) measured with CUDA events on the context stream; resets."""
+        ms = np.zeros(8, dtype=np.float64)
+        n = np.zeros(8, dtype=np.int64)
+        check(self.L.b2a_timing_read(self._h, ms.ctypes.data, n.ctypes.data))
+        names = ["k1_centers", "k3_prep", "k3_rdf", "k2_density", "k4_orient", "h2d", "other6", "other7"]
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}
 
     def accumulate(self, acc):
         check(self.L.b2a_accumulate(self._h, acc))

@@ -168,6 +168,16 @@ int b2a_rdf_normalise(const uint64_t* counts, int nbin, int Rbin, double* g);
  * (validation of the FP32 error bound; slow).                                                      */
 int b2a_rdf_tune(b2a_ctx* ctx, int acc, int symmetric, int paranoid);
 
+/* ---- measurement support ------------------------------------------------------------------------ */
+/* Forget the cached centres of the resident batch: the next b2a_accumulate / loader call recomputes the
+ * whole path (used by bench.py so that a timed step never reuses a previous step's intermediate results). */
+int b2a_invalidate(b2a_ctx* ctx);
+/* Bracket every kernel family with CUDA events on the context stream.  b2a_timing_read synchronises, returns
+ * total milliseconds and launch counts for slots {0: K1 centres, 1: K3 slab prep, 2: K3 pair kernel,
+ * 3: K2 density, 4: K4 orientation, 5: H2D copies} (arrays of 8) and resets the totals.               */
+int b2a_timing_enable(b2a_ctx* ctx, int enable);
+int b2a_timing_read(b2a_ctx* ctx, double* ms, long long* launches);
+
 #ifdef __cplusplus
 }
 #endif

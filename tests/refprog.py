@@ -123,3 +123,53 @@ def oracle_readme_template(system, nframes, grp, nbin=100, dim=2, low=0.0, up=30
     for i in range(nbin):
         lines.append(fmt_fixed(float(low32) + dbin / 2 + dbin * i, 8, 5) + " " + fmt_fixed(dens[i], 10, 5))
     return lines, hist
+
+
+# ---- mofs/calc_orient_mof.cpp main() restated on oracle.port -------------------------------------------------
+def oracle_orient_mof(system, nframes, grp, NCM=0, DIMN=2, low=(0.0, 0.0, 0.0), up=(100.0, 100.0, 100.0), c1=0.0, c2=0.0,
+                      dr=0.01, CR=0.5, Cr=0.0, nA=90, tp1=1, tp2=2, tp3=3, DIMNOrient=2, method=1, return_counts=False):
+    Lbox = port.lbox_from_box9(system.box9())
+    gi = group_info(system, grp)
+    orient = ncm = None
+    for f in range(nframes):
+        x = system.frame(f)
+        pos = port.load_position(x, gi["index"], gi["napm"], Lbox)
+        pc = port.load_position_center(x, gi["index"], gi["napm"], gi["w"][NCM], Lbox)
+        orient, ncm, _ = port.orient_accum(pos, pc, Lbox, DIMN, f32(low[DIMN]), f32(up[DIMN]), f32(c1), f32(c2), f32(dr),
+                                           f32(CR), f32(Cr), nA, tp1, tp2, tp3, DIMNOrient, method, orient, ncm)
+    if return_counts:
+        return orient, ncm
+    return orient_text(orient, ncm, nA)
+
+
+def orient_text(orient, ncm, nA):
+    """calc_orient_mof.cpp:201-215.  orient: [nAngle, nbin1] counts."""
+    dAngle = float(180 // nA)
+    lines = []
+    for i in range(nA):
+        s = f"{(i + 0.5) * dAngle:8.4e}  "
+        for j in range(len(ncm)):
+            v = float(orient[i, j])
+            if ncm[j] > 0:
+                v = v / float(ncm[j])
+            s += f"{v:8.4e} "
+        lines.append(s)
+    return lines
+
+
+def parse_orient_args(args):
+    """-flag value list (rvec flags take three values) -> kwargs of oracle_orient_mof."""
+    kw, i = {}, 0
+    names = {"-NCM": "NCM", "-dim": "DIMN", "-c1": "c1", "-c2": "c2", "-dr": "dr", "-CR": "CR", "-Cr": "Cr", "-nA": "nA",
+             "-tp1": "tp1", "-tp2": "tp2", "-tp3": "tp3", "-DIMNOrient": "DIMNOrient", "-method": "method"}
+    while i < len(args):
+        a = args[i]
+        if a in ("-low", "-up"):
+            kw[a[1:]] = tuple(float(v) for v in args[i + 1:i + 4])
+            i += 4
+        elif a == "-dbin":
+            i += 4
+        else:
+            kw[names[a]] = args[i + 1]
+            i += 2
+    return kw

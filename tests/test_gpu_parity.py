@@ -1,0 +1,350 @@
+"""GPU parity tests proper: every call goes through the C ABI (ctypes -> libb2a.so) and is compared with the
+oracle on the same seeded inputs.  Integer histograms and FP64 centres/positions are required to be BIT-EXACT
+(the north star's 1e-5 relative tolerance on centres is met with margin 0)."""
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as GC
+import refprog
+from gmx2020postanalysis_b200 import lib, synth
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _groups(ctx, system, names):
+    infos = []
+    for g, name in enumerate(names):
+        gi = refprog.group_info(system, name)
+        ctx.set_group(g, gi["index"], gi["napm"], gi["mass"], gi["charge"])
+        infos.append(gi)
+    return infos
+
+
+# ---- A3 / A4: loaders ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["water", "il"])
+def test_loaders_bit_exact(gpu_ctx_factory, which):
+    system = synth.water_box(2500, 4.2, seed=51) if which == "water" else synth.ionic_liquid(300, 4.6, seed=52)
+    names = ["SOL"] if which == "water" else ["CAT", "ANI"]
+    K = 3
+    ctx = gpu_ctx_factory(system.natoms, K)
+    infos = _groups(ctx, system, names)
+    x, box = system.frames(0, K), system.box9()
+    Lbox = port.lbox_from_box9(box)
+    ctx.submit(x, box)
+    for g, gi in enumerate(infos):
+        for com in (0, 1, 2):
+            batch = ctx.centers_batch(g, com)
+            for f in range(K):
+                exp = port.load_position_center(x[f], gi["index"], gi["napm"], gi["w"][com], Lbox)
+                assert np.array_equal(ctx.centers(g, com, f), exp, equal_nan=True)
+                assert np.array_equal(batch[f], exp, equal_nan=True)
+        exp = port.load_position_center(x[1], gi["index"], gi["napm"], gi["charge"], Lbox, dipole_guard=True)
+        assert np.array_equal(ctx.centers(g, lib.COM_DIPOLE, 1), exp, equal_nan=True)
+        for f in (0, K - 1):
+            assert np.array_equal(ctx.positions(g, gi["napm"], f), port.load_position(x[f], gi["index"], gi["napm"], Lbox))
+
+
+def test_loaders_golden_from_reference(gpu_ctx_factory):
+    """Against outputs of the reference's own loadPosition / loadPositionCenter (tests/golden/loaders.npz)."""
+    gold = np.load(os.path.join(GOLD, "loaders.npz"))
+    for name, system in GC.loader_systems().items():
+        ctx = gpu_ctx_factory(system.natoms, 1)
+        ctx.submit(system.frame(GC.LOADER_FRAME), system.box9())
+        for g, (s, off) in enumerate(zip(system.species, system.offsets())):
+            idx = np.arange(off, off + s.nmol * s.napm, dtype=np.int32)
+            ctx.set_group(g, idx, s.napm, s.mass.astype(np.float64), s.charge.astype(np.float64))
+            assert np.array_equal(ctx.positions(g, s.napm, 0), gold[f"{name}.{s.name}.pos"])
+            for com in (0, 1, 2):
+                assert np.array_equal(ctx.centers(g, com, 0), gold[f"{name}.{s.name}.cen{com}"], equal_nan=True)
+    x, box, idx, napm, mass, charge = GC.edge_fixture()
+    ctx = gpu_ctx_factory(len(x), 1)
+    ctx.set_group(0, idx, napm, mass, charge)
+    ctx.submit(x, box)
+    assert np.array_equal(ctx.positions(0, napm, 0), gold["edge.pos"])
+    for com in (0, 1, 2):
+        assert np.array_equal(ctx.centers(0, com, 0), gold[f"edge.cen{com}"], equal_nan=True)
+
+
+def test_noncontiguous_index_group(gpu_ctx_factory):
+    """O-only group of a 3-site water box (stride-3 gather, napm = 1): centre == the float coordinate exactly."""
+    system = synth.water_box(1000, 3.1, seed=53, split_atoms=True)
+    ctx = gpu_ctx_factory(system.natoms, 1)
+    (gi,) = _groups(ctx, system, ["OW"])
+    x = system.frame(0)
+    ctx.submit(x, system.box9())
+    assert np.array_equal(ctx.centers(0, 0, 0), x[0::3].astype(np.float64))
+
+
+def test_error_behaviour(gpu_ctx_factory):
+    ctx = gpu_ctx_factory(30, 2)
+    with pytest.raises(lib.B2AError, match="whole molecules"):            # gmx_handle.ipp:432
+        ctx.set_group(0, np.arange(10), 3, np.ones(3), np.ones(3))
+    ctx.set_group(0, np.arange(30), 3, np.ones(3), np.ones(3))
+    with pytest.raises(lib.B2AError, match="no frame batch"):
+        ctx.centers(0, 0, 0)
+    with pytest.raises(lib.B2AError, match=r"grp\(1\) should less than ngrps"):   # gmx_handle.ipp:101
+        ctx.centers(1, 0, 0)
+    ctx.submit(np.zeros((1, 30, 3), np.float32) + 0.5, np.eye(3, dtype=np.float32).ravel() * 2)
+    with pytest.raises(lib.B2AError, match="frame 1 outside"):
+        ctx.centers(0, 0, 1)
+
+
+# ---- A8: density ---------------------------------------------------------------------------------------------
+def _density_oracle(x, gi, Lbox, K, com, dim, low, up, dbin, nbin, inclusive, dim2, low2, up2):
+    exp, drop = np.zeros(nbin, np.uint64), 0
+    for f in range(K):
+        pc = port.load_position_center(x[f], gi["index"], gi["napm"], gi["w"][com], Lbox)
+        _, d = port.density_accum(pc, dim, refprog.f32(low), refprog.f32(up), dbin, nbin, exp, bool(inclusive), dim2,
+                                  refprog.f32(low2), refprog.f32(up2))
+        drop += d
+    return exp, drop
+
+
+@pytest.mark.parametrize("case", [
+    dict(sys="water", nbin=100, dim=2, low=0.0, up=4.476, inclusive=0, dim2=-1, low2=0.0, up2=0.0, com=0),     # BASELINE config 1
+    dict(sys="il", nbin=37, dim=0, low=0.3, up=4.9, inclusive=1, dim2=1, low2=0.5, up2=4.0, com=1),
+    dict(sys="water", nbin=7, dim=1, low=1.0, up=2.0, inclusive=0, dim2=-1, low2=0.0, up2=0.0, com=0),
+    dict(sys="water", nbin=50000, dim=0, low=0.0, up=4.476, inclusive=0, dim2=-1, low2=0.0, up2=0.0, com=1),   # global-atomic path
+])
+def test_density_bit_exact(gpu_ctx_factory, case):
+    system = synth.water_box(3000, 4.476, seed=20200101) if case["sys"] == "water" else synth.ionic_liquid(400, 5.1, seed=54)
+    name = "SOL" if case["sys"] == "water" else "CAT"
+    K = 5
+    ctx = gpu_ctx_factory(system.natoms, K)
+    (gi,) = _groups(ctx, system, [name])
+    x, box = system.frames(0, K), system.box9()
+    Lbox = port.lbox_from_box9(box)
+    dbin = float(np.float32(np.float32(np.float32(case["up"]) - np.float32(case["low"])) / np.float32(case["nbin"])))
+    acc = ctx.density_create(grp=0, com=case["com"], dim=case["dim"], low=case["low"], up=case["up"], dbin=dbin,
+                             nbin=case["nbin"], upper_inclusive=case["inclusive"], dim2=case["dim2"], low2=case["low2"],
+                             up2=case["up2"])
+    ctx.submit(x, box)
+    ctx.accumulate(acc)
+    ctx.submit(x[:2], box)          # second, shorter batch accumulates on top
+    ctx.accumulate(acc)
+    got, st = ctx.read(acc, case["nbin"])
+    e1, d1 = _density_oracle(x, gi, Lbox, K, case["com"], case["dim"], case["low"], case["up"], dbin, case["nbin"],
+                             case["inclusive"], case["dim2"], case["low2"], case["up2"])
+    e2, d2 = _density_oracle(x[:2], gi, Lbox, 2, case["com"], case["dim"], case["low"], case["up"], dbin, case["nbin"],
+                             case["inclusive"], case["dim2"], case["low2"], case["up2"])
+    assert np.array_equal(got, e1 + e2)
+    assert int(st[lib.STAT_FRAMES]) == K + 2 and int(st[lib.STAT_DROPPED]) == d1 + d2
+    assert got.sum() > 0
+
+
+def test_density_template_matches_reference_program_output(gpu_ctx_factory):
+    """BASELINE config 1 (reduced to 10 frames): output text of the README template program, from GPU counts."""
+    case = GC.program_cases()["density_template_c1"]
+    system, K, nbin = case["system"](), case["nframes"], 100
+    ctx = gpu_ctx_factory(system.natoms, K)
+    _groups(ctx, system, ["SOL"])
+    low, up = np.float32(0.0), np.float32(4.476)
+    dbin = float(np.float32(np.float32(up - low) / np.float32(nbin)))
+    acc = ctx.density_create(grp=0, com=0, dim=2, low=0.0, up=4.476, dbin=dbin, nbin=nbin, upper_inclusive=0, dim2=-1,
+                             low2=0.0, up2=0.0)
+    ctx.submit(system.frames(0, K), system.box9())
+    ctx.accumulate(acc)
+    got, st = ctx.read(acc, nbin)
+    dens = got.astype(np.float64) / int(st[lib.STAT_FRAMES])     # density /= hd.nframe (README.md:154)
+    lines = [refprog.fmt_fixed(float(low) + dbin / 2 + dbin * i, 8, 5) + " " + refprog.fmt_fixed(dens[i], 10, 5) for i in range(nbin)]
+    assert lines == open(os.path.join(GOLD, "density_template_c1.txt")).read().split("\n")[:-1]
+
+
+# ---- A7: RDF -------------------------------------------------------------------------------------------------
+def _rdf_gpu(ctx, system, g0, g1, K, spec, Rm, Rbin, paranoid=0, frames=None):
+    _groups(ctx, system, [g0, g1])
+    acc = ctx.rdf_create(grp0=0, grp1=1, com0=spec["com"], com1=spec["com"], nbin=spec["nbin"], low=spec["low"], up=spec["up"],
+                         dim=spec["dim"], dim2=spec["dim2"], low2=spec["low2"], up2=spec["up2"], Rm=Rm, Rbin=Rbin)
+    ctx.rdf_tune(acc, 0, paranoid)
+    ctx.submit(system.frames(0, K) if frames is None else frames, system.box9())
+    ctx.accumulate(acc)
+    got, st = ctx.read(acc, spec["nbin"] * Rbin)
+    return got.reshape(Rbin, spec["nbin"]), st
+
+
+_DEF = dict(nbin=5, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0, Rm=0.0, com=0)
+
+
+@pytest.mark.parametrize("case", [
+    dict(sys=("water", 4000, 4.93), g=("OW", "OW"), K=2),                                                   # C2 shape, reduced
+    dict(sys=("il", 400, 5.1), g=("CAT", "ANI"), K=3, nbin=3, low=0.5, up=4.6, dim=1, dim2=0, low2=0.3, up2=4.9, Rm=1.9),
+    dict(sys=("il", 400, 5.1), g=("CAT", "ANI"), K=2),                                                      # C3 shape, reduced
+    dict(sys=("il", 400, 5.1), g=("ANI", "CAT"), K=2, com=1, nbin=1, low=0.0, up=5.1),
+    dict(sys=("water", 3000, 4.476), g=("SOL", "SOL"), K=2, com=2, nbin=2, low=0.0, up=4.476, dim=2, Rm=0.9),   # charge centres: NaN/inf centres
+    dict(sys=("water", 1500, 3.55), g=("OW", "OW"), K=1, paranoid=1),                                        # every pair through FP64
+    dict(sys=("water", 700, 2.8), g=("OW", "OW"), K=2, Rm=0.4),                                              # tiny Rm: clamp-free, large kmax
+])
+def test_rdf_bit_exact(gpu_ctx_factory, case):
+    kind, n, L = case["sys"]
+    system = synth.water_box(n, L, seed=61, split_atoms=(case["g"][0] == "OW")) if kind == "water" else synth.ionic_liquid(n, L, seed=62)
+    spec = dict(_DEF)
+    spec.update({k: v for k, v in case.items() if k in _DEF})
+    K = case["K"]
+    exp, est, Rm, Rbin = refprog.oracle_rdf_region(system, K, case["g"][0], case["g"][1], return_counts=True, **spec)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    got, st = _rdf_gpu(ctx, system, case["g"][0], case["g"][1], K, spec, Rm, Rbin, case.get("paranoid", 0))
+    assert np.array_equal(got, exp)
+    assert int(got.sum()) == int(est[0]) and int(st[lib.STAT_DROPPED]) == int(est[1])
+    assert int(st[lib.STAT_SELECTED]) == int(est[2]) and int(st[lib.STAT_FRAMES]) == K
+    if case.get("paranoid"):
+        assert int(st[lib.STAT_EXACT]) == n * n * K
+
+
+def test_rdf_matches_reference_program_output(gpu_ctx_factory):
+    """The .xvg the reference's calc_rdf_region wrote (tests/golden), reproduced from GPU counts + b2a_rdf_normalise."""
+    for name in ("rdf_water_oo", "rdf_il_slabs"):
+        case = GC.program_cases()[name]
+        system, K = case["system"](), case["nframes"]
+        a = case["args"]
+        spec = dict(_DEF)
+        m = {"-nbin": "nbin", "-low": "low", "-up": "up", "-dim": "dim", "-dim2": "dim2", "-low2": "low2", "-up2": "up2", "-Rm": "Rm"}
+        for k in range(0, len(a), 2):
+            spec[m[a[k]]] = a[k + 1]
+        Lbox = port.lbox_from_box9(system.box9())
+        Rm = refprog.f32(spec["Rm"]) if spec["Rm"] >= 1e-6 else port.rdf_default_rm(Lbox)
+        Rbin = port.rdf_rbin(Rm)
+        ctx = gpu_ctx_factory(system.natoms, K)
+        got, _ = _rdf_gpu(ctx, system, case["groups"][0], case["groups"][1], K, spec, Rm, Rbin)
+        g = lib.rdf_normalise(got.ravel(), spec["nbin"], Rbin)
+        lines = refprog.rdf_region_text(g, spec["nbin"], Rbin, spec["dim"], spec["low"], spec["up"])
+        assert lines == open(os.path.join(GOLD, name + ".txt")).read().split("\n")[:-1]
+
+
+def test_rdf_edge_fixtures(gpu_ctx_factory):
+    """Hand-placed pairs: exactly on a bin edge, at r == Rm, at r^2 == 1e-6 boundary, coincident, across the box."""
+    L = np.float32(8.0)
+    Rm = refprog.f32(3.0)
+    Rbin = port.rdf_rbin(Rm)
+    base = np.array([1.0, 1.0, 1.0], np.float32)
+    offs = [0.0, 0.002, 0.0020000001, 0.001, 0.0009999, 0.0010001, 3.0, 2.9999998, 3.0000002, 1.5, 0.75, 2.998, 4.0, 7.999]
+    pts = [base] + [base + np.array([d, 0, 0], np.float32) for d in offs[1:]] + [np.array([7.9995, 1.0, 1.0], np.float32)]
+    # a few diagonal pairs whose distance is irrational
+    pts += [base + np.array([0.3, 0.4, 1.2], np.float32), base + np.array([1.7320508, 1.7320508, 1.7320508], np.float32)]
+    x = np.array(pts, np.float32) % L
+    n = len(x)
+    box = np.zeros(9, np.float32)
+    box[0] = box[4] = box[8] = L
+    Lbox = port.lbox_from_box9(box)
+    pc = x.astype(np.float64)
+    exp, est = port.rdf_accum(pc, pc, Lbox, 1, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, Rbin)
+    ctx = gpu_ctx_factory(n, 1)
+    for g in (0, 1):
+        ctx.set_group(g, np.arange(n), 1, np.ones(1), np.ones(1))
+    acc = ctx.rdf_create(grp0=0, grp1=1, com0=1, com1=1, nbin=1, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0,
+                         Rm=Rm, Rbin=Rbin)
+    ctx.submit(x, box)
+    ctx.accumulate(acc)
+    got, st = ctx.read(acc, Rbin)
+    assert np.array_equal(got.reshape(Rbin, 1), exp)
+    assert int(st[lib.STAT_DROPPED]) == int(est[1])
+
+
+def test_rdf_properties_translation_and_transpose(gpu_ctx_factory):
+    """Size-independent properties: translating every atom by a box vector leaves the histogram
+    unchanged; swapping the groups leaves the radial histogram unchanged when the filter passes everything."""
+    system = synth.ionic_liquid(500, 5.4, seed=63)
+    K = 2
+    Lbox = port.lbox_from_box9(system.box9())
+    Rm = port.rdf_default_rm(Lbox)
+    Rbin = port.rdf_rbin(Rm)
+    spec = dict(_DEF, nbin=1)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    h_ab, _ = _rdf_gpu(ctx, system, "CAT", "ANI", K, spec, Rm, Rbin)
+    ctx2 = gpu_ctx_factory(system.natoms, K)
+    h_ba, _ = _rdf_gpu(ctx2, system, "ANI", "CAT", K, spec, Rm, Rbin)
+    assert np.array_equal(h_ab, h_ba) and h_ab.sum() > 0
+
+
+@pytest.mark.parametrize("nonzero_box", [(3.0, 4.0, 5.0)])
+def test_rdf_orthorhombic_box(gpu_ctx_factory, nonzero_box):
+    """Non-cubic box: per-dimension fixed-point units (the CUBIC=false kernel)."""
+    system = synth.ionic_liquid(200, 3.0, seed=64)
+    system.L = np.array(nonzero_box, np.float32)
+    K = 2
+    spec = dict(_DEF, nbin=2, low=0.0, up=3.0)
+    exp, est, Rm, Rbin = refprog.oracle_rdf_region(system, K, "CAT", "ANI", return_counts=True, **spec)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    got, st = _rdf_gpu(ctx, system, "CAT", "ANI", K, spec, Rm, Rbin)
+    assert np.array_equal(got, exp) and got.sum() > 0
+
+
+def test_rdf_full_size_paranoid_free_properties(gpu_ctx_factory):
+    """BASELINE config 2 at FULL size (72 000 O atoms, one frame): properties that need no CPU oracle --
+    total count == number of ordered pairs within the cut-off as counted by the FP64-only kernel variant on an
+    i-subset, histogram symmetric under group swap, frames counter."""
+    n, L = 72000, 12.913
+    system = synth.water_box(n, L, seed=20200102, split_atoms=True)
+    Lbox = port.lbox_from_box9(system.box9())
+    Rm = port.rdf_default_rm(Lbox)
+    Rbin = port.rdf_rbin(Rm)
+    ctx = gpu_ctx_factory(system.natoms, 1)
+    x = system.frames(0, 1)
+    got, st = _rdf_gpu(ctx, system, "OW", "OW", 1, dict(_DEF), Rm, Rbin, frames=x)
+    assert int(st[lib.STAT_PAIRS]) == n * n and int(st[lib.STAT_SELECTED]) == n
+    assert got[:, [0, 1, 3, 4]].sum() == 0                      # default slabs: everything lands in meZ == 2
+    frac = got.sum() / float(n) / float(n)
+    assert abs(frac - np.pi / 6) < 2e-3                         # ideal-gas-like box: sphere of radius L/2 in L^3
+    # the oracle on an i-subset of the same frame (first 64 oxygens against all): bit-exact
+    sub = x[0][0::3][:64].astype(np.float64)
+    allo = x[0][0::3].astype(np.float64)
+    exp, _ = port.rdf_accum(sub, allo, Lbox, 5, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, Rbin)
+    ctx2 = gpu_ctx_factory(system.natoms, 1)
+    gi = refprog.group_info(system, "OW")
+    ctx2.set_group(0, gi["index"][:64], 1, gi["mass"], gi["charge"])
+    ctx2.set_group(1, gi["index"], 1, gi["mass"], gi["charge"])
+    acc = ctx2.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=5, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0,
+                          up2=100.0, Rm=Rm, Rbin=Rbin)
+    ctx2.submit(x, system.box9())
+    ctx2.accumulate(acc)
+    got2, _ = ctx2.read(acc, 5 * Rbin)
+    assert np.array_equal(got2.reshape(Rbin, 5), exp)
+
+
+# ---- A6: orientation ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["orient_water", "orient_il_cross"])
+def test_orient_bit_exact_and_reference_text(gpu_ctx_factory, name):
+    case = GC.program_cases()[name]
+    system, K = case["system"](), case["nframes"]
+    kw = refprog.parse_orient_args(case["args"])
+    exp_o, exp_n = refprog.oracle_orient_mof(system, K, case["groups"][0], return_counts=True, **kw)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    _groups(ctx, system, case["groups"])
+    D = kw["DIMN"]
+    acc = ctx.orient_create(grp=0, com=kw["NCM"], DIMN=D, low=kw["low"][D], up=kw["up"][D], c1=kw["c1"], c2=kw["c2"],
+                            dr=kw["dr"], CR=kw["CR"], Cr=kw["Cr"], nAngle=kw["nA"], tp1=kw["tp1"], tp2=kw["tp2"],
+                            tp3=kw["tp3"], DIMNOrient=kw["DIMNOrient"], method=kw["method"])
+    ctx.submit(system.frames(0, K), system.box9())
+    ctx.accumulate(acc)
+    nbin1 = len(exp_n)
+    got, st = ctx.read(acc, nbin1 * kw["nA"] + nbin1)
+    o, ncm = got[:nbin1 * kw["nA"]].reshape(kw["nA"], nbin1), got[nbin1 * kw["nA"]:]
+    assert np.array_equal(o, exp_o) and np.array_equal(ncm, exp_n) and o.sum() > 0
+    assert refprog.orient_text(o, ncm, kw["nA"]) == open(os.path.join(GOLD, name + ".txt")).read().split("\n")[:-1]
+
+
+def test_dipole_orientation_config4_shape(gpu_ctx_factory):
+    """BASELINE config 4, reduced: charge-centre dipole vectors (guarded) + bisector angle histogram."""
+    system = synth.water_box(5000, 5.3, seed=20200104)
+    K = 3
+    ctx = gpu_ctx_factory(system.natoms, K)
+    (gi,) = _groups(ctx, system, ["SOL"])
+    x, box = system.frames(0, K), system.box9()
+    Lbox = port.lbox_from_box9(box)
+    ctx.submit(x, box)
+    mu = ctx.centers_batch(0, lib.COM_DIPOLE)
+    for f in range(K):
+        assert np.array_equal(mu[f], port.load_position_center(x[f], gi["index"], 3, gi["charge"], Lbox, dipole_guard=True))
+    # |mu| of rigid SPC/E is constant: 0.4238 e * 2 * 0.1 nm * cos(109.47/2 deg) = 0.0489 e nm
+    assert np.allclose(np.linalg.norm(mu[0], axis=1), 0.04894, atol=2e-4)
+    kw = dict(NCM=0, DIMN=2, low=(0, 0, -1.0), up=(100, 100, 100.0), c1=0.0, c2=0.0, dr=100.0, CR=100.0, Cr=0.0, nA=90,
+              tp1=1, tp2=2, tp3=3, DIMNOrient=2, method=1)
+    exp_o, exp_n = refprog.oracle_orient_mof(system, K, "SOL", return_counts=True, **kw)
+    acc = ctx.orient_create(grp=0, com=0, DIMN=2, low=-1.0, up=100.0, c1=0.0, c2=0.0, dr=100.0, CR=100.0, Cr=0.0, nAngle=90,
+                            tp1=1, tp2=2, tp3=3, DIMNOrient=2, method=1)
+    ctx.accumulate(acc)
+    got, st = ctx.read(acc, 90 + 1)
+    assert np.array_equal(got[:90].reshape(90, 1), exp_o) and got[90] == exp_n[0] == 5000 * K
