@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -68,6 +69,7 @@ struct Group
 {
     int     ngx = 0, napm = 0, nmol = 0;
     int*    d_index = nullptr;
+    std::vector<int> h_index;
     double* d_w[4]  = { nullptr, nullptr, nullptr, nullptr };   // mass, ones, charge, charge(dipole)
     double  wsum[4] = { 0, 0, 0, 0 };
     // centre cache per com for the current batch
@@ -245,6 +247,7 @@ extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int
     Group& g = c->groups[grp];
     free_group(g);
     g.ngx = ngx; g.napm = napm; g.nmol = nmol;
+    g.h_index.assign(index, index + ngx);
     CU(cudaMalloc(&g.d_index, sizeof(int) * ngx));
     CU(cudaMemcpy(g.d_index, index, sizeof(int) * ngx, cudaMemcpyHostToDevice));
     std::vector<double> ones(napm, 1.0);
@@ -464,17 +467,26 @@ extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
 static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
 static float next_up(float v) { return std::nextafterf(v, INFINITY); }
 
-template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID>
-static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, int max_tiles)
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, bool SYM>
+static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, dim3 grid)
 {
-    auto kern = k3_rdf<IPT, THREADS, CLAMP, CUBIC, PARANOID>;
+    auto kern = k3_rdf<IPT, THREADS, CLAMP, CUBIC, PARANOID, SYM>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(max_tiles, p.jsplit, c->nframes);
-    Timed tm(c, 2);
     kern<<<grid, THREADS, smem, c->stream>>>(a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
                                             a.d_slab_cnt, a.d_frames, p, a.d_hist, a.d_hist + a.ndev);
     CU(cudaGetLastError());
     return B2A_OK;
+}
+
+template <bool SYM>
+static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, dim3 grid, bool clamp, bool cubic)
+{
+    constexpr int IPT = 8, TH = 128;
+    if (a.paranoid)
+        return clamp ? (cubic ? launch_rdf<IPT, TH, true, true, true, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, true, false, true, SYM>(c, a, g0, g1, p, smem, grid))
+                     : (cubic ? launch_rdf<IPT, TH, false, true, true, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, false, false, true, SYM>(c, a, g0, g1, p, smem, grid));
+    return clamp ? (cubic ? launch_rdf<IPT, TH, true, true, false, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, true, false, false, SYM>(c, a, g0, g1, p, smem, grid))
+                 : (cubic ? launch_rdf<IPT, TH, false, true, false, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, false, false, false, SYM>(c, a, g0, g1, p, smem, grid));
 }
 
 static int accumulate_rdf(b2a_ctx* c, Acc& a)
@@ -495,24 +507,26 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     p.Rm     = (double)s.Rm;
     p.Rbin_d = (double)s.Rbin;
     p.rbin_bits = kMagicBits + (unsigned)s.Rbin;
+    // symmetric evaluation is legal only when both sides are the very same molecules with the same centre kind
+    p.sym_enabled = (a.symmetric && s.com0 == s.com1 && g0->nmol == g1->nmol && g0->napm == g1->napm && g0->h_index == g1->h_index) ? 1 : 0;
 
     // per-frame fast-path constants and the largest reachable bin
     bool   cubic = true;
     double tmax  = 0.0;
-    // K3 error bound (DESIGN.md): relative error of the FP32 distance <= 4.5 * 2^-24 (cubic), 6.5 * 2^-24 otherwise
     CU(cudaStreamSynchronize(c->stream));   // h_frames reuse
     for (int f = 0; f < c->nframes; ++f)
     {
         const FrameGeom& g = c->h_geom[f];
         if (g.L[0] != g.L[1] || g.L[0] != g.L[2]) cubic = false;
     }
+    // K3 error bound (DESIGN.md): relative error of the FP32 distance <= 4.5 * 2^-24 (cubic), 6.5 * 2^-24 otherwise
     const double eps_true = (cubic ? 4.5 : 6.5) * std::ldexp(1.0, -24);
     const double eps      = eps_true + 1.3e-7;
     for (int f = 0; f < c->nframes; ++f)
     {
         const FrameGeom& g    = c->h_geom[f];
         RdfFrame&        fr   = a.h_frames[f];
-        const double     unit = g.L[0] / 4294967296.0;         // nm per x fixed unit
+        const double     unit = g.L[0] / 4294967296.0;                  // nm per x fixed unit
         const double     sc   = unit * (double)s.Rbin / (double)s.Rm;   // bins per unit
         float lo = (float)(sc * (1.0 - eps)), hi = (float)(sc * (1.0 + eps));
         if ((double)lo > sc * (1.0 - eps)) lo = next_down(lo);
@@ -532,12 +546,15 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     CU(cudaMemcpyAsync(a.d_frames, a.h_frames, sizeof(RdfFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
 
     // shared histogram: every reachable bin if it fits comfortably, else clamp to Rbin (+1 FMNMX pair per pair)
-    const size_t fixed_smem = kTileJ * sizeof(int4) + kQueueCap * sizeof(unsigned long long) + 16;
+    const size_t   fixed_smem  = kTileJ * sizeof(int4) + kQueueCap * sizeof(unsigned) + 16;
     const unsigned full_stride = (unsigned)std::ceil(tmax) + 4;
-    bool clamp = ((size_t)full_stride * 4 + fixed_smem > 56 * 1024);
-    p.kstride  = clamp ? (unsigned)s.Rbin + 3 : full_stride;
-    p.clamp    = clamp;
-    const size_t smem = fixed_smem + (size_t)p.kstride * 4;
+    // Measured on B200 (profiles/r01_k3_tuning.md): clamping out-of-range pairs into ONE trash bin is faster than an
+    // oversize histogram even though it costs two FMNMX per pair -- the ~48% of lanes beyond Rm then hit a single
+    // address (one merged wavefront instead of random bank conflicts) and never enter the undecided queue.
+    bool           clamp       = true;
+    if (const char* e = getenv("B2A_RDF_CLAMP")) clamp = atoi(e) != 0 || ((size_t)full_stride * 4 + fixed_smem > 40 * 1024);
+    p.kstride                  = clamp ? (unsigned)s.Rbin + 3 : full_stride;
+    const size_t smem          = fixed_smem + (size_t)p.kstride * 4;
     if (smem > 200 * 1024) return fail(B2A_ERR_UNSUPPORTED, "rdf: Rbin=%d needs %zu bytes of shared memory per block", s.Rbin, smem);
 
     // prep: slab ids, counts, scatter
@@ -553,23 +570,32 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         CU(cudaGetLastError());
     }
 
-    // tiling: TI molecules of one slab per block, j split so that the grid covers the machine several times
-    const int IPT = 8, THREADS = 128, TI = IPT * THREADS;
-    const int max_tiles = (p.n0 + TI - 1) / TI + std::min(nslab, p.n0);
-    const int itiles    = std::max(1, (p.n0 + TI - 1) / TI);
-    int       jsplit    = std::max(1, (c->sm_count * 16 + itiles * c->nframes - 1) / (itiles * c->nframes));
-    jsplit              = std::min(jsplit, std::max(1, (p.n1 + 511) / 512));
-    p.jsplit            = jsplit;
-    p.jchunk            = (p.n1 + jsplit - 1) / jsplit;
-
-#define B2A_LAUNCH(CL, CB, PA) launch_rdf<8, 128, CL, CB, PA>(c, a, *g0, *g1, p, smem, max_tiles)
-    int rc;
-    if (a.paranoid) rc = clamp ? (cubic ? B2A_LAUNCH(true, true, true) : B2A_LAUNCH(true, false, true))
-                               : (cubic ? B2A_LAUNCH(false, true, true) : B2A_LAUNCH(false, false, true));
-    else rc = clamp ? (cubic ? B2A_LAUNCH(true, true, false) : B2A_LAUNCH(true, false, false))
-                    : (cubic ? B2A_LAUNCH(false, true, false) : B2A_LAUNCH(false, false, false));
-#undef B2A_LAUNCH
-    return rc;
+    // tiling: TI molecules of one slab per block
+    constexpr int TI = 8 * 128;
+    Timed tm(c, 2);
+    {
+        // full mode: j split so that the grid covers the machine several times
+        const int max_tiles = (p.n0 + TI - 1) / TI + std::min(nslab, p.n0);
+        const int itiles    = std::max(1, (p.n0 + TI - 1) / TI);
+        int       jsplit    = std::max(1, (c->sm_count * 24 + itiles * c->nframes - 1) / (itiles * c->nframes));
+        jsplit              = std::min(jsplit, std::max(1, (p.n1 + kTileJ - 1) / kTileJ));
+        p.jsplit            = jsplit;
+        p.jchunk            = (p.n1 + jsplit - 1) / jsplit;
+        p.jchunk            = ((p.jchunk + kTileJ - 1) / kTileJ) * kTileJ;
+        p.jsplit            = (p.n1 + p.jchunk - 1) / p.jchunk;
+        if (int rc = dispatch_rdf<false>(c, a, *g0, *g1, p, smem, dim3(max_tiles, p.jsplit, c->nframes), clamp, cubic)) return rc;
+    }
+    if (p.sym_enabled)
+    {
+        // symmetric mode: work items = per i-tile one diagonal block + chunks of the molecules beyond the tile
+        RdfDev ps  = p;
+        ps.jchunk  = 4 * kTileJ;
+        const int T = (p.n0 + TI - 1) / TI;
+        long long items = 0;
+        for (int t = 0; t < T; ++t) items += 1 + (std::max(0, p.n0 - (t + 1) * TI) + ps.jchunk - 1) / ps.jchunk;
+        if (int rc = dispatch_rdf<true>(c, a, *g0, *g1, ps, smem, dim3((unsigned)items, 1, c->nframes), clamp, cubic)) return rc;
+    }
+    return B2A_OK;
 }
 
 static int accumulate_density(b2a_ctx* c, Acc& a)

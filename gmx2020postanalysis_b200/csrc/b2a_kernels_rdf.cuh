@@ -1,22 +1,27 @@
 // K3: all-pairs minimum-image RDF histogram (reference src/general/calc_rdf_region.cpp:73-95) for sm_100a.
 //
-// Design (measured on B200, see profiles/r01_ubench.md):
-//  * Issue-bound, not HBM- or atomic-bound: every pair costs ~16 issue slots, so the kernel is built to
-//    minimise instructions per pair.
+// Design (measured on B200, see profiles/r01_*.md):
+//  * Issue-bound, not HBM- or atomic-bound: the kernel is built to minimise instructions per pair
+//    (~16 in the hot loop) and to keep the hot loop small enough for the instruction cache.
 //  * Coordinates are 32-bit box fractions (x_fix = rint(x * 2^32/L) mod 2^32, written by K1).  The integer
 //    difference wraps mod 2^32, which IS the minimum image: no floor/round per dimension.
 //  * i-molecules live in registers (IPT per thread), j-molecules are streamed through shared memory and
 //    read as one broadcast LDS.128 per j per warp.
-//  * bin = mantissa of fma(r, scale, 2^23 - 0.5): float->int conversion and floor in the FMA itself.
+//  * bin = mantissa of fma(r, scale, 2^23 - 0.5): float->int conversion and floor inside the FMA.
 //    Two FMAs with scale*(1-eps) and scale*(1+eps) bracket the FP32 error; if they agree the bin is proven
-//    (DESIGN.md "K3 error bound"), otherwise the pair is queued and re-evaluated in FP64 exactly as the
-//    reference does (double periodicity loops, un-fused multiply-adds, IEEE sqrt and divide).  Counts are
-//    therefore bit-exact with no exceptions.
+//    (DESIGN.md "K3 error bound").  Otherwise the (j, thread) pair is queued in shared memory; every
+//    kSubJ j-iterations the block drains the queue: it recomputes the FP32 bins of the queued candidates and
+//    re-evaluates each undecided pair in FP64 exactly as the reference does (double periodicity loops,
+//    un-fused multiply-adds, IEEE sqrt and divide).  Counts are bit-exact with no exceptions.
 //  * The shared histogram covers every reachable bin (r up to the half box diagonal), so the atomic is
 //    unconditional: no range test, no predicate, no divergence.  Bins >= Rbin are simply never flushed.
-//    Queued pairs are counted first (in the low-estimate bin) and CORRECTED by the exact path.
+//    Undecided pairs are counted first (in the low-estimate bin) and CORRECTED by the exact path.
 //  * Slabs (`meZ`) and the region filter depend on i only (calc_rdf_region.cpp:75-77).  A prep pass drops
 //    filtered-out i and groups the rest by slab, so a block sees one slab and needs one histogram.
+//  * SYM: when both groups are the same molecules and every molecule passes the filter into one slab, only
+//    tile pairs with j-tile > i-tile are evaluated and flushed with weight 2 (periodicity(a-b) and
+//    periodicity(b-a) give bit-identical squares because the inequalities in gmx_handle.ipp:412-415 are
+//    strict); diagonal tiles are evaluated in full with weight 1.
 #pragma once
 
 #include <cstdint>
@@ -26,10 +31,10 @@ namespace b2a
 {
 
 constexpr unsigned kMagicBits = 0x4B000000u;   // bits of 2^23 (float)
-constexpr float    kMagic     = 8388607.5f;    // 2^23 - 0.5: fma(r, s, kMagic) rounds to floor-ish(r*s) in the mantissa
-constexpr int      kQueueCap  = 1024;          // exact-path queue entries per block
-constexpr int      kTileJ     = 1024;          // j-molecules staged per shared-memory tile
-constexpr int      kSubJ      = 256;           // j-iterations between queue-drain checks
+constexpr float    kMagic     = 8388607.5f;    // 2^23 - 0.5: fma(r, s, kMagic) rounds to floor(r*s) in the mantissa
+constexpr int      kQueueCap  = 1024;          // (j, thread) candidates per block between drains
+constexpr int      kTileJ     = 512;           // j-molecules staged per shared-memory tile
+constexpr int      kSubJ      = 256;           // j-iterations between queue drains
 
 struct RdfFrame   // per frame (the box may change frame to frame); host-computed
 {
@@ -49,8 +54,8 @@ struct RdfDev
     double   Rm, Rbin_d;
     unsigned rbin_bits;                   // kMagicBits + Rbin
     unsigned kstride;                     // words per shared histogram incl. the leading trash word
-    int      jchunk, jsplit;
-    int      clamp;
+    int      jchunk, jsplit;              // full mode: j range per block; sym mode: jchunk = j per work item
+    int      sym_enabled;                 // host: groups identical and symmetric evaluation requested
 };
 
 // ---- prep: slab id per i, counts per slab -----------------------------------------------------------------
@@ -110,24 +115,105 @@ __device__ __forceinline__ double periodicity_d(double dx, double box)
 }
 
 // returns the reference bin (>= 0), -1 if the pair is not counted, -2 if the reference would write out of bounds
-__device__ __forceinline__ int exact_bin(const double* __restrict__ cA, const double* __restrict__ cB, int n0, int n1,
-                                         int i, int j, const double L[3], const RdfDev& p)
+__device__ __noinline__ int exact_bin(const double* __restrict__ cA, const double* __restrict__ cB, int n0, int n1,
+                                      int i, int j, double L0, double L1, double L2, double rm2, double Rbin_d,
+                                      double Rm, int Rbin)
 {
-    double R = 0.0;
+    const double L[3] = { L0, L1, L2 };
+    double       R    = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {
         const double r = periodicity_d(__dsub_rn(cA[(size_t)k * n0 + i], cB[(size_t)k * n1 + j]), L[k]);
         R              = __dadd_rn(R, __dmul_rn(r, r));
     }
-    if (!(1e-6 < R && R < p.rm2)) return -1;
-    const int meR = __double2int_rz(__ddiv_rn(__dmul_rn(p.Rbin_d, __dsqrt_rn(R)), p.Rm));
-    return (meR >= p.Rbin) ? -2 : meR;
+    if (!(1e-6 < R && R < rm2)) return -1;
+    const int meR = __double2int_rz(__ddiv_rn(__dmul_rn(Rbin_d, __dsqrt_rn(R)), Rm));
+    return (meR >= Rbin) ? -2 : meR;
+}
+
+// ---- FP32 fast path for one pair: identical instruction sequence in the hot loop and in the drain ------------
+template <bool CLAMP, bool CUBIC>
+__device__ __forceinline__ void pair_bins(int xi, int yi, int zi, const int4& pj, float s_lo, float s_hi, float ay,
+                                          float az, float clampf, unsigned& k1, unsigned& k2)
+{
+    float fx = __int2float_rn(xi - pj.x);   // wraps mod 2^32 = minimum image
+    float fy = __int2float_rn(yi - pj.y);
+    float fz = __int2float_rn(zi - pj.z);
+    if (!CUBIC) { fy = __fmul_rn(fy, ay); fz = __fmul_rn(fz, az); }
+    const float r2 = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, __fmul_rn(fx, fx)));
+    float       r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
+    float v1 = __fmaf_rn(r, s_lo, kMagic);
+    float v2 = __fmaf_rn(r, s_hi, kMagic);
+    if (CLAMP) { v1 = fminf(v1, clampf); v2 = fminf(v2, clampf); }
+    k1 = __float_as_uint(v1);
+    k2 = __float_as_uint(v2);
+}
+
+struct RdfBlock   // block-uniform state shared by the hot loop and the cold paths (lives in shared memory)
+{
+    const int4*   A;        // this tile's i-molecules (sorted array + tile start)
+    const int4*   Bsorted;  // SYM: j side indexes the sorted array; full mode: nullptr
+    const double* cA;
+    const double* cB;
+    unsigned*     hist;     // shared histogram, hist[-1] = trash
+    int           tcount, n0, n1, Rbin;
+    unsigned      rbin_bits, lowk_bits;
+    float         s_lo, s_hi, ay, az, clampf;
+    double        L0, L1, L2, rm2, Rbin_d, Rm;
+    unsigned      stats[4];   // exact, moved, dropped, overflow
+};
+
+// Re-examine the IPT pairs (thread t's molecules) x (one j): recompute the FP32 bins, and for every pair the
+// FP32 bracket could not decide run the exact FP64 evaluation and move the count if needed.
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID>
+__device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
+{
+    // phase 1 (converged across the warp): FP32 bins of the thread's IPT pairs, remember the undecided ones
+    unsigned mask = 0;
+    unsigned k1v[IPT];
+#pragma unroll
+    for (int q = 0; q < IPT; ++q)
+    {
+        const int  il = t + q * THREADS;
+        const bool ok = il < b->tcount;
+        const int4 a  = ok ? b->A[il] : make_int4(0, 0, 0, 0);
+        unsigned   k1, k2;
+        pair_bins<CLAMP, CUBIC>(a.x, a.y, a.z, pj, b->s_lo, b->s_hi, b->ay, b->az, b->clampf, k1, k2);
+        const bool amb = ok && (PARANOID || (k1 != k2 && k1 < b->rbin_bits) || k1 <= b->lowk_bits);
+        k1v[q] = k1;
+        mask |= amb ? (1u << q) : 0u;
+    }
+    // phase 2: one exact FP64 evaluation per undecided pair; lanes walk their own masks in lock step
+    const int jorig = b->Bsorted ? b->Bsorted[jglobal].w : jglobal;
+    while (mask)
+    {
+        const int q = __ffs(mask) - 1;
+        mask &= mask - 1;
+        unsigned k1 = 0;
+#pragma unroll
+        for (int u = 0; u < IPT; ++u) k1 = (u == q) ? k1v[u] : k1;
+        const int k1idx = (int)(k1 - kMagicBits);
+        const int iorig = b->A[t + q * THREADS].w;
+        const int ke    = exact_bin(b->cA, b->cB, b->n0, b->n1, iorig, jorig, b->L0, b->L1, b->L2, b->rm2, b->Rbin_d, b->Rm, b->Rbin);
+        atomicAdd(&b->stats[0], 1u);
+        if (ke == -2) atomicAdd(&b->stats[2], 1u);
+        const int target = ke >= 0 ? ke : -1;   // -1 = trash word
+        if (target != k1idx)
+        {
+            atomicSub(&b->hist[k1idx], 1u);
+            atomicAdd(&b->hist[target], 1u);
+            if (k1idx >= 0 && (k1idx < b->Rbin || target >= 0)) atomicAdd(&b->stats[1], 1u);
+        }
+    }
 }
 
 // ---- main kernel ------------------------------------------------------------------------------------------
-// grid: x = i-tile (over slabs), y = j-split, z = frame.  SYM: same group on both sides, i<j tiles only.
-template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID>
+// full mode : grid x = i-tile (over slabs), y = j-split, z = frame
+// SYM mode  : grid x = work item (i-tile, j-chunk beyond the tile | diagonal), z = frame; frames that are not
+//             eligible (not all molecules in one slab) are skipped here and done by the full kernel, and vice versa.
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, bool SYM>
 __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
                                                   const double* __restrict__ cenA, const double* __restrict__ cenB,
                                                   const unsigned* __restrict__ slab_cnt,
@@ -137,15 +223,41 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
 {
     constexpr int TI = IPT * THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int4*               sj    = reinterpret_cast<int4*>(smem_raw);                                    // kTileJ
-    unsigned long long* queue = reinterpret_cast<unsigned long long*>(smem_raw + kTileJ * sizeof(int4)); // kQueueCap
-    unsigned*           hist  = reinterpret_cast<unsigned*>(queue + kQueueCap) + 4;                   // hist[-1] = trash
-    __shared__ unsigned q_count;
-    __shared__ unsigned s_stats[4];   // exact, moved, dropped, overflow
+    int4*     sj    = reinterpret_cast<int4*>(smem_raw);                                   // kTileJ
+    unsigned* queue = reinterpret_cast<unsigned*>(smem_raw + kTileJ * sizeof(int4));       // kQueueCap
+    unsigned* hist  = queue + kQueueCap + 4;                                               // hist[-1] = trash
+    __shared__ unsigned q_count[2];
+    __shared__ RdfBlock blk;
 
     const int f = blockIdx.z;
-    // locate this block's tile: slabs in order, ceil(cnt/TI) tiles each
-    int      slab = -1, tstart = 0, tcount = 0;
+    // is this frame eligible for symmetric evaluation?  (every molecule passed the filter into ONE slab)
+    int sym_slab = -1;
+    if (p.sym_enabled)
+        for (int s = 0; s < p.nslab; ++s)
+            if (slab_cnt[(size_t)f * p.nslab + s] == (unsigned)p.n0) sym_slab = s;
+    if (SYM != (sym_slab >= 0)) return;   // block-uniform
+
+    int slab = -1, tstart = 0, tcount = 0, j0 = 0, j1 = 0, weight = 1;
+    if (SYM)
+    {
+        // work items in order: for tile t = 0..T-1 : [diagonal], then chunks of [(t+1)*TI, n0)
+        const int T = (p.n0 + TI - 1) / TI;
+        int       w = blockIdx.x;
+        for (int t = 0; t < T; ++t)
+        {
+            const int beyond = max(0, p.n0 - (t + 1) * TI);
+            const int nch    = (beyond + p.jchunk - 1) / p.jchunk;
+            if (w < 1 + nch)
+            {
+                slab = sym_slab; tstart = t * TI; tcount = min(TI, p.n0 - tstart);
+                if (w == 0) { j0 = tstart; j1 = tstart + tcount; weight = 1; }
+                else { j0 = (t + 1) * TI + (w - 1) * p.jchunk; j1 = min(p.n0, j0 + p.jchunk); weight = 2; }
+                break;
+            }
+            w -= 1 + nch;
+        }
+    }
+    else
     {
         int      t   = blockIdx.x;
         unsigned off = 0;
@@ -157,124 +269,127 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
             t -= nt;
             off += c;
         }
+        j0 = blockIdx.y * p.jchunk;
+        j1 = min(p.n1, j0 + p.jchunk);
     }
-    if (slab < 0) return;   // block-uniform
+    if (slab < 0 || j1 <= j0) return;   // block-uniform
 
+    const RdfFrame fr = frames[f];
+    const int4*    A  = sortedA + (size_t)f * p.n0 + tstart;
+    const int4*    B  = SYM ? sortedA + (size_t)f * p.n0 : fixB + (size_t)f * p.n1;
     for (unsigned k = threadIdx.x; k < p.kstride; k += THREADS) hist[(int)k - 1] = 0;
-    if (threadIdx.x == 0) q_count = 0;
-    if (threadIdx.x < 4) s_stats[threadIdx.x] = 0;
+    if (threadIdx.x == 0)
+    {
+        q_count[0] = q_count[1] = 0;
+        blk.A = A; blk.Bsorted = SYM ? B : nullptr;
+        blk.cA = cenA + (size_t)f * 3 * p.n0;
+        blk.cB = cenB + (size_t)f * 3 * p.n1;
+        blk.hist = hist; blk.tcount = tcount; blk.n0 = p.n0; blk.n1 = p.n1; blk.Rbin = p.Rbin;
+        blk.rbin_bits = p.rbin_bits; blk.lowk_bits = fr.lowk_bits;
+        blk.s_lo = fr.s_lo; blk.s_hi = fr.s_hi; blk.ay = fr.ay; blk.az = fr.az;
+        blk.clampf = __uint_as_float(p.rbin_bits);
+        blk.L0 = fr.L[0]; blk.L1 = fr.L[1]; blk.L2 = fr.L[2];
+        blk.rm2 = p.rm2; blk.Rbin_d = p.Rbin_d; blk.Rm = p.Rm;
+        blk.stats[0] = blk.stats[1] = blk.stats[2] = blk.stats[3] = 0;
+    }
 
-    const RdfFrame fr   = frames[f];
-    const int4*    A    = sortedA + (size_t)f * p.n0 + tstart;
-    const int4*    B    = fixB + (size_t)f * p.n1;
-    const double*  cA   = cenA + (size_t)f * 3 * p.n0;
-    const double*  cB   = cenB + (size_t)f * 3 * p.n1;
     const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
+    const unsigned cb_ok   = hist_sa - kMagicBits * 4u;
+    const float    clampf  = __uint_as_float(p.rbin_bits);
+    const float    s_lo = fr.s_lo, s_hi = fr.s_hi, ay = fr.ay, az = fr.az;
+    const unsigned lowk = fr.lowk_bits;
+    const bool     partial = tcount < TI;
 
-    int      xi[IPT], yi[IPT], zi[IPT];
-    unsigned mulq[IPT], cbq[IPT];
+    int xi[IPT], yi[IPT], zi[IPT];
 #pragma unroll
     for (int q = 0; q < IPT; ++q)
     {
         const int  il = threadIdx.x + q * THREADS;
-        const bool ok = il < tcount;
-        const int4 a  = ok ? A[il] : make_int4(0, 0, 0, 0);
+        const int4 a  = il < tcount ? A[il] : make_int4(0, 0, 0, 0);
         xi[q] = a.x; yi[q] = a.y; zi[q] = a.z;
-        mulq[q] = ok ? 4u : 0u;                                         // padding lanes hit the trash word only
-        cbq[q]  = ok ? (hist_sa - kMagicBits * 4u) : (hist_sa - 4u);
     }
 
-    const float clampf = __uint_as_float(p.rbin_bits);   // 2^23 + Rbin
-
-    // exact re-evaluation + correction of one queued pair (counted earlier in bin k1idx)
-    auto fix_pair = [&](int il, int j, int k1idx) {
-        const int i  = A[il].w;
-        const int ke = exact_bin(cA, cB, p.n0, p.n1, i, j, fr.L, p);
-        atomicAdd(&s_stats[0], 1u);
-        if (ke == -2) atomicAdd(&s_stats[2], 1u);
-        const int target = ke >= 0 ? ke : -1;          // -1 = trash
-        if (target != k1idx)
-        {
-            atomicSub(&hist[k1idx], 1u);
-            atomicAdd(&hist[target], 1u);
-            if (k1idx >= 0 && (k1idx < p.Rbin || target >= 0)) atomicAdd(&s_stats[1], 1u);
-        }
-    };
-
-    const int j0 = blockIdx.y * p.jchunk;
-    const int j1 = min(p.n1, j0 + p.jchunk);
+    int sub = 0;   // sub-tile counter: selects the ping-pong queue counter
     for (int jt = j0; jt < j1; jt += kTileJ)
     {
         __syncthreads();
         const int cnt = min(kTileJ, j1 - jt);
         for (int t = threadIdx.x; t < cnt; t += THREADS) sj[t] = B[jt + t];
         __syncthreads();
-        for (int js = 0; js < cnt; js += kSubJ)
+        for (int js = 0; js < cnt; js += kSubJ, ++sub)
         {
             const int je = min(cnt, js + kSubJ);
-#pragma unroll 2
-            for (int j = js; j < je; ++j)
+            unsigned* qc = &q_count[sub & 1];
+            if (!partial)
             {
-                const int4 pj = sj[j];
-                unsigned   k1[IPT], k2[IPT];
-                unsigned   dacc = 0, kmin = 0xffffffffu;
-#pragma unroll
-                for (int q = 0; q < IPT; ++q)
+#pragma unroll 2
+                for (int j = js; j < je; ++j)
                 {
-                    float fx = (float)(xi[q] - pj.x);   // wraps mod 2^32 = minimum image
-                    float fy = (float)(yi[q] - pj.y);
-                    float fz = (float)(zi[q] - pj.z);
-                    if (!CUBIC) { fy *= fr.ay; fz *= fr.az; }
-                    const float r2 = fmaf(fz, fz, fmaf(fy, fy, fx * fx));
-                    float       r;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
-                    float v1 = fmaf(r, fr.s_lo, kMagic);
-                    float v2 = fmaf(r, fr.s_hi, kMagic);
-                    if (CLAMP) { v1 = fminf(v1, clampf); v2 = fminf(v2, clampf); }
-                    k1[q] = __float_as_uint(v1);
-                    k2[q] = __float_as_uint(v2);
-                    unsigned addr;
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(addr) : "r"(k1[q]), "r"(mulq[q]), "r"(cbq[q]));
-                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-                    dacc += k2[q] - k1[q];
-                    kmin = min(kmin, k1[q]);
-                }
-                if (PARANOID || dacc != 0 || kmin <= fr.lowk_bits)
-                {
+                    const int4 pj   = sj[j];
+                    unsigned   dacc = 0, kmin = 0xffffffffu;
 #pragma unroll
                     for (int q = 0; q < IPT; ++q)
                     {
-                        if (mulq[q] == 0) continue;
-                        const bool amb = PARANOID || (k1[q] != k2[q] && k1[q] < p.rbin_bits) || k1[q] <= fr.lowk_bits;
-                        if (!amb) continue;
-                        const int      k1idx = (int)(k1[q] - kMagicBits);
-                        const unsigned il    = threadIdx.x + q * THREADS;
-                        const unsigned slot  = atomicAdd(&q_count, 1u);
-                        if (slot < (unsigned)kQueueCap)
-                            queue[slot] = ((unsigned long long)(unsigned)(jt + j) << 32) | ((unsigned long long)(unsigned)(k1idx + 1) << 12) | il;
+                        unsigned k1, k2;
+                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, clampf, k1, k2);
+                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1 * 4u + cb_ok) : "memory");
+                        dacc += k2 - k1;
+                        kmin = min(kmin, k1);
+                    }
+                    if (PARANOID || dacc != 0 || kmin <= lowk)
+                    {
+                        const unsigned slot = atomicAdd(qc, 1u);
+                        if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
                         else
                         {
-                            fix_pair((int)il, jt + j, k1idx);
-                            atomicAdd(&s_stats[3], 1u);
+                            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
+                            atomicAdd(&blk.stats[3], 1u);
                         }
                     }
                 }
             }
-            // drain the exact queue when it is at least half full, and after the last j.  Threads sample q_count
-            // at different times, so the decision is made block-uniform by the barrier's OR-reduction.
-            const bool last = (je == cnt) && (jt + kTileJ >= j1);
-            if (__syncthreads_or(last || q_count >= (unsigned)(kQueueCap / 2)))
+            else
             {
-                const unsigned n = min(q_count, (unsigned)kQueueCap);   // stable: every thread is past its pushes
-                for (unsigned e = threadIdx.x; e < n; e += THREADS)
+                // last tile of a slab: lanes beyond tcount add into the trash word only
+#pragma unroll 1
+                for (int j = js; j < je; ++j)
                 {
-                    const unsigned long long ent = queue[e];
-                    fix_pair((int)(ent & 0xfffu), (int)(ent >> 32), (int)((ent >> 12) & 0xfffffu) - 1);
+                    const int4 pj   = sj[j];
+                    unsigned   dacc = 0, kmin = 0xffffffffu;
+#pragma unroll
+                    for (int q = 0; q < IPT; ++q)
+                    {
+                        const bool ok = (int)(threadIdx.x + q * THREADS) < tcount;
+                        unsigned   k1, k2;
+                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, clampf, k1, k2);
+                        const unsigned addr = ok ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
+                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                        dacc += ok ? (k2 - k1) : 0u;
+                        kmin = ok ? min(kmin, k1) : kmin;
+                    }
+                    if (PARANOID || dacc != 0 || kmin <= lowk)
+                    {
+                        const unsigned slot = atomicAdd(qc, 1u);
+                        if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
+                        else
+                        {
+                            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
+                            atomicAdd(&blk.stats[3], 1u);
+                        }
+                    }
                 }
-                __syncthreads();
-                if (threadIdx.x == 0) q_count = 0;
-                __syncthreads();
             }
+            // drain: every queued (j, thread) candidate is re-examined by whichever thread picks it up
+            __syncthreads();
+            const unsigned n = min(*qc, (unsigned)kQueueCap);
+            for (unsigned e = threadIdx.x; e < n; e += THREADS)
+            {
+                const unsigned ent = queue[e];
+                const int      jl  = (int)(ent >> 16);
+                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, (int)(ent & 0xffffu), sj[jl], jt + jl);
+            }
+            if (threadIdx.x == 0) q_count[(sub + 1) & 1] = 0;   // the other counter was drained one sub-tile ago
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -282,16 +397,16 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
     for (int k = threadIdx.x; k < p.Rbin; k += THREADS)
     {
         const unsigned v = hist[k];
-        if (v) atomicAdd(&gh[k], (unsigned long long)v);
+        if (v) atomicAdd(&gh[k], (unsigned long long)v * (unsigned long long)weight);
     }
     if (threadIdx.x == 0)
     {
-        if (s_stats[0]) atomicAdd(&gstats[2], (unsigned long long)s_stats[0]);
-        if (s_stats[1]) atomicAdd(&gstats[3], (unsigned long long)s_stats[1]);
-        if (s_stats[2]) atomicAdd(&gstats[1], (unsigned long long)s_stats[2]);
-        if (s_stats[3]) atomicAdd(&gstats[6], (unsigned long long)s_stats[3]);
-        atomicAdd(&gstats[5], (unsigned long long)tcount * (unsigned long long)(j1 > j0 ? j1 - j0 : 0));
-        if (blockIdx.y == 0) atomicAdd(&gstats[4], (unsigned long long)tcount);
+        if (blk.stats[0]) atomicAdd(&gstats[2], (unsigned long long)blk.stats[0]);
+        if (blk.stats[1]) atomicAdd(&gstats[3], (unsigned long long)blk.stats[1] * (unsigned long long)weight);
+        if (blk.stats[2]) atomicAdd(&gstats[1], (unsigned long long)blk.stats[2] * (unsigned long long)weight);
+        if (blk.stats[3]) atomicAdd(&gstats[6], (unsigned long long)blk.stats[3]);
+        atomicAdd(&gstats[5], (unsigned long long)tcount * (unsigned long long)(j1 - j0));
+        if (SYM ? (weight == 1) : (blockIdx.y == 0)) atomicAdd(&gstats[4], (unsigned long long)tcount);
     }
 }
 
