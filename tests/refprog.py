@@ -28,7 +28,8 @@ def run_program(exe, workdir, system, nframes, group_names, args, out_name, stdi
     out = os.path.join(workdir, out_name)
     cmd = [exe, "-f", trj, "-s", top, "-n", ndx, "-o", out] + [str(a) for a in args]
     env = dict(os.environ)
-    env["LD_LIBRARY_PATH"] = os.path.join(ROOT, "build") + ":" + env.get("LD_LIBRARY_PATH", "")
+    env["LD_LIBRARY_PATH"] = (os.path.join(ROOT, "build") + ":" + os.path.join(ROOT, "gmx2020postanalysis_b200") + ":"
+                              + env.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run(cmd, input=sel, capture_output=True, text=True, env=env, cwd=workdir)
     if r.returncode != 0:
         raise RuntimeError(f"{exe} failed rc={r.returncode}\n{r.stdout[-2000:]}\n{r.stderr[-2000:]}")
