@@ -538,8 +538,12 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         const double delta_bins = std::sqrt(3.0) * 1.0001 * sc * std::max(1.0, std::max((double)fr.ay, (double)fr.az));
         const unsigned lowk     = (unsigned)std::ceil(delta_bins / (eps - eps_true)) + 2;
         fr.lowk_bits = kMagicBits + lowk;
-        fr.pad = 0;
         for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
+        // r2max: r with bin coordinate Rbin + 0.5 -- both bracket bins are exactly Rbin for any eps < 1e-4
+        {
+            const double r_units = ((double)s.Rbin + 0.5) / sc;
+            fr.r2max = (float)(r_units * r_units);
+        }
         const double rmax_units = 2147483648.0 * std::sqrt(1.0 + (double)fr.ay * fr.ay + (double)fr.az * fr.az) * 1.000001;
         tmax = std::max(tmax, rmax_units * (double)hi);
     }
@@ -563,9 +567,9 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     {
         Timed tm(c, 1);
         dim3 grid((p.n0 + 255) / 256, c->nframes);
-        k3_slab_count<<<grid, 256, 0, c->stream>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
+        k3_slab_count<<<grid, 256, sizeof(unsigned) * nslab, c->stream>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
         CU(cudaGetLastError());
-        k3_slab_scatter<<<grid, 256, sizeof(unsigned) * nslab, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
+        k3_slab_scatter<<<grid, 256, sizeof(unsigned) * 3 * nslab, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
                                                                          a.d_slab_cnt, a.d_slab_cnt + (size_t)nslab * c->maxK, a.d_sortedA);
         CU(cudaGetLastError());
     }

@@ -40,8 +40,8 @@ struct RdfFrame   // per frame (the box may change frame to frame); host-compute
 {
     float    s_lo, s_hi;   // bins per x-fixed-unit, times (1-eps) rounded down / (1+eps) rounded up
     float    ay, az;       // Ly/Lx, Lz/Lx (exactly 1 when cubic)
+    float    r2max;        // CLAMP: squared distance (x fixed units) whose bracket bins are both Rbin
     unsigned lowk_bits;    // kMagicBits + LOWK: bins below LOWK are always re-evaluated (absolute error term)
-    unsigned pad;
     double   L[3];
 };
 
@@ -59,24 +59,35 @@ struct RdfDev
 };
 
 // ---- prep: slab id per i, counts per slab -----------------------------------------------------------------
+// Counters are aggregated per block in shared memory first: with the program defaults every molecule of a frame
+// lands in the same slab, and 72 000 global atomics on one address cost 0.35 ms (measured, profiles/r01_k3_tuning.md).
 __global__ void __launch_bounds__(256) k3_slab_count(const double* __restrict__ cenA, int nframes, RdfDev p,
                                                      int* __restrict__ slab_id, unsigned* __restrict__ slab_cnt)
 {
+    extern __shared__ unsigned scnt[];
     const int f = blockIdx.y;
+    for (int s = threadIdx.x; s < p.nslab; s += blockDim.x) scnt[s] = 0;
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n0 || f >= nframes) return;
-    const double* c   = cenA + (size_t)f * 3 * p.n0;
-    const double  pd  = c[(size_t)p.dim * p.n0 + i];
-    const double  pd2 = c[(size_t)p.dim2 * p.n0 + i];
-    int           s   = -1;
-    if (p.low < pd && pd < p.up && p.low2 < pd2 && pd2 < p.up2)   // strict, :75
+    if (i < p.n0 && f < nframes)
     {
-        // meZ = nbin * (posc - lowPos) / (upPos - lowPos), left to right in double, truncation (:77)
-        const int meZ = __double2int_rz(__ddiv_rn(__dmul_rn((double)p.nbin, __dsub_rn(pd, p.low)), p.width));
-        s             = (meZ < 0 || meZ >= p.nbin) ? p.nbin : meZ;
+        const double* c   = cenA + (size_t)f * 3 * p.n0;
+        const double  pd  = c[(size_t)p.dim * p.n0 + i];
+        const double  pd2 = c[(size_t)p.dim2 * p.n0 + i];
+        int           s   = -1;
+        if (p.low < pd && pd < p.up && p.low2 < pd2 && pd2 < p.up2)   // strict, :75
+        {
+            // meZ = nbin * (posc - lowPos) / (upPos - lowPos), left to right in double, truncation (:77)
+            const int meZ = __double2int_rz(__ddiv_rn(__dmul_rn((double)p.nbin, __dsub_rn(pd, p.low)), p.width));
+            s             = (meZ < 0 || meZ >= p.nbin) ? p.nbin : meZ;
+        }
+        slab_id[(size_t)f * p.n0 + i] = s;
+        if (s >= 0) atomicAdd(&scnt[s], 1u);
     }
-    slab_id[(size_t)f * p.n0 + i] = s;
-    if (s >= 0) atomicAdd(&slab_cnt[(size_t)f * p.nslab + s], 1u);
+    __syncthreads();
+    if (f < nframes)
+        for (int s = threadIdx.x; s < p.nslab; s += blockDim.x)
+            if (scnt[s]) atomicAdd(&slab_cnt[(size_t)f * p.nslab + s], scnt[s]);
 }
 
 // scatter: sortedA[f][off[slab] + k] = {fix.xyz, i}; order inside a slab is arbitrary (integer sums commute)
@@ -85,9 +96,13 @@ __global__ void __launch_bounds__(256) k3_slab_scatter(const int4* __restrict__ 
                                                        const unsigned* __restrict__ slab_cnt,
                                                        unsigned* __restrict__ cursor, int4* __restrict__ sortedA)
 {
-    extern __shared__ unsigned soff[];
+    extern __shared__ unsigned ssm[];
+    unsigned* soff  = ssm;               // slab start in the sorted array
+    unsigned* lcnt  = ssm + nslab;       // this block's count per slab
+    unsigned* lbase = ssm + 2 * nslab;   // this block's reserved range per slab
     const int f = blockIdx.y;
     if (f >= nframes) return;
+    for (int s = threadIdx.x; s < nslab; s += blockDim.x) lcnt[s] = 0;
     if (threadIdx.x == 0)
     {
         unsigned acc = 0;
@@ -95,13 +110,21 @@ __global__ void __launch_bounds__(256) k3_slab_scatter(const int4* __restrict__ 
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n0) return;
-    const int s = slab_id[(size_t)f * n0 + i];
+    int       s = -1;
+    unsigned  rank = 0;
+    if (i < n0)
+    {
+        s = slab_id[(size_t)f * n0 + i];
+        if (s >= 0) rank = atomicAdd(&lcnt[s], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nslab; t += blockDim.x)
+        if (lcnt[t]) lbase[t] = soff[t] + atomicAdd(&cursor[(size_t)f * nslab + t], lcnt[t]);
+    __syncthreads();
     if (s < 0) return;
-    const unsigned pos = soff[s] + atomicAdd(&cursor[(size_t)f * nslab + s], 1u);
-    int4           v   = fixA[(size_t)f * n0 + i];
-    v.w                = i;
-    sortedA[(size_t)f * n0 + pos] = v;
+    int4 v = fixA[(size_t)f * n0 + i];
+    v.w    = i;
+    sortedA[(size_t)f * n0 + lbase[s] + rank] = v;
 }
 
 // ---- exact FP64 evaluation of one pair, operation for operation as calc_rdf_region.cpp:81-92 -----------------
@@ -135,20 +158,20 @@ __device__ __noinline__ int exact_bin(const double* __restrict__ cA, const doubl
 // ---- FP32 fast path for one pair: identical instruction sequence in the hot loop and in the drain ------------
 template <bool CLAMP, bool CUBIC>
 __device__ __forceinline__ void pair_bins(int xi, int yi, int zi, const int4& pj, float s_lo, float s_hi, float ay,
-                                          float az, float clampf, unsigned& k1, unsigned& k2)
+                                          float az, float r2max, unsigned& k1, unsigned& k2)
 {
     float fx = __int2float_rn(xi - pj.x);   // wraps mod 2^32 = minimum image
     float fy = __int2float_rn(yi - pj.y);
     float fz = __int2float_rn(zi - pj.z);
     if (!CUBIC) { fy = __fmul_rn(fy, ay); fz = __fmul_rn(fz, az); }
-    const float r2 = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, __fmul_rn(fx, fx)));
-    float       r;
+    float r2 = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, __fmul_rn(fx, fx)));
+    // CLAMP: every pair beyond the cut-off collapses onto r2max, chosen by the host so that both bracket bins of
+    // sqrt(r2max) equal Rbin (the trash bin): one FMNMX, one shared address for ~half of the lanes, never undecided
+    if (CLAMP) r2 = fminf(r2, r2max);
+    float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
-    float v1 = __fmaf_rn(r, s_lo, kMagic);
-    float v2 = __fmaf_rn(r, s_hi, kMagic);
-    if (CLAMP) { v1 = fminf(v1, clampf); v2 = fminf(v2, clampf); }
-    k1 = __float_as_uint(v1);
-    k2 = __float_as_uint(v2);
+    k1 = __float_as_uint(__fmaf_rn(r, s_lo, kMagic));
+    k2 = __float_as_uint(__fmaf_rn(r, s_hi, kMagic));
 }
 
 struct RdfBlock   // block-uniform state shared by the hot loop and the cold paths (lives in shared memory)
@@ -160,7 +183,7 @@ struct RdfBlock   // block-uniform state shared by the hot loop and the cold pat
     unsigned*     hist;     // shared histogram, hist[-1] = trash
     int           tcount, n0, n1, Rbin;
     unsigned      rbin_bits, lowk_bits;
-    float         s_lo, s_hi, ay, az, clampf;
+    float         s_lo, s_hi, ay, az, r2max;
     double        L0, L1, L2, rm2, Rbin_d, Rm;
     unsigned      stats[4];   // exact, moved, dropped, overflow
 };
@@ -180,7 +203,7 @@ __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
         const bool ok = il < b->tcount;
         const int4 a  = ok ? b->A[il] : make_int4(0, 0, 0, 0);
         unsigned   k1, k2;
-        pair_bins<CLAMP, CUBIC>(a.x, a.y, a.z, pj, b->s_lo, b->s_hi, b->ay, b->az, b->clampf, k1, k2);
+        pair_bins<CLAMP, CUBIC>(a.x, a.y, a.z, pj, b->s_lo, b->s_hi, b->ay, b->az, b->r2max, k1, k2);
         const bool amb = ok && (PARANOID || (k1 != k2 && k1 < b->rbin_bits) || k1 <= b->lowk_bits);
         k1v[q] = k1;
         mask |= amb ? (1u << q) : 0u;
@@ -287,7 +310,7 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
         blk.hist = hist; blk.tcount = tcount; blk.n0 = p.n0; blk.n1 = p.n1; blk.Rbin = p.Rbin;
         blk.rbin_bits = p.rbin_bits; blk.lowk_bits = fr.lowk_bits;
         blk.s_lo = fr.s_lo; blk.s_hi = fr.s_hi; blk.ay = fr.ay; blk.az = fr.az;
-        blk.clampf = __uint_as_float(p.rbin_bits);
+        blk.r2max = fr.r2max;
         blk.L0 = fr.L[0]; blk.L1 = fr.L[1]; blk.L2 = fr.L[2];
         blk.rm2 = p.rm2; blk.Rbin_d = p.Rbin_d; blk.Rm = p.Rm;
         blk.stats[0] = blk.stats[1] = blk.stats[2] = blk.stats[3] = 0;
@@ -295,7 +318,7 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
 
     const unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist);
     const unsigned cb_ok   = hist_sa - kMagicBits * 4u;
-    const float    clampf  = __uint_as_float(p.rbin_bits);
+    const float    r2max   = fr.r2max;
     const float    s_lo = fr.s_lo, s_hi = fr.s_hi, ay = fr.ay, az = fr.az;
     const unsigned lowk = fr.lowk_bits;
     const bool     partial = tcount < TI;
@@ -331,7 +354,7 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
                     for (int q = 0; q < IPT; ++q)
                     {
                         unsigned k1, k2;
-                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, clampf, k1, k2);
+                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
                         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1 * 4u + cb_ok) : "memory");
                         dacc += k2 - k1;
                         kmin = min(kmin, k1);
@@ -361,7 +384,7 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
                     {
                         const bool ok = (int)(threadIdx.x + q * THREADS) < tcount;
                         unsigned   k1, k2;
-                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, clampf, k1, k2);
+                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
                         const unsigned addr = ok ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
                         asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
                         dacc += ok ? (k2 - k1) : 0u;
