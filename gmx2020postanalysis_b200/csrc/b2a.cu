@@ -2,9 +2,8 @@
 // b2a_create fails with B2A_ERR_CUDA.
 #include "b2a.h"
 
-#include "b2a_kernels_center.cuh"
-#include "b2a_kernels_orient.cuh"
 #include "b2a_kernels_rdf.cuh"
+#include "b2a_kernels_stream.cuh"   // pulls in the centre / orientation kernels
 
 #include <algorithm>
 #include <cmath>
@@ -43,6 +42,20 @@ int fail(int code, const char* fmt, ...)
 // Sum in the order Eigen 3.3.9's vectorised Array<double>::sum() uses on SSE2 (two packet accumulators of
 // two doubles, then the scalar tail) -- this is what `atomCenter.sum()` evaluates in the reference
 // (include/itp/gmx_bits/gmx_handle.ipp:195), and for napm > 3 it differs from a sequential sum in the last bit.
+// host side of div_const (b2a_kernels_center.cuh): y = RN(1/d); the fast path needs d and y normal, and Markstein's
+// theorem excludes divisors whose significand is all ones
+DivConst make_div(double d)
+{
+    DivConst c{};
+    c.d   = d;
+    c.inv = 1.0 / d;
+    uint64_t bits;
+    std::memcpy(&bits, &d, sizeof(bits));
+    const bool all_ones = (bits & 0xFFFFFFFFFFFFFull) == 0xFFFFFFFFFFFFFull;
+    c.fast = (std::isnormal(d) && std::isnormal(c.inv) && !all_ones) ? 1 : 0;
+    return c;
+}
+
 double eigen_order_sum(const double* w, int n)
 {
     const int a2 = (n / 4) * 4, a1 = (n / 2) * 2;
@@ -70,6 +83,7 @@ struct Group
     int     ngx = 0, napm = 0, nmol = 0;
     int*    d_index = nullptr;
     std::vector<int> h_index;
+    bool    contiguous = false;   // index[n] == index[0] + n: a block's molecules are one byte range per frame (TMA path)
     double* d_w[4]  = { nullptr, nullptr, nullptr, nullptr };   // mass, ones, charge, charge(dipole)
     double  wsum[4] = { 0, 0, 0, 0 };
     // centre cache per com for the current batch
@@ -174,7 +188,7 @@ extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
     c->maxK   = max_frames;
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&c->d_x, (size_t)natoms * 3 * sizeof(float) * max_frames));
+    CU(cudaMalloc(&c->d_x, (size_t)natoms * 3 * sizeof(float) * max_frames + 64));   // +64: bulk copies are widened to 16-byte boundaries
     CU(cudaMalloc(&c->d_geom, sizeof(FrameGeom) * max_frames));
     CU(cudaMallocHost(&c->h_geom, sizeof(FrameGeom) * max_frames));
     c->h_box.assign((size_t)max_frames * 9, 0.f);
@@ -248,6 +262,8 @@ extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int
     free_group(g);
     g.ngx = ngx; g.napm = napm; g.nmol = nmol;
     g.h_index.assign(index, index + ngx);
+    g.contiguous = true;
+    for (int n = 1; n < ngx && g.contiguous; ++n) g.contiguous = (index[n] == index[0] + n);
     CU(cudaMalloc(&g.d_index, sizeof(int) * ngx));
     CU(cudaMemcpy(g.d_index, index, sizeof(int) * ngx, cudaMemcpyHostToDevice));
     std::vector<double> ones(napm, 1.0);
@@ -309,6 +325,7 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
             g.L[k]        = (double)bk;            // ipp:72-74
             g.half[k]     = g.L[k] / 2;            // ipp:128
             g.inv_unit[k] = 4294967296.0 / g.L[k];
+            g.hsafe[k]    = (float)(g.half[k] * (1.0 - 1e-6));
         }
     }
     std::memcpy(c->h_box.data(), box9, sizeof(float) * 9 * (size_t)nframes);
@@ -324,6 +341,38 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
 
 extern "C" int b2a_batch_frames(b2a_ctx* c) { return c ? c->nframes : -1; }
 
+// ---- TMA-staged streaming launch (contiguous groups) -----------------------------------------------------------
+static bool stream_block(const Group& g, int* M)
+{
+    if (!g.contiguous) return false;
+    if (const char* e = getenv("B2A_NO_TMA")) if (atoi(e)) return false;
+    int m = (32768 / (g.napm * 12) / 32) * 32;   // <= 32 KB of coordinates per stage
+    m     = std::min(m, 256);
+    if (m < 32) return false;
+    *M = m;
+    return true;
+}
+
+template <int MODE>
+static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem)
+{
+    a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;
+    a.atom0 = g.h_index[0]; a.nmol = g.nmol; a.napm = g.napm;
+    a.w = g.d_w[com]; a.wsum = make_div(g.wsum[com]); a.geom = c->d_geom;
+    a.tile_floats = ((M * g.napm * 3 + 8) + 3) & ~3;
+    // frames per block: deep enough to pipeline, small enough to fill the machine
+    const int mblocks = (g.nmol + M - 1) / M;
+    int fpb = 16;
+    while (fpb > 4 && (long long)mblocks * ((c->nframes + fpb - 1) / fpb) < 4LL * c->sm_count) fpb /= 2;
+    a.frames_per_block = fpb;
+    const size_t smem = (size_t)kStages * a.tile_floats * 4 + kStages * 8 + sizeof(FrameGeom) * fpb + sizeof(double) * g.napm + extra_smem;
+    CU(cudaFuncSetAttribute(k_stream<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(mblocks, (c->nframes + fpb - 1) / fpb);
+    k_stream<MODE><<<grid, M, smem, c->stream>>>(a);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
 // ---- K1 launch + cache -----------------------------------------------------------------------------------------
 static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
 {
@@ -333,11 +382,20 @@ static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
     if (!g.d_fix[com]) CU(cudaMalloc(&g.d_fix[com], sizeof(int4) * (size_t)g.nmol * c->maxK));
     (void)need_fix;
     if (g.valid[com] == c->serial) return B2A_OK;
+    Timed tm(c, 0);
+    int   M = 0;
+    if (stream_block(g, &M))
+    {
+        StreamArgs a{};
+        a.cen = g.d_cen[com]; a.fix = g.d_fix[com];
+        if (int rc = launch_stream<0>(c, g, com, M, a, 0)) return rc;
+        g.valid[com] = c->serial;
+        return B2A_OK;
+    }
     const int threads = 128;
     dim3      grid((g.nmol + threads - 1) / threads, c->nframes);
-    Timed     tm(c, 0);
-    k1_centers<4><<<grid, threads, sizeof(double) * g.napm, c->stream>>>(
-        c->d_x, (size_t)c->natoms * 3, c->nframes, g.d_index, g.nmol, g.napm, g.d_w[com], g.wsum[com], c->d_geom,
+    k1_centers<<<grid, threads, sizeof(double) * g.napm, c->stream>>>(
+        c->d_x, (size_t)c->natoms * 3, c->nframes, g.d_index, g.nmol, g.napm, g.d_w[com], make_div(g.wsum[com]), c->d_geom,
         g.d_cen[com], g.d_fix[com]);
     CU(cudaGetLastError());
     g.valid[com] = c->serial;
@@ -610,16 +668,23 @@ static int accumulate_density(b2a_ctx* c, Acc& a)
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
     DensityDev d{};
     d.dim = s.dim; d.dim2 = s.dim2; d.nbin = s.nbin; d.upper_inclusive = s.upper_inclusive;
-    d.low = (double)s.low; d.up = (double)s.up; d.low2 = (double)s.low2; d.up2 = (double)s.up2; d.dbin = s.dbin;
+    d.low = (double)s.low; d.up = (double)s.up; d.low2 = (double)s.low2; d.up2 = (double)s.up2; d.dbin = make_div(s.dbin);
     const int    threads   = 256;
-    const int    smem_bins = s.nbin <= 40000 ? s.nbin : 0;
+    const int    smem_bins = s.nbin <= 24000 ? s.nbin : 0;
+    int          M = 0;
+    if (stream_block(*g, &M))
+    {
+        Timed      tm(c, 3);
+        StreamArgs sa{};
+        sa.den = d; sa.hist = a.d_hist; sa.stats = a.d_hist + a.ndev; sa.smem_bins = smem_bins;
+        return launch_stream<1>(c, *g, s.com, M, sa, sizeof(unsigned) * smem_bins);
+    }
     const size_t smem      = sizeof(double) * g->napm + sizeof(unsigned) * smem_bins;
     CU(cudaFuncSetAttribute(k2_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long total  = (long long)g->nmol * c->nframes;
-    const int       blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)c->sm_count * 8);
-    Timed           tm(c, 3);
+    const dim3 blocks((g->nmol + threads - 1) / threads, (c->nframes + kFramesPerBlock - 1) / kFramesPerBlock);
+    Timed      tm(c, 3);
     k2_density<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->nmol, g->napm,
-                                                     g->d_w[s.com], g->wsum[s.com], c->d_geom, d, a.d_hist, a.d_hist + a.ndev, smem_bins);
+                                                     g->d_w[s.com], make_div(g->wsum[s.com]), c->d_geom, d, a.d_hist, a.d_hist + a.ndev, smem_bins);
     CU(cudaGetLastError());
     return B2A_OK;
 }
@@ -820,17 +885,24 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
     d.DIMN = s.DIMN; d.nAngle = s.nAngle; d.nbin1 = a.nbin1; d.tp1 = s.tp1 - 1; d.tp2 = s.tp2 - 1; d.tp3 = s.tp3 - 1;
     d.DIMNOrient = s.DIMNOrient; d.method = s.method;
     d.low = (double)s.low; d.up = (double)s.up; d.c1 = (double)s.c1; d.c2 = (double)s.c2;
-    d.dr = (double)s.dr; d.CR = (double)s.CR; d.Cr = (double)s.Cr;
+    d.dr = make_div((double)s.dr); d.CR = (double)s.CR; d.Cr = (double)s.Cr;
     const int    threads = 256;
     const size_t hist_words = (size_t)a.nbin1 * s.nAngle + a.nbin1;
-    const int    smem_bins  = hist_words <= 40000 ? (int)hist_words : 0;
+    const int    smem_bins  = hist_words <= 24000 ? (int)hist_words : 0;
+    int          M = 0;
+    if (stream_block(*g, &M))
+    {
+        Timed      tm(c, 4);
+        StreamArgs sa{};
+        sa.ori = d; sa.cosedge = a.d_cosedge; sa.hist = a.d_hist; sa.stats = a.d_hist + a.ndev; sa.smem_bins = smem_bins;
+        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1) + sizeof(unsigned) * smem_bins);
+    }
     const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1) + sizeof(unsigned) * smem_bins;
     CU(cudaFuncSetAttribute(k4_orient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long total  = (long long)g->nmol * c->nframes;
-    const int       blocks = (int)std::min<long long>((total + threads - 1) / threads, (long long)c->sm_count * 8);
-    Timed           tm(c, 4);
+    const dim3 blocks((g->nmol + threads - 1) / threads, (c->nframes + kFramesPerBlock - 1) / kFramesPerBlock);
+    Timed      tm(c, 4);
     k4_orient<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->nmol, g->napm,
-                                                    g->d_w[s.com], g->wsum[s.com], c->d_geom, d, a.d_cosedge, a.d_hist,
+                                                    g->d_w[s.com], make_div(g->wsum[s.com]), c->d_geom, d, a.d_cosedge, a.d_hist,
                                                     a.d_hist + a.ndev, smem_bins);
     CU(cudaGetLastError());
     return B2A_OK;

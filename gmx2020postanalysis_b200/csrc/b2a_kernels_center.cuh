@@ -19,7 +19,31 @@ struct FrameGeom   // per frame; filled on the host at submit time from the floa
     double L[3];         // Lbox[k] = double(fr->box[k][k])
     double half[3];      // Lbox[k] / 2  (ipp:128, 176)
     double inv_unit[3];  // 2^32 / Lbox[k]: box-fraction fixed point used by the RDF fast path
+    float  hsafe[3];     // float slightly BELOW Lbox[k]/2: |x - ref| < hsafe in FP32 proves that no unwrap shift is needed
+    float  pad;
 };
+
+// Division by a block-invariant divisor, correctly rounded, in 3 FP64 instructions instead of the ~35 of __ddiv_rn:
+// with y = RN(1/d) from the host (IEEE division), q0 = RN(x*y), r = x - d*q0 (exact in an FMA), q = RN(q0 + r*y) is the
+// correctly rounded quotient (Markstein, "Computation of elementary functions on the IBM RISC System/6000", 1990).
+// `fast` is cleared by the host when d or 1/d is not a normal number (e.g. the zero charge sum of a neutral molecule,
+// where the reference's x/0 = +-inf/NaN must be reproduced), and huge/tiny/non-finite quotients take the IEEE path.
+struct DivConst
+{
+    double d, inv;
+    int    fast, pad;
+};
+
+__device__ __forceinline__ double div_const(double x, const DivConst& c)
+{
+    const double q0 = __dmul_rn(x, c.inv);
+    if (c.fast && fabs(q0) > 1e-280 && fabs(q0) < 1e280)
+    {
+        const double r = __fma_rn(-c.d, q0, x);
+        return __fma_rn(r, c.inv, q0);
+    }
+    return __ddiv_rn(x, c.d);
+}
 
 __device__ __forceinline__ double unwrap(double t, double ref, double L, double half)
 {
@@ -29,18 +53,79 @@ __device__ __forceinline__ double unwrap(double t, double ref, double L, double 
     return t;
 }
 
+// FP32 pre-test: (double)t - (double)ref is exact and differs from the rounded float difference by <= 2^-24 relative,
+// so |tf - reff| < hsafe (a float a few ulp below L/2) proves -L/2 < t - ref < L/2: the reference's loops would not run.
+__device__ __forceinline__ double unwrap_f(float tf, float reff, double L, double half, float hsafe)
+{
+    const double t = (double)tf;
+    if (fabsf(tf - reff) < hsafe) return t;
+    return unwrap(t, (double)reff, L, half);
+}
+
 __device__ __forceinline__ int to_fixed(double c, double inv_unit)
 {
     // nearest multiple of L/2^32, wrapped mod 2^32: integer differences are then minimum-image for free
     return (int)(unsigned)(unsigned long long)__double2ll_rn(c * inv_unit);
 }
 
-// ---- K1: per-molecule centre, GmxHandle::loadPositionCenter (ipp:150-199) -----------------------------------
+template <bool SMEM>
+__device__ __forceinline__ float ldf(const float* p) { return SMEM ? *p : __ldg(p); }
+
+// ---- per-molecule centre, GmxHandle::loadPositionCenter (ipp:150-199): sequential j order per component ----------
+template <bool SMEM>
+__device__ __forceinline__ void mol_centers3(const float* p, int napm, const double* sw, const DivConst& wsum,
+                                             const FrameGeom& g, double& c0, double& c1, double& c2)
+{
+    const float r0 = ldf<SMEM>(p), r1 = ldf<SMEM>(p + 1), r2 = ldf<SMEM>(p + 2);
+    c0 = c1 = c2 = 0.0;
+    constexpr int U = 4;
+    int           j = 0;
+    for (; j + U <= napm; j += U)
+    {
+        float v[U][3];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            v[u][0] = ldf<SMEM>(p + 3 * (j + u));
+            v[u][1] = ldf<SMEM>(p + 3 * (j + u) + 1);
+            v[u][2] = ldf<SMEM>(p + 3 * (j + u) + 2);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const double wj = sw[j + u];
+            c0 = __dadd_rn(c0, __dmul_rn(unwrap_f(v[u][0], r0, g.L[0], g.half[0], g.hsafe[0]), wj));
+            c1 = __dadd_rn(c1, __dmul_rn(unwrap_f(v[u][1], r1, g.L[1], g.half[1], g.hsafe[1]), wj));
+            c2 = __dadd_rn(c2, __dmul_rn(unwrap_f(v[u][2], r2, g.L[2], g.half[2], g.hsafe[2]), wj));
+        }
+    }
+    for (; j < napm; ++j)
+    {
+        const double wj = sw[j];
+        c0 = __dadd_rn(c0, __dmul_rn(unwrap_f(ldf<SMEM>(p + 3 * j), r0, g.L[0], g.half[0], g.hsafe[0]), wj));
+        c1 = __dadd_rn(c1, __dmul_rn(unwrap_f(ldf<SMEM>(p + 3 * j + 1), r1, g.L[1], g.half[1], g.hsafe[1]), wj));
+        c2 = __dadd_rn(c2, __dmul_rn(unwrap_f(ldf<SMEM>(p + 3 * j + 2), r2, g.L[2], g.half[2], g.hsafe[2]), wj));
+    }
+    c0 = div_const(c0, wsum);
+    c1 = div_const(c1, wsum);
+    c2 = div_const(c2, wsum);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ double center_component(const float* p, int k, int napm, const double* sw, const DivConst& wsum,
+                                                   double L, double half, float hsafe)
+{
+    const float ref = ldf<SMEM>(p + k);
+    double      c   = 0.0;
+    for (int j = 0; j < napm; ++j) c = __dadd_rn(c, __dmul_rn(unwrap_f(ldf<SMEM>(p + 3 * j + k), ref, L, half, hsafe), sw[j]));
+    return div_const(c, wsum);
+}
+
+// ---- K1 (direct loads; used when the index group is not one contiguous run of atoms) -----------------------------
 // cen: [frame][k][i] doubles (= itp::matd column-major per frame); fix: [frame][i] int4 {x,y,z fixed, i}
-template <int UNROLL>
 __global__ void __launch_bounds__(256) k1_centers(const float* __restrict__ x, size_t frame_stride, int nframes,
                                                   const int* __restrict__ index, int nmol, int napm,
-                                                  const double* __restrict__ w, double wsum,
+                                                  const double* __restrict__ w, DivConst wsum,
                                                   const FrameGeom* __restrict__ geom, double* __restrict__ cen,
                                                   int4* __restrict__ fix)
 {
@@ -50,41 +135,10 @@ __global__ void __launch_bounds__(256) k1_centers(const float* __restrict__ x, s
     const int f = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nmol || f >= nframes) return;
-    const FrameGeom g   = geom[f];
-    const int       mol = __ldg(index + (size_t)i * napm);
-    const float*    p   = x + (size_t)f * frame_stride + (size_t)mol * 3;
-    const double r0 = (double)__ldg(p), r1 = (double)__ldg(p + 1), r2 = (double)__ldg(p + 2);
-    double       c0 = 0.0, c1 = 0.0, c2 = 0.0;
-    int          j  = 0;
-    for (; j + UNROLL <= napm; j += UNROLL)
-    {
-        float v[UNROLL][3];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-        {
-            v[u][0] = __ldg(p + 3 * (j + u));
-            v[u][1] = __ldg(p + 3 * (j + u) + 1);
-            v[u][2] = __ldg(p + 3 * (j + u) + 2);
-        }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-        {
-            const double wj = sw[j + u];
-            c0 = __dadd_rn(c0, __dmul_rn(unwrap((double)v[u][0], r0, g.L[0], g.half[0]), wj));
-            c1 = __dadd_rn(c1, __dmul_rn(unwrap((double)v[u][1], r1, g.L[1], g.half[1]), wj));
-            c2 = __dadd_rn(c2, __dmul_rn(unwrap((double)v[u][2], r2, g.L[2], g.half[2]), wj));
-        }
-    }
-    for (; j < napm; ++j)
-    {
-        const double wj = sw[j];
-        c0 = __dadd_rn(c0, __dmul_rn(unwrap((double)__ldg(p + 3 * j), r0, g.L[0], g.half[0]), wj));
-        c1 = __dadd_rn(c1, __dmul_rn(unwrap((double)__ldg(p + 3 * j + 1), r1, g.L[1], g.half[1]), wj));
-        c2 = __dadd_rn(c2, __dmul_rn(unwrap((double)__ldg(p + 3 * j + 2), r2, g.L[2], g.half[2]), wj));
-    }
-    c0 = __ddiv_rn(c0, wsum);
-    c1 = __ddiv_rn(c1, wsum);
-    c2 = __ddiv_rn(c2, wsum);
+    const FrameGeom g = geom[f];
+    const float*    p = x + (size_t)f * frame_stride + (size_t)__ldg(index + (size_t)i * napm) * 3;
+    double          c0, c1, c2;
+    mol_centers3<false>(p, napm, sw, wsum, g, c0, c1, c2);
     double* o = cen + (size_t)f * 3 * nmol;
     o[i]                    = c0;
     o[(size_t)nmol + i]     = c1;
@@ -107,30 +161,43 @@ __global__ void __launch_bounds__(256) k1b_positions(const float* __restrict__ x
     const float* pa  = xf + (size_t)at * 3;
     double*      o   = pos + (size_t)n * 3;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) o[k] = unwrap((double)__ldg(pa + k), (double)__ldg(pr + k), g.L[k], g.half[k]);
+    for (int k = 0; k < 3; ++k) o[k] = unwrap_f(__ldg(pa + k), __ldg(pr + k), g.L[k], g.half[k], g.hsafe[k]);
 }
 
 // ---- K2: centre of the needed dimension(s) -> 1-D histogram, never materialising the centres ----------------
 // README.md:143-150, general/calc_density_region.cpp:59-71, general/density_slit_jhl.cpp:59-77
 struct DensityDev
 {
-    int    dim, dim2, nbin, upper_inclusive;
-    double low, up, low2, up2;   // the program's float `real` bounds widened (comparison is done in double)
-    double dbin;
+    int      dim, dim2, nbin, upper_inclusive;
+    double   low, up, low2, up2;   // the program's float `real` bounds widened (comparison is done in double)
+    DivConst dbin;
 };
 
-__device__ __forceinline__ double center_component(const float* __restrict__ p, int k, int napm, const double* sw,
-                                                   double wsum, double L, double half)
+// returns the bin of this molecule, or -1 (filtered out, or outside the array: counted in ndrop)
+template <bool SMEM>
+__device__ __forceinline__ int density_molecule(const float* p, int napm, const double* sw, const DivConst& wsum,
+                                                const FrameGeom& g, const DensityDev& d, unsigned& nsel, unsigned& ndrop)
 {
-    const double ref = (double)__ldg(p + k);
-    double       c   = 0.0;
-    for (int j = 0; j < napm; ++j) c = __dadd_rn(c, __dmul_rn(unwrap((double)__ldg(p + 3 * j + k), ref, L, half), sw[j]));
-    return __ddiv_rn(c, wsum);
+    const double c  = center_component<SMEM>(p, d.dim, napm, sw, wsum, g.L[d.dim], g.half[d.dim], g.hsafe[d.dim]);
+    bool         ok = (d.low <= c) && (d.upper_inclusive ? (c <= d.up) : (c < d.up));
+    if (ok && d.dim2 >= 0)
+    {
+        const double c2 = center_component<SMEM>(p, d.dim2, napm, sw, wsum, g.L[d.dim2], g.half[d.dim2], g.hsafe[d.dim2]);
+        ok              = (d.low2 <= c2) && (d.upper_inclusive ? (c2 <= d.up2) : (c2 < d.up2));
+    }
+    if (!ok) return -1;
+    nsel++;
+    const int me = __double2int_rz(div_const(__dsub_rn(c, d.low), d.dbin));
+    if (me < 0 || me >= d.nbin) { ndrop++; return -1; }
+    return me;
 }
+
+// grid: x = molecule block, y = frame group.  A thread owns ONE molecule and walks the frames of its group.
+constexpr int kFramesPerBlock = 8;
 
 __global__ void __launch_bounds__(256) k2_density(const float* __restrict__ x, size_t frame_stride, int nframes,
                                                   const int* __restrict__ index, int nmol, int napm,
-                                                  const double* __restrict__ w, double wsum,
+                                                  const double* __restrict__ w, DivConst wsum,
                                                   const FrameGeom* __restrict__ geom, DensityDev d,
                                                   unsigned long long* __restrict__ hist,
                                                   unsigned long long* __restrict__ stats, int smem_bins)
@@ -143,26 +210,18 @@ __global__ void __launch_bounds__(256) k2_density(const float* __restrict__ x, s
     __syncthreads();
     const bool use_smem = smem_bins >= d.nbin;
     unsigned   ndrop = 0, nsel = 0;
-    // grid-stride over (frame, molecule) so one block folds many samples into its private histogram
-    const long long total = (long long)nframes * nmol;
-    for (long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x; n < total; n += (long long)gridDim.x * blockDim.x)
+    const int  i  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int  f0 = blockIdx.y * kFramesPerBlock, f1 = min(nframes, f0 + kFramesPerBlock);
+    if (i < nmol)
     {
-        const int       f = (int)(n / nmol), i = (int)(n % nmol);
-        const FrameGeom g = geom[f];
-        const float*    p = x + (size_t)f * frame_stride + (size_t)__ldg(index + (size_t)i * napm) * 3;
-        const double    c = center_component(p, d.dim, napm, sw, wsum, g.L[d.dim], g.half[d.dim]);
-        bool            ok = (d.low <= c) && (d.upper_inclusive ? (c <= d.up) : (c < d.up));
-        if (ok && d.dim2 >= 0)
+        const size_t moff = (size_t)__ldg(index + (size_t)i * napm) * 3;
+        for (int f = f0; f < f1; ++f)
         {
-            const double c2 = center_component(p, d.dim2, napm, sw, wsum, g.L[d.dim2], g.half[d.dim2]);
-            ok              = (d.low2 <= c2) && (d.upper_inclusive ? (c2 <= d.up2) : (c2 < d.up2));
+            const int me = density_molecule<false>(x + (size_t)f * frame_stride + moff, napm, sw, wsum, geom[f], d, nsel, ndrop);
+            if (me < 0) continue;
+            if (use_smem) atomicAdd(&shist[me], 1u);
+            else atomicAdd(&hist[me], 1ull);
         }
-        if (!ok) continue;
-        nsel++;
-        const int me = __double2int_rz(__ddiv_rn(__dsub_rn(c, d.low), d.dbin));
-        if (me < 0 || me >= d.nbin) { ndrop++; continue; }
-        if (use_smem) atomicAdd(&shist[me], 1u);
-        else atomicAdd(&hist[me], 1ull);
     }
     __syncthreads();
     if (use_smem)
