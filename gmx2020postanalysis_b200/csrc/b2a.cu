@@ -113,6 +113,8 @@ struct Acc
     int       ipt = 0, threads = 0;   // 0 = auto
     // orient
     double* d_cosedge = nullptr;
+    float*  d_fedge   = nullptr;
+    double* d_stab    = nullptr;
     int     nbin1 = 0;
 };
 } // namespace
@@ -206,7 +208,7 @@ static void free_group(Group& g)
 static void free_acc(Acc& a)
 {
     cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
-    cudaFree(a.d_cosedge);
+    cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab);
     if (a.h_frames) cudaFreeHost(a.h_frames);
 }
 
@@ -873,6 +875,37 @@ extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
     edge[0] = 2.0;
     CU(cudaMalloc(&a->d_cosedge, sizeof(double) * (nA + 1)));
     CU(cudaMemcpy(a->d_cosedge, edge.data(), sizeof(double) * (nA + 1), cudaMemcpyHostToDevice));
+    std::vector<float> fedge(nA + 2, -3.0f);
+    for (int k = 0; k <= nA; ++k) fedge[k] = (float)edge[k];
+    CU(cudaMalloc(&a->d_fedge, sizeof(float) * (nA + 2)));
+    CU(cudaMemcpy(a->d_fedge, fedge.data(), sizeof(float) * (nA + 2), cudaMemcpyHostToDevice));
+    // Radial thresholds in s = t1^2 + t2^2 (calc_orient_mof.cpp:175-179): R = sqrt(s) (IEEE, identical on host and
+    // device), selected iff Cr <= R <= CR, meZ = int((R - Cr) / dr).  Everything is monotone in s, so bisection over the
+    // bit patterns of positive doubles finds, for every k, the smallest s with meZ >= k; the device only compares.
+    if (nbin1 > 8000) return fail(B2A_ERR_UNSUPPORTED, "orient: more than 8000 radial bins");
+    const double Cr = (double)s->Cr, CR = (double)s->CR, dr = (double)s->dr;
+    auto rbin = [&](double sv) -> double {             // -1: R < Cr; else (R - Cr) / dr, whose truncation is meZ
+        const double R = std::sqrt(sv);
+        if (!(Cr <= R)) return -1.0;
+        return (R - Cr) / dr;                          // >= 0 here; int(q) >= k  <=>  q >= k for integer k >= 0
+    };
+    auto from_bits = [](uint64_t b) { double v; std::memcpy(&v, &b, 8); return v; };
+    auto smallest_s_with = [&](auto pred) -> double {   // pred monotone false..true over s in [0, +max]; returns +inf if never true
+        uint64_t lo = 0, hi = 0x7FEFFFFFFFFFFFFFull;      // bit patterns of +0 .. DBL_MAX
+        if (pred(from_bits(lo))) return 0.0;
+        if (!pred(from_bits(hi))) return INFINITY;
+        while (hi - lo > 1) { const uint64_t mid = lo + (hi - lo) / 2; if (pred(from_bits(mid))) hi = mid; else lo = mid; }
+        return from_bits(hi);
+    };
+    std::vector<double> stab(nbin1 + 2);
+    for (int k = 0; k <= nbin1; ++k) stab[k] = smallest_s_with([&](double sv) { return rbin(sv) >= (double)k; });
+    {   // largest s with sqrt(s) <= CR  ==  predecessor of the smallest s with sqrt(s) > CR
+        const double first_above = smallest_s_with([&](double sv) { return std::sqrt(sv) > CR; });
+        stab[nbin1 + 1] = std::isinf(first_above) ? first_above : std::nextafter(first_above, -INFINITY);
+        if (first_above == 0.0) stab[nbin1 + 1] = -1.0;   // CR < 0: nothing is ever selected
+    }
+    CU(cudaMalloc(&a->d_stab, sizeof(double) * (nbin1 + 2)));
+    CU(cudaMemcpy(a->d_stab, stab.data(), sizeof(double) * (nbin1 + 2), cudaMemcpyHostToDevice));
     return new_acc(c, std::move(a), id);
 }
 
@@ -885,7 +918,7 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
     d.DIMN = s.DIMN; d.nAngle = s.nAngle; d.nbin1 = a.nbin1; d.tp1 = s.tp1 - 1; d.tp2 = s.tp2 - 1; d.tp3 = s.tp3 - 1;
     d.DIMNOrient = s.DIMNOrient; d.method = s.method;
     d.low = (double)s.low; d.up = (double)s.up; d.c1 = (double)s.c1; d.c2 = (double)s.c2;
-    d.dr = make_div((double)s.dr); d.CR = (double)s.CR; d.Cr = (double)s.Cr;
+    d.CR = (double)s.CR; d.Cr = (double)s.Cr; d.Crf = s.Cr; d.inv_drf = 1.0f / s.dr;
     const int    threads = 256;
     const size_t hist_words = (size_t)a.nbin1 * s.nAngle + a.nbin1;
     const int    smem_bins  = hist_words <= 24000 ? (int)hist_words : 0;
@@ -894,15 +927,15 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
     {
         Timed      tm(c, 4);
         StreamArgs sa{};
-        sa.ori = d; sa.cosedge = a.d_cosedge; sa.hist = a.d_hist; sa.stats = a.d_hist + a.ndev; sa.smem_bins = smem_bins;
-        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1) + sizeof(unsigned) * smem_bins);
+        sa.ori = d; sa.cosedge = a.d_cosedge; sa.fedge = a.d_fedge; sa.stab = a.d_stab; sa.hist = a.d_hist; sa.stats = a.d_hist + a.ndev; sa.smem_bins = smem_bins;
+        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins);
     }
-    const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1) + sizeof(unsigned) * smem_bins;
+    const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins;
     CU(cudaFuncSetAttribute(k4_orient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const dim3 blocks((g->nmol + threads - 1) / threads, (c->nframes + kFramesPerBlock - 1) / kFramesPerBlock);
     Timed      tm(c, 4);
     k4_orient<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->nmol, g->napm,
-                                                    g->d_w[s.com], make_div(g->wsum[s.com]), c->d_geom, d, a.d_cosedge, a.d_hist,
+                                                    g->d_w[s.com], make_div(g->wsum[s.com]), c->d_geom, d, a.d_cosedge, a.d_fedge, a.d_stab, a.d_hist,
                                                     a.d_hist + a.ndev, smem_bins);
     CU(cudaGetLastError());
     return B2A_OK;

@@ -17,7 +17,7 @@ struct OrientDev
 {
     int    DIMN, nAngle, nbin1, tp1, tp2, tp3, DIMNOrient, method;   // tp* are 0-based here
     double   low, up, c1, c2, CR, Cr;
-    DivConst dr;
+    float    Crf, inv_drf;   // FP32 copies for the starting guess of the radial bin
 };
 
 __device__ __forceinline__ double periodicity_o(double dx, double box, float hsafe)
@@ -29,11 +29,39 @@ __device__ __forceinline__ double periodicity_o(double dx, double box, float hsa
     return dx;
 }
 
+// Tables the host prepares with its own libm so that the device never evaluates sqrt/acos/divide on the common path
+// and still reproduces the reference's bins exactly:
+//   sedge[k], k = 0..nAngle  (double): largest cos value whose reference angle bin is >= k (sedge[0] = 2)
+//   fedge[k]                 (float) : the same edges rounded to float, for the FP32 bracket
+//   stab[k],  k = 0..nbin1   (double): smallest s = t1^2 + t2^2 whose R = RN(sqrt(s)) passes Cr <= R and has
+//                                      int((R - Cr) / dr) >= k;  stab[nbin1 + 1] = largest s with RN(sqrt(s)) <= CR
+struct OrientTabs
+{
+    const double* sedge;
+    const float*  fedge;
+    const double* stab;
+};
+
+// exact angle bin of calc_orient_mof.cpp:41-47,193-194 from dot = vecOut . wall and n2 = |vecOut|^2: FP64 sqrt and divide
+__device__ __noinline__ int orient_exact_bin(double dot, double n2, const double* sedge, int nAngle)
+{
+    const double rv = __dsqrt_rn(n2);
+    const double cs = __ddiv_rn(dot, __dmul_rn(rv, 1.0));
+    if (!(cs >= -1.0 && cs <= 1.0)) return -1;   // acos -> NaN in the reference (undefined bin): dropped
+    int lo = 0, hi = nAngle + 1;                 // invariant: cs <= sedge[lo] (sedge[0] = 2), cs > sedge[hi] (virtual)
+    while (hi - lo > 1)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (cs <= sedge[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // One molecule: NCMDens cell (cell_z = ncells + meZ) and orient cell (cell_a = meZ + meA*nbin1), -1 where nothing is
 // counted.  Mirrors calc_orient_mof.cpp:156-199 statement by statement.
 template <bool SMEM>
 __device__ __forceinline__ void orient_molecule(const float* p, int napm, const double* sw, const DivConst& wsum,
-                                                const FrameGeom& g, const OrientDev& d, const double* sedge, int& cell_z,
+                                                const FrameGeom& g, const OrientDev& d, const OrientTabs& tb, int& cell_z,
                                                 int& cell_a, unsigned& nsel, unsigned& ndrop)
 {
     cell_z = cell_a = -1;
@@ -45,11 +73,16 @@ __device__ __forceinline__ void orient_molecule(const float* p, int napm, const 
     if (!(d.low <= cz && cz <= d.up)) return;
     const double t1 = __dsub_rn(d.DIMN == 0 ? c1 : c0, d.c1);
     const double t2 = __dsub_rn(d.DIMN == 2 ? c1 : c2, d.c2);
-    const double R  = __dsqrt_rn(__dadd_rn(__dmul_rn(t1, t1), __dmul_rn(t2, t2)));
-    if (!(d.Cr <= R && R <= d.CR)) return;
+    const double s  = __dadd_rn(__dmul_rn(t1, t1), __dmul_rn(t2, t2));   // the argument of std::sqrt at :175
+    // Cr <= R && R <= CR, meZ = int((R - Cr) / dr) with R = RN(sqrt(s)): all monotone in s, so compare s against the
+    // host-tabulated thresholds.  An FP32 estimate gives the starting bin, FP64 compares make it exact.
+    if (!(s >= tb.stab[0] && s <= tb.stab[d.nbin1 + 1])) return;
     nsel++;
-    const int meZ = __double2int_rz(div_const(__dsub_rn(R, d.Cr), d.dr));
-    if (meZ < 0 || meZ >= d.nbin1) { ndrop++; return; }
+    int meZ = (int)((sqrtf((float)s) - d.Crf) * d.inv_drf);
+    meZ     = max(0, min(meZ, d.nbin1));
+    while (meZ > 0 && s < tb.stab[meZ]) --meZ;
+    while (meZ < d.nbin1 && s >= tb.stab[meZ + 1]) ++meZ;
+    if (meZ >= d.nbin1) { ndrop++; return; }
     cell_z = d.nbin1 * d.nAngle + meZ;
     // getPoint + calcVector (:14-38): unwrapped atoms tp1..3, min-imaged differences
     const float rr[3] = { r0, r1, r2 };
@@ -74,21 +107,24 @@ __device__ __forceinline__ void orient_molecule(const float* p, int napm, const 
     {
         vo[0] = __dadd_rn(v1[0], v2[0]); vo[1] = __dadd_rn(v1[1], v2[1]); vo[2] = __dadd_rn(v1[2], v2[2]);
     }
-    // calcAngle (:41-47) up to the cosine; wall = unit vector along DIMNOrient so r2 == 1 and the dot product is
-    // vo[DIMNOrient] exactly (the other terms are signed zeros)
-    const double rv = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(vo[0], vo[0]), __dmul_rn(vo[1], vo[1])), __dmul_rn(vo[2], vo[2])));
-    const double wl[3] = { d.DIMNOrient == 0 ? 1.0 : 0.0, d.DIMNOrient == 1 ? 1.0 : 0.0, d.DIMNOrient == 2 ? 1.0 : 0.0 };
-    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(vo[0], wl[0]), __dmul_rn(vo[1], wl[1])), __dmul_rn(vo[2], wl[2]));
-    const double cs  = __ddiv_rn(dot, __dmul_rn(rv, 1.0));
-    if (!(cs >= -1.0 && cs <= 1.0)) { ndrop++; return; }   // acos -> NaN in the reference (undefined bin)
-    // bin = #{k in 1..nAngle : cs <= edge[k]} by binary search over the decreasing edge table
-    int lo = 0, hi = d.nAngle + 1;   // invariant: cs <= edge[lo] (edge[0] = 2), cs > edge[hi] (virtual)
+    // calcAngle (:41-47): wall = unit vector along DIMNOrient, so |wall| == 1 and the dot product is vo[DIMNOrient]
+    // exactly (the other two products are signed zeros); cos = dot / |vo|
+    const double n2  = __dadd_rn(__dadd_rn(__dmul_rn(vo[0], vo[0]), __dmul_rn(vo[1], vo[1])), __dmul_rn(vo[2], vo[2]));
+    const double dot = d.DIMNOrient == 0 ? vo[0] : (d.DIMNOrient == 1 ? vo[1] : vo[2]);
+    // FP32 bracket: |cs_f - cs_ref| < 1e-6 (two conversions, rsqrt.approx, one multiply: < 8 * 2^-24), so a value more
+    // than kMargin away from both neighbouring edges (and from +-1, where the reference's acos turns NaN) is decided.
+    constexpr float kMargin = 2e-6f;
+    const float     csf     = (float)dot * rsqrtf((float)n2);
+    int             lo = 0, hi = d.nAngle + 1;
     while (hi - lo > 1)
     {
         const int mid = (lo + hi) >> 1;
-        if (cs <= sedge[mid]) lo = mid; else hi = mid;
+        if (csf <= tb.fedge[mid]) lo = mid; else hi = mid;
     }
-    if (lo >= d.nAngle) { ndrop++; return; }                 // e.g. angle == 180 (:194-196) -> out of bounds
+    const bool proven = (fabsf(csf) < 1.0f - kMargin) && (lo == 0 || csf <= tb.fedge[lo] - kMargin) &&
+                        (lo >= d.nAngle || csf >= tb.fedge[lo + 1] + kMargin);
+    if (!proven) lo = orient_exact_bin(dot, n2, tb.sedge, d.nAngle);
+    if (lo < 0 || lo >= d.nAngle) { ndrop++; return; }       // NaN angle, or angle == 180 (:194-196) -> out of bounds
     cell_a = meZ + lo * d.nbin1;
 }
 
@@ -97,16 +133,21 @@ __global__ void __launch_bounds__(256) k4_orient(const float* __restrict__ x, si
                                                  const int* __restrict__ index, int nmol, int napm,
                                                  const double* __restrict__ w, DivConst wsum,
                                                  const FrameGeom* __restrict__ geom, OrientDev d,
-                                                 const double* __restrict__ cosedge,
+                                                 const double* __restrict__ cosedge, const float* __restrict__ fedge_g,
+                                                 const double* __restrict__ stab_g,
                                                  unsigned long long* __restrict__ hist,
                                                  unsigned long long* __restrict__ stats, int smem_bins)
 {
     extern __shared__ double sm4[];
     double*   sw    = sm4;                    // napm
     double*   sedge = sm4 + napm;             // nAngle + 1
-    unsigned* shist = reinterpret_cast<unsigned*>(sedge + d.nAngle + 1);
+    double*   stab  = sedge + d.nAngle + 1;   // nbin1 + 2
+    float*    fedge = reinterpret_cast<float*>(stab + d.nbin1 + 2);   // nAngle + 1 (+1 pad)
+    unsigned* shist = reinterpret_cast<unsigned*>(fedge + ((d.nAngle + 2) & ~1));
     for (int j = threadIdx.x; j < napm; j += blockDim.x) sw[j] = w[j];
-    for (int j = threadIdx.x; j <= d.nAngle; j += blockDim.x) sedge[j] = cosedge[j];
+    for (int j = threadIdx.x; j <= d.nAngle; j += blockDim.x) { sedge[j] = cosedge[j]; fedge[j] = fedge_g[j]; }
+    for (int j = threadIdx.x; j < d.nbin1 + 2; j += blockDim.x) stab[j] = stab_g[j];
+    const OrientTabs tb{ sedge, fedge, stab };
     for (int b = threadIdx.x; b < smem_bins; b += blockDim.x) shist[b] = 0;
     __syncthreads();
     const int  ncells   = d.nbin1 * d.nAngle;              // orient cells, then nbin1 NCMDens cells
@@ -119,7 +160,7 @@ __global__ void __launch_bounds__(256) k4_orient(const float* __restrict__ x, si
     {
         int cz, ca;
         const FrameGeom g = geom[f];
-        orient_molecule<false>(x + (size_t)f * frame_stride + moff, napm, sw, wsum, g, d, sedge, cz, ca, nsel, ndrop);
+        orient_molecule<false>(x + (size_t)f * frame_stride + moff, napm, sw, wsum, g, d, tb, cz, ca, nsel, ndrop);
         if (cz >= 0) { if (use_smem) atomicAdd(&shist[cz], 1u); else atomicAdd(&hist[cz], 1ull); }
         if (ca >= 0) { if (use_smem) atomicAdd(&shist[ca], 1u); else atomicAdd(&hist[ca], 1ull); }
     }

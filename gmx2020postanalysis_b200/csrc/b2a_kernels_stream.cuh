@@ -63,6 +63,8 @@ struct StreamArgs
     DensityDev       den;
     OrientDev        ori;
     const double*    cosedge;
+    const float*     fedge;
+    const double*    stab;
     unsigned long long* hist;
     unsigned long long* stats;
     int              smem_bins;
@@ -78,8 +80,10 @@ __global__ void __launch_bounds__(256) k_stream(const __grid_constant__ StreamAr
     unsigned long long* bars  = reinterpret_cast<unsigned long long*>(tiles + (size_t)kStages * a.tile_floats);
     FrameGeom*          sgeom = reinterpret_cast<FrameGeom*>(bars + kStages);          // frames_per_block entries
     double*             sw    = reinterpret_cast<double*>(sgeom + a.frames_per_block);
-    double*             sedge = sw + a.napm;
-    unsigned*           shist = reinterpret_cast<unsigned*>(sedge + (MODE == 2 ? a.ori.nAngle + 1 : 0));
+    double*             sedge = sw + a.napm;                                                   // MODE 2: nAngle + 1
+    double*             stab  = sedge + (MODE == 2 ? a.ori.nAngle + 1 : 0);                    // MODE 2: nbin1 + 2
+    float*              fedge = reinterpret_cast<float*>(stab + (MODE == 2 ? a.ori.nbin1 + 2 : 0));   // MODE 2: nAngle + 1
+    unsigned*           shist = reinterpret_cast<unsigned*>(fedge + (MODE == 2 ? ((a.ori.nAngle + 2) & ~1) : 0));
 
     const int M      = blockDim.x;
     const int m0     = blockIdx.x * M;
@@ -96,7 +100,11 @@ __global__ void __launch_bounds__(256) k_stream(const __grid_constant__ StreamAr
         for (int j = threadIdx.x; j < nf * (int)(sizeof(FrameGeom) / sizeof(double)); j += M) dst[j] = src[j];
     }
     if (MODE == 2)
-        for (int j = threadIdx.x; j <= a.ori.nAngle; j += M) sedge[j] = a.cosedge[j];
+    {
+        for (int j = threadIdx.x; j <= a.ori.nAngle; j += M) { sedge[j] = a.cosedge[j]; fedge[j] = a.fedge[j]; }
+        for (int j = threadIdx.x; j < a.ori.nbin1 + 2; j += M) stab[j] = a.stab[j];
+    }
+    const OrientTabs tb{ sedge, fedge, stab };
     if (MODE != 0)
         for (int b = threadIdx.x; b < a.smem_bins; b += M) shist[b] = 0;
     if (threadIdx.x == 0)
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(256) k_stream(const __grid_constant__ StreamAr
             else
             {
                 int cz, ca;
-                orient_molecule<true>(p, a.napm, sw, a.wsum, g, a.ori, sedge, cz, ca, nsel, ndrop);
+                orient_molecule<true>(p, a.napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop);
                 if (cz >= 0)
                 {
                     if (use_smem) atomicAdd(&shist[cz], 1u);
