@@ -102,33 +102,20 @@ def check(rc):
         raise B2AError(rc, load().b2a_last_error().decode())
 
 
+_PINNED_KEEPALIVE = []
+
+
 def pinned_empty(shape, dtype):
-    """numpy array over cudaMallocHost memory (freed when the array's base object dies)."""
+    """numpy array over page-locked host memory (cudaMallocHost through the C ABI) for asynchronous H2D copies.
+    The allocation lives until the process exits."""
     L = load()
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = L.b2a_pinned_alloc(max(n, 1))
     if not p:
         raise B2AError(2, L.b2a_last_error().decode())
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                L.b2a_pinned_free(self.ptr)
-            except Exception:
-                pass
-
-    owner = _Owner(p)
     buf = (C.c_char * max(n, 1)).from_address(p)
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    arr._b2a_owner = owner if hasattr(arr, "__dict__") else None
-    _PINNED_KEEPALIVE[id(buf)] = (owner, buf)
-    return arr
-
-
-_PINNED_KEEPALIVE = {}
+    _PINNED_KEEPALIVE.append(buf)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
 
 class Context:

@@ -1,0 +1,109 @@
+"""Throughput of the other BASELINE.json configs on one GPU (the contract benchmark, bench.py, is config 2).
+
+  C1: README template density profile, 3 000 SPC/E, 100 frames, nbin=100, dim=z, COM   (device + end-to-end)
+  C3: cation-anion COM RDF, 1 000 000-atom ionic liquid (31 250 x (25 + 7) atoms)       (per-frame, K frames)
+  C4: dipole vectors + bisector orientation histogram, 166 666 SPC/E (499 998 atoms)   (K frames)
+Prints one JSON line per config.      python tools/bench_configs.py [--c3-frames 4] [--c4-frames 64]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gmx2020postanalysis_b200 import lib, synth  # noqa: E402
+
+
+def groups(ctx, system, names):
+    for g, name in enumerate(names):
+        idx = system.groups[name]
+        sp = [s for s, off in zip(system.species, system.offsets()) if off <= idx[0] < off + s.nmol * s.napm][0]
+        ctx.set_group(g, idx, sp.napm, sp.mass.astype(np.float64), sp.charge.astype(np.float64))
+
+
+def timeit(ctx, fn, reps):
+    fn(); ctx.sync()
+    t = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    ctx.sync()
+    return (time.perf_counter() - t) / reps
+
+
+def c1(reps=20):
+    system = synth.water_box(3000, 4.476, seed=20200101)
+    K = 100
+    x = lib.pinned_empty((K, system.natoms, 3), np.float32)
+    system.frames(0, K, out=x)
+    ctx = lib.Context(system.natoms, K)
+    groups(ctx, system, ["SOL"])
+    dbin = float(np.float32(np.float32(4.476) / np.float32(100)))
+    acc = ctx.density_create(grp=0, com=0, dim=2, low=0.0, up=4.476, dbin=dbin, nbin=100, upper_inclusive=0, dim2=-1, low2=0.0, up2=0.0)
+    ctx.submit(x, system.box9())
+    dev = timeit(ctx, lambda: ctx.accumulate(acc), reps)
+
+    def e2e():
+        ctx.submit(x, system.box9()); ctx.accumulate(acc); ctx.read(acc, 100)
+    tot = timeit(ctx, e2e, reps)
+    ctx.close()
+    return {"config": "C1 density template, 3000 SPC/E x 100 frames", "device_ms_per_100_frames": dev * 1e3,
+            "e2e_ms_per_100_frames": tot * 1e3, "frames_per_s_device": K / dev, "frames_per_s_e2e": K / tot}
+
+
+def c3(K, reps=3):
+    system = synth.ionic_liquid(31250, 22.1, seed=20200103)
+    x = system.frames(0, K)
+    ctx = lib.Context(system.natoms, K)
+    groups(ctx, system, ["CAT", "ANI"])
+    Rm = float(np.float32(np.float32(22.1) / 2)); Rbin = int(Rm / 0.002)
+    acc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=5, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0, Rm=Rm, Rbin=Rbin)
+    ctx.submit(x, system.box9())
+
+    def step():
+        ctx.invalidate(); ctx.accumulate(acc)
+    dev = timeit(ctx, step, reps)
+    ctx.timing_enable(True); ctx.timing_read(); step(); tm = ctx.timing_read(); ctx.timing_enable(False)
+    cnt, st = ctx.read(acc, 5 * Rbin)
+    ctx.close()
+    pairs = 31250.0 * 31250.0 * K
+    return {"config": "C3 cation-anion COM RDF, 1M-atom ionic liquid", "frames": K, "ms_per_frame": dev * 1e3 / K,
+            "frames_per_s": K / dev, "pair_distances_per_s": pairs / dev, "k1_ms": tm["k1_centers"][0], "k3_ms": tm["k3_rdf"][0],
+            "prep_ms": tm["k3_prep"][0], "Rbin": Rbin, "fp64_reevaluated_per_frame": int(st[lib.STAT_EXACT]) / (reps + 2) / K}
+
+
+def c4(K, reps=10):
+    system = synth.water_box(166666, 17.09, seed=20200104)
+    base = system.frames(0, 4)
+    x = lib.pinned_empty((K, system.natoms, 3), np.float32)
+    for k in range(K):
+        x[k] = base[k % 4]
+    ctx = lib.Context(system.natoms, K)
+    groups(ctx, system, ["SOL"])
+    ori = ctx.orient_create(grp=0, com=0, DIMN=2, low=-1.0, up=100.0, c1=0.0, c2=0.0, dr=100.0, CR=100.0, Cr=0.0, nAngle=90,
+                            tp1=1, tp2=2, tp3=3, DIMNOrient=2, method=1)
+    ctx.submit(x, system.box9())
+
+    def step():
+        ctx.invalidate(); ctx.centers(0, lib.COM_DIPOLE, 0); ctx.accumulate(ori)     # dipole vectors (K1, com 3) + orientation (K4)
+    dev = timeit(ctx, step, reps)
+
+    def e2e():
+        ctx.submit(x, system.box9()); ctx.centers(0, lib.COM_DIPOLE, 0); ctx.accumulate(ori); ctx.read(ori, 91)
+    tot = timeit(ctx, e2e, 3)
+    ctx.close()
+    return {"config": "C4 dipole + orientation, 166 666 SPC/E (499 998 atoms)", "frames": K, "device_frames_per_s": K / dev,
+            "e2e_frames_per_s": K / tot, "device_GBs": K * system.natoms * 12 * 2 / dev / 1e9,
+            "e2e_h2d_GBs": K * system.natoms * 12 / tot / 1e9}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--c3-frames", type=int, default=4)
+    ap.add_argument("--c4-frames", type=int, default=64)
+    a = ap.parse_args()
+    for r in (c1(), c3(a.c3_frames), c4(a.c4_frames)):
+        print(json.dumps(r))
