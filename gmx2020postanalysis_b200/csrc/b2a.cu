@@ -109,7 +109,12 @@ struct Acc
     int4*     d_sortedA = nullptr;
     RdfFrame* d_frames = nullptr;
     RdfFrame* h_frames = nullptr;     // pinned
-    int       symmetric = 0, paranoid = 0;
+    int       symmetric = 0, paranoid = 0, cells = -1;   // cells: -1 auto, 0 never, 1 whenever it culls anything
+    // cell mode scratch (allocated on first use)
+    int*      d_keysA = nullptr; int* d_keysB = nullptr;
+    unsigned* d_cellA = nullptr; unsigned* d_cellB = nullptr;   // [3][maxK][nkeys + 1]: counts, starts, cursors
+    int4*     d_sortedB = nullptr;
+    unsigned  cap_keysA = 0, cap_keysB = 0;
     int       ipt = 0, threads = 0;   // 0 = auto
     // orient
     double* d_cosedge = nullptr;
@@ -209,6 +214,7 @@ static void free_acc(Acc& a)
 {
     cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
     cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab);
+    cudaFree(a.d_keysA); cudaFree(a.d_keysB); cudaFree(a.d_cellA); cudaFree(a.d_cellB); cudaFree(a.d_sortedB);
     if (a.h_frames) cudaFreeHost(a.h_frames);
 }
 
@@ -524,29 +530,86 @@ extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
     return B2A_OK;
 }
 
+extern "C" int b2a_rdf_cells(b2a_ctx* c, int id, int mode)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (a->kind != ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF", id);
+    if (mode < -1 || mode > 1) return fail(B2A_ERR_ARG, "b2a_rdf_cells: mode must be -1 (auto), 0 (never) or 1 (whenever cells cull)");
+    a->cells = mode;
+    return B2A_OK;
+}
+
 static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
 static float next_up(float v) { return std::nextafterf(v, INFINITY); }
 
-template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, bool SYM>
-static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, dim3 grid)
+template <int IPT, int THREADS, bool CUBIC, bool PARANOID, int MODE>
+static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid)
 {
-    auto kern = k3_rdf<IPT, THREADS, CLAMP, CUBIC, PARANOID, SYM>;
+    auto kern = k3_rdf<IPT, THREADS, true, CUBIC, PARANOID, MODE>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, THREADS, smem, c->stream>>>(a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
-                                            a.d_slab_cnt, a.d_frames, p, a.d_hist, a.d_hist + a.ndev);
+                                            a.d_slab_cnt, a.d_frames, p, cd, a.d_hist, a.d_hist + a.ndev);
     CU(cudaGetLastError());
     return B2A_OK;
 }
 
-template <bool SYM>
-static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, dim3 grid, bool clamp, bool cubic)
+template <int IPT, int MODE>
+static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid, bool cubic)
 {
-    constexpr int IPT = 8, TH = 128;
+    constexpr int TH = 128;
     if (a.paranoid)
-        return clamp ? (cubic ? launch_rdf<IPT, TH, true, true, true, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, true, false, true, SYM>(c, a, g0, g1, p, smem, grid))
-                     : (cubic ? launch_rdf<IPT, TH, false, true, true, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, false, false, true, SYM>(c, a, g0, g1, p, smem, grid));
-    return clamp ? (cubic ? launch_rdf<IPT, TH, true, true, false, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, true, false, false, SYM>(c, a, g0, g1, p, smem, grid))
-                 : (cubic ? launch_rdf<IPT, TH, false, true, false, SYM>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, false, false, false, SYM>(c, a, g0, g1, p, smem, grid));
+        return cubic ? launch_rdf<IPT, TH, true, true, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, true, MODE>(c, a, g0, g1, p, cd, smem, grid);
+    return cubic ? launch_rdf<IPT, TH, true, false, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, false, MODE>(c, a, g0, g1, p, cd, smem, grid);
+}
+
+constexpr int kCellIPT = 4;   // i-molecules per thread in cell mode (one cell per block: ~300-500 molecules)
+
+// Cell grid for r_max << L: cells per dimension 2^bits, reach per dimension from the cut-off plus the fixed-point slop.
+// Returns false when cells would not cull enough to beat the brute-force (possibly symmetric) evaluation.
+static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_possible, int* bits, int reach[3])
+{
+    int want = a.cells;
+    if (const char* e = getenv("B2A_RDF_CELLS")) want = atoi(e);
+    if (want == 0) return false;
+    const int    TI    = kCellIPT * 128;
+    const double nmin  = (double)std::min(p.n0, p.n1);
+    double       bestc = 1e30;
+    int          bestb = -1, bestr[3] = { 0, 0, 0 };
+    for (int b = 2; b <= 7; ++b)
+    {
+        const int    nc = 1 << b;
+        const double m  = nmin / ((double)nc * nc * nc);        // mean molecules per cell
+        if (m < 48.0) break;
+        if ((unsigned long long)p.nslab << (3 * b) > (4ull << 20)) break;
+        int  r[3];
+        bool ok = false;
+        for (int k = 0; k < 3; ++k)
+        {
+            int rk = 0;
+            for (int f = 0; f < c->nframes; ++f)
+            {
+                const double L = c->h_geom[f].L[k], cell = L / nc, unit = L / 4294967296.0;
+                // |true dx| < Rm(1+3e-8) can still be counted (float-rounded cut); fixed coordinates are within half a
+                // unit of the truth, and flooring two positions to cells can add one more cell of distance
+                rk = std::max(rk, (int)std::floor((p.Rm * (1.0 + 1e-6) + 2.0 * unit) / cell) + 1);
+            }
+            r[k] = rk;
+            if (2 * rk + 1 < nc) ok = true;
+        }
+        if (!ok) continue;
+        double frac = 1.0;
+        for (int k = 0; k < 3; ++k) frac *= (double)std::min(2 * r[k] + 1, nc) / nc;
+        const double util = m / (std::ceil(m / TI) * TI);       // lane utilisation of a one-cell tile
+        const double cost = frac / std::min(1.0, util) * 1.15;  // 15 %: IPT 4 instead of 8, per-range tile edges
+        if (cost < bestc) { bestc = cost; bestb = b; bestr[0] = r[0]; bestr[1] = r[1]; bestr[2] = r[2]; }
+    }
+    if (bestb < 0) return false;
+    const double brute = sym_possible ? 0.5 : 1.0;
+    if (want < 0 && bestc > 0.8 * brute) return false;
+    *bits = bestb;
+    reach[0] = bestr[0]; reach[1] = bestr[1]; reach[2] = bestr[2];
+    return true;
 }
 
 static int accumulate_rdf(b2a_ctx* c, Acc& a)
@@ -568,11 +631,11 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     p.Rbin_d = (double)s.Rbin;
     p.rbin_bits = kMagicBits + (unsigned)s.Rbin;
     // symmetric evaluation is legal only when both sides are the very same molecules with the same centre kind
-    p.sym_enabled = (a.symmetric && s.com0 == s.com1 && g0->nmol == g1->nmol && g0->napm == g1->napm && g0->h_index == g1->h_index) ? 1 : 0;
+    const bool same = s.com0 == s.com1 && g0->nmol == g1->nmol && g0->napm == g1->napm && g0->h_index == g1->h_index;
+    p.sym_enabled   = (a.symmetric && same) ? 1 : 0;
 
-    // per-frame fast-path constants and the largest reachable bin
-    bool   cubic = true;
-    double tmax  = 0.0;
+    // per-frame fast-path constants
+    bool cubic = true;
     CU(cudaStreamSynchronize(c->stream));   // h_frames reuse
     for (int f = 0; f < c->nframes; ++f)
     {
@@ -598,56 +661,82 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         const double delta_bins = std::sqrt(3.0) * 1.0001 * sc * std::max(1.0, std::max((double)fr.ay, (double)fr.az));
         const unsigned lowk     = (unsigned)std::ceil(delta_bins / (eps - eps_true)) + 2;
         fr.lowk_bits = kMagicBits + lowk;
-        for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
         // r2max: r with bin coordinate Rbin + 0.5 -- both bracket bins are exactly Rbin for any eps < 1e-4
-        {
-            const double r_units = ((double)s.Rbin + 0.5) / sc;
-            fr.r2max = (float)(r_units * r_units);
-        }
-        const double rmax_units = 2147483648.0 * std::sqrt(1.0 + (double)fr.ay * fr.ay + (double)fr.az * fr.az) * 1.000001;
-        tmax = std::max(tmax, rmax_units * (double)hi);
+        const double r_units = ((double)s.Rbin + 0.5) / sc;
+        fr.r2max = (float)(r_units * r_units);
+        for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
     }
     CU(cudaMemcpyAsync(a.d_frames, a.h_frames, sizeof(RdfFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
 
-    // shared histogram: every reachable bin if it fits comfortably, else clamp to Rbin (+1 FMNMX pair per pair)
-    const size_t   fixed_smem  = kTileJ * sizeof(int4) + kQueueCap * sizeof(unsigned) + 16;
-    const unsigned full_stride = (unsigned)std::ceil(tmax) + 4;
-    // Measured on B200 (profiles/r01_k3_tuning.md): clamping out-of-range pairs into ONE trash bin is faster than an
-    // oversize histogram even though it costs two FMNMX per pair -- the ~48% of lanes beyond Rm then hit a single
-    // address (one merged wavefront instead of random bank conflicts) and never enter the undecided queue.
-    bool           clamp       = true;
-    if (const char* e = getenv("B2A_RDF_CLAMP")) clamp = atoi(e) != 0 || ((size_t)full_stride * 4 + fixed_smem > 40 * 1024);
-    p.kstride                  = clamp ? (unsigned)s.Rbin + 3 : full_stride;
-    const size_t smem          = fixed_smem + (size_t)p.kstride * 4;
+    // Shared histogram: pairs beyond the cut-off are clamped into ONE trash bin (bin Rbin).  Measured on B200
+    // (profiles/r01_k3_tuning.md): faster than an oversize histogram -- the ~48 % of lanes beyond Rm hit a single address
+    // (one merged wavefront instead of random bank conflicts) and never enter the undecided queue.
+    const size_t fixed_smem = kTileJ * sizeof(int4) + kQueueCap * sizeof(unsigned) + 16;
+    p.kstride               = (unsigned)s.Rbin + 3;
+    const size_t smem       = fixed_smem + (size_t)p.kstride * 4;
     if (smem > 200 * 1024) return fail(B2A_ERR_UNSUPPORTED, "rdf: Rbin=%d needs %zu bytes of shared memory per block", s.Rbin, smem);
 
-    // prep: slab ids, counts, scatter
+    // prep: slab ids and counts
     const int nslab = p.nslab;
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, c->stream));
+    int  bits = 0, reach[3] = { 0, 0, 0 };
+    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach);
+    CellDev cd{};
     {
         Timed tm(c, 1);
         dim3 grid((p.n0 + 255) / 256, c->nframes);
         k3_slab_count<<<grid, 256, sizeof(unsigned) * nslab, c->stream>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
         CU(cudaGetLastError());
-        k3_slab_scatter<<<grid, 256, sizeof(unsigned) * 3 * nslab, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
-                                                                         a.d_slab_cnt, a.d_slab_cnt + (size_t)nslab * c->maxK, a.d_sortedA);
-        CU(cudaGetLastError());
+        if (!cells)
+        {
+            k3_slab_scatter<<<grid, 256, sizeof(unsigned) * 3 * nslab, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
+                                                                                 a.d_slab_cnt, a.d_slab_cnt + (size_t)nslab * c->maxK, a.d_sortedA);
+            CU(cudaGetLastError());
+        }
+        else
+        {
+            const unsigned nkA = (unsigned)nslab << (3 * bits), nkB = 1u << (3 * bits);
+            if (!a.d_keysA) CU(cudaMalloc(&a.d_keysA, sizeof(int) * (size_t)p.n0 * c->maxK));
+            if (!a.d_keysB) CU(cudaMalloc(&a.d_keysB, sizeof(int) * (size_t)p.n1 * c->maxK));
+            if (!a.d_sortedB) CU(cudaMalloc(&a.d_sortedB, sizeof(int4) * (size_t)p.n1 * c->maxK));
+            if (a.cap_keysA < nkA) { cudaFree(a.d_cellA); a.d_cellA = nullptr; CU(cudaMalloc(&a.d_cellA, sizeof(unsigned) * 3 * (size_t)(nkA + 1) * c->maxK)); a.cap_keysA = nkA; }
+            if (a.cap_keysB < nkB) { cudaFree(a.d_cellB); a.d_cellB = nullptr; CU(cudaMalloc(&a.d_cellB, sizeof(unsigned) * 3 * (size_t)(nkB + 1) * c->maxK)); a.cap_keysB = nkB; }
+            const size_t szA = (size_t)(nkA + 1) * c->maxK, szB = (size_t)(nkB + 1) * c->maxK;
+            unsigned *cntA = a.d_cellA, *stA = a.d_cellA + szA, *curA = a.d_cellA + 2 * szA;
+            unsigned *cntB = a.d_cellB, *stB = a.d_cellB + szB, *curB = a.d_cellB + 2 * szB;
+            CU(cudaMemsetAsync(a.d_cellA, 0, sizeof(unsigned) * 3 * szA, c->stream));
+            CU(cudaMemsetAsync(a.d_cellB, 0, sizeof(unsigned) * 3 * szB, c->stream));
+            dim3 gridB((p.n1 + 255) / 256, c->nframes);
+            k3_cell_keys<<<grid, 256, 0, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, bits, nkA, a.d_keysA, cntA);
+            k3_cell_keys<<<gridB, 256, 0, c->stream>>>(g1->d_fix[s.com1], nullptr, c->nframes, p.n1, bits, nkB, a.d_keysB, cntB);
+            k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cntA, nkA, stA);
+            k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cntB, nkB, stB);
+            k3_cell_scatter<<<grid, 256, 0, c->stream>>>(g0->d_fix[s.com0], a.d_keysA, c->nframes, p.n0, nkA, stA, curA, a.d_sortedA);
+            k3_cell_scatter<<<gridB, 256, 0, c->stream>>>(g1->d_fix[s.com1], a.d_keysB, c->nframes, p.n1, nkB, stB, curB, a.d_sortedB);
+            CU(cudaGetLastError());
+            cd.bits = bits; cd.rx = reach[0]; cd.ry = reach[1]; cd.rz = reach[2];
+            cd.nkeysA = nkA; cd.nkeysB = nkB; cd.startA = stA; cd.startB = stB; cd.sortedB = a.d_sortedB;
+        }
     }
 
-    // tiling: TI molecules of one slab per block
-    constexpr int TI = 8 * 128;
     Timed tm(c, 2);
+    if (cells)
+    {
+        RdfDev pc = p;
+        pc.sym_enabled = 0;
+        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA, 1, c->nframes), cubic);
+    }
+    constexpr int TI = 8 * 128;   // TI molecules of one slab per block
     {
         // full mode: j split so that the grid covers the machine several times
         const int max_tiles = (p.n0 + TI - 1) / TI + std::min(nslab, p.n0);
         const int itiles    = std::max(1, (p.n0 + TI - 1) / TI);
         int       jsplit    = std::max(1, (c->sm_count * 24 + itiles * c->nframes - 1) / (itiles * c->nframes));
         jsplit              = std::min(jsplit, std::max(1, (p.n1 + kTileJ - 1) / kTileJ));
-        p.jsplit            = jsplit;
         p.jchunk            = (p.n1 + jsplit - 1) / jsplit;
         p.jchunk            = ((p.jchunk + kTileJ - 1) / kTileJ) * kTileJ;
         p.jsplit            = (p.n1 + p.jchunk - 1) / p.jchunk;
-        if (int rc = dispatch_rdf<false>(c, a, *g0, *g1, p, smem, dim3(max_tiles, p.jsplit, c->nframes), clamp, cubic)) return rc;
+        if (int rc = dispatch_rdf<8, 0>(c, a, *g0, *g1, p, cd, smem, dim3(max_tiles, p.jsplit, c->nframes), cubic)) return rc;
     }
     if (p.sym_enabled)
     {
@@ -657,7 +746,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         const int T = (p.n0 + TI - 1) / TI;
         long long items = 0;
         for (int t = 0; t < T; ++t) items += 1 + (std::max(0, p.n0 - (t + 1) * TI) + ps.jchunk - 1) / ps.jchunk;
-        if (int rc = dispatch_rdf<true>(c, a, *g0, *g1, ps, smem, dim3((unsigned)items, 1, c->nframes), clamp, cubic)) return rc;
+        if (int rc = dispatch_rdf<8, 1>(c, a, *g0, *g1, ps, cd, smem, dim3((unsigned)items, 1, c->nframes), cubic)) return rc;
     }
     return B2A_OK;
 }

@@ -232,19 +232,95 @@ __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
     }
 }
 
+// ---- cell mode prep (r_max << L): counting sort of both groups by cell ---------------------------------
+// Cells are the top `bits` bits of the fixed-point box fractions, so the cell of a molecule costs three shifts and the
+// periodic wrap of cell indices is a mask.  key = slab * nc^3 + (cx * nc + cy) * nc + cz  (z fastest: the neighbour cells
+// of one (x, y) column are one or two contiguous runs of the sorted array).
+__global__ void __launch_bounds__(256) k3_cell_keys(const int4* __restrict__ fix, const int* __restrict__ slab_id, int nframes,
+                                                    int n, int bits, unsigned nkeys, int* __restrict__ keys,
+                                                    unsigned* __restrict__ counts)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || f >= nframes) return;
+    const int4     v  = fix[(size_t)f * n + i];
+    const unsigned sh = 32u - (unsigned)bits;
+    const unsigned cx = (unsigned)v.x >> sh, cy = (unsigned)v.y >> sh, cz = (unsigned)v.z >> sh;
+    const unsigned cell = (((cx << bits) | cy) << bits) | cz;
+    int            key  = (int)cell;
+    if (slab_id)
+    {
+        const int s = slab_id[(size_t)f * n + i];
+        key         = s < 0 ? -1 : (int)((unsigned)s << (3 * bits) | cell);
+    }
+    keys[(size_t)f * n + i] = key;
+    if (key >= 0) atomicAdd(&counts[(size_t)f * (nkeys + 1) + key], 1u);
+}
+
+// exclusive scan of counts[f][0..nkeys) -> starts[f][0..nkeys]; one block per frame
+__global__ void __launch_bounds__(1024) k3_cell_scan(const unsigned* __restrict__ counts, unsigned nkeys, unsigned* __restrict__ starts)
+{
+    __shared__ unsigned part[1024];
+    const unsigned* c = counts + (size_t)blockIdx.x * (nkeys + 1);
+    unsigned*       o = starts + (size_t)blockIdx.x * (nkeys + 1);
+    const unsigned  chunk = (nkeys + 1023u) / 1024u;
+    const unsigned  b0 = threadIdx.x * chunk, b1 = min(nkeys, b0 + chunk);
+    unsigned        sum = 0;
+    for (unsigned k = b0; k < b1; ++k) sum += c[k];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1)
+    {
+        const unsigned v = threadIdx.x >= (unsigned)off ? part[threadIdx.x - off] : 0u;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned run = part[threadIdx.x] - sum;   // exclusive prefix of this thread's chunk
+    for (unsigned k = b0; k < b1; ++k) { o[k] = run; run += c[k]; }
+    if (threadIdx.x == 1023) o[nkeys] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) k3_cell_scatter(const int4* __restrict__ fix, const int* __restrict__ keys, int nframes,
+                                                       int n, unsigned nkeys, const unsigned* __restrict__ starts,
+                                                       unsigned* __restrict__ cursor, int4* __restrict__ sorted)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || f >= nframes) return;
+    const int key = keys[(size_t)f * n + i];
+    if (key < 0) return;
+    const unsigned pos = starts[(size_t)f * (nkeys + 1) + key] + atomicAdd(&cursor[(size_t)f * (nkeys + 1) + key], 1u);
+    int4           v   = fix[(size_t)f * n + i];
+    v.w                = i;
+    sorted[(size_t)f * n + pos] = v;
+}
+
+struct CellDev   // cell mode parameters (by value)
+{
+    int             bits;          // cells per dimension = 1 << bits
+    int             rx, ry, rz;    // neighbour reach in cells per dimension (covers Rm plus the fixed-point slop)
+    unsigned        nkeysA, nkeysB;
+    const unsigned* startA;        // [frame][nkeysA + 1]
+    const unsigned* startB;        // [frame][nkeysB + 1]
+    const int4*     sortedB;       // [frame][n1]
+};
+
 // ---- main kernel ------------------------------------------------------------------------------------------
-// full mode : grid x = i-tile (over slabs), y = j-split, z = frame
-// SYM mode  : grid x = work item (i-tile, j-chunk beyond the tile | diagonal), z = frame; frames that are not
-//             eligible (not all molecules in one slab) are skipped here and done by the full kernel, and vice versa.
-template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, bool SYM>
+// MODE 0 (full) : grid x = i-tile (over slabs), y = j-split, z = frame
+// MODE 1 (sym)  : grid x = work item (i-tile, j-chunk beyond the tile | diagonal), z = frame; frames that are not
+//                 eligible (not all molecules in one slab) are skipped here and done by the full kernel, and vice versa
+// MODE 2 (cell) : grid x = (slab, cell) key of the i side, z = frame; j runs over the neighbouring cells only
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, int MODE>
 __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
                                                   const double* __restrict__ cenA, const double* __restrict__ cenB,
                                                   const unsigned* __restrict__ slab_cnt,
-                                                  const RdfFrame* __restrict__ frames, RdfDev p,
+                                                  const RdfFrame* __restrict__ frames, RdfDev p, CellDev cd,
                                                   unsigned long long* __restrict__ ghist,
                                                   unsigned long long* __restrict__ gstats)
 {
-    constexpr int TI = IPT * THREADS;
+    constexpr int  TI  = IPT * THREADS;
+    constexpr bool SYM = MODE == 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int4*     sj    = reinterpret_cast<int4*>(smem_raw);                                   // kTileJ
     unsigned* queue = reinterpret_cast<unsigned*>(smem_raw + kTileJ * sizeof(int4));       // kQueueCap
@@ -253,58 +329,75 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
     __shared__ RdfBlock blk;
 
     const int f = blockIdx.z;
-    // is this frame eligible for symmetric evaluation?  (every molecule passed the filter into ONE slab)
-    int sym_slab = -1;
-    if (p.sym_enabled)
-        for (int s = 0; s < p.nslab; ++s)
-            if (slab_cnt[(size_t)f * p.nslab + s] == (unsigned)p.n0) sym_slab = s;
-    if (SYM != (sym_slab >= 0)) return;   // block-uniform
-
-    int slab = -1, tstart = 0, tcount = 0, j0 = 0, j1 = 0, weight = 1;
-    if (SYM)
+    int       slab = -1, tstart = 0, tcount = 0, j0 = 0, j1 = 0, weight = 1;
+    int       cell_a0 = 0, cell_a1 = 0, ccx = 0, ccy = 0, ccz = 0;
+    if (MODE != 2)
     {
-        // work items in order: for tile t = 0..T-1 : [diagonal], then chunks of [(t+1)*TI, n0)
-        const int T = (p.n0 + TI - 1) / TI;
-        int       w = blockIdx.x;
-        for (int t = 0; t < T; ++t)
+        // is this frame eligible for symmetric evaluation?  (every molecule passed the filter into ONE slab)
+        int sym_slab = -1;
+        if (p.sym_enabled)
+            for (int s = 0; s < p.nslab; ++s)
+                if (slab_cnt[(size_t)f * p.nslab + s] == (unsigned)p.n0) sym_slab = s;
+        if (SYM != (sym_slab >= 0)) return;   // block-uniform
+        if (SYM)
         {
-            const int beyond = max(0, p.n0 - (t + 1) * TI);
-            const int nch    = (beyond + p.jchunk - 1) / p.jchunk;
-            if (w < 1 + nch)
+            // work items in order: for tile t = 0..T-1 : [diagonal], then chunks of [(t+1)*TI, n0)
+            const int T = (p.n0 + TI - 1) / TI;
+            int       w = blockIdx.x;
+            for (int t = 0; t < T; ++t)
             {
-                slab = sym_slab; tstart = t * TI; tcount = min(TI, p.n0 - tstart);
-                if (w == 0) { j0 = tstart; j1 = tstart + tcount; weight = 1; }
-                else { j0 = (t + 1) * TI + (w - 1) * p.jchunk; j1 = min(p.n0, j0 + p.jchunk); weight = 2; }
-                break;
+                const int beyond = max(0, p.n0 - (t + 1) * TI);
+                const int nch    = (beyond + p.jchunk - 1) / p.jchunk;
+                if (w < 1 + nch)
+                {
+                    slab = sym_slab; tstart = t * TI; tcount = min(TI, p.n0 - tstart);
+                    if (w == 0) { j0 = tstart; j1 = tstart + tcount; weight = 1; }
+                    else { j0 = (t + 1) * TI + (w - 1) * p.jchunk; j1 = min(p.n0, j0 + p.jchunk); weight = 2; }
+                    break;
+                }
+                w -= 1 + nch;
             }
-            w -= 1 + nch;
         }
+        else
+        {
+            int      t   = blockIdx.x;
+            unsigned off = 0;
+            for (int s = 0; s < p.nslab; ++s)
+            {
+                const unsigned c  = slab_cnt[(size_t)f * p.nslab + s];
+                const int      nt = (int)((c + TI - 1) / TI);
+                if (t < nt) { slab = s; tstart = (int)off + t * TI; tcount = min(TI, (int)c - t * TI); break; }
+                t -= nt;
+                off += c;
+            }
+            j0 = blockIdx.y * p.jchunk;
+            j1 = min(p.n1, j0 + p.jchunk);
+        }
+        if (slab < 0 || j1 <= j0) return;   // block-uniform
     }
     else
     {
-        int      t   = blockIdx.x;
-        unsigned off = 0;
-        for (int s = 0; s < p.nslab; ++s)
-        {
-            const unsigned c  = slab_cnt[(size_t)f * p.nslab + s];
-            const int      nt = (int)((c + TI - 1) / TI);
-            if (t < nt) { slab = s; tstart = (int)off + t * TI; tcount = min(TI, (int)c - t * TI); break; }
-            t -= nt;
-            off += c;
-        }
-        j0 = blockIdx.y * p.jchunk;
-        j1 = min(p.n1, j0 + p.jchunk);
+        const unsigned  key = blockIdx.x;
+        const unsigned* sa  = cd.startA + (size_t)f * (cd.nkeysA + 1);
+        cell_a0 = (int)sa[key];
+        cell_a1 = (int)sa[key + 1];
+        if (cell_a1 <= cell_a0) return;     // empty (slab, cell): block-uniform
+        const unsigned mask = (1u << cd.bits) - 1u;
+        slab = (int)(key >> (3 * cd.bits));
+        ccz  = (int)(key & mask);
+        ccy  = (int)((key >> cd.bits) & mask);
+        ccx  = (int)((key >> (2 * cd.bits)) & mask);
+        tstart = cell_a0;
+        tcount = min(TI, cell_a1 - cell_a0);
     }
-    if (slab < 0 || j1 <= j0) return;   // block-uniform
 
     const RdfFrame fr = frames[f];
-    const int4*    A  = sortedA + (size_t)f * p.n0 + tstart;
-    const int4*    B  = SYM ? sortedA + (size_t)f * p.n0 : fixB + (size_t)f * p.n1;
+    const int4*    B  = MODE == 1 ? sortedA + (size_t)f * p.n0 : (MODE == 2 ? cd.sortedB + (size_t)f * p.n1 : fixB + (size_t)f * p.n1);
     for (unsigned k = threadIdx.x; k < p.kstride; k += THREADS) hist[(int)k - 1] = 0;
     if (threadIdx.x == 0)
     {
         q_count[0] = q_count[1] = 0;
-        blk.A = A; blk.Bsorted = SYM ? B : nullptr;
+        blk.A = sortedA + (size_t)f * p.n0 + tstart; blk.Bsorted = MODE != 0 ? B : nullptr;
         blk.cA = cenA + (size_t)f * 3 * p.n0;
         blk.cB = cenB + (size_t)f * 3 * p.n1;
         blk.hist = hist; blk.tcount = tcount; blk.n0 = p.n0; blk.n1 = p.n1; blk.Rbin = p.Rbin;
@@ -321,98 +414,149 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
     const float    r2max   = fr.r2max;
     const float    s_lo = fr.s_lo, s_hi = fr.s_hi, ay = fr.ay, az = fr.az;
     const unsigned lowk = fr.lowk_bits;
-    const bool     partial = tcount < TI;
 
-    int xi[IPT], yi[IPT], zi[IPT];
-#pragma unroll
-    for (int q = 0; q < IPT; ++q)
-    {
-        const int  il = threadIdx.x + q * THREADS;
-        const int4 a  = il < tcount ? A[il] : make_int4(0, 0, 0, 0);
-        xi[q] = a.x; yi[q] = a.y; zi[q] = a.z;
-    }
+    int                xi[IPT], yi[IPT], zi[IPT];
+    int                sub = 0;   // sub-tile counter: selects the ping-pong queue counter
+    unsigned long long npairs = 0, nsel = 0;
 
-    int sub = 0;   // sub-tile counter: selects the ping-pong queue counter
-    for (int jt = j0; jt < j1; jt += kTileJ)
-    {
-        __syncthreads();
-        const int cnt = min(kTileJ, j1 - jt);
-        for (int t = threadIdx.x; t < cnt; t += THREADS) sj[t] = B[jt + t];
-        __syncthreads();
-        for (int js = 0; js < cnt; js += kSubJ, ++sub)
+    // stream the j-molecules [ja, jb) of B against the i-molecules currently held in registers
+    auto process_range = [&](int ja, int jb) {
+        const bool partial = tcount < TI;
+        for (int jt = ja; jt < jb; jt += kTileJ)
         {
-            const int je = min(cnt, js + kSubJ);
-            unsigned* qc = &q_count[sub & 1];
-            if (!partial)
+            __syncthreads();
+            const int cnt = min(kTileJ, jb - jt);
+            for (int t = threadIdx.x; t < cnt; t += THREADS) sj[t] = B[jt + t];
+            __syncthreads();
+            for (int js = 0; js < cnt; js += kSubJ, ++sub)
             {
+                const int je = min(cnt, js + kSubJ);
+                unsigned* qc = &q_count[sub & 1];
+                if (!partial)
+                {
 #pragma unroll 2
-                for (int j = js; j < je; ++j)
-                {
-                    const int4 pj   = sj[j];
-                    unsigned   dacc = 0, kmin = 0xffffffffu;
+                    for (int j = js; j < je; ++j)
+                    {
+                        const int4 pj   = sj[j];
+                        unsigned   dacc = 0, kmin = 0xffffffffu;
 #pragma unroll
-                    for (int q = 0; q < IPT; ++q)
-                    {
-                        unsigned k1, k2;
-                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
-                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1 * 4u + cb_ok) : "memory");
-                        dacc += k2 - k1;
-                        kmin = min(kmin, k1);
-                    }
-                    if (PARANOID || dacc != 0 || kmin <= lowk)
-                    {
-                        const unsigned slot = atomicAdd(qc, 1u);
-                        if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
-                        else
+                        for (int q = 0; q < IPT; ++q)
                         {
-                            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
-                            atomicAdd(&blk.stats[3], 1u);
+                            unsigned k1, k2;
+                            pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
+                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1 * 4u + cb_ok) : "memory");
+                            dacc += k2 - k1;
+                            kmin = min(kmin, k1);
+                        }
+                        if (PARANOID || dacc != 0 || kmin <= lowk)
+                        {
+                            const unsigned slot = atomicAdd(qc, 1u);
+                            if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
+                            else
+                            {
+                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
+                                atomicAdd(&blk.stats[3], 1u);
+                            }
                         }
                     }
                 }
-            }
-            else
-            {
-                // last tile of a slab: lanes beyond tcount add into the trash word only
+                else
+                {
+                    // partial tile: lanes beyond tcount add into the trash word only
 #pragma unroll 1
-                for (int j = js; j < je; ++j)
-                {
-                    const int4 pj   = sj[j];
-                    unsigned   dacc = 0, kmin = 0xffffffffu;
+                    for (int j = js; j < je; ++j)
+                    {
+                        const int4 pj   = sj[j];
+                        unsigned   dacc = 0, kmin = 0xffffffffu;
 #pragma unroll
-                    for (int q = 0; q < IPT; ++q)
-                    {
-                        const bool ok = (int)(threadIdx.x + q * THREADS) < tcount;
-                        unsigned   k1, k2;
-                        pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
-                        const unsigned addr = ok ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
-                        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-                        dacc += ok ? (k2 - k1) : 0u;
-                        kmin = ok ? min(kmin, k1) : kmin;
-                    }
-                    if (PARANOID || dacc != 0 || kmin <= lowk)
-                    {
-                        const unsigned slot = atomicAdd(qc, 1u);
-                        if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
-                        else
+                        for (int q = 0; q < IPT; ++q)
                         {
-                            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
-                            atomicAdd(&blk.stats[3], 1u);
+                            const bool ok = (int)(threadIdx.x + q * THREADS) < tcount;
+                            unsigned   k1, k2;
+                            pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
+                            const unsigned addr = ok ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
+                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                            dacc += ok ? (k2 - k1) : 0u;
+                            kmin = ok ? min(kmin, k1) : kmin;
+                        }
+                        if (PARANOID || dacc != 0 || kmin <= lowk)
+                        {
+                            const unsigned slot = atomicAdd(qc, 1u);
+                            if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
+                            else
+                            {
+                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
+                                atomicAdd(&blk.stats[3], 1u);
+                            }
                         }
                     }
                 }
+                // drain: every queued (j, thread) candidate is re-examined by whichever thread picks it up
+                __syncthreads();
+                const unsigned n = min(*qc, (unsigned)kQueueCap);
+                for (unsigned e = threadIdx.x; e < n; e += THREADS)
+                {
+                    const unsigned ent = queue[e];
+                    const int      jl  = (int)(ent >> 16);
+                    recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, (int)(ent & 0xffffu), sj[jl], jt + jl);
+                }
+                if (threadIdx.x == 0) q_count[(sub + 1) & 1] = 0;   // the other counter was drained one sub-tile ago
+                __syncthreads();
             }
-            // drain: every queued (j, thread) candidate is re-examined by whichever thread picks it up
-            __syncthreads();
-            const unsigned n = min(*qc, (unsigned)kQueueCap);
-            for (unsigned e = threadIdx.x; e < n; e += THREADS)
-            {
-                const unsigned ent = queue[e];
-                const int      jl  = (int)(ent >> 16);
-                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, (int)(ent & 0xffffu), sj[jl], jt + jl);
-            }
-            if (threadIdx.x == 0) q_count[(sub + 1) & 1] = 0;   // the other counter was drained one sub-tile ago
-            __syncthreads();
+        }
+        npairs += (unsigned long long)tcount * (unsigned long long)(jb > ja ? jb - ja : 0);
+    };
+
+    auto load_tile = [&]() {
+        const int4* A = sortedA + (size_t)f * p.n0 + tstart;
+#pragma unroll
+        for (int q = 0; q < IPT; ++q)
+        {
+            const int  il = threadIdx.x + q * THREADS;
+            const int4 a  = il < tcount ? A[il] : make_int4(0, 0, 0, 0);
+            xi[q] = a.x; yi[q] = a.y; zi[q] = a.z;
+        }
+    };
+
+    if (MODE != 2)
+    {
+        load_tile();
+        process_range(j0, j1);
+        nsel = SYM ? (weight == 1 ? tcount : 0) : (blockIdx.y == 0 ? tcount : 0);
+    }
+    else
+    {
+        const int       nc   = 1 << cd.bits;
+        const unsigned* sb   = cd.startB + (size_t)f * (cd.nkeysB + 1);
+        // distinct neighbour columns: if the reach covers the whole axis, visit every cell of that axis once
+        const int nx = min(2 * cd.rx + 1, nc), ny = min(2 * cd.ry + 1, nc);
+        for (; tstart < cell_a1; tstart += TI)
+        {
+            tcount = min(TI, cell_a1 - tstart);
+            __syncthreads();   // previous sub-tile's drain may still read blk.A / blk.tcount
+            if (threadIdx.x == 0) { blk.A = sortedA + (size_t)f * p.n0 + tstart; blk.tcount = tcount; }
+            load_tile();
+            nsel += tcount;
+            for (int ix = 0; ix < nx; ++ix)
+                for (int iy = 0; iy < ny; ++iy)
+                {
+                    const int      cx  = (ccx - (nx >> 1) + ix + nc) & (nc - 1);
+                    const int      cy  = (ccy - (ny >> 1) + iy + nc) & (nc - 1);
+                    const unsigned col = ((unsigned)cx << cd.bits | (unsigned)cy) << cd.bits;
+                    if (2 * cd.rz + 1 >= nc) { process_range((int)sb[col], (int)sb[col + nc]); continue; }
+                    const int z0 = ccz - cd.rz, z1 = ccz + cd.rz;     // inclusive, may leave [0, nc)
+                    if (z0 < 0)
+                    {
+                        process_range((int)sb[col + z0 + nc], (int)sb[col + nc]);
+                        process_range((int)sb[col], (int)sb[col + z1 + 1]);
+                    }
+                    else if (z1 >= nc)
+                    {
+                        process_range((int)sb[col + z0], (int)sb[col + nc]);
+                        process_range((int)sb[col], (int)sb[col + z1 - nc + 1]);
+                    }
+                    else process_range((int)sb[col + z0], (int)sb[col + z1 + 1]);
+                }
         }
     }
     __syncthreads();
@@ -428,8 +572,8 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
         if (blk.stats[1]) atomicAdd(&gstats[3], (unsigned long long)blk.stats[1] * (unsigned long long)weight);
         if (blk.stats[2]) atomicAdd(&gstats[1], (unsigned long long)blk.stats[2] * (unsigned long long)weight);
         if (blk.stats[3]) atomicAdd(&gstats[6], (unsigned long long)blk.stats[3]);
-        atomicAdd(&gstats[5], (unsigned long long)tcount * (unsigned long long)(j1 - j0));
-        if (SYM ? (weight == 1) : (blockIdx.y == 0)) atomicAdd(&gstats[4], (unsigned long long)tcount);
+        atomicAdd(&gstats[5], npairs);
+        if (nsel) atomicAdd(&gstats[4], nsel);
     }
 }
 

@@ -348,3 +348,58 @@ def test_dipole_orientation_config4_shape(gpu_ctx_factory):
     ctx.accumulate(acc)
     got, st = ctx.read(acc, 90 + 1)
     assert np.array_equal(got[:90].reshape(90, 1), exp_o) and got[90] == exp_n[0] == 5000 * K
+
+
+# ---- cell-binned RDF: identical counts to the all-pairs evaluation ---------------------------------
+def _rdf_gpu_cells(ctx, system, g0, g1, K, spec, Rm, Rbin, cells, paranoid=0, symmetric=0):
+    _groups(ctx, system, [g0, g1])
+    acc = ctx.rdf_create(grp0=0, grp1=1, com0=spec["com"], com1=spec["com"], nbin=spec["nbin"], low=spec["low"], up=spec["up"],
+                         dim=spec["dim"], dim2=spec["dim2"], low2=spec["low2"], up2=spec["up2"], Rm=Rm, Rbin=Rbin)
+    ctx.rdf_tune(acc, symmetric, paranoid)
+    ctx.rdf_cells(acc, cells)
+    ctx.submit(system.frames(0, K), system.box9())
+    ctx.accumulate(acc)
+    got, st = ctx.read(acc, spec["nbin"] * Rbin)
+    return got.reshape(Rbin, spec["nbin"]), st
+
+
+@pytest.mark.parametrize("case", [
+    dict(sys=("water", 4000, 4.93), g=("OW", "OW"), K=2, Rm=0.6),
+    dict(sys=("il", 3000, 9.9), g=("CAT", "ANI"), K=2, Rm=0.9, nbin=3, low=0.5, up=9.0, dim=1, dim2=0, low2=0.3, up2=9.5),
+    dict(sys=("il", 4000, 10.9), g=("ANI", "ANI"), K=1, Rm=1.4, com=1),
+    dict(sys=("water", 3500, 4.7), g=("OW", "OW"), K=1, Rm=0.5, paranoid=1),
+    dict(sys=("il", 3500, 9.0), g=("CAT", "ANI"), K=2, Rm=0.8, box=(9.0, 7.0, 11.0)),
+])
+def test_rdf_cell_mode_bit_exact(gpu_ctx_factory, case):
+    kind, n, L = case["sys"]
+    system = synth.water_box(n, L, seed=81, split_atoms=True) if kind == "water" else synth.ionic_liquid(n, L, seed=82)
+    if "box" in case:
+        system.L = np.array(case["box"], np.float32)
+    spec = dict(_DEF)
+    spec.update({k: v for k, v in case.items() if k in _DEF})
+    K = case["K"]
+    exp, est, Rm, Rbin = refprog.oracle_rdf_region(system, K, case["g"][0], case["g"][1], return_counts=True, **spec)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    got, st = _rdf_gpu_cells(ctx, system, case["g"][0], case["g"][1], K, spec, Rm, Rbin, cells=1, paranoid=case.get("paranoid", 0))
+    assert np.array_equal(got, exp)
+    assert int(st[lib.STAT_DROPPED]) == int(est[1]) and int(st[lib.STAT_SELECTED]) == int(est[2])
+    n0 = len(refprog.group_info(system, case["g"][0])["index"]) // refprog.group_info(system, case["g"][0])["napm"]
+    n1 = len(refprog.group_info(system, case["g"][1])["index"]) // refprog.group_info(system, case["g"][1])["napm"]
+    assert int(st[lib.STAT_PAIRS]) < n0 * n1 * K          # cells were really used: fewer pairs evaluated than all-pairs
+
+
+def test_rdf_cells_equal_brute_force_large(gpu_ctx_factory):
+    """The reference's own check pattern (src/test/nb_cellSearch_anyBoxSize.cpp:288-299): accelerated structure ==
+    brute force, exact integer equality, on a config-5-like box (r_max << L) too large for the CPU oracle."""
+    n, L = 150000, 16.5
+    system = synth.water_box(n, L, seed=20200105, split_atoms=True)
+    Rm, spec = refprog.f32(1.5), dict(_DEF)
+    Rbin = port.rdf_rbin(Rm)
+    res = {}
+    for cells in (0, 1):
+        ctx = gpu_ctx_factory(system.natoms, 1)
+        res[cells] = _rdf_gpu_cells(ctx, system, "OW", "OW", 1, spec, Rm, Rbin, cells=cells, symmetric=1 - cells)
+        ctx.close()
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][0].sum() > 0
+    assert int(res[1][1][lib.STAT_PAIRS]) * 4 < int(res[0][1][lib.STAT_PAIRS])     # cells evaluate far fewer pairs
+    assert int(res[0][1][lib.STAT_DROPPED]) == int(res[1][1][lib.STAT_DROPPED])
