@@ -724,7 +724,10 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     {
         RdfDev pc = p;
         pc.sym_enabled = 0;
-        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA, 1, c->nframes), cubic);
+        // crowded i-cells (i side much denser than the cell grid was sized for) are split over gridDim.y
+        const double per_cell = (double)p.n0 / (double)(1u << (3 * bits));
+        const int    ny       = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_cell / (kCellIPT * 128))));
+        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA, ny, c->nframes), cubic);
     }
     constexpr int TI = 8 * 128;   // TI molecules of one slab per block
     {

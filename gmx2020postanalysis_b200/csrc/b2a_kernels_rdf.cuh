@@ -387,8 +387,9 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
         ccz  = (int)(key & mask);
         ccy  = (int)((key >> cd.bits) & mask);
         ccx  = (int)((key >> (2 * cd.bits)) & mask);
-        tstart = cell_a0;
-        tcount = min(TI, cell_a1 - cell_a0);
+        tstart = cell_a0 + (int)blockIdx.y * TI;   // sub-tiles of a crowded cell are spread over gridDim.y blocks
+        if (tstart >= cell_a1) return;
+        tcount = min(TI, cell_a1 - tstart);
     }
 
     const RdfFrame fr = frames[f];
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
         const unsigned* sb   = cd.startB + (size_t)f * (cd.nkeysB + 1);
         // distinct neighbour columns: if the reach covers the whole axis, visit every cell of that axis once
         const int nx = min(2 * cd.rx + 1, nc), ny = min(2 * cd.ry + 1, nc);
-        for (; tstart < cell_a1; tstart += TI)
+        for (; tstart < cell_a1; tstart += TI * (int)gridDim.y)
         {
             tcount = min(TI, cell_a1 - tstart);
             __syncthreads();   // previous sub-tile's drain may still read blk.A / blk.tcount

@@ -160,3 +160,21 @@ def ionic_liquid(npairs: int, L: float, seed: int = 20200103) -> System:
     sysm.groups = {"CAT": np.arange(nc, dtype=np.int32), "ANI": np.arange(nc, nc + 7 * npairs, dtype=np.int32),
                    "System": np.arange(nc + 7 * npairs, dtype=np.int32)}
     return sysm
+
+
+def mixed_box(n_water: int = 1200000, n_cat: int = 8000, n_ani: int = 8000, n_cos: int = 24000, L: float = 34.0,
+              seed: int = 20200105) -> System:
+    """Config C5: 1.2 M water + 8 000 cation (25 sites) + 8 000 anion (7) + 24 000 six-site cosolvent
+    = 4 000 000 atoms at the defaults.  Groups: SOL, CAT, ANI, COS."""
+    il = ionic_liquid(1, 1.0)
+    cat_t, ani_t = il.species[0], il.species[1]
+    water = Species("SOL", n_water, _SPCE_TMPL, _SPCE_MASS, _SPCE_Q, ["OW", "HW1", "HW2"])
+    cat = Species("CAT", n_cat, cat_t.tmpl, cat_t.mass, cat_t.charge, cat_t.atomnames)
+    ani = Species("ANI", n_ani, ani_t.tmpl, ani_t.mass, ani_t.charge, ani_t.atomnames)
+    cm = np.array([12.011, 12.011, 15.9994, 1.008, 1.008, 1.008], dtype=np.float32)
+    cq = np.array([0.1, -0.2, -0.5, 0.2, 0.2, 0.2], dtype=np.float32)
+    cos = Species("COS", n_cos, _blob_template(6, 0.18, 7003), cm, cq, [f"S{j}" for j in range(6)])
+    sysm = System([water, cat, ani, cos], np.array([L, L, L], np.float32), seed)
+    off = sysm.offsets()
+    sysm.groups = {s.name: np.arange(o, o + s.nmol * s.napm, dtype=np.int32) for s, o in zip(sysm.species, off)}
+    return sysm
