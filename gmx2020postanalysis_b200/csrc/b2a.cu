@@ -83,6 +83,12 @@ struct Group
     int     ngx = 0, napm = 0, nmol = 0;
     int*    d_index = nullptr;
     std::vector<int> h_index;
+    // heterogeneous molecule sizes (GmxHandleFull): CSR offsets, per-atom weights, per-molecule totals
+    bool      csr = false;
+    int       max_napm = 0;
+    int*      d_off = nullptr; int* d_mol_of = nullptr;
+    double*   d_wfull[4] = { nullptr, nullptr, nullptr, nullptr };
+    DivConst* d_div[4]   = { nullptr, nullptr, nullptr, nullptr };
     bool    contiguous = false;   // index[n] == index[0] + n: a block's molecules are one byte range per frame (TMA path)
     double* d_w[4]  = { nullptr, nullptr, nullptr, nullptr };   // mass, ones, charge, charge(dipole)
     double  wsum[4] = { 0, 0, 0, 0 };
@@ -206,7 +212,8 @@ extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
 static void free_group(Group& g)
 {
     cudaFree(g.d_index);
-    for (int k = 0; k < 4; ++k) { cudaFree(g.d_w[k]); cudaFree(g.d_cen[k]); cudaFree(g.d_fix[k]); }
+    for (int k = 0; k < 4; ++k) { cudaFree(g.d_w[k]); cudaFree(g.d_cen[k]); cudaFree(g.d_fix[k]); cudaFree(g.d_wfull[k]); cudaFree(g.d_div[k]); }
+    cudaFree(g.d_off); cudaFree(g.d_mol_of);
     g = Group();
 }
 
@@ -290,6 +297,62 @@ extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int
     return B2A_OK;
 }
 
+extern "C" int b2a_set_group_full(b2a_ctx* c, int grp, const int* index, int ngx, int nmol, const int* napm, const double* mass,
+                                  const double* charge)
+{
+    if (!c || !index || !napm || !mass || !charge) return fail(B2A_ERR_ARG, "b2a_set_group_full: null argument");
+    if (grp < 0 || ngx <= 0 || nmol <= 0) return fail(B2A_ERR_ARG, "b2a_set_group_full: bad sizes");
+    std::vector<int> off(nmol + 1, 0), mol_of(ngx);
+    int              maxn = 0;
+    for (int i = 0; i < nmol; ++i)
+    {
+        if (napm[i] <= 0) return fail(B2A_ERR_ARG, "b2a_set_group_full: molecule %d has no atoms", i);
+        off[i + 1] = off[i] + napm[i];
+        maxn       = std::max(maxn, napm[i]);
+    }
+    if (off[nmol] != ngx) return fail(B2A_ERR_ARG, "b2a_set_group_full: sum of napm (%d) differs from the group size (%d)", off[nmol], ngx);
+    for (int i = 0; i < nmol; ++i)
+    {
+        const int m = index[off[i]];
+        if (m < 0 || m + napm[i] > c->natoms) return fail(B2A_ERR_ARG, "b2a_set_group_full: atom index out of range in molecule %d", i);
+        for (int n = off[i]; n < off[i + 1]; ++n) mol_of[n] = i;
+    }
+    for (int n = 0; n < ngx; ++n)
+        if (index[n] < 0 || index[n] >= c->natoms) return fail(B2A_ERR_ARG, "b2a_set_group_full: atom index %d out of range", index[n]);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    Group& g = c->groups[grp];
+    free_group(g);
+    g.ngx = ngx; g.napm = 0; g.nmol = nmol; g.csr = true; g.max_napm = maxn;
+    g.h_index.assign(index, index + ngx);
+    CU(cudaMalloc(&g.d_index, sizeof(int) * ngx));
+    CU(cudaMemcpy(g.d_index, index, sizeof(int) * ngx, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&g.d_off, sizeof(int) * (nmol + 1)));
+    CU(cudaMemcpy(g.d_off, off.data(), sizeof(int) * (nmol + 1), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&g.d_mol_of, sizeof(int) * ngx));
+    CU(cudaMemcpy(g.d_mol_of, mol_of.data(), sizeof(int) * ngx, cudaMemcpyHostToDevice));
+    std::vector<double> ones(ngx, 1.0);
+    const double*       src[4] = { mass, ones.data(), charge, charge };
+    for (int k = 0; k < 4; ++k)
+    {
+        // per-molecule totals, summed sequentially like totMass / totCharge (gmx_handle_full.ipp:337-340); geometry = napm
+        std::vector<DivConst> div(nmol);
+        for (int i = 0; i < nmol; ++i)
+        {
+            double t = 0.0;
+            for (int n = off[i]; n < off[i + 1]; ++n) t += src[k][n];
+            if (k == 1) t = (double)napm[i];
+            if (k == 3 && std::fabs(t) < 1e-6) t = 1.0;   // 9g_dist_bin_1803.cpp:221
+            div[i] = make_div(t);
+        }
+        CU(cudaMalloc(&g.d_wfull[k], sizeof(double) * ngx));
+        CU(cudaMemcpy(g.d_wfull[k], src[k], sizeof(double) * ngx, cudaMemcpyHostToDevice));
+        CU(cudaMalloc(&g.d_div[k], sizeof(DivConst) * nmol));
+        CU(cudaMemcpy(g.d_div[k], div.data(), sizeof(DivConst) * nmol, cudaMemcpyHostToDevice));
+    }
+    return B2A_OK;
+}
+
 static int get_group(b2a_ctx* c, int grp, Group** out)
 {
     auto it = c->groups.find(grp);
@@ -352,7 +415,7 @@ extern "C" int b2a_batch_frames(b2a_ctx* c) { return c ? c->nframes : -1; }
 // ---- TMA-staged streaming launch (contiguous groups) -----------------------------------------------------------
 static bool stream_block(const Group& g, int* M)
 {
-    if (!g.contiguous) return false;
+    if (!g.contiguous || g.csr) return false;
     if (const char* e = getenv("B2A_NO_TMA")) if (atoi(e)) return false;
     int m = (32768 / (g.napm * 12) / 32) * 32;   // <= 32 KB of coordinates per stage
     m     = std::min(m, 256);
@@ -391,6 +454,15 @@ static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
     (void)need_fix;
     if (g.valid[com] == c->serial) return B2A_OK;
     Timed tm(c, 0);
+    if (g.csr)
+    {
+        dim3 grid((g.nmol + 127) / 128, c->nframes);
+        k1_centers_csr<<<grid, 128, 0, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g.d_index, g.d_off, g.nmol, g.d_wfull[com],
+                                                    g.d_div[com], c->d_geom, g.d_cen[com], g.d_fix[com]);
+        CU(cudaGetLastError());
+        g.valid[com] = c->serial;
+        return B2A_OK;
+    }
     int   M = 0;
     if (stream_block(g, &M))
     {
@@ -444,7 +516,7 @@ extern "C" int b2a_positions(b2a_ctx* c, int grp, int frame, double* out)
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
     if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_positions: frame %d outside batch of %d", frame, c->nframes);
     CU(cudaSetDevice(c->device));
-    const size_t n = (size_t)g->nmol * g->napm;
+    const size_t n = (size_t)g->nmol * (g->csr ? g->max_napm : g->napm);
     if (c->pos_scratch_n < n)
     {
         CU(cudaStreamSynchronize(c->stream));
@@ -454,6 +526,13 @@ extern "C" int b2a_positions(b2a_ctx* c, int grp, int frame, double* out)
         c->pos_scratch_n = n;
     }
     const int threads = 256;
+    if (g->csr)
+    {
+        CU(cudaMemsetAsync(c->d_pos_scratch, 0, sizeof(double) * 3 * n, c->stream));   // slots j >= napm[i] read back as 0
+        k1b_positions_csr<<<(unsigned)((g->ngx + threads - 1) / threads), threads, 0, c->stream>>>(
+            c->d_x + (size_t)frame * c->natoms * 3, g->d_index, g->d_off, g->d_mol_of, g->ngx, g->nmol, c->h_geom[frame], c->d_pos_scratch);
+    }
+    else
     k1b_positions<<<(unsigned)((n + threads - 1) / threads), threads, 0, c->stream>>>(
         c->d_x + (size_t)frame * c->natoms * 3, g->d_index, g->nmol, g->napm, c->h_geom[frame], c->d_pos_scratch);
     CU(cudaGetLastError());
@@ -763,6 +842,15 @@ static int accumulate_density(b2a_ctx* c, Acc& a)
     DensityDev d{};
     d.dim = s.dim; d.dim2 = s.dim2; d.nbin = s.nbin; d.upper_inclusive = s.upper_inclusive;
     d.low = (double)s.low; d.up = (double)s.up; d.low2 = (double)s.low2; d.up2 = (double)s.up2; d.dbin = make_div(s.dbin);
+    if (g->csr)
+    {
+        if (int rc = ensure_centers(c, *g, s.com, false)) return rc;
+        Timed tm(c, 3);
+        dim3  grid((g->nmol + 255) / 256, c->nframes);
+        k2_density_from_centers<<<grid, 256, 0, c->stream>>>(g->d_cen[s.com], c->nframes, g->nmol, d, a.d_hist, a.d_hist + a.ndev);
+        CU(cudaGetLastError());
+        return B2A_OK;
+    }
     const int    threads   = 256;
     const int    smem_bins = s.nbin <= 24000 ? s.nbin : 0;
     int          M = 0;
@@ -923,6 +1011,7 @@ extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
     Group* g;
     if (int rc = get_group(c, s->grp, &g)) return rc;
     if (s->DIMN < 0 || s->DIMN > 2 || s->DIMNOrient < 0 || s->DIMNOrient > 2) return fail(B2A_ERR_ARG, "orient: dim out of range");
+    if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "orientation histogram on a heterogeneous (GmxHandleFull) group is not implemented");
     if (s->tp1 < 1 || s->tp2 < 1 || s->tp3 < 1 || s->tp1 > g->napm || s->tp2 > g->napm || s->tp3 > g->napm)
         return fail(B2A_ERR_ARG, "orient: tp1..3 must lie in 1..napm(%d)", g->napm);
     if (s->nAngle <= 0 || s->nAngle > 180) return fail(B2A_ERR_ARG, "orient: nAngle must be 1..180 (dAngle = 180 / nAngle is integer division)");
@@ -1006,6 +1095,7 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
     const b2a_orient_spec& s = a.ori;
     Group* g;
     if (int rc = get_group(c, s.grp, &g)) return rc;
+    if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "orientation histogram on a heterogeneous (GmxHandleFull) group is not implemented");
     OrientDev d{};
     d.DIMN = s.DIMN; d.nAngle = s.nAngle; d.nbin1 = a.nbin1; d.tp1 = s.tp1 - 1; d.tp2 = s.tp2 - 1; d.tp3 = s.tp3 - 1;
     d.DIMNOrient = s.DIMNOrient; d.method = s.method;

@@ -146,6 +146,55 @@ __global__ void __launch_bounds__(256) k1_centers(const float* __restrict__ x, s
     if (fix) fix[(size_t)f * nmol + i] = make_int4(to_fixed(c0, g.inv_unit[0]), to_fixed(c1, g.inv_unit[1]), to_fixed(c2, g.inv_unit[2]), i);
 }
 
+// ---- K1 for heterogeneous molecule sizes: GmxHandleFull::loadPositionCenter (reference
+// include/itp/gmx_bits/gmx_handle_full.ipp:150-199).  off[i] = first index position of molecule i, wfull[n] = weight of
+// the atom at index position n, div[i] = the molecule's own weight total (totMass / totCharge / napm, full.ipp:323-344)
+__global__ void __launch_bounds__(256) k1_centers_csr(const float* __restrict__ x, size_t frame_stride, int nframes,
+                                                      const int* __restrict__ index, const int* __restrict__ off, int nmol,
+                                                      const double* __restrict__ wfull, const DivConst* __restrict__ div,
+                                                      const FrameGeom* __restrict__ geom, double* __restrict__ cen,
+                                                      int4* __restrict__ fix)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmol || f >= nframes) return;
+    const FrameGeom g  = geom[f];
+    const int       o0 = __ldg(off + i), na = __ldg(off + i + 1) - o0;
+    const float*    p  = x + (size_t)f * frame_stride + (size_t)__ldg(index + o0) * 3;   // atoms are molN + j (full.ipp:187)
+    const double*   w  = wfull + o0;
+    const float     r0 = __ldg(p), r1 = __ldg(p + 1), r2 = __ldg(p + 2);
+    double          c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    for (int j = 0; j < na; ++j)
+    {
+        const double wj = __ldg(w + j);
+        c0 = __dadd_rn(c0, __dmul_rn(unwrap_f(__ldg(p + 3 * j), r0, g.L[0], g.half[0], g.hsafe[0]), wj));
+        c1 = __dadd_rn(c1, __dmul_rn(unwrap_f(__ldg(p + 3 * j + 1), r1, g.L[1], g.half[1], g.hsafe[1]), wj));
+        c2 = __dadd_rn(c2, __dmul_rn(unwrap_f(__ldg(p + 3 * j + 2), r2, g.L[2], g.half[2], g.hsafe[2]), wj));
+    }
+    const DivConst d = div[i];
+    c0 = div_const(c0, d); c1 = div_const(c1, d); c2 = div_const(c2, d);
+    double* o = cen + (size_t)f * 3 * nmol;
+    o[i]                    = c0;
+    o[(size_t)nmol + i]     = c1;
+    o[2 * (size_t)nmol + i] = c2;
+    if (fix) fix[(size_t)f * nmol + i] = make_int4(to_fixed(c0, g.inv_unit[0]), to_fixed(c1, g.inv_unit[1]), to_fixed(c2, g.inv_unit[2]), i);
+}
+
+// GmxHandleFull::loadPosition (full.ipp:115-148): pos is boxd(nmol, maxNapm); slots j >= napm[i] are not touched
+__global__ void __launch_bounds__(256) k1b_positions_csr(const float* __restrict__ xf, const int* __restrict__ index,
+                                                         const int* __restrict__ off, const int* __restrict__ mol_of, int ngx,
+                                                         int nmol, FrameGeom g, double* __restrict__ pos)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= ngx) return;
+    const int    i  = __ldg(mol_of + n), o0 = __ldg(off + i), j = n - o0;
+    const float* pr = xf + (size_t)__ldg(index + o0) * 3;
+    const float* pa = xf + (size_t)__ldg(index + n) * 3;
+    double*      o  = pos + ((size_t)i + (size_t)j * nmol) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] = unwrap_f(__ldg(pa + k), __ldg(pr + k), g.L[k], g.half[k], g.hsafe[k]);
+}
+
 // ---- K1b: unwrapped per-atom positions, GmxHandle::loadPosition (ipp:115-148) --------------------------------
 // one frame; pos in itp::boxd memory order: element (i,j)[k] at (i + j*nmol)*3 + k
 __global__ void __launch_bounds__(256) k1b_positions(const float* __restrict__ xf, const int* __restrict__ index,
@@ -190,6 +239,29 @@ __device__ __forceinline__ int density_molecule(const float* p, int napm, const 
     const int me = __double2int_rz(div_const(__dsub_rn(c, d.low), d.dbin));
     if (me < 0 || me >= d.nbin) { ndrop++; return -1; }
     return me;
+}
+
+// density from already materialised centres (heterogeneous groups: K1 csr writes the centres, this bins them)
+__global__ void __launch_bounds__(256) k2_density_from_centers(const double* __restrict__ cen, int nframes, int nmol, DensityDev d,
+                                                               unsigned long long* __restrict__ hist,
+                                                               unsigned long long* __restrict__ stats)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmol || f >= nframes) return;
+    const double* c0 = cen + (size_t)f * 3 * nmol;
+    const double  c  = c0[(size_t)d.dim * nmol + i];
+    bool          ok = (d.low <= c) && (d.upper_inclusive ? (c <= d.up) : (c < d.up));
+    if (ok && d.dim2 >= 0)
+    {
+        const double c2 = c0[(size_t)d.dim2 * nmol + i];
+        ok              = (d.low2 <= c2) && (d.upper_inclusive ? (c2 <= d.up2) : (c2 < d.up2));
+    }
+    if (!ok) return;
+    atomicAdd(&stats[4], 1ull);
+    const int me = __double2int_rz(div_const(__dsub_rn(c, d.low), d.dbin));
+    if (me < 0 || me >= d.nbin) { atomicAdd(&stats[1], 1ull); return; }
+    atomicAdd(&hist[me], 1ull);
 }
 
 // grid: x = molecule block, y = frame group.  A thread owns ONE molecule and walks the frames of its group.

@@ -19,7 +19,7 @@ COM_MASS, COM_GEOMETRY, COM_CHARGE, COM_DIPOLE = range(4)
 # every symbol include/b2a.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "b2a_last_error", "b2a_version", "b2a_device_count", "b2a_create", "b2a_destroy", "b2a_sync", "b2a_stream",
-    "b2a_pinned_alloc", "b2a_pinned_free", "b2a_set_group", "b2a_set_group_wsum", "b2a_group_nmol",
+    "b2a_pinned_alloc", "b2a_pinned_free", "b2a_set_group", "b2a_set_group_full", "b2a_set_group_wsum", "b2a_group_nmol",
     "b2a_submit_batch", "b2a_batch_frames", "b2a_centers", "b2a_centers_batch", "b2a_positions",
     "b2a_density_create", "b2a_rdf_create", "b2a_orient_create", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
     "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_invalidate", "b2a_timing_enable",
@@ -73,6 +73,7 @@ def load():
         L.b2a_pinned_free.argtypes = [_P]
         L.b2a_pinned_free.restype = None
         L.b2a_set_group.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P]
+        L.b2a_set_group_full.argtypes = [_P, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P]
         L.b2a_set_group_wsum.argtypes = [_P, C.c_int, C.c_int, C.c_double]
         L.b2a_group_nmol.argtypes = [_P, C.c_int]
         L.b2a_submit_batch.argtypes = [_P, C.c_int, _P, _P]
@@ -152,6 +153,14 @@ class Context:
         m = np.ascontiguousarray(mass, dtype=np.float64)
         q = np.ascontiguousarray(charge, dtype=np.float64)
         check(self.L.b2a_set_group(self._h, grp, idx.ctypes.data, len(idx), napm, m.ctypes.data, q.ctypes.data))
+
+    def set_group_full(self, grp, index, napm, mass, charge):
+        """Heterogeneous molecules (GmxHandleFull): napm[nmol], mass/charge per index position."""
+        idx = np.ascontiguousarray(index, dtype=np.int32)
+        na = np.ascontiguousarray(napm, dtype=np.int32)
+        m = np.ascontiguousarray(mass, dtype=np.float64)
+        q = np.ascontiguousarray(charge, dtype=np.float64)
+        check(self.L.b2a_set_group_full(self._h, grp, idx.ctypes.data, len(idx), len(na), na.ctypes.data, m.ctypes.data, q.ctypes.data))
 
     def set_group_wsum(self, grp, com, wsum):
         check(self.L.b2a_set_group_wsum(self._h, grp, com, wsum))

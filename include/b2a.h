@@ -73,6 +73,14 @@ void  b2a_pinned_free(void* p);
  * with the caller's own value (the C++ wrapper passes atomCenter.sum() itself).                     */
 int b2a_set_group(b2a_ctx* ctx, int grp, const int* index, int ngx, int napm, const double* mass, const double* charge);
 int b2a_set_group_wsum(b2a_ctx* ctx, int grp, int com, double wsum);
+/* Heterogeneous molecule sizes: replaces the results of GmxHandleFull::init (reference
+ * include/itp/gmx_bits/gmx_handle_full.ipp:300-344): napm[nmol] atoms per molecule (consecutive runs of index),
+ * mass/charge per index position [ngx]; per-molecule totals are summed sequentially as totMass/totCharge are.
+ * com = 1 uses weight 1 and divisor napm[i] (the intent of full.ipp:166-171, which indexes an empty vector).
+ * Loaders, density and RDF accumulators accept such a group; b2a_positions fills an nmol x max(napm) boxd buffer
+ * (slots j >= napm[i] are returned as 0).                                                                   */
+int b2a_set_group_full(b2a_ctx* ctx, int grp, const int* index, int ngx, int nmol, const int* napm, const double* mass,
+                       const double* charge);
 int b2a_group_nmol(b2a_ctx* ctx, int grp);
 
 /* ---- frames (A1) ------------------------------------------------------------------------------- */

@@ -37,6 +37,8 @@ def lib():
         L.orc_orient_accum.argtypes = [_P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_float, C.c_float, C.c_float,
                                        C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
                                        C.c_int, C.c_int, C.c_int, _P, _P, _P]
+        L.orc_full_load_position.argtypes = [_P, _P, C.c_int, _P, C.c_int, _P, _P]
+        L.orc_full_load_position_center.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P]
         _lib = L
     return _lib
 
@@ -149,3 +151,21 @@ def orient_accum(pos, posc, Lbox, DIMN, low, up, c1, c2, dr, CR, Cr, nAngle, tp1
                            CR, Cr, nAngle, tp1, tp2, tp3, DIMNOrient, method, orient.ctypes.data, ncm.ctypes.data,
                            dropped.ctypes.data)
     return orient, ncm, int(dropped[0])
+
+
+def full_load_position(x, index, napm, Lbox):
+    """GmxHandleFull::loadPosition -> [nmol, max_napm, 3] (slots j >= napm[i] are 0)."""
+    x, index, napm, Lbox = _f32(x), _i32(index), _i32(napm), _f64(Lbox)
+    nmol, mx = len(napm), int(napm.max())
+    out = np.zeros((mx, nmol, 3), dtype=np.float64)
+    lib().orc_full_load_position(x.ctypes.data, index.ctypes.data, nmol, napm.ctypes.data, mx, Lbox.ctypes.data, out.ctypes.data)
+    return out.transpose(1, 0, 2)
+
+
+def full_load_position_center(x, index, napm, w, Lbox, geometry=False):
+    x, index, napm, w, Lbox = _f32(x), _i32(index), _i32(napm), _f64(w), _f64(Lbox)
+    nmol = len(napm)
+    out = np.empty((3, nmol), dtype=np.float64)
+    lib().orc_full_load_position_center(x.ctypes.data, index.ctypes.data, nmol, napm.ctypes.data, w.ctypes.data, int(geometry),
+                                        Lbox.ctypes.data, out.ctypes.data)
+    return out.T

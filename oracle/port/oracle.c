@@ -266,3 +266,56 @@ void orc_orient_accum(const double* pos, const double* posc, int nmol, int napm,
         orient[(size_t)meZ + (size_t)meA * nbin1]++;
     }
 }
+
+/* ---- GmxHandleFull: heterogeneous molecule sizes (include/itp/gmx_bits/gmx_handle_full.ipp:115-199, 323-344) ---- */
+void orc_full_load_position(const float* x, const int* index, int nmol, const int* napm, int max_napm, const double Lbox[3],
+                            double* pos)
+{
+    (void)max_napm;
+    double half[3];
+    for (int k = 0; k < 3; ++k) half[k] = Lbox[k] / 2;
+    int n = 0;
+    for (int i = 0; i < nmol; ++i)
+    {
+        const int molN = index[n];
+        for (int j = 0; j < napm[i]; ++j, ++n)
+            for (int k = 0; k < 3; ++k)
+            {
+                double       t   = x[(size_t)index[n] * 3 + k];
+                const double ref = x[(size_t)molN * 3 + k];
+                while (t - ref > half[k]) t -= Lbox[k];
+                while (t - ref < -half[k]) t += Lbox[k];
+                pos[((size_t)i + (size_t)j * nmol) * 3 + k] = t;
+            }
+    }
+}
+
+/* w: weight per index position; com 1 (geometry) is given its evident intent: weights 1, divisor napm[i] */
+void orc_full_load_position_center(const float* x, const int* index, int nmol, const int* napm, const double* w, int geometry,
+                                   const double Lbox[3], double* posc)
+{
+    double half[3];
+    for (int k = 0; k < 3; ++k) half[k] = Lbox[k] / 2;
+    int n = 0;
+    for (int i = 0; i < nmol; ++i)
+    {
+        const int molN = index[n];
+        double    tot  = 0.0;                       /* totMass / totCharge: sequential sum, full.ipp:337-340 */
+        for (int j = 0; j < napm[i]; ++j) tot += w[n + j];
+        if (geometry) tot = (double)napm[i];
+        for (int k = 0; k < 3; ++k)
+        {
+            double       c   = 0.0;
+            const double ref = x[(size_t)molN * 3 + k];
+            for (int j = 0; j < napm[i]; ++j)
+            {
+                double t = x[(size_t)(molN + j) * 3 + k];
+                while (t - ref > half[k]) t -= Lbox[k];
+                while (t - ref < -half[k]) t += Lbox[k];
+                c += t * (geometry ? 1.0 : w[n + j]);
+            }
+            posc[(size_t)i + (size_t)k * nmol] = c / tot;
+        }
+        n += napm[i];
+    }
+}

@@ -88,6 +88,67 @@ void refshim_load_position_center(void* h, int grp, int com, double* out)
     std::memcpy(out, posc.data(), sizeof(double) * posc.size());
 }
 
+/* ---- GmxHandleFull (heterogeneous molecule sizes), reference include/itp/gmx_bits/gmx_handle_full.ipp ---- */
+struct ShimFull
+{
+    itp::GmxHandleFull hd{ 0, nullptr };
+    std::vector<int>   idx;
+};
+
+void* refshim_full_new(const int* index, int ngx, int nmol, const int* napm, const double* mass, const double* charge)
+{
+    ShimFull* s = new ShimFull;
+    s->hd.ngrps = 1;
+    s->idx.assign(index, index + ngx);
+    snew(s->hd.index, 1);
+    snew(s->hd.ngx, 1);
+    snew(s->hd.fr, 1);
+    s->hd.index[0] = s->idx.data();
+    s->hd.ngx[0]   = ngx;
+    s->hd.napm.resize(1); s->hd.nmol.resize(1); s->hd.mass.resize(1); s->hd.charge.resize(1);
+    s->hd.totMass.resize(1); s->hd.totCharge.resize(1);
+    s->hd.nmol[0] = nmol;
+    s->hd.napm[0].assign(napm, napm + nmol);
+    s->hd.mass[0].resize(nmol); s->hd.charge[0].resize(nmol);
+    s->hd.totMass[0].assign(nmol, 0.0); s->hd.totCharge[0].assign(nmol, 0.0);
+    int n = 0;
+    for (int i = 0; i < nmol; ++i)       /* same accumulation order as get_mass_charge, full.ipp:323-344 */
+    {
+        s->hd.mass[0][i].resize(napm[i]); s->hd.charge[0][i].resize(napm[i]);
+        for (int j = 0; j < napm[i]; ++j, ++n)
+        {
+            s->hd.mass[0][i][j] = mass[n]; s->hd.charge[0][i][j] = charge[n];
+            s->hd.totMass[0][i] += mass[n]; s->hd.totCharge[0][i] += charge[n];
+        }
+    }
+    return s;
+}
+void refshim_full_free(void* h) { delete static_cast<ShimFull*>(h); }
+void refshim_full_set_frame(void* h, float* x, const float* box9)
+{
+    ShimFull* s = static_cast<ShimFull*>(h);
+    s->hd.fr->x = reinterpret_cast<rvec*>(x);
+    s->hd.Lbox[XX] = box9[0]; s->hd.Lbox[YY] = box9[4]; s->hd.Lbox[ZZ] = box9[8];
+}
+/* out: nmol x maxNapm x 3 doubles in boxd order, untouched slots are returned as 0 */
+void refshim_full_load_position(void* h, double* out, int maxNapm)
+{
+    ShimFull* s = static_cast<ShimFull*>(h);
+    itp::boxd pos(s->hd.nmol[0], maxNapm);
+    for (Eigen::Index i = 0; i < pos.size(); ++i) pos.data()[i].setZero();
+    s->hd.loadPosition(pos, 0);
+    std::memcpy(out, pos.data(), sizeof(double) * 3 * pos.size());
+}
+/* center 0 (mass) or 2 (charge); 1 indexes an empty vector in the reference (full.ipp:166-171) and is not callable */
+void refshim_full_load_position_center(void* h, int center, double* out)
+{
+    ShimFull* s = static_cast<ShimFull*>(h);
+    itp::matd posc;
+    s->hd.initPosc(posc, 0);
+    s->hd.loadPositionCenter(posc, 0, center);
+    std::memcpy(out, posc.data(), sizeof(double) * posc.size());
+}
+
 double refshim_periodicity(double dx, double box) { return itp::GmxHandle::periodicity(dx, box); }
 
 /* atomCenter.sum() exactly as ipp:195 evaluates it (Eigen 3.3.9 vectorised redux) */

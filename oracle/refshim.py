@@ -34,6 +34,12 @@ def lib():
         L.refshim_eigen_sum.restype = C.c_double
         L.refshim_eigen_sum.argtypes = [_P, C.c_int]
         L.refshim_rightcols_rowmean.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
+        L.refshim_full_new.restype = _P
+        L.refshim_full_new.argtypes = [_P, C.c_int, C.c_int, _P, _P, _P]
+        L.refshim_full_free.argtypes = [_P]
+        L.refshim_full_set_frame.argtypes = [_P, _P, _P]
+        L.refshim_full_load_position.argtypes = [_P, _P, C.c_int]
+        L.refshim_full_load_position_center.argtypes = [_P, C.c_int, _P]
         _lib = L
     return _lib
 
@@ -79,3 +85,32 @@ def periodicity(dx, box):
 def eigen_sum(w):
     w = np.ascontiguousarray(w, dtype=np.float64)
     return lib().refshim_eigen_sum(w.ctypes.data, len(w))
+
+
+class RefHandleFull:
+    """itp::GmxHandleFull (heterogeneous molecule sizes) populated from arrays; one group."""
+
+    def __init__(self, index, napm, mass, charge):
+        self.index = np.ascontiguousarray(index, dtype=np.int32)
+        self.napm = np.ascontiguousarray(napm, dtype=np.int32)
+        self.nmol = len(self.napm)
+        m = np.ascontiguousarray(mass, dtype=np.float64)
+        q = np.ascontiguousarray(charge, dtype=np.float64)
+        self._h = lib().refshim_full_new(self.index.ctypes.data, len(self.index), self.nmol, self.napm.ctypes.data, m.ctypes.data,
+                                         q.ctypes.data)
+
+    def set_frame(self, x, box9):
+        self._x = np.ascontiguousarray(x, dtype=np.float32)
+        self._b = np.ascontiguousarray(box9, dtype=np.float32)
+        lib().refshim_full_set_frame(self._h, self._x.ctypes.data, self._b.ctypes.data)
+
+    def load_position(self):
+        mx = int(self.napm.max())
+        out = np.zeros((mx, self.nmol, 3), dtype=np.float64)
+        lib().refshim_full_load_position(self._h, out.ctypes.data, mx)
+        return out.transpose(1, 0, 2)
+
+    def load_position_center(self, center=0):
+        out = np.empty((3, self.nmol), dtype=np.float64)
+        lib().refshim_full_load_position_center(self._h, center, out.ctypes.data)
+        return out.T

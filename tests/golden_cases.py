@@ -64,3 +64,11 @@ def program_cases():
                                       "-dr", 0.5, "-CR", 2.0, "-Cr", 0.5, "-nA", 45, "-tp1", 3, "-tp2", 7, "-tp3", 12,
                                       "-DIMNOrient", 1, "-method", 2]),
     }
+
+
+def full_fixture():
+    """Heterogeneous group for GmxHandleFull: all cations (25 atoms) followed by all anions (7 atoms) of a small IL box."""
+    system = synth.ionic_liquid(70, 3.0, seed=13)
+    napm = np.array([25] * 70 + [7] * 70, dtype=np.int32)
+    m, q, *_ = system.atom_tables()
+    return system, system.groups["System"], napm, m.astype(np.float64), q.astype(np.float64)

@@ -403,3 +403,48 @@ def test_rdf_cells_equal_brute_force_large(gpu_ctx_factory):
     assert np.array_equal(res[0][0], res[1][0]) and res[0][0].sum() > 0
     assert int(res[1][1][lib.STAT_PAIRS]) * 4 < int(res[0][1][lib.STAT_PAIRS])     # cells evaluate far fewer pairs
     assert int(res[0][1][lib.STAT_DROPPED]) == int(res[1][1][lib.STAT_DROPPED])
+
+
+# ---- GmxHandleFull: heterogeneous molecule sizes -----------------------------------------------------
+def test_handle_full_loaders_and_accumulators(gpu_ctx_factory):
+    gold = np.load(os.path.join(GOLD, "loaders.npz"))
+    system, idx, napm, m, q = GC.full_fixture()
+    K = 3
+    x, box = system.frames(0, K), system.box9()
+    Lbox = port.lbox_from_box9(box)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    ctx.set_group_full(0, idx, napm, m, q)
+    ctx.set_group(1, system.groups["ANI"], 7, system.species[1].mass.astype(np.float64), system.species[1].charge.astype(np.float64))
+    ctx.submit(x, box)
+    nmol, mx = len(napm), int(napm.max())
+    # against the reference's own outputs (frame LOADER_FRAME) and the oracle (all frames)
+    assert np.array_equal(ctx.positions(0, mx, GC.LOADER_FRAME), gold["full.pos"])
+    assert np.array_equal(ctx.centers(0, 0, GC.LOADER_FRAME), gold["full.cen0"], equal_nan=True)
+    assert np.array_equal(ctx.centers(0, 2, GC.LOADER_FRAME), gold["full.cen2"], equal_nan=True)
+    for f in range(K):
+        assert np.array_equal(ctx.centers(0, 0, f), port.full_load_position_center(x[f], idx, napm, m, Lbox))
+        assert np.array_equal(ctx.centers(0, 1, f), port.full_load_position_center(x[f], idx, napm, m, Lbox, geometry=True))
+        assert np.array_equal(ctx.positions(0, mx, f), port.full_load_position(x[f], idx, napm, Lbox))
+    # density and RDF accumulators on the heterogeneous group
+    dbin = 0.1
+    acc = ctx.density_create(grp=0, com=0, dim=1, low=0.2, up=2.8, dbin=dbin, nbin=26, upper_inclusive=0, dim2=-1, low2=0.0, up2=0.0)
+    ctx.accumulate(acc)
+    got, st = ctx.read(acc, 26)
+    exp = np.zeros(26, np.uint64)
+    for f in range(K):
+        port.density_accum(port.full_load_position_center(x[f], idx, napm, m, Lbox), 1, refprog.f32(0.2), refprog.f32(2.8), dbin, 26, exp)
+    assert np.array_equal(got, exp) and got.sum() > 0
+    Rm = port.rdf_default_rm(Lbox); Rbin = port.rdf_rbin(Rm)
+    racc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=2, low=0.0, up=3.0, dim=2, dim2=0, low2=-100.0, up2=100.0, Rm=Rm, Rbin=Rbin)
+    ctx.accumulate(racc)
+    rgot, _ = ctx.read(racc, 2 * Rbin)
+    rexp = np.zeros((Rbin, 2), np.uint64)
+    gi = refprog.group_info(system, "ANI")
+    for f in range(K):
+        p1 = port.full_load_position_center(x[f], idx, napm, m, Lbox)
+        p2 = port.load_position_center(x[f], gi["index"], 7, gi["w"][0], Lbox)
+        port.rdf_accum(p1, p2, Lbox, 2, 0.0, 3.0, 2, 0, -100.0, 100.0, Rm, Rbin, rexp)
+    assert np.array_equal(rgot.reshape(Rbin, 2), rexp) and rexp.sum() > 0
+    with pytest.raises(lib.B2AError, match="heterogeneous"):
+        ctx.orient_create(grp=0, com=0, DIMN=2, low=0.0, up=3.0, c1=0.0, c2=0.0, dr=1.0, CR=2.0, Cr=0.0, nAngle=90, tp1=1, tp2=2, tp3=3,
+                          DIMNOrient=2, method=1)

@@ -51,6 +51,16 @@ def test_golden_eigen_sum_and_periodicity(gold):
     assert [port.periodicity(a, b) for a, b in GC.periodicity_inputs()] == list(gold["periodicity"])
 
 
+def test_golden_handle_full(gold):
+    """GmxHandleFull loaders (heterogeneous molecule sizes) against the reference's own outputs."""
+    system, idx, napm, m, q = GC.full_fixture()
+    x = system.frame(GC.LOADER_FRAME)
+    Lbox = port.lbox_from_box9(system.box9())
+    assert np.array_equal(port.full_load_position(x, idx, napm, Lbox), gold["full.pos"])
+    assert np.array_equal(port.full_load_position_center(x, idx, napm, m, Lbox), gold["full.cen0"], equal_nan=True)
+    assert np.array_equal(port.full_load_position_center(x, idx, napm, q, Lbox), gold["full.cen2"], equal_nan=True)
+
+
 def _golden_lines(name):
     with open(os.path.join(GOLD, name + ".txt")) as fp:
         return fp.read().split("\n")[:-1]

@@ -40,6 +40,12 @@ def loaders():
     out["edge.pos"] = np.ascontiguousarray(rh.load_position())
     for com in (0, 1, 2):
         out[f"edge.cen{com}"] = np.ascontiguousarray(rh.load_position_center(com))
+    system, idx, napm, m, q = CASES.full_fixture()
+    rf = refshim.RefHandleFull(idx, napm, m, q)
+    rf.set_frame(system.frame(CASES.LOADER_FRAME), system.box9())
+    out["full.pos"] = np.ascontiguousarray(rf.load_position())
+    out["full.cen0"] = np.ascontiguousarray(rf.load_position_center(0))
+    out["full.cen2"] = np.ascontiguousarray(rf.load_position_center(2))
     w = np.array([12.011, 1.008, 1.008, 14.007, 12.011, 15.9994, 1.008, 0.3, 7.7, 1e-3, 5.5], dtype=np.float64)
     out["eigen_sum"] = np.array([refshim.eigen_sum(w[:n]) for n in range(1, len(w) + 1)])
     pd = CASES.periodicity_inputs()
