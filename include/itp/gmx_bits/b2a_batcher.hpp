@@ -1,0 +1,136 @@
+// FrameBatcher -- shared by the drop-in handles: decodes K frames at a time into a pinned host batch, ships them to
+// the GPU with one asynchronous copy (b2a_submit_batch) and keeps a t_trxframe pointing at the current frame.
+// It is the piece that lets the per-frame API (readFirstFrame / readNextFrame / hd.fr->x) survive on top of batches
+// (SURVEY.md H4).
+#pragma once
+
+#include <b2a.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace itp
+{
+namespace b2a_detail
+{
+    inline void check(int rc)
+    {
+        if (rc != B2A_OK) gmx_fatal(FARGS, "%s", b2a_last_error());   // the reference aborts through gmx_fatal too
+    }
+
+    class FrameBatcher
+    {
+    public:
+        FrameBatcher()
+        {
+            if (const char* e = std::getenv("B2A_BATCH")) k_ = std::max(1, std::atoi(e));
+        }
+        ~FrameBatcher()
+        {
+            if (ctx_) b2a_destroy(ctx_);
+            if (bx_) b2a_pinned_free(bx_);
+        }
+        FrameBatcher(const FrameBatcher&) = delete;
+        FrameBatcher& operator=(const FrameBatcher&) = delete;
+
+        b2a_ctx* ctx(int natoms)
+        {
+            if (!ctx_)
+            {
+                int dev = 0;
+                if (const char* e = std::getenv("B2A_DEVICE")) dev = std::atoi(e);
+                check(b2a_create(&ctx_, dev, natoms, k_));
+            }
+            return ctx_;
+        }
+        b2a_ctx* ctx() const { return ctx_; }
+        int      frames() const { return n_; }
+        int      current() const { return cur_; }
+        int      capacity() const { return k_; }
+        long     serial() const { return serial_; }
+
+        // (re)start: `first` was just filled by read_first_frame
+        bool start(gmx_output_env_t* oenv, t_trxstatus* status, const t_trxframe& first, t_trxframe* fr)
+        {
+            oenv_ = oenv; status_ = status; io_ = first; eof_ = false;
+            natoms_ = io_.natoms;
+            const size_t n3 = (size_t)natoms_ * 3;
+            if (!bx_)
+            {
+                bx_ = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
+                if (!bx_) gmx_fatal(FARGS, "%s", b2a_last_error());
+                bbox_.resize(9 * (size_t)k_);
+                btime_.resize(k_);
+            }
+            if (io_.bV) bv_.resize(n3 * k_);
+            if (io_.bF) bf_.resize(n3 * k_);
+            if (!fill(true)) return false;
+            point(0, fr);
+            return true;
+        }
+
+        // advance one frame; refills the batch when it is exhausted
+        bool next(t_trxframe* fr)
+        {
+            if (cur_ + 1 < n_) { point(cur_ + 1, fr); return true; }
+            if (eof_ || !fill(false)) return false;
+            point(0, fr);
+            return true;
+        }
+
+        // number of frames skipped when the caller consumes the rest of the batch as a block
+        int skip_to_batch_end()
+        {
+            const int skipped = n_ - 1 - cur_;
+            cur_ = n_ - 1;
+            return skipped;
+        }
+
+    private:
+        bool fill(bool first)
+        {
+            const size_t n3 = (size_t)natoms_ * 3;
+            int          n  = 0;
+            for (; n < k_; ++n)
+            {
+                if (!(first && n == 0))
+                    if (eof_ || !read_next_frame(oenv_, status_, &io_)) { eof_ = true; break; }
+                if (io_.bX) std::memcpy(bx_ + (size_t)n * n3, io_.x, n3 * sizeof(float));
+                if (io_.bV) std::memcpy(bv_.data() + (size_t)n * n3, io_.v, n3 * sizeof(float));
+                if (io_.bF) std::memcpy(bf_.data() + (size_t)n * n3, io_.f, n3 * sizeof(float));
+                std::memcpy(bbox_.data() + 9 * (size_t)n, &io_.box[0][0], 9 * sizeof(float));
+                btime_[n] = io_.time;
+            }
+            if (n == 0) return false;
+            n_ = n;
+            ++serial_;
+            if (io_.bX) check(b2a_submit_batch(ctx(natoms_), n, bx_, bbox_.data()));
+            return true;
+        }
+
+        void point(int k, t_trxframe* fr)
+        {
+            const size_t n3 = (size_t)natoms_ * 3;
+            *fr        = io_;
+            fr->x      = io_.bX ? reinterpret_cast<rvec*>(bx_ + (size_t)k * n3) : nullptr;
+            fr->v      = io_.bV ? reinterpret_cast<rvec*>(bv_.data() + (size_t)k * n3) : nullptr;
+            fr->f      = io_.bF ? reinterpret_cast<rvec*>(bf_.data() + (size_t)k * n3) : nullptr;
+            fr->time   = btime_[k];
+            fr->natoms = natoms_;
+            std::memcpy(&fr->box[0][0], bbox_.data() + 9 * (size_t)k, 9 * sizeof(float));
+            cur_ = k;
+        }
+
+        b2a_ctx*           ctx_ = nullptr;
+        gmx_output_env_t*  oenv_ = nullptr;
+        t_trxstatus*       status_ = nullptr;
+        t_trxframe         io_{};
+        int                natoms_ = 0, k_ = 16, n_ = 0, cur_ = 0;
+        bool               eof_ = false;
+        long               serial_ = 0;
+        float*             bx_ = nullptr;
+        std::vector<float> bv_, bf_, bbox_, btime_;
+    };
+} // namespace b2a_detail
+} // namespace itp

@@ -66,3 +66,19 @@ def test_live_reference_vs_dropin_other_programs(tmp_path):
         ran += 1
     if ran == 0:
         pytest.skip("no reference binaries on this box")
+
+
+@pytest.mark.parametrize("center", [0, 2])
+def test_handle_full_dropin_matches_reference_build(center, tmp_path, monkeypatch):
+    """GmxHandleFull (heterogeneous molecule sizes): the same exerciser source built against the reference's own header
+    and against the drop-in header dumps identical centres and unwrapped positions (17 significant digits)."""
+    from gmx2020postanalysis_b200 import synth
+    ref_exe, new_exe = os.path.join(refprog.REFDIR, "full_dump"), os.path.join(DROPIN, "full_dump")
+    if not (os.path.exists(ref_exe) and os.path.exists(new_exe)):
+        pytest.skip("full_dump binaries not built (needs /root/reference at build time)")
+    monkeypatch.setenv("B2A_BATCH", "2")
+    system = synth.ionic_liquid(60, 3.2, seed=74)
+    args = ["-center", center]
+    ref = refprog.run_program(ref_exe, str(tmp_path / "ref"), system, 5, ["System", "ANI"], args, "o.dat")
+    got = refprog.run_program(new_exe, str(tmp_path / "new"), system, 5, ["System", "ANI"], args, "o.dat")
+    assert len(ref) > 600 and got == ref
