@@ -10,9 +10,8 @@
 // names start with `b2a` are extensions that ported programs use to reach the fused device accumulators.
 #pragma once
 
-#include <b2a.h>
+#include "b2a_batcher.hpp"
 
-#include <memory>
 #include <map>
 
 namespace itp
@@ -21,7 +20,6 @@ namespace itp
     {
     public:
         GmxHandle(int argc, char** argv);
-        ~GmxHandle();
         GmxHandle(const GmxHandle&) = delete;
         GmxHandle(GmxHandle&&) = delete;
         GmxHandle& operator=(const GmxHandle&) = delete;
@@ -49,8 +47,8 @@ namespace itp
         static double periodicity(double dx, double box);
 
         // ---- extensions (not in the reference): fused device accumulators over whole batches ----------------
-        b2a_ctx* b2aContext() { return ctx_; }
-        int  b2aBatchFrames() const { return batch_n_; }          // frames in the resident batch
+        b2a_ctx* b2aContext() { return batch_.ctx(); }
+        int  b2aBatchFrames() const { return batch_.frames(); }          // frames in the resident batch
         bool b2aReadNextBatch();                                   // skip to the first frame of the next batch
         int  b2aDensity(const b2a_density_spec& s);
         int  b2aRdf(const b2a_rdf_spec& s, bool symmetric = true);
@@ -62,10 +60,7 @@ namespace itp
         int  get_natom_per_mol(int grp);
         vecd get_mass(int grp);
         vecd get_charge(int grp);
-        void b2aCheck(int rc);
         void b2aEnsure();
-        bool b2aFillBatch(bool first);
-        void b2aPointFrame(int k);
         vecd weights(int grp, int com);
 
     public:
@@ -101,21 +96,11 @@ namespace itp
         int                     ePBC;
 
     private:
-        b2a_ctx*            ctx_      = nullptr;
-        int                 natoms_   = 0;
-        int                 batch_k_  = 16;     // frames per batch (env B2A_BATCH)
-        int                 batch_n_  = 0;      // frames in the current batch
-        int                 cur_      = 0;      // current frame inside the batch
-        bool                eof_      = false;
-        bool                groups_up_ = false;
-        float*              bx_ = nullptr;      // pinned [K][natoms][3]
-        std::vector<float>  bv_, bf_;           // host-only copies when velocities / forces are read
-        std::vector<float>  bbox_;              // [K][9]
-        std::vector<float>  btime_;             // [K]
-        t_trxframe          io_{};              // frame object the trajectory reader fills
-        // host cache of batch centres: key (grp << 2 | com) -> [n][3][nmol] doubles, valid for batch serial
+        b2a_detail::FrameBatcher batch_;          // pinned K-frame batches (env B2A_BATCH), device context
+        int                      natoms_ = 0;
+        bool                     groups_up_ = false;
+        // host cache of batch centres: key (grp << 2 | com) -> [n][3][nmol] doubles, valid for one batch serial
         struct CenCache { std::vector<double> buf; long serial = -1; };
-        std::map<int, CenCache> cen_;
-        long                serial_ = 0;
+        std::map<int, CenCache>  cen_;
     };
 } // namespace itp

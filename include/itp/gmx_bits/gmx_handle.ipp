@@ -17,21 +17,8 @@ namespace itp
         dt = time = preTime = 0.0;
         Lbox[0] = Lbox[1] = Lbox[2] = 0.0;
         nthreads = 0;
-        if (const char* e = std::getenv("B2A_BATCH")) batch_k_ = std::max(1, std::atoi(e));
-    }
-
-    inline GmxHandle::~GmxHandle()
-    {
-        if (ctx_) b2a_destroy(ctx_);
-        if (bx_) b2a_pinned_free(bx_);
-        // top / ir / index / fr are deliberately left alone: the reference never frees them either and programs
-        // may hold pointers into them until exit (SURVEY.md 8b "Ownership").
-    }
-
-    inline void GmxHandle::b2aCheck(int rc)
-    {
-        // the C ABI returns codes; the reference aborts through gmx_fatal -- same observable behaviour
-        if (rc != B2A_OK) gmx_fatal(FARGS, "%s", b2a_last_error());
+        // top / ir / index / fr are never freed: the reference never frees them either and programs may hold pointers
+        // into them until exit (SURVEY.md 8b "Ownership"); the device context and pinned batch die with batch_.
     }
 
     // ---- init: command line, topology, index groups, molecule discovery (reference ipp:11-66) -------------------
@@ -137,87 +124,30 @@ namespace itp
     // ---- device context, groups, batches -------------------------------------------------------------------------
     inline void GmxHandle::b2aEnsure()
     {
-        if (!ctx_)
-        {
-            int dev = 0;
-            if (const char* e = std::getenv("B2A_DEVICE")) dev = std::atoi(e);
-            b2aCheck(b2a_create(&ctx_, dev, natoms_, batch_k_));
-        }
+        b2a_ctx* c = batch_.ctx(natoms_);
         if (!groups_up_ && napm.size() == ngrps)
         {
             for (int g = 0; g != ngrps; ++g)
             {
-                b2aCheck(b2a_set_group(ctx_, g, index[g], ngx[g], napm[g], mass[g].data(), charge[g].data()));
+                b2a_detail::check(b2a_set_group(c, g, index[g], ngx[g], napm[g], mass[g].data(), charge[g].data()));
                 // hand over Eigen's own evaluation of atomCenter.sum() (ipp:195) so centres are bit-identical
-                for (int com = 0; com < 3; ++com) b2aCheck(b2a_set_group_wsum(ctx_, g, com, weights(g, com).sum()));
+                for (int com = 0; com < 3; ++com) b2a_detail::check(b2a_set_group_wsum(c, g, com, weights(g, com).sum()));
             }
             groups_up_ = true;
         }
-    }
-
-    inline void GmxHandle::b2aPointFrame(int k)
-    {
-        const size_t n3 = (size_t)natoms_ * 3;
-        *fr        = io_;
-        fr->x      = io_.bX ? reinterpret_cast<rvec*>(bx_ + (size_t)k * n3) : nullptr;
-        fr->v      = io_.bV ? reinterpret_cast<rvec*>(bv_.data() + (size_t)k * n3) : nullptr;
-        fr->f      = io_.bF ? reinterpret_cast<rvec*>(bf_.data() + (size_t)k * n3) : nullptr;
-        fr->time   = btime_[k];
-        fr->natoms = natoms_;
-        std::memcpy(&fr->box[0][0], bbox_.data() + 9 * (size_t)k, 9 * sizeof(float));
-        cur_ = k;
-    }
-
-    // Decode up to K frames into the pinned batch and ship them with one asynchronous copy.
-    inline bool GmxHandle::b2aFillBatch(bool first)
-    {
-        const size_t n3 = (size_t)natoms_ * 3;
-        int          n  = 0;
-        for (; n < batch_k_; ++n)
-        {
-            if (!(first && n == 0))
-            {
-                if (eof_ || !read_next_frame(oenv, status, &io_)) { eof_ = true; break; }
-            }
-            if (io_.bX) std::memcpy(bx_ + (size_t)n * n3, io_.x, n3 * sizeof(float));
-            if (io_.bV) std::memcpy(bv_.data() + (size_t)n * n3, io_.v, n3 * sizeof(float));
-            if (io_.bF) std::memcpy(bf_.data() + (size_t)n * n3, io_.f, n3 * sizeof(float));
-            std::memcpy(bbox_.data() + 9 * (size_t)n, &io_.box[0][0], 9 * sizeof(float));
-            btime_[n] = io_.time;
-        }
-        if (n == 0) return false;
-        batch_n_ = n;
-        ++serial_;
-        if (io_.bX)
-        {
-            b2aEnsure();
-            b2aCheck(b2a_submit_batch(ctx_, n, bx_, bbox_.data()));
-        }
-        return true;
     }
 
     // ---- frame stepping (reference ipp:68-95) ----------------------------------------------------------------------
     inline bool GmxHandle::readFirstFrame()
     {
         // a second call restarts the trajectory, like read_first_frame does (two-pass programs rely on it)
-        io_ = t_trxframe{};
-        eof_ = false;
-        bool b = read_first_frame(oenv, &status, get_ftp2fn(efTRX), &io_, flags);
+        t_trxframe io{};
+        bool       b = read_first_frame(oenv, &status, get_ftp2fn(efTRX), &io, flags);
         if (b)
         {
-            natoms_ = io_.natoms;
-            const size_t n3 = (size_t)natoms_ * 3;
-            if (!bx_)
-            {
-                bx_ = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * batch_k_));
-                if (!bx_) gmx_fatal(FARGS, "%s", b2a_last_error());
-                bbox_.resize(9 * (size_t)batch_k_);
-                btime_.resize(batch_k_);
-            }
-            if (io_.bV) bv_.resize(n3 * batch_k_);
-            if (io_.bF) bf_.resize(n3 * batch_k_);
-            b = b2aFillBatch(true);
-            if (b) b2aPointFrame(0);
+            natoms_ = io.natoms;
+            b2aEnsure();
+            b = batch_.start(oenv, status, io, fr);
         }
         b && (nframe = 1);
         Lbox[XX] = fr->box[XX][XX];
@@ -230,13 +160,7 @@ namespace itp
 
     inline bool GmxHandle::readNextFrame()
     {
-        bool b;
-        if (cur_ + 1 < batch_n_) { b2aPointFrame(cur_ + 1); b = true; }
-        else
-        {
-            b = !eof_ && b2aFillBatch(false);
-            if (b) b2aPointFrame(0);
-        }
+        const bool b = batch_.next(fr);
         b && (++nframe);
         Lbox[XX] = fr->box[XX][XX];   // updated even at end of file, as in the reference (ipp:85-87)
         Lbox[YY] = fr->box[YY][YY];
@@ -252,8 +176,7 @@ namespace itp
 
     inline bool GmxHandle::b2aReadNextBatch()
     {
-        nframe += batch_n_ - 1 - cur_;   // the frames of this batch that were consumed as a block
-        cur_ = batch_n_ - 1;
+        nframe += batch_.skip_to_batch_end();   // the frames of this batch that were consumed as a block
         return readNextFrame();
     }
 
@@ -276,7 +199,7 @@ namespace itp
         if (grp >= ngrps) gmx_fatal(FARGS, "grp(%d) should less than ngrps(%d)!", grp, ngrps);
         b2aEnsure();
         // boxd = column-major array of Array3d: element (i,j)[k] at (i + j*nmol)*3 + k -- written in place
-        b2aCheck(b2a_positions(ctx_, grp, cur_, reinterpret_cast<double*>(pos.data())));
+        b2a_detail::check(b2a_positions(batch_.ctx(), grp, batch_.current(), reinterpret_cast<double*>(pos.data())));
     }
 
     inline void GmxHandle::loadPositionCenter(matd& posc, int grp, int center)   // ipp:150-199
@@ -287,13 +210,13 @@ namespace itp
         // one kernel launch + one D2H per (group, centre kind) per BATCH; frames are then handed out from the host copy
         CenCache&    c  = cen_[(grp << 2) | center];
         const size_t n3 = 3 * (size_t)nmol[grp];
-        if (c.serial != serial_)
+        if (c.serial != batch_.serial())
         {
-            c.buf.resize(n3 * batch_k_);
-            b2aCheck(b2a_centers_batch(ctx_, grp, center, c.buf.data()));
-            c.serial = serial_;
+            c.buf.resize(n3 * batch_.capacity());
+            b2a_detail::check(b2a_centers_batch(batch_.ctx(), grp, center, c.buf.data()));
+            c.serial = batch_.serial();
         }
-        std::memcpy(posc.data(), c.buf.data() + n3 * cur_, n3 * sizeof(double));   // matd(nmol,3) column-major
+        std::memcpy(posc.data(), c.buf.data() + n3 * batch_.current(), n3 * sizeof(double));   // matd(nmol,3) column-major
     }
 
     // ---- velocity / force loaders: no unwrapping, host side (ipp:201-339) ------------------------------------------------
@@ -407,7 +330,7 @@ namespace itp
     {
         b2aEnsure();
         int acc = -1;
-        b2aCheck(b2a_density_create(ctx_, &s, &acc));
+        b2a_detail::check(b2a_density_create(batch_.ctx(), &s, &acc));
         return acc;
     }
 
@@ -415,8 +338,8 @@ namespace itp
     {
         b2aEnsure();
         int acc = -1;
-        b2aCheck(b2a_rdf_create(ctx_, &s, &acc));
-        b2aCheck(b2a_rdf_tune(ctx_, acc, symmetric ? 1 : 0, 0));
+        b2a_detail::check(b2a_rdf_create(batch_.ctx(), &s, &acc));
+        b2a_detail::check(b2a_rdf_tune(batch_.ctx(), acc, symmetric ? 1 : 0, 0));
         return acc;
     }
 
@@ -424,17 +347,17 @@ namespace itp
     {
         b2aEnsure();
         int acc = -1;
-        b2aCheck(b2a_orient_create(ctx_, &s, &acc));
+        b2a_detail::check(b2a_orient_create(batch_.ctx(), &s, &acc));
         return acc;
     }
 
-    inline void GmxHandle::b2aAccumulate(int acc) { b2aCheck(b2a_accumulate(ctx_, acc)); }
+    inline void GmxHandle::b2aAccumulate(int acc) { b2a_detail::check(b2a_accumulate(batch_.ctx(), acc)); }
 
     inline void GmxHandle::b2aRead(int acc, std::vector<uint64_t>& counts, uint64_t* stats)
     {
         size_t n = 0;
-        b2aCheck(b2a_acc_size(ctx_, acc, &n));
+        b2a_detail::check(b2a_acc_size(batch_.ctx(), acc, &n));
         counts.assign(n, 0);
-        b2aCheck(b2a_acc_read(ctx_, acc, counts.data(), stats));
+        b2a_detail::check(b2a_acc_read(batch_.ctx(), acc, counts.data(), stats));
     }
 } // namespace itp
