@@ -91,6 +91,8 @@ struct Group
     DivConst* d_div[4]   = { nullptr, nullptr, nullptr, nullptr };
     bool    contiguous = false;   // index[n] == index[0] + n: a block's molecules are one byte range per frame (TMA path)
     double* d_w[4]  = { nullptr, nullptr, nullptr, nullptr };   // mass, ones, charge, charge(dipole)
+    float*  d_wf[4] = { nullptr, nullptr, nullptr, nullptr };   // the same, rounded to float (FP32-bracketed fast paths)
+    std::vector<double> h_w[4];
     double  wsum[4] = { 0, 0, 0, 0 };
     // centre cache per com for the current batch
     double*  d_cen[4]   = { nullptr, nullptr, nullptr, nullptr };
@@ -122,6 +124,8 @@ struct Acc
     int4*     d_sortedB = nullptr;
     unsigned  cap_keysA = 0, cap_keysB = 0;
     int       ipt = 0, threads = 0;   // 0 = auto
+    int       fast = 1;               // density / orient: 0 literal FP64, 1 FP32 bracket + FP64 queue, 2 validate
+    unsigned char* d_lut = nullptr;   // orient: cos cell -> first candidate angle bin
     // orient
     double* d_cosedge = nullptr;
     float*  d_fedge   = nullptr;
@@ -145,6 +149,7 @@ struct b2a_ctx
     std::map<int, Group> groups;
     std::vector<std::unique_ptr<Acc>> accs;
     double*      d_pos_scratch = nullptr;
+    unsigned*    d_work = nullptr;   // work-item counter of the persistent streaming kernels
     size_t       pos_scratch_n = 0;
     // optional CUDA-event timing per kernel family (bench.py): pairs are resolved lazily in b2a_timing_read
     bool         timing = false;
@@ -212,7 +217,7 @@ extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
 static void free_group(Group& g)
 {
     cudaFree(g.d_index);
-    for (int k = 0; k < 4; ++k) { cudaFree(g.d_w[k]); cudaFree(g.d_cen[k]); cudaFree(g.d_fix[k]); cudaFree(g.d_wfull[k]); cudaFree(g.d_div[k]); }
+    for (int k = 0; k < 4; ++k) { cudaFree(g.d_w[k]); cudaFree(g.d_wf[k]); cudaFree(g.d_cen[k]); cudaFree(g.d_fix[k]); cudaFree(g.d_wfull[k]); cudaFree(g.d_div[k]); }
     cudaFree(g.d_off); cudaFree(g.d_mol_of);
     g = Group();
 }
@@ -220,7 +225,7 @@ static void free_group(Group& g)
 static void free_acc(Acc& a)
 {
     cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
-    cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab);
+    cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab); cudaFree(a.d_lut);
     cudaFree(a.d_keysA); cudaFree(a.d_keysB); cudaFree(a.d_cellA); cudaFree(a.d_cellB); cudaFree(a.d_sortedB);
     if (a.h_frames) cudaFreeHost(a.h_frames);
 }
@@ -232,7 +237,7 @@ extern "C" void b2a_destroy(b2a_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->groups) free_group(kv.second);
     for (auto& a : c->accs) if (a) free_acc(*a);
-    cudaFree(c->d_x); cudaFree(c->d_geom); cudaFree(c->d_pos_scratch);
+    cudaFree(c->d_x); cudaFree(c->d_geom); cudaFree(c->d_pos_scratch); cudaFree(c->d_work);
     if (c->h_geom) cudaFreeHost(c->h_geom);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -287,6 +292,11 @@ extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int
     {
         CU(cudaMalloc(&g.d_w[k], sizeof(double) * napm));
         CU(cudaMemcpy(g.d_w[k], src[k], sizeof(double) * napm, cudaMemcpyHostToDevice));
+        g.h_w[k].assign(src[k], src[k] + napm);
+        std::vector<float> wf(napm);
+        for (int j = 0; j < napm; ++j) wf[j] = (float)src[k][j];
+        CU(cudaMalloc(&g.d_wf[k], sizeof(float) * napm));
+        CU(cudaMemcpy(g.d_wf[k], wf.data(), sizeof(float) * napm, cudaMemcpyHostToDevice));
     }
     g.wsum[0] = eigen_order_sum(mass, napm);
     g.wsum[1] = eigen_order_sum(ones.data(), napm);
@@ -397,6 +407,9 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
             g.half[k]     = g.L[k] / 2;            // ipp:128
             g.inv_unit[k] = 4294967296.0 / g.L[k];
             g.hsafe[k]    = (float)(g.half[k] * (1.0 - 1e-6));
+            g.ff.L[k]     = bk;
+            g.ff.invL[k]  = (float)(1.0 / g.L[k]);
+            g.ff.hs2[k]   = (float)(g.half[k] * (1.0 - 1e-5));
         }
     }
     std::memcpy(c->h_box.data(), box9, sizeof(float) * 9 * (size_t)nframes);
@@ -424,24 +437,65 @@ static bool stream_block(const Group& g, int* M)
     return true;
 }
 
-template <int MODE>
-static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem)
+// Constants of the FP32 bracket (b2a_kernels_fast.cuh).  The fast path assumes centre = x_0 + sum w_j u_j / W, i.e. that
+// W is the sum of the weights (not the guarded divisor of a neutral molecule's dipole), and that rho = sum|w| / |W| is
+// moderate (charge centres of nearly neutral molecules amplify every rounding error); otherwise it stays off.
+static FastParams fast_params(const Group& g, int com, int mode)
+{
+    FastParams fp{};
+    if (const char* e = getenv("B2A_FAST")) mode = atoi(e);
+    if (mode <= 0 || g.csr || g.h_w[com].empty()) return fp;
+    const double W = g.wsum[com];
+    double       sum = 0.0, sabs = 0.0;
+    for (double w : g.h_w[com]) { sum += w; sabs += std::fabs(w); }
+    if (!std::isnormal(W) || !(std::fabs(sum / W - 1.0) < 1e-12)) return fp;
+    const double rho = sabs / std::fabs(W);
+    if (!(rho < 1e3)) return fp;
+    const double eps = std::ldexp(1.0, -24);
+    fp.enabled = mode >= 2 ? 2 : 1;
+    fp.invW    = (float)(1.0 / W);
+    fp.e1      = (float)(1.05 * eps);
+    fp.e2      = (float)(1.05 * eps * rho);
+    fp.e3      = (float)(1.05 * eps * rho * (g.napm + 4));
+    return fp;
+}
+
+template <int MODE, int NAPM_T>
+static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode)
 {
     a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;
     a.atom0 = g.h_index[0]; a.nmol = g.nmol; a.napm = g.napm;
     a.w = g.d_w[com]; a.wsum = make_div(g.wsum[com]); a.geom = c->d_geom;
     a.tile_floats = ((M * g.napm * 3 + 8) + 3) & ~3;
-    // frames per block: deep enough to pipeline, small enough to fill the machine
-    const int mblocks = (g.nmol + M - 1) / M;
-    int fpb = 16;
-    while (fpb > 4 && (long long)mblocks * ((c->nframes + fpb - 1) / fpb) < 4LL * c->sm_count) fpb /= 2;
-    a.frames_per_block = fpb;
-    const size_t smem = (size_t)kStages * a.tile_floats * 4 + kStages * 8 + sizeof(FrameGeom) * fpb + sizeof(double) * g.napm + extra_smem;
-    CU(cudaFuncSetAttribute(k_stream<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(mblocks, (c->nframes + fpb - 1) / fpb);
-    k_stream<MODE><<<grid, M, smem, c->stream>>>(a);
+    a.wf = g.d_wf[com];
+    a.fp = fast_params(g, com, MODE == 0 ? 0 : fast_mode);
+    // work items: (molecule block, 4 consecutive frames); persistent blocks pull them from a counter
+    a.mblocks     = (g.nmol + M - 1) / M;
+    a.item_frames = 4;
+    if (const char* e = getenv("B2A_ITEM_FRAMES")) a.item_frames = std::max(1, atoi(e));
+    a.nitems      = a.mblocks * ((c->nframes + a.item_frames - 1) / a.item_frames);
+    if (!c->d_work) CU(cudaMalloc(&c->d_work, sizeof(unsigned)));
+    a.work = c->d_work;
+    size_t smem = (size_t)kStages * a.tile_floats * 4 + kStages * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
+    if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut : 0);
+    auto kern = k_stream<MODE, NAPM_T>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M + 32, smem));
+    if (per_sm < 1) return fail(B2A_ERR_UNSUPPORTED, "streaming kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+    const int grid = std::min(a.nitems, per_sm * c->sm_count);
+    CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned), c->stream));
+    kern<<<grid, M + 32, smem, c->stream>>>(a);   // M consumer threads (one molecule each) + one producer warp
     CU(cudaGetLastError());
     return B2A_OK;
+}
+
+template <int MODE>
+static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode = 0)
+{
+    // three-site molecules (water) get fully unrolled atom loops; everything else runs the generic instantiation
+    if (g.napm == 3) return launch_stream_t<MODE, 3>(c, g, com, M, a, extra_smem, fast_mode);
+    return launch_stream_t<MODE, 0>(c, g, com, M, a, extra_smem, fast_mode);
 }
 
 // ---- K1 launch + cache -----------------------------------------------------------------------------------------
@@ -606,6 +660,16 @@ extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
     if (a->kind != ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF", id);
     a->symmetric = symmetric;
     a->paranoid  = paranoid;
+    return B2A_OK;
+}
+
+extern "C" int b2a_acc_fast(b2a_ctx* c, int id, int mode)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (a->kind == ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is an RDF: use b2a_rdf_tune", id);
+    if (mode < 0 || mode > 2) return fail(B2A_ERR_ARG, "b2a_acc_fast: mode must be 0 (FP64 only), 1 (FP32 bracket + FP64 queue) or 2 (validate)");
+    a->fast = mode;
     return B2A_OK;
 }
 
@@ -859,7 +923,8 @@ static int accumulate_density(b2a_ctx* c, Acc& a)
         Timed      tm(c, 3);
         StreamArgs sa{};
         sa.den = d; sa.hist = a.d_hist; sa.stats = a.d_hist + a.ndev; sa.smem_bins = smem_bins;
-        return launch_stream<1>(c, *g, s.com, M, sa, sizeof(unsigned) * smem_bins);
+        sa.df.low = s.low; sa.df.up = s.up; sa.df.low2 = s.low2; sa.df.up2 = s.up2; sa.df.inv_dbin = (float)(1.0 / s.dbin);
+        return launch_stream<1>(c, *g, s.com, M, sa, sizeof(unsigned) * smem_bins, a.fast);
     }
     const size_t smem      = sizeof(double) * g->napm + sizeof(unsigned) * smem_bins;
     CU(cudaFuncSetAttribute(k2_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1060,6 +1125,19 @@ extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
     for (int k = 0; k <= nA; ++k) fedge[k] = (float)edge[k];
     CU(cudaMalloc(&a->d_fedge, sizeof(float) * (nA + 2)));
     CU(cudaMemcpy(a->d_fedge, fedge.data(), sizeof(float) * (nA + 2), cudaMemcpyHostToDevice));
+    {   // fast path: cos cell ci = [-1 + 2 ci / N, -1 + 2 (ci + 1) / N) -> the lowest angle bin any value below the upper end of the
+        // NEXT cell can have (one cell of slack for the float rounding of the cell index); the device walks up from there
+        std::vector<unsigned char> lut(kCosLut);
+        for (int ci = 0; ci < kCosLut; ++ci)
+        {
+            const float ub = (float)(-1.0 + 2.0 * (ci + 2) / kCosLut);
+            int         lo = 0;
+            while (lo < nA && ub <= fedge[lo + 1]) ++lo;
+            lut[ci] = (unsigned char)lo;
+        }
+        CU(cudaMalloc(&a->d_lut, kCosLut));
+        CU(cudaMemcpy(a->d_lut, lut.data(), kCosLut, cudaMemcpyHostToDevice));
+    }
     // Radial thresholds in s = t1^2 + t2^2 (calc_orient_mof.cpp:175-179): R = sqrt(s) (IEEE, identical on host and
     // device), selected iff Cr <= R <= CR, meZ = int((R - Cr) / dr).  Everything is monotone in s, so bisection over the
     // bit patterns of positive doubles finds, for every k, the smallest s with meZ >= k; the device only compares.
@@ -1110,7 +1188,12 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
         Timed      tm(c, 4);
         StreamArgs sa{};
         sa.ori = d; sa.cosedge = a.d_cosedge; sa.fedge = a.d_fedge; sa.stab = a.d_stab; sa.hist = a.d_hist; sa.stats = a.d_hist + a.ndev; sa.smem_bins = smem_bins;
-        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins);
+        sa.of.low = s.low; sa.of.up = s.up; sa.of.c1 = s.c1; sa.of.c2 = s.c2; sa.of.Cr = s.Cr; sa.of.CR = s.CR;
+        sa.of.inv_dr = 1.0f / s.dr; sa.of.cr_lo = s.Cr > 0.f ? s.Cr : -3.0e38f;
+        sa.lut = a.d_lut;
+        // the bracket needs monotone radial bins
+        const int fast = (s.dr > 0.f && s.CR > s.Cr) ? a.fast : 0;
+        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins, fast);
     }
     const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins;
     CU(cudaFuncSetAttribute(k4_orient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

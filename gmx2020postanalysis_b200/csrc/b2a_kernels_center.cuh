@@ -14,6 +14,14 @@
 namespace b2a
 {
 
+struct FastFrame   // per frame, FP32 view of the box for the bracketed fast paths (b2a_kernels_fast.cuh)
+{
+    float L[3];      // the float box diagonal itself (Lbox is its widening, so this is exact)
+    float invL[3];   // fl(1 / L)
+    float hs2[3];    // (L/2)(1 - 1e-5): |offset| below this proves the whole-box shift count
+    float pad[3];
+};
+
 struct FrameGeom   // per frame; filled on the host at submit time from the float box diagonal (ipp:72-74)
 {
     double L[3];         // Lbox[k] = double(fr->box[k][k])
@@ -21,7 +29,10 @@ struct FrameGeom   // per frame; filled on the host at submit time from the floa
     double inv_unit[3];  // 2^32 / Lbox[k]: box-fraction fixed point used by the RDF fast path
     float  hsafe[3];     // float slightly BELOW Lbox[k]/2: |x - ref| < hsafe in FP32 proves that no unwrap shift is needed
     float  pad;
+    FastFrame ff;
+    double pad16;        // sizeof == 144: the streaming kernels fetch one FrameGeom per stage with a 16-byte-granular bulk copy
 };
+static_assert(sizeof(FrameGeom) % 16 == 0, "FrameGeom is moved with cp.async.bulk");
 
 // Division by a block-invariant divisor, correctly rounded, in 3 FP64 instructions instead of the ~35 of __ddiv_rn:
 // with y = RN(1/d) from the host (IEEE division), q0 = RN(x*y), r = x - d*q0 (exact in an FMA), q = RN(q0 + r*y) is the

@@ -9,12 +9,13 @@
 // (profiles/r01_hbm.md).  The per-molecule arithmetic is the same FP64 code as in the direct kernels.
 #pragma once
 
-#include "b2a_kernels_orient.cuh"
+#include "b2a_kernels_fast.cuh"
 
 namespace b2a
 {
 
-constexpr int kStages = 4;
+constexpr int kStages   = 4;
+constexpr int kFastQueue = 1024;  // undecided (molecule, frame) entries per block; drained when half full, overflow runs inline
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -54,7 +55,10 @@ struct StreamArgs
     const double*    w;
     DivConst         wsum;
     const FrameGeom* geom;
-    int              frames_per_block;
+    int              item_frames;    // frames per work item
+    int              mblocks;        // molecule blocks (blockDim.x molecules each)
+    int              nitems;         // mblocks * ceil(nframes / item_frames)
+    unsigned*        work;           // device counter, zeroed before the launch: next work item to hand out
     int              tile_floats;    // floats reserved per stage (blockDim.x * napm * 3 + 8)
     // MODE 0: centres
     double*          cen;
@@ -68,96 +72,228 @@ struct StreamArgs
     unsigned long long* hist;
     unsigned long long* stats;
     int              smem_bins;
+    // FP32-bracketed fast path (b2a_kernels_fast.cuh)
+    FastParams           fp;
+    const float*         wf;     // weights rounded to float
+    DensityFast          df;
+    OrientFast           of;
+    const unsigned char* lut;    // MODE 2: kCosLut first-candidate angle bins
 };
 
-// MODE 0 = K1 centres (+fixed point), 1 = K2 density, 2 = K4 orientation
-template <int MODE>
-__global__ void __launch_bounds__(256) k_stream(const __grid_constant__ StreamArgs a)
+struct StageDesc { int m, f, poff, pad; };   // molecule block, frame, float offset of the block's first atom inside the stage; m < 0: end
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// MODE 0 = K1 centres (+fixed point), 1 = K2 density, 2 = K4 orientation.  NAPM_T: atoms per molecule at compile time
+// (loops unroll completely), 0 = run-time value.
+//
+// Persistent, warp-specialised blocks.  The grid is sized to the machine (resident blocks x SMs); every block pulls work
+// items (molecule block, item_frames consecutive frames) from a global counter.  One PRODUCER warp streams the
+// (molecule block, frame) tiles plus that frame's geometry through a kStages-deep ring with cp.async.bulk (UBLKCP),
+// signalling a `full` mbarrier per stage; the CONSUMER warps (blockDim.x/32 - 1, one molecule per thread) wait on `full`,
+// compute out of shared memory and release the stage by arriving on its `empty` mbarrier, warp by warp.  There is no
+// block-wide barrier inside the stream: a slow warp never stalls the others, the ring never drains between items, and
+// tables / histogram zero+flush happen once per block for the whole launch.
+template <int MODE, int NAPM_T>
+__global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamArgs a)
 {
     extern __shared__ __align__(16) unsigned char sraw[];
-    // layout: [tiles: kStages x tile_floats floats, 16-B aligned] [bars] [frame geometry] [weights] [edges] [histogram]
+    // layout: [tiles: kStages x tile_floats floats] [frame geometry per stage] [full bars] [empty bars] [stage descriptors]
+    //         [weights] [edges] [float weights] [histogram] [undecided queue] [cos look-up table]
     float*              tiles = reinterpret_cast<float*>(sraw);
-    unsigned long long* bars  = reinterpret_cast<unsigned long long*>(tiles + (size_t)kStages * a.tile_floats);
-    FrameGeom*          sgeom = reinterpret_cast<FrameGeom*>(bars + kStages);          // frames_per_block entries
-    double*             sw    = reinterpret_cast<double*>(sgeom + a.frames_per_block);
-    double*             sedge = sw + a.napm;                                                   // MODE 2: nAngle + 1
+    FrameGeom*          sgeom = reinterpret_cast<FrameGeom*>(tiles + (size_t)kStages * a.tile_floats);     // kStages entries (TMA)
+    unsigned long long* full  = reinterpret_cast<unsigned long long*>(sgeom + kStages);
+    unsigned long long* empty = full + kStages;
+    StageDesc*          sdesc = reinterpret_cast<StageDesc*>(empty + kStages);
+    double*             sw    = reinterpret_cast<double*>(sdesc + kStages);
+    const int           napm  = NAPM_T ? NAPM_T : a.napm;
+    double*             sedge = sw + napm;                                                     // MODE 2: nAngle + 1
     double*             stab  = sedge + (MODE == 2 ? a.ori.nAngle + 1 : 0);                    // MODE 2: nbin1 + 2
     float*              fedge = reinterpret_cast<float*>(stab + (MODE == 2 ? a.ori.nbin1 + 2 : 0));   // MODE 2: nAngle + 1
-    unsigned*           shist = reinterpret_cast<unsigned*>(fedge + (MODE == 2 ? ((a.ori.nAngle + 2) & ~1) : 0));
+    float*              swf   = fedge + (MODE == 2 ? ((a.ori.nAngle + 2) & ~1) : 0);                  // napm rounded up to even
+    unsigned*           shist = reinterpret_cast<unsigned*>(swf + ((napm + 1) & ~1));
+    uint2*              fqueue = reinterpret_cast<uint2*>(shist + (MODE != 0 ? ((a.smem_bins + 1) & ~1) : 0));
+    unsigned char*      slut   = reinterpret_cast<unsigned char*>(fqueue + (MODE != 0 ? kFastQueue : 0));
+    __shared__ unsigned fq_n;
 
-    const int M      = blockDim.x;
-    const int m0     = blockIdx.x * M;
-    const int mvalid = min(M, a.nmol - m0);
-    const int f0     = blockIdx.y * a.frames_per_block;
-    const int f1     = min(a.nframes, f0 + a.frames_per_block);
-    const int nf     = f1 - f0;
-    if (mvalid <= 0 || nf <= 0) return;
-
-    for (int j = threadIdx.x; j < a.napm; j += M) sw[j] = a.w[j];
-    {   // frame geometry once per block: it is indexed by a run-time dimension, which must not end up in local memory
-        const double* src = reinterpret_cast<const double*>(a.geom + f0);
-        double*       dst = reinterpret_cast<double*>(sgeom);
-        for (int j = threadIdx.x; j < nf * (int)(sizeof(FrameGeom) / sizeof(double)); j += M) dst[j] = src[j];
-    }
+    const int T = blockDim.x;          // all threads (prologue / epilogue loops)
+    const int M = blockDim.x - 32;     // consumer threads = molecules per tile
+    for (int j = threadIdx.x; j < napm; j += T) { sw[j] = a.w[j]; if (MODE != 0) swf[j] = a.wf[j]; }
+    if (MODE == 2 && a.fp.enabled)
+        for (int j = threadIdx.x; j < kCosLut / 4; j += T) reinterpret_cast<unsigned*>(slut)[j] = reinterpret_cast<const unsigned*>(a.lut)[j];
+    if (threadIdx.x == 0) fq_n = 0;
     if (MODE == 2)
     {
-        for (int j = threadIdx.x; j <= a.ori.nAngle; j += M) { sedge[j] = a.cosedge[j]; fedge[j] = a.fedge[j]; }
-        for (int j = threadIdx.x; j < a.ori.nbin1 + 2; j += M) stab[j] = a.stab[j];
+        for (int j = threadIdx.x; j <= a.ori.nAngle; j += T) { sedge[j] = a.cosedge[j]; fedge[j] = a.fedge[j]; }
+        for (int j = threadIdx.x; j < a.ori.nbin1 + 2; j += T) stab[j] = a.stab[j];
     }
     const OrientTabs tb{ sedge, fedge, stab };
     if (MODE != 0)
-        for (int b = threadIdx.x; b < a.smem_bins; b += M) shist[b] = 0;
+        for (int b = threadIdx.x; b < a.smem_bins; b += T) shist[b] = 0;
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < kStages; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)(M >> 5)); }
         mbar_fence_init();
     }
     __syncthreads();
 
-    // the byte range of this block's molecules in frame f, widened to 16-byte boundaries
-    const size_t   first_float = ((size_t)a.atom0 + (size_t)m0 * a.napm) * 3;
-    const unsigned nbytes      = (unsigned)mvalid * a.napm * 12u;
-    auto issue = [&](int k) {   // k-th frame of this block -> stage k % kStages   (thread 0 only)
-        const int            s   = k % kStages;
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + (size_t)(f0 + k) * a.frame_stride + first_float);
-        const unsigned       sh  = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
-        const unsigned       nb  = (sh + nbytes + 15u) & ~15u;
-        mbar_expect_tx(&bars[s], nb);
-        tma_load_1d(tiles + (size_t)s * a.tile_floats, src - sh, nb, &bars[s]);
-    };
-    if (threadIdx.x == 0)
-        for (int k = 0; k < min(kStages, nf); ++k) issue(k);
-
-    const bool active = (int)threadIdx.x < mvalid;
-    const int  i      = m0 + threadIdx.x;
-    unsigned   ndrop = 0, nsel = 0;
+    unsigned   ndrop = 0, nsel = 0, nexact = 0, nbad = 0;
     const bool use_smem = MODE == 1 ? a.smem_bins >= a.den.nbin
                                     : (MODE == 2 ? a.smem_bins >= a.ori.nbin1 * a.ori.nAngle + a.ori.nbin1 : false);
 
-    for (int k = 0; k < nf; ++k)
+    if ((int)threadIdx.x >= M)
     {
-        const int s = k % kStages;
-        mbar_wait(&bars[s], (unsigned)((k / kStages) & 1));
-        const int f = f0 + k;
-        if (active)
+        // ---- producer warp: one elected lane walks the items and keeps the ring full ------------------------------------
+        if (threadIdx.x == M)
         {
-            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(a.x + (size_t)f * a.frame_stride + first_float) & 15u);
-            const float*   p  = tiles + (size_t)s * a.tile_floats + (sh >> 2) + (size_t)threadIdx.x * a.napm * 3;
-            const FrameGeom& g = sgeom[k];
-            if (MODE == 0)
+            // the next item is claimed one item ahead, so the round trip of the global atomic is off the refill path
+            unsigned it = atomicAdd(a.work, 1u), next = atomicAdd(a.work, 1u);
+            int      f = 0, fend = 0, m = -1;
+            for (unsigned n = 0;; ++n)
             {
-                double c0, c1, c2;
-                mol_centers3<true>(p, a.napm, sw, a.wsum, g, c0, c1, c2);
-                double* o = a.cen + (size_t)f * 3 * a.nmol;
-                o[i]                      = c0;
-                o[(size_t)a.nmol + i]     = c1;
-                o[2 * (size_t)a.nmol + i] = c2;
-                if (a.fix)
-                    a.fix[(size_t)f * a.nmol + i] = make_int4(to_fixed(c0, g.inv_unit[0]), to_fixed(c1, g.inv_unit[1]), to_fixed(c2, g.inv_unit[2]), i);
+                const int s = (int)(n % kStages);
+                if (n >= (unsigned)kStages) mbar_wait(&empty[s], ((n / kStages) - 1u) & 1u);
+                if (m >= 0 && f >= fend) { m = -1; it = next; next = atomicAdd(a.work, 1u); }
+                if (m < 0 && it < (unsigned)a.nitems)
+                {
+                    m    = (int)(it % (unsigned)a.mblocks);
+                    f    = (int)(it / (unsigned)a.mblocks) * a.item_frames;
+                    fend = min(a.nframes, f + a.item_frames);
+                }
+                if (m < 0)
+                {
+                    sdesc[s].m = -1;       // end of stream: consumers stop at the first such stage
+                    mbar_arrive(&full[s]);
+                    break;
+                }
+                const int            mvalid = min(M, a.nmol - m * M);
+                const unsigned       nbytes = (unsigned)mvalid * napm * 12u;
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + (size_t)f * a.frame_stride + ((size_t)a.atom0 + (size_t)m * M * napm) * 3);
+                const unsigned       sh  = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+                const unsigned       nb  = (sh + nbytes + 15u) & ~15u;   // the byte range widened to 16-byte boundaries
+                sdesc[s] = StageDesc{ m, f, (int)(s * a.tile_floats + (sh >> 2)), 0 };
+                mbar_expect_tx(&full[s], nb + (unsigned)sizeof(FrameGeom));
+                tma_load_1d(tiles + (size_t)s * a.tile_floats, src - sh, nb, &full[s]);
+                tma_load_1d(&sgeom[s], a.geom + f, (unsigned)sizeof(FrameGeom), &full[s]);
+                ++f;
             }
-            else if (MODE == 1)
+        }
+    }
+    else
+    {
+        // ---- consumer warps ------------------------------------------------------------------------------------------------
+        const unsigned toff = threadIdx.x * (unsigned)napm * 3u;
+        for (unsigned n = 0;; ++n)
+        {
+            const int s = (int)(n % kStages);
+            mbar_wait(&full[s], (n / kStages) & 1u);
+            const StageDesc sd = sdesc[s];
+            if (sd.m < 0) break;   // the stream is in order: nothing follows the first end marker
+            const int f = sd.f;
+            const int i = sd.m * M + (int)threadIdx.x;
+            if (i < a.nmol)
             {
-                const int me = density_molecule<true>(p, a.napm, sw, a.wsum, g, a.den, nsel, ndrop);
+                const float*     p = tiles + sd.poff + toff;
+                const FrameGeom& g = sgeom[s];
+                if (MODE == 0)
+                {
+                    double c0, c1, c2;
+                    mol_centers3<true>(p, napm, sw, a.wsum, g, c0, c1, c2);
+                    double* o = a.cen + (size_t)f * 3 * a.nmol;
+                    o[i]                      = c0;
+                    o[(size_t)a.nmol + i]     = c1;
+                    o[2 * (size_t)a.nmol + i] = c2;
+                    if (a.fix)
+                        a.fix[(size_t)f * a.nmol + i] = make_int4(to_fixed(c0, g.inv_unit[0]), to_fixed(c1, g.inv_unit[1]), to_fixed(c2, g.inv_unit[2]), i);
+                }
+                else if (MODE == 1)
+                {
+                    int me;
+                    if (a.fp.enabled == 1)
+                    {
+                        me = density_fast<true>(p, napm, swf, a.fp, g.ff, a.den, a.df, nsel, ndrop);
+                        if (me == -2)
+                        {
+                            const unsigned slot = atomicAdd(&fq_n, 1u);
+                            if (slot < (unsigned)kFastQueue) fqueue[slot] = make_uint2((unsigned)i, (unsigned)f);
+                            else { me = density_molecule<true>(p, napm, sw, a.wsum, g, a.den, nsel, ndrop); nexact++; }
+                        }
+                    }
+                    else
+                    {
+                        me = density_molecule<true>(p, napm, sw, a.wsum, g, a.den, nsel, ndrop);
+                        if (a.fp.enabled == 2)   // validation: a proven FP32 answer must equal the FP64 one
+                        {
+                            unsigned fs = 0, fd = 0;
+                            const int mf = density_fast<true>(p, napm, swf, a.fp, g.ff, a.den, a.df, fs, fd);
+                            if (mf == -2) nexact++;
+                            else if (mf != me) nbad++;
+                        }
+                    }
+                    if (me >= 0)
+                    {
+                        if (use_smem) atomicAdd(&shist[me], 1u);
+                        else atomicAdd(&a.hist[me], 1ull);
+                    }
+                }
+                else
+                {
+                    int cz = -1, ca = -1;
+                    if (a.fp.enabled == 1)
+                    {
+                        if (!orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, cz, ca, nsel, ndrop))
+                        {
+                            cz = ca = -1;
+                            const unsigned slot = atomicAdd(&fq_n, 1u);
+                            if (slot < (unsigned)kFastQueue) fqueue[slot] = make_uint2((unsigned)i, (unsigned)f);
+                            else { orient_molecule<true>(p, napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop); nexact++; }
+                        }
+                    }
+                    else
+                    {
+                        orient_molecule<true>(p, napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop);
+                        if (a.fp.enabled == 2)
+                        {
+                            unsigned fs = 0, fd = 0;
+                            int      fz = -1, fa = -1;
+                            if (!orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, fz, fa, fs, fd)) nexact++;
+                            else if (fz != cz || fa != ca) nbad++;
+                        }
+                    }
+                    if (cz >= 0)
+                    {
+                        if (use_smem) atomicAdd(&shist[cz], 1u);
+                        else atomicAdd(&a.hist[cz], 1ull);
+                    }
+                    if (ca >= 0)
+                    {
+                        if (use_smem) atomicAdd(&shist[ca], 1u);
+                        else atomicAdd(&a.hist[ca], 1ull);
+                    }
+                }
+            }
+            __syncwarp();
+            if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);   // this warp is done with stage s
+        }
+    }
+    if (MODE != 0)
+    {
+        __syncthreads();
+        // undecided molecules: literal FP64 evaluation, read back from global memory (their stage has been refilled)
+        const unsigned nq = min(fq_n, (unsigned)kFastQueue);
+        for (unsigned e = threadIdx.x; e < nq; e += T)
+        {
+            const uint2      ent = fqueue[e];
+            const int        f   = (int)ent.y;
+            const float*     pg  = a.x + (size_t)f * a.frame_stride + ((size_t)a.atom0 + (size_t)ent.x * napm) * 3;
+            const FrameGeom& g   = a.geom[f];
+            nexact++;
+            if (MODE == 1)
+            {
+                const int me = density_molecule<false>(pg, napm, sw, a.wsum, g, a.den, nsel, ndrop);
                 if (me >= 0)
                 {
                     if (use_smem) atomicAdd(&shist[me], 1u);
@@ -167,7 +303,7 @@ __global__ void __launch_bounds__(256) k_stream(const __grid_constant__ StreamAr
             else
             {
                 int cz, ca;
-                orient_molecule<true>(p, a.napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop);
+                orient_molecule<false>(pg, napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop);
                 if (cz >= 0)
                 {
                     if (use_smem) atomicAdd(&shist[cz], 1u);
@@ -180,24 +316,24 @@ __global__ void __launch_bounds__(256) k_stream(const __grid_constant__ StreamAr
                 }
             }
         }
-        __syncthreads();   // every thread is done with stage s: it may be refilled
-        if (threadIdx.x == 0 && k + kStages < nf) issue(k + kStages);
-    }
-    if (MODE != 0)
-    {
+        __syncthreads();
         const int nb = MODE == 1 ? a.den.nbin : a.ori.nbin1 * a.ori.nAngle + a.ori.nbin1;
         if (use_smem)
-            for (int b = threadIdx.x; b < nb; b += M)
+            for (int b = threadIdx.x; b < nb; b += T)
                 if (shist[b]) atomicAdd(&a.hist[b], (unsigned long long)shist[b]);
         for (int o = 16; o > 0; o >>= 1)
         {
             ndrop += __shfl_xor_sync(0xffffffffu, ndrop, o);
             nsel += __shfl_xor_sync(0xffffffffu, nsel, o);
+            nexact += __shfl_xor_sync(0xffffffffu, nexact, o);
+            nbad += __shfl_xor_sync(0xffffffffu, nbad, o);
         }
         if ((threadIdx.x & 31) == 0)
         {
             if (ndrop) atomicAdd(&a.stats[1], (unsigned long long)ndrop);
             if (nsel) atomicAdd(&a.stats[4], (unsigned long long)nsel);
+            if (nexact) atomicAdd(&a.stats[2], (unsigned long long)nexact);
+            if (nbad) atomicAdd(&a.stats[7], (unsigned long long)nbad);
         }
     }
 }

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libb2a.so")
 _lib = None
 _P = C.c_void_p
 
-STAT_FRAMES, STAT_DROPPED, STAT_EXACT, STAT_MOVED, STAT_SELECTED, STAT_PAIRS, STAT_OVERFLOW = range(7)
+STAT_FRAMES, STAT_DROPPED, STAT_EXACT, STAT_MOVED, STAT_SELECTED, STAT_PAIRS, STAT_OVERFLOW, STAT_MISPROVEN = range(8)
 STAT_NSLOTS = 8
 COM_MASS, COM_GEOMETRY, COM_CHARGE, COM_DIPOLE = range(4)
 
@@ -22,7 +22,7 @@ SYMBOLS = [
     "b2a_pinned_alloc", "b2a_pinned_free", "b2a_set_group", "b2a_set_group_full", "b2a_set_group_wsum", "b2a_group_nmol",
     "b2a_submit_batch", "b2a_batch_frames", "b2a_centers", "b2a_centers_batch", "b2a_positions",
     "b2a_density_create", "b2a_rdf_create", "b2a_orient_create", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
-    "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_invalidate", "b2a_timing_enable",
+    "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_acc_fast", "b2a_invalidate", "b2a_timing_enable",
     "b2a_timing_read",
 ]
 
@@ -92,6 +92,7 @@ def load():
         L.b2a_rdf_normalise.argtypes = [_P, C.c_int, C.c_int, _P]
         L.b2a_rdf_tune.argtypes = [_P, C.c_int, C.c_int, C.c_int]
         L.b2a_rdf_cells.argtypes = [_P, C.c_int, C.c_int]
+        L.b2a_acc_fast.argtypes = [_P, C.c_int, C.c_int]
         L.b2a_invalidate.argtypes = [_P]
         L.b2a_timing_enable.argtypes = [_P, C.c_int]
         L.b2a_timing_read.argtypes = [_P, _P, _P]
@@ -224,6 +225,10 @@ class Context:
 
     def rdf_cells(self, acc, mode):
         check(self.L.b2a_rdf_cells(self._h, acc, mode))
+
+    def acc_fast(self, acc, mode):
+        """density / orient: 0 literal FP64, 1 FP32 bracket + FP64 queue (default), 2 validate (STAT_MISPROVEN)."""
+        check(self.L.b2a_acc_fast(self._h, acc, mode))
 
     def invalidate(self):
         """Drop cached centres so the next accumulate redoes the whole path on the resident batch."""

@@ -140,11 +140,14 @@ typedef struct b2a_orient_spec
 enum {
     B2A_STAT_FRAMES   = 0,  /* frames accumulated */
     B2A_STAT_DROPPED  = 1,  /* samples whose bin lies outside the array (memory corruption in the reference) */
-    B2A_STAT_EXACT    = 2,  /* rdf: pairs re-evaluated in FP64 because FP32 could not decide the bin */
+    B2A_STAT_EXACT    = 2,  /* samples (rdf: pairs; density/orient: molecules) re-evaluated in FP64 because the FP32
+                               bracket could not decide them */
     B2A_STAT_MOVED    = 3,  /* rdf: of those, pairs whose bin changed */
     B2A_STAT_SELECTED = 4,  /* molecules passing the region filter (summed over frames) */
     B2A_STAT_PAIRS    = 5,  /* rdf: pair distances physically evaluated */
     B2A_STAT_OVERFLOW = 6,  /* rdf: exact-queue overflows handled inline */
+    B2A_STAT_MISPROVEN = 7, /* density/orient validation mode (b2a_acc_fast 2): samples whose FP32-proven result differs
+                               from the FP64 evaluation; must be 0 */
     B2A_STAT_NSLOTS   = 8
 };
 
@@ -175,6 +178,11 @@ int b2a_rdf_normalise(const uint64_t* counts, int nbin, int Rbin, double* g);
  * region filter into one slab (counts are identical); paranoid=1 re-evaluates EVERY pair in FP64
  * (validation of the FP32 error bound; slow).                                                      */
 int b2a_rdf_tune(b2a_ctx* ctx, int acc, int symmetric, int paranoid);
+/* density / orientation accumulators: 1 (default) = every molecule is first evaluated in FP32 with a rigorous error
+ * bound and only the undecided ones are re-evaluated by the literal FP64 code (counts are identical, the kernel reaches
+ * the HBM roofline); 0 = literal FP64 for every molecule; 2 = validation: both, B2A_STAT_MISPROVEN counts disagreements.
+ * The environment variable B2A_FAST overrides the mode.                                                             */
+int b2a_acc_fast(b2a_ctx* ctx, int acc, int mode);
 /* Cell-binned evaluation for cut-offs much shorter than the box (the brute-force loop of calc_rdf_region.cpp:73-95
  * wastes > 99 % of its pairs when Rm = 3 nm in a 34 nm box; pattern and its exactness check in the reference:
  * src/test/nb_cellSearch_anyBoxSize.cpp:194-299).  Counts are identical to the all-pairs evaluation.

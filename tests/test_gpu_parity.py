@@ -350,6 +350,54 @@ def test_dipole_orientation_config4_shape(gpu_ctx_factory):
     assert np.array_equal(got[:90].reshape(90, 1), exp_o) and got[90] == exp_n[0] == 5000 * K
 
 
+# ---- FP32-bracketed fast paths of K2 / K4: proven answers must equal the literal FP64 ones -------------------------
+@pytest.mark.parametrize("which", ["water", "il", "water_shaken"])
+def test_fast_paths_validate_against_fp64(gpu_ctx_factory, which):
+    """Mode 2 evaluates every molecule both ways and counts FP32-proven results that the FP64 code contradicts (must be
+    0); modes 0 (FP64 only) and 1 (bracket + queue) must give identical histograms and statistics."""
+    if which == "il":
+        system, name, napm = synth.ionic_liquid(2000, 8.7, seed=91), "CAT", None
+    else:
+        system, name = synth.water_box(40000, 10.62, seed=77), "SOL"
+    K = 4
+    x, box = system.frames(0, K), system.box9()
+    if which == "water_shaken":          # centres pushed onto bin edges / region bounds: exercises the undecided queue
+        L = float(np.float32(box[0]))
+        x = x.copy()
+        x[:, :, 2] = np.round(x[:, :, 2] / (L / 64)) * np.float32(L / 64)
+        x[:, :, 0] += np.float32(3.0 * L)        # whole system far outside [0, L)
+        x[:, 1::9, 1] += np.float32(2.0 * L)     # one atom of every third molecule two boxes away: multi-box unwrap
+    ctx = gpu_ctx_factory(system.natoms, K)
+    _groups(ctx, system, [name])
+    L = float(np.float32(box[0]))
+    xoff = 3.0 * L if which == "water_shaken" else 0.0
+    dens = dict(grp=0, com=0, dim=2, low=0.0, up=L, dbin=float(np.float32(L) / np.float32(64)), nbin=64, upper_inclusive=0,
+                dim2=0, low2=0.1 * L + xoff, up2=0.9 * L + xoff)
+    ori = dict(grp=0, com=0, DIMN=2, low=0.2 * L, up=0.9 * L, c1=0.5 * L + xoff, c2=0.5 * L, dr=0.05, CR=0.45 * L, Cr=0.3, nAngle=90,
+               tp1=1, tp2=2, tp3=3, DIMNOrient=1, method=1)
+    ori2 = dict(ori, method=2, nAngle=180, DIMNOrient=0, Cr=0.0, dr=0.011)
+    ctx.submit(x, box)
+    for kind, spec in (("density", dens), ("orient", ori), ("orient", ori2)):
+        res = []
+        for mode in (0, 1, 2):
+            acc = ctx.density_create(**spec) if kind == "density" else ctx.orient_create(**spec)
+            ctx.acc_fast(acc, mode)
+            ctx.accumulate(acc)
+            res.append(ctx.read(acc, ctx.acc_size(acc)))
+        (c0, s0), (c1, s1), (c2, s2) = res
+        assert c0.sum() > 0
+        assert np.array_equal(c0, c1) and np.array_equal(c0, c2), kind
+        assert int(s2[lib.STAT_MISPROVEN]) == 0, kind
+        for st in (lib.STAT_DROPPED, lib.STAT_SELECTED, lib.STAT_FRAMES):
+            assert int(s0[st]) == int(s1[st]) == int(s2[st]), (kind, st)
+        nmol = ctx.nmol(0) * K
+        assert int(s1[lib.STAT_EXACT]) == int(s2[lib.STAT_EXACT])
+        if which != "water_shaken":
+            assert int(s1[lib.STAT_EXACT]) < 0.05 * nmol, (kind, int(s1[lib.STAT_EXACT]), nmol)   # the bracket decides almost all
+        else:
+            assert int(s1[lib.STAT_EXACT]) > 0
+
+
 # ---- cell-binned RDF (SURVEY 8f-1): identical counts to the all-pairs evaluation ---------------------------------
 def _rdf_gpu_cells(ctx, system, g0, g1, K, spec, Rm, Rbin, cells, paranoid=0, symmetric=0):
     _groups(ctx, system, [g0, g1])

@@ -66,10 +66,15 @@ def main():
     rows = []
     ms = timed(k1, "k1_centers")
     rows.append(("k1_centers (mass centres, matd + fixed point written)", ms, K * (nat * 12 + nmol * (24 + 16))))
-    ms = timed(lambda: ctx.accumulate(den), "k2_density")
-    rows.append(("k2_density (centre z -> 100-bin histogram, fused)", ms, K * nat * 12))
-    ms = timed(lambda: ctx.accumulate(ori), "k4_orient")
-    rows.append(("k4_orient (centre + bisector angle histogram, fused)", ms, K * nat * 12))
+    for mode, tag in ((1, "FP32 bracket + FP64 queue"), (0, "literal FP64")):
+        for acc, slot, what in ((den, "k2_density", "k2_density (centre z -> 100-bin histogram, fused)"),
+                                (ori, "k4_orient", "k4_orient (centre + bisector angle histogram, fused)")):
+            ctx.acc_fast(acc, mode)
+            ctx.reset(acc)
+            ms = timed(lambda: ctx.accumulate(acc), slot)
+            cnt, st = ctx.read(acc, ctx.acc_size(acc))
+            rows.append((f"{what} [{tag}; {int(st[lib.STAT_EXACT])} of {int(st[lib.STAT_FRAMES]) * nmol} molecules re-evaluated in FP64]",
+                         ms, K * nat * 12))
     for name, ms, nbytes in rows:
         gbs = nbytes / (ms * 1e-3) / 1e9
         print(json.dumps({"kernel": name, "ms_per_launch": ms, "frames": K, "atoms": nat, "algorithmic_bytes": nbytes,
