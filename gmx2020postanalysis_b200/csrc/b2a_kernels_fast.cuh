@@ -132,47 +132,26 @@ struct OrientFast
     float cr_lo;                             // Cr when Cr > 0, else -huge: `Cr <= R` is then always true (R >= 0)
 };
 
-// returns 1: proven, cell_z / cell_a / nsel / ndrop set exactly like orient_molecule(); 0: undecided (nothing touched)
+// returns 1: proven, cell_z / cell_a / nsel / ndrop set exactly like orient_molecule(); 0: undecided (nothing touched).
+// Written branch-light: every "cannot decide" condition is accumulated into one predicate and tested once; only the two
+// proven-outside cases (slab filter, radial selection) leave early.
 template <bool SMEM>
 __device__ __forceinline__ int orient_fast(const float* p, int napm, const float* swf, const FastParams& fp, const FastFrame& ff,
                                            const OrientDev& d, const OrientFast& of, const float* fedge, const unsigned char* lut,
                                            int& cell_z, int& cell_a, unsigned& nsel, unsigned& ndrop)
 {
     const float r0 = ldf<SMEM>(p), r1 = ldf<SMEM>(p + 1), r2 = ldf<SMEM>(p + 2);
+    const float L0 = ff.L[0], L1 = ff.L[1], L2 = ff.L[2], iL0 = ff.invL[0], iL1 = ff.invL[1], iL2 = ff.invL[2];
     float       a0 = 0.f, a1 = 0.f, a2 = 0.f, mu0 = 0.f, mu1 = 0.f, mu2 = 0.f, m_d = 0.f;
 #pragma unroll 2
     for (int j = 1; j < napm; ++j)
     {
-        const float u0 = fast_offset(ldf<SMEM>(p + 3 * j), r0, ff.L[0], ff.invL[0], mu0, m_d);
-        const float u1 = fast_offset(ldf<SMEM>(p + 3 * j + 1), r1, ff.L[1], ff.invL[1], mu1, m_d);
-        const float u2 = fast_offset(ldf<SMEM>(p + 3 * j + 2), r2, ff.L[2], ff.invL[2], mu2, m_d);
+        const float u0 = fast_offset(ldf<SMEM>(p + 3 * j), r0, L0, iL0, mu0, m_d);
+        const float u1 = fast_offset(ldf<SMEM>(p + 3 * j + 1), r1, L1, iL1, mu1, m_d);
+        const float u2 = fast_offset(ldf<SMEM>(p + 3 * j + 2), r2, L2, iL2, mu2, m_d);
         const float w  = swf[j];
         a0 = __fmaf_rn(w, u0, a0); a1 = __fmaf_rn(w, u1, a1); a2 = __fmaf_rn(w, u2, a2);
     }
-    if (!(mu0 < ff.hs2[0] && mu1 < ff.hs2[1] && mu2 < ff.hs2[2])) return 0;
-    const float m_u = fmaxf(mu0, fmaxf(mu1, mu2));
-    const float c[3] = { __fmaf_rn(a0, fp.invW, r0), __fmaf_rn(a1, fp.invW, r1), __fmaf_rn(a2, fp.invW, r2) };
-    // slab filter lowPos <= posc(i, DIMN) <= upPos (:158)
-    const float cz = d.DIMN == 0 ? c[0] : (d.DIMN == 1 ? c[1] : c[2]);
-    const float Ez = fast_center_err(cz, m_u, m_d, fp);
-    const int   in = fast_in_range(cz, Ez, of.low, of.up);
-    if (in < 0) return 0;
-    cell_z = cell_a = -1;
-    if (in == 0) return 1;
-    // R = sqrt(t1^2 + t2^2) (:160-175); |R^ - R| <= sqrt2 (Ec + eps |t|) + 4 eps R  <  1.5 Ec + 6 eps R
-    const float ca = d.DIMN == 0 ? c[1] : c[0], cb = d.DIMN == 2 ? c[1] : c[2];
-    const float Ec = fmaxf(fast_center_err(ca, m_u, m_d, fp), fast_center_err(cb, m_u, m_d, fp));
-    const float ta = ca - of.c1, tb = cb - of.c2;
-    const float R  = sqrtf(__fmaf_rn(ta, ta, tb * tb));
-    const float ER = __fmaf_rn(R, 6.0f * kEps, 1.5f * Ec);
-    if (R + ER < of.cr_lo || R - ER > of.CR) return 1;              // proven not selected
-    if (!(R - ER > of.cr_lo && R + ER < of.CR)) return 0;           // undecided
-    const float q  = (R - of.Cr) * of.inv_dr;
-    const float Eq = __fmaf_rn(ER, of.inv_dr * 1.01f, fabsf(q) * (3.2f * kEps));
-    const float k  = floorf(q);
-    const float fr = q - k;
-    if (!(fr > Eq && fr < 1.0f - Eq) || !(q < 2.0e9f) || q < 0.f) return 0;
-    const int meZ = (int)k;
     // vectors p1 - p2, p1 - p3 (:31-38).  The reference subtracts the unwrapped atoms and applies periodicity(): the
     // result is the representative of x_tp1 - x_tp2 (mod L) in [-L/2, L/2], which fast_offset() computes directly; it is
     // proven (and unique) when |v^| < hs2, and then |v^ - v| <= eps (|d| + |v^|)
@@ -180,46 +159,73 @@ __device__ __forceinline__ int orient_fast(const float* p, int napm, const float
     {
         const float* q1 = p + 3 * d.tp1; const float* q2 = p + 3 * d.tp2; const float* q3 = p + 3 * d.tp3;
         const float  x0 = ldf<SMEM>(q1), x1 = ldf<SMEM>(q1 + 1), x2 = ldf<SMEM>(q1 + 2);
-        v1[0] = fast_offset(x0, ldf<SMEM>(q2), ff.L[0], ff.invL[0], mv0, m_dv);
-        v1[1] = fast_offset(x1, ldf<SMEM>(q2 + 1), ff.L[1], ff.invL[1], mv1, m_dv);
-        v1[2] = fast_offset(x2, ldf<SMEM>(q2 + 2), ff.L[2], ff.invL[2], mv2, m_dv);
-        v2[0] = fast_offset(x0, ldf<SMEM>(q3), ff.L[0], ff.invL[0], mv0, m_dv);
-        v2[1] = fast_offset(x1, ldf<SMEM>(q3 + 1), ff.L[1], ff.invL[1], mv1, m_dv);
-        v2[2] = fast_offset(x2, ldf<SMEM>(q3 + 2), ff.L[2], ff.invL[2], mv2, m_dv);
+        v1[0] = fast_offset(x0, ldf<SMEM>(q2), L0, iL0, mv0, m_dv);
+        v1[1] = fast_offset(x1, ldf<SMEM>(q2 + 1), L1, iL1, mv1, m_dv);
+        v1[2] = fast_offset(x2, ldf<SMEM>(q2 + 2), L2, iL2, mv2, m_dv);
+        v2[0] = fast_offset(x0, ldf<SMEM>(q3), L0, iL0, mv0, m_dv);
+        v2[1] = fast_offset(x1, ldf<SMEM>(q3 + 1), L1, iL1, mv1, m_dv);
+        v2[2] = fast_offset(x2, ldf<SMEM>(q3 + 2), L2, iL2, mv2, m_dv);
     }
-    if (!(mv0 < ff.hs2[0] && mv1 < ff.hs2[1] && mv2 < ff.hs2[2])) return 0;
+    const float h0 = ff.hs2[0], h1 = ff.hs2[1], h2 = ff.hs2[2];
+    bool        und = !(fmaxf(mu0, mv0) < h0 && fmaxf(mu1, mv1) < h1 && fmaxf(mu2, mv2) < h2);   // a shift count is not proven
+    const float m_u = fmaxf(mu0, fmaxf(mu1, mu2));
+    const float c0 = __fmaf_rn(a0, fp.invW, r0), c1 = __fmaf_rn(a1, fp.invW, r1), c2 = __fmaf_rn(a2, fp.invW, r2);
+    // one error bound for all three centre components (|c| replaced by the largest of them)
+    const float Ec = fast_center_err(fmaxf(fabsf(c0), fmaxf(fabsf(c1), fabsf(c2))), m_u, m_d, fp);
+    // slab filter lowPos <= posc(i, DIMN) <= upPos (:158)
+    const float cz = d.DIMN == 0 ? c0 : (d.DIMN == 1 ? c1 : c2);
+    if (!und && (cz + Ec < of.low || cz - Ec > of.up)) { cell_z = cell_a = -1; return 1; }   // proven outside
+    und = und || !(cz - Ec > of.low && cz + Ec < of.up);
+    // R = sqrt(t1^2 + t2^2) (:160-175); |R^ - R| <= sqrt2 (Ec + eps |t|) + 4 eps R (sqrt.approx: 2^-23 relative)  <  1.5 Ec + 8 eps R
+    const float ca = d.DIMN == 0 ? c1 : c0, cb = d.DIMN == 2 ? c1 : c2;
+    const float ta = ca - of.c1, tb = cb - of.c2;
+    float       R;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(__fmaf_rn(ta, ta, tb * tb)));
+    const float ER = __fmaf_rn(R, 8.0f * kEps, 1.5f * Ec);
+    if (!und && (R + ER < of.cr_lo || R - ER > of.CR)) { cell_z = cell_a = -1; return 1; }   // proven not selected
+    und = und || !(R - ER > of.cr_lo && R + ER < of.CR);
+    const float q  = (R - of.Cr) * of.inv_dr;
+    const float Eq = __fmaf_rn(ER, of.inv_dr * 1.01f, fabsf(q) * (3.2f * kEps));
+    const float k  = floorf(q);
+    const float fr = q - k;
+    und = und || !(fr > Eq && fr < 1.0f - Eq && q < 2.0e9f && q >= 0.f);
     const float m_v = fmaxf(mv0, fmaxf(mv1, mv2));
     const float Ev  = (1.05f * kEps) * (m_dv + m_v);
-    float vo[3], Evo;
+    float vo0, vo1, vo2, Evo;
     if (d.method == 2)
     {
-        vo[0] = __fmaf_rn(v1[1], v2[2], -(v1[2] * v2[1]));
-        vo[1] = __fmaf_rn(v1[2], v2[0], -(v1[0] * v2[2]));
-        vo[2] = __fmaf_rn(v1[0], v2[1], -(v1[1] * v2[0]));
+        vo0 = __fmaf_rn(v1[1], v2[2], -(v1[2] * v2[1]));
+        vo1 = __fmaf_rn(v1[2], v2[0], -(v1[0] * v2[2]));
+        vo2 = __fmaf_rn(v1[0], v2[1], -(v1[1] * v2[0]));
         // |d(ab - cd)| <= Ev (|a|+|b|+|c|+|d|) + 2 Ev^2 + 2 eps (|ab| + |cd|)
         Evo = 1.05f * (4.0f * m_v * Ev + 2.0f * Ev * Ev + 4.0f * kEps * m_v * m_v);
     }
     else
     {
-        vo[0] = v1[0] + v2[0]; vo[1] = v1[1] + v2[1]; vo[2] = v1[2] + v2[2];
-        Evo = 2.1f * Ev + (2.1f * kEps) * m_v;
+        vo0 = v1[0] + v2[0]; vo1 = v1[1] + v2[1]; vo2 = v1[2] + v2[2];
+        Evo = __fmaf_rn(2.1f * kEps, m_v, 2.1f * Ev);
     }
     // cos = vo[DIMNOrient] / |vo| (:41-47 with the unit wall vector): |dcos| <= (1 + sqrt3) Evo / |vo| + rounding
-    const float n2   = __fmaf_rn(vo[2], vo[2], __fmaf_rn(vo[1], vo[1], vo[0] * vo[0]));
-    const float rinv = rsqrtf(n2);
-    const float dot  = d.DIMNOrient == 0 ? vo[0] : (d.DIMNOrient == 1 ? vo[1] : vo[2]);
-    const float cs   = dot * rinv;
-    const float rel  = Evo * rinv;
-    if (!(rel < 0.05f)) return 0;                                   // |vo| not well above its error (also NaN / zero vector)
-    const float Ecs = __fmaf_rn(rel, 3.0f, 10.0f * kEps) + 1.3e-7f; // + the float rounding of the tabulated edges
-    if (!(fabsf(cs) < 1.0f - Ecs)) return 0;                        // near +-1 the reference's acos may return NaN
+    const float n2   = __fmaf_rn(vo2, vo2, __fmaf_rn(vo1, vo1, vo0 * vo0));
+    float       rinv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(n2));
+    const float dot = d.DIMNOrient == 0 ? vo0 : (d.DIMNOrient == 1 ? vo1 : vo2);
+    const float cs  = dot * rinv;
+    const float rel = Evo * rinv;
+    const float Ecs = __fmaf_rn(rel, 3.0f, 10.0f * kEps + 1.3e-7f);   // + the float rounding of the tabulated edges
+    // |vo| must be well above its error and far from denormal (ftz), cos away from +-1 where the reference's acos may be NaN
+    und = und || !(rel < 0.05f && n2 > 1.0e-30f && fabsf(cs) < 1.0f - Ecs);
     // angle bin: start from the first candidate of the cos cell, walk down the (decreasing) edge table
     int ci = (int)((cs + 1.0f) * (0.5f * kCosLut));
     ci     = min(max(ci, 0), kCosLut - 1);
     int lo = lut[ci];
     while (lo < d.nAngle && cs <= fedge[lo + 1]) ++lo;
-    if (!((lo == 0 || cs <= fedge[lo] - Ecs) && (lo >= d.nAngle || cs >= fedge[lo + 1] + Ecs))) return 0;
+    const float e_up = fedge[lo], e_dn = fedge[min(lo + 1, d.nAngle)];
+    und = und || !((lo == 0 || cs <= e_up - Ecs) && (lo >= d.nAngle || cs >= e_dn + Ecs));
+    if (und) return 0;
     // proven: account exactly like orient_molecule()
+    const int meZ = (int)k;
+    cell_z = cell_a = -1;
     nsel++;
     if (meZ >= d.nbin1) { ndrop++; return 1; }
     cell_z = d.nbin1 * d.nAngle + meZ;
