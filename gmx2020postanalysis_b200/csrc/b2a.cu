@@ -3,6 +3,7 @@
 #include "b2a.h"
 
 #include "b2a_kernels_rdf.cuh"
+#include "b2a_kernels_coord.cuh"
 #include "b2a_kernels_stream.cuh"   // pulls in the centre / orientation kernels
 
 #include <algorithm>
@@ -100,7 +101,7 @@ struct Group
     uint64_t valid[4]   = { 0, 0, 0, 0 };   // batch serial the cache belongs to
 };
 
-enum AccKind { ACC_DENSITY, ACC_RDF, ACC_ORIENT };
+enum AccKind { ACC_DENSITY, ACC_RDF, ACC_ORIENT, ACC_COORD };
 
 struct Acc
 {
@@ -108,6 +109,7 @@ struct Acc
     b2a_density_spec   den{};
     b2a_rdf_spec       rdf{};
     b2a_orient_spec    ori{};
+    b2a_coord_spec     coord{};
     size_t             ncounters = 0;       // public counters (reference layout size)
     size_t             ndev      = 0;       // device u64 words before the stats block
     unsigned long long* d_hist   = nullptr; // [ndev + NSLOTS]
@@ -126,6 +128,12 @@ struct Acc
     int       ipt = 0, threads = 0;   // 0 = auto
     int       fast = 1;               // density / orient: 0 literal FP64, 1 FP32 bracket + FP64 queue, 2 validate
     unsigned char* d_lut = nullptr;   // orient: cos cell -> first candidate angle bin
+    // coord
+    int*        d_cnt = nullptr;      // [maxK][n0] pair counts of the last batch
+    unsigned*   d_table = nullptr;    // [maxK][max_count] per-frame histogram of counts of the last batch
+    CoordFrame* d_cframes = nullptr;
+    CoordFrame* h_cframes = nullptr;  // pinned
+    int         table_frames = 0;     // frames of the batch d_table describes
     // orient
     double* d_cosedge = nullptr;
     float*  d_fedge   = nullptr;
@@ -150,6 +158,11 @@ struct b2a_ctx
     std::vector<std::unique_ptr<Acc>> accs;
     double*      d_pos_scratch = nullptr;
     unsigned*    d_work = nullptr;   // work-item counter of the persistent streaming kernels
+    // velocities / forces of the current batch (fr->v, fr->f), uploaded on demand; [0] is unused (x lives in d_x)
+    float*       d_field[3] = { nullptr, nullptr, nullptr };
+    uint64_t     field_serial[3] = { 0, 0, 0 };   // batch serial the upload belongs to
+    double*      d_field_cen = nullptr;
+    size_t       field_cen_n = 0;
     size_t       pos_scratch_n = 0;
     // optional CUDA-event timing per kernel family (bench.py): pairs are resolved lazily in b2a_timing_read
     bool         timing = false;
@@ -226,6 +239,8 @@ static void free_acc(Acc& a)
 {
     cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
     cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab); cudaFree(a.d_lut);
+    cudaFree(a.d_cnt); cudaFree(a.d_table); cudaFree(a.d_cframes);
+    if (a.h_cframes) cudaFreeHost(a.h_cframes);
     cudaFree(a.d_keysA); cudaFree(a.d_keysB); cudaFree(a.d_cellA); cudaFree(a.d_cellB); cudaFree(a.d_sortedB);
     if (a.h_frames) cudaFreeHost(a.h_frames);
 }
@@ -238,6 +253,7 @@ extern "C" void b2a_destroy(b2a_ctx* c)
     for (auto& kv : c->groups) free_group(kv.second);
     for (auto& a : c->accs) if (a) free_acc(*a);
     cudaFree(c->d_x); cudaFree(c->d_geom); cudaFree(c->d_pos_scratch); cudaFree(c->d_work);
+    cudaFree(c->d_field[1]); cudaFree(c->d_field[2]); cudaFree(c->d_field_cen);
     if (c->h_geom) cudaFreeHost(c->h_geom);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -595,6 +611,98 @@ extern "C" int b2a_positions(b2a_ctx* c, int grp, int frame, double* out)
     return B2A_OK;
 }
 
+// ---- velocities / forces (reference ipp:201-339): no unwrapping ------------------------------------------------------
+extern "C" int b2a_submit_field(b2a_ctx* c, int field, int nframes, const float* data)
+{
+    if (!c || !data) return fail(B2A_ERR_ARG, "b2a_submit_field: null argument");
+    if (field != B2A_FIELD_V && field != B2A_FIELD_F) return fail(B2A_ERR_ARG, "b2a_submit_field: field must be B2A_FIELD_V or B2A_FIELD_F");
+    if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
+    if (nframes != c->nframes) return fail(B2A_ERR_ARG, "b2a_submit_field: %d frames, but the current batch holds %d", nframes, c->nframes);
+    CU(cudaSetDevice(c->device));
+    if (!c->d_field[field]) CU(cudaMalloc(&c->d_field[field], (size_t)c->natoms * 3 * sizeof(float) * c->maxK));
+    CU(cudaMemcpyAsync(c->d_field[field], data, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->stream));
+    c->field_serial[field] = c->serial;
+    return B2A_OK;
+}
+
+static int field_ready(b2a_ctx* c, int field, Group** g, int grp)
+{
+    if (field != B2A_FIELD_V && field != B2A_FIELD_F) return fail(B2A_ERR_ARG, "field must be B2A_FIELD_V or B2A_FIELD_F");
+    if (int rc = get_group(c, grp, g)) return rc;
+    if ((*g)->csr) return fail(B2A_ERR_UNSUPPORTED, "velocity / force loaders on a heterogeneous (GmxHandleFull) group are not implemented");
+    if (c->nframes <= 0 || !c->d_field[field] || c->field_serial[field] != c->serial)
+        return fail(B2A_ERR_STATE, "no %s submitted for the current batch (b2a_submit_field)", field == B2A_FIELD_V ? "velocities" : "forces");
+    return B2A_OK;
+}
+
+static int run_field_centers(b2a_ctx* c, int field, Group& g, int com)
+{
+    if (com < 0 || com > 2) return fail(B2A_ERR_ARG, "com(%d) must be 0 (mass), 1 (geometry) or 2 (charge)", com);
+    const size_t n = (size_t)3 * g.nmol * c->nframes;
+    if (c->field_cen_n < n)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_field_cen); c->d_field_cen = nullptr;
+        CU(cudaMalloc(&c->d_field_cen, sizeof(double) * 3 * (size_t)g.nmol * c->maxK));
+        c->field_cen_n = (size_t)3 * g.nmol * c->maxK;
+    }
+    Timed tm(c, 0);
+    dim3  grid((g.nmol + 127) / 128, c->nframes);
+    k1_field_centers<<<grid, 128, sizeof(double) * g.napm, c->stream>>>(c->d_field[field], (size_t)c->natoms * 3, c->nframes, g.d_index, g.nmol,
+                                                                         g.napm, g.d_w[com], make_div(g.wsum[com]), c->d_field_cen);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
+extern "C" int b2a_field_centers_batch(b2a_ctx* c, int field, int grp, int com, double* out)
+{
+    if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_centers_batch: null argument");
+    Group* g;
+    if (int rc = field_ready(c, field, &g, grp)) return rc;
+    CU(cudaSetDevice(c->device));
+    if (int rc = run_field_centers(c, field, *g, com)) return rc;
+    CU(cudaMemcpyAsync(out, c->d_field_cen, sizeof(double) * 3 * g->nmol * c->nframes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
+extern "C" int b2a_field_centers(b2a_ctx* c, int field, int grp, int com, int frame, double* out)
+{
+    if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_centers: null argument");
+    Group* g;
+    if (int rc = field_ready(c, field, &g, grp)) return rc;
+    if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_field_centers: frame %d outside batch of %d", frame, c->nframes);
+    CU(cudaSetDevice(c->device));
+    if (int rc = run_field_centers(c, field, *g, com)) return rc;
+    CU(cudaMemcpyAsync(out, c->d_field_cen + (size_t)frame * 3 * g->nmol, sizeof(double) * 3 * g->nmol, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
+extern "C" int b2a_field_values(b2a_ctx* c, int field, int grp, int frame, double* out)
+{
+    if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_values: null argument");
+    Group* g;
+    if (int rc = field_ready(c, field, &g, grp)) return rc;
+    if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_field_values: frame %d outside batch of %d", frame, c->nframes);
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)g->nmol * g->napm;
+    if (c->pos_scratch_n < n)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_pos_scratch);
+        c->d_pos_scratch = nullptr;
+        CU(cudaMalloc(&c->d_pos_scratch, sizeof(double) * 3 * n));
+        c->pos_scratch_n = n;
+    }
+    k1b_field_values<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_field[field] + (size_t)frame * c->natoms * 3, g->d_index, g->nmol,
+                                                                         g->napm, c->d_pos_scratch);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, c->d_pos_scratch, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
 // ---- accumulators ----------------------------------------------------------------------------------------------
 static int new_acc(b2a_ctx* c, std::unique_ptr<Acc> a, int* id)
 {
@@ -677,7 +785,7 @@ extern "C" int b2a_rdf_cells(b2a_ctx* c, int id, int mode)
 {
     Acc* a;
     if (int rc = get_acc(c, id, &a)) return rc;
-    if (a->kind != ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF", id);
+    if (a->kind != ACC_RDF && a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF or coordination-number accumulator", id);
     if (mode < -1 || mode > 1) return fail(B2A_ERR_ARG, "b2a_rdf_cells: mode must be -1 (auto), 0 (never) or 1 (whenever cells cull)");
     a->cells = mode;
     return B2A_OK;
@@ -937,6 +1045,7 @@ static int accumulate_density(b2a_ctx* c, Acc& a)
 }
 
 static int accumulate_orient(b2a_ctx* c, Acc& a);
+static int accumulate_coord(b2a_ctx* c, Acc& a);
 
 __global__ void k_add_frames(unsigned long long* stats, unsigned long long n) { stats[0] += n; }
 
@@ -952,6 +1061,7 @@ extern "C" int b2a_accumulate(b2a_ctx* c, int id)
         case ACC_DENSITY: rc = accumulate_density(c, *a); break;
         case ACC_RDF: rc = accumulate_rdf(c, *a); break;
         case ACC_ORIENT: rc = accumulate_orient(c, *a); break;
+        case ACC_COORD: rc = accumulate_coord(c, *a); break;
     }
     if (rc) return rc;
     k_add_frames<<<1, 1, 0, c->stream>>>(a->d_hist + a->ndev, (unsigned long long)c->nframes);
@@ -1203,5 +1313,213 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
                                                     g->d_w[s.com], make_div(g->wsum[s.com]), c->d_geom, d, a.d_cosedge, a.d_fedge, a.d_stab, a.d_hist,
                                                     a.d_hist + a.ndev, smem_bins);
     CU(cudaGetLastError());
+    return B2A_OK;
+}
+
+// ---- coordination numbers (K5) -------------------------------------------------------------------------------------
+extern "C" int b2a_coord_create(b2a_ctx* c, const b2a_coord_spec* s, int* id)
+{
+    if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_coord_create: null argument");
+    Group *g0, *g1;
+    if (int rc = get_group(c, s->grp0, &g0)) return rc;
+    if (int rc = get_group(c, s->grp1, &g1)) return rc;
+    if (!(s->Rmin > 0.f) || s->dim < 0 || s->dim > 2 || s->max_count <= 0 || s->max_count > 8192)
+        return fail(B2A_ERR_ARG, "b2a_coord_create: bad spec (Rmin=%g dim=%d max_count=%d)", (double)s->Rmin, s->dim, s->max_count);
+    if (s->com0 < 0 || s->com0 > 3 || s->com1 < 0 || s->com1 > 3) return fail(B2A_ERR_ARG, "com out of range");
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<Acc> a(new Acc);
+    a->kind      = ACC_COORD;
+    a->coord     = *s;
+    a->ncounters = a->ndev = (size_t)s->max_count;
+    CU(cudaMalloc(&a->d_slab_id, sizeof(int) * (size_t)g0->nmol * c->maxK));
+    CU(cudaMalloc(&a->d_slab_cnt, sizeof(unsigned) * 2 * (size_t)c->maxK));
+    CU(cudaMalloc(&a->d_sortedA, sizeof(int4) * (size_t)g0->nmol * c->maxK));
+    CU(cudaMalloc(&a->d_cnt, sizeof(int) * (size_t)g0->nmol * c->maxK));
+    CU(cudaMalloc(&a->d_table, sizeof(unsigned) * (size_t)s->max_count * c->maxK));
+    CU(cudaMalloc(&a->d_cframes, sizeof(CoordFrame) * c->maxK));
+    CU(cudaMallocHost(&a->h_cframes, sizeof(CoordFrame) * c->maxK));
+    return new_acc(c, std::move(a), id);
+}
+
+template <int IPT, int MODE>
+static int launch_coord(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const CoordDev& p, const CellDev& cd, dim3 grid, bool cubic)
+{
+    const b2a_coord_spec& s = a.coord;
+    if (cubic)
+        k5_coord<IPT, 128, true, MODE><<<grid, 128, 0, c->stream>>>(a.d_sortedA, g1.d_fix[s.com1], g0.d_cen[s.com0], g1.d_cen[s.com1], a.d_slab_cnt,
+                                                                  a.d_cframes, p, cd, a.d_cnt, a.d_hist + a.ndev);
+    else
+        k5_coord<IPT, 128, false, MODE><<<grid, 128, 0, c->stream>>>(a.d_sortedA, g1.d_fix[s.com1], g0.d_cen[s.com0], g1.d_cen[s.com1], a.d_slab_cnt,
+                                                                   a.d_cframes, p, cd, a.d_cnt, a.d_hist + a.ndev);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
+static int accumulate_coord(b2a_ctx* c, Acc& a)
+{
+    const b2a_coord_spec& s = a.coord;
+    Group *g0, *g1;
+    if (int rc = get_group(c, s.grp0, &g0)) return rc;
+    if (int rc = get_group(c, s.grp1, &g1)) return rc;
+    if (int rc = ensure_centers(c, *g0, s.com0, true)) return rc;
+    if (int rc = ensure_centers(c, *g1, s.com1, true)) return rc;
+    const int n0 = g0->nmol, n1 = g1->nmol;
+
+    bool cubic = true;
+    CU(cudaStreamSynchronize(c->stream));   // h_cframes reuse
+    for (int f = 0; f < c->nframes; ++f)
+        if (c->h_geom[f].L[0] != c->h_geom[f].L[1] || c->h_geom[f].L[0] != c->h_geom[f].L[2]) cubic = false;
+    // FP32 error of r^2 (x fixed units^2): 3 I2FP + FMUL/FFMA/FFMA -> 5 * 2^-24 relative (7 * 2^-24 with the two axis-ratio
+    // multiplies of a non-cubic box), plus the 2^32 grid: every component of the difference is within 1 unit of the truth, so
+    // |r - r_true| <= sqrt(3) a, a = the largest axis ratio, and |r^2 - r_true^2| <= 2 sqrt(3) a r + 3 a^2.
+    const double erel = (cubic ? 5.0 : 7.0) * std::ldexp(1.0, -24) + 1e-7;
+    for (int f = 0; f < c->nframes; ++f)
+    {
+        const FrameGeom& g  = c->h_geom[f];
+        CoordFrame&      fr = a.h_cframes[f];
+        const double     unit = g.L[0] / 4294967296.0;
+        fr.ay = (float)(g.L[1] / g.L[0]);
+        fr.az = (float)(g.L[2] / g.L[0]);
+        const double amax = std::max(1.0, std::max((double)fr.ay, (double)fr.az)) * (1.0 + 1e-6);
+        const double rT   = (double)s.Rmin / unit, T = rT * rT;
+        const double slop = (2.0 * std::sqrt(3.0) * amax * rT + 3.0 * amax * amax) * 1.01;
+        const double lo   = T * (1.0 - erel) - slop, hi = T * (1.0 + erel) + slop;
+        float t_in = (float)lo;
+        if ((double)t_in > lo) t_in = next_down(t_in);
+        float t_out = (float)hi;
+        if ((double)t_out < hi) t_out = next_up(t_out);
+        fr.t_in  = t_in;
+        fr.t_mid = 0.5f * (t_in + t_out);
+        // |r2 - t_mid| <= w must cover (t_in, t_out]: half width plus the rounding of t_mid and of the subtraction
+        fr.w = next_up((float)((0.5 * ((double)t_out - (double)t_in) + 4.0 * std::ldexp(1.0, -24) * (double)t_out) * (1.0 + 1e-6)));
+        const double rs = 1e-3 / unit * (1.0 + 1e-6) + std::sqrt(3.0) * amax * 1.01 + 1.0;
+        fr.t_small = next_up((float)(rs * rs * (1.0 + erel)));
+        for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
+    }
+    CU(cudaMemcpyAsync(a.d_cframes, a.h_cframes, sizeof(CoordFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)c->maxK, c->stream));
+    CU(cudaMemsetAsync(a.d_cnt, 0, sizeof(int) * (size_t)n0 * c->nframes, c->stream));
+    CU(cudaMemsetAsync(a.d_table, 0, sizeof(unsigned) * (size_t)s.max_count * c->nframes, c->stream));
+
+    CoordSelect sel{};
+    sel.dim = s.dim; sel.use_cyl = s.use_cyl; sel.low = (double)s.low; sel.up = (double)s.up;
+    sel.cx = (double)s.cx; sel.cy = (double)s.cy; sel.rlow = (double)s.Rlow; sel.rup = (double)s.Rup;
+    CoordDev p{};
+    p.n0 = n0; p.n1 = n1; p.rmin = (double)s.Rmin;
+    // cell grid: same chooser as the RDF (cut-off = Rmin)
+    RdfDev rp{};
+    rp.n0 = n0; rp.n1 = n1; rp.nslab = 1; rp.Rm = (double)s.Rmin;
+    int        bits = 0, reach[3] = { 0, 0, 0 };
+    Acc        probe; probe.cells = a.cells;
+    const bool cells = choose_cells(c, probe, rp, false, &bits, reach);
+    CellDev    cd{};
+    dim3       grid((n0 + 255) / 256, c->nframes);
+    {
+        Timed tm(c, 1);
+        k5_select<<<grid, 256, 0, c->stream>>>(g0->d_cen[s.com0], c->nframes, n0, sel, a.d_slab_id, a.d_slab_cnt);
+        CU(cudaGetLastError());
+        if (!cells)
+        {
+            k3_slab_scatter<<<grid, 256, sizeof(unsigned) * 3, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, n0, 1, a.d_slab_cnt,
+                                                                            a.d_slab_cnt + (size_t)c->maxK, a.d_sortedA);
+            CU(cudaGetLastError());
+        }
+        else
+        {
+            const unsigned nk = 1u << (3 * bits);
+            if (!a.d_keysA) CU(cudaMalloc(&a.d_keysA, sizeof(int) * (size_t)n0 * c->maxK));
+            if (!a.d_keysB) CU(cudaMalloc(&a.d_keysB, sizeof(int) * (size_t)n1 * c->maxK));
+            if (!a.d_sortedB) CU(cudaMalloc(&a.d_sortedB, sizeof(int4) * (size_t)n1 * c->maxK));
+            if (a.cap_keysA < nk) { cudaFree(a.d_cellA); a.d_cellA = nullptr; CU(cudaMalloc(&a.d_cellA, sizeof(unsigned) * 3 * (size_t)(nk + 1) * c->maxK)); a.cap_keysA = nk; }
+            if (a.cap_keysB < nk) { cudaFree(a.d_cellB); a.d_cellB = nullptr; CU(cudaMalloc(&a.d_cellB, sizeof(unsigned) * 3 * (size_t)(nk + 1) * c->maxK)); a.cap_keysB = nk; }
+            const size_t sz = (size_t)(nk + 1) * c->maxK;
+            unsigned *cntA = a.d_cellA, *stA = a.d_cellA + sz, *curA = a.d_cellA + 2 * sz;
+            unsigned *cntB = a.d_cellB, *stB = a.d_cellB + sz, *curB = a.d_cellB + 2 * sz;
+            CU(cudaMemsetAsync(a.d_cellA, 0, sizeof(unsigned) * 3 * sz, c->stream));
+            CU(cudaMemsetAsync(a.d_cellB, 0, sizeof(unsigned) * 3 * sz, c->stream));
+            dim3 gridB((n1 + 255) / 256, c->nframes);
+            k3_cell_keys<<<grid, 256, 0, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, n0, bits, nk, a.d_keysA, cntA);
+            k3_cell_keys<<<gridB, 256, 0, c->stream>>>(g1->d_fix[s.com1], nullptr, c->nframes, n1, bits, nk, a.d_keysB, cntB);
+            k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cntA, nk, stA);
+            k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cntB, nk, stB);
+            k3_cell_scatter<<<grid, 256, 0, c->stream>>>(g0->d_fix[s.com0], a.d_keysA, c->nframes, n0, nk, stA, curA, a.d_sortedA);
+            k3_cell_scatter<<<gridB, 256, 0, c->stream>>>(g1->d_fix[s.com1], a.d_keysB, c->nframes, n1, nk, stB, curB, a.d_sortedB);
+            CU(cudaGetLastError());
+            cd.bits = bits; cd.rx = reach[0]; cd.ry = reach[1]; cd.rz = reach[2];
+            cd.nkeysA = nk; cd.nkeysB = nk; cd.startA = stA; cd.startB = stB; cd.sortedB = a.d_sortedB;
+        }
+    }
+    {
+        Timed tm(c, 6);
+        if (cells)
+        {
+            const double per_cell = (double)n0 / (double)(1u << (3 * bits));
+            const int    ny       = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_cell / (kCellIPT * 128))));
+            if (int rc = launch_coord<kCellIPT, 2>(c, a, *g0, *g1, p, cd, dim3(cd.nkeysA, ny, c->nframes), cubic)) return rc;
+        }
+        else
+        {
+            constexpr int TI = 8 * 128;
+            const int itiles = std::max(1, (n0 + TI - 1) / TI);
+            int       jsplit = std::max(1, (c->sm_count * 24 + itiles * c->nframes - 1) / (itiles * c->nframes));
+            jsplit           = std::min(jsplit, std::max(1, (n1 + kTileJ - 1) / kTileJ));
+            p.jchunk         = ((n1 + jsplit - 1) / jsplit + kTileJ - 1) / kTileJ * kTileJ;
+            p.jsplit         = (n1 + p.jchunk - 1) / p.jchunk;
+            if (int rc = launch_coord<8, 0>(c, a, *g0, *g1, p, cd, dim3(itiles, p.jsplit, c->nframes), cubic)) return rc;
+        }
+        k5_hist<<<grid, 256, sizeof(unsigned) * (s.max_count + 2), c->stream>>>(a.d_cnt, a.d_slab_id, c->nframes, n0, s.max_count, a.d_table, a.d_hist,
+                                                                                 a.d_hist + a.ndev);
+        CU(cudaGetLastError());
+    }
+    a.table_frames = c->nframes;
+    return B2A_OK;
+}
+
+extern "C" int b2a_coord_read_frames(b2a_ctx* c, int id, uint32_t* table, uint32_t* numA)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not a coordination-number accumulator", id);
+    if (!table || !numA) return fail(B2A_ERR_ARG, "null argument");
+    if (a->table_frames <= 0) return fail(B2A_ERR_STATE, "nothing accumulated yet");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(table, a->d_table, sizeof(unsigned) * (size_t)a->coord.max_count * a->table_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(numA, a->d_slab_cnt, sizeof(unsigned) * a->table_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return B2A_OK;
+}
+
+extern "C" int b2a_coord_counts(b2a_ctx* c, int id, int frame, int32_t* count)
+{
+    Acc* a;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not a coordination-number accumulator", id);
+    if (!count || frame < 0 || frame >= a->table_frames) return fail(B2A_ERR_ARG, "b2a_coord_counts: bad argument");
+    Group* g0;
+    if (int rc = get_group(c, a->coord.grp0, &g0)) return rc;
+    CU(cudaSetDevice(c->device));
+    const size_t     n0 = (size_t)g0->nmol;
+    std::vector<int> sel(n0);
+    CU(cudaMemcpyAsync(count, a->d_cnt + frame * n0, sizeof(int) * n0, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(sel.data(), a->d_slab_id + frame * n0, sizeof(int) * n0, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n0; ++i)
+        if (sel[i] < 0) count[i] = -1;
+    return B2A_OK;
+}
+
+// host post-processing of calc_pair_dist_bulk.cpp:89-92: totPair[k] += tmpPair[k] / numA, frame by frame in double
+extern "C" int b2a_coord_fold(const uint32_t* table, const uint32_t* numA, int nframes, int max_count, double* totPair)
+{
+    if (!table || !numA || !totPair || nframes < 0 || max_count <= 0) return fail(B2A_ERR_ARG, "b2a_coord_fold: bad argument");
+    for (int f = 0; f < nframes; ++f)
+    {
+        if (numA[f] == 0) continue;   // tmpPair is empty: the loop at :89 does not run
+        for (int k = 0; k < max_count; ++k)
+        {
+            const uint32_t v = table[(size_t)f * max_count + k];
+            if (v) totPair[k] += (double)v / (int)numA[f];
+        }
+    }
     return B2A_OK;
 }

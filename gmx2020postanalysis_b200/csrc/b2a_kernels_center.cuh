@@ -224,6 +224,46 @@ __global__ void __launch_bounds__(256) k1b_positions(const float* __restrict__ x
     for (int k = 0; k < 3; ++k) o[k] = unwrap_f(__ldg(pa + k), __ldg(pr + k), g.L[k], g.half[k], g.hsafe[k]);
 }
 
+// ---- velocity / force loaders: the same weighted mean and gather WITHOUT unwrapping -------------------------------
+// GmxHandle::loadVelocityCenter / loadForceCenter (ipp:228-269, 298-339): atoms molN + j, sequential j order, one
+// division by atomCenter.sum() per component.  cen: [frame][k][i] like K1.
+__global__ void __launch_bounds__(256) k1_field_centers(const float* __restrict__ v, size_t frame_stride, int nframes,
+                                                        const int* __restrict__ index, int nmol, int napm,
+                                                        const double* __restrict__ w, DivConst wsum, double* __restrict__ cen)
+{
+    extern __shared__ double sw[];
+    for (int j = threadIdx.x; j < napm; j += blockDim.x) sw[j] = w[j];
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmol || f >= nframes) return;
+    const float* p  = v + (size_t)f * frame_stride + (size_t)__ldg(index + (size_t)i * napm) * 3;
+    double       c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    for (int j = 0; j < napm; ++j)
+    {
+        const double wj = sw[j];
+        c0 = __dadd_rn(c0, __dmul_rn((double)__ldg(p + 3 * j), wj));
+        c1 = __dadd_rn(c1, __dmul_rn((double)__ldg(p + 3 * j + 1), wj));
+        c2 = __dadd_rn(c2, __dmul_rn((double)__ldg(p + 3 * j + 2), wj));
+    }
+    double* o = cen + (size_t)f * 3 * nmol;
+    o[i]                    = div_const(c0, wsum);
+    o[(size_t)nmol + i]     = div_const(c1, wsum);
+    o[2 * (size_t)nmol + i] = div_const(c2, wsum);
+}
+
+// GmxHandle::loadVelocity / loadForce (ipp:201-226, 271-296): vel(i,j)[k] = fr->v[index[grp][n]][k], boxd memory order
+__global__ void __launch_bounds__(256) k1b_field_values(const float* __restrict__ vf, const int* __restrict__ index, int nmol,
+                                                        int napm, double* __restrict__ out)
+{
+    const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long long)nmol * napm) return;
+    const int    i  = (int)(n % nmol), j = (int)(n / nmol);
+    const float* pa = vf + (size_t)__ldg(index + (size_t)i * napm + j) * 3;
+    double*      o  = out + (size_t)n * 3;
+    o[0] = (double)__ldg(pa); o[1] = (double)__ldg(pa + 1); o[2] = (double)__ldg(pa + 2);
+}
+
 // ---- K2: centre of the needed dimension(s) -> 1-D histogram, never materialising the centres ----------------
 // README.md:143-150, general/calc_density_region.cpp:59-71, general/density_slit_jhl.cpp:59-77
 struct DensityDev

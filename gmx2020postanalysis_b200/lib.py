@@ -15,13 +15,16 @@ _P = C.c_void_p
 STAT_FRAMES, STAT_DROPPED, STAT_EXACT, STAT_MOVED, STAT_SELECTED, STAT_PAIRS, STAT_OVERFLOW, STAT_MISPROVEN = range(8)
 STAT_NSLOTS = 8
 COM_MASS, COM_GEOMETRY, COM_CHARGE, COM_DIPOLE = range(4)
+FIELD_V, FIELD_F = 1, 2
 
 # every symbol include/b2a.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "b2a_last_error", "b2a_version", "b2a_device_count", "b2a_create", "b2a_destroy", "b2a_sync", "b2a_stream",
     "b2a_pinned_alloc", "b2a_pinned_free", "b2a_set_group", "b2a_set_group_full", "b2a_set_group_wsum", "b2a_group_nmol",
     "b2a_submit_batch", "b2a_batch_frames", "b2a_centers", "b2a_centers_batch", "b2a_positions",
-    "b2a_density_create", "b2a_rdf_create", "b2a_orient_create", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
+    "b2a_submit_field", "b2a_field_centers", "b2a_field_centers_batch", "b2a_field_values",
+    "b2a_density_create", "b2a_rdf_create", "b2a_orient_create", "b2a_coord_create", "b2a_coord_read_frames",
+    "b2a_coord_counts", "b2a_coord_fold", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
     "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_acc_fast", "b2a_invalidate", "b2a_timing_enable",
     "b2a_timing_read",
 ]
@@ -44,6 +47,12 @@ class OrientSpec(C.Structure):
                 ("c1", C.c_float), ("c2", C.c_float), ("dr", C.c_float), ("CR", C.c_float), ("Cr", C.c_float),
                 ("nAngle", C.c_int), ("tp1", C.c_int), ("tp2", C.c_int), ("tp3", C.c_int), ("DIMNOrient", C.c_int),
                 ("method", C.c_int)]
+
+
+class CoordSpec(C.Structure):
+    _fields_ = [("grp0", C.c_int), ("grp1", C.c_int), ("com0", C.c_int), ("com1", C.c_int), ("Rmin", C.c_float),
+                ("dim", C.c_int), ("low", C.c_float), ("up", C.c_float), ("use_cyl", C.c_int), ("cx", C.c_float),
+                ("cy", C.c_float), ("Rlow", C.c_float), ("Rup", C.c_float), ("max_count", C.c_int)]
 
 
 class B2AError(RuntimeError):
@@ -81,9 +90,17 @@ def load():
         L.b2a_centers.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
         L.b2a_centers_batch.argtypes = [_P, C.c_int, C.c_int, _P]
         L.b2a_positions.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.b2a_submit_field.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.b2a_field_centers.argtypes = [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P]
+        L.b2a_field_centers_batch.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
+        L.b2a_field_values.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
         L.b2a_density_create.argtypes = [_P, C.POINTER(DensitySpec), C.POINTER(C.c_int)]
         L.b2a_rdf_create.argtypes = [_P, C.POINTER(RdfSpec), C.POINTER(C.c_int)]
         L.b2a_orient_create.argtypes = [_P, C.POINTER(OrientSpec), C.POINTER(C.c_int)]
+        L.b2a_coord_create.argtypes = [_P, C.POINTER(CoordSpec), C.POINTER(C.c_int)]
+        L.b2a_coord_read_frames.argtypes = [_P, C.c_int, _P, _P]
+        L.b2a_coord_counts.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.b2a_coord_fold.argtypes = [_P, _P, C.c_int, C.c_int, _P]
         L.b2a_accumulate.argtypes = [_P, C.c_int]
         L.b2a_acc_reset.argtypes = [_P, C.c_int]
         L.b2a_acc_size.argtypes = [_P, C.c_int, C.POINTER(C.c_size_t)]
@@ -201,6 +218,33 @@ class Context:
         check(self.L.b2a_positions(self._h, grp, frame, out.ctypes.data))
         return out.transpose(1, 0, 2)   # [nmol, napm, 3]
 
+    # ---- velocities / forces -----------------------------------------------------------------------------
+    def submit_field(self, field, data):
+        """field: FIELD_V / FIELD_F; data [K, natoms, 3] float32 for the frames of the current batch."""
+        d = np.ascontiguousarray(data, dtype=np.float32)
+        if d.ndim == 2:
+            d = d[None]
+        self._keep.append(d)
+        check(self.L.b2a_submit_field(self._h, field, d.shape[0], d.ctypes.data))
+
+    def field_centers(self, field, grp, com=0, frame=0):
+        n = max(self.nmol(grp), 0)
+        out = np.empty((3, n), dtype=np.float64)
+        check(self.L.b2a_field_centers(self._h, field, grp, com, frame, out.ctypes.data))
+        return out.T
+
+    def field_centers_batch(self, field, grp, com=0):
+        n, K = max(self.nmol(grp), 0), max(self.L.b2a_batch_frames(self._h), 0)
+        out = np.empty((K, 3, n), dtype=np.float64)
+        check(self.L.b2a_field_centers_batch(self._h, field, grp, com, out.ctypes.data))
+        return out.transpose(0, 2, 1)
+
+    def field_values(self, field, grp, napm, frame=0):
+        n = max(self.nmol(grp), 0)
+        out = np.empty((napm, n, 3), dtype=np.float64)
+        check(self.L.b2a_field_values(self._h, field, grp, frame, out.ctypes.data))
+        return out.transpose(1, 0, 2)
+
     # ---- accumulators ----------------------------------------------------------------------------------
     def density_create(self, **kw):
         s = DensitySpec(**kw)
@@ -219,6 +263,31 @@ class Context:
         a = C.c_int()
         check(self.L.b2a_orient_create(self._h, C.byref(s), C.byref(a)))
         return a.value
+
+    def coord_create(self, **kw):
+        kw.setdefault("use_cyl", 0)
+        for k in ("cx", "cy", "Rlow", "Rup"):
+            kw.setdefault(k, 0.0)
+        s = CoordSpec(**kw)
+        a = C.c_int()
+        check(self.L.b2a_coord_create(self._h, C.byref(s), C.byref(a)))
+        self._coord_max = getattr(self, "_coord_max", {})
+        self._coord_max[a.value] = (kw["max_count"], kw["grp0"])
+        return a.value
+
+    def coord_read_frames(self, acc):
+        """-> (table [frames, max_count] uint32, numA [frames] uint32) of the last accumulated batch."""
+        K = max(self.L.b2a_batch_frames(self._h), 0)
+        mc = self._coord_max[acc][0]
+        table = np.zeros((K, mc), dtype=np.uint32)
+        numA = np.zeros(K, dtype=np.uint32)
+        check(self.L.b2a_coord_read_frames(self._h, acc, table.ctypes.data, numA.ctypes.data))
+        return table, numA
+
+    def coord_counts(self, acc, frame):
+        out = np.empty(max(self.nmol(self._coord_max[acc][1]), 0), dtype=np.int32)
+        check(self.L.b2a_coord_counts(self._h, acc, frame, out.ctypes.data))
+        return out
 
     def rdf_tune(self, acc, symmetric=0, paranoid=0):
         check(self.L.b2a_rdf_tune(self._h, acc, symmetric, paranoid))
@@ -242,7 +311,7 @@ class Context:
         ms = np.zeros(8, dtype=np.float64)
         n = np.zeros(8, dtype=np.int64)
         check(self.L.b2a_timing_read(self._h, ms.ctypes.data, n.ctypes.data))
-        names = ["k1_centers", "k3_prep", "k3_rdf", "k2_density", "k4_orient", "h2d", "other6", "other7"]
+        names = ["k1_centers", "k3_prep", "k3_rdf", "k2_density", "k4_orient", "h2d", "k5_coord", "other7"]
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}
 
     def accumulate(self, acc):
@@ -266,6 +335,16 @@ class Context:
         stats = np.zeros(STAT_NSLOTS, dtype=np.uint64)
         check(self.L.b2a_acc_read(self._h, acc, counts.ctypes.data, stats.ctypes.data))
         return counts, stats
+
+
+def coord_fold(table, numA, tot=None):
+    """totPair[k] += tmpPair[k] / numA frame by frame (calc_pair_dist_bulk.cpp:89-92)."""
+    table = np.ascontiguousarray(table, dtype=np.uint32)
+    numA = np.ascontiguousarray(numA, dtype=np.uint32)
+    if tot is None:
+        tot = np.zeros(table.shape[1], dtype=np.float64)
+    check(load().b2a_coord_fold(table.ctypes.data, numA.ctypes.data, table.shape[0], table.shape[1], tot.ctypes.data))
+    return tot
 
 
 def rdf_normalise(counts, nbin, Rbin):

@@ -19,11 +19,13 @@
  *   b2a_centers        <- GmxHandle::loadPositionCenter    (ipp:150-199), com 0/1/2; com 3 = dipole
  *                         numerator with the neutral-molecule guard of
  *                         src/general/9g_dist_bin_1803.cpp:215-222
+ *   b2a_submit_field / b2a_field_* <- fr->v, fr->f; GmxHandle::loadVelocity[Center] / loadForce[Center] (ipp:201-339)
  *   b2a_density_*      <- README.md:129-154 template loop; src/general/calc_density_region.cpp:59-71;
  *                         src/general/density_slit_jhl.cpp:59-77
  *   b2a_rdf_*          <- src/general/calc_rdf_region.cpp:52-64 (setup), 73-95 (pair loop),
  *                         100-115 (normalisation); GmxHandle::periodicity (ipp:410-417)
  *   b2a_orient_*       <- src/mofs/calc_orient_mof.cpp:14-63, 120-200
+ *   b2a_coord_*        <- src/mofs/calc_pair_dist_bulk.cpp:14-23, 66-100; src/mofs/calc_pair_dist.cpp:80-106
  */
 #ifndef B2A_H
 #define B2A_H
@@ -98,6 +100,18 @@ int b2a_centers_batch(b2a_ctx* ctx, int grp, int com, double* out);
 /* out: nmol x napm x 3 doubles in itp::boxd memory order: element (i,j)[k] at (i + j*nmol)*3 + k */
 int b2a_positions(b2a_ctx* ctx, int grp, int frame, double* out);
 
+/* ---- velocities / forces (fr->v, fr->f of TRR trajectories): the loaders that do not unwrap ----- */
+enum { B2A_FIELD_V = 1, B2A_FIELD_F = 2 };
+/* data: [nframes][natoms][3] float, the v or f arrays of the frames of the CURRENT batch (call after
+ * b2a_submit_batch; nframes must match).                                                          */
+int b2a_submit_field(b2a_ctx* ctx, int field, int nframes, const float* data);
+/* GmxHandle::loadVelocityCenter / loadForceCenter (ipp:228-269, 298-339), com 0/1/2; layouts as
+ * b2a_centers / b2a_centers_batch                                                                 */
+int b2a_field_centers(b2a_ctx* ctx, int field, int grp, int com, int frame, double* out);
+int b2a_field_centers_batch(b2a_ctx* ctx, int field, int grp, int com, double* out);
+/* GmxHandle::loadVelocity / loadForce (ipp:201-226, 271-296); layout as b2a_positions             */
+int b2a_field_values(b2a_ctx* ctx, int field, int grp, int frame, double* out);
+
 /* ---- fused accumulators: process every frame of the current batch on the device ---------------- */
 typedef struct b2a_density_spec
 {
@@ -136,6 +150,18 @@ typedef struct b2a_orient_spec
     int   method;            /* 1 sum, 2 cross product (:184-191) */
 } b2a_orient_spec;
 
+typedef struct b2a_coord_spec
+{
+    int   grp0, grp1;        /* i runs over grp0, j over grp1 (calc_pair_dist_bulk.cpp:69,78) */
+    int   com0, com1;        /* centre kind (the programs use -ncm for both, :66-67) */
+    float Rmin;              /* counted when 1e-3 < distance <= Rmin (:81) */
+    int   dim;
+    float low, up;           /* lowPos <= posc1(i,dim) <= upPos, inclusive (:71) */
+    int   use_cyl;           /* calc_pair_dist.cpp:85-86: also Rlow <= sqrt((x-cx)^2 + (y-cy)^2) <= Rup */
+    float cx, cy, Rlow, Rup;
+    int   max_count;         /* size of the histogram of counts; pairNumber >= max_count is counted in B2A_STAT_DROPPED */
+} b2a_coord_spec;
+
 /* stats slots common to all accumulators (u64 each) */
 enum {
     B2A_STAT_FRAMES   = 0,  /* frames accumulated */
@@ -154,6 +180,17 @@ enum {
 int b2a_density_create(b2a_ctx* ctx, const b2a_density_spec* spec, int* acc);
 int b2a_rdf_create(b2a_ctx* ctx, const b2a_rdf_spec* spec, int* acc);
 int b2a_orient_create(b2a_ctx* ctx, const b2a_orient_spec* spec, int* acc);
+
+/* coordination numbers (mofs/calc_pair_dist_bulk.cpp:66-92, mofs/calc_pair_dist.cpp:80-106): counters[k] = number of
+ * selected molecules with pairNumber == k, summed over frames; B2A_STAT_SELECTED = sum of numA.  The reference normalises
+ * per frame (totPair[k] += tmpPair[k] / numA, :89-92), so the per-frame tables of the last accumulated batch are
+ * readable too, and b2a_coord_fold performs that accumulation in frame order.                                       */
+int b2a_coord_create(b2a_ctx* ctx, const b2a_coord_spec* spec, int* acc);
+/* table: [frames of the last batch][max_count] tmpPair; numA: [frames] */
+int b2a_coord_read_frames(b2a_ctx* ctx, int acc, uint32_t* table, uint32_t* numA);
+/* pairNumber of every molecule of grp0 in one frame of the last batch (-1: filtered out) */
+int b2a_coord_counts(b2a_ctx* ctx, int acc, int frame, int32_t* count);
+int b2a_coord_fold(const uint32_t* table, const uint32_t* numA, int nframes, int max_count, double* totPair);
 
 /* queue the accumulation of the whole current batch (asynchronous) */
 int b2a_accumulate(b2a_ctx* ctx, int acc);
@@ -195,7 +232,7 @@ int b2a_rdf_cells(b2a_ctx* ctx, int acc, int mode);
 int b2a_invalidate(b2a_ctx* ctx);
 /* Bracket every kernel family with CUDA events on the context stream.  b2a_timing_read synchronises, returns
  * total milliseconds and launch counts for slots {0: K1 centres, 1: K3 slab prep, 2: K3 pair kernel,
- * 3: K2 density, 4: K4 orientation, 5: H2D copies} (arrays of 8) and resets the totals.               */
+ * 3: K2 density, 4: K4 orientation, 5: H2D copies, 6: K5 coordination pair kernel} (arrays of 8) and resets the totals.               */
 int b2a_timing_enable(b2a_ctx* ctx, int enable);
 int b2a_timing_read(b2a_ctx* ctx, double* ms, long long* launches);
 

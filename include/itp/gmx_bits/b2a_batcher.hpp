@@ -30,6 +30,8 @@ namespace b2a_detail
         {
             if (ctx_) b2a_destroy(ctx_);
             if (bx_) b2a_pinned_free(bx_);
+            if (bv_) b2a_pinned_free(bv_);
+            if (bf_) b2a_pinned_free(bf_);
         }
         FrameBatcher(const FrameBatcher&) = delete;
         FrameBatcher& operator=(const FrameBatcher&) = delete;
@@ -63,8 +65,9 @@ namespace b2a_detail
                 bbox_.resize(9 * (size_t)k_);
                 btime_.resize(k_);
             }
-            if (io_.bV) bv_.resize(n3 * k_);
-            if (io_.bF) bf_.resize(n3 * k_);
+            if (io_.bV && !bv_) bv_ = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
+            if (io_.bF && !bf_) bf_ = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
+            if ((io_.bV && !bv_) || (io_.bF && !bf_)) gmx_fatal(FARGS, "%s", b2a_last_error());
             if (!fill(true)) return false;
             point(0, fr);
             return true;
@@ -97,8 +100,8 @@ namespace b2a_detail
                 if (!(first && n == 0))
                     if (eof_ || !read_next_frame(oenv_, status_, &io_)) { eof_ = true; break; }
                 if (io_.bX) std::memcpy(bx_ + (size_t)n * n3, io_.x, n3 * sizeof(float));
-                if (io_.bV) std::memcpy(bv_.data() + (size_t)n * n3, io_.v, n3 * sizeof(float));
-                if (io_.bF) std::memcpy(bf_.data() + (size_t)n * n3, io_.f, n3 * sizeof(float));
+                if (io_.bV) std::memcpy(bv_ + (size_t)n * n3, io_.v, n3 * sizeof(float));
+                if (io_.bF) std::memcpy(bf_ + (size_t)n * n3, io_.f, n3 * sizeof(float));
                 std::memcpy(bbox_.data() + 9 * (size_t)n, &io_.box[0][0], 9 * sizeof(float));
                 btime_[n] = io_.time;
             }
@@ -106,6 +109,9 @@ namespace b2a_detail
             n_ = n;
             ++serial_;
             if (io_.bX) check(b2a_submit_batch(ctx(natoms_), n, bx_, bbox_.data()));
+            // velocities / forces (TRR) ride along so that loadVelocity[Center] / loadForce[Center] run on the device too
+            if (io_.bX && io_.bV) check(b2a_submit_field(ctx(natoms_), B2A_FIELD_V, n, bv_));
+            if (io_.bX && io_.bF) check(b2a_submit_field(ctx(natoms_), B2A_FIELD_F, n, bf_));
             return true;
         }
 
@@ -114,8 +120,8 @@ namespace b2a_detail
             const size_t n3 = (size_t)natoms_ * 3;
             *fr        = io_;
             fr->x      = io_.bX ? reinterpret_cast<rvec*>(bx_ + (size_t)k * n3) : nullptr;
-            fr->v      = io_.bV ? reinterpret_cast<rvec*>(bv_.data() + (size_t)k * n3) : nullptr;
-            fr->f      = io_.bF ? reinterpret_cast<rvec*>(bf_.data() + (size_t)k * n3) : nullptr;
+            fr->v      = io_.bV ? reinterpret_cast<rvec*>(bv_ + (size_t)k * n3) : nullptr;
+            fr->f      = io_.bF ? reinterpret_cast<rvec*>(bf_ + (size_t)k * n3) : nullptr;
             fr->time   = btime_[k];
             fr->natoms = natoms_;
             std::memcpy(&fr->box[0][0], bbox_.data() + 9 * (size_t)k, 9 * sizeof(float));
@@ -129,8 +135,8 @@ namespace b2a_detail
         int                natoms_ = 0, k_ = 16, n_ = 0, cur_ = 0;
         bool               eof_ = false;
         long               serial_ = 0;
-        float*             bx_ = nullptr;
-        std::vector<float> bv_, bf_, bbox_, btime_;
+        float*             bx_ = nullptr, *bv_ = nullptr, *bf_ = nullptr;
+        std::vector<float> bbox_, btime_;
     };
 } // namespace b2a_detail
 } // namespace itp

@@ -62,6 +62,8 @@ namespace itp
         vecd get_charge(int grp);
         void b2aEnsure();
         vecd weights(int grp, int com);
+        void loadField(boxd& out, int grp, int field);
+        void loadFieldCenter(matd& out, int grp, int com, int field);
 
     public:
         std::vector<const char*> desc = { "do some analysis for trajectort." };

@@ -219,58 +219,34 @@ namespace itp
         std::memcpy(posc.data(), c.buf.data() + n3 * batch_.current(), n3 * sizeof(double));   // matd(nmol,3) column-major
     }
 
-    // ---- velocity / force loaders: no unwrapping, host side (ipp:201-339) ------------------------------------------------
-    inline void GmxHandle::loadVelocity(boxd& vel, int grp)
+    // ---- velocity / force loaders (ipp:201-339): same weighted mean / gather without unwrapping, on the device ---------------
+    inline void GmxHandle::loadField(boxd& out, int grp, int field)
     {
         if (grp >= ngrps) gmx_fatal(FARGS, "grp(%d) should less than ngrps(%d)!", grp, ngrps);
-        const int nm = nmol[grp], na = napm[grp];
-        for (int i = 0, n = 0; i != nm; ++i)
-            for (int j = 0; j != na; ++j, ++n)
-                for (int k = 0; k != 3; ++k) vel(i, j)[k] = fr->v[index[grp][n]][k];
+        b2aEnsure();
+        b2a_detail::check(b2a_field_values(batch_.ctx(), field, grp, batch_.current(), reinterpret_cast<double*>(out.data())));
     }
 
-    inline void GmxHandle::loadForce(boxd& force, int grp)
+    inline void GmxHandle::loadFieldCenter(matd& out, int grp, int com, int field)
     {
         if (grp >= ngrps) gmx_fatal(FARGS, "grp(%d) should less than ngrps(%d)!", grp, ngrps);
-        const int nm = nmol[grp], na = napm[grp];
-        for (int i = 0, n = 0; i != nm; ++i)
-            for (int j = 0; j != na; ++j, ++n)
-                for (int k = 0; k != 3; ++k) force(i, j)[k] = fr->f[index[grp][n]][k];
-    }
-
-    inline void GmxHandle::loadVelocityCenter(matd& velc, int grp, int com)
-    {
-        if (grp >= ngrps) gmx_fatal(FARGS, "grp(%d) should less than ngrps(%d)!", grp, ngrps);
-        const vecd   w = weights(grp, com);
-        const double s = w.sum();
-        for (int i = 0; i != nmol[grp]; ++i)
+        if (com < 0 || com > 2) gmx_fatal(FARGS, "center(%d) should be 0 (mass), 1 (geometry) or 2 (charge)", com);
+        b2aEnsure();
+        CenCache&    c  = cen_[(field << 8) | (grp << 2) | com];
+        const size_t n3 = 3 * (size_t)nmol[grp];
+        if (c.serial != batch_.serial())
         {
-            const int first = index[grp][i * napm[grp]];
-            for (int k = 0; k != 3; ++k)
-            {
-                double acc = 0.0;
-                for (int j = 0; j != napm[grp]; ++j) acc += double(fr->v[first + j][k]) * w[j];
-                velc(i, k) = acc / s;
-            }
+            c.buf.resize(n3 * batch_.capacity());
+            b2a_detail::check(b2a_field_centers_batch(batch_.ctx(), field, grp, com, c.buf.data()));
+            c.serial = batch_.serial();
         }
+        std::memcpy(out.data(), c.buf.data() + n3 * batch_.current(), n3 * sizeof(double));
     }
 
-    inline void GmxHandle::loadForceCenter(matd& forcec, int grp, int com)
-    {
-        if (grp >= ngrps) gmx_fatal(FARGS, "grp(%d) should less than ngrps(%d)!", grp, ngrps);
-        const vecd   w = weights(grp, com);
-        const double s = w.sum();
-        for (int i = 0; i != nmol[grp]; ++i)
-        {
-            const int first = index[grp][i * napm[grp]];
-            for (int k = 0; k != 3; ++k)
-            {
-                double acc = 0.0;
-                for (int j = 0; j != napm[grp]; ++j) acc += double(fr->f[first + j][k]) * w[j];
-                forcec(i, k) = acc / s;
-            }
-        }
-    }
+    inline void GmxHandle::loadVelocity(boxd& vel, int grp) { loadField(vel, grp, B2A_FIELD_V); }
+    inline void GmxHandle::loadForce(boxd& force, int grp) { loadField(force, grp, B2A_FIELD_F); }
+    inline void GmxHandle::loadVelocityCenter(matd& velc, int grp, int com) { loadFieldCenter(velc, grp, com, B2A_FIELD_V); }
+    inline void GmxHandle::loadForceCenter(matd& forcec, int grp, int com) { loadFieldCenter(forcec, grp, com, B2A_FIELD_F); }
 
     // ---- LJ table of the two template molecules (ipp:341-376) --------------------------------------------------------------
     inline void GmxHandle::loadLJParameter(int group1, int group2, matd& c6, matd& c12)

@@ -39,6 +39,11 @@ def lib():
                                        C.c_int, C.c_int, C.c_int, _P, _P, _P]
         L.orc_full_load_position.argtypes = [_P, _P, C.c_int, _P, C.c_int, _P, _P]
         L.orc_full_load_position_center.argtypes = [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P]
+        L.orc_field_center.argtypes = [_P, _P, C.c_int, C.c_int, _P, C.c_double, _P]
+        L.orc_field_values.argtypes = [_P, _P, C.c_int, C.c_int, _P]
+        L.orc_pair_count.restype = C.c_int
+        L.orc_pair_count.argtypes = [_P, C.c_int, _P, C.c_int, _P, C.c_float, C.c_int, C.c_float, C.c_float, C.c_int,
+                                     C.c_float, C.c_float, C.c_float, C.c_float, _P]
         _lib = L
     return _lib
 
@@ -169,3 +174,32 @@ def full_load_position_center(x, index, napm, w, Lbox, geometry=False):
     lib().orc_full_load_position_center(x.ctypes.data, index.ctypes.data, nmol, napm.ctypes.data, w.ctypes.data, int(geometry),
                                         Lbox.ctypes.data, out.ctypes.data)
     return out.T
+
+
+def field_center(v, index, napm, w):
+    """loadVelocityCenter / loadForceCenter -> [nmol, 3] (column-major memory)."""
+    v, index, w = _f32(v), _i32(index), _f64(w)
+    nmol = len(index) // napm
+    out = np.empty((3, nmol), dtype=np.float64)
+    lib().orc_field_center(v.ctypes.data, index.ctypes.data, nmol, napm, w.ctypes.data, eigen_sum(w), out.ctypes.data)
+    return out.T
+
+
+def field_values(v, index, napm):
+    """loadVelocity / loadForce -> [nmol, napm, 3] view of the boxd buffer."""
+    v, index = _f32(v), _i32(index)
+    nmol = len(index) // napm
+    out = np.empty((napm, nmol, 3), dtype=np.float64)
+    lib().orc_field_values(v.ctypes.data, index.ctypes.data, nmol, napm, out.ctypes.data)
+    return out.transpose(1, 0, 2)
+
+
+def pair_count(posc1, posc2, Lbox, Rmin, dim, low, up, cyl=None):
+    """calc_pair_dist_bulk.cpp:66-92 (cyl=None) / calc_pair_dist.cpp:80-106 (cyl=(cx, cy, Rlow, Rup)).
+    -> (count[n0] int32 with -1 for filtered-out i, numA)."""
+    p1, p2, Lbox = _colmajor(posc1), _colmajor(posc2), _f64(Lbox)
+    count = np.empty(p1.shape[1], dtype=np.int32)
+    cx, cy, rl, ru = cyl if cyl is not None else (0.0, 0.0, 0.0, 0.0)
+    numA = lib().orc_pair_count(p1.ctypes.data, p1.shape[1], p2.ctypes.data, p2.shape[1], Lbox.ctypes.data, Rmin, dim, low, up,
+                                int(cyl is not None), cx, cy, rl, ru, count.ctypes.data)
+    return count, int(numA)

@@ -319,3 +319,66 @@ void orc_full_load_position_center(const float* x, const int* index, int nmol, c
         n += napm[i];
     }
 }
+
+void orc_field_center(const float* v, const int* index, int nmol, int napm, const double* w, double wsum, double* out)
+{
+    int n = 0;
+    for (int i = 0; i < nmol; ++i)
+    {
+        const int molN = index[n];
+        for (int k = 0; k < 3; ++k)
+        {
+            double c = 0.0;
+            for (int j = 0; j < napm; ++j)
+            {
+                const double t = v[(size_t)(molN + j) * 3 + k];
+                c += t * w[j];
+            }
+            out[(size_t)i + (size_t)k * nmol] = c / wsum;
+        }
+        n += napm;
+    }
+}
+
+void orc_field_values(const float* v, const int* index, int nmol, int napm, double* out)
+{
+    int n = 0;
+    for (int i = 0; i < nmol; ++i)
+        for (int j = 0; j < napm; ++j, ++n)
+            for (int k = 0; k < 3; ++k) out[((size_t)i + (size_t)j * nmol) * 3 + k] = v[(size_t)index[n] * 3 + k];
+}
+
+int orc_pair_count(const double* posc1, int n0, const double* posc2, int n1, const double Lbox[3], float Rmin, int dim,
+                   float lowPos, float upPos, int use_cyl, float cx, float cy, float Rlow, float Rup, int* count)
+{
+    int numA = 0;
+#pragma omp parallel for schedule(static) reduction(+ : numA)
+    for (int i = 0; i < n0; ++i)
+    {
+        count[i]        = -1;
+        const double pd = posc1[(size_t)i + (size_t)dim * n0];
+        if (!(lowPos <= pd && pd <= upPos)) continue;
+        if (use_cyl)
+        {
+            /* std::pow(x, 2) is x * x (gcc folds it; glibc's pow is exact for squares as well) */
+            const double ax = posc1[i] - cx, ay = posc1[(size_t)i + n0] - cy;
+            const double L1 = sqrt(ax * ax + ay * ay);
+            if (!(Rlow <= L1 && L1 <= Rup)) continue;
+        }
+        numA++;
+        int pairNumber = 0;
+        for (int j = 0; j < n1; ++j)
+        {
+            double ret = 0.0;
+            for (int k = 0; k < 3; ++k)
+            {
+                const double r = orc_periodicity(posc1[(size_t)i + (size_t)k * n0] - posc2[(size_t)j + (size_t)k * n1], Lbox[k]);
+                ret += r * r;
+            }
+            const double distance = sqrt(ret);
+            if (distance > 1e-3 && distance <= Rmin) pairNumber++;
+        }
+        count[i] = pairNumber;
+    }
+    return numA;
+}

@@ -88,6 +88,28 @@ void refshim_load_position_center(void* h, int grp, int com, double* out)
     std::memcpy(out, posc.data(), sizeof(double) * posc.size());
 }
 
+/* velocities / forces: point fr->v / fr->f at caller arrays, then the unmodified loaders (gmx_handle.ipp:201-339) */
+void refshim_set_vf(void* h, float* v, float* f)
+{
+    Shim* s     = static_cast<Shim*>(h);
+    s->hd.fr->v = reinterpret_cast<rvec*>(v);
+    s->hd.fr->f = reinterpret_cast<rvec*>(f);
+}
+void refshim_load_field(void* h, int grp, int force, double* out)
+{
+    Shim*     s   = static_cast<Shim*>(h);
+    itp::boxd val = s->hd.initPos(grp);
+    if (force) s->hd.loadForce(val, grp); else s->hd.loadVelocity(val, grp);
+    std::memcpy(out, val.data(), sizeof(double) * 3 * val.size());
+}
+void refshim_load_field_center(void* h, int grp, int force, int com, double* out)
+{
+    Shim*     s   = static_cast<Shim*>(h);
+    itp::matd val = s->hd.initPosc(grp);
+    if (force) s->hd.loadForceCenter(val, grp, com); else s->hd.loadVelocityCenter(val, grp, com);
+    std::memcpy(out, val.data(), sizeof(double) * val.size());
+}
+
 /* ---- GmxHandleFull (heterogeneous molecule sizes), reference include/itp/gmx_bits/gmx_handle_full.ipp ---- */
 struct ShimFull
 {

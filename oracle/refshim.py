@@ -29,6 +29,9 @@ def lib():
         L.refshim_set_frame.argtypes = [_P, _P, _P]
         L.refshim_load_position.argtypes = [_P, C.c_int, _P]
         L.refshim_load_position_center.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.refshim_set_vf.argtypes = [_P, _P, _P]
+        L.refshim_load_field.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.refshim_load_field_center.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
         L.refshim_periodicity.restype = C.c_double
         L.refshim_periodicity.argtypes = [C.c_double, C.c_double]
         L.refshim_eigen_sum.restype = C.c_double
@@ -69,6 +72,21 @@ class RefHandle:
     def load_position_center(self, com=0):
         out = np.empty((3, self.nmol), dtype=np.float64)
         lib().refshim_load_position_center(self._h, 0, com, out.ctypes.data)
+        return out.T
+
+    def set_vf(self, v, f):
+        self._v = np.ascontiguousarray(v, dtype=np.float32)
+        self._f = np.ascontiguousarray(f, dtype=np.float32)
+        lib().refshim_set_vf(self._h, self._v.ctypes.data, self._f.ctypes.data)
+
+    def load_field(self, force=False):
+        out = np.empty((self.napm, self.nmol, 3), dtype=np.float64)
+        lib().refshim_load_field(self._h, 0, int(force), out.ctypes.data)
+        return out.transpose(1, 0, 2)
+
+    def load_field_center(self, force=False, com=0):
+        out = np.empty((3, self.nmol), dtype=np.float64)
+        lib().refshim_load_field_center(self._h, 0, int(force), com, out.ctypes.data)
         return out.T
 
     def __del__(self):

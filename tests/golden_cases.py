@@ -63,7 +63,19 @@ def program_cases():
                                 args=["-NCM", 1, "-dim", 0, "-low", 0.2, 0, 0, "-up", 3.8, 100, 100, "-c1", 2.0, "-c2", 2.0,
                                       "-dr", 0.5, "-CR", 2.0, "-Cr", 0.5, "-nA", 45, "-tp1", 3, "-tp2", 7, "-tp3", 12,
                                       "-DIMNOrient", 1, "-method", 2]),
+        # coordination numbers (mofs/calc_pair_dist_bulk.cpp): anions within Rmin of every cation of a slab
+        "pair_dist_il": dict(exe="calc_pair_dist_bulk", system=lambda: synth.ionic_liquid(300, 4.4, seed=26), nframes=4,
+                             groups=["CAT", "ANI"], args=["-ncm", 0, "-Rmin", 0.8, "-dim", 2, "-low", 0.6, "-up", 3.9]),
     }
+
+
+def field_fixture():
+    """Velocities / forces for the loaders that do not unwrap (gmx_handle.ipp:201-339): any float array does."""
+    system = synth.ionic_liquid(60, 2.9, seed=12)
+    rng = np.random.default_rng(17)
+    v = rng.normal(size=(system.natoms, 3)).astype(np.float32)
+    f = (rng.normal(size=(system.natoms, 3)) * 300.0).astype(np.float32)
+    return system, v, f
 
 
 def full_fixture():

@@ -174,3 +174,35 @@ def parse_orient_args(args):
             kw[names[a]] = args[i + 1]
             i += 2
     return kw
+
+
+# ---- mofs/calc_pair_dist_bulk.cpp main() restated on oracle.port ---------------------------------------------
+def pair_dist_text(tables, numAs):
+    """calc_pair_dist_bulk.cpp:89-107 from per-frame histograms of pairNumber (tables[f][k]) and numA[f]."""
+    tot = {}
+    for tab, numA in zip(tables, numAs):
+        if numA == 0:
+            continue
+        for k in np.nonzero(tab)[0]:
+            tot[int(k)] = tot.get(int(k), 0.0) + float(tab[k]) / int(numA)      # totPair[p.first] += p.second / numA
+    total = 0.0
+    for k in sorted(tot):
+        total += tot[k]
+    return [f"{k:8d}\t{tot[k] / total:12.5f}" for k in sorted(tot)]
+
+
+def oracle_pair_dist_bulk(system, nframes, grp0, grp1, ncm=0, Rmin=0.8, dim=2, low=0.0, up=12.0, return_counts=False):
+    Lbox = port.lbox_from_box9(system.box9())
+    g0, g1 = group_info(system, grp0), group_info(system, grp1)
+    counts, tables, numAs = [], [], []
+    for f in range(nframes):
+        x = system.frame(f)
+        p1 = port.load_position_center(x, g0["index"], g0["napm"], g0["w"][ncm], Lbox)
+        p2 = port.load_position_center(x, g1["index"], g1["napm"], g1["w"][ncm], Lbox)
+        cnt, numA = port.pair_count(p1, p2, Lbox, f32(Rmin), dim, f32(low), f32(up))
+        counts.append(cnt)
+        tables.append(np.bincount(cnt[cnt >= 0], minlength=1))
+        numAs.append(numA)
+    if return_counts:
+        return counts, numAs
+    return pair_dist_text(tables, numAs)

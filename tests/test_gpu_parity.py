@@ -350,6 +350,99 @@ def test_dipole_orientation_config4_shape(gpu_ctx_factory):
     assert np.array_equal(got[:90].reshape(90, 1), exp_o) and got[90] == exp_n[0] == 5000 * K
 
 
+# ---- 8f-4: velocity / force loaders and coordination numbers --------------------------------------------------------
+def test_velocity_force_loaders(gpu_ctx_factory):
+    """loadVelocity[Center] / loadForce[Center] on the device, bit-exact vs the oracle and the reference's own outputs."""
+    system, v, f = GC.field_fixture()
+    gold = np.load(os.path.join(GOLD, "loaders.npz"))
+    K = 2
+    ctx = gpu_ctx_factory(system.natoms, K)
+    infos = _groups(ctx, system, ["CAT", "ANI"])
+    ctx.submit(system.frames(0, K), system.box9())
+    with pytest.raises(lib.B2AError):
+        ctx.field_centers(lib.FIELD_V, 0)              # nothing submitted for this batch yet
+    v2, f2 = np.stack([v, v[::-1]]), np.stack([f, 2 * f])
+    ctx.submit_field(lib.FIELD_V, v2)
+    ctx.submit_field(lib.FIELD_F, f2)
+    for g, (gi, sp) in enumerate(zip(infos, system.species)):
+        for field, arr, tag in ((lib.FIELD_V, v2, "vel"), (lib.FIELD_F, f2, "force")):
+            for com in (0, 1, 2):
+                got = ctx.field_centers_batch(field, g, com)
+                for k in range(K):
+                    assert np.array_equal(got[k], port.field_center(arr[k], gi["index"], gi["napm"], gi["w"][com]), equal_nan=True)
+                assert np.array_equal(got[0], gold[f"field.{sp.name}.{tag}.cen{com}"], equal_nan=True)
+                assert np.array_equal(ctx.field_centers(field, g, com, 1), got[1], equal_nan=True)
+            assert np.array_equal(ctx.field_values(field, g, gi["napm"], 1), port.field_values(arr[1], gi["index"], gi["napm"]))
+            assert np.array_equal(ctx.field_values(field, g, gi["napm"], 0), gold[f"field.{sp.name}.{tag}"])
+    ctx.submit(system.frames(0, K), system.box9())     # a new batch invalidates the uploaded fields
+    with pytest.raises(lib.B2AError):
+        ctx.field_values(lib.FIELD_F, 0, infos[0]["napm"], 0)
+
+
+def test_coord_matches_reference_program_output(gpu_ctx_factory):
+    """mofs/calc_pair_dist_bulk.cpp on an ionic liquid: per-molecule counts vs the oracle, text vs the reference program."""
+    case = GC.program_cases()["pair_dist_il"]
+    system, K = case["system"](), case["nframes"]
+    ctx = gpu_ctx_factory(system.natoms, K)
+    _groups(ctx, system, case["groups"])
+    exp_counts, exp_numA = refprog.oracle_pair_dist_bulk(system, K, "CAT", "ANI", ncm=0, Rmin=0.8, dim=2, low=0.6, up=3.9,
+                                                         return_counts=True)
+    acc = ctx.coord_create(grp0=0, grp1=1, com0=0, com1=0, Rmin=0.8, dim=2, low=0.6, up=3.9, max_count=64)
+    tot = None
+    for lo in (0, 2):                                   # two batches of two frames: per-frame tables fold in frame order
+        ctx.submit(system.frames(lo, 2), system.box9())
+        ctx.accumulate(acc)
+        table, numA = ctx.coord_read_frames(acc)
+        for k in range(2):
+            assert np.array_equal(ctx.coord_counts(acc, k), exp_counts[lo + k])
+            assert int(numA[k]) == exp_numA[lo + k]
+            assert np.array_equal(table[k], np.bincount(exp_counts[lo + k][exp_counts[lo + k] >= 0], minlength=64))
+        tot = lib.coord_fold(table, numA, tot)
+    total = 0.0
+    for k in np.nonzero(tot)[0]:
+        total += tot[k]
+    lines = [f"{k:8d}\t{tot[k] / total:12.5f}" for k in np.nonzero(tot)[0]]
+    assert lines == open(os.path.join(GOLD, "pair_dist_il.txt")).read().split("\n")[:-1]
+    counts, st = ctx.read(acc, 64)
+    assert int(counts.sum()) == sum(exp_numA) == int(st[lib.STAT_SELECTED]) and int(st[lib.STAT_DROPPED]) == 0
+
+
+@pytest.mark.parametrize("case", [
+    dict(sys=("water", 20000, 8.43), g=("OW", "OW"), Rmin=0.35, low=-100.0, up=100.0, cyl=None),        # self group: d = 0 excluded by d > 1e-3
+    dict(sys=("il", 2500, 9.3), g=("CAT", "ANI"), Rmin=0.75, low=1.0, up=8.0, cyl=(4.6, 4.7, 0.5, 3.9)),  # calc_pair_dist.cpp filter
+])
+def test_coord_cells_and_brute_force_bit_exact(gpu_ctx_factory, case):
+    kind, n, L = case["sys"]
+    system = synth.water_box(n, L, seed=61, split_atoms=True) if kind == "water" else synth.ionic_liquid(n, L, seed=62)
+    K = 2
+    ctx = gpu_ctx_factory(system.natoms, K)
+    g0, g1 = _groups(ctx, system, list(case["g"]))
+    x, box = system.frames(0, K), system.box9()
+    Lbox = port.lbox_from_box9(box)
+    ctx.submit(x, box)
+    kw = dict(grp0=0, grp1=1, com0=0, com1=0, Rmin=case["Rmin"], dim=2, low=case["low"], up=case["up"], max_count=32)
+    if case["cyl"]:
+        kw.update(use_cyl=1, cx=case["cyl"][0], cy=case["cyl"][1], Rlow=case["cyl"][2], Rup=case["cyl"][3])
+    res = {}
+    for cells in (0, 1):
+        acc = ctx.coord_create(**kw)
+        ctx.rdf_cells(acc, cells)
+        ctx.accumulate(acc)
+        res[cells] = [ctx.coord_counts(acc, k) for k in range(K)] + [ctx.read(acc, 32)]
+    cyl = tuple(refprog.f32(v) for v in case["cyl"]) if case["cyl"] else None
+    for k in range(K):
+        p1 = port.load_position_center(x[k], g0["index"], g0["napm"], g0["w"][0], Lbox)
+        p2 = port.load_position_center(x[k], g1["index"], g1["napm"], g1["w"][0], Lbox)
+        exp, numA = port.pair_count(p1, p2, Lbox, refprog.f32(case["Rmin"]), 2, refprog.f32(case["low"]), refprog.f32(case["up"]), cyl)
+        assert numA > 0 and exp.max() > 2
+        assert np.array_equal(res[0][k], exp) and np.array_equal(res[1][k], exp)
+    (c0, s0), (c1, s1) = res[0][K], res[1][K]
+    assert np.array_equal(c0, c1) and int(s0[lib.STAT_SELECTED]) == int(s1[lib.STAT_SELECTED])
+    if kind == "water":                                                 # (2 500 ion pairs are too few for a cell grid: both runs are brute force)
+        assert int(s1[lib.STAT_PAIRS]) < 0.5 * int(s0[lib.STAT_PAIRS])  # the cell list really culled
+    assert int(s0[lib.STAT_EXACT]) > 0                                  # and the FP64 path was exercised
+
+
 # ---- FP32-bracketed fast paths of K2 / K4: proven answers must equal the literal FP64 ones -------------------------
 @pytest.mark.parametrize("which", ["water", "il", "water_shaken"])
 def test_fast_paths_validate_against_fp64(gpu_ctx_factory, which):

@@ -61,6 +61,19 @@ def test_golden_handle_full(gold):
     assert np.array_equal(port.full_load_position_center(x, idx, napm, q, Lbox), gold["full.cen2"], equal_nan=True)
 
 
+def test_golden_velocity_force_loaders(gold):
+    """loadVelocity[Center] / loadForce[Center] (no unwrapping) against the reference's own outputs."""
+    system, v, f = GC.field_fixture()
+    for s, off in zip(system.species, system.offsets()):
+        idx = np.arange(off, off + s.nmol * s.napm, dtype=np.int32)
+        ws = {0: s.mass.astype(np.float64), 1: np.ones(s.napm), 2: s.charge.astype(np.float64)}
+        for arr, tag in ((v, "vel"), (f, "force")):
+            assert np.array_equal(port.field_values(arr, idx, s.napm), gold[f"field.{s.name}.{tag}"])
+            for com in (0, 1, 2):
+                assert np.array_equal(port.field_center(arr, idx, s.napm, ws[com]), gold[f"field.{s.name}.{tag}.cen{com}"],
+                                      equal_nan=True), (s.name, tag, com)
+
+
 def _golden_lines(name):
     with open(os.path.join(GOLD, name + ".txt")) as fp:
         return fp.read().split("\n")[:-1]
@@ -80,6 +93,9 @@ def _oracle_lines(name, case):
         return refprog.oracle_readme_template(system, case["nframes"], case["groups"][0], **kw)[0]
     if case["exe"] == "calc_orient_mof":
         return refprog.oracle_orient_mof(system, case["nframes"], case["groups"][0], **refprog.parse_orient_args(a))
+    if case["exe"] == "calc_pair_dist_bulk":
+        kw = {a[k][1:]: a[k + 1] for k in range(0, len(a), 2)}
+        return refprog.oracle_pair_dist_bulk(system, case["nframes"], case["groups"][0], case["groups"][1], **kw)
     raise AssertionError(case["exe"])
 
 
@@ -112,7 +128,7 @@ def test_live_loaders_random():
 
 
 @needs_ref
-@pytest.mark.parametrize("name", ["rdf_il_slabs", "orient_water"])
+@pytest.mark.parametrize("name", ["rdf_il_slabs", "orient_water", "pair_dist_il"])
 def test_live_program_output(name, tmp_path):
     case = GC.program_cases()[name]
     if not refprog.have_ref(case["exe"]):

@@ -40,6 +40,16 @@ def loaders():
     out["edge.pos"] = np.ascontiguousarray(rh.load_position())
     for com in (0, 1, 2):
         out[f"edge.cen{com}"] = np.ascontiguousarray(rh.load_position_center(com))
+    system, v, fo = CASES.field_fixture()
+    for s, off in zip(system.species, system.offsets()):
+        idx = np.arange(off, off + s.nmol * s.napm, dtype=np.int32)
+        rh = refshim.RefHandle(idx, s.napm, s.mass, s.charge)
+        rh.set_frame(system.frame(0), system.box9())
+        rh.set_vf(v, fo)
+        for force, tag in ((False, "vel"), (True, "force")):
+            out[f"field.{s.name}.{tag}"] = np.ascontiguousarray(rh.load_field(force))
+            for com in (0, 1, 2):
+                out[f"field.{s.name}.{tag}.cen{com}"] = np.ascontiguousarray(rh.load_field_center(force, com))
     system, idx, napm, m, q = CASES.full_fixture()
     rf = refshim.RefHandleFull(idx, napm, m, q)
     rf.set_frame(system.frame(CASES.LOADER_FRAME), system.box9())
