@@ -6,19 +6,25 @@ import struct
 import numpy as np
 
 
-def write_trajectory(path, frames, box9, times=None):
-    """frames: iterable of [natoms,3] float32 arrays (or one [nframes,natoms,3] array)."""
+def write_trajectory(path, frames, box9, times=None, velocities=None, forces=None):
+    """frames: iterable of [natoms,3] float32 arrays (or one [nframes,natoms,3] array); velocities / forces: optional
+    arrays of the same shape (the v / f blocks of a TRR-like trajectory)."""
     frames = list(frames) if not isinstance(frames, np.ndarray) else [frames[k] for k in range(frames.shape[0])]
     nat = frames[0].shape[0]
     box9 = np.asarray(box9, dtype=np.float32).reshape(-1, 9)
+    flags = 1 | (2 if velocities is not None else 0) | (4 if forces is not None else 0)
     with open(path, "wb") as fp:
         fp.write(b"B2ATRJ01")
-        fp.write(struct.pack("<iiii", nat, len(frames), 1, 0))
+        fp.write(struct.pack("<iiii", nat, len(frames), flags, 0))
         for k, x in enumerate(frames):
             t = float(times[k]) if times is not None else float(k)
             fp.write(struct.pack("<f", t))
             fp.write(np.ascontiguousarray(box9[min(k, box9.shape[0] - 1)], dtype="<f4").tobytes())
             fp.write(np.ascontiguousarray(x, dtype="<f4").tobytes())
+            if velocities is not None:
+                fp.write(np.ascontiguousarray(velocities[k], dtype="<f4").tobytes())
+            if forces is not None:
+                fp.write(np.ascontiguousarray(forces[k], dtype="<f4").tobytes())
 
 
 def write_topology(path, system):
@@ -46,10 +52,10 @@ def write_index(path, groups):
                 fp.write(" ".join(str(v) for v in idx1[s:s + 15]) + "\n")
 
 
-def write_system(prefix, system, nframes, groups=None, f0=0):
+def write_system(prefix, system, nframes, groups=None, f0=0, velocities=None, forces=None):
     """Writes prefix.b2t / prefix.b2p / prefix.ndx; returns the three paths."""
     trj, top, ndx = prefix + ".b2t", prefix + ".b2p", prefix + ".ndx"
-    write_trajectory(trj, system.frames(f0, nframes), system.box9())
+    write_trajectory(trj, system.frames(f0, nframes), system.box9(), velocities=velocities, forces=forces)
     write_topology(top, system)
     write_index(ndx, groups if groups is not None else system.groups)
     return trj, top, ndx

@@ -18,11 +18,12 @@ def have_ref(prog: str) -> bool:
     return os.path.exists(os.path.join(REFDIR, prog)) and os.path.exists(os.path.join(ROOT, "build", "libgmxstub.so"))
 
 
-def run_program(exe, workdir, system, nframes, group_names, args, out_name, stdin_sel=None):
+def run_program(exe, workdir, system, nframes, group_names, args, out_name, stdin_sel=None, velocities=None, forces=None):
     """Writes the system, runs `exe`, returns the non-comment lines of the output file."""
     os.makedirs(workdir, exist_ok=True)
     groups = {g: system.groups[g] for g in dict.fromkeys(group_names)}
-    trj, top, ndx = trajio.write_system(os.path.join(workdir, "sys"), system, nframes, groups=groups)
+    trj, top, ndx = trajio.write_system(os.path.join(workdir, "sys"), system, nframes, groups=groups, velocities=velocities,
+                                        forces=forces)
     names = list(groups)
     sel = stdin_sel if stdin_sel is not None else " ".join(str(names.index(g)) for g in group_names) + "\n"
     out = os.path.join(workdir, out_name)

@@ -68,6 +68,23 @@ def test_live_reference_vs_dropin_other_programs(tmp_path):
         pytest.skip("no reference binaries on this box")
 
 
+def test_velocity_program_dropin_matches_reference_build(tmp_path, monkeypatch):
+    """phaseChange/calc_kineticEnergy.cpp (TRX_READ_V, loadVelocityCenter + loadPositionCenter): the unmodified source
+    built against the drop-in header (velocity centres computed on the device) writes the same file as the reference build."""
+    import numpy as np
+    from gmx2020postanalysis_b200 import synth
+    exe = "calc_kineticEnergy"
+    if not refprog.have_ref(exe) or not os.path.exists(os.path.join(DROPIN, exe)):
+        pytest.skip("calc_kineticEnergy binaries not built (needs /root/reference at build time)")
+    monkeypatch.setenv("B2A_BATCH", "3")
+    system, nframes = synth.water_box(900, 3.0, seed=75), 7
+    v = np.random.default_rng(76).normal(size=(nframes, system.natoms, 3)).astype(np.float32)
+    args = ["-low1", 0.2, "-up1", 2.7, "-low2", 0.1, "-up2", 2.9]
+    ref = refprog.run_program(os.path.join(refprog.REFDIR, exe), str(tmp_path / "ref"), system, nframes, ["SOL"], args, "o.xvg", velocities=v)
+    got = refprog.run_program(os.path.join(DROPIN, exe), str(tmp_path / "new"), system, nframes, ["SOL"], args, "o.xvg", velocities=v)
+    assert len(ref) == nframes + 1 and got == ref
+
+
 @pytest.mark.parametrize("center", [0, 2])
 def test_handle_full_dropin_matches_reference_build(center, tmp_path, monkeypatch):
     """GmxHandleFull (heterogeneous molecule sizes): the same exerciser source built against the reference's own header

@@ -440,7 +440,7 @@ def test_coord_cells_and_brute_force_bit_exact(gpu_ctx_factory, case):
     assert np.array_equal(c0, c1) and int(s0[lib.STAT_SELECTED]) == int(s1[lib.STAT_SELECTED])
     if kind == "water":                                                 # (2 500 ion pairs are too few for a cell grid: both runs are brute force)
         assert int(s1[lib.STAT_PAIRS]) < 0.5 * int(s0[lib.STAT_PAIRS])  # the cell list really culled
-    assert int(s0[lib.STAT_EXACT]) > 0                                  # and the FP64 path was exercised
+        assert int(s0[lib.STAT_EXACT]) >= n * K                         # every self pair (d = 0) went through the FP64 path
 
 
 # ---- FP32-bracketed fast paths of K2 / K4: proven answers must equal the literal FP64 ones -------------------------
