@@ -818,12 +818,13 @@ constexpr int kCellIPT = 4;   // i-molecules per thread in cell mode (one cell p
 
 // Cell grid for r_max << L: cells per dimension 2^bits, reach per dimension from the cut-off plus the fixed-point slop.
 // Returns false when cells would not cull enough to beat the brute-force (possibly symmetric) evaluation.
-static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_possible, int* bits, int reach[3])
+static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_possible, int* bits, int reach[3], int ti = kCellIPT * 128,
+                         double* cost_out = nullptr)
 {
     int want = a.cells;
     if (const char* e = getenv("B2A_RDF_CELLS")) want = atoi(e);
     if (want == 0) return false;
-    const int    TI    = kCellIPT * 128;
+    const int    TI    = ti;
     const double nmin  = (double)std::min(p.n0, p.n1);
     double       bestc = 1e30;
     int          bestb = -1, bestr[3] = { 0, 0, 0 };
@@ -831,7 +832,7 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
     {
         const int    nc = 1 << b;
         const double m  = nmin / ((double)nc * nc * nc);        // mean molecules per cell
-        if (m < 48.0) break;
+        if (m < (ti >= 512 ? 48.0 : 12.0)) break;
         if ((unsigned long long)p.nslab << (3 * b) > (4ull << 20)) break;
         int  r[3];
         bool ok = false;
@@ -856,6 +857,7 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
         if (cost < bestc) { bestc = cost; bestb = b; bestr[0] = r[0]; bestr[1] = r[1]; bestr[2] = r[2]; }
     }
     if (bestb < 0) return false;
+    if (cost_out) *cost_out = bestc;
     const double brute = sym_possible ? 0.5 : 1.0;
     if (want < 0 && bestc > 0.8 * brute) return false;
     *bits = bestb;
@@ -1409,9 +1411,28 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
     // cell grid: same chooser as the RDF (cut-off = Rmin)
     RdfDev rp{};
     rp.n0 = n0; rp.n1 = n1; rp.nslab = 1; rp.Rm = (double)s.Rmin;
-    int        bits = 0, reach[3] = { 0, 0, 0 };
+    // one i-cell per block: pick the register tile (1, 2 or 4 molecules per thread) whose lane utilisation x per-pair
+    // overhead (fewer i per streamed j = more shared loads per pair; measured on B200) is cheapest
+    int        bits = 0, reach[3] = { 0, 0, 0 }, cell_ipt = 4;
     Acc        probe; probe.cells = a.cells;
-    const bool cells = choose_cells(c, probe, rp, false, &bits, reach);
+    bool       cells = false;
+    {
+        const int    ipts[3] = { 4, 2, 1 };
+        const double over[3] = { 1.0, 1.25, 1.7 };
+        double       best = 1e30;
+        for (int t = 0; t < 3; ++t)
+        {
+            if (const char* e = getenv("B2A_COORD_IPT")) if (atoi(e) != ipts[t]) continue;
+            int    b = 0, r[3];
+            double cost = 0.0;
+            Acc    force = probe; force.cells = probe.cells == 0 ? 0 : 1;   // get the cost even when it would not win
+            if (!choose_cells(c, force, rp, false, &b, r, ipts[t] * 128, &cost)) continue;
+            if (cost * over[t] < best) { best = cost * over[t]; bits = b; reach[0] = r[0]; reach[1] = r[1]; reach[2] = r[2]; cell_ipt = ipts[t]; }
+        }
+        int want = probe.cells;
+        if (const char* e = getenv("B2A_RDF_CELLS")) want = atoi(e);
+        cells = best < 1e29 && want != 0 && (want > 0 || best < 0.8);
+    }
     CellDev    cd{};
     dim3       grid((n0 + 255) / 256, c->nframes);
     {
@@ -1454,8 +1475,13 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
         if (cells)
         {
             const double per_cell = (double)n0 / (double)(1u << (3 * bits));
-            const int    ny       = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_cell / (kCellIPT * 128))));
-            if (int rc = launch_coord<kCellIPT, 2>(c, a, *g0, *g1, p, cd, dim3(cd.nkeysA, ny, c->nframes), cubic)) return rc;
+            const int    ny       = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_cell / (cell_ipt * 128))));
+            const dim3   cgrid(cd.nkeysA, ny, c->nframes);
+            int          rc       = 0;
+            if (cell_ipt == 4) rc = launch_coord<4, 2>(c, a, *g0, *g1, p, cd, cgrid, cubic);
+            else if (cell_ipt == 2) rc = launch_coord<2, 2>(c, a, *g0, *g1, p, cd, cgrid, cubic);
+            else rc = launch_coord<1, 2>(c, a, *g0, *g1, p, cd, cgrid, cubic);
+            if (rc) return rc;
         }
         else
         {

@@ -100,6 +100,32 @@ def c4(K, reps=10):
             "e2e_h2d_GBs": K * system.natoms * 12 / tot / 1e9}
 
 
+def coord(K=4, reps=3):
+    """8f-4: coordination numbers (mofs/calc_pair_dist_bulk.cpp) on the C3 ionic liquid: anions within 0.8 nm of every cation."""
+    system = synth.ionic_liquid(31250, 22.1, seed=20200103)
+    x = system.frames(0, K)
+    ctx = lib.Context(system.natoms, K)
+    groups(ctx, system, ["CAT", "ANI"])
+    ctx.submit(x, system.box9())
+    out = {"config": "coordination numbers, 31 250 cations x 31 250 anions, Rmin 0.8 nm", "frames": K}
+    for cells, tag in ((0, "brute_force"), (1, "cell_list")):
+        acc = ctx.coord_create(grp0=0, grp1=1, com0=0, com1=0, Rmin=0.8, dim=2, low=-100.0, up=100.0, max_count=64)
+        ctx.rdf_cells(acc, cells)
+
+        def step():
+            ctx.invalidate(); ctx.accumulate(acc)
+        dev = timeit(ctx, step, reps)
+        ctx.reset(acc)
+        ctx.timing_enable(True); ctx.timing_read(); step(); tm = ctx.timing_read(); ctx.timing_enable(False)
+        cnt, st = ctx.read(acc, 64)
+        out[tag] = {"ms_per_frame": dev * 1e3 / K, "k5_ms_per_frame": tm["k5_coord"][0] / K, "evaluated_pairs_per_frame": int(st[lib.STAT_PAIRS]) / K,
+                    "evaluated_pairs_per_s": int(st[lib.STAT_PAIRS]) / (tm["k5_coord"][0] * 1e-3),
+                    "reference_equivalent_pairs_per_s": 31250.0 * 31250.0 * K / dev, "fp64_reevaluated_per_frame": int(st[lib.STAT_EXACT]) / K,
+                    "mean_coordination": float((cnt * np.arange(64)).sum() / max(cnt.sum(), 1))}
+    ctx.close()
+    return out
+
+
 def c5(K=1, reps=2):
     """4M atoms, 4 species, all 10 group pairs, Rm = 3 nm (Rbin 1500): cell-binned K3 vs brute force on the big pair."""
     system = synth.mixed_box()
@@ -149,7 +175,7 @@ if __name__ == "__main__":
     ap.add_argument("--only-c5", action="store_true")
     a = ap.parse_args()
     ap2 = a
-    runs = [c1, lambda: c3(a.c3_frames), lambda: c4(a.c4_frames)] if not a.only_c5 else []
+    runs = [c1, lambda: c3(a.c3_frames), lambda: c4(a.c4_frames), coord] if not a.only_c5 else []
     if a.c5 or a.only_c5:
         runs.append(c5)
     for r in runs:
