@@ -35,6 +35,10 @@ constexpr float    kMagic     = 8388607.5f;    // 2^23 - 0.5: fma(r, s, kMagic) 
 constexpr int      kQueueCap  = 1024;          // (j, thread) candidates per block between drains
 constexpr int      kTileJ     = 512;           // j-molecules staged per shared-memory tile
 constexpr int      kSubJ      = 256;           // j-iterations between queue drains
+#ifndef B2A_K3_PACKED
+#define B2A_K3_PACKED 1
+#endif
+constexpr bool     kPacked    = B2A_K3_PACKED != 0;   // issue the FP32 chain of two pairs as packed f32x2 instructions
 
 struct RdfFrame   // per frame (the box may change frame to frame); host-computed
 {
@@ -172,6 +176,52 @@ __device__ __forceinline__ void pair_bins(int xi, int yi, int zi, const int4& pj
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
     k1 = __float_as_uint(__fmaf_rn(r, s_lo, kMagic));
     k2 = __float_as_uint(__fmaf_rn(r, s_hi, kMagic));
+}
+
+// ---- the same, two pairs per instruction ---------------------------------------------------------------------------
+// Blackwell has packed FP32 arithmetic (PTX fma.rn.f32x2 / mul.rn.f32x2, SASS FFMA2 / FMUL2): one issue slot, two IEEE
+// round-to-nearest results on a 64-bit register pair.  The kernel is issue-bound, so the r^2 chain and the two bin FMAs of
+// TWO i-molecules against the same j are issued together: 5 packed instructions replace 10.  Every lane result is
+// bit-identical to pair_bins() (same operations, same rounding), which the out-of-line recheck path keeps using.
+__device__ __forceinline__ unsigned long long f2pack(float a, float b)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2mul(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <bool CLAMP, bool CUBIC>
+__device__ __forceinline__ void pair_bins2(int xa, int ya, int za, int xb, int yb, int zb, const int4& pj, unsigned long long s_lo2,
+                                           unsigned long long s_hi2, unsigned long long magic2, unsigned long long ay2,
+                                           unsigned long long az2, float r2max, unsigned& k1a, unsigned& k2a, unsigned& k1b, unsigned& k2b)
+{
+    unsigned long long fx = f2pack(__int2float_rn(xa - pj.x), __int2float_rn(xb - pj.x));
+    unsigned long long fy = f2pack(__int2float_rn(ya - pj.y), __int2float_rn(yb - pj.y));
+    unsigned long long fz = f2pack(__int2float_rn(za - pj.z), __int2float_rn(zb - pj.z));
+    if (!CUBIC) { fy = f2mul(fy, ay2); fz = f2mul(fz, az2); }
+    const unsigned long long r2 = f2fma(fz, fz, f2fma(fy, fy, f2mul(fx, fx)));
+    float r2a, r2b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r2a), "=f"(r2b) : "l"(r2));
+    if (CLAMP) { r2a = fminf(r2a, r2max); r2b = fminf(r2b, r2max); }
+    float ra, rb;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(r2a));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(r2b));
+    const unsigned long long r  = f2pack(ra, rb);
+    const unsigned long long k1 = f2fma(r, s_lo2, magic2), k2 = f2fma(r, s_hi2, magic2);
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(k1a), "=r"(k1b) : "l"(k1));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(k2a), "=r"(k2b) : "l"(k2));
 }
 
 struct RdfBlock   // block-uniform state shared by the hot loop and the cold paths (lives in shared memory)
@@ -415,6 +465,8 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
     const float    r2max   = fr.r2max;
     const float    s_lo = fr.s_lo, s_hi = fr.s_hi, ay = fr.ay, az = fr.az;
     const unsigned lowk = fr.lowk_bits;
+    const unsigned long long s_lo2 = f2pack(s_lo, s_lo), s_hi2 = f2pack(s_hi, s_hi), magic2 = f2pack(kMagic, kMagic),
+                             ay2 = f2pack(ay, ay), az2 = f2pack(az, az);
 
     int                xi[IPT], yi[IPT], zi[IPT];
     int                sub = 0;   // sub-tile counter: selects the ping-pong queue counter
@@ -440,14 +492,31 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
                     {
                         const int4 pj   = sj[j];
                         unsigned   dacc = 0, kmin = 0xffffffffu;
-#pragma unroll
-                        for (int q = 0; q < IPT; ++q)
+                        if (IPT % 2 == 0 && kPacked)
                         {
-                            unsigned k1, k2;
-                            pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
-                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1 * 4u + cb_ok) : "memory");
-                            dacc += k2 - k1;
-                            kmin = min(kmin, k1);
+#pragma unroll
+                            for (int q = 0; q < IPT; q += 2)
+                            {
+                                unsigned k1a, k2a, k1b, k2b;
+                                pair_bins2<CLAMP, CUBIC>(xi[q], yi[q], zi[q], xi[q + 1], yi[q + 1], zi[q + 1], pj, s_lo2, s_hi2, magic2, ay2, az2,
+                                                         r2max, k1a, k2a, k1b, k2b);
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1a * 4u + cb_ok) : "memory");
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1b * 4u + cb_ok) : "memory");
+                                dacc += (k2a - k1a) + (k2b - k1b);
+                                kmin = min(kmin, min(k1a, k1b));
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int q = 0; q < IPT; ++q)
+                            {
+                                unsigned k1, k2;
+                                pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1 * 4u + cb_ok) : "memory");
+                                dacc += k2 - k1;
+                                kmin = min(kmin, k1);
+                            }
                         }
                         if (PARANOID || dacc != 0 || kmin <= lowk)
                         {
