@@ -74,6 +74,19 @@ __device__ __forceinline__ float pair_r2(int xi, int yi, int zi, const int4& pj,
     return __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, __fmul_rn(fx, fx)));
 }
 
+// two i-molecules against one j with packed f32x2 arithmetic (see pair_bins2): bit-identical lanes, half the issue slots
+template <bool CUBIC>
+__device__ __forceinline__ void pair_r2x2(int xa, int ya, int za, int xb, int yb, int zb, const int4& pj, unsigned long long ay2,
+                                          unsigned long long az2, float& r2a, float& r2b)
+{
+    unsigned long long fx = f2pack(__int2float_rn(xa - pj.x), __int2float_rn(xb - pj.x));
+    unsigned long long fy = f2pack(__int2float_rn(ya - pj.y), __int2float_rn(yb - pj.y));
+    unsigned long long fz = f2pack(__int2float_rn(za - pj.z), __int2float_rn(zb - pj.z));
+    if (!CUBIC) { fy = f2mul(fy, ay2); fz = f2mul(fz, az2); }
+    const unsigned long long r2 = f2fma(fz, fz, f2fma(fy, fy, f2mul(fx, fx)));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r2a), "=f"(r2b) : "l"(r2));
+}
+
 // calcDistance (calc_pair_dist_bulk.cpp:14-23) + the test at :81, operation for operation
 __device__ __noinline__ int coord_exact(const double* __restrict__ cA, const double* __restrict__ cB, int n0, int n1, int i, int j,
                                         double L0, double L1, double L2, double rmin)
@@ -178,6 +191,7 @@ __global__ void __launch_bounds__(THREADS) k5_coord(const int4* __restrict__ sor
         blk.nexact = blk.noverflow = 0;
     }
     const float t_in = fr.t_in, t_mid = fr.t_mid, wband = fr.w, t_small = fr.t_small, ay = fr.ay, az = fr.az;
+    const unsigned long long ay2 = f2pack(ay, ay), az2 = f2pack(az, az);
 
     int                xi[IPT], yi[IPT], zi[IPT], cnt[IPT];
     int                sub = 0;
@@ -199,13 +213,29 @@ __global__ void __launch_bounds__(THREADS) k5_coord(const int4* __restrict__ sor
                 {
                     const int4 pj = sj[j];
                     float      m1 = 3.0e38f, m2 = 3.0e38f;
-#pragma unroll
-                    for (int q = 0; q < IPT; ++q)
+                    if (IPT % 2 == 0 && kPacked)
                     {
-                        const float r2 = pair_r2<CUBIC>(xi[q], yi[q], zi[q], pj, ay, az);
-                        cnt[q] += r2 <= t_in ? 1 : 0;
-                        m1 = fminf(m1, fabsf(r2 - t_mid));
-                        m2 = fminf(m2, r2);
+#pragma unroll
+                        for (int q = 0; q < IPT; q += 2)
+                        {
+                            float r2a, r2b;
+                            pair_r2x2<CUBIC>(xi[q], yi[q], zi[q], xi[q + 1], yi[q + 1], zi[q + 1], pj, ay2, az2, r2a, r2b);
+                            cnt[q] += r2a <= t_in ? 1 : 0;
+                            cnt[q + 1] += r2b <= t_in ? 1 : 0;
+                            m1 = fminf(m1, fminf(fabsf(r2a - t_mid), fabsf(r2b - t_mid)));
+                            m2 = fminf(m2, fminf(r2a, r2b));
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int q = 0; q < IPT; ++q)
+                        {
+                            const float r2 = pair_r2<CUBIC>(xi[q], yi[q], zi[q], pj, ay, az);
+                            cnt[q] += r2 <= t_in ? 1 : 0;
+                            m1 = fminf(m1, fabsf(r2 - t_mid));
+                            m2 = fminf(m2, r2);
+                        }
                     }
                     if (m1 <= wband || m2 <= t_small)   // some pair of this thread with j is undecided (lanes beyond tcount may trip it too)
                     {

@@ -9,12 +9,14 @@
  * reader with -b/-e/-dt time selection).
  */
 #include "gromacs/gmxstub_api.h"
+#include "../xdrtraj.hpp"
 
 #include <cctype>
 #include <cmath>
 #include <cstring>
 #include <map>
 #include <sstream>
+#include <thread>
 
 struct gmx_output_env_t
 {
@@ -482,6 +484,8 @@ struct t_trxstatus
     double  t0      = 0;
     std::string fn;
     std::vector<float> scratch;
+    int     fmt     = 0; /* 0: B2ATRJ01, 1: XTC, 2: TRR (xdrtraj.hpp) */
+    std::vector<unsigned char> blob;
 };
 
 namespace
@@ -535,23 +539,135 @@ bool next_selected(t_trxstatus* st, float hdr[10])
     return false;
 }
 
+/* ---- real GROMACS wire formats (XTC / TRR), decoded by xdrtraj.hpp ------------------------------------------------ */
+bool read_bytes(FILE* fp, void* dst, size_t n) { return std::fread(dst, 1, n, fp) == n; }
+
+/* XTC: positions the file after the coordinate block of the next selected frame; the block is left in st->blob.
+ * hdr receives time and box.  Returns false at end of file.                                                         */
+bool xtc_next(t_trxstatus* st, xdrtraj::XtcHeader* h)
+{
+    for (;;)
+    {
+        unsigned char hb[xdrtraj::kXtcHeaderBytes];
+        if (!read_bytes(st->fp, hb, sizeof(hb))) return false;
+        if (!xdrtraj::xtc_parse_header(hb, h)) gmx_fatal(FARGS, "%s: bad XTC frame header (magic)", st->fn.c_str());
+        if (h->natoms != st->natoms) gmx_fatal(FARGS, "%s: number of atoms changes between frames", st->fn.c_str());
+        unsigned char pre[40];
+        const size_t  npre = h->natoms <= 9 ? 4 : 40;
+        if (!read_bytes(st->fp, pre, npre)) return false;
+        const size_t total = xdrtraj::xtc_coord_block_bytes(pre, h->natoms);
+        bool         past  = false;
+        const bool   sel   = time_selected(st, h->time, &past);
+        if (past) return false;
+        st->next++;
+        if (!sel) { std::fseek(st->fp, static_cast<long>(total - npre), SEEK_CUR); continue; }
+        if (!st->have_t0) { st->have_t0 = true; st->t0 = h->time; }
+        st->blob.resize(total);
+        std::memcpy(st->blob.data(), pre, npre);
+        if (!read_bytes(st->fp, st->blob.data() + npre, total - npre)) gmx_fatal(FARGS, "%s: truncated XTC frame", st->fn.c_str());
+        return true;
+    }
+}
+
+bool trr_next(t_trxstatus* st, xdrtraj::TrrHeader* h)
+{
+    for (;;)
+    {
+        unsigned char hb[128];
+        const long    pos = std::ftell(st->fp);
+        const size_t  got = std::fread(hb, 1, sizeof(hb), st->fp);
+        if (got < 96) return false;
+        if (!xdrtraj::trr_parse_header(hb, got, h)) gmx_fatal(FARGS, "%s: bad TRR frame header", st->fn.c_str());
+        if (h->natoms != st->natoms) gmx_fatal(FARGS, "%s: number of atoms changes between frames", st->fn.c_str());
+        const size_t body = xdrtraj::trr_body_bytes(*h);
+        bool         past = false;
+        const bool   sel  = time_selected(st, h->t, &past);
+        if (past) return false;
+        st->next++;
+        if (!sel) { std::fseek(st->fp, pos + static_cast<long>(h->header_bytes + body), SEEK_SET); continue; }
+        if (!st->have_t0) { st->have_t0 = true; st->t0 = h->t; }
+        std::fseek(st->fp, pos + static_cast<long>(h->header_bytes), SEEK_SET);
+        st->blob.resize(body);
+        if (!read_bytes(st->fp, st->blob.data(), body)) gmx_fatal(FARGS, "%s: truncated TRR frame", st->fn.c_str());
+        return true;
+    }
+}
+
 t_trxstatus* open_trx(const char* fn)
 {
     t_trxstatus* st = new t_trxstatus;
     st->fp          = gmx_ffopen(fn, "rb");
     st->fn          = fn;
     std::setvbuf(st->fp, nullptr, _IOFBF, 8 << 20);
+    unsigned char first[128];
+    const size_t  got = std::fread(first, 1, sizeof(first), st->fp);
+    std::fseek(st->fp, 0, SEEK_SET);
+    if (got >= 8 && xdrtraj::be32(first) == (uint32_t)xdrtraj::kXtcMagic)
+    {
+        st->fmt = 1; st->natoms = (int)xdrtraj::be32(first + 4); st->nframes = -1; st->fflags = 1;
+        return st;
+    }
+    if (got >= 96 && xdrtraj::be32(first) == (uint32_t)xdrtraj::kTrrMagic)
+    {
+        xdrtraj::TrrHeader h;
+        if (!xdrtraj::trr_parse_header(first, got, &h)) gmx_fatal(FARGS, "%s: bad TRR header", fn);
+        st->fmt = 2; st->natoms = h.natoms; st->nframes = -1;
+        st->fflags = (h.x_size ? 1 : 0) | (h.v_size ? 2 : 0) | (h.f_size ? 4 : 0);
+        return st;
+    }
     TrjHeader h;
     read_exact(st->fp, &h, 1, fn);
-    if (std::memcmp(h.magic, "B2ATRJ01", 8) != 0) gmx_fatal(FARGS, "%s is not a gmxstub trajectory (bad magic)", fn);
+    if (std::memcmp(h.magic, "B2ATRJ01", 8) != 0) gmx_fatal(FARGS, "%s is neither an XTC / TRR file nor a gmxstub trajectory (bad magic)", fn);
     st->natoms  = h.natoms;
     st->nframes = h.nframes;
     st->fflags  = h.flags;
     return st;
 }
 
+bool deliver_xdr(t_trxstatus* st, t_trxframe* fr)
+{
+    const size_t n3 = static_cast<size_t>(st->natoms) * 3;
+    fr->natoms = st->natoms;
+    fr->bStep = TRUE; fr->bTime = TRUE; fr->bBox = TRUE;
+    fr->bX = fr->bV = fr->bF = FALSE;
+    if (st->fmt == 1)
+    {
+        xdrtraj::XtcHeader h;
+        if (!xtc_next(st, &h)) return false;
+        fr->time = h.time; fr->step = h.step;
+        for (int k = 0; k < 9; ++k) fr->box[k / 3][k % 3] = h.box[k];
+        if ((st->want & (TRX_READ_X | TRX_NEED_X)) && fr->x)
+        {
+            if (!xdrtraj::xtc_decode_coords(st->blob.data(), st->blob.size(), st->natoms, &fr->x[0][0]))
+                gmx_fatal(FARGS, "%s: corrupt XTC coordinate block in frame %d", st->fn.c_str(), st->next - 1);
+            fr->bX = TRUE;
+        }
+    }
+    else
+    {
+        xdrtraj::TrrHeader h;
+        if (!trr_next(st, &h)) return false;
+        fr->time = (float)h.t; fr->step = h.step;
+        const unsigned char* p  = st->blob.data() + h.ir_size + h.e_size;
+        const size_t         rs = h.dbl ? 8 : 4;
+        if (h.box_size) { float b[9]; xdrtraj::trr_read_reals(p, h.dbl, 9, b); for (int k = 0; k < 9; ++k) fr->box[k / 3][k % 3] = b[k]; }
+        p += h.box_size + h.vir_size + h.pres_size + h.top_size + h.sym_size;
+        auto rd = [&](int size, int want_bit, rvec* dst, gmx_bool* have) {
+            if (!size) return;
+            if ((st->want & want_bit) && dst) { xdrtraj::trr_read_reals(p, h.dbl, n3, &dst[0][0]); *have = TRUE; }
+            p += n3 * rs;
+        };
+        rd(h.x_size, TRX_READ_X | TRX_NEED_X, fr->x, &fr->bX);
+        rd(h.v_size, TRX_READ_V | TRX_NEED_V, fr->v, &fr->bV);
+        rd(h.f_size, TRX_READ_F | TRX_NEED_F, fr->f, &fr->bF);
+    }
+    st->nread++;
+    return true;
+}
+
 bool deliver(t_trxstatus* st, t_trxframe* fr)
 {
+    if (st->fmt != 0) return deliver_xdr(st, fr);
     float hdr[10];
     if (!next_selected(st, hdr)) return false;
     fr->time  = hdr[0];
@@ -610,6 +726,57 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
 {
     if (!st || !(st->fflags & 1)) return 0;
     const size_t n3   = static_cast<size_t>(st->natoms) * 3;
+    if (st->fmt == 1)
+    {
+        /* XTC frames are independent: slice K compressed frames out of the file, then decode them on K host threads
+         * straight into the caller's (pinned) batch */
+        std::vector<std::vector<unsigned char>> blobs;
+        while ((int)blobs.size() < max_frames)
+        {
+            xdrtraj::XtcHeader h;
+            if (!xtc_next(st, &h)) break;
+            const size_t k = blobs.size();
+            time_out[k]    = h.time;
+            std::memcpy(box_out + 9 * k, h.box, 9 * sizeof(float));
+            blobs.emplace_back(std::move(st->blob));
+            st->nread++;
+        }
+        const int n = (int)blobs.size();
+        int       nthreads = std::min<int>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+        if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(n, std::atoi(e)));
+        std::vector<int> bad(std::max(n, 1), 0);
+        auto work = [&](int t) {
+            for (int k = t; k < n; k += nthreads)
+                if (!xdrtraj::xtc_decode_coords(blobs[k].data(), blobs[k].size(), st->natoms, x_out + n3 * k)) bad[k] = 1;
+        };
+        if (nthreads <= 1) work(0);
+        else
+        {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; ++t) pool.emplace_back(work, t);
+            for (auto& th : pool) th.join();
+        }
+        for (int k = 0; k < n; ++k)
+            if (bad[k]) gmx_fatal(FARGS, "%s: corrupt XTC coordinate block", st->fn.c_str());
+        return n;
+    }
+    if (st->fmt == 2)
+    {
+        int got = 0;
+        t_trxframe fr{};
+        const int  want = st->want;
+        st->want        = TRX_READ_X;
+        while (got < max_frames)
+        {
+            fr.x = reinterpret_cast<rvec*>(x_out + n3 * got);
+            if (!deliver_xdr(st, &fr)) break;
+            time_out[got] = fr.time;
+            std::memcpy(box_out + 9 * static_cast<size_t>(got), &fr.box[0][0], 9 * sizeof(float));
+            ++got;
+        }
+        st->want = want;
+        return got;
+    }
     const size_t rest = frame_floats(st) - 10 - n3;
     int          got  = 0;
     while (got < max_frames)
@@ -624,4 +791,78 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
         ++got;
     }
     return got;
+}
+
+/* ---- writers for the real formats (tests, tools) --------------------------------------------------------------- */
+extern "C" int gmxstub_write_xtc(const char* path, int natoms, int nframes, const float* x, const float* box9, int nbox,
+                                 const float* times, float precision)
+{
+    FILE* fp = std::fopen(path, "wb");
+    if (!fp) return -1;
+    for (int k = 0; k < nframes; ++k)
+    {
+        xdrtraj::Writer w;
+        xdrtraj::xtc_write_frame(w, natoms, k, times ? times[k] : (float)k, box9 + 9 * static_cast<size_t>(std::min(k, nbox - 1)),
+                                 x + static_cast<size_t>(natoms) * 3 * k, precision);
+        std::fwrite(w.buf.data(), 1, w.buf.size(), fp);
+    }
+    std::fclose(fp);
+    return 0;
+}
+
+extern "C" int gmxstub_write_trr(const char* path, int natoms, int nframes, const float* x, const float* v, const float* f,
+                                 const float* box9, int nbox, const float* times)
+{
+    FILE* fp = std::fopen(path, "wb");
+    if (!fp) return -1;
+    const size_t n3 = static_cast<size_t>(natoms) * 3;
+    for (int k = 0; k < nframes; ++k)
+    {
+        xdrtraj::Writer w;
+        xdrtraj::trr_write_frame(w, natoms, k, times ? times[k] : (float)k, box9 + 9 * static_cast<size_t>(std::min(k, nbox - 1)),
+                                 x ? x + n3 * k : nullptr, v ? v + n3 * k : nullptr, f ? f + n3 * k : nullptr);
+        std::fwrite(w.buf.data(), 1, w.buf.size(), fp);
+    }
+    std::fclose(fp);
+    return 0;
+}
+
+/* decode-only entry for tests: all frames of an XTC / TRR / stub file through read_first_frame / read_next_frame */
+extern "C" int gmxstub_read_all(const char* path, int max_frames, int want_flags, float* x_out, float* v_out, float* f_out,
+                                float* box_out, float* time_out, int* natoms_out)
+{
+    t_trxstatus* st = nullptr;
+    t_trxframe   fr{};
+    if (!read_first_frame(nullptr, &st, path, &fr, want_flags)) return 0;
+    const size_t n3 = static_cast<size_t>(fr.natoms) * 3;
+    if (natoms_out) *natoms_out = fr.natoms;
+    int n = 0;
+    do
+    {
+        if (n >= max_frames) break;
+        if (x_out && fr.bX) std::memcpy(x_out + n3 * n, fr.x, n3 * sizeof(float));
+        if (v_out && fr.bV) std::memcpy(v_out + n3 * n, fr.v, n3 * sizeof(float));
+        if (f_out && fr.bF) std::memcpy(f_out + n3 * n, fr.f, n3 * sizeof(float));
+        if (box_out) std::memcpy(box_out + 9 * static_cast<size_t>(n), &fr.box[0][0], 9 * sizeof(float));
+        if (time_out) time_out[n] = fr.time;
+        ++n;
+    } while (read_next_frame(nullptr, st, &fr));
+    close_trx(st);
+    return n;
+}
+
+extern "C" int gmxstub_read_batches(const char* path, int batch, int max_frames, float* x_out, float* box_out, float* time_out)
+{
+    t_trxstatus* st = open_trx(path);
+    st->want        = TRX_READ_X;
+    const size_t n3 = static_cast<size_t>(st->natoms) * 3;
+    int          n  = 0;
+    while (n < max_frames)
+    {
+        const int got = gmxstub_read_frames(st, std::min(batch, max_frames - n), x_out + n3 * n, box_out + 9 * static_cast<size_t>(n), time_out + n);
+        if (got <= 0) break;
+        n += got;
+    }
+    close_trx(st);
+    return n;
 }

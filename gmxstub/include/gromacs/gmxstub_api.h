@@ -293,3 +293,18 @@ int   gmx_ffclose(FILE* fp);
  * x_out: [K][natoms][3] floats, box_out: [K][9] floats, time_out: [K] floats.            */
 int gmxstub_read_frames(t_trxstatus* status, int max_frames, float* x_out, float* box_out, float* time_out);
 int gmxstub_natoms(const t_trxstatus* status);
+#define GMXSTUB_BATCH_READ 1
+/* The stand-in reads its own raw format and real XTC / TRR files (gmxstub/xdrtraj.hpp; recognised by magic).
+ * Writers and whole-file readers for tests and tools:                                                        */
+#ifdef __cplusplus
+extern "C" {
+#endif
+int gmxstub_write_xtc(const char* path, int natoms, int nframes, const float* x, const float* box9, int nbox, const float* times, float precision);
+int gmxstub_write_trr(const char* path, int natoms, int nframes, const float* x, const float* v, const float* f, const float* box9, int nbox,
+                      const float* times);
+int gmxstub_read_all(const char* path, int max_frames, int want_flags, float* x_out, float* v_out, float* f_out, float* box_out, float* time_out,
+                     int* natoms_out);
+int gmxstub_read_batches(const char* path, int batch, int max_frames, float* x_out, float* box_out, float* time_out);
+#ifdef __cplusplus
+}
+#endif

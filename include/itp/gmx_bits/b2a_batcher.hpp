@@ -95,6 +95,31 @@ namespace b2a_detail
         {
             const size_t n3 = (size_t)natoms_ * 3;
             int          n  = 0;
+#ifdef GMXSTUB_BATCH_READ
+            // The libgromacs stand-in can hand out K frames per call and decodes XTC frames on K host threads, straight
+            // into the pinned batch.  With the real libgromacs this block compiles away and the loop below runs.
+            if (io_.bX && !io_.bV && !io_.bF && !std::getenv("B2A_NO_BATCH_READ"))
+            {
+                if (first)
+                {
+                    std::memcpy(bx_, io_.x, n3 * sizeof(float));
+                    std::memcpy(bbox_.data(), &io_.box[0][0], 9 * sizeof(float));
+                    btime_[0] = io_.time;
+                    n         = 1;
+                }
+                if (!eof_ && n < k_)
+                {
+                    const int got = gmxstub_read_frames(status_, k_ - n, bx_ + (size_t)n * n3, bbox_.data() + 9 * (size_t)n, btime_.data() + n);
+                    if (got < k_ - n) eof_ = true;
+                    n += got;
+                }
+                if (n == 0) return false;
+                n_ = n;
+                ++serial_;
+                check(b2a_submit_batch(ctx(natoms_), n, bx_, bbox_.data()));
+                return true;
+            }
+#endif
             for (; n < k_; ++n)
             {
                 if (!(first && n == 0))

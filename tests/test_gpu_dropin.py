@@ -85,6 +85,47 @@ def test_velocity_program_dropin_matches_reference_build(tmp_path, monkeypatch):
     assert len(ref) == nframes + 1 and got == ref
 
 
+@pytest.mark.parametrize("batch", ["4", "1"])
+def test_dropin_reads_xtc_and_trr(batch, tmp_path, monkeypatch):
+    """8f-2: the drop-in program fed by a real XTC file (K frames decoded on K host threads into the pinned batch) and by a
+    TRR file gives the same output as when fed the raw-float file holding the same (quantised) coordinates."""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    from gmx2020postanalysis_b200 import synth, trajio
+    import test_trajfmt as TF
+    L = C.CDLL(TF.STUB)
+    L.gmxstub_write_xtc.argtypes = [C.c_char_p, C.c_int, C.c_int, TF._P, TF._P, C.c_int, TF._P, C.c_float]
+    L.gmxstub_write_trr.argtypes = [C.c_char_p, C.c_int, C.c_int, TF._P, TF._P, TF._P, TF._P, C.c_int, TF._P]
+    monkeypatch.setenv("B2A_BATCH", batch)
+    exe = _dropin("calc_rdf_region")
+    system = synth.water_box(700, 2.8, seed=86, split_atoms=True)
+    K = 6
+    x = system.frames(0, K)
+    xq = TF.quantise(x, 1000.0)
+    box = np.ascontiguousarray(system.box9(), np.float32).reshape(1, 9)
+    outs = {}
+    for kind in ("raw", "xtc", "trr"):
+        d = tmp_path / kind
+        d.mkdir()
+        trj = str(d / ("sys." + {"raw": "b2t", "xtc": "xtc", "trr": "trr"}[kind]))
+        if kind == "raw":
+            trajio.write_trajectory(trj, xq, system.box9())
+        elif kind == "xtc":
+            TF.write_xtc(L, trj, x, system.box9())
+        else:
+            assert L.gmxstub_write_trr(trj.encode(), x.shape[1], K, xq.ctypes.data, None, None, box.ctypes.data, 1, None) == 0
+        trajio.write_topology(str(d / "sys.b2p"), system)
+        trajio.write_index(str(d / "sys.ndx"), {"OW": system.groups["OW"]})
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.path.join(ROOT, "gmx2020postanalysis_b200") + ":"
+                   + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([exe, "-f", trj, "-s", str(d / "sys.b2p"), "-n", str(d / "sys.ndx"), "-o", str(d / "o.xvg")], input="0 0\n",
+                           capture_output=True, text=True, env=env, cwd=str(d))
+        assert r.returncode == 0, r.stderr[-800:]
+        outs[kind] = refprog.data_lines(str(d / "o.xvg"))
+    assert len(outs["raw"]) > 100 and outs["raw"] == outs["xtc"] == outs["trr"]
+
+
 @pytest.mark.parametrize("center", [0, 2])
 def test_handle_full_dropin_matches_reference_build(center, tmp_path, monkeypatch):
     """GmxHandleFull (heterogeneous molecule sizes): the same exerciser source built against the reference's own header

@@ -1,0 +1,139 @@
+"""Real-trajectory ingestion: the XTC / TRR codecs of the libgromacs stand-in (gmxstub/xdrtraj.hpp).
+libgromacs 2020.1 itself is not available and the reference holds no trajectory fixtures, so these formats are pinned
+against the codec's own writer: decoding returns exactly the quantised coordinates the format defines, for every code
+path of the compression (small systems, water-like runs, huge coordinate ranges), frame by frame and through the
+multi-threaded batch reader; and the reference's own analysis program gives the same output from an XTC file as from the
+raw-float file holding the same quantised coordinates."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import refprog
+from gmx2020postanalysis_b200 import synth, trajio
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STUB = os.path.join(ROOT, "build", "libgmxstub.so")
+_P = C.c_void_p
+TRX_READ_X, TRX_READ_V, TRX_READ_F = 1 << 0, 1 << 2, 1 << 4     # gmxstub/include/gromacs/fileio/trxio.h
+
+
+@pytest.fixture(scope="module")
+def stub():
+    if not os.path.exists(STUB):
+        pytest.skip("build/libgmxstub.so not built")
+    L = C.CDLL(STUB)
+    L.gmxstub_write_xtc.argtypes = [C.c_char_p, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_float]
+    L.gmxstub_write_trr.argtypes = [C.c_char_p, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P]
+    L.gmxstub_read_all.argtypes = [C.c_char_p, C.c_int, C.c_int, _P, _P, _P, _P, _P, C.POINTER(C.c_int)]
+    L.gmxstub_read_batches.argtypes = [C.c_char_p, C.c_int, C.c_int, _P, _P, _P]
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def write_xtc(L, path, x, box9, times=None, precision=1000.0):
+    x = np.ascontiguousarray(x, np.float32)
+    b = np.ascontiguousarray(box9, np.float32).reshape(-1, 9)
+    t = np.ascontiguousarray(times, np.float32) if times is not None else None
+    assert L.gmxstub_write_xtc(path.encode(), x.shape[1], x.shape[0], _ptr(x), _ptr(b), b.shape[0], _ptr(t), precision) == 0
+
+
+def read_all(L, path, nmax, natoms, flags=TRX_READ_X):
+    x = np.zeros((nmax, natoms, 3), np.float32); v = np.zeros_like(x); f = np.zeros_like(x)
+    box = np.zeros((nmax, 9), np.float32); t = np.zeros(nmax, np.float32); na = C.c_int()
+    n = L.gmxstub_read_all(path.encode(), nmax, flags, _ptr(x), _ptr(v), _ptr(f), _ptr(box), _ptr(t), C.byref(na))
+    return n, na.value, x[:n], v[:n], f[:n], box[:n], t[:n]
+
+
+def quantise(x, precision):
+    """What an XTC file stores: int(x * precision +- 0.5) in float arithmetic, returned as int * (1 / precision)."""
+    p = np.float32(precision)
+    lf = x.astype(np.float32) * p
+    lf = lf + np.where(lf >= 0, np.float32(0.5), np.float32(-0.5)).astype(np.float32)
+    li = np.trunc(lf).astype(np.int32)
+    return li.astype(np.float32) * (np.float32(1.0) / p)
+
+
+@pytest.mark.parametrize("case", ["water", "il", "tiny", "huge_range", "precision100"])
+def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, case):
+    prec = 1000.0
+    if case == "water":
+        system = synth.water_box(1500, 3.6, seed=81); x = system.frames(0, 5); box = system.box9()
+    elif case == "il":
+        system = synth.ionic_liquid(200, 4.0, seed=82); x = system.frames(0, 3); box = system.box9()
+    elif case == "tiny":                       # natoms <= 9: stored as plain floats, no quantisation
+        x = np.random.default_rng(1).normal(size=(4, 7, 3)).astype(np.float32); box = np.eye(3, dtype=np.float32).ravel() * 5
+    elif case == "huge_range":                 # coordinate span > 2^24 / precision: every component coded with its own bit width
+        rng = np.random.default_rng(2)
+        x = (rng.uniform(-20000, 20000, size=(2, 64, 3))).astype(np.float32); box = np.eye(3, dtype=np.float32).ravel() * 4e4
+    else:
+        system = synth.water_box(800, 2.9, seed=83); x = system.frames(0, 2); box = system.box9(); prec = 100.0
+    path = str(tmp_path / "t.xtc")
+    times = np.arange(x.shape[0], dtype=np.float32) * 2.5
+    write_xtc(stub, path, x, box, times, prec)
+    n, natoms, got, _, _, gbox, gt = read_all(stub, path, x.shape[0] + 3, x.shape[1])
+    assert n == x.shape[0] and natoms == x.shape[1]
+    exp = x if case == "tiny" else quantise(x, prec)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(gt, times) and np.array_equal(gbox, np.repeat(np.asarray(box, np.float32).reshape(1, 9), n, axis=0))
+    if case == "water":                        # neighbours are coded as small differences: well under half the raw size
+        assert os.path.getsize(path) < 0.45 * x.nbytes
+    # the batch reader decodes the frames on several threads: same result, any batch size
+    for batch in (1, 2, 16):
+        bx = np.zeros_like(x); bb = np.zeros((x.shape[0], 9), np.float32); bt = np.zeros(x.shape[0], np.float32)
+        assert stub.gmxstub_read_batches(path.encode(), batch, x.shape[0], _ptr(bx), _ptr(bb), _ptr(bt)) == x.shape[0]
+        assert np.array_equal(bx, exp) and np.array_equal(bt, times)
+
+
+def test_trr_round_trip_exact(stub, tmp_path):
+    system = synth.ionic_liquid(50, 2.8, seed=84)
+    K = 4
+    x = system.frames(0, K)
+    rng = np.random.default_rng(3)
+    v = rng.normal(size=x.shape).astype(np.float32); f = (rng.normal(size=x.shape) * 500).astype(np.float32)
+    box = np.ascontiguousarray(system.box9(), np.float32).reshape(1, 9)
+    path = str(tmp_path / "t.trr")
+    assert stub.gmxstub_write_trr(path.encode(), x.shape[1], K, _ptr(x), _ptr(v), _ptr(f), _ptr(box), 1, None) == 0
+    n, natoms, gx, gv, gf, gbox, gt = read_all(stub, path, K + 2, x.shape[1], TRX_READ_X | TRX_READ_V | TRX_READ_F)
+    assert n == K and natoms == x.shape[1]
+    assert np.array_equal(gx, x) and np.array_equal(gv, v) and np.array_equal(gf, f)
+    assert np.array_equal(gt, np.arange(K, dtype=np.float32))
+    # coordinates only: v / f blocks are skipped
+    n, _, gx, gv, _, _, _ = read_all(stub, path, K, x.shape[1], TRX_READ_X)
+    assert n == K and np.array_equal(gx, x) and not gv.any()
+    # a file without velocities
+    path2 = str(tmp_path / "x.trr")
+    assert stub.gmxstub_write_trr(path2.encode(), x.shape[1], K, _ptr(x), None, None, _ptr(box), 1, None) == 0
+    n, _, gx, _, _, _, _ = read_all(stub, path2, K, x.shape[1], TRX_READ_X | TRX_READ_V)
+    assert n == K and np.array_equal(gx, x)
+
+
+def test_reference_program_reads_xtc_like_raw(stub, tmp_path):
+    """The reference's own calc_rdf_region (oracle/_ref) on an XTC file == on the raw file of the quantised coordinates."""
+    if not refprog.have_ref("calc_rdf_region"):
+        pytest.skip("oracle/_ref not built")
+    import subprocess
+    system = synth.water_box(500, 2.5, seed=85, split_atoms=True)
+    K = 3
+    xq = quantise(system.frames(0, K), 1000.0)
+    outs = []
+    for kind in ("raw", "xtc"):
+        d = tmp_path / kind
+        d.mkdir()
+        trj = str(d / ("sys.b2t" if kind == "raw" else "sys.xtc"))
+        if kind == "raw":
+            trajio.write_trajectory(trj, xq, system.box9())
+        else:
+            write_xtc(stub, trj, system.frames(0, K), system.box9())
+        trajio.write_topology(str(d / "sys.b2p"), system)
+        trajio.write_index(str(d / "sys.ndx"), {"OW": system.groups["OW"]})
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([os.path.join(refprog.REFDIR, "calc_rdf_region"), "-f", trj, "-s", str(d / "sys.b2p"), "-n", str(d / "sys.ndx"),
+                            "-o", str(d / "o.xvg")], input="0 0\n", capture_output=True, text=True, env=env, cwd=str(d))
+        assert r.returncode == 0, r.stderr[-500:]
+        outs.append(refprog.data_lines(str(d / "o.xvg")))
+    assert len(outs[0]) > 100 and outs[0] == outs[1]
