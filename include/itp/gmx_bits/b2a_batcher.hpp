@@ -29,9 +29,12 @@ namespace b2a_detail
         ~FrameBatcher()
         {
             if (ctx_) b2a_destroy(ctx_);
-            if (bx_) b2a_pinned_free(bx_);
-            if (bv_) b2a_pinned_free(bv_);
-            if (bf_) b2a_pinned_free(bf_);
+            for (int p = 0; p < 2; ++p)
+            {
+                if (px_[p]) b2a_pinned_free(px_[p]);
+                if (pv_[p]) b2a_pinned_free(pv_[p]);
+                if (pf_[p]) b2a_pinned_free(pf_[p]);
+            }
         }
         FrameBatcher(const FrameBatcher&) = delete;
         FrameBatcher& operator=(const FrameBatcher&) = delete;
@@ -58,16 +61,15 @@ namespace b2a_detail
             oenv_ = oenv; status_ = status; io_ = first; eof_ = false;
             natoms_ = io_.natoms;
             const size_t n3 = (size_t)natoms_ * 3;
-            if (!bx_)
+            for (int p = 0; p < 2; ++p)
             {
-                bx_ = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
-                if (!bx_) gmx_fatal(FARGS, "%s", b2a_last_error());
-                bbox_.resize(9 * (size_t)k_);
-                btime_.resize(k_);
+                if (!px_[p]) px_[p] = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
+                if (io_.bV && !pv_[p]) pv_[p] = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
+                if (io_.bF && !pf_[p]) pf_[p] = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
+                if (!px_[p] || (io_.bV && !pv_[p]) || (io_.bF && !pf_[p])) gmx_fatal(FARGS, "%s", b2a_last_error());
             }
-            if (io_.bV && !bv_) bv_ = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
-            if (io_.bF && !bf_) bf_ = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
-            if ((io_.bV && !bv_) || (io_.bF && !bf_)) gmx_fatal(FARGS, "%s", b2a_last_error());
+            bbox_.resize(9 * (size_t)k_);
+            btime_.resize(k_);
             if (!fill(true)) return false;
             point(0, fr);
             return true;
@@ -95,6 +97,8 @@ namespace b2a_detail
         {
             const size_t n3 = (size_t)natoms_ * 3;
             int          n  = 0;
+            flip_ ^= 1;
+            bx_ = px_[flip_]; bv_ = pv_[flip_]; bf_ = pf_[flip_];
 #ifdef GMXSTUB_BATCH_READ
             // The libgromacs stand-in can hand out K frames per call and decodes XTC frames on K host threads, straight
             // into the pinned batch.  With the real libgromacs this block compiles away and the loop below runs.
@@ -160,7 +164,12 @@ namespace b2a_detail
         int                natoms_ = 0, k_ = 16, n_ = 0, cur_ = 0;
         bool               eof_ = false;
         long               serial_ = 0;
-        float*             bx_ = nullptr, *bv_ = nullptr, *bf_ = nullptr;
+        // Two pinned staging buffers, used alternately: the asynchronous H2D copy of batch k may still be reading its
+        // buffer while the host already decodes batch k+1 into the other one; b2a_submit_batch(k+1) synchronises the
+        // stream before anything else, so by the time buffer k%2 is refilled (batch k+2) its copy has completed.
+        float*             px_[2] = { nullptr, nullptr }, *pv_[2] = { nullptr, nullptr }, *pf_[2] = { nullptr, nullptr };
+        float*             bx_ = nullptr, *bv_ = nullptr, *bf_ = nullptr;   // the buffers of the batch being filled / served
+        int                flip_ = 0;
         std::vector<float> bbox_, btime_;
     };
 } // namespace b2a_detail
