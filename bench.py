@@ -31,6 +31,10 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 NMOL, LBOX, SEED = 72000, 12.913, 20200102
 ISSUE_SLOTS_PER_PAIR = 19                           # algorithmic work per evaluated pair
+# dram__bytes_read.sum + dram__bytes_write.sum of one k3_rdf launch, per frame of the launch, from the ncu --set full
+# capture summarised in profiles/r01_k3_ncu.md (the kernel re-reads its 1.15 MB/frame of fixed-point coordinates from L2,
+# not from HBM; nothing is written back but the 26 KB histogram)
+K3_DRAM_BYTES_PER_FRAME = 4.64e6
 WORKLOAD = "O-O RDF, 216k-atom SPC/E water box (72k O, L=12.913 nm, Rm=L/2, Rbin=3228, nbin=5), calc_rdf_region defaults"
 
 
@@ -308,7 +312,8 @@ def main():
                     "frames_per_s": e2e_value / (NMOL * NMOL), "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": int(sum(n for k, (t, n) in timing.items() if k in ("k1_centers", "k3_rdf")) + 2 * prep_n + args.steps),
             "roofline": {"bound": "fp32_issue", "kernel": "k3_rdf", "achieved": achieved_inst / 1e12, "peak": peak_inst / 1e12,
-                         "unit": "Tinst/s", "frac": achieved_inst / peak_inst if peak_inst else None, "traffic": None,
+                         "unit": "Tinst/s", "frac": achieved_inst / peak_inst if peak_inst else None,
+                         "traffic": K3_DRAM_BYTES_PER_FRAME * F, "traffic_unit": "bytes per k3_rdf launch (ncu, profiles/r01_k3_ncu.md)",
                          "how": f"evaluated pairs per launch x {ISSUE_SLOTS_PER_PAIR} issue slots (BASELINE.md section 4) / mean CUDA-event "
                                 "duration of the k3_rdf launches inside the timed region; peak = 148 SM x 128 lanes x SM clock "
                                 "sampled by nvidia-smi during the timed region",

@@ -629,7 +629,6 @@ static int field_ready(b2a_ctx* c, int field, Group** g, int grp)
 {
     if (field != B2A_FIELD_V && field != B2A_FIELD_F) return fail(B2A_ERR_ARG, "field must be B2A_FIELD_V or B2A_FIELD_F");
     if (int rc = get_group(c, grp, g)) return rc;
-    if ((*g)->csr) return fail(B2A_ERR_UNSUPPORTED, "velocity / force loaders on a heterogeneous (GmxHandleFull) group are not implemented");
     if (c->nframes <= 0 || !c->d_field[field] || c->field_serial[field] != c->serial)
         return fail(B2A_ERR_STATE, "no %s submitted for the current batch (b2a_submit_field)", field == B2A_FIELD_V ? "velocities" : "forces");
     return B2A_OK;
@@ -648,6 +647,13 @@ static int run_field_centers(b2a_ctx* c, int field, Group& g, int com)
     }
     Timed tm(c, 0);
     dim3  grid((g.nmol + 127) / 128, c->nframes);
+    if (g.csr)
+    {
+        k1_field_centers_csr<<<grid, 128, 0, c->stream>>>(c->d_field[field], (size_t)c->natoms * 3, c->nframes, g.d_index, g.d_off, g.nmol,
+                                                          g.d_wfull[com], g.d_div[com], c->d_field_cen);
+        CU(cudaGetLastError());
+        return B2A_OK;
+    }
     k1_field_centers<<<grid, 128, sizeof(double) * g.napm, c->stream>>>(c->d_field[field], (size_t)c->natoms * 3, c->nframes, g.d_index, g.nmol,
                                                                          g.napm, g.d_w[com], make_div(g.wsum[com]), c->d_field_cen);
     CU(cudaGetLastError());
@@ -685,6 +691,7 @@ extern "C" int b2a_field_values(b2a_ctx* c, int field, int grp, int frame, doubl
     Group* g;
     if (int rc = field_ready(c, field, &g, grp)) return rc;
     if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_field_values: frame %d outside batch of %d", frame, c->nframes);
+    if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "b2a_field_values on a heterogeneous (GmxHandleFull) group: the reference class has no loadVelocity / loadForce");
     CU(cudaSetDevice(c->device));
     const size_t n = (size_t)g->nmol * g->napm;
     if (c->pos_scratch_n < n)

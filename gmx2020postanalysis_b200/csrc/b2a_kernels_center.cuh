@@ -252,6 +252,33 @@ __global__ void __launch_bounds__(256) k1_field_centers(const float* __restrict_
     o[2 * (size_t)nmol + i] = div_const(c2, wsum);
 }
 
+// GmxHandleFull::loadVelocityCenter (gmx_handle_full.ipp:201-250): per-molecule atom counts and weight totals
+__global__ void __launch_bounds__(256) k1_field_centers_csr(const float* __restrict__ v, size_t frame_stride, int nframes,
+                                                            const int* __restrict__ index, const int* __restrict__ off, int nmol,
+                                                            const double* __restrict__ wfull, const DivConst* __restrict__ div,
+                                                            double* __restrict__ cen)
+{
+    const int f = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmol || f >= nframes) return;
+    const int     o0 = __ldg(off + i), na = __ldg(off + i + 1) - o0;
+    const float*  p  = v + (size_t)f * frame_stride + (size_t)__ldg(index + o0) * 3;
+    const double* w  = wfull + o0;
+    double        c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    for (int j = 0; j < na; ++j)
+    {
+        const double wj = __ldg(w + j);
+        c0 = __dadd_rn(c0, __dmul_rn((double)__ldg(p + 3 * j), wj));
+        c1 = __dadd_rn(c1, __dmul_rn((double)__ldg(p + 3 * j + 1), wj));
+        c2 = __dadd_rn(c2, __dmul_rn((double)__ldg(p + 3 * j + 2), wj));
+    }
+    const DivConst d = div[i];
+    double*        o = cen + (size_t)f * 3 * nmol;
+    o[i]                    = div_const(c0, d);
+    o[(size_t)nmol + i]     = div_const(c1, d);
+    o[2 * (size_t)nmol + i] = div_const(c2, d);
+}
+
 // GmxHandle::loadVelocity / loadForce (ipp:201-226, 271-296): vel(i,j)[k] = fr->v[index[grp][n]][k], boxd memory order
 __global__ void __launch_bounds__(256) k1b_field_values(const float* __restrict__ vf, const int* __restrict__ index, int nmol,
                                                         int napm, double* __restrict__ out)

@@ -174,23 +174,20 @@ namespace itp
         std::memcpy(posc.data(), c.buf.data() + n3 * batch_.current(), n3 * sizeof(double));
     }
 
-    inline void GmxHandleFull::loadVelocityCenter(matd& velc, int grp, int com)   // full.ipp:201-250, host side (no unwrap)
+    inline void GmxHandleFull::loadVelocityCenter(matd& velc, int grp, int com)   // full.ipp:201-250: no unwrap, on the device
     {
         if (grp >= ngrps) gmx_fatal(FARGS, "grp(%d) should less than ngrps(%d)!", grp, ngrps);
-        int n = 0;
-        for (int i = 0; i != nmol[grp]; ++i)
+        if (com < 0 || com > 2) gmx_fatal(FARGS, "center(%d) should be 0 (mass), 1 (geometry) or 2 (charge)", com);
+        b2aEnsure();
+        CenCache&    c  = cen_[(1 << 8) | (grp << 2) | com];
+        const size_t n3 = 3 * (size_t)nmol[grp];
+        if (c.serial != batch_.serial())
         {
-            const int    first = index[grp][n];
-            const double tot   = com == 0 ? totMass[grp][i] : (com == 2 ? totCharge[grp][i] : (double)napm[grp][i]);
-            for (int k = 0; k != 3; ++k)
-            {
-                double acc = 0.0;
-                for (int j = 0; j != napm[grp][i]; ++j)
-                    acc += double(fr->v[first + j][k]) * (com == 0 ? mass[grp][i][j] : (com == 2 ? charge[grp][i][j] : 1.0));
-                velc(i, k) = acc / tot;
-            }
-            n += napm[grp][i];
+            c.buf.resize(n3 * batch_.capacity());
+            b2a_detail::check(b2a_field_centers_batch(batch_.ctx(), B2A_FIELD_V, grp, com, c.buf.data()));
+            c.serial = batch_.serial();
         }
+        std::memcpy(velc.data(), c.buf.data() + n3 * batch_.current(), n3 * sizeof(double));
     }
 
     inline FILE* GmxHandleFull::openWrite(std::string fnm, bool writeInfo)   // full.ipp:252-267

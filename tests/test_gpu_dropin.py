@@ -140,3 +140,9 @@ def test_handle_full_dropin_matches_reference_build(center, tmp_path, monkeypatc
     ref = refprog.run_program(ref_exe, str(tmp_path / "ref"), system, 5, ["System", "ANI"], args, "o.dat")
     got = refprog.run_program(new_exe, str(tmp_path / "new"), system, 5, ["System", "ANI"], args, "o.dat")
     assert len(ref) > 600 and got == ref
+    # with velocities (TRX_READ_V): GmxHandleFull::loadVelocityCenter, per-molecule totals, on the device
+    import numpy as np
+    v = np.random.default_rng(77).normal(size=(5, system.natoms, 3)).astype(np.float32)
+    ref = refprog.run_program(ref_exe, str(tmp_path / "refv"), system, 5, ["System", "ANI"], args + ["-vel", 1], "o.dat", velocities=v)
+    got = refprog.run_program(new_exe, str(tmp_path / "newv"), system, 5, ["System", "ANI"], args + ["-vel", 1], "o.dat", velocities=v)
+    assert sum(ln.startswith("v ") for ln in ref) == 5 * (120 + 60) and got == ref
