@@ -43,38 +43,39 @@ namespace itp
         void b2aEnsure();
 
     public:
+        // ---- what a program sets before init() --------------------------------------------------------------------------
         std::vector<const char*> desc = { "do some analysis for trajectort." };
+        std::vector<t_pargs>  pa;                 // user-defined options
+        std::vector<t_filenm> fnm;                // user-defined files
+        int ngrps;                                // number of index groups to ask for (default 1)
+        int flags;                                // TRX_READ_* (default TRX_READ_X)
+        int nthreads;                             // "-threads" option of the reference; unused by the device path
 
-        double               Lbox[3];
-        char**               grpname;
-        int*                     ngx;
-        t_topology*              top;
-        t_inputrec*               ir;
-        double                    dt;
-        double                  time;
-        double               preTime;
-        int**                  index;
-        t_trxframe*               fr;
-        int                    flags;
-        int                    ngrps;
-        int                   nframe;
-        std::vector<t_pargs>      pa;
-        std::vector<t_filenm>    fnm;
+        // ---- filled by init(): topology, groups, molecules ----------------------------------------------------------------
+        t_topology* top;
+        t_inputrec* ir;
+        char** grpname;
+        int*   ngx;
+        int**  index;
+        std::vector<int> nmol;                    // molecules per group
+        stdMatrix<int>   napm;                    // [grp][mol] atoms per molecule
+        stdMatrix<std::vector<double>> mass;      // [grp][mol][atom]
+        stdMatrix<std::vector<double>> charge;    // [grp][mol][atom]
+        stdMatrix<double> totMass;                // [grp][mol]
+        stdMatrix<double> totCharge;              // [grp][mol]
 
-        stdMatrix<int>          napm;      // atoms per molecule, per group
-        std::vector<int>        nmol;      // molecules per group
-        stdMatrix<std::vector<double>>     mass;      // [grp][mol][atom]
-        stdMatrix<std::vector<double>>   charge;
-        stdMatrix<double>    totMass;      // [grp][mol]
-        stdMatrix<double>  totCharge;
-        int                 nthreads;
+        // ---- per frame ----------------------------------------------------------------------------------------------------------
+        t_trxframe* fr;                           // CURRENT frame; x / v / f point into the pinned batch
+        double Lbox[3];                           // box diagonal
+        double time, preTime, dt;                 // dt lags one frame, like the reference
+        int    nframe;                            // frames read so far
 
     protected:
-        int                     argc;
-        char**                  argv;
-        t_trxstatus*          status;
-        gmx_output_env_t*       oenv;
-        int                     ePBC;
+        int    argc;
+        char** argv;
+        t_trxstatus*      status;
+        gmx_output_env_t* oenv;
+        int    ePBC;
 
     private:
         b2a_detail::FrameBatcher batch_;

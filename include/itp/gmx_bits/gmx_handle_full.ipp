@@ -10,7 +10,7 @@
 namespace itp
 {
     inline GmxHandleFull::GmxHandleFull(int argc, char** argv) :
-        flags(TRX_READ_X), ngrps(1), nframe(0), argc(argc), argv(argv), status(nullptr), oenv(nullptr), ePBC(0)
+        ngrps(1), flags(TRX_READ_X), nframe(0), argc(argc), argv(argv), status(nullptr), oenv(nullptr), ePBC(0)
     {
         grpname = nullptr; ngx = nullptr; top = nullptr; ir = nullptr; index = nullptr; fr = nullptr;
         dt = time = preTime = 0.0;
