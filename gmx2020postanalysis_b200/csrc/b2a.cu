@@ -426,6 +426,14 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
             g.ff.L[k]     = bk;
             g.ff.invL[k]  = (float)(1.0 / g.L[k]);
             g.ff.hs2[k]   = (float)(g.half[k] * (1.0 - 1e-5));
+            g.fk.negL2[2 * k] = g.fk.negL2[2 * k + 1] = -bk;
+            g.fk.invL2[2 * k] = g.fk.invL2[2 * k + 1] = g.ff.invL[k];
+        }
+        {   // one-threshold variant of the shift proof (orient_fast3): |u^| < min_k hs2 and |d| <= 2 max_k L keep the FP32 error
+            // of an offset below eps * 2.5 Lmax, which must stay well inside the 1e-5 * L_k / 2 margin of hs2 for every k
+            const float Lmax = std::max(g.ff.L[0], std::max(g.ff.L[1], g.ff.L[2])), Lmin = std::min(g.ff.L[0], std::min(g.ff.L[1], g.ff.L[2]));
+            g.fk.hsmin = (Lmax < 30.f * Lmin) ? std::min(g.ff.hs2[0], std::min(g.ff.hs2[1], g.ff.hs2[2])) : 0.f;
+            g.fk.dmax  = 2.f * Lmax;
         }
     }
     std::memcpy(c->h_box.data(), box9, sizeof(float) * 9 * (size_t)nframes);
@@ -476,7 +484,7 @@ static FastParams fast_params(const Group& g, int com, int mode)
     return fp;
 }
 
-template <int MODE, int NAPM_T>
+template <int MODE, int NAPM_T, int VAR = 0>
 static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode)
 {
     a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;
@@ -494,7 +502,7 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     a.work = c->d_work;
     size_t smem = (size_t)kStages * a.tile_floats * 4 + kStages * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
     if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut : 0);
-    auto kern = k_stream<MODE, NAPM_T>;
+    auto kern = k_stream<MODE, NAPM_T, VAR>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M + 32, smem));
@@ -507,9 +515,11 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
 }
 
 template <int MODE>
-static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode = 0)
+static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode = 0, int var = 0)
 {
     // three-site molecules (water) get fully unrolled atom loops; everything else runs the generic instantiation
+    if constexpr (MODE == 2)
+        if (g.napm == 3 && var == 1) return launch_stream_t<2, 3, 1>(c, g, com, M, a, extra_smem, fast_mode);
     if (g.napm == 3) return launch_stream_t<MODE, 3>(c, g, com, M, a, extra_smem, fast_mode);
     return launch_stream_t<MODE, 0>(c, g, com, M, a, extra_smem, fast_mode);
 }
@@ -1240,10 +1250,10 @@ extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
     edge[0] = 2.0;
     CU(cudaMalloc(&a->d_cosedge, sizeof(double) * (nA + 1)));
     CU(cudaMemcpy(a->d_cosedge, edge.data(), sizeof(double) * (nA + 1), cudaMemcpyHostToDevice));
-    std::vector<float> fedge(nA + 2, -3.0f);
+    std::vector<float> fedge(nA + 3, -3.0f);   // two sentinels below every cosine: the loop-free bin search reads fedge[lo + 2]
     for (int k = 0; k <= nA; ++k) fedge[k] = (float)edge[k];
-    CU(cudaMalloc(&a->d_fedge, sizeof(float) * (nA + 2)));
-    CU(cudaMemcpy(a->d_fedge, fedge.data(), sizeof(float) * (nA + 2), cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&a->d_fedge, sizeof(float) * (nA + 3)));
+    CU(cudaMemcpy(a->d_fedge, fedge.data(), sizeof(float) * (nA + 3), cudaMemcpyHostToDevice));
     {   // fast path: cos cell ci = [-1 + 2 ci / N, -1 + 2 (ci + 1) / N) -> the lowest angle bin any value below the upper end of the
         // NEXT cell can have (one cell of slack for the float rounding of the cell index); the device walks up from there
         std::vector<unsigned char> lut(kCosLut);
@@ -1312,7 +1322,15 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
         sa.lut = a.d_lut;
         // the bracket needs monotone radial bins
         const int fast = (s.dr > 0.f && s.CR > s.Cr) ? a.fast : 0;
-        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins, fast);
+        // three-site molecule with vectors (reference atom -> the other two): packed fast path orient_fast3
+        int var = 0;
+        if (g->napm == 3 && d.tp1 == 0 && ((d.tp2 == 1 && d.tp3 == 2) || (d.tp2 == 2 && d.tp3 == 1)))
+        {
+            var = 1;
+            sa.ori_sign = s.method == 1 ? -1.f : (d.tp2 == 1 ? 1.f : -1.f);
+        }
+        if (const char* e = getenv("B2A_ORIENT_VAR")) var = std::min(var, atoi(e));
+        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 4) & ~1) + sizeof(unsigned) * smem_bins, fast, var);
     }
     const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins;
     CU(cudaFuncSetAttribute(k4_orient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -8,6 +8,7 @@
 // the reference's sequential order, which is why this is a thread-per-molecule loop and not a shuffle tree.
 #pragma once
 
+#include <cstddef>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -22,6 +23,17 @@ struct FastFrame   // per frame, FP32 view of the box for the bracketed fast pat
     float pad[3];
 };
 
+// The same box, laid out for packed FP32 arithmetic (fma.rn.f32x2 works on register PAIRS): every constant appears twice
+// in a row, so one LDS.64 / LDS.128 delivers a ready-made pair.  Used by the three-site orientation fast path.
+struct __align__(16) FastPack
+{
+    float negL2[6];   // {-L0, -L0, -L1, -L1, -L2, -L2}
+    float invL2[6];   // {1/L0, 1/L0, ...}
+    float hsmin;      // min_k hs2[k]; 0 when the box is too elongated for the one-threshold shift proof (everything undecided)
+    float dmax;       // 2 max_k L[k]: raw atom-atom differences beyond this are not handled by the packed path
+    float pad[2];
+};
+
 struct FrameGeom   // per frame; filled on the host at submit time from the float box diagonal (ipp:72-74)
 {
     double L[3];         // Lbox[k] = double(fr->box[k][k])
@@ -30,8 +42,10 @@ struct FrameGeom   // per frame; filled on the host at submit time from the floa
     float  hsafe[3];     // float slightly BELOW Lbox[k]/2: |x - ref| < hsafe in FP32 proves that no unwrap shift is needed
     float  pad;
     FastFrame ff;
-    double pad16;        // sizeof == 144: the streaming kernels fetch one FrameGeom per stage with a 16-byte-granular bulk copy
+    double pad16;        // keeps `fk` on a 16-byte boundary
+    FastPack fk;         // sizeof == 208: the streaming kernels fetch one FrameGeom per stage with a 16-byte-granular bulk copy
 };
+static_assert(offsetof(FrameGeom, fk) % 16 == 0, "FastPack is read with 128-bit shared loads");
 static_assert(sizeof(FrameGeom) % 16 == 0, "FrameGeom is moved with cp.async.bulk");
 
 // Division by a block-invariant divisor, correctly rounded, in 3 FP64 instructions instead of the ~35 of __ddiv_rn:

@@ -22,6 +22,7 @@
 #pragma once
 
 #include "b2a_kernels_orient.cuh"
+#include "b2a_packed.cuh"
 
 namespace b2a
 {
@@ -225,6 +226,114 @@ __device__ __forceinline__ int orient_fast(const float* p, int napm, const float
     if (und) return 0;
     // proven: account exactly like orient_molecule()
     const int meZ = (int)k;
+    cell_z = cell_a = -1;
+    nsel++;
+    if (meZ >= d.nbin1) { ndrop++; return 1; }
+    cell_z = d.nbin1 * d.nAngle + meZ;
+    if (lo >= d.nAngle) { ndrop++; return 1; }
+    cell_a = meZ + lo * d.nbin1;
+    return 1;
+}
+
+// ---- K4 fast path for three-site molecules whose first vector atom is the molecule's reference atom -----------------------
+// (water: tp1 = O, {tp2, tp3} = the two H).  Same bracket as orient_fast(), restructured around what the instruction
+// stream of that function showed (profiles/r01_hbm.md: ~300 instructions per molecule, twice the HBM-rate budget):
+//  * With tp1 the reference atom, the vectors are the unwrapped offsets themselves: x~_0 - x~_j = -u_j, and periodicity()
+//    leaves them alone because the reference's unwrap loops already made |u_j| <= L/2 (gmx_handle.ipp:139-142,
+//    calc_orient_mof.cpp:31-38).  The six extra minimum-image evaluations disappear; m_v = m_u and m_dv = m_d.
+//  * The offsets of atoms 1 and 2 are evaluated together, per dimension, in packed FP32 (FADD2 / FFMA2): 12 issue slots
+//    instead of 24.  Each lane is bit-identical to fast_offset().
+//  * One threshold proves all six shift counts (min_k hs2[k], FastPack::hsmin) and one bounds all raw differences
+//    (FastPack::dmax); the maxima are FMNMX3 trees over |.| operands.
+//  * The angle bin is found without a loop: the look-up cell names the first candidate bin, one compare against the next
+//    edge moves up at most one bin, and the margin test against the two enclosing edges doubles as the proof that no
+//    further step was needed (fedge[0] = 2 and fedge[nAngle + 1 ..] = -3 make the end bins pass without special cases).
+// `wsgn` is the sign that turns the computed vector into the reference's vecOut: method 1: -(u1 + u2) -> -1;
+// method 2: (-u_tp2) x (-u_tp3) = +-(u1 x u2) -> +1 for (tp2, tp3) = (2nd, 3rd atom), -1 when swapped.
+template <bool SMEM>
+__device__ __forceinline__ int orient_fast3(const float* p, float w1, float w2, float wsgn, const FastParams& fp, const FastPack& fk,
+                                            const OrientDev& d, const OrientFast& of, const float* fedge, const unsigned char* lut,
+                                            int& cell_z, int& cell_a, unsigned& nsel, unsigned& ndrop)
+{
+    const float x0[3] = { ldf<SMEM>(p), ldf<SMEM>(p + 1), ldf<SMEM>(p + 2) };
+    const unsigned long long magic2 = f2pack(kRndMagic, kRndMagic);
+    float u1[3], u2[3], m_u = 0.f, m_d = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const unsigned long long nL2 = *reinterpret_cast<const unsigned long long*>(&fk.negL2[2 * k]);
+        const unsigned long long iL2 = *reinterpret_cast<const unsigned long long*>(&fk.invL2[2 * k]);
+        const unsigned long long X   = f2pack(ldf<SMEM>(p + 3 + k), ldf<SMEM>(p + 6 + k));
+        const unsigned long long D   = f2sub(X, f2pack(x0[k], x0[k]));            // d = fl(x_j - x_0)
+        const unsigned long long N   = f2sub(f2fma(D, iL2, magic2), magic2);     // rint(d / L)
+        const unsigned long long U   = f2fma(N, nL2, D);                         // u^ = fl(d - n L)
+        float da, db;
+        f2unpack(D, da, db);
+        f2unpack(U, u1[k], u2[k]);
+        m_d = fmaxf(fmaxf(m_d, fabsf(da)), fabsf(db));
+        m_u = fmaxf(fmaxf(m_u, fabsf(u1[k])), fabsf(u2[k]));
+    }
+    bool und = !(m_u < fk.hsmin && m_d <= fk.dmax);   // a shift count is not proven / outside the error model
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) c[k] = __fmaf_rn(__fmaf_rn(w2, u2[k], w1 * u1[k]), fp.invW, x0[k]);
+    const float Ec = fast_center_err(fmaxf(fabsf(c[0]), fmaxf(fabsf(c[1]), fabsf(c[2]))), m_u, m_d, fp);
+    // slab filter lowPos <= posc(i, DIMN) <= upPos (:158)
+    const float cz = d.DIMN == 0 ? c[0] : (d.DIMN == 1 ? c[1] : c[2]);
+    if (!(cz - Ec > of.low && cz + Ec < of.up))       // not proven inside: proven outside, or undecided
+    {
+        if (!und && (cz + Ec < of.low || cz - Ec > of.up)) { cell_z = cell_a = -1; return 1; }
+        und = true;
+    }
+    // R = sqrt(t1^2 + t2^2) (:160-175), bounds as in orient_fast()
+    const float ca = d.DIMN == 0 ? c[1] : c[0], cb = d.DIMN == 2 ? c[1] : c[2];
+    const float ta = ca - of.c1, tb = cb - of.c2;
+    float       R;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(__fmaf_rn(ta, ta, tb * tb)));
+    const float ER = __fmaf_rn(R, 8.0f * kEps, 1.5f * Ec);
+    if (!(R - ER > of.cr_lo && R + ER < of.CR))       // not proven selected: proven not selected, or undecided
+    {
+        if (!und && (R + ER < of.cr_lo || R - ER > of.CR)) { cell_z = cell_a = -1; return 1; }
+        und = true;
+    }
+    const float q  = (R - of.Cr) * of.inv_dr;
+    const float Eq = __fmaf_rn(ER, of.inv_dr * 1.01f, fabsf(q) * (3.2f * kEps));
+    const float kq = floorf(q);
+    const float fr = q - kq;
+    und = und || !(fr > Eq && fr < 1.0f - Eq && q < 2.0e9f && q >= 0.f);
+    // vecOut up to the sign wsgn; |v^ - v| <= Ev per component with m_v = m_u, m_dv = m_d
+    const float Ev = (1.05f * kEps) * (m_d + m_u);
+    float vo0, vo1, vo2, Evo;
+    if (d.method == 2)
+    {
+        vo0 = __fmaf_rn(u1[1], u2[2], -(u1[2] * u2[1]));
+        vo1 = __fmaf_rn(u1[2], u2[0], -(u1[0] * u2[2]));
+        vo2 = __fmaf_rn(u1[0], u2[1], -(u1[1] * u2[0]));
+        Evo = 1.05f * (4.0f * m_u * Ev + 2.0f * Ev * Ev + 4.0f * kEps * m_u * m_u);
+    }
+    else
+    {
+        vo0 = u1[0] + u2[0]; vo1 = u1[1] + u2[1]; vo2 = u1[2] + u2[2];
+        Evo = __fmaf_rn(2.1f * kEps, m_u, 2.1f * Ev);
+    }
+    const float n2 = __fmaf_rn(vo2, vo2, __fmaf_rn(vo1, vo1, vo0 * vo0));
+    float       rinv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(n2));
+    const float dot = d.DIMNOrient == 0 ? vo0 : (d.DIMNOrient == 1 ? vo1 : vo2);
+    const float cs  = dot * (rinv * wsgn);
+    const float rel = Evo * rinv;
+    const float Ecs = __fmaf_rn(rel, 3.0f, 10.0f * kEps + 1.3e-7f);
+    und = und || !(rel < 0.05f && n2 > 1.0e-30f && fabsf(cs) < 1.0f - Ecs);
+    // angle bin, loop-free (see the header comment); a NaN or out-of-range cs has set `und` above and only needs a valid cell
+    const unsigned ci = min((unsigned)__float2int_rz(__fmaf_rn(cs, 0.5f * kCosLut, 0.5f * kCosLut)), (unsigned)(kCosLut - 1));
+    int            lo = lut[ci];
+    const float    ea = fedge[lo], eb = fedge[lo + 1], ec = fedge[lo + 2];
+    const bool     step = cs <= eb;
+    lo += step ? 1 : 0;
+    const float e_up = step ? eb : ea, e_dn = step ? ec : eb;
+    und = und || !(cs <= e_up - Ecs && cs >= e_dn + Ecs);
+    if (und) return 0;
+    const int meZ = (int)kq;
     cell_z = cell_a = -1;
     nsel++;
     if (meZ >= d.nbin1) { ndrop++; return 1; }

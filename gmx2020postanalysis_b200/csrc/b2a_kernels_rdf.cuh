@@ -27,6 +27,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "b2a_packed.cuh"
+
 namespace b2a
 {
 
@@ -183,25 +185,6 @@ __device__ __forceinline__ void pair_bins(int xi, int yi, int zi, const int4& pj
 // round-to-nearest results on a 64-bit register pair.  The kernel is issue-bound, so the r^2 chain and the two bin FMAs of
 // TWO i-molecules against the same j are issued together: 5 packed instructions replace 10.  Every lane result is
 // bit-identical to pair_bins() (same operations, same rounding), which the out-of-line recheck path keeps using.
-__device__ __forceinline__ unsigned long long f2pack(float a, float b)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f2mul(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f2fma(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 template <bool CLAMP, bool CUBIC>
 __device__ __forceinline__ void pair_bins2(int xa, int ya, int za, int xb, int yb, int zb, const int4& pj, unsigned long long s_lo2,
                                            unsigned long long s_hi2, unsigned long long magic2, unsigned long long ay2,

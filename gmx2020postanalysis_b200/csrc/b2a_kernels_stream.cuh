@@ -78,6 +78,7 @@ struct StreamArgs
     DensityFast          df;
     OrientFast           of;
     const unsigned char* lut;    // MODE 2: kCosLut first-candidate angle bins
+    float                ori_sign;   // MODE 2, VAR 1: sign that turns orient_fast3's vector into the reference's vecOut
 };
 
 struct StageDesc { int m, f, poff, pad; };   // molecule block, frame, float offset of the block's first atom inside the stage; m < 0: end
@@ -97,7 +98,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 // compute out of shared memory and release the stage by arriving on its `empty` mbarrier, warp by warp.  There is no
 // block-wide barrier inside the stream: a slow warp never stalls the others, the ring never drains between items, and
 // tables / histogram zero+flush happen once per block for the whole launch.
-template <int MODE, int NAPM_T>
+// VAR (MODE 2 only): 1 = three-site molecule whose vector atoms are (reference atom, the other two) -> orient_fast3().
+template <int MODE, int NAPM_T, int VAR>
 __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamArgs a)
 {
     extern __shared__ __align__(16) unsigned char sraw[];
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
     double*             sedge = sw + napm;                                                     // MODE 2: nAngle + 1
     double*             stab  = sedge + (MODE == 2 ? a.ori.nAngle + 1 : 0);                    // MODE 2: nbin1 + 2
     float*              fedge = reinterpret_cast<float*>(stab + (MODE == 2 ? a.ori.nbin1 + 2 : 0));   // MODE 2: nAngle + 1
-    float*              swf   = fedge + (MODE == 2 ? ((a.ori.nAngle + 2) & ~1) : 0);                  // napm rounded up to even
+    float*              swf   = fedge + (MODE == 2 ? ((a.ori.nAngle + 4) & ~1) : 0);                  // napm rounded up to even
     unsigned*           shist = reinterpret_cast<unsigned*>(swf + ((napm + 1) & ~1));
     uint2*              fqueue = reinterpret_cast<uint2*>(shist + (MODE != 0 ? ((a.smem_bins + 1) & ~1) : 0));
     unsigned char*      slut   = reinterpret_cast<unsigned char*>(fqueue + (MODE != 0 ? kFastQueue : 0));
@@ -127,7 +129,8 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
     if (threadIdx.x == 0) fq_n = 0;
     if (MODE == 2)
     {
-        for (int j = threadIdx.x; j <= a.ori.nAngle; j += T) { sedge[j] = a.cosedge[j]; fedge[j] = a.fedge[j]; }
+        for (int j = threadIdx.x; j <= a.ori.nAngle; j += T) sedge[j] = a.cosedge[j];
+        for (int j = threadIdx.x; j < a.ori.nAngle + 3; j += T) fedge[j] = a.fedge[j];   // two -3 sentinels past the last edge
         for (int j = threadIdx.x; j < a.ori.nbin1 + 2; j += T) stab[j] = a.stab[j];
     }
     const OrientTabs tb{ sedge, fedge, stab };
@@ -186,6 +189,9 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
     {
         // ---- consumer warps ------------------------------------------------------------------------------------------------
         const unsigned toff = threadIdx.x * (unsigned)napm * 3u;
+        // orient_fast3: the two off-reference weights and the sign of the computed vector, kept in registers
+        const float w3a = (MODE == 2 && VAR == 1) ? a.wf[1] : 0.f, w3b = (MODE == 2 && VAR == 1) ? a.wf[2] : 0.f;
+        const float w3s = (MODE == 2 && VAR == 1) ? a.ori_sign : 0.f;
         for (unsigned n = 0;; ++n)
         {
             const int s = (int)(n % kStages);
@@ -244,7 +250,9 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
                     int cz = -1, ca = -1;
                     if (a.fp.enabled == 1)
                     {
-                        if (!orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, cz, ca, nsel, ndrop))
+                        const int proven = VAR == 1 ? orient_fast3<true>(p, w3a, w3b, w3s, a.fp, g.fk, a.ori, a.of, fedge, slut, cz, ca, nsel, ndrop)
+                                                    : orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, cz, ca, nsel, ndrop);
+                        if (!proven)
                         {
                             cz = ca = -1;
                             const unsigned slot = atomicAdd(&fq_n, 1u);
@@ -259,7 +267,9 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
                         {
                             unsigned fs = 0, fd = 0;
                             int      fz = -1, fa = -1;
-                            if (!orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, fz, fa, fs, fd)) nexact++;
+                            const int proven = VAR == 1 ? orient_fast3<true>(p, w3a, w3b, w3s, a.fp, g.fk, a.ori, a.of, fedge, slut, fz, fa, fs, fd)
+                                                        : orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, fz, fa, fs, fd);
+                            if (!proven) nexact++;
                             else if (fz != cz || fa != ca) nbad++;
                         }
                     }

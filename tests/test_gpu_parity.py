@@ -491,6 +491,61 @@ def test_fast_paths_validate_against_fp64(gpu_ctx_factory, which):
             assert int(s1[lib.STAT_EXACT]) > 0
 
 
+@pytest.mark.parametrize("var", [
+    dict(DIMN=2, DIMNOrient=2, method=1, tp=(1, 2, 3)),
+    dict(DIMN=0, DIMNOrient=1, method=2, tp=(1, 3, 2)),
+    dict(DIMN=1, DIMNOrient=0, method=2, tp=(1, 2, 3), box=(9.3, 7.1, 11.9)),
+    dict(DIMN=2, DIMNOrient=0, method=1, tp=(1, 3, 2), box=(6.0, 12.0, 8.0), nAngle=180),
+    dict(DIMN=2, DIMNOrient=2, method=1, tp=(2, 1, 3)),           # first vector atom is not the reference atom: generic path
+])
+def test_orient_three_site_packed_fast_path(gpu_ctx_factory, var):
+    """The packed three-site fast path (orient_fast3: vectors = unwrapped offsets, FADD2/FFMA2, loop-free angle bin) against
+    the literal FP64 kernel (mode 0), in validation mode (mode 2: proven-but-different must be 0) and against the oracle."""
+    box = var.get("box", (8.1, 8.1, 8.1))
+    system = synth.water_box(12000, box[0], seed=4242)
+    K = 3
+    x = system.frames(0, K).copy()
+    box9 = np.tile(np.diag(np.array(box, np.float32)).reshape(1, 9), (K, 1)).astype(np.float32)
+    if "box" in var:                       # squeeze the cubic synthetic box into the orthorhombic one, then re-wrap per atom
+        x *= (np.array(box, np.float32) / np.float32(box[0]))
+    x[1] += np.float32(2.0) * np.array(box, np.float32)          # a frame far outside [0, L)
+    x[2, 4::9, 2] -= np.float32(box[2])                          # some H atoms one box below their O
+    ctx = gpu_ctx_factory(system.natoms, K)
+    (gi,) = _groups(ctx, system, ["SOL"])
+    L = [float(np.float32(b)) for b in box]
+    D = var["DIMN"]
+    a_, b_ = [k for k in range(3) if k != D]
+    spec = dict(grp=0, com=0, DIMN=D, low=0.1 * L[D], up=0.8 * L[D], c1=0.5 * L[a_], c2=0.5 * L[b_], dr=0.07, CR=0.42 * min(L[a_], L[b_]),
+                Cr=0.2, nAngle=var.get("nAngle", 90), tp1=var["tp"][0], tp2=var["tp"][1], tp3=var["tp"][2], DIMNOrient=var["DIMNOrient"],
+                method=var["method"])
+    ctx.submit(x, box9)
+    res = []
+    for mode in (0, 1, 2):
+        acc = ctx.orient_create(**spec)
+        ctx.acc_fast(acc, mode)
+        ctx.accumulate(acc)
+        res.append(ctx.read(acc, ctx.acc_size(acc)))
+    (c0, s0), (c1, s1), (c2, s2) = res
+    assert c0.sum() > 0
+    assert np.array_equal(c0, c1) and np.array_equal(c0, c2)
+    assert int(s2[lib.STAT_MISPROVEN]) == 0
+    for st in (lib.STAT_DROPPED, lib.STAT_SELECTED, lib.STAT_FRAMES):
+        assert int(s0[st]) == int(s1[st]) == int(s2[st])
+    assert 0 < int(s1[lib.STAT_EXACT]) < 0.05 * ctx.nmol(0) * K
+    # and the literal kernel itself against the oracle port on the same frames
+    nbin1, nA = int((np.float32(spec["CR"]) - np.float32(spec["Cr"])) / np.float32(spec["dr"])), spec["nAngle"]
+    f32 = np.float32
+    o = ncm = None
+    for f in range(K):
+        Lbox = port.lbox_from_box9(box9[f:f + 1])
+        pos = port.load_position(x[f], gi["index"], 3, Lbox)
+        pc = port.load_position_center(x[f], gi["index"], 3, gi["w"][0], Lbox)
+        o, ncm, _ = port.orient_accum(pos, pc, Lbox, D, f32(spec["low"]), f32(spec["up"]), f32(spec["c1"]), f32(spec["c2"]), f32(spec["dr"]),
+                                      f32(spec["CR"]), f32(spec["Cr"]), nA, spec["tp1"], spec["tp2"], spec["tp3"], spec["DIMNOrient"],
+                                      spec["method"], o, ncm)
+    assert np.array_equal(c0[:nA * nbin1].reshape(nA, nbin1), o) and np.array_equal(c0[nA * nbin1:], ncm)
+
+
 # ---- cell-binned RDF (SURVEY 8f-1): identical counts to the all-pairs evaluation ---------------------------------
 def _rdf_gpu_cells(ctx, system, g0, g1, K, spec, Rm, Rbin, cells, paranoid=0, symmetric=0):
     _groups(ctx, system, [g0, g1])
