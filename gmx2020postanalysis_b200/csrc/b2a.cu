@@ -128,6 +128,7 @@ struct Acc
     int       ipt = 0, threads = 0;   // 0 = auto
     int       fast = 1;               // density / orient: 0 literal FP64, 1 FP32 bracket + FP64 queue, 2 validate
     unsigned char* d_lut = nullptr;   // orient: cos cell -> first candidate angle bin
+    float2*        d_fmh = nullptr;   // orient: per angle bin {midpoint, shrunk halfwidth} of its cosine interval
     // coord
     int*        d_cnt = nullptr;      // [maxK][n0] pair counts of the last batch
     unsigned*   d_table = nullptr;    // [maxK][max_count] per-frame histogram of counts of the last batch
@@ -238,7 +239,7 @@ static void free_group(Group& g)
 static void free_acc(Acc& a)
 {
     cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
-    cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab); cudaFree(a.d_lut);
+    cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab); cudaFree(a.d_lut); cudaFree(a.d_fmh);
     cudaFree(a.d_cnt); cudaFree(a.d_table); cudaFree(a.d_cframes);
     if (a.h_cframes) cudaFreeHost(a.h_cframes);
     cudaFree(a.d_keysA); cudaFree(a.d_keysB); cudaFree(a.d_cellA); cudaFree(a.d_cellB); cudaFree(a.d_sortedB);
@@ -490,17 +491,19 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;
     a.atom0 = g.h_index[0]; a.nmol = g.nmol; a.napm = g.napm;
     a.w = g.d_w[com]; a.wsum = make_div(g.wsum[com]); a.geom = c->d_geom;
-    a.tile_floats = ((M * g.napm * 3 + 8) + 3) & ~3;
+    const int MT  = VAR == 1 ? 2 * M : M;   // molecules per tile: VAR 1 evaluates two per consumer thread
+    a.tile_floats = ((MT * g.napm * 3 + 8) + 3) & ~3;
     a.wf = g.d_wf[com];
     a.fp = fast_params(g, com, MODE == 0 ? 0 : fast_mode);
     // work items: (molecule block, 4 consecutive frames); persistent blocks pull them from a counter
-    a.mblocks     = (g.nmol + M - 1) / M;
+    a.mblocks     = (g.nmol + MT - 1) / MT;
     a.item_frames = 4;
     if (const char* e = getenv("B2A_ITEM_FRAMES")) a.item_frames = std::max(1, atoi(e));
     a.nitems      = a.mblocks * ((c->nframes + a.item_frames - 1) / a.item_frames);
     if (!c->d_work) CU(cudaMalloc(&c->d_work, sizeof(unsigned)));
     a.work = c->d_work;
-    size_t smem = (size_t)kStages * a.tile_floats * 4 + kStages * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
+    constexpr int NS = stream_stages(MODE, VAR);
+    size_t smem = (size_t)NS * a.tile_floats * 4 + NS * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
     if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut : 0);
     auto kern = k_stream<MODE, NAPM_T, VAR>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -519,7 +522,12 @@ static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs 
 {
     // three-site molecules (water) get fully unrolled atom loops; everything else runs the generic instantiation
     if constexpr (MODE == 2)
-        if (g.napm == 3 && var == 1) return launch_stream_t<2, 3, 1>(c, g, com, M, a, extra_smem, fast_mode);
+        if (g.napm == 3 && var == 1)
+        {
+            int mc = M;   // consumer threads; each evaluates two molecules, so a tile holds 2 * mc
+            if (const char* e = getenv("B2A_K4_THREADS")) mc = std::max(32, std::min(256, atoi(e) / 32 * 32));
+            return launch_stream_t<2, 3, 1>(c, g, com, mc, a, extra_smem, fast_mode);
+        }
     if (g.napm == 3) return launch_stream_t<MODE, 3>(c, g, com, M, a, extra_smem, fast_mode);
     return launch_stream_t<MODE, 0>(c, g, com, M, a, extra_smem, fast_mode);
 }
@@ -1266,6 +1274,18 @@ extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
         }
         CU(cudaMalloc(&a->d_lut, kCosLut));
         CU(cudaMemcpy(a->d_lut, lut.data(), kCosLut, cudaMemcpyHostToDevice));
+        // interval form of "bin == k": edge[k + 1] < c <= edge[k]  <=  |c - mid| < hw, with hw shrunk by more than the float
+        // roundings of mid, of c - mid and of hw - E on the device (7.5 * 2^-24 for |values| <= 3) and rounded towards zero
+        std::vector<float2> fmh(nA + 2);
+        for (int k = 0; k <= nA + 1; ++k)
+        {
+            const double up = k <= nA ? edge[k] : -3.0, dn = k < nA ? edge[k + 1] : -3.0;
+            const double hw = (up - dn) / 2 - 6e-7;
+            fmh[k].x = (float)((up + dn) / 2);
+            fmh[k].y = hw > 0 ? std::nextafter((float)hw, 0.0f) : 0.0f;
+        }
+        CU(cudaMalloc(&a->d_fmh, sizeof(float2) * (nA + 2)));
+        CU(cudaMemcpy(a->d_fmh, fmh.data(), sizeof(float2) * (nA + 2), cudaMemcpyHostToDevice));
     }
     // Radial thresholds in s = t1^2 + t2^2 (calc_orient_mof.cpp:175-179): R = sqrt(s) (IEEE, identical on host and
     // device), selected iff Cr <= R <= CR, meZ = int((R - Cr) / dr).  Everything is monotone in s, so bisection over the
@@ -1319,18 +1339,18 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
         sa.ori = d; sa.cosedge = a.d_cosedge; sa.fedge = a.d_fedge; sa.stab = a.d_stab; sa.hist = a.d_hist; sa.stats = a.d_hist + a.ndev; sa.smem_bins = smem_bins;
         sa.of.low = s.low; sa.of.up = s.up; sa.of.c1 = s.c1; sa.of.c2 = s.c2; sa.of.Cr = s.Cr; sa.of.CR = s.CR;
         sa.of.inv_dr = 1.0f / s.dr; sa.of.cr_lo = s.Cr > 0.f ? s.Cr : -3.0e38f;
-        sa.lut = a.d_lut;
+        sa.lut = a.d_lut; sa.fmh = a.d_fmh;
         // the bracket needs monotone radial bins
         const int fast = (s.dr > 0.f && s.CR > s.Cr) ? a.fast : 0;
         // three-site molecule with vectors (reference atom -> the other two): packed fast path orient_fast3
         int var = 0;
-        if (g->napm == 3 && d.tp1 == 0 && ((d.tp2 == 1 && d.tp3 == 2) || (d.tp2 == 2 && d.tp3 == 1)))
+        if (g->napm == 3 && smem_bins > 0 && d.tp1 == 0 && ((d.tp2 == 1 && d.tp3 == 2) || (d.tp2 == 2 && d.tp3 == 1)))
         {
             var = 1;
             sa.ori_sign = s.method == 1 ? -1.f : (d.tp2 == 1 ? 1.f : -1.f);
         }
         if (const char* e = getenv("B2A_ORIENT_VAR")) var = std::min(var, atoi(e));
-        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 4) & ~1) + sizeof(unsigned) * smem_bins, fast, var);
+        return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 4) & ~1) + sizeof(float2) * (s.nAngle + 2) + sizeof(unsigned) * smem_bins, fast, var);
     }
     const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins;
     CU(cudaFuncSetAttribute(k4_orient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

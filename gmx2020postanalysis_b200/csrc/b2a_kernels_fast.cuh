@@ -237,110 +237,169 @@ __device__ __forceinline__ int orient_fast(const float* p, int napm, const float
 
 // ---- K4 fast path for three-site molecules whose first vector atom is the molecule's reference atom -----------------------
 // (water: tp1 = O, {tp2, tp3} = the two H).  Same bracket as orient_fast(), restructured around what the instruction
-// stream of that function showed (profiles/r01_hbm.md: ~300 instructions per molecule, twice the HBM-rate budget):
+// stream of that function showed (profiles/r01_hbm.md: ~300 instructions per molecule, against the ~200 issue slots per
+// molecule that HBM leaves):
 //  * With tp1 the reference atom, the vectors are the unwrapped offsets themselves: x~_0 - x~_j = -u_j, and periodicity()
 //    leaves them alone because the reference's unwrap loops already made |u_j| <= L/2 (gmx_handle.ipp:139-142,
 //    calc_orient_mof.cpp:31-38).  The six extra minimum-image evaluations disappear; m_v = m_u and m_dv = m_d.
-//  * The offsets of atoms 1 and 2 are evaluated together, per dimension, in packed FP32 (FADD2 / FFMA2): 12 issue slots
-//    instead of 24.  Each lane is bit-identical to fast_offset().
+//  * TWO molecules per thread, one in each half of a 64-bit register pair: every add / multiply / fma of the chain (offsets,
+//    centre, error bounds, radius, bin coordinate, vector, cosine) is one packed FP32 instruction (FADD2 / FMUL2 / FFMA2)
+//    for both molecules.  Each half is the IEEE operation the scalar code would execute.  Only what has no packed form
+//    stays per molecule: |.|-maxima (FMNMX3), compares, MUFU.SQRT / RSQ, float -> int, table look-ups.
 //  * One threshold proves all six shift counts (min_k hs2[k], FastPack::hsmin) and one bounds all raw differences
-//    (FastPack::dmax); the maxima are FMNMX3 trees over |.| operands.
-//  * The angle bin is found without a loop: the look-up cell names the first candidate bin, one compare against the next
-//    edge moves up at most one bin, and the margin test against the two enclosing edges doubles as the proof that no
-//    further step was needed (fedge[0] = 2 and fedge[nAngle + 1 ..] = -3 make the end bins pass without special cases).
+//    (FastPack::dmax).
+//  * The fraction test of the radial bin and the angle-bin test are |value - midpoint| < halfwidth - error: one compare
+//    instead of two.  The angle bin is found without a
+//    loop: the look-up cell names the first candidate bin, one compare against the next edge moves up at most one bin, and
+//    the interval test against that bin's {midpoint, halfwidth} (host table, halfwidth shrunk by the float roundings of
+//    the table) doubles as the proof that no further step was needed.
 // `wsgn` is the sign that turns the computed vector into the reference's vecOut: method 1: -(u1 + u2) -> -1;
 // method 2: (-u_tp2) x (-u_tp3) = +-(u1 x u2) -> +1 for (tp2, tp3) = (2nd, 3rd atom), -1 when swapped.
-template <bool SMEM>
-__device__ __forceinline__ int orient_fast3(const float* p, float w1, float w2, float wsgn, const FastParams& fp, const FastPack& fk,
-                                            const OrientDev& d, const OrientFast& of, const float* fedge, const unsigned char* lut,
-                                            int& cell_z, int& cell_a, unsigned& nsel, unsigned& ndrop)
+__device__ __forceinline__ unsigned long long f2bc(float a) { return f2pack(a, a); }
+
+// the inputs of orient_fast3x2(): coordinates of two molecules (A in the low, B in the high half of every pair) and the packed
+// frame constants.  (Handing the stage back to the producer right after these loads, before the arithmetic, was tried and
+// is slower: 0.097 vs 0.090 ms per 64 frames -- the kernel waits on its own dependency chains, not on the feed.)
+struct Mol3x2
 {
-    const float x0[3] = { ldf<SMEM>(p), ldf<SMEM>(p + 1), ldf<SMEM>(p + 2) };
-    const unsigned long long magic2 = f2pack(kRndMagic, kRndMagic);
-    float u1[3], u2[3], m_u = 0.f, m_d = 0.f;
+    unsigned long long X0[3], X1[3], X2[3];   // atom 0 (reference), 1, 2; component k
+    unsigned long long nL2[3], iL2[3];        // (-L_k, -L_k), (1/L_k, 1/L_k)
+    float              hsmin, dmax;
+};
+
+template <bool SMEM>
+__device__ __forceinline__ void load3x2(Mol3x2& m, const float* pA, const float* pB, const FastPack& fk)
+{
 #pragma unroll
     for (int k = 0; k < 3; ++k)
     {
-        const unsigned long long nL2 = *reinterpret_cast<const unsigned long long*>(&fk.negL2[2 * k]);
-        const unsigned long long iL2 = *reinterpret_cast<const unsigned long long*>(&fk.invL2[2 * k]);
-        const unsigned long long X   = f2pack(ldf<SMEM>(p + 3 + k), ldf<SMEM>(p + 6 + k));
-        const unsigned long long D   = f2sub(X, f2pack(x0[k], x0[k]));            // d = fl(x_j - x_0)
-        const unsigned long long N   = f2sub(f2fma(D, iL2, magic2), magic2);     // rint(d / L)
-        const unsigned long long U   = f2fma(N, nL2, D);                         // u^ = fl(d - n L)
-        float da, db;
-        f2unpack(D, da, db);
-        f2unpack(U, u1[k], u2[k]);
-        m_d = fmaxf(fmaxf(m_d, fabsf(da)), fabsf(db));
-        m_u = fmaxf(fmaxf(m_u, fabsf(u1[k])), fabsf(u2[k]));
+        m.nL2[k] = *reinterpret_cast<const unsigned long long*>(&fk.negL2[2 * k]);
+        m.iL2[k] = *reinterpret_cast<const unsigned long long*>(&fk.invL2[2 * k]);
+        m.X0[k]  = f2pack(ldf<SMEM>(pA + k), ldf<SMEM>(pB + k));
+        m.X1[k]  = f2pack(ldf<SMEM>(pA + 3 + k), ldf<SMEM>(pB + 3 + k));
+        m.X2[k]  = f2pack(ldf<SMEM>(pA + 6 + k), ldf<SMEM>(pB + 6 + k));
     }
-    bool und = !(m_u < fk.hsmin && m_d <= fk.dmax);   // a shift count is not proven / outside the error model
-    float c[3];
+    m.hsmin = fk.hsmin; m.dmax = fk.dmax;
+}
+
+__device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, bool validB, float w1, float w2, float wsgn, const FastParams& fp,
+                                               const OrientDev& d, const OrientFast& of, const float* fedge, const float2* fmh,
+                                               const unsigned char* lut, int res[2], int meZ[2], int lo[2])
+{
+    typedef unsigned long long P;   // (molecule A, molecule B)
+    const P magic2 = f2bc(kRndMagic);
+    P       U1[3], U2[3];
+    float   mdA = 0.f, mdB = 0.f, muA = 0.f, muB = 0.f;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) c[k] = __fmaf_rn(__fmaf_rn(w2, u2[k], w1 * u1[k]), fp.invW, x0[k]);
-    const float Ec = fast_center_err(fmaxf(fabsf(c[0]), fmaxf(fabsf(c[1]), fabsf(c[2]))), m_u, m_d, fp);
-    // slab filter lowPos <= posc(i, DIMN) <= upPos (:158)
-    const float cz = d.DIMN == 0 ? c[0] : (d.DIMN == 1 ? c[1] : c[2]);
-    if (!(cz - Ec > of.low && cz + Ec < of.up))       // not proven inside: proven outside, or undecided
+    for (int k = 0; k < 3; ++k)
     {
-        if (!und && (cz + Ec < of.low || cz - Ec > of.up)) { cell_z = cell_a = -1; return 1; }
-        und = true;
+        const P D1 = f2sub(m.X1[k], m.X0[k]);   // d = fl(x_j - x_0)
+        const P D2 = f2sub(m.X2[k], m.X0[k]);
+        U1[k]      = f2fma(f2sub(f2fma(D1, m.iL2[k], magic2), magic2), m.nL2[k], D1);   // u^ = fl(d - rint(d / L) L)
+        U2[k]      = f2fma(f2sub(f2fma(D2, m.iL2[k], magic2), magic2), m.nL2[k], D2);
+        float a, b, e, f;
+        f2unpack(D1, a, b); f2unpack(D2, e, f);
+        mdA = fmaxf(fmaxf(mdA, fabsf(a)), fabsf(e)); mdB = fmaxf(fmaxf(mdB, fabsf(b)), fabsf(f));
+        f2unpack(U1[k], a, b); f2unpack(U2[k], e, f);
+        muA = fmaxf(fmaxf(muA, fabsf(a)), fabsf(e)); muB = fmaxf(fmaxf(muB, fabsf(b)), fabsf(f));
     }
-    // R = sqrt(t1^2 + t2^2) (:160-175), bounds as in orient_fast()
-    const float ca = d.DIMN == 0 ? c[1] : c[0], cb = d.DIMN == 2 ? c[1] : c[2];
-    const float ta = ca - of.c1, tb = cb - of.c2;
-    float       R;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(R) : "f"(__fmaf_rn(ta, ta, tb * tb)));
-    const float ER = __fmaf_rn(R, 8.0f * kEps, 1.5f * Ec);
-    if (!(R - ER > of.cr_lo && R + ER < of.CR))       // not proven selected: proven not selected, or undecided
+    bool undA = !(muA < m.hsmin && mdA <= m.dmax), undB = !(muB < m.hsmin && mdB <= m.dmax);   // shift count not proven
+    const P MU = f2pack(muA, muB), MD = f2pack(mdA, mdB);
+    const P W1 = f2bc(w1), W2 = f2bc(w2), IW = f2bc(fp.invW);
+    P       C[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) C[k] = f2fma(f2fma(W2, U2[k], f2mul(W1, U1[k])), IW, m.X0[k]);
+    float c0a, c0b, c1a, c1b, c2a, c2b;
+    f2unpack(C[0], c0a, c0b); f2unpack(C[1], c1a, c1b); f2unpack(C[2], c2a, c2b);
+    const P CM = f2pack(fmaxf(fabsf(c0a), fmaxf(fabsf(c1a), fabsf(c2a))), fmaxf(fabsf(c0b), fmaxf(fabsf(c1b), fabsf(c2b))));
+    const P Ec = f2fma(CM, f2bc(fp.e1), f2fma(MD, f2bc(fp.e2), f2mul(MU, f2bc(fp.e3))));      // fast_center_err()
+    // slab filter (:158) and radial selection (:160-177); DIMN picks the components
+    const P Cz = d.DIMN == 0 ? C[0] : (d.DIMN == 1 ? C[1] : C[2]);
+    const P Ca = d.DIMN == 0 ? C[1] : C[0], Cb = d.DIMN == 2 ? C[1] : C[2];
+    bool    outA = false, outB = false;   // proven "not counted"
     {
-        if (!und && (R + ER < of.cr_lo || R - ER > of.CR)) { cell_z = cell_a = -1; return 1; }
-        und = true;
+        const P LO = f2sub(Cz, Ec), HI = f2add(Cz, Ec);
+        float   la, lb, ha, hb;
+        f2unpack(LO, la, lb); f2unpack(HI, ha, hb);
+        if (!(la > of.low && ha < of.up)) { if (!undA && (ha < of.low || la > of.up)) outA = true; else undA = true; }   // outside, or undecided
+        if (!(lb > of.low && hb < of.up)) { if (!undB && (hb < of.low || lb > of.up)) outB = true; else undB = true; }
     }
-    const float q  = (R - of.Cr) * of.inv_dr;
-    const float Eq = __fmaf_rn(ER, of.inv_dr * 1.01f, fabsf(q) * (3.2f * kEps));
-    const float kq = floorf(q);
-    const float fr = q - kq;
-    und = und || !(fr > Eq && fr < 1.0f - Eq && q < 2.0e9f && q >= 0.f);
-    // vecOut up to the sign wsgn; |v^ - v| <= Ev per component with m_v = m_u, m_dv = m_d
-    const float Ev = (1.05f * kEps) * (m_d + m_u);
-    float vo0, vo1, vo2, Evo;
+    const P Ta = f2sub(Ca, f2bc(of.c1)), Tb = f2sub(Cb, f2bc(of.c2));
+    const P S  = f2fma(Ta, Ta, f2mul(Tb, Tb));
+    float   sa, sb, ra, rb;
+    f2unpack(S, sa, sb);
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(sa));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(sb));
+    const P R  = f2pack(ra, rb);
+    const P ER = f2fma(R, f2bc(8.0f * kEps), f2mul(Ec, f2bc(1.5f)));    // |R^ - R| < 1.5 Ec + 8 eps R
+    {
+        const P LO = f2sub(R, ER), HI = f2add(R, ER);
+        float   la, lb, ha, hb;
+        f2unpack(LO, la, lb); f2unpack(HI, ha, hb);
+        if (!(la > of.cr_lo && ha < of.CR)) { if (!undA && (ha < of.cr_lo || la > of.CR)) outA = true; else undA = true; }
+        if (!(lb > of.cr_lo && hb < of.CR)) { if (!undB && (hb < of.cr_lo || lb > of.CR)) outB = true; else undB = true; }
+    }
+    // radial bin coordinate q = (R - Cr) / dr: proven when its fraction is further than Eq from 0 and 1 and 0 <= q < 2e9
+    const P Q  = f2mul(f2sub(R, f2bc(of.Cr)), f2bc(of.inv_dr));
+    const P Eq = f2fma(ER, f2bc(of.inv_dr * 1.01f), f2mul(Q, f2bc(3.2f * kEps)));
+    float   qa, qb;
+    f2unpack(Q, qa, qb);
+    const float kqa = floorf(qa), kqb = floorf(qb);
+    {
+        // |fr - 1/2| < 1/2 - Eq  <=>  Eq < fr < 1 - Eq; q - floor(q) is exact, the two roundings here are inside the 4 eps
+        const P G = f2sub(f2sub(Q, f2pack(kqa, kqb)), f2bc(0.5f)), H = f2sub(f2bc(0.5f - 4.0f * kEps), Eq);
+        float   ga, gb, ha, hb;
+        f2unpack(G, ga, gb); f2unpack(H, ha, hb);
+        // as unsigned integers the bit patterns of [+0, 2e9) are ordered and everything negative / NaN lies above
+        undA = undA || !(fabsf(ga) < ha) || !(__float_as_uint(qa) < __float_as_uint(2.0e9f));
+        undB = undB || !(fabsf(gb) < hb) || !(__float_as_uint(qb) < __float_as_uint(2.0e9f));
+    }
+    // vecOut up to the sign wsgn; |v^ - v| <= Ev per component
+    const P Ev = f2mul(f2add(MD, MU), f2bc(1.05f * kEps));
+    P       VO[3], Evo;
     if (d.method == 2)
     {
-        vo0 = __fmaf_rn(u1[1], u2[2], -(u1[2] * u2[1]));
-        vo1 = __fmaf_rn(u1[2], u2[0], -(u1[0] * u2[2]));
-        vo2 = __fmaf_rn(u1[0], u2[1], -(u1[1] * u2[0]));
-        Evo = 1.05f * (4.0f * m_u * Ev + 2.0f * Ev * Ev + 4.0f * kEps * m_u * m_u);
+        VO[0] = f2sub(f2mul(U1[1], U2[2]), f2mul(U1[2], U2[1]));
+        VO[1] = f2sub(f2mul(U1[2], U2[0]), f2mul(U1[0], U2[2]));
+        VO[2] = f2sub(f2mul(U1[0], U2[1]), f2mul(U1[1], U2[0]));
+        // |d(ab - cd)| <= Ev (|a|+|b|+|c|+|d|) + 2 Ev^2 + 2 eps (|ab| + |cd|), inflated by 5 %
+        Evo = f2mul(f2fma(f2mul(MU, f2bc(4.0f)), Ev, f2fma(f2add(Ev, Ev), Ev, f2mul(f2mul(MU, f2bc(4.0f * kEps)), MU))), f2bc(1.05f));
     }
     else
     {
-        vo0 = u1[0] + u2[0]; vo1 = u1[1] + u2[1]; vo2 = u1[2] + u2[2];
-        Evo = __fmaf_rn(2.1f * kEps, m_u, 2.1f * Ev);
+        VO[0] = f2add(U1[0], U2[0]); VO[1] = f2add(U1[1], U2[1]); VO[2] = f2add(U1[2], U2[2]);
+        Evo   = f2fma(MU, f2bc(2.1f * kEps), f2mul(Ev, f2bc(2.1f)));
     }
-    const float n2 = __fmaf_rn(vo2, vo2, __fmaf_rn(vo1, vo1, vo0 * vo0));
-    float       rinv;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(n2));
-    const float dot = d.DIMNOrient == 0 ? vo0 : (d.DIMNOrient == 1 ? vo1 : vo2);
-    const float cs  = dot * (rinv * wsgn);
-    const float rel = Evo * rinv;
-    const float Ecs = __fmaf_rn(rel, 3.0f, 10.0f * kEps + 1.3e-7f);
-    und = und || !(rel < 0.05f && n2 > 1.0e-30f && fabsf(cs) < 1.0f - Ecs);
-    // angle bin, loop-free (see the header comment); a NaN or out-of-range cs has set `und` above and only needs a valid cell
-    const unsigned ci = min((unsigned)__float2int_rz(__fmaf_rn(cs, 0.5f * kCosLut, 0.5f * kCosLut)), (unsigned)(kCosLut - 1));
-    int            lo = lut[ci];
-    const float    ea = fedge[lo], eb = fedge[lo + 1], ec = fedge[lo + 2];
-    const bool     step = cs <= eb;
-    lo += step ? 1 : 0;
-    const float e_up = step ? eb : ea, e_dn = step ? ec : eb;
-    und = und || !(cs <= e_up - Ecs && cs >= e_dn + Ecs);
-    if (und) return 0;
-    const int meZ = (int)kq;
-    cell_z = cell_a = -1;
-    nsel++;
-    if (meZ >= d.nbin1) { ndrop++; return 1; }
-    cell_z = d.nbin1 * d.nAngle + meZ;
-    if (lo >= d.nAngle) { ndrop++; return 1; }
-    cell_a = meZ + lo * d.nbin1;
-    return 1;
+    const P N2 = f2fma(VO[2], VO[2], f2fma(VO[1], VO[1], f2mul(VO[0], VO[0])));
+    float   n2a, n2b, ria, rib;
+    f2unpack(N2, n2a, n2b);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ria) : "f"(n2a));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rib) : "f"(n2b));
+    const P RI  = f2pack(ria, rib);
+    const P DOT = d.DIMNOrient == 0 ? VO[0] : (d.DIMNOrient == 1 ? VO[1] : VO[2]);
+    const P CS  = f2mul(DOT, f2mul(RI, f2bc(wsgn)));
+    const P REL = f2mul(Evo, RI);
+    const P Ecs = f2fma(REL, f2bc(3.0f), f2bc(10.0f * kEps));   // the float roundings of the edge table are inside fmh[].y
+    const P OM  = f2sub(f2bc(1.0f), Ecs);
+    const P CI  = f2fma(CS, f2bc(0.5f * kCosLut), f2bc(0.5f * kCosLut));
+    float   csa, csb, rela, relb, ecsa, ecsb, oma, omb, cia, cib;
+    f2unpack(CS, csa, csb); f2unpack(REL, rela, relb); f2unpack(Ecs, ecsa, ecsb); f2unpack(OM, oma, omb); f2unpack(CI, cia, cib);
+    undA = undA || !(rela < 0.05f && n2a > 1.0e-30f && fabsf(csa) < oma);
+    undB = undB || !(relb < 0.05f && n2b > 1.0e-30f && fabsf(csb) < omb);
+    // angle bin; a NaN or out-of-range cosine has set `und` above and only needs a valid look-up cell
+    int loA = lut[min((unsigned)__float2int_rz(cia), (unsigned)(kCosLut - 1))];
+    int loB = lut[min((unsigned)__float2int_rz(cib), (unsigned)(kCosLut - 1))];
+    loA += csa <= fedge[loA + 1] ? 1 : 0;
+    loB += csb <= fedge[loB + 1] ? 1 : 0;
+    const float2 mhA = fmh[loA], mhB = fmh[loB];
+    undA = undA || !(fabsf(csa - mhA.x) < mhA.y - ecsa);
+    undB = undB || !(fabsf(csb - mhB.x) < mhB.y - ecsb);
+    // per molecule: 0 = undecided, 1 = proven "not counted", 2 = proven selected with radial bin meZ and angle bin lo (either may
+    // still lie outside its array: the caller accounts for that exactly like orient_molecule())
+    res[0] = (outA || !validA) ? 1 : (undA ? 0 : 2);   // a molecule past the end of the group counts as "not counted"
+    res[1] = (outB || !validB) ? 1 : (undB ? 0 : 2);
+    meZ[0] = (int)kqa; meZ[1] = (int)kqb;
+    lo[0] = loA; lo[1] = loB;
 }
 
 } // namespace b2a

@@ -15,6 +15,8 @@ namespace b2a
 {
 
 constexpr int kStages   = 4;
+// the two-molecules-per-thread orientation variant stages 512-molecule tiles: three of them keep three blocks on an SM
+__host__ __device__ constexpr int stream_stages(int mode, int var) { return (mode == 2 && var == 1) ? 3 : kStages; }
 constexpr int kFastQueue = 1024;  // undecided (molecule, frame) entries per block; drained when half full, overflow runs inline
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -44,6 +46,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity)
+        : "memory");
+}
+
+// the producer's wait for a free stage: the ring is normally full, so this thread would spin for most of the kernel and
+// take issue slots from the consumer warps of its scheduler (ncu: 20 try_wait round trips per tile); the suspend-time hint
+// lets the hardware park it until the phase completes or the limit (ns) expires
+__device__ __forceinline__ void mbar_wait_parked(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(20000u)
         : "memory");
 }
 
@@ -78,7 +96,8 @@ struct StreamArgs
     DensityFast          df;
     OrientFast           of;
     const unsigned char* lut;    // MODE 2: kCosLut first-candidate angle bins
-    float                ori_sign;   // MODE 2, VAR 1: sign that turns orient_fast3's vector into the reference's vecOut
+    float                ori_sign;   // MODE 2, VAR 1: sign that turns orient_fast3x2's vector into the reference's vecOut
+    const float2*        fmh;        // MODE 2: per angle bin {midpoint, halfwidth - table roundings} of its cosine interval
 };
 
 struct StageDesc { int m, f, poff, pad; };   // molecule block, frame, float offset of the block's first atom inside the stage; m < 0: end
@@ -98,31 +117,35 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 // compute out of shared memory and release the stage by arriving on its `empty` mbarrier, warp by warp.  There is no
 // block-wide barrier inside the stream: a slow warp never stalls the others, the ring never drains between items, and
 // tables / histogram zero+flush happen once per block for the whole launch.
-// VAR (MODE 2 only): 1 = three-site molecule whose vector atoms are (reference atom, the other two) -> orient_fast3().
+// VAR (MODE 2 only): 1 = three-site molecule whose vector atoms are (reference atom, the other two) -> orient_fast3x2(),
+// two molecules per consumer thread (a tile holds 2 x consumer-thread-count molecules).
 template <int MODE, int NAPM_T, int VAR>
-__global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamArgs a)
+__global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream(const __grid_constant__ StreamArgs a)
 {
+    constexpr int NS = stream_stages(MODE, VAR);   // depth of the TMA ring
     extern __shared__ __align__(16) unsigned char sraw[];
-    // layout: [tiles: kStages x tile_floats floats] [frame geometry per stage] [full bars] [empty bars] [stage descriptors]
+    // layout: [tiles: NS x tile_floats floats] [frame geometry per stage] [full bars] [empty bars] [stage descriptors]
     //         [weights] [edges] [float weights] [histogram] [undecided queue] [cos look-up table]
     float*              tiles = reinterpret_cast<float*>(sraw);
-    FrameGeom*          sgeom = reinterpret_cast<FrameGeom*>(tiles + (size_t)kStages * a.tile_floats);     // kStages entries (TMA)
-    unsigned long long* full  = reinterpret_cast<unsigned long long*>(sgeom + kStages);
-    unsigned long long* empty = full + kStages;
-    StageDesc*          sdesc = reinterpret_cast<StageDesc*>(empty + kStages);
-    double*             sw    = reinterpret_cast<double*>(sdesc + kStages);
+    FrameGeom*          sgeom = reinterpret_cast<FrameGeom*>(tiles + (size_t)NS * a.tile_floats);     // NS entries (TMA)
+    unsigned long long* full  = reinterpret_cast<unsigned long long*>(sgeom + NS);
+    unsigned long long* empty = full + NS;
+    StageDesc*          sdesc = reinterpret_cast<StageDesc*>(empty + NS);
+    double*             sw    = reinterpret_cast<double*>(sdesc + NS);
     const int           napm  = NAPM_T ? NAPM_T : a.napm;
     double*             sedge = sw + napm;                                                     // MODE 2: nAngle + 1
     double*             stab  = sedge + (MODE == 2 ? a.ori.nAngle + 1 : 0);                    // MODE 2: nbin1 + 2
     float*              fedge = reinterpret_cast<float*>(stab + (MODE == 2 ? a.ori.nbin1 + 2 : 0));   // MODE 2: nAngle + 1
-    float*              swf   = fedge + (MODE == 2 ? ((a.ori.nAngle + 4) & ~1) : 0);                  // napm rounded up to even
+    float2*             fmh   = reinterpret_cast<float2*>(fedge + (MODE == 2 ? ((a.ori.nAngle + 4) & ~1) : 0));   // MODE 2: nAngle + 2
+    float*              swf   = reinterpret_cast<float*>(fmh + (MODE == 2 ? a.ori.nAngle + 2 : 0));              // napm rounded up to even
     unsigned*           shist = reinterpret_cast<unsigned*>(swf + ((napm + 1) & ~1));
     uint2*              fqueue = reinterpret_cast<uint2*>(shist + (MODE != 0 ? ((a.smem_bins + 1) & ~1) : 0));
     unsigned char*      slut   = reinterpret_cast<unsigned char*>(fqueue + (MODE != 0 ? kFastQueue : 0));
     __shared__ unsigned fq_n;
 
     const int T = blockDim.x;          // all threads (prologue / epilogue loops)
-    const int M = blockDim.x - 32;     // consumer threads = molecules per tile
+    const int M = blockDim.x - 32;     // consumer threads
+    const int MT = (MODE == 2 && VAR == 1) ? 2 * M : M;   // molecules per tile (VAR 1: two per consumer thread)
     for (int j = threadIdx.x; j < napm; j += T) { sw[j] = a.w[j]; if (MODE != 0) swf[j] = a.wf[j]; }
     if (MODE == 2 && a.fp.enabled)
         for (int j = threadIdx.x; j < kCosLut / 4; j += T) reinterpret_cast<unsigned*>(slut)[j] = reinterpret_cast<const unsigned*>(a.lut)[j];
@@ -131,6 +154,7 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
     {
         for (int j = threadIdx.x; j <= a.ori.nAngle; j += T) sedge[j] = a.cosedge[j];
         for (int j = threadIdx.x; j < a.ori.nAngle + 3; j += T) fedge[j] = a.fedge[j];   // two -3 sentinels past the last edge
+        for (int j = threadIdx.x; j < a.ori.nAngle + 2; j += T) fmh[j] = a.fmh[j];
         for (int j = threadIdx.x; j < a.ori.nbin1 + 2; j += T) stab[j] = a.stab[j];
     }
     const OrientTabs tb{ sedge, fedge, stab };
@@ -138,7 +162,7 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
         for (int b = threadIdx.x; b < a.smem_bins; b += T) shist[b] = 0;
     if (threadIdx.x == 0)
     {
-        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)(M >> 5)); }
+        for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)(M >> 5)); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -157,8 +181,8 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
             int      f = 0, fend = 0, m = -1;
             for (unsigned n = 0;; ++n)
             {
-                const int s = (int)(n % kStages);
-                if (n >= (unsigned)kStages) mbar_wait(&empty[s], ((n / kStages) - 1u) & 1u);
+                const int s = (int)(n % NS);
+                if (n >= (unsigned)NS) mbar_wait_parked(&empty[s], ((n / NS) - 1u) & 1u);
                 if (m >= 0 && f >= fend) { m = -1; it = next; next = atomicAdd(a.work, 1u); }
                 if (m < 0 && it < (unsigned)a.nitems)
                 {
@@ -172,9 +196,9 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
                     mbar_arrive(&full[s]);
                     break;
                 }
-                const int            mvalid = min(M, a.nmol - m * M);
+                const int            mvalid = min(MT, a.nmol - m * MT);
                 const unsigned       nbytes = (unsigned)mvalid * napm * 12u;
-                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + (size_t)f * a.frame_stride + ((size_t)a.atom0 + (size_t)m * M * napm) * 3);
+                const unsigned char* src = reinterpret_cast<const unsigned char*>(a.x + (size_t)f * a.frame_stride + ((size_t)a.atom0 + (size_t)m * MT * napm) * 3);
                 const unsigned       sh  = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
                 const unsigned       nb  = (sh + nbytes + 15u) & ~15u;   // the byte range widened to 16-byte boundaries
                 sdesc[s] = StageDesc{ m, f, (int)(s * a.tile_floats + (sh >> 2)), 0 };
@@ -189,20 +213,22 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
     {
         // ---- consumer warps ------------------------------------------------------------------------------------------------
         const unsigned toff = threadIdx.x * (unsigned)napm * 3u;
-        // orient_fast3: the two off-reference weights and the sign of the computed vector, kept in registers
+        // orient_fast3x2: the two off-reference weights and the sign of the computed vector, kept in registers
         const float w3a = (MODE == 2 && VAR == 1) ? a.wf[1] : 0.f, w3b = (MODE == 2 && VAR == 1) ? a.wf[2] : 0.f;
         const float w3s = (MODE == 2 && VAR == 1) ? a.ori_sign : 0.f;
         for (unsigned n = 0;; ++n)
         {
-            const int s = (int)(n % kStages);
-            mbar_wait(&full[s], (n / kStages) & 1u);
+            const int s = (int)(n % NS);
+            mbar_wait(&full[s], (n / NS) & 1u);
             const StageDesc sd = sdesc[s];
             if (sd.m < 0) break;   // the stream is in order: nothing follows the first end marker
             const int f = sd.f;
-            const int i = sd.m * M + (int)threadIdx.x;
-            if (i < a.nmol)
+            const int i = sd.m * MT + (int)threadIdx.x;
+            // (VAR 1 masks molecules past the end of the group instead of branching around them)
+            const bool vA = i < a.nmol;
+            if ((MODE == 2 && VAR == 1) || vA)
             {
-                const float*     p = tiles + sd.poff + toff;
+                const float*     p = tiles + sd.poff + (vA ? toff : 0u);   // !vA: the tile's first molecule, evaluated and ignored
                 const FrameGeom& g = sgeom[s];
                 if (MODE == 0)
                 {
@@ -247,41 +273,103 @@ __global__ void __launch_bounds__(288) k_stream(const __grid_constant__ StreamAr
                 }
                 else
                 {
-                    int cz = -1, ca = -1;
-                    if (a.fp.enabled == 1)
-                    {
-                        const int proven = VAR == 1 ? orient_fast3<true>(p, w3a, w3b, w3s, a.fp, g.fk, a.ori, a.of, fedge, slut, cz, ca, nsel, ndrop)
-                                                    : orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, cz, ca, nsel, ndrop);
-                        if (!proven)
+                    auto count = [&](int cz, int ca) {
+                        if (cz >= 0)
                         {
+                            if (use_smem) atomicAdd(&shist[cz], 1u);
+                            else atomicAdd(&a.hist[cz], 1ull);
+                        }
+                        if (ca >= 0)
+                        {
+                            if (use_smem) atomicAdd(&shist[ca], 1u);
+                            else atomicAdd(&a.hist[ca], 1ull);
+                        }
+                    };
+                    // undecided by the FP32 bracket: queue for the literal FP64 code (inline when the queue is full)
+                    // (a full queue evaluates inline, from global memory like the drain at the end of the kernel)
+                    auto undecided = [&](int im) {
+                        const unsigned slot = atomicAdd(&fq_n, 1u);
+                        if (slot < (unsigned)kFastQueue) { fqueue[slot] = make_uint2((unsigned)im, (unsigned)f); return; }
+                        int          cz, ca;
+                        const float* pg = a.x + (size_t)f * a.frame_stride + ((size_t)a.atom0 + (size_t)im * napm) * 3;
+                        orient_molecule<false>(pg, napm, sw, a.wsum, a.geom[f], a.ori, tb, cz, ca, nsel, ndrop);
+                        nexact++;
+                        count(cz, ca);
+                    };
+                    if constexpr (VAR == 1)
+                    {
+                        const int    iB = i + M;                 // second molecule of this thread
+                        const bool   vB = iB < a.nmol;
+                        const float* pB = vB ? p + (unsigned)M * 9u : p;   // past the end of the group: a copy that is ignored
+                        int res[2], meZ[2], lo[2];
+                        if (a.fp.enabled)
+                        {
+                            Mol3x2 mol;
+                            load3x2<true>(mol, p, pB, g.fk);
+                            orient_fast3x2(mol, vA, vB, w3a, w3b, w3s, a.fp, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
+                        }
+                        // accounting of a proven molecule, statement for statement as at the end of orient_molecule(); the host
+                        // selects this variant only when the histogram fits in shared memory
+                        auto cells = [&](int l, int& cz, int& ca, unsigned& ns, unsigned& nd) {
                             cz = ca = -1;
-                            const unsigned slot = atomicAdd(&fq_n, 1u);
-                            if (slot < (unsigned)kFastQueue) fqueue[slot] = make_uint2((unsigned)i, (unsigned)f);
-                            else { orient_molecule<true>(p, napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop); nexact++; }
+                            if (res[l] != 2) return;
+                            ns++;
+                            if (meZ[l] >= a.ori.nbin1) { nd++; return; }
+                            cz = a.ori.nbin1 * a.ori.nAngle + meZ[l];
+                            if (lo[l] >= a.ori.nAngle) { nd++; return; }
+                            ca = meZ[l] + lo[l] * a.ori.nbin1;
+                        };
+                        if (a.fp.enabled == 1)
+                        {
+#pragma unroll
+                            for (int l = 0; l < 2; ++l)
+                            {
+                                if (res[l] == 0) { undecided(l ? iB : i); continue; }
+                                int cz, ca;
+                                cells(l, cz, ca, nsel, ndrop);
+                                if (cz >= 0) atomicAdd(&shist[cz], 1u);
+                                if (ca >= 0) atomicAdd(&shist[ca], 1u);
+                            }
+                        }
+                        else
+                        {
+                            for (int l = 0; l < 2; ++l)
+                            {
+                                if (!(l ? vB : vA)) continue;
+                                int ez, ea;
+                                orient_molecule<true>(l ? pB : p, napm, sw, a.wsum, g, a.ori, tb, ez, ea, nsel, ndrop);
+                                if (a.fp.enabled == 2)   // validation: a proven FP32 answer must equal the FP64 one
+                                {
+                                    unsigned fs = 0, fd = 0;
+                                    int      fz, fa;
+                                    cells(l, fz, fa, fs, fd);
+                                    if (!res[l]) nexact++;
+                                    else if (fz != ez || fa != ea) nbad++;
+                                }
+                                count(ez, ea);
+                            }
                         }
                     }
                     else
                     {
-                        orient_molecule<true>(p, napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop);
-                        if (a.fp.enabled == 2)
+                        int cz = -1, ca = -1;
+                        if (a.fp.enabled == 1)
                         {
-                            unsigned fs = 0, fd = 0;
-                            int      fz = -1, fa = -1;
-                            const int proven = VAR == 1 ? orient_fast3<true>(p, w3a, w3b, w3s, a.fp, g.fk, a.ori, a.of, fedge, slut, fz, fa, fs, fd)
-                                                        : orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, fz, fa, fs, fd);
-                            if (!proven) nexact++;
-                            else if (fz != cz || fa != ca) nbad++;
+                            if (orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, cz, ca, nsel, ndrop)) count(cz, ca);
+                            else undecided(i);
                         }
-                    }
-                    if (cz >= 0)
-                    {
-                        if (use_smem) atomicAdd(&shist[cz], 1u);
-                        else atomicAdd(&a.hist[cz], 1ull);
-                    }
-                    if (ca >= 0)
-                    {
-                        if (use_smem) atomicAdd(&shist[ca], 1u);
-                        else atomicAdd(&a.hist[ca], 1ull);
+                        else
+                        {
+                            orient_molecule<true>(p, napm, sw, a.wsum, g, a.ori, tb, cz, ca, nsel, ndrop);
+                            if (a.fp.enabled == 2)
+                            {
+                                unsigned fs = 0, fd = 0;
+                                int      fz = -1, fa = -1;
+                                if (!orient_fast<true>(p, napm, swf, a.fp, g.ff, a.ori, a.of, fedge, slut, fz, fa, fs, fd)) nexact++;
+                                else if (fz != cz || fa != ca) nbad++;
+                            }
+                            count(cz, ca);
+                        }
                     }
                 }
             }
