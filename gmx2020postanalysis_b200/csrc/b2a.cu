@@ -491,7 +491,8 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;
     a.atom0 = g.h_index[0]; a.nmol = g.nmol; a.napm = g.napm;
     a.w = g.d_w[com]; a.wsum = make_div(g.wsum[com]); a.geom = c->d_geom;
-    const int MT  = VAR == 1 ? 2 * M : M;   // molecules per tile: VAR 1 evaluates two per consumer thread
+    // molecules per tile: MODE 2 / VAR 1 evaluates two per consumer thread, MODE 0 / VAR 2 spends three lanes on each
+    const int MT  = (MODE == 2 && VAR == 1) ? 2 * M : ((MODE == 0 && VAR == 2) ? 10 * (M / 32) : M);
     a.tile_floats = ((MT * g.napm * 3 + 8) + 3) & ~3;
     a.wf = g.d_wf[com];
     a.fp = fast_params(g, com, MODE == 0 ? 0 : fast_mode);
@@ -521,6 +522,14 @@ template <int MODE>
 static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode = 0, int var = 0)
 {
     // three-site molecules (water) get fully unrolled atom loops; everything else runs the generic instantiation
+    if constexpr (MODE == 0)
+    {
+        // larger molecules: one lane per (molecule, dimension), ten molecules per warp, <= 24 KB of atoms per stage
+        int kvar = g.napm >= 8 ? 2 : 0;   // measured cross-over (tools/bench_hbm_napm.py): 7 atoms 0.63 vs 0.57, 8 atoms 0.50 vs 0.58, 25 atoms 0.19 vs 0.47
+        if (const char* e = getenv("B2A_K1_VAR")) kvar = atoi(e);
+        const int warps = std::min(8, 24576 / (120 * g.napm));
+        if (kvar == 2 && g.napm != 3 && warps >= 1) return launch_stream_t<0, 0, 2>(c, g, com, 32 * warps, a, extra_smem, fast_mode);
+    }
     if constexpr (MODE == 2)
         if (g.napm == 3 && var == 1)
         {

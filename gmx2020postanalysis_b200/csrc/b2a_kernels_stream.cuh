@@ -16,7 +16,7 @@ namespace b2a
 
 constexpr int kStages   = 4;
 // the two-molecules-per-thread orientation variant stages 512-molecule tiles: three of them keep three blocks on an SM
-__host__ __device__ constexpr int stream_stages(int mode, int var) { return (mode == 2 && var == 1) ? 3 : kStages; }
+__host__ __device__ constexpr int stream_stages(int mode, int var) { return ((mode == 2 && var == 1) || (mode == 0 && var == 2)) ? 3 : kStages; }
 constexpr int kFastQueue = 1024;  // undecided (molecule, frame) entries per block; drained when half full, overflow runs inline
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
 
     const int T = blockDim.x;          // all threads (prologue / epilogue loops)
     const int M = blockDim.x - 32;     // consumer threads
-    const int MT = (MODE == 2 && VAR == 1) ? 2 * M : M;   // molecules per tile (VAR 1: two per consumer thread)
+    // molecules per tile.  MODE 2 / VAR 1: two per consumer thread.  MODE 0 / VAR 2: THREE LANES per molecule (one per
+    // dimension), ten molecules per warp -- the exact FP64 centre of a large molecule is one long dependent chain per
+    // dimension, and its atoms take 12 * napm bytes of every stage: one thread per molecule leaves an SM with a handful of
+    // warps crawling along those chains (napm = 25: 0.19 of HBM peak, tools/bench_hbm_napm.py)
+    const int MT = (MODE == 2 && VAR == 1) ? 2 * M : ((MODE == 0 && VAR == 2) ? 10 * (M >> 5) : M);
     for (int j = threadIdx.x; j < napm; j += T) { sw[j] = a.w[j]; if (MODE != 0) swf[j] = a.wf[j]; }
     if (MODE == 2 && a.fp.enabled)
         for (int j = threadIdx.x; j < kCosLut / 4; j += T) reinterpret_cast<unsigned*>(slut)[j] = reinterpret_cast<const unsigned*>(a.lut)[j];
@@ -226,7 +230,27 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
             const int i = sd.m * MT + (int)threadIdx.x;
             // (VAR 1 masks molecules past the end of the group instead of branching around them)
             const bool vA = i < a.nmol;
-            if ((MODE == 2 && VAR == 1) || vA)
+            if constexpr (MODE == 0 && VAR == 2)
+            {
+                const int  lane = (int)threadIdx.x & 31, ml = lane / 3, k = lane - 3 * ml;
+                const int  il = (int)(threadIdx.x >> 5) * 10 + ml;            // molecule inside the tile
+                const int  im = sd.m * MT + il;
+                const bool ok = lane < 30 && im < a.nmol;
+                const FrameGeom& g = sgeom[s];
+                double           ck = 0.0;
+                if (ok)
+                {
+                    ck = center_component<true>(tiles + sd.poff + (unsigned)il * (unsigned)napm * 3u, k, napm, sw, a.wsum, g.L[k], g.half[k], g.hsafe[k]);
+                    a.cen[(size_t)f * 3 * a.nmol + (size_t)k * a.nmol + im] = ck;
+                }
+                if (a.fix)
+                {   // the fixed-point triple of a molecule sits in three neighbouring lanes
+                    const int fk = ok ? to_fixed(ck, g.inv_unit[k]) : 0;
+                    const int fy = __shfl_down_sync(0xffffffffu, fk, 1), fz = __shfl_down_sync(0xffffffffu, fk, 2);
+                    if (ok && k == 0) a.fix[(size_t)f * a.nmol + im] = make_int4(fk, fy, fz, im);
+                }
+            }
+            else if ((MODE == 2 && VAR == 1) || vA)
             {
                 const float*     p = tiles + sd.poff + (vA ? toff : 0u);   // !vA: the tile's first molecule, evaluated and ignored
                 const FrameGeom& g = sgeom[s];
