@@ -146,6 +146,27 @@ __device__ __forceinline__ double center_component(const float* p, int k, int na
     return div_const(c, wsum);
 }
 
+// the same value (same operations in the same order), written so that only the additions sit on the dependent chain: the loads,
+// conversions, unwrap pre-tests and multiplications of four atoms at a time are independent of the running sum
+template <bool SMEM>
+__device__ __forceinline__ double center_component_pipelined(const float* p, int k, int napm, const double* sw, const DivConst& wsum,
+                                                             double L, double half, float hsafe)
+{
+    const float ref = ldf<SMEM>(p + k);
+    double      c   = 0.0;
+    int         j   = 0;
+    for (; j + 4 <= napm; j += 4)
+    {
+        double t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) t[u] = __dmul_rn(unwrap_f(ldf<SMEM>(p + 3 * (j + u) + k), ref, L, half, hsafe), sw[j + u]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) c = __dadd_rn(c, t[u]);
+    }
+    for (; j < napm; ++j) c = __dadd_rn(c, __dmul_rn(unwrap_f(ldf<SMEM>(p + 3 * j + k), ref, L, half, hsafe), sw[j]));
+    return div_const(c, wsum);
+}
+
 // ---- K1 (direct loads; used when the index group is not one contiguous run of atoms) -----------------------------
 // cen: [frame][k][i] doubles (= itp::matd column-major per frame); fix: [frame][i] int4 {x,y,z fixed, i}
 __global__ void __launch_bounds__(256) k1_centers(const float* __restrict__ x, size_t frame_stride, int nframes,

@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
                 double           ck = 0.0;
                 if (ok)
                 {
-                    ck = center_component<true>(tiles + sd.poff + (unsigned)il * (unsigned)napm * 3u, k, napm, sw, a.wsum, g.L[k], g.half[k], g.hsafe[k]);
+                    ck = center_component_pipelined<true>(tiles + sd.poff + (unsigned)il * (unsigned)napm * 3u, k, napm, sw, a.wsum, g.L[k], g.half[k], g.hsafe[k]);
                     a.cen[(size_t)f * 3 * a.nmol + (size_t)k * a.nmol + im] = ck;
                 }
                 if (a.fix)
