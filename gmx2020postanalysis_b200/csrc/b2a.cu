@@ -852,8 +852,11 @@ constexpr int kCellIPT = 4;   // i-molecules per thread in cell mode (one cell p
 
 // Cell grid for r_max << L: cells per dimension 2^bits, reach per dimension from the cut-off plus the fixed-point slop.
 // Returns false when cells would not cull enough to beat the brute-force (possibly symmetric) evaluation.
+// `columns`: the caller cuts its i-tiles from whole (cx, cy) columns of cells (k3_rdf MODE 2) instead of giving every cell a
+// tile of its own (k5_coord): tiles are always full, so cells may be much finer than a tile, and a tile that spans several
+// cells along z searches the union of their z ranges.
 static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_possible, int* bits, int reach[3], int ti = kCellIPT * 128,
-                         double* cost_out = nullptr)
+                         double* cost_out = nullptr, bool columns = false)
 {
     int want = a.cells;
     if (const char* e = getenv("B2A_RDF_CELLS")) want = atoi(e);
@@ -866,7 +869,7 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
     {
         const int    nc = 1 << b;
         const double m  = nmin / ((double)nc * nc * nc);        // mean molecules per cell
-        if (m < (ti >= 512 ? 48.0 : 12.0)) break;
+        if (m < (columns ? 3.0 : (ti >= 512 ? 48.0 : 12.0))) break;
         if ((unsigned long long)p.nslab << (3 * b) > (4ull << 20)) break;
         int  r[3];
         bool ok = false;
@@ -884,10 +887,28 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
             if (2 * rk + 1 < nc) ok = true;
         }
         if (!ok) continue;
-        double frac = 1.0;
-        for (int k = 0; k < 3; ++k) frac *= (double)std::min(2 * r[k] + 1, nc) / nc;
-        const double util = m / (std::ceil(m / TI) * TI);       // lane utilisation of a one-cell tile
-        const double cost = frac / std::min(1.0, util) * 1.15;  // 15 %: IPT 4 instead of 8, per-range tile edges
+        double frac = 1.0, util, cost;
+        if (!columns)
+        {
+            for (int k = 0; k < 3; ++k) frac *= (double)std::min(2 * r[k] + 1, nc) / nc;
+            util = m / (std::ceil(m / TI) * TI);       // lane utilisation of a one-cell tile
+            cost = frac / std::min(1.0, util) * 1.15;  // 15 %: IPT 4 instead of 8, per-range tile edges
+        }
+        else
+        {
+            // a tile of TI molecules spans TI / m cells of its column (+1 for the alignment) and searches the union of their z
+            // ranges; every neighbour column costs a fixed ~64 j of tile edges, barriers and queue drains on top
+            const double p0    = (double)p.n0 / ((double)nc * nc * nc);
+            const double zc    = std::min((double)nc, 2.0 * r[2] + 1.0 + (double)TI / std::max(p0, 1e-9));
+            const double col   = p0 * nc;                                  // molecules per i column
+            util               = col / (std::ceil(col / TI) * TI);
+            const double jrun  = zc * (double)p.n1 / ((double)nc * nc * nc);   // j molecules per neighbour column
+            frac               = (double)std::min(2 * r[0] + 1, nc) * std::min(2 * r[1] + 1, nc) * zc / ((double)nc * nc * nc);
+            cost               = frac / std::min(1.0, util) * (1.0 + 64.0 / std::max(jrun, 1.0)) * 1.1;
+            // one block per tile: a small i side leaves most of the machine idle, where the all-pairs kernel would split j
+            const double blocks = std::ceil(col / TI) * (double)nc * nc * c->nframes;
+            cost /= std::min(1.0, blocks / (4.0 * c->sm_count));
+        }
         if (cost < bestc) { bestc = cost; bestb = b; bestr[0] = r[0]; bestr[1] = r[1]; bestr[2] = r[2]; }
     }
     if (bestb < 0) return false;
@@ -967,7 +988,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     const int nslab = p.nslab;
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, c->stream));
     int  bits = 0, reach[3] = { 0, 0, 0 };
-    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach);
+    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, kCellIPT * 128, nullptr, true);
     CellDev cd{};
     {
         Timed tm(c, 1);
@@ -1011,10 +1032,10 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     {
         RdfDev pc = p;
         pc.sym_enabled = 0;
-        // crowded i-cells (i side much denser than the cell grid was sized for) are split over gridDim.y
-        const double per_cell = (double)p.n0 / (double)(1u << (3 * bits));
-        const int    ny       = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_cell / (kCellIPT * 128))));
-        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA, ny, c->nframes), cubic);
+        // one block row per column of i-cells; its tiles are spread over gridDim.y (a block loops if a column is more crowded)
+        const double per_col = (double)p.n0 / (double)(1u << (2 * bits));
+        const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCellIPT * 128))));
+        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, ny, c->nframes), cubic);
     }
     constexpr int TI = 8 * 128;   // TI molecules of one slab per block
     {

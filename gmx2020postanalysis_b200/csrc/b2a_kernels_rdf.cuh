@@ -343,7 +343,8 @@ struct CellDev   // cell mode parameters (by value)
 // MODE 0 (full) : grid x = i-tile (over slabs), y = j-split, z = frame
 // MODE 1 (sym)  : grid x = work item (i-tile, j-chunk beyond the tile | diagonal), z = frame; frames that are not
 //                 eligible (not all molecules in one slab) are skipped here and done by the full kernel, and vice versa
-// MODE 2 (cell) : grid x = (slab, cell) key of the i side, z = frame; j runs over the neighbouring cells only
+// MODE 2 (cell) : grid x = (slab, cx, cy) column of i-cells, y = tile of the column, z = frame; j runs over the neighbouring
+//                 columns, restricted to the cells within reach of the tile's own z span
 template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, int MODE>
 __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
                                                   const double* __restrict__ cenA, const double* __restrict__ cenB,
@@ -363,7 +364,7 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
 
     const int f = blockIdx.z;
     int       slab = -1, tstart = 0, tcount = 0, j0 = 0, j1 = 0, weight = 1;
-    int       cell_a0 = 0, cell_a1 = 0, ccx = 0, ccy = 0, ccz = 0;
+    int       cell_a0 = 0, cell_a1 = 0, ccx = 0, ccy = 0;
     if (MODE != 2)
     {
         // is this frame eligible for symmetric evaluation?  (every molecule passed the filter into ONE slab)
@@ -410,18 +411,18 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
     }
     else
     {
-        const unsigned  key = blockIdx.x;
+        // one block per COLUMN of i-cells (fixed slab, cx, cy): the sorted array holds a column's molecules contiguously, in
+        // order of cz, so full tiles of TI molecules are cut from it regardless of how few molecules one cell holds
+        const unsigned  col = blockIdx.x;
         const unsigned* sa  = cd.startA + (size_t)f * (cd.nkeysA + 1);
-        cell_a0 = (int)sa[key];
-        cell_a1 = (int)sa[key + 1];
-        if (cell_a1 <= cell_a0) return;     // empty (slab, cell): block-uniform
+        cell_a0 = (int)sa[col << cd.bits];
+        cell_a1 = (int)sa[(col << cd.bits) + (1u << cd.bits)];
         const unsigned mask = (1u << cd.bits) - 1u;
-        slab = (int)(key >> (3 * cd.bits));
-        ccz  = (int)(key & mask);
-        ccy  = (int)((key >> cd.bits) & mask);
-        ccx  = (int)((key >> (2 * cd.bits)) & mask);
-        tstart = cell_a0 + (int)blockIdx.y * TI;   // sub-tiles of a crowded cell are spread over gridDim.y blocks
-        if (tstart >= cell_a1) return;
+        slab = (int)(col >> (2 * cd.bits));
+        ccy  = (int)(col & mask);
+        ccx  = (int)((col >> cd.bits) & mask);
+        tstart = cell_a0 + (int)blockIdx.y * TI;   // the tiles of a column are spread over gridDim.y blocks
+        if (tstart >= cell_a1) return;             // empty column / no tile left: block-uniform
         tcount = min(TI, cell_a1 - tstart);
     }
 
@@ -583,21 +584,25 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
         const unsigned* sb   = cd.startB + (size_t)f * (cd.nkeysB + 1);
         // distinct neighbour columns: if the reach covers the whole axis, visit every cell of that axis once
         const int nx = min(2 * cd.rx + 1, nc), ny = min(2 * cd.ry + 1, nc);
+        const unsigned  zsh  = 32u - (unsigned)cd.bits;
         for (; tstart < cell_a1; tstart += TI * (int)gridDim.y)
         {
             tcount = min(TI, cell_a1 - tstart);
-            __syncthreads();   // previous sub-tile's drain may still read blk.A / blk.tcount
+            __syncthreads();   // previous tile's drain may still read blk.A / blk.tcount
             if (threadIdx.x == 0) { blk.A = sortedA + (size_t)f * p.n0 + tstart; blk.tcount = tcount; }
             load_tile();
             nsel += tcount;
+            // cells the tile spans along z (cell = top bits of the fixed-point coordinate; the column is sorted by it)
+            const int4* At  = sortedA + (size_t)f * p.n0 + tstart;
+            const int   cza = (int)((unsigned)At[0].z >> zsh), czb = (int)((unsigned)At[tcount - 1].z >> zsh);
+            const int   z0 = cza - cd.rz, z1 = czb + cd.rz;           // inclusive, may leave [0, nc)
             for (int ix = 0; ix < nx; ++ix)
                 for (int iy = 0; iy < ny; ++iy)
                 {
                     const int      cx  = (ccx - (nx >> 1) + ix + nc) & (nc - 1);
                     const int      cy  = (ccy - (ny >> 1) + iy + nc) & (nc - 1);
                     const unsigned col = ((unsigned)cx << cd.bits | (unsigned)cy) << cd.bits;
-                    if (2 * cd.rz + 1 >= nc) { process_range((int)sb[col], (int)sb[col + nc]); continue; }
-                    const int z0 = ccz - cd.rz, z1 = ccz + cd.rz;     // inclusive, may leave [0, nc)
+                    if (z1 - z0 + 1 >= nc) { process_range((int)sb[col], (int)sb[col + nc]); continue; }
                     if (z0 < 0)
                     {
                         process_range((int)sb[col + z0 + nc], (int)sb[col + nc]);
