@@ -908,6 +908,7 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
             // one block per tile: a small i side leaves most of the machine idle, where the all-pairs kernel would split j
             const double blocks = std::ceil(col / TI) * (double)nc * nc * c->nframes;
             cost /= std::min(1.0, blocks / (4.0 * c->sm_count));
+            if (sym_possible) cost *= 0.5;   // k3_rdf MODE 2 evaluates eligible frames symmetrically as well
         }
         if (cost < bestc) { bestc = cost; bestb = b; bestr[0] = r[0]; bestr[1] = r[1]; bestr[2] = r[2]; }
     }
@@ -1031,11 +1032,11 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     if (cells)
     {
         RdfDev pc = p;
-        pc.sym_enabled = 0;
         // one block row per column of i-cells; its tiles are spread over gridDim.y (a block loops if a column is more crowded)
         const double per_col = (double)p.n0 / (double)(1u << (2 * bits));
         const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCellIPT * 128))));
-        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, ny, c->nframes), cubic);
+        // symmetric evaluation doubles the block rows: even = beyond-the-tile part of the j runs, odd = the tile against itself
+        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes), cubic);
     }
     constexpr int TI = 8 * 128;   // TI molecules of one slab per block
     {

@@ -364,7 +364,8 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
 
     const int f = blockIdx.z;
     int       slab = -1, tstart = 0, tcount = 0, j0 = 0, j1 = 0, weight = 1;
-    int       cell_a0 = 0, cell_a1 = 0, ccx = 0, ccy = 0;
+    int       cell_a0 = 0, cell_a1 = 0, ccx = 0, ccy = 0, crole = 0, cny = 1;
+    bool      csym = false;   // cell mode: this frame is evaluated symmetrically
     if (MODE != 2)
     {
         // is this frame eligible for symmetric evaluation?  (every molecule passed the filter into ONE slab)
@@ -421,13 +422,31 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
         slab = (int)(col >> (2 * cd.bits));
         ccy  = (int)(col & mask);
         ccx  = (int)((col >> cd.bits) & mask);
-        tstart = cell_a0 + (int)blockIdx.y * TI;   // the tiles of a column are spread over gridDim.y blocks
+        // Symmetric evaluation in cell mode (same molecules on both sides, every molecule of the frame in ONE slab): the j side
+        // is the i side's own sorted array, and a pair of sorted positions t1 < t2 is evaluated once, by the tile that holds
+        // t1, with weight 2 (the neighbourhood relation of cells is symmetric, so t1 lies in the j runs of t2's tile exactly
+        // when t2 lies in the j runs of t1's).  Block rows alternate: even = the part of every j run BEYOND the tile, weight 2;
+        // odd = the tile against itself in full (both orders of every pair, self pairs rejected by the exact path), weight 1.
+        if (p.sym_enabled)
+        {
+            csym = slab_cnt[(size_t)f * p.nslab + slab] == (unsigned)p.n0;
+            crole = (int)(blockIdx.y & 1u);
+            if (crole == 1 && !csym) return;       // nothing to do for a diagonal block of an ineligible frame
+            cny = (int)(gridDim.y >> 1);
+            tstart = cell_a0 + (int)(blockIdx.y >> 1) * TI;
+            if (csym) weight = crole == 0 ? 2 : 1;
+        }
+        else
+        {
+            cny = (int)gridDim.y;
+            tstart = cell_a0 + (int)blockIdx.y * TI;   // the tiles of a column are spread over gridDim.y blocks
+        }
         if (tstart >= cell_a1) return;             // empty column / no tile left: block-uniform
         tcount = min(TI, cell_a1 - tstart);
     }
 
     const RdfFrame fr = frames[f];
-    const int4*    B  = MODE == 1 ? sortedA + (size_t)f * p.n0 : (MODE == 2 ? cd.sortedB + (size_t)f * p.n1 : fixB + (size_t)f * p.n1);
+    const int4*    B  = (MODE == 1 || (MODE == 2 && csym)) ? sortedA + (size_t)f * p.n0 : (MODE == 2 ? cd.sortedB + (size_t)f * p.n1 : fixB + (size_t)f * p.n1);
     for (unsigned k = threadIdx.x; k < p.kstride; k += THREADS) hist[(int)k - 1] = 0;
     if (threadIdx.x == 0)
     {
@@ -581,17 +600,20 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
     else
     {
         const int       nc   = 1 << cd.bits;
-        const unsigned* sb   = cd.startB + (size_t)f * (cd.nkeysB + 1);
+        // j runs: offsets of the j side's sort -- in symmetric frames the i side's own, restricted to its (single) slab
+        const unsigned* sb   = csym ? cd.startA + (size_t)f * (cd.nkeysA + 1) + ((size_t)slab << (3 * cd.bits)) : cd.startB + (size_t)f * (cd.nkeysB + 1);
         // distinct neighbour columns: if the reach covers the whole axis, visit every cell of that axis once
         const int nx = min(2 * cd.rx + 1, nc), ny = min(2 * cd.ry + 1, nc);
         const unsigned  zsh  = 32u - (unsigned)cd.bits;
-        for (; tstart < cell_a1; tstart += TI * (int)gridDim.y)
+        for (; tstart < cell_a1; tstart += TI * cny)
         {
             tcount = min(TI, cell_a1 - tstart);
             __syncthreads();   // previous tile's drain may still read blk.A / blk.tcount
             if (threadIdx.x == 0) { blk.A = sortedA + (size_t)f * p.n0 + tstart; blk.tcount = tcount; }
             load_tile();
+            if (csym && crole == 1) { process_range(tstart, tstart + tcount); continue; }   // the tile against itself
             nsel += tcount;
+            const int jmin = csym ? tstart + tcount : 0;   // symmetric: only sorted positions beyond the tile
             // cells the tile spans along z (cell = top bits of the fixed-point coordinate; the column is sorted by it)
             const int4* At  = sortedA + (size_t)f * p.n0 + tstart;
             const int   cza = (int)((unsigned)At[0].z >> zsh), czb = (int)((unsigned)At[tcount - 1].z >> zsh);
@@ -602,18 +624,18 @@ __global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sorte
                     const int      cx  = (ccx - (nx >> 1) + ix + nc) & (nc - 1);
                     const int      cy  = (ccy - (ny >> 1) + iy + nc) & (nc - 1);
                     const unsigned col = ((unsigned)cx << cd.bits | (unsigned)cy) << cd.bits;
-                    if (z1 - z0 + 1 >= nc) { process_range((int)sb[col], (int)sb[col + nc]); continue; }
+                    if (z1 - z0 + 1 >= nc) { process_range(max(jmin, (int)sb[col]), (int)sb[col + nc]); continue; }
                     if (z0 < 0)
                     {
-                        process_range((int)sb[col + z0 + nc], (int)sb[col + nc]);
-                        process_range((int)sb[col], (int)sb[col + z1 + 1]);
+                        process_range(max(jmin, (int)sb[col + z0 + nc]), (int)sb[col + nc]);
+                        process_range(max(jmin, (int)sb[col]), (int)sb[col + z1 + 1]);
                     }
                     else if (z1 >= nc)
                     {
-                        process_range((int)sb[col + z0], (int)sb[col + nc]);
-                        process_range((int)sb[col], (int)sb[col + z1 - nc + 1]);
+                        process_range(max(jmin, (int)sb[col + z0]), (int)sb[col + nc]);
+                        process_range(max(jmin, (int)sb[col]), (int)sb[col + z1 - nc + 1]);
                     }
-                    else process_range((int)sb[col + z0], (int)sb[col + z1 + 1]);
+                    else process_range(max(jmin, (int)sb[col + z0]), (int)sb[col + z1 + 1]);
                 }
         }
     }

@@ -565,6 +565,12 @@ def _rdf_gpu_cells(ctx, system, g0, g1, K, spec, Rm, Rbin, cells, paranoid=0, sy
     dict(sys=("il", 4000, 10.9), g=("ANI", "ANI"), K=1, Rm=1.4, com=1),
     dict(sys=("water", 3500, 4.7), g=("OW", "OW"), K=1, Rm=0.5, paranoid=1),
     dict(sys=("il", 3500, 9.0), g=("CAT", "ANI"), K=2, Rm=0.8, box=(9.0, 7.0, 11.0)),
+    # symmetric evaluation inside cell mode (same group on both sides, one slab): beyond-the-tile runs x 2 + tile diagonals
+    dict(sys=("water", 6000, 5.65), g=("OW", "OW"), K=2, Rm=0.7, symmetric=1),
+    dict(sys=("il", 4000, 10.9), g=("ANI", "ANI"), K=2, Rm=1.1, com=1, symmetric=1, box=(10.9, 9.0, 12.5)),
+    dict(sys=("water", 3500, 4.7), g=("OW", "OW"), K=1, Rm=0.5, paranoid=1, symmetric=1),
+    # same, but the region filter spreads the molecules over slabs: frames are not eligible and fall back to the full evaluation
+    dict(sys=("water", 5000, 5.3), g=("OW", "OW"), K=2, Rm=0.6, symmetric=1, nbin=4, low=0.4, up=4.9, dim=2),
 ])
 def test_rdf_cell_mode_bit_exact(gpu_ctx_factory, case):
     kind, n, L = case["sys"]
@@ -576,7 +582,8 @@ def test_rdf_cell_mode_bit_exact(gpu_ctx_factory, case):
     K = case["K"]
     exp, est, Rm, Rbin = refprog.oracle_rdf_region(system, K, case["g"][0], case["g"][1], return_counts=True, **spec)
     ctx = gpu_ctx_factory(system.natoms, K)
-    got, st = _rdf_gpu_cells(ctx, system, case["g"][0], case["g"][1], K, spec, Rm, Rbin, cells=1, paranoid=case.get("paranoid", 0))
+    got, st = _rdf_gpu_cells(ctx, system, case["g"][0], case["g"][1], K, spec, Rm, Rbin, cells=1, paranoid=case.get("paranoid", 0),
+                             symmetric=case.get("symmetric", 0))
     assert np.array_equal(got, exp)
     assert int(st[lib.STAT_DROPPED]) == int(est[1]) and int(st[lib.STAT_SELECTED]) == int(est[2])
     n0 = len(refprog.group_info(system, case["g"][0])["index"]) // refprog.group_info(system, case["g"][0])["napm"]
@@ -596,9 +603,14 @@ def test_rdf_cells_equal_brute_force_large(gpu_ctx_factory):
         ctx = gpu_ctx_factory(system.natoms, 1)
         res[cells] = _rdf_gpu_cells(ctx, system, "OW", "OW", 1, spec, Rm, Rbin, cells=cells, symmetric=1 - cells)
         ctx.close()
-    assert np.array_equal(res[0][0], res[1][0]) and res[0][0].sum() > 0
+    ctx = gpu_ctx_factory(system.natoms, 1)
+    res[2] = _rdf_gpu_cells(ctx, system, "OW", "OW", 1, spec, Rm, Rbin, cells=1, symmetric=1)      # cells AND symmetric
+    ctx.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][0], res[2][0]) and res[0][0].sum() > 0
     assert int(res[1][1][lib.STAT_PAIRS]) * 4 < int(res[0][1][lib.STAT_PAIRS])     # cells evaluate far fewer pairs
-    assert int(res[0][1][lib.STAT_DROPPED]) == int(res[1][1][lib.STAT_DROPPED])
+    assert int(res[2][1][lib.STAT_PAIRS]) * 1.8 < int(res[1][1][lib.STAT_PAIRS])   # ... and half of those when symmetric
+    for st in (lib.STAT_DROPPED, lib.STAT_SELECTED):
+        assert int(res[0][1][st]) == int(res[1][1][st]) == int(res[2][1][st])
 
 
 # ---- GmxHandleFull: heterogeneous molecule sizes -----------------------------------------------------
