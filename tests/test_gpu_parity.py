@@ -546,6 +546,79 @@ def test_orient_three_site_packed_fast_path(gpu_ctx_factory, var):
     assert np.array_equal(c0[:nA * nbin1].reshape(nA, nbin1), o) and np.array_equal(c0[nA * nbin1:], ncm)
 
 
+# ---- boxes that change from frame to frame (NPT), short batches, degenerate selections -------------------------------
+def test_box_changes_per_frame_and_degenerate_selections(gpu_ctx_factory):
+    """Every frame of a batch carries its own box (ipp:72-74 re-reads Lbox per frame): RDF (all-pairs, symmetric-ineligible
+    and cell mode), density and orientation against the oracle frame by frame; a batch shorter than the context's capacity;
+    region filters that select nothing; one-molecule groups."""
+    system = synth.ionic_liquid(400, 5.0, seed=4711)
+    K = 3
+    scale = np.array([[1.0, 1.0, 1.0], [1.03, 0.98, 1.01], [0.96, 1.02, 0.99]], np.float32)
+    x = system.frames(0, K) * scale[:, None, :]
+    box9 = np.zeros((K, 9), np.float32)
+    for f in range(K):
+        box9[f, 0::4] = np.float32(5.0) * scale[f]
+    ctx = gpu_ctx_factory(system.natoms, 8)               # capacity 8, batches of 3 and 1
+    gc, ga = _groups(ctx, system, ["CAT", "ANI"])
+    Rm = refprog.f32(1.1)
+    Rbin = port.rdf_rbin(Rm)
+    f32 = refprog.f32
+    spec = dict(nbin=3, low=0.4, up=4.7, dim=1, dim2=0, low2=0.2, up2=4.9)
+    exp = {c: np.zeros((Rbin, 3), np.uint64) for c in (0, 1)}
+    dexp = np.zeros(40, np.uint64)
+    for f in range(K):
+        Lbox = port.lbox_from_box9(box9[f])
+        pc = port.load_position_center(x[f], gc["index"], gc["napm"], gc["w"][0], Lbox)
+        pa = port.load_position_center(x[f], ga["index"], ga["napm"], ga["w"][0], Lbox)
+        for c in (0, 1):
+            port.rdf_accum(pc, pa, Lbox, 3, f32(spec["low"]), f32(spec["up"]), spec["dim"], spec["dim2"], f32(spec["low2"]), f32(spec["up2"]),
+                           Rm, Rbin, exp[c])
+        port.density_accum(pa, 2, f32(0.3), f32(4.5), float(np.float32(np.float32(4.2) / np.float32(40))), 40, dexp)
+        # loaders see the frame's own box
+        assert np.array_equal(ctx_centers_after_submit(ctx, x, box9, f, 0), pc)
+    for cells in (0, 1):
+        acc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, Rm=Rm, Rbin=Rbin, **spec)
+        ctx.rdf_tune(acc, 1, 0)
+        ctx.rdf_cells(acc, cells)
+        ctx.submit(x, box9)
+        ctx.accumulate(acc)
+        ctx.submit(x[:1], box9[:1])                       # a second, shorter batch into the same accumulator
+        ctx.accumulate(acc)
+        got, st = ctx.read(acc, 3 * Rbin)
+        Lbox = port.lbox_from_box9(box9[0])
+        extra = np.zeros((Rbin, 3), np.uint64)
+        port.rdf_accum(port.load_position_center(x[0], gc["index"], gc["napm"], gc["w"][0], Lbox),
+                       port.load_position_center(x[0], ga["index"], ga["napm"], ga["w"][0], Lbox), Lbox, 3, f32(spec["low"]), f32(spec["up"]),
+                       spec["dim"], spec["dim2"], f32(spec["low2"]), f32(spec["up2"]), Rm, Rbin, extra)
+        assert np.array_equal(got.reshape(Rbin, 3), exp[cells] + extra) and int(st[lib.STAT_FRAMES]) == K + 1
+    den = ctx.density_create(grp=1, com=0, dim=2, low=0.3, up=4.5, dbin=float(np.float32(np.float32(4.2) / np.float32(40))), nbin=40,
+                             upper_inclusive=0, dim2=-1, low2=0.0, up2=0.0)
+    ctx.submit(x, box9)
+    ctx.accumulate(den)
+    assert np.array_equal(ctx.read(den, 40)[0], dexp)
+    # filters that select nothing: zero histograms, zero selected, no error
+    empty = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, Rm=Rm, Rbin=Rbin, nbin=2, low=50.0, up=60.0, dim=0, dim2=2, low2=-100.0, up2=100.0)
+    ctx.accumulate(empty)
+    got, st = ctx.read(empty, 2 * Rbin)
+    assert got.sum() == 0 and int(st[lib.STAT_SELECTED]) == 0
+    # one-molecule groups: a single pair, wrapped across the box
+    ctx1 = gpu_ctx_factory(2, 1)
+    for g in (0, 1):
+        ctx1.set_group(g, np.array([g], np.int32), 1, np.ones(1), np.ones(1))
+    one = ctx1.rdf_create(grp0=0, grp1=1, com0=1, com1=1, Rm=f32(1.0), Rbin=500, nbin=1, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0)
+    ctx1.submit(np.array([[[0.05, 1.0, 1.0], [3.95, 1.0, 1.0]]], np.float32), np.array([4, 0, 0, 0, 4, 0, 0, 0, 4], np.float32))
+    ctx1.accumulate(one)
+    got, _ = ctx1.read(one, 500)
+    e1, _ = port.rdf_accum(np.array([[0.05, 1.0, 1.0]], np.float32).astype(np.float64), np.array([[3.95, 1.0, 1.0]], np.float32).astype(np.float64),
+                           np.array([4.0, 4.0, 4.0]), 1, -100.0, 100.0, 0, 2, -100.0, 100.0, f32(1.0), 500)
+    assert got.sum() == 1 and np.array_equal(got.reshape(500, 1), e1)
+
+
+def ctx_centers_after_submit(ctx, x, box9, f, grp):
+    ctx.submit(x, box9)
+    return ctx.centers(grp, 0, f)
+
+
 # ---- cell-binned RDF (SURVEY 8f-1): identical counts to the all-pairs evaluation ---------------------------------
 def _rdf_gpu_cells(ctx, system, g0, g1, K, spec, Rm, Rbin, cells, paranoid=0, symmetric=0):
     _groups(ctx, system, [g0, g1])
