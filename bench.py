@@ -29,13 +29,40 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-NMOL, LBOX, SEED = 72000, 12.913, 20200102
 ISSUE_SLOTS_PER_PAIR = 19                           # algorithmic work per evaluated pair
 # dram__bytes_read.sum + dram__bytes_write.sum of one k3_rdf launch, per frame of the launch, from the ncu --set full
 # capture summarised in profiles/r01_k3_ncu.md (the kernel re-reads its 1.15 MB/frame of fixed-point coordinates from L2,
 # not from HBM; nothing is written back but the 26 KB histogram)
 K3_DRAM_BYTES_PER_FRAME = 4.64e6
-WORKLOAD = "O-O RDF, 216k-atom SPC/E water box (72k O, L=12.913 nm, Rm=L/2, Rbin=3228, nbin=5), calc_rdf_region defaults"
+
+
+class Workload:
+    """The RDF job a bench line is quoted on.  `c2` is the headline (BASELINE.json configs[1], what the driver runs); `c3`
+    (configs[2], the frame-sharded multi-GPU case) is selectable for the scaling runs recorded in profiles/."""
+
+    def __init__(self, name):
+        from gmx2020postanalysis_b200 import synth
+        self.name = name
+        if name == "c2":
+            self.L, self.seed = 12.913, 20200102                   # SURVEY.md 8(d), config C2
+            self.system = synth.water_box(72000, self.L, seed=self.seed, split_atoms=True)
+            self.g0 = self.g1 = "OW"
+            self.text = "O-O RDF, 216k-atom SPC/E water box (72k O, L=12.913 nm, Rm=L/2, Rbin=3228, nbin=5), calc_rdf_region defaults"
+            self.dram_per_frame = K3_DRAM_BYTES_PER_FRAME
+        elif name == "c3":
+            self.L, self.seed = 22.1, 20200103                     # SURVEY.md 8(d), config C3
+            self.system = synth.ionic_liquid(31250, self.L, seed=self.seed)
+            self.g0, self.g1 = "CAT", "ANI"
+            self.text = ("cation-anion molecular-COM RDF, 1M-atom ionic liquid (31 250 x (25-site cation + 7-site anion), L=22.1 nm, "
+                         "Rm=L/2, Rbin=5525, nbin=5), calc_rdf_region defaults")
+            self.dram_per_frame = None
+        else:
+            raise SystemExit(f"unknown --config {name}")
+        import refprog
+        self.gi0, self.gi1 = refprog.group_info(self.system, self.g0), refprog.group_info(self.system, self.g1)
+        self.n0 = len(self.gi0["index"]) // self.gi0["napm"]
+        self.n1 = len(self.gi1["index"]) // self.gi1["napm"]
+        self.same = self.g0 == self.g1
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -91,20 +118,21 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_sample(system, n_i, tmpdir, x0):
+def cpu_reference_sample(wl, n_i, tmpdir, x0):
     """Runs the reference's own calc_rdf_region (oracle/_ref, 1 thread in the pair loop -- the reference has no
-    threading there) on grp0 = first n_i oxygens x grp1 = all oxygens of one frame.  Returns (pairs/s, kind, secs)."""
+    threading there) on grp0 = the first n_i molecules of group 0 x grp1 = all of group 1, one frame.  Returns
+    (pairs/s, kind, secs)."""
     import refprog
     from gmx2020postanalysis_b200 import trajio
-    n1 = system.species[0].nmol
-    ow = system.groups["OW"]
+    system, n1 = wl.system, wl.n1
+    i0, i1 = wl.gi0["index"], wl.gi1["index"]
     exe = os.path.join(refprog.REFDIR, "calc_rdf_region")
     if refprog.have_ref("calc_rdf_region"):
-        prefix = os.path.join(tmpdir, "c2")
+        prefix = os.path.join(tmpdir, wl.name)
         if not os.path.exists(prefix + ".b2t"):
             trajio.write_trajectory(prefix + ".b2t", x0[None], system.box9())
             trajio.write_topology(prefix + ".b2p", system)
-        trajio.write_index(prefix + ".ndx", {"OW_sub": ow[:n_i], "OW": ow})
+        trajio.write_index(prefix + ".ndx", {"G0_sub": i0[:n_i * wl.gi0["napm"]], "G1": i1})
         env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
                    OMP_NUM_THREADS="1")
         cmd = [exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", prefix + ".ndx", "-o", prefix + ".xvg"]
@@ -119,14 +147,15 @@ def cpu_reference_sample(system, n_i, tmpdir, x0):
     os.environ["OMP_NUM_THREADS"] = "1"
     Lbox = port.lbox_from_box9(system.box9())
     Rm = port.rdf_default_rm(Lbox)
-    o = x0[0::3].astype(np.float64)
+    p0 = port.load_position_center(x0, wl.gi0["index"][:n_i * wl.gi0["napm"]], wl.gi0["napm"], wl.gi0["w"][0], Lbox)
+    p1 = port.load_position_center(x0, wl.gi1["index"], wl.gi1["napm"], wl.gi1["w"][0], Lbox)
     t = time.perf_counter()
-    port.rdf_accum(o[:n_i], o, Lbox, 5, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, port.rdf_rbin(Rm))
+    port.rdf_accum(p0, p1, Lbox, 5, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, port.rdf_rbin(Rm))
     dt = time.perf_counter() - t
     return n_i * n1 / dt, "port", dt
 
 
-def cpu_reference_all_cores(system, n_i, procs, tmpdir, x0):
+def cpu_reference_all_cores(wl, n_i, procs, tmpdir, x0):
     """The reference has no threading in the pair loop; the most its code can use of a host is one PROCESS per core, each on
     its own share of the i-molecules (what a user would do by hand with index groups).  Returns aggregate pairs/s, or None
     where the reference binaries did not travel."""
@@ -134,10 +163,11 @@ def cpu_reference_all_cores(system, n_i, procs, tmpdir, x0):
     from gmx2020postanalysis_b200 import trajio
     if not refprog.have_ref("calc_rdf_region"):
         return None
-    n1 = system.species[0].nmol
-    ow = system.groups["OW"]
+    system, n1 = wl.system, wl.n1
+    i0, i1, na = wl.gi0["index"], wl.gi1["index"], wl.gi0["napm"]
+    n_i = min(n_i, wl.n0 // procs)
     exe = os.path.join(refprog.REFDIR, "calc_rdf_region")
-    prefix = os.path.join(tmpdir, "c2")
+    prefix = os.path.join(tmpdir, wl.name)
     if not os.path.exists(prefix + ".b2t"):
         trajio.write_trajectory(prefix + ".b2t", x0[None], system.box9())
         trajio.write_topology(prefix + ".b2p", system)
@@ -145,7 +175,7 @@ def cpu_reference_all_cores(system, n_i, procs, tmpdir, x0):
     cmds = []
     for q in range(procs):
         ndx = os.path.join(tmpdir, f"p{q}.ndx")
-        trajio.write_index(ndx, {"OW_sub": ow[q * n_i:(q + 1) * n_i], "OW": ow})
+        trajio.write_index(ndx, {"G0_sub": i0[q * n_i * na:(q + 1) * n_i * na], "G1": i1})
         cmds.append([exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", ndx, "-o", os.path.join(tmpdir, f"p{q}.xvg")])
     t = time.perf_counter()
     ps = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, cwd=tmpdir, text=True)
@@ -164,18 +194,18 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from gmx2020postanalysis_b200 import synth
-    system = synth.water_box(NMOL, LBOX, seed=SEED, split_atoms=True)
+    wl = Workload(args.config)
+    system = wl.system
     x0 = system.frame(0)
-    n_i = args.ref_sample
+    n_i = min(args.ref_sample, wl.n0)
     rates, kind = [], "reference"
     with tempfile.TemporaryDirectory() as td:
         for s in range(args.warmup + args.steps):
-            rate, kind, dt = cpu_reference_sample(system, n_i, td, x0)
+            rate, kind, dt = cpu_reference_sample(wl, n_i, td, x0)
             if s >= args.warmup:
                 rates.append((rate, dt))
         procs = os.cpu_count() or 1
-        all_cores = cpu_reference_all_cores(system, n_i, procs, td, x0) if kind == "reference" else None
+        all_cores = cpu_reference_all_cores(wl, n_i, procs, td, x0) if kind == "reference" else None
     tot_pairs = sum(r * d for r, d in rates)
     tot_s = sum(d for _, d in rates)
     value = tot_pairs / tot_s
@@ -183,18 +213,18 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "rdf_pair_distances_per_s", "value": value, "unit": "pair-distances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(rates),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "frames_per_s": value / (NMOL * NMOL),
-        "config": {"workload": WORKLOAD, "sample": f"{n_i} of {NMOL} i-molecules x all {NMOL} j-molecules of frame 0 per step"},
+        "frames_per_s": value / (wl.n0 * wl.n1),
+        "config": {"workload": wl.text, "sample": f"{n_i} of {wl.n0} i-molecules x all {wl.n1} j-molecules of frame 0 per step"},
         "cpu_baseline": {"value": value, "unit": "pair-distances/s", "cores": 1, "kind": kind,
-                         "sample": f"{n_i} x {NMOL} ordered pairs per step, {len(rates)} steps, whole-process wall time "
-                                   "(includes reading the 2.6 MB frame)", "host_cpus": os.cpu_count()},
+                         "sample": f"{n_i} x {wl.n1} ordered pairs per step, {len(rates)} steps, whole-process wall time "
+                                   "(includes reading the frame)", "host_cpus": os.cpu_count()},
         "e2e": {"value": value, "unit": "pair-distances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     if all_cores:
         # not the reference's own mode of operation (its frame loop is single-threaded): reported beside `value`, never instead
         line["cpu_all_cores"] = {"value": all_cores, "unit": "pair-distances/s", "processes": procs,
-                                 "sample": f"{procs} concurrent reference processes, {n_i} x {NMOL} ordered pairs each, wall time of the slowest"}
+                                 "sample": f"{procs} concurrent reference processes, {min(n_i, wl.n0 // procs)} x {wl.n1} ordered pairs each, wall time of the slowest"}
     print(json.dumps(line))
     return 0
 
@@ -211,6 +241,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8000, help="i-molecules of the cpu_baseline leg (~15 s of one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--symmetric", type=int, default=1)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3"], help="c2 = headline (BASELINE configs[1]); c3 = configs[2]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -230,18 +261,19 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     F = args.frames_per_step
-    system = synth.water_box(NMOL, LBOX, seed=SEED, split_atoms=True)
+    wl = Workload(args.config)
+    system, LBOX = wl.system, wl.L
     natoms = system.natoms
     # rank-private, distinct frames in pinned host memory (frames shard contiguously across ranks)
     xh = torch.empty((F, natoms, 3), dtype=torch.float32).pin_memory()
     system.frames(rank * F, F, out=xh.numpy())
+    xh2 = torch.empty((F, natoms, 3), dtype=torch.float32).pin_memory()      # second host buffer of the end-to-end loop
+    xh2.copy_(xh)
     box = system.box9()
 
     ctx = lib.Context(natoms, F, device=local)
-    ow = system.groups["OW"]
-    m, q = system.species[0].mass[:1].astype(np.float64), system.species[0].charge[:1].astype(np.float64)
-    for g in (0, 1):
-        ctx.set_group(g, ow, 1, m, q)
+    for g, gi in enumerate((wl.gi0, wl.gi1)):
+        ctx.set_group(g, gi["index"], gi["napm"], gi["mass"], gi["charge"])
     Lbox = np.array([float(np.float32(LBOX))] * 3)
     Rm = float(np.float32(np.float32(LBOX) / np.float32(2)))        # calc_rdf_region.cpp:52-57
     Rbin = int(Rm / 0.002)                                          # :58
@@ -259,7 +291,7 @@ def main():
         torch.cuda.synchronize(local)
         ctx.sync()
 
-    pairs_step = float(F) * NMOL * NMOL          # reference-equivalent ordered pairs per rank per step
+    pairs_step = float(F) * wl.n0 * wl.n1        # reference-equivalent ordered pairs per rank per step
 
     # ---- phase 1: device-resident ------------------------------------------------------------------------
     ctx.submit(xh.numpy(), box)
@@ -302,10 +334,15 @@ def main():
     ctx.reset(acc)
     barrier()
     t0 = time.perf_counter()
+    # every step uploads its own frames from pinned memory and reads its own result back; the upload of step s+1 is queued
+    # (double-buffered, on the copy stream) before the host blocks on the result of step s, so it overlaps the kernels of s
+    ctx.submit(xh.numpy(), box)                  # H2D of step 0
     for s in range(args.steps):
-        ctx.submit(xh.numpy(), box)              # H2D of this step's frames from pinned memory
         ctx.accumulate(acc)
-        counts_e2e, stats_e2e = ctx.read(acc, ncounters)   # D2H of the step's result (u64 histogram + stats)
+        if s + 1 < args.steps:
+            ctx.submit(xh2.numpy(), box)         # H2D of step s+1 (second pinned buffer: ping-pong, as the drop-in batcher does)
+            xh, xh2 = xh2, xh
+        counts_e2e, stats_e2e = ctx.read(acc, ncounters)   # D2H of step s's result (u64 histogram + stats)
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = F * natoms * 12 + F * 36 + F * 72
@@ -340,19 +377,19 @@ def main():
             "metric": "rdf_pair_distances_per_s", "value": value, "unit": "pair-distances/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "frames_per_s": value / (NMOL * NMOL),
+            "frames_per_s": value / (wl.n0 * wl.n1),
             "evaluated_pairs_per_s": evaluated_all / (tot_ms_max * 1e-3),
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "parallelism": f"frame-sharded x{world}",
-                       "l2": "flushed between timed steps (256 MiB write)", "symmetric_i_lt_j": bool(args.symmetric),
+            "config": {"workload": wl.text, "frames_per_step_per_gpu": F, "parallelism": f"frame-sharded x{world}",
+                       "l2": "flushed between timed steps (256 MiB write)", "symmetric_i_lt_j": bool(args.symmetric) and wl.same,
                        "pairs": "value counts reference-equivalent ordered pairs (N0*N1 per frame); roofline counts only evaluated pairs"},
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
                        "samples": clocks.get("samples"), "power_w_max": clocks.get("power_w_max")},
             "e2e": {"value": e2e_value, "unit": "pair-distances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_s": e2e_value / (NMOL * NMOL), "ms_per_step": 1e3 * e2e_s_max / args.steps},
+                    "frames_per_s": e2e_value / (wl.n0 * wl.n1), "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": int(sum(n for k, (t, n) in timing.items() if k in ("k1_centers", "k3_rdf")) + 2 * prep_n + args.steps),
             "roofline": {"bound": "fp32_issue", "kernel": "k3_rdf", "achieved": achieved_inst / 1e12, "peak": peak_inst / 1e12,
                          "unit": "Tinst/s", "frac": achieved_inst / peak_inst if peak_inst else None,
-                         "traffic": K3_DRAM_BYTES_PER_FRAME * F, "traffic_unit": "bytes per k3_rdf launch (ncu, profiles/r01_k3_ncu.md)",
+                         "traffic": wl.dram_per_frame * F if wl.dram_per_frame else None, "traffic_unit": "bytes per k3_rdf launch (ncu, profiles/r01_k3_ncu.md)",
                          "how": f"evaluated pairs per launch x {ISSUE_SLOTS_PER_PAIR} issue slots (BASELINE.md section 4) / mean CUDA-event "
                                 "duration of the k3_rdf launches inside the timed region; peak = 148 SM x 128 lanes x SM clock "
                                 "sampled by nvidia-smi during the timed region",
@@ -365,11 +402,12 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             with tempfile.TemporaryDirectory() as td:
-                rate, kind, dt = cpu_reference_sample(system, args.cpu_sample, td, xh.numpy()[0])
+                n_cpu = min(args.cpu_sample, wl.n0)
+                rate, kind, dt = cpu_reference_sample(wl, n_cpu, td, xh.numpy()[0])
             line["cpu_baseline"] = {"value": rate, "unit": "pair-distances/s", "cores": 1, "kind": kind,
-                                    "sample": f"{args.cpu_sample} of {NMOL} i-molecules x all {NMOL} j-molecules of one frame "
+                                    "sample": f"{n_cpu} of {wl.n0} i-molecules x all {wl.n1} j-molecules of one frame "
                                               f"({dt:.1f} s, whole-process wall time)", "host_cpus": os.cpu_count(),
-                                    "frames_per_s": rate / (NMOL * NMOL)}
+                                    "frames_per_s": rate / (wl.n0 * wl.n1)}
         print(json.dumps(line))
     ctx.close()
     if world > 1:

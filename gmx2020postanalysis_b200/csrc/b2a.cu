@@ -148,9 +148,21 @@ struct b2a_ctx
     int          device = 0;
     cudaStream_t stream = nullptr;
     int          natoms = 0, maxK = 0;
+    // The frame batch is double-buffered: b2a_submit_batch copies into the buffer the kernels of the previous batch are NOT
+    // reading, on its own stream, so the H2D copy of batch k+1 overlaps the kernels of batch k.  d_x / d_geom / h_geom always
+    // point at the CURRENT batch (what every kernel launched after the submit reads).
     float*       d_x    = nullptr;
     FrameGeom*   d_geom = nullptr;
     FrameGeom*   h_geom = nullptr;   // pinned
+    float*       d_xbuf[2]    = { nullptr, nullptr };
+    FrameGeom*   d_geombuf[2] = { nullptr, nullptr };
+    FrameGeom*   h_geombuf[2] = { nullptr, nullptr };
+    cudaStream_t copy_stream  = nullptr;
+    cudaEvent_t  ev_copied[2] = { nullptr, nullptr };   // copy stream: the upload into buffer b has finished
+    cudaEvent_t  ev_free[2]   = { nullptr, nullptr };   // main stream: every kernel launched while b was current has finished
+    int          cur = 0;
+    cudaEvent_t  ev_field = nullptr;                    // main stream: the last velocity / force upload has finished
+    bool         field_pending = false;
     std::vector<float> h_box;        // [K][9]
     int          nframes = 0;
     uint64_t     serial  = 0;
@@ -220,9 +232,17 @@ extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
     c->maxK   = max_frames;
     CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&c->d_x, (size_t)natoms * 3 * sizeof(float) * max_frames + 64));   // +64: bulk copies are widened to 16-byte boundaries
-    CU(cudaMalloc(&c->d_geom, sizeof(FrameGeom) * max_frames));
-    CU(cudaMallocHost(&c->h_geom, sizeof(FrameGeom) * max_frames));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b)
+    {
+        CU(cudaMalloc(&c->d_xbuf[b], (size_t)natoms * 3 * sizeof(float) * max_frames + 64));   // +64: bulk copies are widened to 16-byte boundaries
+        CU(cudaMalloc(&c->d_geombuf[b], sizeof(FrameGeom) * max_frames));
+        CU(cudaMallocHost(&c->h_geombuf[b], sizeof(FrameGeom) * max_frames));
+        CU(cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming));
+    }
+    CU(cudaEventCreateWithFlags(&c->ev_field, cudaEventDisableTiming));
+    c->cur = 0; c->d_x = c->d_xbuf[0]; c->d_geom = c->d_geombuf[0]; c->h_geom = c->h_geombuf[0];
     c->h_box.assign((size_t)max_frames * 9, 0.f);
     *out = c.release();
     return B2A_OK;
@@ -253,9 +273,18 @@ extern "C" void b2a_destroy(b2a_ctx* c)
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->groups) free_group(kv.second);
     for (auto& a : c->accs) if (a) free_acc(*a);
-    cudaFree(c->d_x); cudaFree(c->d_geom); cudaFree(c->d_pos_scratch); cudaFree(c->d_work);
+    cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->d_pos_scratch); cudaFree(c->d_work);
     cudaFree(c->d_field[1]); cudaFree(c->d_field[2]); cudaFree(c->d_field_cen);
-    if (c->h_geom) cudaFreeHost(c->h_geom);
+    for (int b = 0; b < 2; ++b)
+    {
+        cudaFree(c->d_xbuf[b]); cudaFree(c->d_geombuf[b]);
+        if (c->h_geombuf[b]) cudaFreeHost(c->h_geombuf[b]);
+        if (c->ev_copied[b]) cudaEventDestroy(c->ev_copied[b]);
+        if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]);
+    }
+    if (c->ev_field) cudaEventDestroy(c->ev_field);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -411,15 +440,25 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
     if (!c || !x || !box9) return fail(B2A_ERR_ARG, "b2a_submit_batch: null argument");
     if (nframes <= 0 || nframes > c->maxK) return fail(B2A_ERR_ARG, "b2a_submit_batch: nframes %d outside 1..%d", nframes, c->maxK);
     CU(cudaSetDevice(c->device));
-    // h_geom is reused: make sure the previous upload has left the pinned buffer
-    CU(cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < nframes; ++f)
+        for (int k = 0; k < 3; ++k)
+            if (!(box9[(size_t)f * 9 + 4 * k] > 0.f)) return fail(B2A_ERR_ARG, "b2a_submit_batch: frame %d has non-positive box length", f);
+    // The previous upload must have left the caller's pinned buffer before the caller may refill it (callers alternate
+    // between two host buffers); this also bounds how far the host can run ahead of the device.
+    CU(cudaEventSynchronize(c->ev_copied[c->cur]));
+    if (c->field_pending) { CU(cudaEventSynchronize(c->ev_field)); c->field_pending = false; }
+    // Everything launched so far read the current buffer; from here on the other one becomes current.  Its last readers
+    // (two submits ago) are covered by ev_free, its last upload by ev_copied (which also frees its pinned geometry staging).
+    CU(cudaEventRecord(c->ev_free[c->cur], c->stream));
+    const int b = c->cur ^ 1;
+    CU(cudaEventSynchronize(c->ev_copied[b]));
+    c->cur = b; c->d_x = c->d_xbuf[b]; c->d_geom = c->d_geombuf[b]; c->h_geom = c->h_geombuf[b];
     for (int f = 0; f < nframes; ++f)
     {
         FrameGeom& g = c->h_geom[f];
         for (int k = 0; k < 3; ++k)
         {
             const float bk = box9[(size_t)f * 9 + 4 * k];
-            if (!(bk > 0.f)) return fail(B2A_ERR_ARG, "b2a_submit_batch: frame %d has non-positive box length", f);
             g.L[k]        = (double)bk;            // ipp:72-74
             g.half[k]     = g.L[k] / 2;            // ipp:128
             g.inv_unit[k] = 4294967296.0 / g.L[k];
@@ -439,9 +478,14 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
     }
     std::memcpy(c->h_box.data(), box9, sizeof(float) * 9 * (size_t)nframes);
     {
+        // upload on the copy stream (overlaps the kernels of the previous batch, which read the other buffer); kernels
+        // launched after this call wait for it through ev_copied.  `x` must stay untouched until then, as before.
         Timed t(c, 5);
-        CU(cudaMemcpyAsync(c->d_x, x, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->stream));
-        CU(cudaMemcpyAsync(c->d_geom, c->h_geom, sizeof(FrameGeom) * nframes, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+        CU(cudaMemcpyAsync(c->d_x, x, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaMemcpyAsync(c->d_geom, c->h_geom, sizeof(FrameGeom) * nframes, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
     }
     c->nframes = nframes;
     c->serial++;
@@ -648,6 +692,8 @@ extern "C" int b2a_submit_field(b2a_ctx* c, int field, int nframes, const float*
     CU(cudaSetDevice(c->device));
     if (!c->d_field[field]) CU(cudaMalloc(&c->d_field[field], (size_t)c->natoms * 3 * sizeof(float) * c->maxK));
     CU(cudaMemcpyAsync(c->d_field[field], data, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->ev_field, c->stream));   // the caller's buffer is free again once this has passed (b2a_submit_batch waits)
+    c->field_pending = true;
     c->field_serial[field] = c->serial;
     return B2A_OK;
 }

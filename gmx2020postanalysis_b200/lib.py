@@ -196,8 +196,10 @@ class Context:
         if b.shape[0] == 1 and K > 1:
             b = np.ascontiguousarray(np.repeat(b, K, axis=0))
         assert x.shape[1:] == (self.natoms, 3) and b.shape[0] == K
-        self._keep = [x, b]
         check(self.L.b2a_submit_batch(self._h, K, x.ctypes.data, b.ctypes.data))
+        # the copy is asynchronous: keep this batch's arrays AND the previous one's alive (the library only guarantees that
+        # the upload before last has completed when b2a_submit_batch returns)
+        self._keep = ([x, b] + getattr(self, "_keep", []))[:8]
         return K
 
     def centers(self, grp, com=0, frame=0):

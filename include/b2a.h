@@ -88,7 +88,12 @@ int b2a_group_nmol(b2a_ctx* ctx, int grp);
 /* ---- frames (A1) ------------------------------------------------------------------------------- */
 /* x: [nframes][natoms][3] float (rvec layout), box9: [nframes][9] float row-major matrix; only the
  * diagonal is used, as in the reference (ipp:72-74).  Replaces the current batch; cached centres of
- * the previous batch are invalidated.                                                             */
+ * the previous batch are invalidated.  The upload is asynchronous and double-buffered on the device: it runs on its
+ * own stream into the buffer the kernels of the PREVIOUS batch are not reading, so a caller that submits batch k+1
+ * right after queueing the accumulators of batch k (and only then reads results of batch k) overlaps the H2D copy
+ * with the kernels.  Everything launched after the call waits for the upload.  `x` (pinned memory for a truly
+ * asynchronous copy) must stay unmodified until the NEXT b2a_submit_batch has returned or the context has been
+ * synchronised; callers alternate between two host buffers (include/itp/gmx_bits/b2a_batcher.hpp does).         */
 int b2a_submit_batch(b2a_ctx* ctx, int nframes, const float* x, const float* box9);
 int b2a_batch_frames(b2a_ctx* ctx);
 

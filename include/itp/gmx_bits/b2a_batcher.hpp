@@ -165,8 +165,8 @@ namespace b2a_detail
         bool               eof_ = false;
         long               serial_ = 0;
         // Two pinned staging buffers, used alternately: the asynchronous H2D copy of batch k may still be reading its
-        // buffer while the host already decodes batch k+1 into the other one; b2a_submit_batch(k+1) synchronises the
-        // stream before anything else, so by the time buffer k%2 is refilled (batch k+2) its copy has completed.
+        // buffer while the host already decodes batch k+1 into the other one; b2a_submit_batch(k+1) waits for the upload of batch k (and for pending field uploads)
+        // before it returns, so by the time buffer k%2 is refilled (batch k+2) its copy has completed.
         float*             px_[2] = { nullptr, nullptr }, *pv_[2] = { nullptr, nullptr }, *pf_[2] = { nullptr, nullptr };
         float*             bx_ = nullptr, *bv_ = nullptr, *bf_ = nullptr;   // the buffers of the batch being filled / served
         int                flip_ = 0;
