@@ -1089,11 +1089,18 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         // full mode: j split so that the grid covers the machine several times
         const int max_tiles = (p.n0 + TI - 1) / TI + std::min(nslab, p.n0);
         const int itiles    = std::max(1, (p.n0 + TI - 1) / TI);
-        int       jsplit    = std::max(1, (c->sm_count * 24 + itiles * c->nframes - 1) / (itiles * c->nframes));
-        jsplit              = std::min(jsplit, std::max(1, (p.n1 + kTileJ - 1) / kTileJ));
-        p.jchunk            = (p.n1 + jsplit - 1) / jsplit;
-        p.jchunk            = ((p.jchunk + kTileJ - 1) / kTileJ) * kTileJ;
-        p.jsplit            = (p.n1 + p.jchunk - 1) / p.jchunk;
+        // j split: the grid runs in waves of `slots` resident blocks and the under-filled last wave is lost time, so offer
+        // about ten waves, but never chunks below two j tiles (per-block set-up, histogram zeroing and flush).  Measured on
+        // config 3 (31 i-tiles x 8 frames): 4.4 waves -> 0.75 of FP32 issue, 7 -> 0.78, 10.4 -> 0.79; config 2 full
+        // evaluation: 5.4 waves -> 0.85, 10.7 -> 0.87.
+        const int resident = std::max(1, std::min(5, (int)((227 * 1024) / (smem + 1024))));   // 96 registers x 128 threads: 5
+        int       waves    = 10;
+        if (const char* e = getenv("B2A_K3_WAVES")) waves = std::max(1, atoi(e));
+        int       jsplit   = std::max(1, (c->sm_count * resident * waves + itiles * c->nframes - 1) / (itiles * c->nframes));
+        jsplit             = std::min(jsplit, std::max(1, p.n1 / (2 * kTileJ)));
+        p.jchunk           = (p.n1 + jsplit - 1) / jsplit;
+        p.jchunk           = ((p.jchunk + kTileJ - 1) / kTileJ) * kTileJ;
+        p.jsplit           = (p.n1 + p.jchunk - 1) / p.jchunk;
         if (int rc = dispatch_rdf<8, 0>(c, a, *g0, *g1, p, cd, smem, dim3(max_tiles, p.jsplit, c->nframes), cubic)) return rc;
     }
     if (p.sym_enabled)
