@@ -885,23 +885,22 @@ static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p,
     return B2A_OK;
 }
 
-template <int IPT, int MODE>
+template <int IPT, int MODE, int TH = 128>
 static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid, bool cubic)
 {
-    constexpr int TH = 128;
     if (a.paranoid)
         return cubic ? launch_rdf<IPT, TH, true, true, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, true, MODE>(c, a, g0, g1, p, cd, smem, grid);
     return cubic ? launch_rdf<IPT, TH, true, false, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, false, MODE>(c, a, g0, g1, p, cd, smem, grid);
 }
 
-constexpr int kCellIPT = 4;   // i-molecules per thread in cell mode (one cell per block: ~300-500 molecules)
+constexpr int kCellIPT = 4, kCellThreads = 64;   // cell mode: 256-molecule tiles (64 threads x 4): half the z span of a 512-molecule tile; measured on config 5: 512 -> 17.7 ms, 256 (128 x 2) -> 13.2, 256 (64 x 4) -> 12.5, 128 (32 x 4) -> 13.5
 
 // Cell grid for r_max << L: cells per dimension 2^bits, reach per dimension from the cut-off plus the fixed-point slop.
 // Returns false when cells would not cull enough to beat the brute-force (possibly symmetric) evaluation.
 // `columns`: the caller cuts its i-tiles from whole (cx, cy) columns of cells (k3_rdf MODE 2) instead of giving every cell a
 // tile of its own (k5_coord): tiles are always full, so cells may be much finer than a tile, and a tile that spans several
 // cells along z searches the union of their z ranges.
-static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_possible, int* bits, int reach[3], int ti = kCellIPT * 128,
+static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_possible, int* bits, int reach[3], int ti = kCellIPT * kCellThreads,
                          double* cost_out = nullptr, bool columns = false)
 {
     int want = a.cells;
@@ -1035,7 +1034,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     const int nslab = p.nslab;
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, c->stream));
     int  bits = 0, reach[3] = { 0, 0, 0 };
-    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, kCellIPT * 128, nullptr, true);
+    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, kCellIPT * kCellThreads, nullptr, true);
     CellDev cd{};
     {
         Timed tm(c, 1);
@@ -1080,9 +1079,9 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         RdfDev pc = p;
         // one block row per column of i-cells; its tiles are spread over gridDim.y (a block loops if a column is more crowded)
         const double per_col = (double)p.n0 / (double)(1u << (2 * bits));
-        const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCellIPT * 128))));
+        const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCellIPT * kCellThreads))));
         // symmetric evaluation doubles the block rows: even = beyond-the-tile part of the j runs, odd = the tile against itself
-        return dispatch_rdf<kCellIPT, 2>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes), cubic);
+        return dispatch_rdf<kCellIPT, 2, kCellThreads>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes), cubic);
     }
     constexpr int TI = 8 * 128;   // TI molecules of one slab per block
     {
@@ -1108,6 +1107,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         // symmetric mode: work items = per i-tile one diagonal block + chunks of the molecules beyond the tile
         RdfDev ps  = p;
         ps.jchunk  = 4 * kTileJ;
+        if (const char* e = getenv("B2A_K3_SYMCHUNK")) ps.jchunk = std::max(1, atoi(e)) * kTileJ;
         const int T = (p.n0 + TI - 1) / TI;
         long long items = 0;
         for (int t = 0; t < T; ++t) items += 1 + (std::max(0, p.n0 - (t + 1) * TI) + ps.jchunk - 1) / ps.jchunk;
