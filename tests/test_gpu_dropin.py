@@ -46,6 +46,18 @@ def test_fused_port_matches_reference_output(tmp_path, monkeypatch):
         assert got == _golden(name)
 
 
+@pytest.mark.parametrize("name,exe", [("density_template_c1", "readme_template_fused"), ("orient_water", "calc_orient_mof_fused"),
+                                      ("orient_il_cross", "calc_orient_mof_fused"), ("pair_dist_il", "calc_pair_dist_bulk_fused")])
+@pytest.mark.parametrize("batch", ["16", "3"])
+def test_other_fused_ports_match_reference_output(name, exe, batch, tmp_path, monkeypatch):
+    """The density template, calc_orient_mof and calc_pair_dist_bulk ported to the fused accumulators (K2 / K4 / K5: same
+    command line, frame loop replaced by one accumulate per resident batch) write the reference program's output file."""
+    case = GC.program_cases()[name]
+    monkeypatch.setenv("B2A_BATCH", batch)
+    got = refprog.run_program(_dropin(exe), str(tmp_path), case["system"](), case["nframes"], case["groups"], case["args"], "out.xvg")
+    assert got == _golden(name)
+
+
 def test_live_reference_vs_dropin_other_programs(tmp_path):
     """Programs without a golden file: run both builds here and compare (only where oracle/_ref travelled)."""
     from gmx2020postanalysis_b200 import synth
