@@ -76,8 +76,11 @@ def main():
                        LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.path.join(ROOT, "gmx2020postanalysis_b200") + ":"
                        + os.environ.get("LD_LIBRARY_PATH", ""))
 
+            import re
+
             def run(trj, tag):
-                best = 1e30
+                """-> (whole-process wall time, seconds the program itself measured around its frame loop), best of two"""
+                best, loop = 1e30, 1e30
                 for rep in range(2):
                     t = time.perf_counter()
                     r = subprocess.run([exe, "-f", trj, "-s", os.path.join(td, "c2.b2p"), "-n", os.path.join(td, "c2.ndx"), "-o",
@@ -85,12 +88,16 @@ def main():
                     best = min(best, time.perf_counter() - t)
                     if r.returncode != 0:
                         raise RuntimeError(r.stderr[-800:])
-                return best
+                    m = re.search(r"frame loop ([0-9.]+) s", r.stdout)
+                    if m:
+                        loop = min(loop, float(m.group(1)))
+                return best, loop
             e2e = {}
             for kind, long_f, short_f in (("xtc", xtc, short_xtc), ("raw", raw, short_raw)):
-                t_short, t_long = run(short_f, kind + "_s"), run(long_f, kind)
+                (t_short, _), (t_long, loop_long) = run(short_f, kind + "_s"), run(long_f, kind)
                 e2e[kind] = {"wall_s_%d_frames" % K1: t_short, "wall_s_%d_frames" % K: t_long,
-                             "frames_per_s_steady": (K - K1) / max(t_long - t_short, 1e-9)}
+                             "frame_loop_s": loop_long, "frames_per_s_frame_loop": K / loop_long,
+                             "frames_per_s_from_wall_difference": (K - K1) / max(t_long - t_short, 1e-9)}
             e2e["outputs_identical"] = open(os.path.join(td, "xtc.xvg")).read().split("\n")[3:] == open(os.path.join(td, "raw.xvg")).read().split("\n")[3:]
             out["fused_program"] = e2e
     print(json.dumps(out))
