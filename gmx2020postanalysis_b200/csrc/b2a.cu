@@ -575,11 +575,13 @@ static int launch_stream(b2a_ctx* c, const Group& g, int com, int M, StreamArgs 
         if (kvar == 2 && g.napm != 3 && warps >= 1) return launch_stream_t<0, 0, 2>(c, g, com, 32 * warps, a, extra_smem, fast_mode);
     }
     if constexpr (MODE == 2)
-        if (g.napm == 3 && var == 1)
+        if (var == 1)
         {
-            int mc = M;   // consumer threads; each evaluates two molecules, so a tile holds 2 * mc
+            // consumer threads; each evaluates two molecules, so a tile holds 2 * mc of them: at most 24 KB per stage
+            int mc = std::min(M, std::max(32, (24576 / (24 * g.napm)) / 32 * 32));
             if (const char* e = getenv("B2A_K4_THREADS")) mc = std::max(32, std::min(256, atoi(e) / 32 * 32));
-            return launch_stream_t<2, 3, 1>(c, g, com, mc, a, extra_smem, fast_mode);
+            if (g.napm == 3) return launch_stream_t<2, 3, 1>(c, g, com, mc, a, extra_smem, fast_mode);
+            if (2 * mc * g.napm * 12 <= 32768) return launch_stream_t<2, 0, 1>(c, g, com, mc, a, extra_smem, fast_mode);
         }
     if (g.napm == 3) return launch_stream_t<MODE, 3>(c, g, com, M, a, extra_smem, fast_mode);
     return launch_stream_t<MODE, 0>(c, g, com, M, a, extra_smem, fast_mode);
@@ -1427,11 +1429,23 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
         // the bracket needs monotone radial bins
         const int fast = (s.dr > 0.f && s.CR > s.Cr) ? a.fast : 0;
         // three-site molecule with vectors (reference atom -> the other two): packed fast path orient_fast3
-        int var = 0;
-        if (g->napm == 3 && smem_bins > 0 && d.tp1 == 0 && ((d.tp2 == 1 && d.tp3 == 2) || (d.tp2 == 2 && d.tp3 == 1)))
+        // two molecules per thread in packed FP32 whenever the histogram fits in shared memory; three-site molecules whose
+        // vectors run from the reference atom to the other two additionally reuse the unwrapped offsets as the vectors
+        int var = smem_bins > 0 ? 1 : 0;
+        sa.ori_sign = 1.f;
+        {   // shared-memory bank conflicts of the one-molecule-per-lane reads: g lanes per bank, g = gcd(3 napm, 32)
+            int gcd = 1;
+            while (gcd < 32 && (3 * g->napm) % (2 * gcd) == 0) gcd *= 2;
+            int sh = 5;
+            for (int v = gcd; v > 1; v >>= 1) --sh;
+            sa.rot_shift = (gcd >= 8 && gcd <= g->napm && !getenv("B2A_NO_ROT")) ? sh : 5;   // the walk needs g distinct atoms; measured
+            // (tools/bench_hbm_napm.py): 8 atoms 0.34 -> 0.43, 16 atoms 0.21 -> 0.32 of HBM peak; 2- and 4-way conflicts (6, 12 atoms) are cheaper
+            // than the extra atom and index arithmetic of the rotated walk
+        }
+        if (g->napm == 3 && d.tp1 == 0 && ((d.tp2 == 1 && d.tp3 == 2) || (d.tp2 == 2 && d.tp3 == 1)))
         {
-            var = 1;
-            sa.ori_sign = s.method == 1 ? -1.f : (d.tp2 == 1 ? 1.f : -1.f);
+            sa.ori_reuse = 1;
+            sa.ori_sign  = s.method == 1 ? -1.f : (d.tp2 == 1 ? 1.f : -1.f);
         }
         if (const char* e = getenv("B2A_ORIENT_VAR")) var = std::min(var, atoi(e));
         return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 4) & ~1) + sizeof(float2) * (s.nAngle + 2) + sizeof(unsigned) * smem_bins, fast, var);

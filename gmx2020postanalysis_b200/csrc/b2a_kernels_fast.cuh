@@ -282,33 +282,16 @@ __device__ __forceinline__ void load3x2(Mol3x2& m, const float* pA, const float*
     m.hsmin = fk.hsmin; m.dmax = fk.dmax;
 }
 
-__device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, bool validB, float w1, float w2, float wsgn, const FastParams& fp,
-                                               const OrientDev& d, const OrientFast& of, const float* fedge, const float2* fmh,
-                                               const unsigned char* lut, int res[2], int meZ[2], int lo[2])
+// ---- the part of the two-molecule bracket that follows the centres and the two vectors -----------------------------------------
+// C: centre components; MU / MD: per-molecule maxima of |offset| and |raw difference| behind the centre (error of the centre);
+// V1, V2: the two vectors up to the sign vsgn; MV / MDV: the maxima behind them (error of the vectors)
+__device__ __forceinline__ void orient_tail_x2(const unsigned long long C[3], unsigned long long MU, unsigned long long MD,
+                                               const unsigned long long V1[3], const unsigned long long V2[3], unsigned long long MV,
+                                               unsigned long long MDV, bool undA, bool undB, bool validA, bool validB, float vsgn,
+                                               const FastParams& fp, const OrientDev& d, const OrientFast& of, const float* fedge,
+                                               const float2* fmh, const unsigned char* lut, int res[2], int meZ[2], int lo[2])
 {
-    typedef unsigned long long P;   // (molecule A, molecule B)
-    const P magic2 = f2bc(kRndMagic);
-    P       U1[3], U2[3];
-    float   mdA = 0.f, mdB = 0.f, muA = 0.f, muB = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-    {
-        const P D1 = f2sub(m.X1[k], m.X0[k]);   // d = fl(x_j - x_0)
-        const P D2 = f2sub(m.X2[k], m.X0[k]);
-        U1[k]      = f2fma(f2sub(f2fma(D1, m.iL2[k], magic2), magic2), m.nL2[k], D1);   // u^ = fl(d - rint(d / L) L)
-        U2[k]      = f2fma(f2sub(f2fma(D2, m.iL2[k], magic2), magic2), m.nL2[k], D2);
-        float a, b, e, f;
-        f2unpack(D1, a, b); f2unpack(D2, e, f);
-        mdA = fmaxf(fmaxf(mdA, fabsf(a)), fabsf(e)); mdB = fmaxf(fmaxf(mdB, fabsf(b)), fabsf(f));
-        f2unpack(U1[k], a, b); f2unpack(U2[k], e, f);
-        muA = fmaxf(fmaxf(muA, fabsf(a)), fabsf(e)); muB = fmaxf(fmaxf(muB, fabsf(b)), fabsf(f));
-    }
-    bool undA = !(muA < m.hsmin && mdA <= m.dmax), undB = !(muB < m.hsmin && mdB <= m.dmax);   // shift count not proven
-    const P MU = f2pack(muA, muB), MD = f2pack(mdA, mdB);
-    const P W1 = f2bc(w1), W2 = f2bc(w2), IW = f2bc(fp.invW);
-    P       C[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) C[k] = f2fma(f2fma(W2, U2[k], f2mul(W1, U1[k])), IW, m.X0[k]);
+    typedef unsigned long long P;
     float c0a, c0b, c1a, c1b, c2a, c2b;
     f2unpack(C[0], c0a, c0b); f2unpack(C[1], c1a, c1b); f2unpack(C[2], c2a, c2b);
     const P CM = f2pack(fmaxf(fabsf(c0a), fmaxf(fabsf(c1a), fabsf(c2a))), fmaxf(fabsf(c0b), fmaxf(fabsf(c1b), fabsf(c2b))));
@@ -355,20 +338,20 @@ __device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, boo
         undB = undB || !(fabsf(gb) < hb) || !(__float_as_uint(qb) < __float_as_uint(2.0e9f));
     }
     // vecOut up to the sign wsgn; |v^ - v| <= Ev per component
-    const P Ev = f2mul(f2add(MD, MU), f2bc(1.05f * kEps));
+    const P Ev = f2mul(f2add(MDV, MV), f2bc(1.05f * kEps));
     P       VO[3], Evo;
     if (d.method == 2)
     {
-        VO[0] = f2sub(f2mul(U1[1], U2[2]), f2mul(U1[2], U2[1]));
-        VO[1] = f2sub(f2mul(U1[2], U2[0]), f2mul(U1[0], U2[2]));
-        VO[2] = f2sub(f2mul(U1[0], U2[1]), f2mul(U1[1], U2[0]));
+        VO[0] = f2sub(f2mul(V1[1], V2[2]), f2mul(V1[2], V2[1]));
+        VO[1] = f2sub(f2mul(V1[2], V2[0]), f2mul(V1[0], V2[2]));
+        VO[2] = f2sub(f2mul(V1[0], V2[1]), f2mul(V1[1], V2[0]));
         // |d(ab - cd)| <= Ev (|a|+|b|+|c|+|d|) + 2 Ev^2 + 2 eps (|ab| + |cd|), inflated by 5 %
-        Evo = f2mul(f2fma(f2mul(MU, f2bc(4.0f)), Ev, f2fma(f2add(Ev, Ev), Ev, f2mul(f2mul(MU, f2bc(4.0f * kEps)), MU))), f2bc(1.05f));
+        Evo = f2mul(f2fma(f2mul(MV, f2bc(4.0f)), Ev, f2fma(f2add(Ev, Ev), Ev, f2mul(f2mul(MV, f2bc(4.0f * kEps)), MV))), f2bc(1.05f));
     }
     else
     {
-        VO[0] = f2add(U1[0], U2[0]); VO[1] = f2add(U1[1], U2[1]); VO[2] = f2add(U1[2], U2[2]);
-        Evo   = f2fma(MU, f2bc(2.1f * kEps), f2mul(Ev, f2bc(2.1f)));
+        VO[0] = f2add(V1[0], V2[0]); VO[1] = f2add(V1[1], V2[1]); VO[2] = f2add(V1[2], V2[2]);
+        Evo   = f2fma(MV, f2bc(2.1f * kEps), f2mul(Ev, f2bc(2.1f)));
     }
     const P N2 = f2fma(VO[2], VO[2], f2fma(VO[1], VO[1], f2mul(VO[0], VO[0])));
     float   n2a, n2b, ria, rib;
@@ -377,7 +360,7 @@ __device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, boo
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rib) : "f"(n2b));
     const P RI  = f2pack(ria, rib);
     const P DOT = d.DIMNOrient == 0 ? VO[0] : (d.DIMNOrient == 1 ? VO[1] : VO[2]);
-    const P CS  = f2mul(DOT, f2mul(RI, f2bc(wsgn)));
+    const P CS  = f2mul(DOT, f2mul(RI, f2bc(vsgn)));
     const P REL = f2mul(Evo, RI);
     const P Ecs = f2fma(REL, f2bc(3.0f), f2bc(10.0f * kEps));   // the float roundings of the edge table are inside fmh[].y
     const P OM  = f2sub(f2bc(1.0f), Ecs);
@@ -400,6 +383,99 @@ __device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, boo
     res[1] = (outB || !validB) ? 1 : (undB ? 0 : 2);
     meZ[0] = (int)kqa; meZ[1] = (int)kqb;
     lo[0] = loA; lo[1] = loB;
+}
+
+// Three-site molecule, vectors from the reference atom to the other two: the vectors ARE the unwrapped offsets (see above).
+__device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, bool validB, float w1, float w2, float wsgn, const FastParams& fp,
+                                               const OrientDev& d, const OrientFast& of, const float* fedge, const float2* fmh,
+                                               const unsigned char* lut, int res[2], int meZ[2], int lo[2])
+{
+    typedef unsigned long long P;   // (molecule A, molecule B)
+    const P magic2 = f2bc(kRndMagic);
+    P       U1[3], U2[3];
+    float   mdA = 0.f, mdB = 0.f, muA = 0.f, muB = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const P D1 = f2sub(m.X1[k], m.X0[k]);   // d = fl(x_j - x_0)
+        const P D2 = f2sub(m.X2[k], m.X0[k]);
+        U1[k]      = f2fma(f2sub(f2fma(D1, m.iL2[k], magic2), magic2), m.nL2[k], D1);   // u^ = fl(d - rint(d / L) L)
+        U2[k]      = f2fma(f2sub(f2fma(D2, m.iL2[k], magic2), magic2), m.nL2[k], D2);
+        float a, b, e, f;
+        f2unpack(D1, a, b); f2unpack(D2, e, f);
+        mdA = fmaxf(fmaxf(mdA, fabsf(a)), fabsf(e)); mdB = fmaxf(fmaxf(mdB, fabsf(b)), fabsf(f));
+        f2unpack(U1[k], a, b); f2unpack(U2[k], e, f);
+        muA = fmaxf(fmaxf(muA, fabsf(a)), fabsf(e)); muB = fmaxf(fmaxf(muB, fabsf(b)), fabsf(f));
+    }
+    const bool undA = !(muA < m.hsmin && mdA <= m.dmax), undB = !(muB < m.hsmin && mdB <= m.dmax);   // shift count not proven
+    const P MU = f2pack(muA, muB), MD = f2pack(mdA, mdB);
+    const P W1 = f2bc(w1), W2 = f2bc(w2), IW = f2bc(fp.invW);
+    P       C[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) C[k] = f2fma(f2fma(W2, U2[k], f2mul(W1, U1[k])), IW, m.X0[k]);
+    orient_tail_x2(C, MU, MD, U1, U2, MU, MD, undA, undB, validA, validB, wsgn, fp, d, of, fedge, fmh, lut, res, meZ, lo);
+}
+
+// Any molecule, any three vector atoms, two molecules per thread: the offsets of every atom from the reference atom feed the
+// weighted centre sum as they are produced (nothing per atom stays live), the two vectors are the minimum images of
+// x_tp1 - x_tp2 and x_tp1 - x_tp3 (proven and unique below hsmin, exactly as in orient_fast()).
+// `rot` (0 when the stride is odd): with one molecule per lane the lanes of a warp read their atom j at a stride of 3 * napm
+// words, which for even napm puts 2 to 16 lanes on the same shared-memory bank.  The FP32 sums here do not depend on the
+// order of the atoms, so lane block m = lane / (32 / g), g = gcd(3 napm, 32), starts its walk at atom m: the g lanes that
+// would collide read g different atoms, 3 m words apart, and 3 m mod g is a permutation.  The walk then includes the
+// reference atom itself (offset exactly 0, contributes nothing), so that the wrap-around is a whole molecule = a multiple of g.
+template <bool SMEM>
+__device__ __forceinline__ void orient_fastNx2(const float* pA, const float* pB, bool validA, bool validB, int napm, int rot, const float* swf,
+                                               const FastParams& fp, const FastPack& fk, const OrientDev& d, const OrientFast& of,
+                                               const float* fedge, const float2* fmh, const unsigned char* lut, int res[2], int meZ[2],
+                                               int lo[2])
+{
+    typedef unsigned long long P;
+    const P magic2 = f2bc(kRndMagic);
+    P       X0[3], nL2[3], iL2[3], ACC[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        nL2[k] = *reinterpret_cast<const P*>(&fk.negL2[2 * k]);
+        iL2[k] = *reinterpret_cast<const P*>(&fk.invL2[2 * k]);
+        X0[k]  = f2pack(ldf<SMEM>(pA + k), ldf<SMEM>(pB + k));
+        ACC[k] = f2bc(0.f);
+    }
+    float mdA = 0.f, mdB = 0.f, muA = 0.f, muB = 0.f;
+    auto offset = [&](P X, P REF, int k, float& ma_d, float& mb_d, float& ma_u, float& mb_u) -> P {
+        const P D = f2sub(X, REF);
+        const P U = f2fma(f2sub(f2fma(D, iL2[k], magic2), magic2), nL2[k], D);
+        float   a, b;
+        f2unpack(D, a, b); ma_d = fmaxf(ma_d, fabsf(a)); mb_d = fmaxf(mb_d, fabsf(b));
+        f2unpack(U, a, b); ma_u = fmaxf(ma_u, fabsf(a)); mb_u = fmaxf(mb_u, fabsf(b));
+        return U;
+    };
+    int jj = rot;   // rot < napm (host)
+#pragma unroll 2
+    for (int j = rot ? 0 : 1; j < napm; ++j)
+    {
+        const int ja = rot ? jj : j;
+        const P   W  = f2bc(swf[ja]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            ACC[k] = f2fma(W, offset(f2pack(ldf<SMEM>(pA + 3 * ja + k), ldf<SMEM>(pB + 3 * ja + k)), X0[k], k, mdA, mdB, muA, muB), ACC[k]);
+        jj = jj + 1 == napm ? 0 : jj + 1;
+    }
+    float mdvA = 0.f, mdvB = 0.f, mvA = 0.f, mvB = 0.f;
+    P     V1[3], V2[3], C[3];
+    const P IW = f2bc(fp.invW);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+    {
+        const P T1 = f2pack(ldf<SMEM>(pA + 3 * d.tp1 + k), ldf<SMEM>(pB + 3 * d.tp1 + k));
+        V1[k] = offset(T1, f2pack(ldf<SMEM>(pA + 3 * d.tp2 + k), ldf<SMEM>(pB + 3 * d.tp2 + k)), k, mdvA, mdvB, mvA, mvB);
+        V2[k] = offset(T1, f2pack(ldf<SMEM>(pA + 3 * d.tp3 + k), ldf<SMEM>(pB + 3 * d.tp3 + k)), k, mdvA, mdvB, mvA, mvB);
+        C[k]  = f2fma(ACC[k], IW, X0[k]);
+    }
+    const bool undA = !(fmaxf(muA, mvA) < fk.hsmin && fmaxf(mdA, mdvA) <= fk.dmax);
+    const bool undB = !(fmaxf(muB, mvB) < fk.hsmin && fmaxf(mdB, mdvB) <= fk.dmax);
+    orient_tail_x2(C, f2pack(muA, muB), f2pack(mdA, mdB), V1, V2, f2pack(mvA, mvB), f2pack(mdvA, mdvB), undA, undB, validA, validB, 1.0f,
+                   fp, d, of, fedge, fmh, lut, res, meZ, lo);
 }
 
 } // namespace b2a

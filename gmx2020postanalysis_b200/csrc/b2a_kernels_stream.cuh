@@ -97,6 +97,8 @@ struct StreamArgs
     OrientFast           of;
     const unsigned char* lut;    // MODE 2: kCosLut first-candidate angle bins
     float                ori_sign;   // MODE 2, VAR 1: sign that turns orient_fast3x2's vector into the reference's vecOut
+    int                  rot_shift;  // MODE 2, VAR 1: log2(32 / gcd(3 napm, 32)); 5 = odd stride, no rotation
+    int                  ori_reuse;  // MODE 2, VAR 1, three-site molecules: the vector atoms are (reference atom, the other two)
     const float2*        fmh;        // MODE 2: per angle bin {midpoint, halfwidth - table roundings} of its cosine interval
 };
 
@@ -117,8 +119,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 // compute out of shared memory and release the stage by arriving on its `empty` mbarrier, warp by warp.  There is no
 // block-wide barrier inside the stream: a slow warp never stalls the others, the ring never drains between items, and
 // tables / histogram zero+flush happen once per block for the whole launch.
-// VAR (MODE 2 only): 1 = three-site molecule whose vector atoms are (reference atom, the other two) -> orient_fast3x2(),
-// two molecules per consumer thread (a tile holds 2 x consumer-thread-count molecules).
+// VAR (MODE 2): 1 = two molecules per consumer thread in packed FP32 (a tile holds 2 x consumer-thread-count molecules):
+// orient_fastNx2() for any molecule, orient_fast3x2() for three-site molecules whose vector atoms are (reference atom, the
+// other two).
 template <int MODE, int NAPM_T, int VAR>
 __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream(const __grid_constant__ StreamArgs a)
 {
@@ -149,7 +152,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
     // dimension), ten molecules per warp -- the exact FP64 centre of a large molecule is one long dependent chain per
     // dimension, and its atoms take 12 * napm bytes of every stage: one thread per molecule leaves an SM with a handful of
     // warps crawling along those chains (napm = 25: 0.19 of HBM peak, tools/bench_hbm_napm.py)
-    const int MT = (MODE == 2 && VAR == 1) ? 2 * M : ((MODE == 0 && VAR == 2) ? 10 * (M >> 5) : M);
+    const int MT = (MODE == 2 && VAR == 1) ? 2 * M : ((MODE == 0 && VAR == 2) ? 10 * (M >> 5) : M);   // (host: launch_stream_t)
     for (int j = threadIdx.x; j < napm; j += T) { sw[j] = a.w[j]; if (MODE != 0) swf[j] = a.wf[j]; }
     if (MODE == 2 && a.fp.enabled)
         for (int j = threadIdx.x; j < kCosLut / 4; j += T) reinterpret_cast<unsigned*>(slut)[j] = reinterpret_cast<const unsigned*>(a.lut)[j];
@@ -218,8 +221,10 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
         // ---- consumer warps ------------------------------------------------------------------------------------------------
         const unsigned toff = threadIdx.x * (unsigned)napm * 3u;
         // orient_fast3x2: the two off-reference weights and the sign of the computed vector, kept in registers
-        const float w3a = (MODE == 2 && VAR == 1) ? a.wf[1] : 0.f, w3b = (MODE == 2 && VAR == 1) ? a.wf[2] : 0.f;
+        const float w3a = (MODE == 2 && VAR == 1 && NAPM_T == 3) ? a.wf[1] : 0.f, w3b = (MODE == 2 && VAR == 1 && NAPM_T == 3) ? a.wf[2] : 0.f;
         const float w3s = (MODE == 2 && VAR == 1) ? a.ori_sign : 0.f;
+        // bank-conflict rotation of the atom walk (orient_fastNx2): lane block index, 0 for odd strides
+        const int lane_rot = (MODE == 2 && VAR == 1 && a.rot_shift < 5) ? (int)((threadIdx.x & 31u) >> a.rot_shift) : 0;
         for (unsigned n = 0;; ++n)
         {
             const int s = (int)(n % NS);
@@ -324,13 +329,18 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
                     {
                         const int    iB = i + M;                 // second molecule of this thread
                         const bool   vB = iB < a.nmol;
-                        const float* pB = vB ? p + (unsigned)M * 9u : p;   // past the end of the group: a copy that is ignored
+                        const float* pB = vB ? p + (unsigned)M * (unsigned)napm * 3u : p;   // past the end of the group: a copy that is ignored
                         int res[2], meZ[2], lo[2];
                         if (a.fp.enabled)
                         {
-                            Mol3x2 mol;
-                            load3x2<true>(mol, p, pB, g.fk);
-                            orient_fast3x2(mol, vA, vB, w3a, w3b, w3s, a.fp, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
+                            if (NAPM_T == 3 && a.ori_reuse)   // block-uniform: vectors = the unwrapped offsets themselves
+                            {
+                                Mol3x2 mol;
+                                load3x2<true>(mol, p, pB, g.fk);
+                                orient_fast3x2(mol, vA, vB, w3a, w3b, w3s, a.fp, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
+                            }
+                            else
+                                orient_fastNx2<true>(p, pB, vA, vB, napm, lane_rot, swf, a.fp, g.fk, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
                         }
                         // accounting of a proven molecule, statement for statement as at the end of orient_molecule(); the host
                         // selects this variant only when the histogram fits in shared memory

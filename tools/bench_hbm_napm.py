@@ -57,8 +57,15 @@ def main():
         ms1 = timed(k1, "k1_centers")
         ms2 = timed(lambda: ctx.accumulate(den), "k2_density")
         b1, b2 = K * (nat * 12 + nmol * 40), K * nat * 12
-        print(json.dumps({"napm": napm, "nmol": nmol, "k1_ms": ms1, "k1_frac": b1 / (ms1 * 1e-3) / 1e9 / hbm, "k2_ms": ms2,
-                          "k2_frac": b2 / (ms2 * 1e-3) / 1e9 / hbm}))
+        row = {"napm": napm, "nmol": nmol, "k1_ms": ms1, "k1_frac": b1 / (ms1 * 1e-3) / 1e9 / hbm, "k2_ms": ms2,
+               "k2_frac": b2 / (ms2 * 1e-3) / 1e9 / hbm}
+        if napm >= 3:
+            # K4 on the generic path: the vector atoms are NOT (reference atom, the other two), so nothing is reused
+            ori = ctx.orient_create(grp=0, com=0, DIMN=2, low=-1.0, up=100.0, c1=0.0, c2=0.0, dr=100.0, CR=100.0, Cr=0.0, nAngle=90,
+                                    tp1=2, tp2=1, tp3=3, DIMNOrient=2, method=1)
+            ms4 = timed(lambda: ctx.accumulate(ori), "k4_orient")
+            row.update(k4_ms=ms4, k4_frac=b2 / (ms4 * 1e-3) / 1e9 / hbm)
+        print(json.dumps(row))
         ctx.close()
 
 
