@@ -173,10 +173,11 @@ if __name__ == "__main__":
     ap.add_argument("--c4-frames", type=int, default=64)
     ap.add_argument("--c5", action="store_true")
     ap.add_argument("--only-c5", action="store_true")
+    ap.add_argument("--c5-frames", type=int, default=1)
     a = ap.parse_args()
     ap2 = a
     runs = [c1, lambda: c3(a.c3_frames), lambda: c4(a.c4_frames), coord] if not a.only_c5 else []
     if a.c5 or a.only_c5:
-        runs.append(c5)
+        runs.append(lambda: c5(a.c5_frames))
     for r in runs:
         print(json.dumps(r()))
