@@ -215,6 +215,8 @@ extern "C" int b2a_device_count(void)
     return n;
 }
 
+extern "C" void b2a_destroy(b2a_ctx* c);
+
 extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
 {
     if (!out || natoms <= 0 || max_frames <= 0) return fail(B2A_ERR_ARG, "b2a_create: natoms and max_frames must be positive");
@@ -226,7 +228,9 @@ extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
     }
     if (device < 0 || device >= ndev) return fail(B2A_ERR_ARG, "b2a_create: device %d out of range (%d visible)", device, ndev);
     CU(cudaSetDevice(device));
-    std::unique_ptr<b2a_ctx> c(new b2a_ctx);
+    // a context that fails half-way through (e.g. the batch does not fit in device memory) is torn down completely
+    struct Undo { void operator()(b2a_ctx* p) const { b2a_destroy(p); } };
+    std::unique_ptr<b2a_ctx, Undo> c(new b2a_ctx);
     c->device = device;
     c->natoms = natoms;
     c->maxK   = max_frames;
@@ -270,10 +274,10 @@ extern "C" void b2a_destroy(b2a_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& kv : c->groups) free_group(kv.second);
     for (auto& a : c->accs) if (a) free_acc(*a);
-    cudaStreamSynchronize(c->copy_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_work);
     cudaFree(c->d_field[1]); cudaFree(c->d_field[2]); cudaFree(c->d_field_cen);
     for (int b = 0; b < 2; ++b)
@@ -284,8 +288,9 @@ extern "C" void b2a_destroy(b2a_ctx* c)
         if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]);
     }
     if (c->ev_field) cudaEventDestroy(c->ev_field);
-    cudaStreamDestroy(c->copy_stream);
-    cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();   // a context torn down after a failed allocation must not leave a sticky error behind
     delete c;
 }
 
@@ -547,6 +552,8 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     a.nitems      = a.mblocks * ((c->nframes + a.item_frames - 1) / a.item_frames);
     if (!c->d_work) CU(cudaMalloc(&c->d_work, sizeof(unsigned)));
     a.work = c->d_work;
+    a.park_ns = 20000u;
+    if (const char* e = getenv("B2A_PARK_NS")) a.park_ns = (unsigned)std::max(0, atoi(e));
     constexpr int NS = stream_stages(MODE, VAR);
     size_t smem = (size_t)NS * a.tile_floats * 4 + NS * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
     if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut : 0);

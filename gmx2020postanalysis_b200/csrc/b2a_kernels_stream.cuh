@@ -52,8 +52,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // the producer's wait for a free stage: the ring is normally full, so this thread would spin for most of the kernel and
 // take issue slots from the consumer warps of its scheduler (ncu: 20 try_wait round trips per tile); the suspend-time hint
 // lets the hardware park it until the phase completes or the limit (ns) expires
-__device__ __forceinline__ void mbar_wait_parked(unsigned long long* bar, unsigned parity)
+__device__ __forceinline__ void mbar_wait_parked(unsigned long long* bar, unsigned parity, unsigned park_ns)
 {
+    if (park_ns == 0) { mbar_wait(bar, parity); return; }
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -61,7 +62,7 @@ __device__ __forceinline__ void mbar_wait_parked(unsigned long long* bar, unsign
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(20000u)
+        "r"(parity), "r"(park_ns)
         : "memory");
 }
 
@@ -78,6 +79,7 @@ struct StreamArgs
     int              nitems;         // mblocks * ceil(nframes / item_frames)
     unsigned*        work;           // device counter, zeroed before the launch: next work item to hand out
     int              tile_floats;    // floats reserved per stage (blockDim.x * napm * 3 + 8)
+    unsigned         park_ns;        // suspend-time hint of the producer's wait for a free stage (0: plain try_wait loop)
     // MODE 0: centres
     double*          cen;
     int4*            fix;
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
             for (unsigned n = 0;; ++n)
             {
                 const int s = (int)(n % NS);
-                if (n >= (unsigned)NS) mbar_wait_parked(&empty[s], ((n / NS) - 1u) & 1u);
+                if (n >= (unsigned)NS) mbar_wait_parked(&empty[s], ((n / NS) - 1u) & 1u, a.park_ns);
                 if (m >= 0 && f >= fend) { m = -1; it = next; next = atomicAdd(a.work, 1u); }
                 if (m < 0 && it < (unsigned)a.nitems)
                 {
