@@ -56,6 +56,13 @@ class Workload:
             self.text = ("cation-anion molecular-COM RDF, 1M-atom ionic liquid (31 250 x (25-site cation + 7-site anion), L=22.1 nm, "
                          "Rm=L/2, Rbin=5525, nbin=5), calc_rdf_region defaults")
             self.dram_per_frame = None
+        elif name == "c5":
+            self.L, self.seed = 34.0, 20200105
+            self.system = synth.mixed_box()
+            self.g0 = self.g1 = "SOL"                              # the CPU sample is taken on the dominant pair
+            self.text = ("mixed-species RDF sweep, 4M atoms (1.2M water + 8k cation + 8k anion + 24k cosolvent, L=34 nm), all 10 group "
+                         "pairs, Rm=3 nm, Rbin=1500, nbin=1 (cell-binned K3)")
+            self.dram_per_frame = None
         else:
             raise SystemExit(f"unknown --config {name}")
         import refprog
@@ -63,6 +70,18 @@ class Workload:
         self.n0 = len(self.gi0["index"]) // self.gi0["napm"]
         self.n1 = len(self.gi1["index"]) // self.gi1["napm"]
         self.same = self.g0 == self.g1
+        # the device job: groups to register and the (grp0, grp1) pairs to accumulate
+        if name == "c5":
+            names = ["SOL", "CAT", "ANI", "COS"]
+            self.groups = [refprog.group_info(self.system, n) for n in names]
+            self.pairs = [(a, b) for a in range(4) for b in range(a, 4)]
+            self.Rm, self.nbin = 3.0, 1
+        else:
+            self.groups = [self.gi0, self.gi1]
+            self.pairs = [(0, 1)]
+            self.Rm, self.nbin = float(np.float32(np.float32(self.L) / np.float32(2))), 5      # calc_rdf_region.cpp:52-57, :23
+        nm = [len(g["index"]) // g["napm"] for g in self.groups]
+        self.pairs_per_frame = float(sum(nm[a] * nm[b] for a, b in self.pairs))                # reference-equivalent ordered pairs
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -136,6 +155,8 @@ def cpu_reference_sample(wl, n_i, tmpdir, x0):
         env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
                    OMP_NUM_THREADS="1")
         cmd = [exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", prefix + ".ndx", "-o", prefix + ".xvg"]
+        if wl.name == "c5":
+            cmd += ["-Rm", "3", "-nbin", "1"]
         t = time.perf_counter()
         r = subprocess.run(cmd, input="0 1\n", capture_output=True, text=True, env=env, cwd=tmpdir)
         dt = time.perf_counter() - t
@@ -176,7 +197,8 @@ def cpu_reference_all_cores(wl, n_i, procs, tmpdir, x0):
     for q in range(procs):
         ndx = os.path.join(tmpdir, f"p{q}.ndx")
         trajio.write_index(ndx, {"G0_sub": i0[q * n_i * na:(q + 1) * n_i * na], "G1": i1})
-        cmds.append([exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", ndx, "-o", os.path.join(tmpdir, f"p{q}.xvg")])
+        cmds.append([exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", ndx, "-o", os.path.join(tmpdir, f"p{q}.xvg")]
+                    + (["-Rm", "3", "-nbin", "1"] if wl.name == "c5" else []))
     t = time.perf_counter()
     ps = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, cwd=tmpdir, text=True)
           for cmd in cmds]
@@ -197,7 +219,7 @@ def run_reference_arm(args):
     wl = Workload(args.config)
     system = wl.system
     x0 = system.frame(0)
-    n_i = min(args.ref_sample, wl.n0)
+    n_i = max(1, min(args.ref_sample, wl.n0, int(7.2e7 // wl.n1)))      # ~1-2 s of one core per step
     rates, kind = [], "reference"
     with tempfile.TemporaryDirectory() as td:
         for s in range(args.warmup + args.steps):
@@ -213,7 +235,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": "rdf_pair_distances_per_s", "value": value, "unit": "pair-distances/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(rates),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "frames_per_s": value / (wl.n0 * wl.n1),
+        "frames_per_s": value / wl.pairs_per_frame,
         "config": {"workload": wl.text, "sample": f"{n_i} of {wl.n0} i-molecules x all {wl.n1} j-molecules of frame 0 per step"},
         "cpu_baseline": {"value": value, "unit": "pair-distances/s", "cores": 1, "kind": kind,
                          "sample": f"{n_i} x {wl.n1} ordered pairs per step, {len(rates)} steps, whole-process wall time "
@@ -241,7 +263,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=8000, help="i-molecules of the cpu_baseline leg (~15 s of one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--symmetric", type=int, default=1)
-    ap.add_argument("--config", default="c2", choices=["c2", "c3"], help="c2 = headline (BASELINE configs[1]); c3 = configs[2]")
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
+                    help="c2 = headline (BASELINE configs[1]); c3 = configs[2]; c5 = configs[4] (use --frames-per-step 2)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -272,16 +295,26 @@ def main():
     box = system.box9()
 
     ctx = lib.Context(natoms, F, device=local)
-    for g, gi in enumerate((wl.gi0, wl.gi1)):
+    for g, gi in enumerate(wl.groups):
         ctx.set_group(g, gi["index"], gi["napm"], gi["mass"], gi["charge"])
-    Lbox = np.array([float(np.float32(LBOX))] * 3)
-    Rm = float(np.float32(np.float32(LBOX) / np.float32(2)))        # calc_rdf_region.cpp:52-57
-    Rbin = int(Rm / 0.002)                                          # :58
-    nbin = 5
-    acc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=nbin, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0,
-                         up2=100.0, Rm=Rm, Rbin=Rbin)
-    ctx.rdf_tune(acc, args.symmetric, 0)
+    Rm = wl.Rm
+    Rbin = int(np.float32(Rm) / 0.002)                              # :58
+    nbin = wl.nbin
+    accs = []
+    for g0, g1 in wl.pairs:
+        a_ = ctx.rdf_create(grp0=g0, grp1=g1, com0=0, com1=0, nbin=nbin, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0,
+                            up2=100.0, Rm=Rm, Rbin=Rbin)
+        ctx.rdf_tune(a_, args.symmetric, 0)
+        accs.append(a_)
     ncounters = nbin * Rbin
+
+    def accumulate_all():
+        for a_ in accs:
+            ctx.accumulate(a_)
+
+    def read_all():
+        out = [ctx.read(a_, ncounters) for a_ in accs]
+        return sum(int(c.sum()) for c, _ in out), np.sum([st for _, st in out], axis=0)
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
 
@@ -291,16 +324,17 @@ def main():
         torch.cuda.synchronize(local)
         ctx.sync()
 
-    pairs_step = float(F) * wl.n0 * wl.n1        # reference-equivalent ordered pairs per rank per step
+    pairs_step = float(F) * wl.pairs_per_frame   # reference-equivalent ordered pairs per rank per step
 
     # ---- phase 1: device-resident ------------------------------------------------------------------------
     ctx.submit(xh.numpy(), box)
     ctx.sync()
     for _ in range(args.warmup):
         ctx.invalidate()
-        ctx.accumulate(acc)
+        accumulate_all()
     ctx.sync()
-    ctx.reset(acc)
+    for a_ in accs:
+        ctx.reset(a_)
     ctx.timing_enable(True)
     ctx.timing_read()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -313,7 +347,7 @@ def main():
             flush.zero_()                        # L2 flush between timed iterations (outside the event pair)
         ev[s][0].record(stream)
         ctx.invalidate()
-        ctx.accumulate(acc)
+        accumulate_all()
         ev[s][1].record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall
@@ -322,37 +356,42 @@ def main():
     tot_ms = float(sum(step_ms))
     timing = ctx.timing_read()
     ctx.timing_enable(False)
-    counts_dev, stats_dev = ctx.read(acc, ncounters)
+    _, stats_dev = read_all()
     evaluated_pairs = float(stats_dev[lib.STAT_PAIRS])           # physically evaluated by this rank over the timed steps
 
     # ---- phase 2: end to end through the C ABI with host buffers -------------------------------------------
-    ctx.reset(acc)
+    def reset_all():
+        for a_ in accs:
+            ctx.reset(a_)
+    reset_all()
     for _ in range(2):
         ctx.submit(xh.numpy(), box)
-        ctx.accumulate(acc)
-        ctx.read(acc, ncounters)
-    ctx.reset(acc)
+        accumulate_all()
+        read_all()
+    reset_all()
     barrier()
     t0 = time.perf_counter()
     # every step uploads its own frames from pinned memory and reads its own result back; the upload of step s+1 is queued
     # (double-buffered, on the copy stream) before the host blocks on the result of step s, so it overlaps the kernels of s
     ctx.submit(xh.numpy(), box)                  # H2D of step 0
     for s in range(args.steps):
-        ctx.accumulate(acc)
+        accumulate_all()
         if s + 1 < args.steps:
             ctx.submit(xh2.numpy(), box)         # H2D of step s+1 (second pinned buffer: ping-pong, as the drop-in batcher does)
             xh, xh2 = xh2, xh
-        counts_e2e, stats_e2e = ctx.read(acc, ncounters)   # D2H of step s's result (u64 histogram + stats)
+        read_all()                               # D2H of step s's results (u64 histograms + stats)
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = F * natoms * 12 + F * 36 + F * 72
-    d2h = (ctx.acc_size(acc) + lib.STAT_NSLOTS) * 8
+    d2h = sum((ctx.acc_size(a_) + lib.STAT_NSLOTS) * 8 for a_ in accs)
 
     # ---- the single collective: merge rank-private histograms ------------------------------------------------
     t0 = time.perf_counter()
-    b2d.allreduce_accumulator(ctx, acc)
+    for a_ in accs:
+        b2d.allreduce_accumulator(ctx, a_)
     allreduce_ms = 1e3 * (time.perf_counter() - t0)
-    merged, mstats = ctx.read(acc, ncounters)
+    merged_sum, mstats = read_all()
+    mstats[lib.STAT_FRAMES] = mstats[lib.STAT_FRAMES] // len(accs)          # every accumulator saw every frame
 
     # ---- max over ranks -----------------------------------------------------------------------------------------
     red = torch.tensor([tot_ms, e2e_s, evaluated_pairs], dtype=torch.float64, device=f"cuda:{local}")
@@ -377,15 +416,15 @@ def main():
             "metric": "rdf_pair_distances_per_s", "value": value, "unit": "pair-distances/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "frames_per_s": value / (wl.n0 * wl.n1),
+            "frames_per_s": value / wl.pairs_per_frame,
             "evaluated_pairs_per_s": evaluated_all / (tot_ms_max * 1e-3),
             "config": {"workload": wl.text, "frames_per_step_per_gpu": F, "parallelism": f"frame-sharded x{world}",
-                       "l2": "flushed between timed steps (256 MiB write)", "symmetric_i_lt_j": bool(args.symmetric) and wl.same,
+                       "l2": "flushed between timed steps (256 MiB write)", "symmetric_i_lt_j": bool(args.symmetric) and wl.same, "group_pairs": len(accs),
                        "pairs": "value counts reference-equivalent ordered pairs (N0*N1 per frame); roofline counts only evaluated pairs"},
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
                        "samples": clocks.get("samples"), "power_w_max": clocks.get("power_w_max")},
             "e2e": {"value": e2e_value, "unit": "pair-distances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_s": e2e_value / (wl.n0 * wl.n1), "ms_per_step": 1e3 * e2e_s_max / args.steps},
+                    "frames_per_s": e2e_value / wl.pairs_per_frame, "ms_per_step": 1e3 * e2e_s_max / args.steps},
             "gpu_launches": int(sum(n for k, (t, n) in timing.items() if k in ("k1_centers", "k3_rdf")) + 2 * prep_n + args.steps),
             "roofline": {"bound": "fp32_issue", "kernel": "k3_rdf", "achieved": achieved_inst / 1e12, "peak": peak_inst / 1e12,
                          "unit": "Tinst/s", "frac": achieved_inst / peak_inst if peak_inst else None,
@@ -397,17 +436,17 @@ def main():
             "kernel_ms": {"k1_centers": k1_ms / max(args.steps, 1), "k3_prep": prep_ms / max(args.steps, 1),
                           "k3_rdf": k3_ms / max(args.steps, 1)},
             "allreduce_ms": allreduce_ms,
-            "check": {"counted_pairs_merged": int(merged.sum()), "fp64_reevaluated": int(mstats[lib.STAT_EXACT]),
+            "check": {"counted_pairs_merged": int(merged_sum), "fp64_reevaluated": int(mstats[lib.STAT_EXACT]),
                       "dropped_oob": int(mstats[lib.STAT_DROPPED]), "frames_merged": int(mstats[lib.STAT_FRAMES])},
         }
         if world == 1 and not args.no_cpu_baseline:
             with tempfile.TemporaryDirectory() as td:
-                n_cpu = min(args.cpu_sample, wl.n0)
+                n_cpu = max(1, min(args.cpu_sample, wl.n0, int(6.0e8 // wl.n1)))    # ~10 s of one core
                 rate, kind, dt = cpu_reference_sample(wl, n_cpu, td, xh.numpy()[0])
             line["cpu_baseline"] = {"value": rate, "unit": "pair-distances/s", "cores": 1, "kind": kind,
                                     "sample": f"{n_cpu} of {wl.n0} i-molecules x all {wl.n1} j-molecules of one frame "
                                               f"({dt:.1f} s, whole-process wall time)", "host_cpus": os.cpu_count(),
-                                    "frames_per_s": rate / (wl.n0 * wl.n1)}
+                                    "frames_per_s": rate / wl.pairs_per_frame}
         print(json.dumps(line))
     ctx.close()
     if world > 1:
