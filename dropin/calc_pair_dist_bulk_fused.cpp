@@ -27,19 +27,13 @@ gmx_main(temp)
     b2a_coord_spec spec{};
     spec.grp0 = 0; spec.grp1 = 1; spec.com0 = spec.com1 = NCM; spec.Rmin = Rmin; spec.dim = dim; spec.low = lowPos; spec.up = upPos;
     spec.use_cyl = 0; spec.max_count = max_count;
-    int acc = -1;
-    itp::b2a_detail::check(b2a_coord_create(hd.b2aContext(), &spec, &acc));
+    const int acc = hd.b2aCoord(spec);
 
-    std::vector<double>   totPair(max_count, 0.0);
-    std::vector<uint32_t> table, numA;
+    std::vector<double> totPair(max_count, 0.0);
     do
     {
         hd.b2aAccumulate(acc);
-        const int nf = hd.b2aBatchFrames();
-        table.resize((size_t)nf * max_count);
-        numA.resize(nf);
-        itp::b2a_detail::check(b2a_coord_read_frames(hd.b2aContext(), acc, table.data(), numA.data()));
-        itp::b2a_detail::check(b2a_coord_fold(table.data(), numA.data(), nf, max_count, totPair.data()));
+        hd.b2aCoordFold(acc, max_count, totPair);   // per-frame tables of this batch, folded in frame order
     } while (hd.b2aReadNextBatch());
 
     double totol = 0;

@@ -53,6 +53,10 @@ namespace itp
         int  b2aDensity(const b2a_density_spec& s);
         int  b2aRdf(const b2a_rdf_spec& s, bool symmetric = true);
         int  b2aOrient(const b2a_orient_spec& s);
+        int  b2aCoord(const b2a_coord_spec& s);                    // coordination numbers (mofs/calc_pair_dist*.cpp)
+        // after b2aAccumulate(acc) of a coordination accumulator: totPair[k] += tmpPair[k] / numA for every frame of the batch, in
+        // frame order (calc_pair_dist_bulk.cpp:89-92); totPair must hold spec.max_count doubles
+        void b2aCoordFold(int acc, int max_count, std::vector<double>& totPair);
         void b2aAccumulate(int acc);                               // whole resident batch, once per batch
         void b2aRead(int acc, std::vector<uint64_t>& counts, uint64_t* stats = nullptr);
 

@@ -327,6 +327,23 @@ namespace itp
         return acc;
     }
 
+    inline int GmxHandle::b2aCoord(const b2a_coord_spec& s)
+    {
+        b2aEnsure();
+        int acc = -1;
+        b2a_detail::check(b2a_coord_create(batch_.ctx(), &s, &acc));
+        return acc;
+    }
+
+    inline void GmxHandle::b2aCoordFold(int acc, int max_count, std::vector<double>& totPair)
+    {
+        const int nf = batch_.frames();
+        std::vector<uint32_t> table((size_t)nf * max_count), numA(nf);
+        totPair.resize(max_count, 0.0);
+        b2a_detail::check(b2a_coord_read_frames(batch_.ctx(), acc, table.data(), numA.data()));
+        b2a_detail::check(b2a_coord_fold(table.data(), numA.data(), nf, max_count, totPair.data()));
+    }
+
     inline void GmxHandle::b2aAccumulate(int acc) { b2a_detail::check(b2a_accumulate(batch_.ctx(), acc)); }
 
     inline void GmxHandle::b2aRead(int acc, std::vector<uint64_t>& counts, uint64_t* stats)
