@@ -101,6 +101,21 @@ struct Group
     uint64_t valid[4]   = { 0, 0, 0, 0 };   // batch serial the cache belongs to
 };
 
+// One group's molecules counting-sorted by cell (K3 cell mode), shared by every accumulator of the same batch that needs the
+// same sort: a sweep over all pairs of G groups sorts each group once (per slab signature), not once per pair.
+struct CellSort
+{
+    int      grp = -1, com = 0, bits = 0, with_slab = 0, nbin = 0, dim = 0, dim2 = 0;
+    double   low = 0, up = 0, low2 = 0, up2 = 0;     // slab signature (only when with_slab)
+    uint64_t serial = 0;                             // batch serial the arrays were built from (0: never)
+    int*      keys   = nullptr;                      // [maxK][n]
+    unsigned* cells  = nullptr;                      // [3][maxK][nkeys + 1]: counts, starts, cursors
+    int4*     sorted = nullptr;                      // [maxK][n]
+    size_t    cap_n = 0;
+    unsigned  cap_keys = 0, nkeys = 0;
+    unsigned* starts(int maxK) const { return cells + (size_t)(nkeys + 1) * maxK; }
+};
+
 enum AccKind { ACC_DENSITY, ACC_RDF, ACC_ORIENT, ACC_COORD };
 
 struct Acc
@@ -117,6 +132,7 @@ struct Acc
     int*      d_slab_id = nullptr;
     unsigned* d_slab_cnt = nullptr;   // [maxK][nslab] counts then [maxK][nslab] cursors
     int4*     d_sortedA = nullptr;
+    int4*     sortedA_view = nullptr;   // what the next k3_rdf launch reads: d_sortedA (slab sort) or a shared CellSort array
     RdfFrame* d_frames = nullptr;
     RdfFrame* h_frames = nullptr;     // pinned
     int       symmetric = 0, paranoid = 0, cells = -1;   // cells: -1 auto, 0 never, 1 whenever it culls anything
@@ -169,6 +185,7 @@ struct b2a_ctx
     int          sm_count = 148;
     std::map<int, Group> groups;
     std::vector<std::unique_ptr<Acc>> accs;
+    std::vector<std::unique_ptr<CellSort>> cell_sorts;
     double*      d_pos_scratch = nullptr;
     unsigned*    d_work = nullptr;   // work-item counter of the persistent streaming kernels
     // velocities / forces of the current batch (fr->v, fr->f), uploaded on demand; [0] is unused (x lives in d_x)
@@ -277,6 +294,7 @@ extern "C" void b2a_destroy(b2a_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& kv : c->groups) free_group(kv.second);
     for (auto& a : c->accs) if (a) free_acc(*a);
+    for (auto& cs : c->cell_sorts) { cudaFree(cs->keys); cudaFree(cs->cells); cudaFree(cs->sorted); }
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_work);
     cudaFree(c->d_field[1]); cudaFree(c->d_field[2]); cudaFree(c->d_field_cen);
@@ -331,6 +349,7 @@ extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int
     CU(cudaStreamSynchronize(c->stream));
     Group& g = c->groups[grp];
     free_group(g);
+    for (auto& e : c->cell_sorts) if (e->grp == grp) e->serial = 0;   // sorted views of the old group are stale
     g.ngx = ngx; g.napm = napm; g.nmol = nmol;
     g.h_index.assign(index, index + ngx);
     g.contiguous = true;
@@ -384,6 +403,7 @@ extern "C" int b2a_set_group_full(b2a_ctx* c, int grp, const int* index, int ngx
     CU(cudaStreamSynchronize(c->stream));
     Group& g = c->groups[grp];
     free_group(g);
+    for (auto& e : c->cell_sorts) if (e->grp == grp) e->serial = 0;   // sorted views of the old group are stale
     g.ngx = ngx; g.napm = 0; g.nmol = nmol; g.csr = true; g.max_napm = maxn;
     g.h_index.assign(index, index + ngx);
     CU(cudaMalloc(&g.d_index, sizeof(int) * ngx));
@@ -429,6 +449,7 @@ extern "C" int b2a_set_group_wsum(b2a_ctx* c, int grp, int com, double wsum)
     if (int rc = get_group(c, grp, &g)) return rc;
     g->wsum[com]  = wsum;
     g->valid[com] = 0;
+    for (auto& e : c->cell_sorts) if (e->grp == grp) e->serial = 0;
     return B2A_OK;
 }
 
@@ -888,7 +909,7 @@ static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p,
 {
     auto kern = k3_rdf<IPT, THREADS, true, CUBIC, PARANOID, MODE>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, THREADS, smem, c->stream>>>(a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
+    kern<<<grid, THREADS, smem, c->stream>>>(a.sortedA_view ? a.sortedA_view : a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
                                             a.d_slab_cnt, a.d_frames, p, cd, a.d_hist, a.d_hist + a.ndev);
     CU(cudaGetLastError());
     return B2A_OK;
@@ -975,6 +996,56 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
     return true;
 }
 
+// Sorted-by-cell view of one group for the current batch, built on first use and shared afterwards (see CellSort).  `slab` is
+// the accumulator whose slab ids enter the key (its k3_slab_count has been queued), or nullptr for a plain cell sort.
+static int cell_sort(b2a_ctx* c, int grp, Group& g, int com, int bits, const Acc* slab, const RdfDev& p, CellSort** out)
+{
+    const int      n     = g.nmol;
+    const unsigned nkeys = (slab ? (unsigned)p.nslab : 1u) << (3 * bits);
+    CellSort*      cs    = nullptr;
+    for (auto& e : c->cell_sorts)
+    {
+        if (e->grp != grp || e->com != com || e->bits != bits || e->with_slab != (slab ? 1 : 0)) continue;
+        if (slab && !(e->nbin == p.nbin && e->dim == p.dim && e->dim2 == p.dim2 && e->low == p.low && e->up == p.up && e->low2 == p.low2 && e->up2 == p.up2))
+            continue;
+        cs = e.get();
+        break;
+    }
+    if (!cs)
+    {
+        c->cell_sorts.emplace_back(new CellSort);
+        cs = c->cell_sorts.back().get();
+        cs->grp = grp; cs->com = com; cs->bits = bits; cs->with_slab = slab ? 1 : 0;
+        if (slab) { cs->nbin = p.nbin; cs->dim = p.dim; cs->dim2 = p.dim2; cs->low = p.low; cs->up = p.up; cs->low2 = p.low2; cs->up2 = p.up2; }
+    }
+    *out = cs;
+    if ((size_t)n > cs->cap_n)
+    {
+        cudaFree(cs->keys); cudaFree(cs->sorted); cs->keys = nullptr; cs->sorted = nullptr; cs->cap_n = 0; cs->serial = 0;
+        CU(cudaMalloc(&cs->keys, sizeof(int) * (size_t)n * c->maxK));
+        CU(cudaMalloc(&cs->sorted, sizeof(int4) * (size_t)n * c->maxK));
+        cs->cap_n = (size_t)n;
+    }
+    if (nkeys > cs->cap_keys)
+    {
+        cudaFree(cs->cells); cs->cells = nullptr; cs->cap_keys = 0; cs->serial = 0;
+        CU(cudaMalloc(&cs->cells, sizeof(unsigned) * 3 * (size_t)(nkeys + 1) * c->maxK));
+        cs->cap_keys = nkeys;
+    }
+    if (cs->serial == c->serial && cs->nkeys == nkeys) return B2A_OK;   // built for this batch already
+    cs->nkeys = nkeys;
+    const size_t sz = (size_t)(nkeys + 1) * c->maxK;
+    unsigned *cnt = cs->cells, *st = cs->cells + sz, *cur = cs->cells + 2 * sz;
+    CU(cudaMemsetAsync(cs->cells, 0, sizeof(unsigned) * 3 * sz, c->stream));
+    dim3 grid((n + 255) / 256, c->nframes);
+    k3_cell_keys<<<grid, 256, 0, c->stream>>>(g.d_fix[com], slab ? slab->d_slab_id : nullptr, c->nframes, n, bits, nkeys, cs->keys, cnt);
+    k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cnt, nkeys, st);
+    k3_cell_scatter<<<grid, 256, 0, c->stream>>>(g.d_fix[com], cs->keys, c->nframes, n, nkeys, st, cur, cs->sorted);
+    CU(cudaGetLastError());
+    cs->serial = c->serial;
+    return B2A_OK;
+}
+
 static int accumulate_rdf(b2a_ctx* c, Acc& a)
 {
     const b2a_rdf_spec& s = a.rdf;
@@ -1050,6 +1121,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         dim3 grid((p.n0 + 255) / 256, c->nframes);
         k3_slab_count<<<grid, 256, sizeof(unsigned) * nslab, c->stream>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
         CU(cudaGetLastError());
+        a.sortedA_view = nullptr;
         if (!cells)
         {
             k3_slab_scatter<<<grid, 256, sizeof(unsigned) * 3 * nslab, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
@@ -1058,27 +1130,15 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         }
         else
         {
-            const unsigned nkA = (unsigned)nslab << (3 * bits), nkB = 1u << (3 * bits);
-            if (!a.d_keysA) CU(cudaMalloc(&a.d_keysA, sizeof(int) * (size_t)p.n0 * c->maxK));
-            if (!a.d_keysB) CU(cudaMalloc(&a.d_keysB, sizeof(int) * (size_t)p.n1 * c->maxK));
-            if (!a.d_sortedB) CU(cudaMalloc(&a.d_sortedB, sizeof(int4) * (size_t)p.n1 * c->maxK));
-            if (a.cap_keysA < nkA) { cudaFree(a.d_cellA); a.d_cellA = nullptr; CU(cudaMalloc(&a.d_cellA, sizeof(unsigned) * 3 * (size_t)(nkA + 1) * c->maxK)); a.cap_keysA = nkA; }
-            if (a.cap_keysB < nkB) { cudaFree(a.d_cellB); a.d_cellB = nullptr; CU(cudaMalloc(&a.d_cellB, sizeof(unsigned) * 3 * (size_t)(nkB + 1) * c->maxK)); a.cap_keysB = nkB; }
-            const size_t szA = (size_t)(nkA + 1) * c->maxK, szB = (size_t)(nkB + 1) * c->maxK;
-            unsigned *cntA = a.d_cellA, *stA = a.d_cellA + szA, *curA = a.d_cellA + 2 * szA;
-            unsigned *cntB = a.d_cellB, *stB = a.d_cellB + szB, *curB = a.d_cellB + 2 * szB;
-            CU(cudaMemsetAsync(a.d_cellA, 0, sizeof(unsigned) * 3 * szA, c->stream));
-            CU(cudaMemsetAsync(a.d_cellB, 0, sizeof(unsigned) * 3 * szB, c->stream));
-            dim3 gridB((p.n1 + 255) / 256, c->nframes);
-            k3_cell_keys<<<grid, 256, 0, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, bits, nkA, a.d_keysA, cntA);
-            k3_cell_keys<<<gridB, 256, 0, c->stream>>>(g1->d_fix[s.com1], nullptr, c->nframes, p.n1, bits, nkB, a.d_keysB, cntB);
-            k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cntA, nkA, stA);
-            k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cntB, nkB, stB);
-            k3_cell_scatter<<<grid, 256, 0, c->stream>>>(g0->d_fix[s.com0], a.d_keysA, c->nframes, p.n0, nkA, stA, curA, a.d_sortedA);
-            k3_cell_scatter<<<gridB, 256, 0, c->stream>>>(g1->d_fix[s.com1], a.d_keysB, c->nframes, p.n1, nkB, stB, curB, a.d_sortedB);
-            CU(cudaGetLastError());
+            // both groups sorted by cell: shared with the other accumulators of this batch (cell_sort)
+            CellSort *sA = nullptr, *sB = nullptr;
+            if (int rc = cell_sort(c, s.grp0, *g0, s.com0, bits, &a, p, &sA)) return rc;
+            if (int rc = cell_sort(c, s.grp1, *g1, s.com1, bits, nullptr, p, &sB)) return rc;
+            const unsigned  nkA = sA->nkeys, nkB = sB->nkeys;
+            const unsigned *stA = sA->starts(c->maxK), *stB = sB->starts(c->maxK);
+            a.sortedA_view = sA->sorted;
             cd.bits = bits; cd.rx = reach[0]; cd.ry = reach[1]; cd.rz = reach[2];
-            cd.nkeysA = nkA; cd.nkeysB = nkB; cd.startA = stA; cd.startB = stB; cd.sortedB = a.d_sortedB;
+            cd.nkeysA = nkA; cd.nkeysB = nkB; cd.startA = stA; cd.startB = stB; cd.sortedB = sB->sorted;
         }
     }
 
