@@ -1,4 +1,4 @@
-"""Definitions of the golden-fixture cases, shared by tools/make_golden.py (which asks the REFERENCE for the
+"""Definitions of the golden-fixture cases, shared by tests/make_golden.py (which asks the REFERENCE for the
 answers) and the tests (which ask the oracle / the GPU path).  Inputs are regenerated from seeds by the
 deterministic synthetic generator, so only the reference's outputs are committed."""
 import numpy as np

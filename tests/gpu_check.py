@@ -1,5 +1,5 @@
 """Quick GPU bring-up: parity of every kernel against the oracle on small systems, then C2-size timing.
-Run under gpurun:  python tools/gpu_check.py [--big]"""
+Run under gpurun:  python tests/gpu_check.py [--big]"""
 import os
 import sys
 import time

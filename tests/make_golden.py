@@ -2,7 +2,7 @@
 analysis programs compiled unmodified from /root/reference against gmxstub).  Runs only in the dev container;
 the fixtures are committed and are what pins the oracle on boxes without /root/reference.
 
-    python tools/make_golden.py
+    python tests/make_golden.py
 """
 import os
 import sys

@@ -1,4 +1,4 @@
-"""Helpers shared by the oracle-pinning tests and tools/make_golden.py: run a reference program from
+"""Helpers shared by the oracle-pinning tests and tests/make_golden.py: run a reference program from
 oracle/_ref on a synthetic system and reproduce its output text from oracle.port results."""
 from __future__ import annotations
 

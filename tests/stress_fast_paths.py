@@ -4,7 +4,7 @@ with atoms pushed across box faces and whole boxes away, random filters, bins an
 mode 0 (literal FP64), 1 (bracket + queue) and 2 (validation: both, counting FP32-proven answers the FP64 code contradicts).
 Pass = identical histograms and statistics in all three modes and zero contradictions.  One line per case, summary at the end.
 
-    python tools/stress_fast_paths.py [--cases 60] [--seed 1]
+    python tests/stress_fast_paths.py [--cases 60] [--seed 1]
 """
 import argparse
 import os
@@ -17,11 +17,11 @@ sys.path.insert(0, ROOT)
 from gmx2020postanalysis_b200 import lib, synth  # noqa: E402
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=60)
     ap.add_argument("--seed", type=int, default=1)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     rng = np.random.default_rng(a.seed)
     bad = 0
     for case in range(a.cases):

@@ -4,7 +4,7 @@ that are not one contiguous run), random masses / charges, cubic and elongated b
 away; centres for com 0 / 1 / 2 over the whole batch and unwrapped positions of one frame must equal the oracle's doubles bit for
 bit.  One line per case.
 
-    python tools/stress_loaders.py [--cases 60] [--seed 1]
+    python tests/stress_loaders.py [--cases 60] [--seed 1]
 """
 import argparse
 import os
@@ -18,11 +18,11 @@ from gmx2020postanalysis_b200 import lib, synth  # noqa: E402
 from oracle import port  # noqa: E402
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=60)
     ap.add_argument("--seed", type=int, default=1)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     rng = np.random.default_rng(a.seed)
     bad = 0
     for case in range(a.cases):

@@ -3,7 +3,7 @@
 symmetric evaluation.  The paranoid kernel is the reference's arithmetic (pinned against the oracle in tests/); this tool widens
 the input space far beyond the fixtures.  One line per case.
 
-    python tools/stress_rdf.py [--cases 40] [--seed 1]
+    python tests/stress_rdf.py [--cases 40] [--seed 1]
 """
 import argparse
 import os
@@ -18,11 +18,11 @@ import refprog  # noqa: E402
 from gmx2020postanalysis_b200 import lib, synth  # noqa: E402
 
 
-def main():
+def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=1)
-    a = ap.parse_args()
+    a = ap.parse_args(argv)
     rng = np.random.default_rng(a.seed)
     bad = 0
     for case in range(a.cases):

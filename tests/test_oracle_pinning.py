@@ -1,6 +1,6 @@
 """The oracle (oracle/port/oracle.c) against the REFERENCE: (1) live, where oracle/_ref exists -- the
 reference's own loaders and programs compiled unmodified; (2) always, against the committed fixtures under
-tests/golden/ that tools/make_golden.py produced from (1)."""
+tests/golden/ that tests/make_golden.py produced from (1)."""
 import os
 
 import numpy as np
