@@ -58,6 +58,21 @@ def test_other_fused_ports_match_reference_output(name, exe, batch, tmp_path, mo
     assert got == _golden(name)
 
 
+def test_density_slit_fused_port_matches_reference_build(tmp_path, monkeypatch):
+    """general/density_slit_jhl.cpp ported to K2 (both region tests inclusive, second filter dimension, volume normalisation) against
+    the reference build of the original on the same trajectory."""
+    from gmx2020postanalysis_b200 import synth
+    exe = "density_slit_jhl"
+    if not refprog.have_ref(exe) or not os.path.exists(os.path.join(DROPIN, exe + "_fused")):
+        pytest.skip("binaries not built (needs /root/reference at build time)")
+    monkeypatch.setenv("B2A_BATCH", "4")
+    system = synth.water_box(2500, 4.2, seed=79)
+    args = ["-nbin1", 60, "-dim1", 2, "-dim2", 0, "-low1", 0.3, "-up1", 3.9, "-low2", 0.5, "-up2", 3.7, "-yy", 4.2]
+    ref = refprog.run_program(os.path.join(refprog.REFDIR, exe), str(tmp_path / "ref"), system, 9, ["SOL"], args, "o.xvg")
+    got = refprog.run_program(os.path.join(DROPIN, exe + "_fused"), str(tmp_path / "new"), system, 9, ["SOL"], args, "o.xvg")
+    assert len(ref) == 60 and got == ref and any(float(ln.split()[1]) > 0 for ln in ref)
+
+
 def test_live_reference_vs_dropin_other_programs(tmp_path):
     """Programs without a golden file: run both builds here and compare (only where oracle/_ref travelled)."""
     from gmx2020postanalysis_b200 import synth
