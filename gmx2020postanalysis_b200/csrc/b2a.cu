@@ -116,7 +116,7 @@ struct CellSort
     unsigned* starts(int maxK) const { return cells + (size_t)(nkeys + 1) * maxK; }
 };
 
-enum AccKind { ACC_DENSITY, ACC_RDF, ACC_ORIENT, ACC_COORD };
+enum AccKind { ACC_DENSITY, ACC_RDF, ACC_ORIENT, ACC_COORD, ACC_REGION };
 
 struct Acc
 {
@@ -125,6 +125,7 @@ struct Acc
     b2a_rdf_spec       rdf{};
     b2a_orient_spec    ori{};
     b2a_coord_spec     coord{};
+    b2a_region_spec    region{};
     size_t             ncounters = 0;       // public counters (reference layout size)
     size_t             ndev      = 0;       // device u64 words before the stats block
     unsigned long long* d_hist   = nullptr; // [ndev + NSLOTS]
@@ -846,6 +847,30 @@ extern "C" int b2a_density_create(b2a_ctx* c, const b2a_density_spec* s, int* id
     return new_acc(c, std::move(a), id);
 }
 
+extern "C" int b2a_region_create(b2a_ctx* c, const b2a_region_spec* s, int* id)
+{
+    if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_region_create: null argument");
+    Group* g;
+    if (int rc = get_group(c, s->grp, &g)) return rc;
+    if (s->com < 0 || s->com > 3) return fail(B2A_ERR_ARG, "com(%d) out of range", s->com);
+    if (s->nfilter < 0 || s->nfilter > 3 || s->nbdim < 0 || s->nbdim > 2) return fail(B2A_ERR_ARG, "b2a_region_create: 0..3 filters and 0..2 binned dimensions");
+    for (int q = 0; q < s->nfilter; ++q)
+        if (s->fdim[q] < 0 || s->fdim[q] > 2) return fail(B2A_ERR_ARG, "b2a_region_create: filter dimension out of range");
+    size_t n = 1;
+    for (int b = 0; b < s->nbdim; ++b)
+    {
+        if (s->bdim[b] < 0 || s->bdim[b] > 2 || s->nb[b] <= 0 || !(s->dbin[b] > 0)) return fail(B2A_ERR_ARG, "b2a_region_create: bad binned dimension %d", b);
+        n *= (size_t)s->nb[b];
+    }
+    if (n > ((size_t)1 << 28)) return fail(B2A_ERR_UNSUPPORTED, "b2a_region_create: %zu counters", n);
+    CU(cudaSetDevice(c->device));
+    std::unique_ptr<Acc> a(new Acc);
+    a->kind   = ACC_REGION;
+    a->region = *s;
+    a->ncounters = a->ndev = n;
+    return new_acc(c, std::move(a), id);
+}
+
 extern "C" int b2a_rdf_create(b2a_ctx* c, const b2a_rdf_spec* s, int* id)
 {
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_rdf_create: null argument");
@@ -1185,6 +1210,24 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     return B2A_OK;
 }
 
+static int accumulate_region(b2a_ctx* c, Acc& a)
+{
+    const b2a_region_spec& s = a.region;
+    Group* g;
+    if (int rc = get_group(c, s.grp, &g)) return rc;
+    if (int rc = ensure_centers(c, *g, s.com, false)) return rc;   // K1: exact FP64 centres, cached for the batch
+    RegionDev d{};
+    d.nfilter = s.nfilter; d.wrap = s.wrap; d.cyl = s.cyl; d.nbdim = s.nbdim;
+    for (int q = 0; q < 3; ++q) { d.fdim[q] = s.fdim[q]; d.fincl[q] = s.fincl[q]; d.flow[q] = s.flow[q]; d.fup[q] = s.fup[q]; }
+    d.cx = (double)s.cx; d.cy = (double)s.cy; d.R2 = s.R2;
+    for (int b = 0; b < 2; ++b) { d.bdim[b] = s.bdim[b]; d.nb[b] = s.nb[b]; d.blow[b] = (double)s.blow[b]; d.dbin[b] = s.dbin[b]; }
+    Timed tm(c, 3);
+    dim3  grid((g->nmol + 255) / 256, c->nframes);
+    k2g_region<<<grid, 256, 0, c->stream>>>(g->d_cen[s.com], c->nframes, g->nmol, d, c->d_geom, a.d_hist, a.d_hist + a.ndev);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
 static int accumulate_density(b2a_ctx* c, Acc& a)
 {
     const b2a_density_spec& s = a.den;
@@ -1242,6 +1285,7 @@ extern "C" int b2a_accumulate(b2a_ctx* c, int id)
         case ACC_RDF: rc = accumulate_rdf(c, *a); break;
         case ACC_ORIENT: rc = accumulate_orient(c, *a); break;
         case ACC_COORD: rc = accumulate_coord(c, *a); break;
+        case ACC_REGION: rc = accumulate_region(c, *a); break;
     }
     if (rc) return rc;
     k_add_frames<<<1, 1, 0, c->stream>>>(a->d_hist + a->ndev, (unsigned long long)c->nframes);

@@ -377,6 +377,73 @@ __global__ void __launch_bounds__(256) k2_density_from_centers(const double* __r
     atomicAdd(&hist[me], 1ull);
 }
 
+// ---- general region counter / histogram over materialised centres (b2a_region_spec) -----------------------------------------
+struct RegionDev
+{
+    int    nfilter, fdim[3], fincl[3], wrap, cyl, nbdim, bdim[2], nb[2];
+    float  flow[3], fup[3];
+    double cx, cy, R2, blow[2], dbin[2];
+};
+
+__global__ void __launch_bounds__(256) k2g_region(const double* __restrict__ cen, int nframes, int nmol, RegionDev d,
+                                                  const FrameGeom* __restrict__ geom, unsigned long long* __restrict__ hist,
+                                                  unsigned long long* __restrict__ stats)
+{
+    const int  f  = blockIdx.y;
+    const int  i  = blockIdx.x * blockDim.x + threadIdx.x;
+    bool       ok = i < nmol && f < nframes;
+    long long  cell = 0;
+    bool       oob  = false;
+    if (ok)
+    {
+        const double* c0 = cen + (size_t)f * 3 * nmol;
+        for (int q = 0; q < d.nfilter && ok; ++q)
+        {
+            const double p = c0[(size_t)d.fdim[q] * nmol + i];
+            if (d.wrap)
+            {
+                // calc_numdens_pore.cpp:15-22: `real tmp` wrapped with the double box length, bounds compared in float
+                const double L = geom[f].L[d.fdim[q]];
+                float        t = (float)p;
+                while ((double)t > L) t = (float)__dsub_rn((double)t, L);
+                while (t < 0.f) t = (float)__dadd_rn((double)t, L);
+                ok = (d.flow[q] <= t) && (d.fincl[q] ? (t <= d.fup[q]) : (t < d.fup[q]));
+            }
+            else
+                ok = ((double)d.flow[q] <= p) && (d.fincl[q] ? (p <= (double)d.fup[q]) : (p < (double)d.fup[q]));
+        }
+        if (ok && d.cyl)
+        {
+            const double dx = __dsub_rn(c0[i], d.cx), dy = __dsub_rn(c0[(size_t)nmol + i], d.cy);
+            ok              = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= d.R2;     // std::pow(v, 2) is v * v, correctly rounded
+        }
+        if (ok)
+        {
+            long long stride = 1;
+            for (int b = 0; b < d.nbdim; ++b)
+            {
+                const double p  = c0[(size_t)d.bdim[b] * nmol + i];
+                const double q  = __ddiv_rn(__dsub_rn(p, d.blow[b]), d.dbin[b]);
+                const int    me = (q >= -2.0e9 && q <= 2.0e9) ? __double2int_rz(q) : -1;
+                if (me < 0 || me >= d.nb[b]) oob = true;     // the reference indexes outside its array here
+                cell += (long long)me * stride;
+                stride *= d.nb[b];
+            }
+        }
+    }
+    // one counter (nbdim == 0): count per warp, one atomic per warp
+    if (d.nbdim == 0)
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0 && m) { atomicAdd(&hist[0], (unsigned long long)__popc(m)); atomicAdd(&stats[4], (unsigned long long)__popc(m)); }
+        return;
+    }
+    if (!ok) return;
+    atomicAdd(&stats[4], 1ull);
+    if (oob) { atomicAdd(&stats[1], 1ull); return; }
+    atomicAdd(&hist[cell], 1ull);
+}
+
 // grid: x = molecule block, y = frame group.  A thread owns ONE molecule and walks the frames of its group.
 constexpr int kFramesPerBlock = 8;
 

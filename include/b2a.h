@@ -130,6 +130,31 @@ typedef struct b2a_density_spec
     float  low2, up2;
 } b2a_density_spec;
 
+/* General region counter / histogram over molecule centres: the remaining members of the density family.
+ *   mofs/calc_density_distribution_in_pore.cpp:47-60  z profile inside a cylinder: one half-open filter, `cyl`, one binned dimension
+ *   mofs/calc_areaDensityDistributionPore.cpp:56-68   2-D map: three half-open filters, two binned dimensions (dens(me1, me2))
+ *   mofs/calc_numdens_pore.cpp:12-27, 72-80           molecules inside a box after wrapping into [0, L]: `wrap`, three filters, no bins
+ * All arithmetic is the programs': doubles for the centre, the program's `real` bounds widened in the comparison, truncation of
+ * (p - low) / dbin.  Counters: me0 + me1 * nb[0] (Eigen column-major), or one counter when nbdim == 0.                            */
+typedef struct b2a_region_spec
+{
+    int    grp, com;
+    int    nfilter;            /* 0..3 region tests, all must pass: low <= p < up, or p <= up where fincl */
+    int    fdim[3];
+    float  flow[3], fup[3];
+    int    fincl[3];
+    int    wrap;               /* calc_numdens_pore.cpp:15-20: p is first cast to float and moved into [0, L] by repeated -+L (float
+                                  variable, double box length), and the bounds are compared in float                               */
+    int    cyl;                /* calc_density_distribution_in_pore.cpp:52-53: pow(x - cx, 2) + pow(y - cy, 2) <= R2 (x = dim 0, y = dim 1) */
+    float  cx, cy;
+    double R2;                 /* as the program computes it: double(Rmof) * Rmof                                                    */
+    int    nbdim;              /* 0, 1 or 2 binned dimensions */
+    int    bdim[2];
+    float  blow[2];
+    double dbin[2];            /* bin widths as the program holds them (a `real` widened, or a double)                               */
+    int    nb[2];
+} b2a_region_spec;
+
 typedef struct b2a_rdf_spec
 {
     int   grp0, grp1;        /* i runs over grp0, j over grp1 (calc_rdf_region.cpp:73,79) */
@@ -183,6 +208,7 @@ enum {
 };
 
 int b2a_density_create(b2a_ctx* ctx, const b2a_density_spec* spec, int* acc);
+int b2a_region_create(b2a_ctx* ctx, const b2a_region_spec* spec, int* acc);
 int b2a_rdf_create(b2a_ctx* ctx, const b2a_rdf_spec* spec, int* acc);
 int b2a_orient_create(b2a_ctx* ctx, const b2a_orient_spec* spec, int* acc);
 

@@ -51,6 +51,7 @@ namespace itp
         int  b2aBatchFrames() const { return batch_.frames(); }          // frames in the resident batch
         bool b2aReadNextBatch();                                   // skip to the first frame of the next batch
         int  b2aDensity(const b2a_density_spec& s);
+        int  b2aRegion(const b2a_region_spec& s);                  // filters / cylinder / wrap + 0..2 binned dimensions
         int  b2aRdf(const b2a_rdf_spec& s, bool symmetric = true);
         int  b2aOrient(const b2a_orient_spec& s);
         int  b2aCoord(const b2a_coord_spec& s);                    // coordination numbers (mofs/calc_pair_dist*.cpp)

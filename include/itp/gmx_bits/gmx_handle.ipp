@@ -310,6 +310,14 @@ namespace itp
         return acc;
     }
 
+    inline int GmxHandle::b2aRegion(const b2a_region_spec& s)
+    {
+        b2aEnsure();
+        int acc = -1;
+        b2a_detail::check(b2a_region_create(batch_.ctx(), &s, &acc));
+        return acc;
+    }
+
     inline int GmxHandle::b2aRdf(const b2a_rdf_spec& s, bool symmetric)
     {
         b2aEnsure();

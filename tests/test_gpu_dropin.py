@@ -73,6 +73,23 @@ def test_density_slit_fused_port_matches_reference_build(tmp_path, monkeypatch):
     assert len(ref) == 60 and got == ref and any(float(ln.split()[1]) > 0 for ln in ref)
 
 
+@pytest.mark.parametrize("name", ["calc_density_distribution_in_pore", "calc_areaDensityDistributionPore", "calc_numdens_pore"])
+@pytest.mark.parametrize("batch", ["16", "4"])
+def test_region_fused_ports_match_reference_builds(name, batch, tmp_path, monkeypatch):
+    """The rest of the density family (z profile inside a cylinder, 2-D map behind three region tests, wrapped box count) ported to
+    the general region accumulator: same files as the reference builds of the originals, on the sweep's trajectory and arguments."""
+    ref_exe, new_exe = os.path.join(refprog.REFDIR, name), os.path.join(DROPIN, name + "_fused")
+    if not (refprog.have_ref(name) and os.path.exists(new_exe)):
+        pytest.skip("binaries not built (needs /root/reference at build time)")
+    monkeypatch.setenv("B2A_BATCH", batch)
+    st_ref, ref = SW.run(ref_exe, str(tmp_path / "ref"), name)
+    st_new, new = SW.run(new_exe, str(tmp_path / "new"), name)
+    assert st_ref == "ok" and st_new == "ok", (ref, new)
+    assert sorted(new) == sorted(ref) and all(new[fn] == ref[fn] for fn in ref)
+    body = [ln for fn in ref for ln in ref[fn] if not ln.startswith("#")]
+    assert any(any(float(v) != 0.0 for v in ln.split()[(1 if len(ln.split()) > 1 and name != "calc_areaDensityDistributionPore" else 0):]) for ln in body)
+
+
 def test_live_reference_vs_dropin_other_programs(tmp_path):
     """Programs without a golden file: run both builds here and compare (only where oracle/_ref travelled)."""
     from gmx2020postanalysis_b200 import synth

@@ -546,6 +546,67 @@ def test_orient_three_site_packed_fast_path(gpu_ctx_factory, var):
     assert np.array_equal(c0[:nA * nbin1].reshape(nA, nbin1), o) and np.array_equal(c0[nA * nbin1:], ncm)
 
 
+# ---- general region accumulator (rest of the density family, A8) ----------------------------------------------------
+def test_region_accumulator_against_numpy(gpu_ctx_factory):
+    """b2a_region_create: half-open and inclusive filters, cylinder test, 1-D and 2-D bins, wrapped box count, restated in
+    numpy on the oracle's centres (the ported programs are compared with the reference builds in test_gpu_dropin.py)."""
+    system = synth.ionic_liquid(900, 6.3, seed=333)
+    K = 3
+    x, box = system.frames(0, K).copy(), system.box9()
+    x[1] += np.float32(2.0) * np.float32(box[0])              # one frame two boxes away: exercises the wrap
+    ctx = gpu_ctx_factory(system.natoms, K)
+    (gi,) = _groups(ctx, system, ["ANI"])
+    Lbox = port.lbox_from_box9(box)
+    cen = [port.load_position_center(x[f], gi["index"], gi["napm"], gi["w"][0], Lbox) for f in range(K)]
+    ctx.submit(x, box)
+    f32 = np.float32
+    L = float(Lbox[0])
+
+    def run(**kw):
+        acc = ctx.region_create(0, 0, **kw)
+        ctx.accumulate(acc)
+        return ctx.read(acc, ctx.acc_size(acc))
+
+    # (1) z profile inside a cylinder (calc_density_distribution_in_pore.cpp:47-60)
+    lo, up, cx, cy, Rm, nb = f32(0.7), f32(5.4), f32(3.1), f32(2.9), f32(2.2), 37
+    dbin = float(f32(f32(up - lo) / f32(nb)))
+    R2 = float(Rm) * float(Rm)
+    exp, sel, drop = np.zeros(nb, np.uint64), 0, 0
+    for c in cen:
+        ok = (float(lo) <= c[:, 2]) & (c[:, 2] < float(up)) & ((c[:, 0] - float(cx)) ** 2 + (c[:, 1] - float(cy)) ** 2 <= R2)
+        me = np.trunc((c[ok, 2] - float(lo)) / dbin).astype(np.int64)
+        sel += int(ok.sum()); drop += int((me >= nb).sum())
+        np.add.at(exp, me[me < nb], 1)
+    got, st = run(filters=[(2, lo, up, 0)], cyl=(cx, cy, R2), bins=[(2, lo, dbin, nb)])
+    assert np.array_equal(got, exp) and got.sum() > 0 and int(st[lib.STAT_SELECTED]) == sel and int(st[lib.STAT_DROPPED]) == drop
+    # (2) 2-D map behind three filters, one of them inclusive (calc_areaDensityDistributionPore.cpp:56-68; slit variant :60-61)
+    db = float(f32(0.21))
+    n1, n2 = int(f32(f32(5.0) - f32(1.0)) / f32(0.21)), int(f32(f32(5.5) - f32(0.5)) / f32(0.21))
+    exp = np.zeros((n2, n1), np.uint64)
+    for c in cen:
+        ok = (1.0 <= c[:, 0]) & (c[:, 0] < 5.0) & (0.5 <= c[:, 1]) & (c[:, 1] < 5.5) & (float(f32(0.3)) <= c[:, 2]) & (c[:, 2] <= float(f32(6.0)))
+        m1 = np.trunc((c[ok, 0] - 1.0) / db).astype(np.int64); m2 = np.trunc((c[ok, 1] - 0.5) / db).astype(np.int64)
+        keep = (m1 < n1) & (m2 < n2)
+        np.add.at(exp, (m2[keep], m1[keep]), 1)
+    got, st = run(filters=[(0, 1.0, 5.0, 0), (1, 0.5, 5.5, 0), (2, 0.3, 6.0, 1)], bins=[(0, 1.0, db, n1), (1, 0.5, db, n2)])
+    assert np.array_equal(got.reshape(n2, n1), exp) and got.sum() > 0
+    # (3) wrapped box count (calc_numdens_pore.cpp:12-27): float variable, double box length
+    lo3, up3 = (f32(0.4), f32(1.1), f32(0.0)), (f32(5.9), f32(4.7), f32(6.1))
+    cnt = 0
+    for c in cen:
+        ok = np.ones(len(c), bool)
+        for m in range(3):
+            t = c[:, m].astype(np.float32)
+            for _ in range(8):
+                t = np.where(t.astype(np.float64) > L, (t.astype(np.float64) - L).astype(np.float32), t)
+            for _ in range(8):
+                t = np.where(t < f32(0), (t.astype(np.float64) + L).astype(np.float32), t)
+            ok &= (lo3[m] <= t) & (t < up3[m])
+        cnt += int(ok.sum())
+    got, st = run(filters=[(m, lo3[m], up3[m], 0) for m in range(3)], wrap=1)
+    assert int(got[0]) == cnt > 0 and int(st[lib.STAT_FRAMES]) == K
+
+
 # ---- boxes that change from frame to frame (NPT), short batches, degenerate selections -------------------------------
 def test_box_changes_per_frame_and_degenerate_selections(gpu_ctx_factory):
     """Every frame of a batch carries its own box (ipp:72-74 re-reads Lbox per frame): RDF (all-pairs, symmetric-ineligible
