@@ -859,7 +859,7 @@ extern "C" int b2a_region_create(b2a_ctx* c, const b2a_region_spec* s, int* id)
     size_t n = 1;
     for (int b = 0; b < s->nbdim; ++b)
     {
-        if (s->bdim[b] < 0 || s->bdim[b] > 2 || s->nb[b] <= 0 || !(s->dbin[b] > 0)) return fail(B2A_ERR_ARG, "b2a_region_create: bad binned dimension %d", b);
+        if (s->bdim[b] < 0 || s->bdim[b] > 3 || s->nb[b] <= 0 || !(s->dbin[b] > 0)) return fail(B2A_ERR_ARG, "b2a_region_create: bad binned dimension %d", b);
         n *= (size_t)s->nb[b];
     }
     if (n > ((size_t)1 << 28)) return fail(B2A_ERR_UNSUPPORTED, "b2a_region_create: %zu counters", n);

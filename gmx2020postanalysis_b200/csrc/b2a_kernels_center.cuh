@@ -422,8 +422,14 @@ __global__ void __launch_bounds__(256) k2g_region(const double* __restrict__ cen
             long long stride = 1;
             for (int b = 0; b < d.nbdim; ++b)
             {
-                const double p  = c0[(size_t)d.bdim[b] * nmol + i];
-                const double q  = __ddiv_rn(__dsub_rn(p, d.blow[b]), d.dbin[b]);
+                double p;
+                if (d.bdim[b] == 3)
+                {   // radial bin: std::sqrt(pow(x - cx, 2) + pow(y - cy, 2)) (calc_radius_distribution_in_pore.cpp:47-49)
+                    const double dx = __dsub_rn(c0[i], d.cx), dy = __dsub_rn(c0[(size_t)nmol + i], d.cy);
+                    p               = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+                }
+                else p = c0[(size_t)d.bdim[b] * nmol + i];
+                const double q  = d.bdim[b] == 3 && d.blow[b] == 0.0 ? __ddiv_rn(p, d.dbin[b]) : __ddiv_rn(__dsub_rn(p, d.blow[b]), d.dbin[b]);
                 const int    me = (q >= -2.0e9 && q <= 2.0e9) ? __double2int_rz(q) : -1;
                 if (me < 0 || me >= d.nb[b]) oob = true;     // the reference indexes outside its array here
                 cell += (long long)me * stride;

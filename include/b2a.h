@@ -149,7 +149,8 @@ typedef struct b2a_region_spec
     float  cx, cy;
     double R2;                 /* as the program computes it: double(Rmof) * Rmof                                                    */
     int    nbdim;              /* 0, 1 or 2 binned dimensions */
-    int    bdim[2];
+    int    bdim[2];            /* 0, 1, 2: a centre component; 3: the distance from the cylinder axis, sqrt(pow(x - cx, 2) + pow(y - cy, 2))
+                                  (mofs/calc_radius_distribution_in_pore.cpp:47-49)                                                  */
     float  blow[2];
     double dbin[2];            /* bin widths as the program holds them (a `real` widened, or a double)                               */
     int    nb[2];
