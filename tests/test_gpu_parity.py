@@ -304,6 +304,72 @@ def test_rdf_full_size_paranoid_free_properties(gpu_ctx_factory):
     assert np.array_equal(got2.reshape(Rbin, 5), exp)
 
 
+def test_full_size_configs_3_4_5_properties(gpu_ctx_factory):
+    """BASELINE configs 3, 4 and 5 at FULL size, one frame each, through properties that need no full-size CPU run:
+    C3 (1 M-atom ionic liquid): cation-anion == anion-cation, i-subset bit-exact against the oracle, sphere fraction;
+    C4 (499 998-atom water): literal FP64, bracketed and validated orientation histograms identical, every molecule counted once;
+    C5 (4 M atoms): cell-binned symmetric water-water == symmetric all-pairs, cross pair cell-binned == all-pairs."""
+    # ---- C3
+    system = synth.ionic_liquid(31250, 22.1, seed=20200103)
+    Lbox = port.lbox_from_box9(system.box9())
+    Rm = port.rdf_default_rm(Lbox)
+    Rbin = port.rdf_rbin(Rm)
+    x = system.frames(0, 1)
+    ctx = gpu_ctx_factory(system.natoms, 1)
+    h_ab, st = _rdf_gpu(ctx, system, "CAT", "ANI", 1, dict(_DEF, nbin=1), Rm, Rbin, frames=x)
+    ctx.close()
+    ctx = gpu_ctx_factory(system.natoms, 1)
+    h_ba, _ = _rdf_gpu(ctx, system, "ANI", "CAT", 1, dict(_DEF, nbin=1), Rm, Rbin, frames=x)
+    ctx.close()
+    assert np.array_equal(h_ab, h_ba) and int(st[lib.STAT_PAIRS]) == 31250 * 31250
+    assert abs(h_ab.sum() / 31250.0 ** 2 - np.pi / 6) < 3e-3
+    gc, ga = refprog.group_info(system, "CAT"), refprog.group_info(system, "ANI")
+    pc = port.load_position_center(x[0], gc["index"][:48 * 25], 25, gc["w"][0], Lbox)
+    pa = port.load_position_center(x[0], ga["index"], 7, ga["w"][0], Lbox)
+    exp, _ = port.rdf_accum(pc, pa, Lbox, 1, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, Rbin)
+    ctx = gpu_ctx_factory(system.natoms, 1)
+    ctx.set_group(0, gc["index"][:48 * 25], 25, gc["mass"], gc["charge"])
+    ctx.set_group(1, ga["index"], 7, ga["mass"], ga["charge"])
+    acc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=1, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0, Rm=Rm, Rbin=Rbin)
+    ctx.submit(x, system.box9()); ctx.accumulate(acc)
+    assert np.array_equal(ctx.read(acc, Rbin)[0].reshape(Rbin, 1), exp)
+    ctx.close()
+    # ---- C4
+    system = synth.water_box(166666, 17.09, seed=20200104)
+    x = system.frames(0, 1)
+    ctx = gpu_ctx_factory(system.natoms, 1)
+    _groups(ctx, system, ["SOL"])
+    ctx.submit(x, system.box9())
+    res = []
+    for mode in (0, 1, 2):
+        acc = ctx.orient_create(grp=0, com=0, DIMN=2, low=-1.0, up=100.0, c1=0.0, c2=0.0, dr=100.0, CR=100.0, Cr=0.0, nAngle=90,
+                                tp1=1, tp2=2, tp3=3, DIMNOrient=2, method=1)
+        ctx.acc_fast(acc, mode); ctx.accumulate(acc)
+        res.append(ctx.read(acc, 91))
+    (c0, s0), (c1, s1), (c2, s2) = res
+    assert np.array_equal(c0, c1) and np.array_equal(c0, c2) and int(s2[lib.STAT_MISPROVEN]) == 0
+    assert int(c0[90]) == 166666 and int(c0[:90].sum()) + int(s0[lib.STAT_DROPPED]) == 166666
+    mu = ctx.centers_batch(0, lib.COM_DIPOLE)[0]
+    assert np.allclose(np.linalg.norm(mu, axis=1), 0.04894, atol=2e-4)          # rigid SPC/E dipole, every molecule
+    ctx.close()
+    # ---- C5
+    system = synth.mixed_box()
+    x = system.frames(0, 1)
+    Rm5 = refprog.f32(3.0)
+    Rbin5 = port.rdf_rbin(Rm5)
+    out = {}
+    for tag, g, cells, sym in (("ww_cells", ("SOL", "SOL"), 1, 1), ("ww_all", ("SOL", "SOL"), 0, 1), ("wc_cells", ("SOL", "COS"), 1, 0), ("wc_all", ("SOL", "COS"), 0, 0)):
+        ctx = gpu_ctx_factory(system.natoms, 1)
+        _groups(ctx, system, list(g))
+        acc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=1, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0, Rm=Rm5, Rbin=Rbin5)
+        ctx.rdf_tune(acc, sym, 0); ctx.rdf_cells(acc, cells)
+        ctx.submit(x, system.box9()); ctx.accumulate(acc)
+        out[tag] = ctx.read(acc, Rbin5)
+        ctx.close()
+    assert np.array_equal(out["ww_cells"][0], out["ww_all"][0]) and np.array_equal(out["wc_cells"][0], out["wc_all"][0])
+    assert out["ww_cells"][0].sum() > 4e9 and int(out["ww_cells"][1][lib.STAT_PAIRS]) * 20 < int(out["ww_all"][1][lib.STAT_PAIRS])
+
+
 # ---- A6: orientation ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["orient_water", "orient_il_cross"])
 def test_orient_bit_exact_and_reference_text(gpu_ctx_factory, name):
