@@ -1186,7 +1186,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         // about ten waves, but never chunks below two j tiles (per-block set-up, histogram zeroing and flush).  Measured on
         // config 3 (31 i-tiles x 8 frames): 4.4 waves -> 0.75 of FP32 issue, 7 -> 0.78, 10.4 -> 0.79; config 2 full
         // evaluation: 5.4 waves -> 0.85, 10.7 -> 0.87.
-        const int resident = std::max(1, std::min(5, (int)((227 * 1024) / (smem + 1024))));   // 96 registers x 128 threads: 5
+        const int resident = std::max(1, std::min(6, (int)((227 * 1024) / (smem + 1024))));   // 80 registers x 128 threads: 6
         int       waves    = 10;
         if (const char* e = getenv("B2A_K3_WAVES")) waves = std::max(1, atoi(e));
         int       jsplit   = std::max(1, (c->sm_count * resident * waves + itiles * c->nframes - 1) / (itiles * c->nframes));

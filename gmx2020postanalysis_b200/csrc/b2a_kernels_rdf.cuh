@@ -345,8 +345,10 @@ struct CellDev   // cell mode parameters (by value)
 //                 eligible (not all molecules in one slab) are skipped here and done by the full kernel, and vice versa
 // MODE 2 (cell) : grid x = (slab, cx, cy) column of i-cells, y = tile of the column, z = frame; j runs over the neighbouring
 //                 columns, restricted to the cells within reach of the tile's own z span
+// (launch bound: 6 resident blocks of the 8 x 128 tile = 80 registers instead of the 96 the compiler takes unconstrained, 36 bytes
+//  of spills: 634.7 -> 652.4 frames/s on config 2; 7 blocks = 72 registers spill into the hot loop: 603.7)
 template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, int MODE>
-__global__ void __launch_bounds__(THREADS) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
+__global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
                                                   const double* __restrict__ cenA, const double* __restrict__ cenB,
                                                   const unsigned* __restrict__ slab_cnt,
                                                   const RdfFrame* __restrict__ frames, RdfDev p, CellDev cd,
