@@ -446,7 +446,7 @@ static int get_group(b2a_ctx* c, int grp, Group** out)
 extern "C" int b2a_set_group_wsum(b2a_ctx* c, int grp, int com, double wsum)
 {
     if (!c || com < 0 || com > 3) return fail(B2A_ERR_ARG, "b2a_set_group_wsum: bad argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
     g->wsum[com]  = wsum;
     g->valid[com] = 0;
@@ -657,7 +657,7 @@ static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
 extern "C" int b2a_centers(b2a_ctx* c, int grp, int com, int frame, double* out)
 {
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_centers: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
     if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_centers: frame %d outside batch of %d", frame, c->nframes);
@@ -671,7 +671,7 @@ extern "C" int b2a_centers(b2a_ctx* c, int grp, int com, int frame, double* out)
 extern "C" int b2a_centers_batch(b2a_ctx* c, int grp, int com, double* out)
 {
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_centers_batch: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
     CU(cudaSetDevice(c->device));
     if (int rc = ensure_centers(c, *g, com, false)) return rc;
@@ -683,7 +683,7 @@ extern "C" int b2a_centers_batch(b2a_ctx* c, int grp, int com, double* out)
 extern "C" int b2a_positions(b2a_ctx* c, int grp, int frame, double* out)
 {
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_positions: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
     if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_positions: frame %d outside batch of %d", frame, c->nframes);
@@ -767,7 +767,7 @@ static int run_field_centers(b2a_ctx* c, int field, Group& g, int com)
 extern "C" int b2a_field_centers_batch(b2a_ctx* c, int field, int grp, int com, double* out)
 {
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_centers_batch: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = field_ready(c, field, &g, grp)) return rc;
     CU(cudaSetDevice(c->device));
     if (int rc = run_field_centers(c, field, *g, com)) return rc;
@@ -779,7 +779,7 @@ extern "C" int b2a_field_centers_batch(b2a_ctx* c, int field, int grp, int com, 
 extern "C" int b2a_field_centers(b2a_ctx* c, int field, int grp, int com, int frame, double* out)
 {
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_centers: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = field_ready(c, field, &g, grp)) return rc;
     if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_field_centers: frame %d outside batch of %d", frame, c->nframes);
     CU(cudaSetDevice(c->device));
@@ -792,7 +792,7 @@ extern "C" int b2a_field_centers(b2a_ctx* c, int field, int grp, int com, int fr
 extern "C" int b2a_field_values(b2a_ctx* c, int field, int grp, int frame, double* out)
 {
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_values: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = field_ready(c, field, &g, grp)) return rc;
     if (frame < 0 || frame >= c->nframes) return fail(B2A_ERR_ARG, "b2a_field_values: frame %d outside batch of %d", frame, c->nframes);
     if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "b2a_field_values on a heterogeneous (GmxHandleFull) group: the reference class has no loadVelocity / loadForce");
@@ -835,7 +835,7 @@ static int get_acc(b2a_ctx* c, int id, Acc** out)
 extern "C" int b2a_density_create(b2a_ctx* c, const b2a_density_spec* s, int* id)
 {
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_density_create: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, s->grp, &g)) return rc;
     if (s->nbin <= 0 || s->dim < 0 || s->dim > 2 || s->dim2 > 2 || !(s->dbin > 0)) return fail(B2A_ERR_ARG, "b2a_density_create: bad spec");
     if (s->com < 0 || s->com > 3) return fail(B2A_ERR_ARG, "com(%d) out of range", s->com);
@@ -850,7 +850,7 @@ extern "C" int b2a_density_create(b2a_ctx* c, const b2a_density_spec* s, int* id
 extern "C" int b2a_region_create(b2a_ctx* c, const b2a_region_spec* s, int* id)
 {
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_region_create: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, s->grp, &g)) return rc;
     if (s->com < 0 || s->com > 3) return fail(B2A_ERR_ARG, "com(%d) out of range", s->com);
     if (s->nfilter < 0 || s->nfilter > 3 || s->nbdim < 0 || s->nbdim > 2) return fail(B2A_ERR_ARG, "b2a_region_create: 0..3 filters and 0..2 binned dimensions");
@@ -874,7 +874,7 @@ extern "C" int b2a_region_create(b2a_ctx* c, const b2a_region_spec* s, int* id)
 extern "C" int b2a_rdf_create(b2a_ctx* c, const b2a_rdf_spec* s, int* id)
 {
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_rdf_create: null argument");
-    Group *g0, *g1;
+    Group *g0 = nullptr, *g1 = nullptr;
     if (int rc = get_group(c, s->grp0, &g0)) return rc;
     if (int rc = get_group(c, s->grp1, &g1)) return rc;
     if (s->nbin <= 0 || s->Rbin <= 0 || !(s->Rm > 0.f) || s->dim < 0 || s->dim > 2 || s->dim2 < 0 || s->dim2 > 2)
@@ -898,7 +898,7 @@ extern "C" int b2a_rdf_create(b2a_ctx* c, const b2a_rdf_spec* s, int* id)
 
 extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF", id);
     a->symmetric = symmetric;
@@ -908,7 +908,7 @@ extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
 
 extern "C" int b2a_acc_fast(b2a_ctx* c, int id, int mode)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind == ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is an RDF: use b2a_rdf_tune", id);
     if (mode < 0 || mode > 2) return fail(B2A_ERR_ARG, "b2a_acc_fast: mode must be 0 (FP64 only), 1 (FP32 bracket + FP64 queue) or 2 (validate)");
@@ -918,7 +918,7 @@ extern "C" int b2a_acc_fast(b2a_ctx* c, int id, int mode)
 
 extern "C" int b2a_rdf_cells(b2a_ctx* c, int id, int mode)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_RDF && a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF or coordination-number accumulator", id);
     if (mode < -1 || mode > 1) return fail(B2A_ERR_ARG, "b2a_rdf_cells: mode must be -1 (auto), 0 (never) or 1 (whenever cells cull)");
@@ -1074,7 +1074,7 @@ static int cell_sort(b2a_ctx* c, int grp, Group& g, int com, int bits, const Acc
 static int accumulate_rdf(b2a_ctx* c, Acc& a)
 {
     const b2a_rdf_spec& s = a.rdf;
-    Group *g0, *g1;
+    Group *g0 = nullptr, *g1 = nullptr;
     if (int rc = get_group(c, s.grp0, &g0)) return rc;
     if (int rc = get_group(c, s.grp1, &g1)) return rc;
     if (int rc = ensure_centers(c, *g0, s.com0, true)) return rc;
@@ -1213,7 +1213,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
 static int accumulate_region(b2a_ctx* c, Acc& a)
 {
     const b2a_region_spec& s = a.region;
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, s.grp, &g)) return rc;
     if (int rc = ensure_centers(c, *g, s.com, false)) return rc;   // K1: exact FP64 centres, cached for the batch
     RegionDev d{};
@@ -1231,7 +1231,7 @@ static int accumulate_region(b2a_ctx* c, Acc& a)
 static int accumulate_density(b2a_ctx* c, Acc& a)
 {
     const b2a_density_spec& s = a.den;
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, s.grp, &g)) return rc;
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
     DensityDev d{};
@@ -1274,7 +1274,7 @@ __global__ void k_add_frames(unsigned long long* stats, unsigned long long n) { 
 
 extern "C" int b2a_accumulate(b2a_ctx* c, int id)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     CU(cudaSetDevice(c->device));
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
@@ -1295,7 +1295,7 @@ extern "C" int b2a_accumulate(b2a_ctx* c, int id)
 
 extern "C" int b2a_acc_reset(b2a_ctx* c, int id)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(a->d_hist, 0, sizeof(unsigned long long) * (a->ndev + B2A_STAT_NSLOTS), c->stream));
@@ -1304,7 +1304,7 @@ extern "C" int b2a_acc_reset(b2a_ctx* c, int id)
 
 extern "C" int b2a_acc_size(b2a_ctx* c, int id, size_t* n)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (!n) return fail(B2A_ERR_ARG, "null argument");
     *n = a->ndev;   // device words before the stats block; the merge covers ndev + B2A_STAT_NSLOTS
@@ -1313,7 +1313,7 @@ extern "C" int b2a_acc_size(b2a_ctx* c, int id, size_t* n)
 
 extern "C" int b2a_acc_device_ptr(b2a_ctx* c, int id, void** p)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (!p) return fail(B2A_ERR_ARG, "null argument");
     *p = a->d_hist;
@@ -1322,7 +1322,7 @@ extern "C" int b2a_acc_device_ptr(b2a_ctx* c, int id, void** p)
 
 extern "C" int b2a_acc_read(b2a_ctx* c, int id, uint64_t* counts, uint64_t* stats)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (!counts) return fail(B2A_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
@@ -1407,7 +1407,7 @@ extern "C" int b2a_timing_read(b2a_ctx* c, double* ms, long long* launches)
 extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
 {
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_orient_create: null argument");
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, s->grp, &g)) return rc;
     if (s->DIMN < 0 || s->DIMN > 2 || s->DIMNOrient < 0 || s->DIMNOrient > 2) return fail(B2A_ERR_ARG, "orient: dim out of range");
     if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "orientation histogram on a heterogeneous (GmxHandleFull) group is not implemented");
@@ -1517,7 +1517,7 @@ extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
 static int accumulate_orient(b2a_ctx* c, Acc& a)
 {
     const b2a_orient_spec& s = a.ori;
-    Group* g;
+    Group* g = nullptr;
     if (int rc = get_group(c, s.grp, &g)) return rc;
     if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "orientation histogram on a heterogeneous (GmxHandleFull) group is not implemented");
     OrientDev d{};
@@ -1576,7 +1576,7 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
 extern "C" int b2a_coord_create(b2a_ctx* c, const b2a_coord_spec* s, int* id)
 {
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_coord_create: null argument");
-    Group *g0, *g1;
+    Group *g0 = nullptr, *g1 = nullptr;
     if (int rc = get_group(c, s->grp0, &g0)) return rc;
     if (int rc = get_group(c, s->grp1, &g1)) return rc;
     if (!(s->Rmin > 0.f) || s->dim < 0 || s->dim > 2 || s->max_count <= 0 || s->max_count > 8192)
@@ -1614,7 +1614,7 @@ static int launch_coord(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const CoordDev
 static int accumulate_coord(b2a_ctx* c, Acc& a)
 {
     const b2a_coord_spec& s = a.coord;
-    Group *g0, *g1;
+    Group *g0 = nullptr, *g1 = nullptr;
     if (int rc = get_group(c, s.grp0, &g0)) return rc;
     if (int rc = get_group(c, s.grp1, &g1)) return rc;
     if (int rc = ensure_centers(c, *g0, s.com0, true)) return rc;
@@ -1757,7 +1757,7 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
 
 extern "C" int b2a_coord_read_frames(b2a_ctx* c, int id, uint32_t* table, uint32_t* numA)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not a coordination-number accumulator", id);
     if (!table || !numA) return fail(B2A_ERR_ARG, "null argument");
@@ -1771,11 +1771,11 @@ extern "C" int b2a_coord_read_frames(b2a_ctx* c, int id, uint32_t* table, uint32
 
 extern "C" int b2a_coord_counts(b2a_ctx* c, int id, int frame, int32_t* count)
 {
-    Acc* a;
+    Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not a coordination-number accumulator", id);
     if (!count || frame < 0 || frame >= a->table_frames) return fail(B2A_ERR_ARG, "b2a_coord_counts: bad argument");
-    Group* g0;
+    Group* g0 = nullptr;
     if (int rc = get_group(c, a->coord.grp0, &g0)) return rc;
     CU(cudaSetDevice(c->device));
     const size_t     n0 = (size_t)g0->nmol;
