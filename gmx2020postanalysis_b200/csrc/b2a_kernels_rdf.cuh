@@ -35,8 +35,14 @@ namespace b2a
 constexpr unsigned kMagicBits = 0x4B000000u;   // bits of 2^23 (float)
 constexpr float    kMagic     = 8388607.5f;    // 2^23 - 0.5: fma(r, s, kMagic) rounds to floor(r*s) in the mantissa
 constexpr int      kQueueCap  = 1024;          // (j, thread) candidates per block between drains
-constexpr int      kTileJ     = 512;           // j-molecules staged per shared-memory tile
-constexpr int      kSubJ      = 256;           // j-iterations between queue drains
+#ifndef B2A_K3_TILEJ
+#define B2A_K3_TILEJ 512
+#endif
+#ifndef B2A_K3_SUBJ
+#define B2A_K3_SUBJ 256
+#endif
+constexpr int      kTileJ     = B2A_K3_TILEJ;  // j-molecules staged per shared-memory tile
+constexpr int      kSubJ      = B2A_K3_SUBJ;   // j-iterations between queue drains
 #ifndef B2A_K3_PACKED
 #define B2A_K3_PACKED 1
 #endif
