@@ -1,0 +1,41 @@
+// calc_density_time (reference src/mofs/calc_density_time.cpp), ported to the device.
+//
+// Same command line and output file: the number of molecules inside the pore (z slab + cylinder) for every frame.  The per-frame
+// loop (:38-54) becomes one b2aAccumulate() of a region accumulator with per-frame counters per resident batch; the time stamps
+// of the batch come from the batcher.
+#include <itp/gmx>
+
+gmx_main(temp)
+{
+    itp::GmxHandle hd(argc, argv);
+
+    real lowPos = 7.761, upPos = 12.239, centerX = 2.829, centerY = 2.056, Rmof = 0.927;
+    hd.pa = {
+        { "-upPos", FALSE, etREAL, { &upPos }, "up position of region of pore (nm)" },
+        { "-lowPos", FALSE, etREAL, { &lowPos }, "low position of region of pore (nm)" },
+        { "-centerX", FALSE, etREAL, { &centerX }, "center X position of mofs pore (nm)" },
+        { "-centerY", FALSE, etREAL, { &centerY }, "center Y position of mofs pore (nm)" },
+        { "-Rmof", FALSE, etREAL, { &Rmof }, "Radius of mofs pore (nm)" }
+    };
+    hd.fnm = { { efXVG, "-o", "DensityTime", ffWRITE } };
+    hd.init();
+    hd.readFirstFrame();
+
+    b2a_region_spec spec{};
+    spec.grp = 0; spec.com = B2A_COM_MASS;
+    spec.nfilter = 1; spec.fdim[0] = ZZ; spec.flow[0] = lowPos; spec.fup[0] = upPos; spec.fincl[0] = 0;
+    spec.cyl = 1; spec.cx = centerX; spec.cy = centerY; spec.R2 = double(Rmof) * Rmof;   // :33
+    spec.nbdim = 0; spec.per_frame = 1;
+    const int acc = hd.b2aRegion(spec);
+
+    auto ofile = hd.openWrite(hd.get_opt2fn("-o"));
+    std::vector<uint64_t> per;
+    do
+    {
+        hd.b2aAccumulate(acc);
+        hd.b2aRegionFrames(acc, per);
+        for (int k = 0; k < hd.b2aBatchFrames(); ++k) fmt::print(ofile, "{:8.4f} {:10d}\n", hd.b2aBatchTime(k), (int)per[k]);
+    } while (hd.b2aReadNextBatch());
+    fclose(ofile);
+    return 0;
+}

@@ -126,6 +126,8 @@ struct Acc
     b2a_orient_spec    ori{};
     b2a_coord_spec     coord{};
     b2a_region_spec    region{};
+    unsigned long long* d_perframe = nullptr;   // region accumulators with per_frame: [maxK][ncounters] of the last batch
+    int                perframe_frames = 0;
     size_t             ncounters = 0;       // public counters (reference layout size)
     size_t             ndev      = 0;       // device u64 words before the stats block
     unsigned long long* d_hist   = nullptr; // [ndev + NSLOTS]
@@ -282,7 +284,7 @@ static void free_acc(Acc& a)
 {
     cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
     cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab); cudaFree(a.d_lut); cudaFree(a.d_fmh);
-    cudaFree(a.d_cnt); cudaFree(a.d_table); cudaFree(a.d_cframes);
+    cudaFree(a.d_cnt); cudaFree(a.d_table); cudaFree(a.d_cframes); cudaFree(a.d_perframe);
     if (a.h_cframes) cudaFreeHost(a.h_cframes);
     cudaFree(a.d_keysA); cudaFree(a.d_keysB); cudaFree(a.d_cellA); cudaFree(a.d_cellB); cudaFree(a.d_sortedB);
     if (a.h_frames) cudaFreeHost(a.h_frames);
@@ -868,6 +870,11 @@ extern "C" int b2a_region_create(b2a_ctx* c, const b2a_region_spec* s, int* id)
     a->kind   = ACC_REGION;
     a->region = *s;
     a->ncounters = a->ndev = n;
+    if (s->per_frame)
+    {
+        if (n * (size_t)c->maxK > ((size_t)1 << 28)) return fail(B2A_ERR_UNSUPPORTED, "b2a_region_create: per-frame table of %zu x %d counters", n, c->maxK);
+        CU(cudaMalloc(&a->d_perframe, sizeof(unsigned long long) * n * c->maxK));
+    }
     return new_acc(c, std::move(a), id);
 }
 
@@ -1223,8 +1230,22 @@ static int accumulate_region(b2a_ctx* c, Acc& a)
     for (int b = 0; b < 2; ++b) { d.bdim[b] = s.bdim[b]; d.nb[b] = s.nb[b]; d.blow[b] = (double)s.blow[b]; d.dbin[b] = s.dbin[b]; }
     Timed tm(c, 3);
     dim3  grid((g->nmol + 255) / 256, c->nframes);
-    k2g_region<<<grid, 256, 0, c->stream>>>(g->d_cen[s.com], c->nframes, g->nmol, d, c->d_geom, a.d_hist, a.d_hist + a.ndev);
+    if (a.d_perframe) CU(cudaMemsetAsync(a.d_perframe, 0, sizeof(unsigned long long) * a.ndev * c->nframes, c->stream));
+    k2g_region<<<grid, 256, 0, c->stream>>>(g->d_cen[s.com], c->nframes, g->nmol, d, c->d_geom, a.d_hist, a.d_hist + a.ndev, a.d_perframe, a.ndev);
     CU(cudaGetLastError());
+    a.perframe_frames = c->nframes;
+    return B2A_OK;
+}
+
+extern "C" int b2a_region_read_frames(b2a_ctx* c, int id, unsigned long long* out)
+{
+    Acc* a = nullptr;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (a->kind != ACC_REGION || !a->d_perframe) return fail(B2A_ERR_ARG, "accumulator %d keeps no per-frame counters (b2a_region_spec.per_frame)", id);
+    if (!out) return fail(B2A_ERR_ARG, "b2a_region_read_frames: null output");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(out, a->d_perframe, sizeof(unsigned long long) * a->ndev * a->perframe_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return B2A_OK;
 }
 

@@ -387,7 +387,8 @@ struct RegionDev
 
 __global__ void __launch_bounds__(256) k2g_region(const double* __restrict__ cen, int nframes, int nmol, RegionDev d,
                                                   const FrameGeom* __restrict__ geom, unsigned long long* __restrict__ hist,
-                                                  unsigned long long* __restrict__ stats)
+                                                  unsigned long long* __restrict__ stats, unsigned long long* __restrict__ perframe,
+                                                  size_t ncounters)
 {
     const int  f  = blockIdx.y;
     const int  i  = blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,13 +442,19 @@ __global__ void __launch_bounds__(256) k2g_region(const double* __restrict__ cen
     if (d.nbdim == 0)
     {
         const unsigned m = __ballot_sync(0xffffffffu, ok);
-        if ((threadIdx.x & 31) == 0 && m) { atomicAdd(&hist[0], (unsigned long long)__popc(m)); atomicAdd(&stats[4], (unsigned long long)__popc(m)); }
+        if ((threadIdx.x & 31) == 0 && m)
+        {
+            atomicAdd(&hist[0], (unsigned long long)__popc(m));
+            atomicAdd(&stats[4], (unsigned long long)__popc(m));
+            if (perframe) atomicAdd(&perframe[(size_t)f], (unsigned long long)__popc(m));
+        }
         return;
     }
     if (!ok) return;
     atomicAdd(&stats[4], 1ull);
     if (oob) { atomicAdd(&stats[1], 1ull); return; }
     atomicAdd(&hist[cell], 1ull);
+    if (perframe) atomicAdd(&perframe[(size_t)f * ncounters + cell], 1ull);
 }
 
 // grid: x = molecule block, y = frame group.  A thread owns ONE molecule and walks the frames of its group.

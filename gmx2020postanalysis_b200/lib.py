@@ -23,7 +23,7 @@ SYMBOLS = [
     "b2a_pinned_alloc", "b2a_pinned_free", "b2a_set_group", "b2a_set_group_full", "b2a_set_group_wsum", "b2a_group_nmol",
     "b2a_submit_batch", "b2a_batch_frames", "b2a_centers", "b2a_centers_batch", "b2a_positions",
     "b2a_submit_field", "b2a_field_centers", "b2a_field_centers_batch", "b2a_field_values",
-    "b2a_density_create", "b2a_region_create", "b2a_rdf_create", "b2a_orient_create", "b2a_coord_create", "b2a_coord_read_frames",
+    "b2a_density_create", "b2a_region_create", "b2a_region_read_frames", "b2a_rdf_create", "b2a_orient_create", "b2a_coord_create", "b2a_coord_read_frames",
     "b2a_coord_counts", "b2a_coord_fold", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
     "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_acc_fast", "b2a_invalidate", "b2a_timing_enable",
     "b2a_timing_read",
@@ -34,7 +34,7 @@ class RegionSpec(C.Structure):
     _fields_ = [("grp", C.c_int), ("com", C.c_int), ("nfilter", C.c_int), ("fdim", C.c_int * 3), ("flow", C.c_float * 3),
                 ("fup", C.c_float * 3), ("fincl", C.c_int * 3), ("wrap", C.c_int), ("cyl", C.c_int), ("cx", C.c_float), ("cy", C.c_float),
                 ("R2", C.c_double), ("nbdim", C.c_int), ("bdim", C.c_int * 2), ("blow", C.c_float * 2), ("dbin", C.c_double * 2),
-                ("nb", C.c_int * 2)]
+                ("nb", C.c_int * 2), ("per_frame", C.c_int)]
 
 
 class DensitySpec(C.Structure):
@@ -103,6 +103,7 @@ def load():
         L.b2a_field_values.argtypes = [_P, C.c_int, C.c_int, C.c_int, _P]
         L.b2a_density_create.argtypes = [_P, C.POINTER(DensitySpec), C.POINTER(C.c_int)]
         L.b2a_region_create.argtypes = [_P, C.POINTER(RegionSpec), C.POINTER(C.c_int)]
+        L.b2a_region_read_frames.argtypes = [_P, C.c_int, _P]
         L.b2a_rdf_create.argtypes = [_P, C.POINTER(RdfSpec), C.POINTER(C.c_int)]
         L.b2a_orient_create.argtypes = [_P, C.POINTER(OrientSpec), C.POINTER(C.c_int)]
         L.b2a_coord_create.argtypes = [_P, C.POINTER(CoordSpec), C.POINTER(C.c_int)]
@@ -262,10 +263,16 @@ class Context:
         check(self.L.b2a_density_create(self._h, C.byref(s), C.byref(a)))
         return a.value
 
-    def region_create(self, grp, com=0, filters=(), wrap=0, cyl=None, bins=()):
+    def region_read_frames(self, acc, nframes):
+        n = self.acc_size(acc)
+        out = np.zeros((nframes, n), dtype=np.uint64)
+        check(self.L.b2a_region_read_frames(self._h, acc, out.ctypes.data))
+        return out
+
+    def region_create(self, grp, com=0, filters=(), wrap=0, cyl=None, bins=(), per_frame=0):
         """filters: (dim, low, up, inclusive) x 0..3; cyl: (cx, cy, R2) or None; bins: (dim, low, dbin, n) x 0..2."""
         s = RegionSpec()
-        s.grp, s.com, s.nfilter, s.wrap, s.nbdim = grp, com, len(filters), int(wrap), len(bins)
+        s.grp, s.com, s.nfilter, s.wrap, s.nbdim, s.per_frame = grp, com, len(filters), int(wrap), len(bins), int(per_frame)
         for q, (dim, lo, up, incl) in enumerate(filters):
             s.fdim[q], s.flow[q], s.fup[q], s.fincl[q] = dim, lo, up, int(incl)
         if cyl is not None:

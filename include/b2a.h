@@ -154,6 +154,8 @@ typedef struct b2a_region_spec
     float  blow[2];
     double dbin[2];            /* bin widths as the program holds them (a `real` widened, or a double)                               */
     int    nb[2];
+    int    per_frame;          /* also keep the counters of every frame of the last accumulated batch (time series programs:
+                                  mofs/calc_density_time.cpp:38-55), readable with b2a_region_read_frames                             */
 } b2a_region_spec;
 
 typedef struct b2a_rdf_spec
@@ -210,6 +212,8 @@ enum {
 
 int b2a_density_create(b2a_ctx* ctx, const b2a_density_spec* spec, int* acc);
 int b2a_region_create(b2a_ctx* ctx, const b2a_region_spec* spec, int* acc);
+/* out: [frames of the last accumulated batch][counters] (spec.per_frame must have been set) */
+int b2a_region_read_frames(b2a_ctx* ctx, int acc, unsigned long long* out);
 int b2a_rdf_create(b2a_ctx* ctx, const b2a_rdf_spec* spec, int* acc);
 int b2a_orient_create(b2a_ctx* ctx, const b2a_orient_spec* spec, int* acc);
 

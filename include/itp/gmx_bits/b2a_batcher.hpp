@@ -51,6 +51,7 @@ namespace b2a_detail
         }
         b2a_ctx* ctx() const { return ctx_; }
         int      frames() const { return n_; }
+        float    time_of(int k) const { return btime_[k]; }   // fr->time of frame k of the resident batch
         int      current() const { return cur_; }
         int      capacity() const { return k_; }
         long     serial() const { return serial_; }

@@ -49,9 +49,12 @@ namespace itp
         // ---- extensions (not in the reference): fused device accumulators over whole batches ----------------
         b2a_ctx* b2aContext() { return batch_.ctx(); }
         int  b2aBatchFrames() const { return batch_.frames(); }          // frames in the resident batch
+        float b2aBatchTime(int k) const { return batch_.time_of(k); }    // fr->time of frame k of the resident batch
         bool b2aReadNextBatch();                                   // skip to the first frame of the next batch
         int  b2aDensity(const b2a_density_spec& s);
         int  b2aRegion(const b2a_region_spec& s);                  // filters / cylinder / wrap + 0..2 binned dimensions
+        // per-frame counters of the batch just accumulated (spec.per_frame): out[frame][counter]
+        void b2aRegionFrames(int acc, std::vector<uint64_t>& out);
         int  b2aRdf(const b2a_rdf_spec& s, bool symmetric = true);
         int  b2aOrient(const b2a_orient_spec& s);
         int  b2aCoord(const b2a_coord_spec& s);                    // coordination numbers (mofs/calc_pair_dist*.cpp)

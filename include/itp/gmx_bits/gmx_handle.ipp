@@ -318,6 +318,14 @@ namespace itp
         return acc;
     }
 
+    inline void GmxHandle::b2aRegionFrames(int acc, std::vector<uint64_t>& out)
+    {
+        size_t n = 0;
+        b2a_detail::check(b2a_acc_size(batch_.ctx(), acc, &n));
+        out.assign(n * (size_t)batch_.frames(), 0);
+        b2a_detail::check(b2a_region_read_frames(batch_.ctx(), acc, reinterpret_cast<unsigned long long*>(out.data())));
+    }
+
     inline int GmxHandle::b2aRdf(const b2a_rdf_spec& s, bool symmetric)
     {
         b2aEnsure();
