@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark: O-O RDF of the 216k-atom synthetic water box (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2a|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2a|reference] [--config c2|c3|c5]
+
+`--config` selects another BASELINE.json workload for the runs recorded in profiles/ (c3: cation-anion RDF of the 1M-atom ionic
+liquid; c5: all 10 group pairs of the 4M-atom mixed box, cell-binned; use --frames-per-step 2 there); the default c2 is the
+headline the driver measures.
 
 A "step" is one pass of the whole hot path over one batch of F frames (default 8): centres of both groups
 (K1), slab prep, all-pairs minimum-image histogram (K3).  `value` is measured with the batch already resident
