@@ -17,7 +17,7 @@ namespace b2a
 constexpr int kStages   = 4;
 // the two-molecules-per-thread orientation variant stages 512-molecule tiles: three of them keep three blocks on an SM
 __host__ __device__ constexpr int stream_stages(int mode, int var) { return ((mode == 2 && var == 1) || (mode == 0 && var == 2)) ? 3 : kStages; }
-constexpr int kFastQueue = 1024;  // undecided (molecule, frame) entries per block; drained when half full, overflow runs inline
+constexpr int kFastQueue = 1024;  // undecided (molecule, frame) entries per block, drained at the end of the block; overflow is evaluated inline
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
