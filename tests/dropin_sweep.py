@@ -44,7 +44,7 @@ PROGRAMS = {
     "calc_qmsd_pore3": (1, 0, 0, [], ["-low", "-up"]),
     "calc_qmsd_pore3_thread": (1, 0, 0, [], ["-low", "-up"]),
     "calc_radius_distribution_in_pore": (1, 0, 0, ["-upPos", "-lowPos", "-centerX", "-centerY", "-Rmof"], []),
-    "calc_radius_distribution_in_pore_time": (1, 0, 0, ["-centerX", "-centerY", "-Cr", "-CR"], []),
+    "calc_radius_distribution_in_pore_time": (1, 0, 0, ["-centerX", "-centerY", "-Cr", "-CR", "-x1", "-x2", "-y1", "-y2", "-z1", "-z2"], []),
     "calc_radius_integration_distribution_in_pore": (1, 0, 0, ["-centerX", "-centerY", "-Cr", "-CR"], []),
     "calc_rdf_mof_pore": (2, 0, 0, ["-up", "-low", "-centerX", "-centerY", "-Rmof"], []),
     "calc_rdf_region": (2, 0, 0, ["-up", "-low", "-low2", "-up2"], []),
@@ -54,9 +54,9 @@ PROGRAMS = {
 
 
 def _value(opt, L):
-    if opt.startswith("-up"):
+    if opt.startswith("-up") or opt in ("-x2", "-y2", "-z2"):
         return 0.9 * L
-    if opt.startswith("-low"):
+    if opt.startswith("-low") or opt in ("-x1", "-y1", "-z1"):
         return 0.1 * L
     if opt in ("-centerX", "-centerY", "-c1", "-c2"):
         return 0.5 * L
@@ -67,6 +67,14 @@ def _value(opt, L):
     if opt == "-Rmin":
         return 0.7
     raise KeyError(opt)
+
+
+# programs whose own arrays are overrun by the generic region values get hand-made arguments (as a function of the box length)
+ARGS_OVERRIDE = {
+    # no r <= CR test in the program (:88-92): the box must lie inside the circle, or rdf[meZ] is out of bounds and Eigen aborts
+    "calc_radius_distribution_in_pore_time": lambda L: ["-centerX", 0.5 * L, "-centerY", 0.5 * L, "-Cr", 0.0, "-CR", 0.45 * L, "-dr", 0.03,
+                                                        "-x1", 0.3 * L, "-x2", 0.7 * L, "-y1", 0.3 * L, "-y2", 0.7 * L, "-z1", 0.1 * L, "-z2", 0.9 * L],
+}
 
 
 def case(name):
@@ -86,6 +94,8 @@ def case(name):
         args += [o, f"{_value(o, L):.4f}"]
     for o in rvecs:
         args += [o] + [f"{_value(o, L):.4f}"] * 3
+    if name in ARGS_OVERRIDE:
+        args = [a if isinstance(a, str) else f"{a:.4f}" for a in ARGS_OVERRIDE[name](L)]
     rng = np.random.default_rng(9103)
     v = rng.normal(size=(K, system.natoms, 3)).astype(np.float32) if need_v else None
     f = rng.normal(size=(K, system.natoms, 3)).astype(np.float32) if need_f else None

@@ -73,7 +73,7 @@ def test_density_slit_fused_port_matches_reference_build(tmp_path, monkeypatch):
     assert len(ref) == 60 and got == ref and any(float(ln.split()[1]) > 0 for ln in ref)
 
 
-@pytest.mark.parametrize("name", ["calc_density_distribution_in_pore", "calc_areaDensityDistributionPore", "calc_numdens_pore", "calc_pair_dist", "calc_radius_distribution_in_pore", "calc_density_time"])
+@pytest.mark.parametrize("name", ["calc_density_distribution_in_pore", "calc_areaDensityDistributionPore", "calc_numdens_pore", "calc_pair_dist", "calc_radius_distribution_in_pore", "calc_density_time", "calc_radius_distribution_in_pore_time"])
 @pytest.mark.parametrize("batch", ["16", "4"])
 def test_region_fused_ports_match_reference_builds(name, batch, tmp_path, monkeypatch):
     """The rest of the density family (z profile inside a cylinder, 2-D map behind three region tests, wrapped box count) ported to
