@@ -16,6 +16,8 @@
 #include <cstring>
 #include <map>
 #include <sstream>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 struct gmx_output_env_t
@@ -730,32 +732,55 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
     {
         /* XTC frames are independent: slice K compressed frames out of the file, then decode them on K host threads
          * straight into the caller's (pinned) batch */
-        std::vector<std::vector<unsigned char>> blobs;
-        while ((int)blobs.size() < max_frames)
+        // The reader (this thread) slices the frames off the file one after the other; the decode threads pick a frame up as
+        // soon as it has been read, so the serial read of the batch overlaps its decode.
+        std::vector<std::vector<unsigned char>> blobs(max_frames);
+        std::vector<int>                        bad(std::max(max_frames, 1), 0);
+        int nthreads = std::min<int>(max_frames, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+        if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(max_frames, std::atoi(e)));
+        std::mutex              mu;
+        std::condition_variable cv;
+        int                     ready = 0, claimed = 0;   // frames read so far / frames handed to a decode thread
+        bool                    done = false;             // the reader has stopped (batch full or end of file)
+        auto work = [&]() {
+            for (;;)
+            {
+                int k;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return claimed < ready || done; });
+                    if (claimed >= ready) return;         // done, and nothing left
+                    k = claimed++;
+                }
+                if (!xdrtraj::xtc_decode_coords(blobs[k].data(), blobs[k].size(), st->natoms, x_out + n3 * k)) bad[k] = 1;
+            }
+        };
+        std::vector<std::thread> pool;
+        if (nthreads > 1)
+            for (int t = 0; t < nthreads; ++t) pool.emplace_back(work);
+        int n = 0;
+        while (n < max_frames)
         {
             xdrtraj::XtcHeader h;
             if (!xtc_next(st, &h)) break;
-            const size_t k = blobs.size();
-            time_out[k]    = h.time;
-            std::memcpy(box_out + 9 * k, h.box, 9 * sizeof(float));
-            blobs.emplace_back(std::move(st->blob));
+            time_out[n] = h.time;
+            std::memcpy(box_out + 9 * (size_t)n, h.box, 9 * sizeof(float));
+            blobs[n] = std::move(st->blob);
             st->nread++;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready = ++n;
+            }
+            cv.notify_one();
         }
-        const int n = (int)blobs.size();
-        int       nthreads = std::min<int>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
-        if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(n, std::atoi(e)));
-        std::vector<int> bad(std::max(n, 1), 0);
-        auto work = [&](int t) {
-            for (int k = t; k < n; k += nthreads)
-                if (!xdrtraj::xtc_decode_coords(blobs[k].data(), blobs[k].size(), st->natoms, x_out + n3 * k)) bad[k] = 1;
-        };
-        if (nthreads <= 1) work(0);
-        else
         {
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nthreads; ++t) pool.emplace_back(work, t);
-            for (auto& th : pool) th.join();
+            std::lock_guard<std::mutex> lk(mu);
+            done = true;
         }
+        cv.notify_all();
+        if (nthreads > 1)
+            for (auto& th : pool) th.join();
+        else work();
         for (int k = 0; k < n; ++k)
             if (bad[k]) gmx_fatal(FARGS, "%s: corrupt XTC coordinate block", st->fn.c_str());
         return n;
