@@ -96,3 +96,22 @@ def test_stub_trajectory_roundtrip(tmp_path):
                        env=env, input="0\n")
     assert r.returncode == 0, r.stderr
     assert "Nr. of molecules in group: 64" in r.stdout
+
+
+def test_dropin_build_is_complete():
+    """Where the reference was present at build time (this container), build/dropin holds every live program of the sweep table, the
+    ported programs named in dropin/Makefile, and oracle/_ref the matching reference builds."""
+    import re
+    import dropin_sweep as SW
+    dropin, ref = os.path.join(ROOT, "build", "dropin"), os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isdir(dropin) or not os.path.exists(os.path.join(ref, "calc_rdf_region")):
+        pytest.skip("drop-in programs not built (needs /root/reference at build time)")
+    for name in SW.PROGRAMS:
+        assert os.access(os.path.join(dropin, name), os.X_OK), name
+        assert os.access(os.path.join(ref, name), os.X_OK), name
+    mk = open(os.path.join(ROOT, "dropin", "Makefile")).read()
+    fused = re.search(r"^FUSED\s*:=\s*(.*)$", mk, re.M).group(1).split()
+    assert len(fused) >= 12
+    for name in fused:
+        assert os.access(os.path.join(dropin, name), os.X_OK), name
+        assert os.path.exists(os.path.join(ROOT, "dropin", name + ".cpp")), name
