@@ -547,7 +547,7 @@ inline bool trr_parse_header(const unsigned char* p, size_t avail, TrrHeader* h)
     size_t off = 4;
     int    slen = (int)be32(p + off); off += 4;           // strlen(version) + 1
     int    n2   = (int)be32(p + off); off += 4;
-    if (n2 == slen) { n2 = (int)be32(p + off); off += 4; } // the string itself is preceded by its own length fields
+    if (n2 == slen) { n2 = (int)be32(p + off); off += 4; } // tolerate writers that repeat strlen + 1 before the XDR string
     if (n2 < 0 || n2 > 64) return false;
     off += ((size_t)n2 + 3) & ~(size_t)3;
     int* f[13] = { &h->ir_size, &h->e_size, &h->box_size, &h->vir_size, &h->pres_size, &h->top_size, &h->sym_size,
@@ -578,7 +578,7 @@ inline void trr_write_frame(Writer& w, int natoms, int step, float time, const f
 {
     static const char version[] = "GMX_trn_file";
     w.i32(kTrrMagic);
-    w.i32(13); w.i32(13); w.i32(12);
+    w.i32(13); w.i32(12);                                  // strlen + 1 (checked by readers), then the XDR string: length, bytes
     w.opaque(reinterpret_cast<const unsigned char*>(version), 12);
     const int n3 = natoms * 3 * 4;
     w.i32(0); w.i32(0); w.i32(36); w.i32(0); w.i32(0); w.i32(0); w.i32(0);

@@ -1,9 +1,12 @@
 """Real-trajectory ingestion: the XTC / TRR codecs of the libgromacs stand-in (gmxstub/xdrtraj.hpp).
 libgromacs 2020.1 itself is not available and the reference holds no trajectory fixtures, so these formats are pinned
-against the codec's own writer: decoding returns exactly the quantised coordinates the format defines, for every code
+against (1) the codec's own writer: decoding returns exactly the quantised coordinates the format defines, for every code
 path of the compression (small systems, water-like runs, huge coordinate ranges), frame by frame and through the
-multi-threaded batch reader; and the reference's own analysis program gives the same output from an XTC file as from the
-raw-float file holding the same quantised coordinates."""
+multi-threaded batch reader; (2) an independent pure-Python reader of the published formats (tests/xtc_classic.py, no
+shared code, classic algorithm) that must see the same frames in the files the stand-in writes; (3) XTC and double-
+precision TRR files packed by hand from the format description, which the stand-in must read; and the reference's own
+analysis program gives the same output from an XTC file as from the raw-float file holding the same quantised
+coordinates."""
 import ctypes as C
 import os
 
@@ -11,6 +14,7 @@ import numpy as np
 import pytest
 
 import refprog
+import xtc_classic
 from gmx2020postanalysis_b200 import synth, trajio
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -80,6 +84,12 @@ def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, cas
     exp = x if case == "tiny" else quantise(x, prec)
     assert np.array_equal(got, exp)
     assert np.array_equal(gt, times) and np.array_equal(gbox, np.repeat(np.asarray(box, np.float32).reshape(1, 9), n, axis=0))
+    # an independent reader of the published format (tests/xtc_classic.py: plain bit stream, big-integer triples) sees the
+    # same frames: header layout, bit order, run / swap logic and the adaptive width all agree with the stand-in's codec
+    indep = xtc_classic.read_frames(path)
+    assert len(indep) == n and all(fr["natoms"] == natoms for fr in indep)
+    assert np.array_equal(np.stack([fr["x"] for fr in indep]), got)
+    assert [fr["time"] for fr in indep] == list(times) and all(np.array_equal(fr["box"], gbox[0]) for fr in indep)
     if case == "water":                        # neighbours are coded as small differences: well under half the raw size
         assert os.path.getsize(path) < 0.45 * x.nbytes
     # the batch reader decodes the frames on several threads: same result, any batch size
@@ -102,6 +112,10 @@ def test_trr_round_trip_exact(stub, tmp_path):
     assert n == K and natoms == x.shape[1]
     assert np.array_equal(gx, x) and np.array_equal(gv, v) and np.array_equal(gf, f)
     assert np.array_equal(gt, np.arange(K, dtype=np.float32))
+    indep = xtc_classic.read_trr_frames(path)          # independent reader of the published layout
+    assert len(indep) == K and all(fr["natoms"] == x.shape[1] for fr in indep)
+    assert all(np.array_equal(fr["x"], x[k]) and np.array_equal(fr["v"], v[k]) and np.array_equal(fr["f"], f[k])
+               and np.array_equal(fr["box"], box[0]) and fr["step"] == k for k, fr in enumerate(indep))
     # coordinates only: v / f blocks are skipped
     n, _, gx, gv, _, _, _ = read_all(stub, path, K, x.shape[1], TRX_READ_X)
     assert n == K and np.array_equal(gx, x) and not gv.any()
@@ -110,6 +124,62 @@ def test_trr_round_trip_exact(stub, tmp_path):
     assert stub.gmxstub_write_trr(path2.encode(), x.shape[1], K, _ptr(x), None, None, _ptr(box), 1, None) == 0
     n, _, gx, _, _, _, _ = read_all(stub, path2, K, x.shape[1], TRX_READ_X | TRX_READ_V)
     assert n == K and np.array_equal(gx, x)
+
+
+def test_xtc_written_elsewhere_without_runs(stub, tmp_path):
+    """An XTC file packed by hand in Python from the published format by the simplest legal writer (every atom as a full
+    triple, run flag 0): no stand-in encoder involved, so the stand-in's decoder is checked against the format itself."""
+    import struct
+    rng = np.random.default_rng(6)
+    K, natoms, prec = 2, 40, 1000.0
+    ints = rng.integers(-3000, 9000, size=(K, natoms, 3))
+    blob = b""
+    for k in range(K):
+        lo, hi = ints[k].min(axis=0), ints[k].max(axis=0)
+        sizes = [int(hi[q] - lo[q] + 1) for q in range(3)]
+        nbits = (sizes[0] * sizes[1] * sizes[2]).bit_length()
+        stream, count = 0, 0
+        for a in range(natoms):
+            u = [int(ints[k, a, q] - lo[q]) for q in range(3)]
+            val, left = (u[0] * sizes[1] + u[1]) * sizes[2] + u[2], nbits
+            while left > 8:                               # least significant piece first
+                stream = (stream << 8) | (val & 0xFF); val >>= 8; left -= 8; count += 8
+            stream = (stream << left) | val; count += left
+            stream <<= 1; count += 1                      # run flag 0
+        pad = -count % 8
+        data = (stream << pad).to_bytes((count + pad) // 8, "big")
+        blob += struct.pack(">iiif", 1995, natoms, k, 1.5 * k) + (np.eye(3) * 12).astype(">f4").tobytes()
+        blob += struct.pack(">if", natoms, prec) + struct.pack(">6i", *[int(t) for t in lo], *[int(t) for t in hi])
+        blob += struct.pack(">ii", 20, len(data)) + data + b"\0" * (-len(data) % 4)
+    path = str(tmp_path / "hand.xtc")
+    open(path, "wb").write(blob)
+    n, na, gx, _, _, gbox, gt = read_all(stub, path, K + 1, natoms)
+    assert n == K and na == natoms
+    assert np.array_equal(gx, ints.astype(np.float32) * (np.float32(1.0) / np.float32(prec)))
+    assert np.array_equal(gt, np.float32(1.5) * np.arange(K, dtype=np.float32)) and gbox[0][0] == 12 and gbox[0][4] == 12
+    assert np.array_equal(np.stack([fr["x"] for fr in xtc_classic.read_frames(path)]), gx)
+
+
+def test_trr_written_elsewhere_double_precision(stub, tmp_path):
+    """A double-precision TRR frame sequence laid out by hand from the published format (no stand-in writer involved):
+    header with strlen + 1 and the XDR string, 8-byte reals for time / lambda / box / x / v."""
+    import struct
+    rng = np.random.default_rng(5)
+    K, natoms = 3, 11
+    x = rng.normal(size=(K, natoms, 3)); v = rng.normal(size=(K, natoms, 3))
+    box = np.diag([3.0, 4.0, 5.0]).ravel()
+    blob = b""
+    for k in range(K):
+        blob += struct.pack(">iii", 1993, 13, 12) + b"GMX_trn_file"
+        blob += struct.pack(">13i", 0, 0, 72, 0, 0, 0, 0, natoms * 24, natoms * 24, 0, natoms, 10 * k, 0)
+        blob += struct.pack(">dd", 0.5 * k, 0.0) + box.astype(">f8").tobytes() + x[k].astype(">f8").tobytes() + v[k].astype(">f8").tobytes()
+    path = str(tmp_path / "d.trr")
+    open(path, "wb").write(blob)
+    n, na, gx, gv, _, gbox, gt = read_all(stub, path, K + 1, natoms, TRX_READ_X | TRX_READ_V)
+    assert n == K and na == natoms
+    assert np.array_equal(gx, x.astype(np.float32)) and np.array_equal(gv, v.astype(np.float32))
+    assert np.array_equal(gbox[0], box.astype(np.float32)) and np.array_equal(gt, np.float32(0.5) * np.arange(K, dtype=np.float32))
+    assert [fr["step"] for fr in xtc_classic.read_trr_frames(path)] == [0, 10, 20]
 
 
 def test_reference_program_reads_xtc_like_raw(stub, tmp_path):
