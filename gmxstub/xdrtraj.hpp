@@ -200,6 +200,59 @@ inline void receiveints(BitBuf& b, int num_of_ints, int num_of_bits, const unsig
     nums[0] = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
 }
 
+// the decoder's lambdas must be inlined: out of line, the bit position they capture by reference lives in memory and every
+// field pays a store-to-load round trip
+#if defined(__GNUC__)
+#define XDRTRAJ_INLINE __attribute__((always_inline))
+#else
+#define XDRTRAJ_INLINE
+#endif
+
+// ---- decoder helpers ----------------------------------------------------------------------------------------------------
+// q = v / d by one multiply-high with m = floor((2^64 - 1) / d) + 1: m d = 2^64 + e with 0 < e <= d, so
+// floor(v m / 2^64) = floor(v / d + v e / (d 2^64)) is the quotient whenever v e < 2^64, i.e. for every v <= lim =
+// (2^64 - 1) / d.  The large triples of ordinary systems (three 13-bit ranges: v < 2^39, d < 2^13) stay on this path.
+struct XtcDiv
+{
+    uint32_t d;
+    uint64_t m, lim;
+    static XtcDiv make(uint32_t d) { return XtcDiv{ d, d > 1 ? (~0ull / d) + 1 : 0, d > 1 ? ~0ull / d : 0 }; }
+};
+
+// constants that turn the next n <= 56 stream bits (as little-endian bytes b) into the value sendints() packed:
+// (b & mask) are the whole bytes, byte number n / 8 holds the remaining n % 8 bits at its top
+struct XtcField
+{
+    int      n, shift, drop;
+    uint64_t mask;
+    static XtcField make(int n)
+    {
+        const int full = n >> 3, rem = n & 7;
+        return XtcField{ n, 8 * (full < 8 ? full : 0), 8 - rem, full >= 8 ? ~0ull : ((1ull << (8 * full)) - 1ull) };
+    }
+};
+
+struct XtcSmallTable     // per adaptive width index: divisor, field constants, half range
+{
+    XtcDiv   div[128];
+    XtcField field[128];
+    int      half[128];
+    static const XtcSmallTable& get()
+    {
+        static const XtcSmallTable t = [] {
+            XtcSmallTable s{};
+            for (int k = 0; k < LASTIDX && k < 128; ++k)
+            {
+                s.div[k]   = XtcDiv::make((uint32_t)magicints[k]);
+                s.field[k] = XtcField::make(k);
+                s.half[k]  = magicints[k] / 2;
+            }
+            return s;
+        }();
+        return t;
+    }
+};
+
 // ---- XTC coordinate block: decode --------------------------------------------------------------------------------------
 // p points at the second natoms field of a frame (after magic, natoms, step, time, box); returns bytes consumed, 0 on error
 inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms, float* x, float* precision_out = nullptr)
@@ -236,55 +289,56 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
     }
     else bitsize = sizeofints(3, sizeint);
 
-    int      smaller  = magicints[std::max(FIRSTIDX, smallidx - 1)] / 2;
-    int      smallnum = magicints[smallidx] / 2;
-
-    // Decoder state.  The classic implementation reads the stream one byte at a time and undoes the mixed-radix packing by
-    // long division over a byte array; here bits come out of a 64-bit window (refilled four bytes at a time) and a packed
-    // triple of at most 64 bits is unpacked with two multiply-high divisions by an invariant divisor (the divisor of the
-    // small triples only changes when the run-length flag says so).  Same integers, ~2.5x the frames per second per thread.
-    std::vector<unsigned char> data(padded + 16, 0);   // the window may be refilled up to 8 bytes past the end of the stream
+    // Decoder state.  The classic implementation reads the stream one byte at a time, undoes the mixed-radix packing by long
+    // division over a byte array and carries the adaptive width along in three variables; here
+    //  * a field of up to 56 bits comes out of one unaligned 64-bit load at the current bit position (no refill branch),
+    //    and the "whole bytes least significant first, then the remaining high bits" order of sendints() is one byte swap,
+    //    one mask and one shift with constants that depend only on the field width;
+    //  * a packed triple of at most 64 bits is unpacked with two multiply-high divisions by an invariant divisor;
+    //  * everything that depends on the adaptive width `smallidx` (divisor, field constants, offset) is a table look-up,
+    //    and the run-length flag is consumed without a branch.
+    // Same integers as the classic code.
+    constexpr size_t kSlack = 192;                     // one loop iteration consumes < 120 bytes (checked at its top)
+    std::vector<unsigned char> data(padded + kSlack, 0);
     std::memcpy(data.data(), p + off, nbytes);
     const unsigned char* q = data.data();
-    size_t   pos = 0;
-    uint64_t win = 0;      // the low `have` bits are the next bits of the stream, most significant first
-    int      have = 0;
-    auto bits = [&](int n) -> uint32_t {                       // 0 <= n <= 32
-        if (have < n) { win = (win << 32) | be32(q + pos); pos += 4; have += 32; }
-        have -= n;
-        return n == 32 ? (uint32_t)(win >> have) : (uint32_t)(win >> have) & ((1u << n) - 1u);
+    size_t bitpos = 0;
+    auto window = [&]() XDRTRAJ_INLINE -> uint64_t {                          // the next >= 57 bits of the stream, left-aligned
+        uint64_t w;
+        std::memcpy(&w, q + (bitpos >> 3), 8);
+        return __builtin_bswap64(w) << (bitpos & 7);
     };
-    // the value of an n-bit field as sendints() packed it: whole bytes least significant first, then the remaining high bits
+    auto bits = [&](int n) XDRTRAJ_INLINE -> uint32_t {                       // 0 <= n <= 32
+        if (n == 0) return 0;
+        const uint32_t v = (uint32_t)(window() >> (64 - n));
+        bitpos += (size_t)n;
+        return v;
+    };
+    const XtcField fbig = XtcField::make(bitsize);
+    auto packed56 = [&](const XtcField& f) XDRTRAJ_INLINE -> uint64_t {       // f.n <= 56
+        const uint64_t b = __builtin_bswap64(window());        // stream bytes in little-endian order
+        bitpos += (size_t)f.n;
+        return (b & f.mask) | ((((b >> f.shift) & 0xffu) >> f.drop) << f.shift);
+    };
+    // the value of an n-bit field of any width, 32 bits at a time
     auto packed = [&](int n) -> uint64_t {                     // 0 < n <= 64
         uint64_t v = 0;
         int      sh = 0;
         for (; n >= 32; n -= 32, sh += 32) v |= (uint64_t)__builtin_bswap32(bits(32)) << sh;
-        if (n > 0)
-        {
-            // left-align the n bits, swap the bytes: the whole bytes land in place, the trailing partial byte (its `rem` bits
-            // sit at the top of their byte) is shifted down
-            const int      full = n >> 3, rem = n & 7;
-            const uint32_t w    = __builtin_bswap32(bits(n) << (32 - n));
-            uint32_t       u    = full ? (full == 4 ? w : (w & ((1u << (8 * full)) - 1u))) : 0u;
-            if (rem) u |= (((w >> (8 * full)) & 0xffu) >> (8 - rem)) << (8 * full);
-            v |= (uint64_t)u << sh;
-        }
+        if (n > 0) v |= packed56(XtcField::make(n)) << sh;
         return v;
     };
-    struct Div { uint32_t d; uint64_t m; };                    // q = v / d for v < 2^32 by one multiply-high
-    auto mkdiv = [](uint32_t d) { return Div{ d, d > 1 ? (~0ull / d) + 1 : 0 }; };
-    auto divmod = [](uint64_t v, const Div& dv, uint32_t& r) -> uint64_t {
-        if (v >> 32 || dv.d <= 1) { const uint64_t qq = dv.d ? v / dv.d : 0; r = (uint32_t)(v - qq * dv.d); return qq; }
+    auto divmod = [](uint64_t v, const XtcDiv& dv, uint32_t& r) XDRTRAJ_INLINE -> uint64_t {
+        if (v > dv.lim) { const uint64_t qq = dv.d ? v / dv.d : 0; r = (uint32_t)(v - qq * dv.d); return qq; }
         const uint64_t qq = (uint64_t)(((unsigned __int128)v * dv.m) >> 64);
         r = (uint32_t)(v - qq * dv.d);
         return qq;
     };
-    Div dsmall = mkdiv((unsigned)magicints[smallidx]);
-    const Div dl1 = mkdiv(sizeint[1]), dl2 = mkdiv(sizeint[2]);
-    auto triple = [&](int nbits_, const Div& d1, const Div& d2, int out[3]) {
-        if (nbits_ <= 64)
+    const XtcDiv dl1 = XtcDiv::make(sizeint[1]), dl2 = XtcDiv::make(sizeint[2]);
+    auto triple = [&](const XtcField& f, const XtcDiv& d1, const XtcDiv& d2, int out[3]) XDRTRAJ_INLINE {
+        if (f.n <= 64)
         {
-            uint64_t v = packed(nbits_);
+            uint64_t v = f.n <= 56 ? packed56(f) : packed(f.n);
             uint32_t r;
             v = divmod(v, d2, r); out[2] = (int)r;
             v = divmod(v, d1, r); out[1] = (int)r;
@@ -293,13 +347,14 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
         }
         // wider than 64 bits (coordinate ranges close to 2^24 per component): 128-bit arithmetic
         unsigned __int128 v = 0;
-        int sh = 0, n = nbits_;
+        int sh = 0, n = f.n;
         for (; n >= 32; n -= 32, sh += 32) v |= (unsigned __int128)__builtin_bswap32(bits(32)) << sh;
         if (n > 0) v |= (unsigned __int128)packed(n) << sh;
         out[2] = (int)(v % d2.d); v /= d2.d;
         out[1] = (int)(v % d1.d); v /= d1.d;
         out[0] = (int)v;
     };
+    const XtcSmallTable& small = XtcSmallTable::get();
 
     const float inv = 1.0f / precision;
     float*      lfp = x;
@@ -307,31 +362,31 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
     int         thiscoord[3], prevcoord[3];
     while (i < lsize)
     {
-        if (pos > nbytes + 12) return 0;   // corrupt stream
+        if ((bitpos >> 3) > nbytes) return 0;   // corrupt stream
         if (bitsize == 0)
         {
             thiscoord[0] = (int)bits((int)bitsizeint[0]);
             thiscoord[1] = (int)bits((int)bitsizeint[1]);
             thiscoord[2] = (int)bits((int)bitsizeint[2]);
         }
-        else triple(bitsize, dl1, dl2, thiscoord);
+        else triple(fbig, dl1, dl2, thiscoord);
         i++;
         for (int k = 0; k < 3; ++k) { thiscoord[k] += minint[k]; prevcoord[k] = thiscoord[k]; }
-        const unsigned flag = bits(1);
-        int            is_smaller = 0;
-        if (flag == 1)
-        {
-            run        = (int)bits(5);
-            is_smaller = run % 3;
-            run -= is_smaller;
-            is_smaller--;
-        }
+        // one flag bit, and five more bits (new run length and width change) only when it is set
+        const uint32_t six  = (uint32_t)(window() >> 58);
+        const int      flag = (int)(six >> 5), r5 = (int)(six & 31u), m3 = r5 % 3;
+        bitpos += (size_t)(1 + 5 * flag);
+        const int is_smaller = (m3 - 1) & -flag;
+        run ^= (run ^ (r5 - m3)) & -flag;
         if (run > 0)
         {
             if (i + run / 3 > lsize) return 0;
+            const XtcDiv&   ds = small.div[smallidx];
+            const XtcField& fs = small.field[smallidx];
+            const int       smallnum = small.half[smallidx];
             for (int k = 0; k < run; k += 3)
             {
-                triple(smallidx, dsmall, dsmall, thiscoord);
+                triple(fs, ds, ds, thiscoord);
                 i++;
                 for (int d = 0; d < 3; ++d) thiscoord[d] += prevcoord[d] - smallnum;
                 if (k == 0)
@@ -349,19 +404,8 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
         {
             *lfp++ = thiscoord[0] * inv; *lfp++ = thiscoord[1] * inv; *lfp++ = thiscoord[2] * inv;
         }
-        smallidx += is_smaller;
+        smallidx += is_smaller;                 // the offset and divisor of the small triples follow through the tables
         if (smallidx < FIRSTIDX || smallidx >= LASTIDX) return 0;
-        if (is_smaller < 0)
-        {
-            smallnum = smaller;
-            smaller  = smallidx > FIRSTIDX ? magicints[smallidx - 1] / 2 : 0;
-        }
-        else if (is_smaller > 0)
-        {
-            smaller  = smallnum;
-            smallnum = magicints[smallidx] / 2;
-        }
-        if (is_smaller != 0) dsmall = mkdiv((unsigned)magicints[smallidx]);
     }
     return off + padded;
 }

@@ -62,7 +62,7 @@ def quantise(x, precision):
     return li.astype(np.float32) * (np.float32(1.0) / p)
 
 
-@pytest.mark.parametrize("case", ["water", "il", "tiny", "huge_range", "precision100"])
+@pytest.mark.parametrize("case", ["water", "il", "tiny", "huge_range", "precision100", "wide60", "wide66", "wide_runs30", "wide_runs400"])
 def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, case):
     prec = 1000.0
     if case == "water":
@@ -74,6 +74,13 @@ def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, cas
     elif case == "huge_range":                 # coordinate span > 2^24 / precision: every component coded with its own bit width
         rng = np.random.default_rng(2)
         x = (rng.uniform(-20000, 20000, size=(2, 64, 3))).astype(np.float32); box = np.eye(3, dtype=np.float32).ravel() * 4e4
+    elif case in ("wide60", "wide66"):         # packed triples of 57..64 bits and of more than 64 bits (128-bit unpacking)
+        span = 500.0 if case == "wide60" else 2000.0
+        x = np.random.default_rng(7).uniform(-span, span, size=(2, 50, 3)).astype(np.float32); box = np.eye(3, dtype=np.float32).ravel() * 2 * span
+    elif case.startswith("wide_runs"):         # runs whose small triples are 45..70 bits wide: triplets of atoms scattered far apart
+        rng = np.random.default_rng(8); spread = float(case[9:])
+        cen = rng.uniform(-2000, 2000, size=(2, 40, 1, 3))
+        x = (cen + rng.uniform(-spread, spread, size=(2, 40, 3, 3))).reshape(2, 120, 3).astype(np.float32); box = np.eye(3, dtype=np.float32).ravel() * 5000
     else:
         system = synth.water_box(800, 2.9, seed=83); x = system.frames(0, 2); box = system.box9(); prec = 100.0
     path = str(tmp_path / "t.xtc")
