@@ -19,6 +19,8 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <sys/mman.h>
+#include <sys/stat.h>
 
 struct gmx_output_env_t
 {
@@ -488,6 +490,12 @@ struct t_trxstatus
     std::vector<float> scratch;
     int     fmt     = 0; /* 0: B2ATRJ01, 1: XTC, 2: TRR (xdrtraj.hpp) */
     std::vector<unsigned char> blob;
+    /* XTC files are mapped read-only: frames are decoded straight out of the page cache (no read() copy, no per-frame
+     * buffer), and the batch reader's decode threads fault the pages in themselves.  map == nullptr: FILE* path. */
+    const unsigned char* map = nullptr;
+    size_t  map_size = 0, mpos = 0;
+    const unsigned char* cur = nullptr; /* coordinate block of the frame xtc_next() delivered last ... */
+    size_t  cur_avail = 0;              /* ... and the readable bytes from there on */
 };
 
 namespace
@@ -544,10 +552,32 @@ bool next_selected(t_trxstatus* st, float hdr[10])
 /* ---- real GROMACS wire formats (XTC / TRR), decoded by xdrtraj.hpp ------------------------------------------------ */
 bool read_bytes(FILE* fp, void* dst, size_t n) { return std::fread(dst, 1, n, fp) == n; }
 
-/* XTC: positions the file after the coordinate block of the next selected frame; the block is left in st->blob.
- * hdr receives time and box.  Returns false at end of file.                                                         */
+/* XTC: positions the file after the coordinate block of the next selected frame; the block is at st->cur (inside the
+ * mapping, or in st->blob on the FILE* path).  hdr receives time and box.  Returns false at end of file.               */
 bool xtc_next(t_trxstatus* st, xdrtraj::XtcHeader* h)
 {
+    while (st->map)
+    {
+        const size_t hb = xdrtraj::kXtcHeaderBytes;
+        if (st->mpos + hb > st->map_size) return false;
+        const unsigned char* p = st->map + st->mpos;
+        if (!xdrtraj::xtc_parse_header(p, h)) gmx_fatal(FARGS, "%s: bad XTC frame header (magic)", st->fn.c_str());
+        if (h->natoms != st->natoms) gmx_fatal(FARGS, "%s: number of atoms changes between frames", st->fn.c_str());
+        const size_t npre = h->natoms <= 9 ? 4 : 40;
+        if (st->mpos + hb + npre > st->map_size) return false;
+        const size_t total = xdrtraj::xtc_coord_block_bytes(p + hb, h->natoms);
+        bool         past  = false;
+        const bool   sel   = time_selected(st, h->time, &past);
+        if (past) return false;
+        if (st->mpos + hb + total > st->map_size) gmx_fatal(FARGS, "%s: truncated XTC frame", st->fn.c_str());
+        st->next++;
+        st->cur       = p + hb;
+        st->cur_avail = st->map_size - (st->mpos + hb);
+        st->mpos += hb + total;
+        if (!sel) continue;
+        if (!st->have_t0) { st->have_t0 = true; st->t0 = h->time; }
+        return true;
+    }
     for (;;)
     {
         unsigned char hb[xdrtraj::kXtcHeaderBytes];
@@ -567,6 +597,7 @@ bool xtc_next(t_trxstatus* st, xdrtraj::XtcHeader* h)
         st->blob.resize(total);
         std::memcpy(st->blob.data(), pre, npre);
         if (!read_bytes(st->fp, st->blob.data() + npre, total - npre)) gmx_fatal(FARGS, "%s: truncated XTC frame", st->fn.c_str());
+        st->cur = st->blob.data(); st->cur_avail = st->blob.size();
         return true;
     }
 }
@@ -607,6 +638,16 @@ t_trxstatus* open_trx(const char* fn)
     if (got >= 8 && xdrtraj::be32(first) == (uint32_t)xdrtraj::kXtcMagic)
     {
         st->fmt = 1; st->natoms = (int)xdrtraj::be32(first + 4); st->nframes = -1; st->fflags = 1;
+        struct stat sb;
+        if (!std::getenv("GMXSTUB_NO_MMAP") && fstat(fileno(st->fp), &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0)
+        {
+            void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fileno(st->fp), 0);
+            if (m != MAP_FAILED)
+            {
+                madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+                st->map = static_cast<const unsigned char*>(m); st->map_size = (size_t)sb.st_size;
+            }
+        }
         return st;
     }
     if (got >= 96 && xdrtraj::be32(first) == (uint32_t)xdrtraj::kTrrMagic)
@@ -640,7 +681,7 @@ bool deliver_xdr(t_trxstatus* st, t_trxframe* fr)
         for (int k = 0; k < 9; ++k) fr->box[k / 3][k % 3] = h.box[k];
         if ((st->want & (TRX_READ_X | TRX_NEED_X)) && fr->x)
         {
-            if (!xdrtraj::xtc_decode_coords(st->blob.data(), st->blob.size(), st->natoms, &fr->x[0][0]))
+            if (!xdrtraj::xtc_decode_coords(st->cur, st->cur_avail, st->natoms, &fr->x[0][0]))
                 gmx_fatal(FARGS, "%s: corrupt XTC coordinate block in frame %d", st->fn.c_str(), st->next - 1);
             fr->bX = TRUE;
         }
@@ -716,6 +757,7 @@ bool read_next_frame(const gmx_output_env_t* /*oenv*/, t_trxstatus* status, t_tr
 void close_trx(t_trxstatus* status)
 {
     if (!status) return;
+    if (status->map) munmap(const_cast<unsigned char*>(status->map), status->map_size);
     if (status->fp) std::fclose(status->fp);
     delete status;
 }
@@ -734,7 +776,9 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
          * straight into the caller's (pinned) batch */
         // The reader (this thread) slices the frames off the file one after the other; the decode threads pick a frame up as
         // soon as it has been read, so the serial read of the batch overlaps its decode.
-        std::vector<std::vector<unsigned char>> blobs(max_frames);
+        std::vector<std::vector<unsigned char>> blobs(st->map ? 0 : max_frames);   // FILE* path only: owned copies
+        std::vector<const unsigned char*>       src(std::max(max_frames, 1), nullptr);
+        std::vector<size_t>                     src_avail(std::max(max_frames, 1), 0);
         std::vector<int>                        bad(std::max(max_frames, 1), 0);
         int nthreads = std::min<int>(max_frames, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
         if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(max_frames, std::atoi(e)));
@@ -752,7 +796,7 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
                     if (claimed >= ready) return;         // done, and nothing left
                     k = claimed++;
                 }
-                if (!xdrtraj::xtc_decode_coords(blobs[k].data(), blobs[k].size(), st->natoms, x_out + n3 * k)) bad[k] = 1;
+                if (!xdrtraj::xtc_decode_coords(src[k], src_avail[k], st->natoms, x_out + n3 * k)) bad[k] = 1;
             }
         };
         std::vector<std::thread> pool;
@@ -765,7 +809,8 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
             if (!xtc_next(st, &h)) break;
             time_out[n] = h.time;
             std::memcpy(box_out + 9 * (size_t)n, h.box, 9 * sizeof(float));
-            blobs[n] = std::move(st->blob);
+            if (st->map) { src[n] = st->cur; src_avail[n] = st->cur_avail; }
+            else { blobs[n] = std::move(st->blob); src[n] = blobs[n].data(); src_avail[n] = blobs[n].size(); }
             st->nread++;
             {
                 std::lock_guard<std::mutex> lk(mu);

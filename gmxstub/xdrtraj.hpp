@@ -298,10 +298,18 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
     //  * everything that depends on the adaptive width `smallidx` (divisor, field constants, offset) is a table look-up,
     //    and the run-length flag is consumed without a branch.
     // Same integers as the classic code.
-    constexpr size_t kSlack = 192;                     // one loop iteration consumes < 120 bytes (checked at its top)
-    std::vector<unsigned char> data(padded + kSlack, 0);
-    std::memcpy(data.data(), p + off, nbytes);
-    const unsigned char* q = data.data();
+    // One loop iteration consumes < 120 bytes and the window load reads 8 bytes from the current position (the position is
+    // checked at the top of every iteration): with kSlack readable bytes behind the block (a frame inside a mapped file or
+    // a larger buffer) the stream is decoded in place, otherwise from a zero-padded copy.
+    constexpr size_t kSlack = 192;
+    std::vector<unsigned char> data;
+    const unsigned char*       q = p + off;
+    if (avail < off + padded + kSlack)
+    {
+        data.assign(padded + kSlack, 0);
+        std::memcpy(data.data(), p + off, nbytes);
+        q = data.data();
+    }
     size_t bitpos = 0;
     auto window = [&]() XDRTRAJ_INLINE -> uint64_t {                          // the next >= 57 bits of the stream, left-aligned
         uint64_t w;

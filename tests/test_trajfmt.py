@@ -63,7 +63,7 @@ def quantise(x, precision):
 
 
 @pytest.mark.parametrize("case", ["water", "il", "tiny", "huge_range", "precision100", "wide60", "wide66", "wide_runs30", "wide_runs400"])
-def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, case):
+def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, case, monkeypatch):
     prec = 1000.0
     if case == "water":
         system = synth.water_box(1500, 3.6, seed=81); x = system.frames(0, 5); box = system.box9()
@@ -104,6 +104,13 @@ def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, cas
         bx = np.zeros_like(x); bb = np.zeros((x.shape[0], 9), np.float32); bt = np.zeros(x.shape[0], np.float32)
         assert stub.gmxstub_read_batches(path.encode(), batch, x.shape[0], _ptr(bx), _ptr(bb), _ptr(bt)) == x.shape[0]
         assert np.array_equal(bx, exp) and np.array_equal(bt, times)
+    # the stand-in maps XTC files and decodes in place; the FILE* path (pipes, GMXSTUB_NO_MMAP) gives the same frames
+    monkeypatch.setenv("GMXSTUB_NO_MMAP", "1")
+    n2, _, got2, _, _, _, gt2 = read_all(stub, path, x.shape[0] + 3, x.shape[1])
+    assert n2 == n and np.array_equal(got2, exp) and np.array_equal(gt2, times)
+    bx = np.zeros_like(x); bb = np.zeros((x.shape[0], 9), np.float32); bt = np.zeros(x.shape[0], np.float32)
+    assert stub.gmxstub_read_batches(path.encode(), 2, x.shape[0], _ptr(bx), _ptr(bb), _ptr(bt)) == x.shape[0]
+    assert np.array_equal(bx, exp)
 
 
 def test_trr_round_trip_exact(stub, tmp_path):
