@@ -100,6 +100,26 @@ def main():
                              "frames_per_s_from_wall_difference": (K - K1) / max(t_long - t_short, 1e-9)}
             e2e["outputs_identical"] = open(os.path.join(td, "xtc.xvg")).read().split("\n")[3:] == open(os.path.join(td, "raw.xvg")).read().split("\n")[3:]
             out["fused_program"] = e2e
+            # an HBM-class analysis (the README's density template, K2 over all atoms): the device needs ~0.05 ms per frame, so
+            # this program runs at whatever rate the frames arrive (decode threads / file read, then the H2D copy)
+            exe2 = os.path.join(ROOT, "build", "dropin", "readme_template_fused")
+            if os.path.exists(exe2):
+                trajio.write_index(os.path.join(td, "all.ndx"), {"SOL": np.arange(system.natoms, dtype=np.int32)})
+                dens = {}
+                for batch in ("8", "16", "32"):
+                    for kind, trj in (("xtc", xtc), ("raw", raw)):
+                        loop = 1e30
+                        for rep in range(2):
+                            r = subprocess.run([exe2, "-f", trj, "-s", os.path.join(td, "c2.b2p"), "-n", os.path.join(td, "all.ndx"), "-o",
+                                                os.path.join(td, "dens_" + kind + ".xvg"), "-nbin", "100", "-dim", "2", "-low", "0", "-up", "%g" % box_l],
+                                               input="0\n", capture_output=True, text=True, env=dict(env, B2A_BATCH=batch), cwd=td)
+                            if r.returncode != 0:
+                                raise RuntimeError(r.stderr[-800:])
+                            m = re.search(r"frame loop ([0-9.]+) s", r.stdout)
+                            loop = min(loop, float(m.group(1)))
+                        dens.setdefault(kind, {})["batch_" + batch] = K / loop
+                dens["outputs_identical"] = open(os.path.join(td, "dens_xtc.xvg")).read().split("\n")[3:] == open(os.path.join(td, "dens_raw.xvg")).read().split("\n")[3:]
+                out["density_program_frames_per_s"] = dens
     print(json.dumps(out))
 
 
