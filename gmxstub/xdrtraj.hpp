@@ -107,7 +107,8 @@ inline void sendbits(BitBuf& b, int num_of_bits, unsigned num)
 {
     while (num_of_bits >= 8)
     {
-        b.lastbyte   = (b.lastbyte << 8) | ((num >> (num_of_bits - 8)) & 0xff);
+        // (fields wider than 32 bits only ever carry leading zeros: sendints() pads a short number this way)
+        b.lastbyte   = (b.lastbyte << 8) | (num_of_bits - 8 < 32 ? ((num >> (num_of_bits - 8)) & 0xff) : 0u);
         b.c[b.cnt++] = (unsigned char)(b.lastbyte >> b.lastbits);
         num_of_bits -= 8;
     }
@@ -280,7 +281,7 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
     if (avail < off + padded || smallidx < FIRSTIDX || smallidx >= LASTIDX) return 0;
 
     unsigned sizeint[3], bitsizeint[3] = { 0, 0, 0 };
-    for (int k = 0; k < 3; ++k) sizeint[k] = (unsigned)(maxint[k] - minint[k] + 1);
+    for (int k = 0; k < 3; ++k) sizeint[k] = (unsigned)maxint[k] - (unsigned)minint[k] + 1u;   // unsigned: a corrupt header must not be UB
     int bitsize;
     if ((sizeint[0] | sizeint[1] | sizeint[2]) > 0xffffff)
     {
@@ -379,7 +380,8 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
         }
         else triple(fbig, dl1, dl2, thiscoord);
         i++;
-        for (int k = 0; k < 3; ++k) { thiscoord[k] += minint[k]; prevcoord[k] = thiscoord[k]; }
+        // (sums in unsigned arithmetic: identical for valid files, and a corrupt stream wraps instead of overflowing)
+        for (int k = 0; k < 3; ++k) { thiscoord[k] = (int)((unsigned)thiscoord[k] + (unsigned)minint[k]); prevcoord[k] = thiscoord[k]; }
         // one flag bit, and five more bits (new run length and width change) only when it is set
         const uint32_t six  = (uint32_t)(window() >> 58);
         const int      flag = (int)(six >> 5), r5 = (int)(six & 31u), m3 = r5 % 3;
@@ -396,7 +398,7 @@ inline size_t xtc_decode_coords(const unsigned char* p, size_t avail, int natoms
             {
                 triple(fs, ds, ds, thiscoord);
                 i++;
-                for (int d = 0; d < 3; ++d) thiscoord[d] += prevcoord[d] - smallnum;
+                for (int d = 0; d < 3; ++d) thiscoord[d] = (int)((unsigned)thiscoord[d] + (unsigned)prevcoord[d] - (unsigned)smallnum);
                 if (k == 0)
                 {
                     // the first two atoms of a run were interchanged by the writer (water: O after its first H)

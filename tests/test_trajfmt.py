@@ -113,6 +113,21 @@ def test_xtc_round_trip_is_exactly_the_quantised_coordinates(stub, tmp_path, cas
     assert np.array_equal(bx, exp)
 
 
+def test_xtc_decoder_survives_corrupt_input(tmp_path):
+    """Bit flips in header and stream, truncation, with and without in-place slack, under ASan + UBSan: the decoder either
+    decodes or reports failure; it never reads outside the buffer it was given (tests/fuzz_xtc.cpp)."""
+    import subprocess
+    exe = str(tmp_path / "fuzz_xtc")
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                         "-I" + os.path.join(ROOT, "gmxstub"), os.path.join(ROOT, "tests", "fuzz_xtc.cpp"), "-o", exe],
+                        capture_output=True, text=True)
+    if cc.returncode != 0:
+        pytest.skip("sanitizer build not available: " + cc.stderr[-200:])
+    r = subprocess.run([exe, "30000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "decoded" in r.stdout and "rejected" in r.stdout
+
+
 def test_trr_round_trip_exact(stub, tmp_path):
     system = synth.ionic_liquid(50, 2.8, seed=84)
     K = 4
