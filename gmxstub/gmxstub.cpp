@@ -602,8 +602,28 @@ bool xtc_next(t_trxstatus* st, xdrtraj::XtcHeader* h)
     }
 }
 
+/* TRR: the body (everything after lambda) of the next selected frame is at st->cur */
 bool trr_next(t_trxstatus* st, xdrtraj::TrrHeader* h)
 {
+    while (st->map)
+    {
+        if (st->mpos + 96 > st->map_size) return false;
+        const unsigned char* p = st->map + st->mpos;
+        if (!xdrtraj::trr_parse_header(p, st->map_size - st->mpos, h)) gmx_fatal(FARGS, "%s: bad TRR frame header", st->fn.c_str());
+        if (h->natoms != st->natoms) gmx_fatal(FARGS, "%s: number of atoms changes between frames", st->fn.c_str());
+        const size_t body = xdrtraj::trr_body_bytes(*h);
+        bool         past = false;
+        const bool   sel  = time_selected(st, h->t, &past);
+        if (past) return false;
+        if (st->mpos + h->header_bytes + body > st->map_size) gmx_fatal(FARGS, "%s: truncated TRR frame", st->fn.c_str());
+        st->next++;
+        st->cur       = p + h->header_bytes;
+        st->cur_avail = body;
+        st->mpos += h->header_bytes + body;
+        if (!sel) continue;
+        if (!st->have_t0) { st->have_t0 = true; st->t0 = h->t; }
+        return true;
+    }
     for (;;)
     {
         unsigned char hb[128];
@@ -622,8 +642,20 @@ bool trr_next(t_trxstatus* st, xdrtraj::TrrHeader* h)
         std::fseek(st->fp, pos + static_cast<long>(h->header_bytes), SEEK_SET);
         st->blob.resize(body);
         if (!read_bytes(st->fp, st->blob.data(), body)) gmx_fatal(FARGS, "%s: truncated TRR frame", st->fn.c_str());
+        st->cur = st->blob.data(); st->cur_avail = body;
         return true;
     }
+}
+
+/* XTC / TRR files are read through a read-only mapping when they are regular files (GMXSTUB_NO_MMAP=1: FILE* path) */
+void map_trajectory(t_trxstatus* st)
+{
+    struct stat sb;
+    if (std::getenv("GMXSTUB_NO_MMAP") || fstat(fileno(st->fp), &sb) != 0 || !S_ISREG(sb.st_mode) || sb.st_size <= 0) return;
+    void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fileno(st->fp), 0);
+    if (m == MAP_FAILED) return;
+    madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
+    st->map = static_cast<const unsigned char*>(m); st->map_size = (size_t)sb.st_size;
 }
 
 t_trxstatus* open_trx(const char* fn)
@@ -638,16 +670,7 @@ t_trxstatus* open_trx(const char* fn)
     if (got >= 8 && xdrtraj::be32(first) == (uint32_t)xdrtraj::kXtcMagic)
     {
         st->fmt = 1; st->natoms = (int)xdrtraj::be32(first + 4); st->nframes = -1; st->fflags = 1;
-        struct stat sb;
-        if (!std::getenv("GMXSTUB_NO_MMAP") && fstat(fileno(st->fp), &sb) == 0 && S_ISREG(sb.st_mode) && sb.st_size > 0)
-        {
-            void* m = mmap(nullptr, (size_t)sb.st_size, PROT_READ, MAP_PRIVATE, fileno(st->fp), 0);
-            if (m != MAP_FAILED)
-            {
-                madvise(m, (size_t)sb.st_size, MADV_SEQUENTIAL);
-                st->map = static_cast<const unsigned char*>(m); st->map_size = (size_t)sb.st_size;
-            }
-        }
+        map_trajectory(st);
         return st;
     }
     if (got >= 96 && xdrtraj::be32(first) == (uint32_t)xdrtraj::kTrrMagic)
@@ -656,6 +679,7 @@ t_trxstatus* open_trx(const char* fn)
         if (!xdrtraj::trr_parse_header(first, got, &h)) gmx_fatal(FARGS, "%s: bad TRR header", fn);
         st->fmt = 2; st->natoms = h.natoms; st->nframes = -1;
         st->fflags = (h.x_size ? 1 : 0) | (h.v_size ? 2 : 0) | (h.f_size ? 4 : 0);
+        map_trajectory(st);
         return st;
     }
     TrjHeader h;
@@ -691,7 +715,7 @@ bool deliver_xdr(t_trxstatus* st, t_trxframe* fr)
         xdrtraj::TrrHeader h;
         if (!trr_next(st, &h)) return false;
         fr->time = (float)h.t; fr->step = h.step;
-        const unsigned char* p  = st->blob.data() + h.ir_size + h.e_size;
+        const unsigned char* p  = st->cur + h.ir_size + h.e_size;
         const size_t         rs = h.dbl ? 8 : 4;
         if (h.box_size) { float b[9]; xdrtraj::trr_read_reals(p, h.dbl, 9, b); for (int k = 0; k < 9; ++k) fr->box[k / 3][k % 3] = b[k]; }
         p += h.box_size + h.vir_size + h.pres_size + h.top_size + h.sym_size;

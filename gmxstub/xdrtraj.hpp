@@ -617,6 +617,13 @@ inline bool trr_parse_header(const unsigned char* p, size_t avail, TrrHeader* h)
     }
     if (real_size != 4 && real_size != 8) return false;
     h->dbl = real_size == 8;
+    // every block is either absent or exactly as large as natoms says (readers index the body by these sizes)
+    const long long n3rs = (long long)h->natoms * 3 * real_size;
+    for (int blk : { h->x_size, h->v_size, h->f_size })
+        if (blk != 0 && blk != n3rs) return false;
+    if (h->natoms < 0 || (h->box_size != 0 && h->box_size != 9 * real_size)) return false;
+    for (int blk : { h->ir_size, h->e_size, h->vir_size, h->pres_size, h->top_size, h->sym_size })
+        if (blk < 0) return false;
     if (h->dbl) { h->t = be_double(p + off); h->lambda = be_double(p + off + 8); off += 16; }
     else { h->t = be_float(p + off); h->lambda = be_float(p + off + 4); off += 8; }
     h->header_bytes = off;

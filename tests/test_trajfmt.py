@@ -128,7 +128,7 @@ def test_xtc_decoder_survives_corrupt_input(tmp_path):
     assert "decoded" in r.stdout and "rejected" in r.stdout
 
 
-def test_trr_round_trip_exact(stub, tmp_path):
+def test_trr_round_trip_exact(stub, tmp_path, monkeypatch):
     system = synth.ionic_liquid(50, 2.8, seed=84)
     K = 4
     x = system.frames(0, K)
@@ -148,6 +148,11 @@ def test_trr_round_trip_exact(stub, tmp_path):
     # coordinates only: v / f blocks are skipped
     n, _, gx, gv, _, _, _ = read_all(stub, path, K, x.shape[1], TRX_READ_X)
     assert n == K and np.array_equal(gx, x) and not gv.any()
+    # the FILE* path (no mapping) reads the same frames
+    monkeypatch.setenv("GMXSTUB_NO_MMAP", "1")
+    n, _, gx, gv, gf, _, _ = read_all(stub, path, K + 2, x.shape[1], TRX_READ_X | TRX_READ_V | TRX_READ_F)
+    assert n == K and np.array_equal(gx, x) and np.array_equal(gv, v) and np.array_equal(gf, f)
+    monkeypatch.delenv("GMXSTUB_NO_MMAP")
     # a file without velocities
     path2 = str(tmp_path / "x.trr")
     assert stub.gmxstub_write_trr(path2.encode(), x.shape[1], K, _ptr(x), None, None, _ptr(box), 1, None) == 0
