@@ -11,16 +11,16 @@ gmx_main(temp)
     int  dim1 = 0, dim2 = 1, dim3 = 2;
     real lowPos1 = 1.66, upPos1 = 3.996, lowPos2 = 1.133, upPos2 = 3.073, lowPos3 = 7.761, upPos3 = 12.239, dbin = 0.002;
     hd.pa = {
-        { "-dim1", FALSE, etINT, { &dim1 }, "dim1." },
-        { "-up1", FALSE, etREAL, { &upPos1 }, "up1 position of region of pore (nm)" },
-        { "-low1", FALSE, etREAL, { &lowPos1 }, "low1 position of region of pore (nm)" },
-        { "-dim2", FALSE, etINT, { &dim2 }, "dim2." },
-        { "-up2", FALSE, etREAL, { &upPos2 }, "up2 position of region of pore (nm)" },
-        { "-low2", FALSE, etREAL, { &lowPos2 }, "low2 position of region of pore (nm)" },
-        { "-dim3", FALSE, etINT, { &dim3 }, "dim3." },
-        { "-up3", FALSE, etREAL, { &upPos3 }, "up3 position of region of pore (nm)" },
-        { "-low3", FALSE, etREAL, { &lowPos3 }, "low3 position of region of pore (nm)" },
-        { "-dbin", FALSE, etREAL, { &dbin }, "dbin" }
+        { "-dim1", FALSE, etINT, { &dim1 }, "axis of filter 1 (0 = x, 1 = y, 2 = z)" },
+        { "-up1", FALSE, etREAL, { &upPos1 }, "upper bound of filter 1 [nm]" },
+        { "-low1", FALSE, etREAL, { &lowPos1 }, "lower bound of filter 1 [nm]" },
+        { "-dim2", FALSE, etINT, { &dim2 }, "axis of filter 2 (0 = x, 1 = y, 2 = z)" },
+        { "-up2", FALSE, etREAL, { &upPos2 }, "upper bound of filter 2 [nm]" },
+        { "-low2", FALSE, etREAL, { &lowPos2 }, "lower bound of filter 2 [nm]" },
+        { "-dim3", FALSE, etINT, { &dim3 }, "axis of filter 3 (0 = x, 1 = y, 2 = z)" },
+        { "-up3", FALSE, etREAL, { &upPos3 }, "upper bound of filter 3 [nm]" },
+        { "-low3", FALSE, etREAL, { &lowPos3 }, "lower bound of filter 3 [nm]" },
+        { "-dbin", FALSE, etREAL, { &dbin }, "bin width [nm]" }
     };
     hd.fnm = { { efXVG, "-o", "areaDensity", ffWRITE } };
     hd.init();

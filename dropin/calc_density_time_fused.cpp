@@ -11,11 +11,11 @@ gmx_main(temp)
 
     real lowPos = 7.761, upPos = 12.239, centerX = 2.829, centerY = 2.056, Rmof = 0.927;
     hd.pa = {
-        { "-upPos", FALSE, etREAL, { &upPos }, "up position of region of pore (nm)" },
-        { "-lowPos", FALSE, etREAL, { &lowPos }, "low position of region of pore (nm)" },
-        { "-centerX", FALSE, etREAL, { &centerX }, "center X position of mofs pore (nm)" },
-        { "-centerY", FALSE, etREAL, { &centerY }, "center Y position of mofs pore (nm)" },
-        { "-Rmof", FALSE, etREAL, { &Rmof }, "Radius of mofs pore (nm)" }
+        { "-upPos", FALSE, etREAL, { &upPos }, "upper bound of the pore region [nm]" },
+        { "-lowPos", FALSE, etREAL, { &lowPos }, "lower bound of the pore region [nm]" },
+        { "-centerX", FALSE, etREAL, { &centerX }, "pore axis, x coordinate [nm]" },
+        { "-centerY", FALSE, etREAL, { &centerY }, "pore axis, y coordinate [nm]" },
+        { "-Rmof", FALSE, etREAL, { &Rmof }, "pore radius [nm]" }
     };
     hd.fnm = { { efXVG, "-o", "DensityTime", ffWRITE } };
     hd.init();

@@ -12,9 +12,9 @@ gmx_main(temp)
     rvec lowPos = { 0, 0, 0 }, upPos = { 30, 30, 30 };
     int  com = 0;
     hd.pa = {
-        { "-low", FALSE, etRVEC, { lowPos }, "low position" },
-        { "-up", FALSE, etRVEC, { upPos }, "up position" },
-        { "-com", FALSE, etINT, { &com }, "center of molecule, 0:mass, 1:geometry, 2:charge" }
+        { "-low", FALSE, etRVEC, { lowPos }, "lower bound" },
+        { "-up", FALSE, etRVEC, { upPos }, "upper bound" },
+        { "-com", FALSE, etINT, { &com }, "molecular centre: 0 = mass, 1 = geometric, 2 = charge" }
     };
     hd.fnm = { { efXVG, "-o", "calc_numdens_pore", ffWRITE } };
     hd.init();

@@ -13,22 +13,22 @@ gmx_main(temp)
     real cylCenter1 = 0.0, cylCenter2 = 0.0, dr = 0.01, CR = 0.5, Cr = 0.0;
     int  nAngle = 90, NCM = 0, DIMN = 2, tp1 = 1, tp2 = 2, tp3 = 3, DIMNOrient = 2, method = 1;
     hd.pa = {
-        { "-NCM", FALSE, etINT, { &NCM }, "center of molecule\n0: mass; 1: geometry; 2: charge" },
+        { "-NCM", FALSE, etINT, { &NCM }, "molecular centre: 0 = mass, 1 = geometric, 2 = charge" },
         { "-dim", FALSE, etINT, { &DIMN }, "axis of the slab filter; the radius is taken in the other two dimensions" },
-        { "-dbin", FALSE, etRVEC, { dbin }, "the distance of dbin (nm)" },
-        { "-low", FALSE, etRVEC, { low }, "the low position of region (nm)" },
-        { "-up", FALSE, etRVEC, { up }, "the up position of region (nm)" },
-        { "-c1", FALSE, etREAL, { &cylCenter1 }, "the center of the circle1 (nm)" },
-        { "-c2", FALSE, etREAL, { &cylCenter2 }, "the center of the circle2 (nm)" },
-        { "-dr", FALSE, etREAL, { &dr }, "the dr bin of R (nm)" },
-        { "-CR", FALSE, etREAL, { &CR }, "the up region of R (nm)" },
-        { "-Cr", FALSE, etREAL, { &Cr }, "the low region of R (nm)" },
-        { "-nA", FALSE, etINT, { &nAngle }, "number of bin sets of angle" },
-        { "-tp1", FALSE, etINT, { &tp1 }, "atom type 1" },
-        { "-tp2", FALSE, etINT, { &tp2 }, "atom type 2" },
-        { "-tp3", FALSE, etINT, { &tp3 }, "atom type 3" },
+        { "-dbin", FALSE, etRVEC, { dbin }, "bin width [nm]" },
+        { "-low", FALSE, etRVEC, { low }, "lower bound of the region [nm]" },
+        { "-up", FALSE, etRVEC, { up }, "upper bound of the region [nm]" },
+        { "-c1", FALSE, etREAL, { &cylCenter1 }, "circle centre, first coordinate [nm]" },
+        { "-c2", FALSE, etREAL, { &cylCenter2 }, "circle centre, second coordinate [nm]" },
+        { "-dr", FALSE, etREAL, { &dr }, "radial bin width [nm]" },
+        { "-CR", FALSE, etREAL, { &CR }, "outer radius of the radial range [nm]" },
+        { "-Cr", FALSE, etREAL, { &Cr }, "inner radius of the radial range [nm]" },
+        { "-nA", FALSE, etINT, { &nAngle }, "number of angle bins" },
+        { "-tp1", FALSE, etINT, { &tp1 }, "position of vector atom 1 inside the molecule" },
+        { "-tp2", FALSE, etINT, { &tp2 }, "position of vector atom 2 inside the molecule" },
+        { "-tp3", FALSE, etINT, { &tp3 }, "position of vector atom 3 inside the molecule" },
         { "-DIMNOrient", FALSE, etINT, { &DIMNOrient }, "axis of the wall vector" },
-        { "-method", FALSE, etINT, { &method }, "1: v1 + v2, 2: v1 x v2" }
+        { "-method", FALSE, etINT, { &method }, "molecular vector: 1 = sum of the two bond vectors, 2 = their cross product" }
     };
     hd.fnm = { { efXVG, "-o", "orient", ffWRITE } };
     hd.init();

@@ -13,11 +13,11 @@ gmx_main(temp)
     int  NCM = 0, dim = 2;
     real Rmin = 0.8, lowPos = 0.0, upPos = 12.0;
     hd.pa = {
-        { "-ncm", FALSE, etINT, { &NCM }, "kind of center, 0(mass), 1(geometry), 2(charge)" },
-        { "-Rmin", FALSE, etREAL, { &Rmin }, "the distance for which the RDF shows a first minimum (nm)" },
-        { "-dim", FALSE, etINT, { &dim }, "dim to analysis, 0(x), 1(y), 2(z)" },
-        { "-low", FALSE, etREAL, { &lowPos }, "low position (nm)" },
-        { "-up", FALSE, etREAL, { &upPos }, "up position (nm)" }
+        { "-ncm", FALSE, etINT, { &NCM }, "molecular centre: 0 = mass, 1 = geometric, 2 = charge" },
+        { "-Rmin", FALSE, etREAL, { &Rmin }, "first-shell cut-off: position of the first RDF minimum [nm]" },
+        { "-dim", FALSE, etINT, { &dim }, "profile axis: 0 = x, 1 = y, 2 = z" },
+        { "-low", FALSE, etREAL, { &lowPos }, "lower bound [nm]" },
+        { "-up", FALSE, etREAL, { &upPos }, "upper bound [nm]" }
     };
     hd.fnm = { { efXVG, "-o", "pair_dist", ffWRITE } };
     hd.init();

@@ -12,15 +12,15 @@ gmx_main(temp)
     int  dim = 2, NCM = 0;
     real lowPos = 7.073, upPos = 12.927, centerX = 2.829, centerY = 2.056, Rmin = 0.8, Rlow = 0, Rup = 0.4;
     hd.pa = {
-        { "-dim", FALSE, etINT, { &dim }, "dim, 0(x), 1(y), 2(z)" },
-        { "-up", FALSE, etREAL, { &upPos }, "up position of region of molecule/ion (nm)" },
-        { "-low", FALSE, etREAL, { &lowPos }, "low position of region of molecule/ion (nm)" },
-        { "-centerX", FALSE, etREAL, { &centerX }, "center X (nm)" },
-        { "-centerY", FALSE, etREAL, { &centerY }, "center Y (nm)" },
-        { "-ncm", FALSE, etINT, { &NCM }, "kind of center, 0(mass), 1(geometry), 2(charge)" },
-        { "-Rmin", FALSE, etREAL, { &Rmin }, "the distance for which the RDF shows a first minimum (nm)" },
-        { "-Rlow", FALSE, etREAL, { &Rlow }, "low distance to conter of pore (nm)" },
-        { "-Rup", FALSE, etREAL, { &Rup }, "up distance to center of pore (nm)" }
+        { "-dim", FALSE, etINT, { &dim }, "axis of the slab: 0 = x, 1 = y, 2 = z" },
+        { "-up", FALSE, etREAL, { &upPos }, "upper bound of the selection slab [nm]" },
+        { "-low", FALSE, etREAL, { &lowPos }, "lower bound of the selection slab [nm]" },
+        { "-centerX", FALSE, etREAL, { &centerX }, "axis position, x [nm]" },
+        { "-centerY", FALSE, etREAL, { &centerY }, "axis position, y [nm]" },
+        { "-ncm", FALSE, etINT, { &NCM }, "molecular centre: 0 = mass, 1 = geometric, 2 = charge" },
+        { "-Rmin", FALSE, etREAL, { &Rmin }, "first-shell cut-off: position of the first RDF minimum [nm]" },
+        { "-Rlow", FALSE, etREAL, { &Rlow }, "smallest distance from the pore axis [nm]" },
+        { "-Rup", FALSE, etREAL, { &Rup }, "largest distance from the pore axis [nm]" }
     };
     hd.fnm = { { efXVG, "-o", "pair_dist", ffWRITE } };
     hd.init();

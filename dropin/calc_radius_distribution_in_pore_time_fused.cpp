@@ -12,18 +12,18 @@ gmx_main(temp)
     real x1 = 0, x2 = 0, y1 = 0, y2 = 0, z1 = 0, z2 = 0, centerX = 2.829, centerY = 2.056, dr = 0.01, Cr = 0, CR = 0.5;
     int  dim = 2;
     hd.pa = {
-        { "-x1", FALSE, etREAL, { &x1 }, "low x position of region of pore (nm)" },
-        { "-x2", FALSE, etREAL, { &x2 }, "up x position of region of pore (nm)" },
-        { "-y1", FALSE, etREAL, { &y1 }, "low y position of region of pore (nm)" },
-        { "-y2", FALSE, etREAL, { &y2 }, "up y position of region of pore (nm)" },
-        { "-z1", FALSE, etREAL, { &z1 }, "low z position of region of pore (nm)" },
-        { "-z2", FALSE, etREAL, { &z2 }, "up z position of region of pore (nm)" },
-        { "-centerX", FALSE, etREAL, { &centerX }, "center X position of mofs pore (nm)" },
-        { "-centerY", FALSE, etREAL, { &centerY }, "center Y position of mofs pore (nm)" },
-        { "-dim", FALSE, etINT, { &dim }, "dim to analysis. 0, x; 1, y; 2, z" },
-        { "-dr", FALSE, etREAL, { &dr }, "dr of bin along radius (nm)" },
-        { "-Cr", FALSE, etREAL, { &Cr }, "min R region of pore (nm)" },
-        { "-CR", FALSE, etREAL, { &CR }, "max R region of pore (nm)" },
+        { "-x1", FALSE, etREAL, { &x1 }, "pore box: lower x bound [nm]" },
+        { "-x2", FALSE, etREAL, { &x2 }, "pore box: upper x bound [nm]" },
+        { "-y1", FALSE, etREAL, { &y1 }, "pore box: lower y bound [nm]" },
+        { "-y2", FALSE, etREAL, { &y2 }, "pore box: upper y bound [nm]" },
+        { "-z1", FALSE, etREAL, { &z1 }, "pore box: lower z bound [nm]" },
+        { "-z2", FALSE, etREAL, { &z2 }, "pore box: upper z bound [nm]" },
+        { "-centerX", FALSE, etREAL, { &centerX }, "pore axis, x coordinate [nm]" },
+        { "-centerY", FALSE, etREAL, { &centerY }, "pore axis, y coordinate [nm]" },
+        { "-dim", FALSE, etINT, { &dim }, "pore axis direction: 0 = x, 1 = y, 2 = z" },
+        { "-dr", FALSE, etREAL, { &dr }, "radial bin width [nm]" },
+        { "-Cr", FALSE, etREAL, { &Cr }, "inner radius of the histogram [nm]" },
+        { "-CR", FALSE, etREAL, { &CR }, "outer radius of the histogram [nm]" },
     };
     hd.fnm = { { efXVG, "-o", "rdf_time_in_pore", ffWRITE } };
     hd.init();

@@ -17,14 +17,14 @@ gmx_main(temp)
     int  nbin = 5, dim = 0, dim2 = 2;
     real lowPos = -100, upPos = 100, lowPos2 = -100, upPos2 = 100, Rm = 0;
     hd.pa = {
-        { "-nbin", FALSE, etINT, { &nbin }, "nbins." },
-        { "-up", FALSE, etREAL, { &upPos }, "up position of region of molecule/ion (nm)" },
-        { "-low", FALSE, etREAL, { &lowPos }, "low position of region of molecule/ion (nm)" },
-        { "-dim", FALSE, etINT, { &dim }, "dim of up and low position, 0(x), 1(y), 2(z)" },
-        { "-dim2", FALSE, etINT, { &dim2 }, "dim2" },
-        { "-low2", FALSE, etREAL, { &lowPos2 }, "z1" },
-        { "-up2", FALSE, etREAL, { &upPos2 }, "z2" },
-        { "-Rm", FALSE, etREAL, { &Rm }, "Rm" }
+        { "-nbin", FALSE, etINT, { &nbin }, "number of histogram bins" },
+        { "-up", FALSE, etREAL, { &upPos }, "upper bound of the selection slab [nm]" },
+        { "-low", FALSE, etREAL, { &lowPos }, "lower bound of the selection slab [nm]" },
+        { "-dim", FALSE, etINT, { &dim }, "axis the two bounds refer to: 0 = x, 1 = y, 2 = z" },
+        { "-dim2", FALSE, etINT, { &dim2 }, "axis of the second slab (0 = x, 1 = y, 2 = z)" },
+        { "-low2", FALSE, etREAL, { &lowPos2 }, "lower z bound [nm]" },
+        { "-up2", FALSE, etREAL, { &upPos2 }, "upper z bound [nm]" },
+        { "-Rm", FALSE, etREAL, { &Rm }, "largest pair distance [nm]" }
     };
     hd.fnm = { { efXVG, "-o", "rdf_region", ffWRITE } };
     hd.init();

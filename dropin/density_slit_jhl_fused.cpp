@@ -13,14 +13,14 @@ gmx_main(temp)
     int  nbin1 = 100, dim1 = 0, dim2 = 2;
     real lowPos1 = 0, upPos1 = 30, upPos2 = 0, lowPos2 = 10, yy = 0;
     hd.pa = {
-        { "-nbin1", FALSE, etINT, { &nbin1 }, "nbins." },
-        { "-dim1", FALSE, etINT, { &dim1 }, "dim, 0(x), 1(y), 2(z)" },
-        { "-dim2", FALSE, etINT, { &dim2 }, "dim, 0(x), 1(y), 2(z)" },
-        { "-up1", FALSE, etREAL, { &upPos1 }, "up position of region of molecule/ion (nm)" },
-        { "-low1", FALSE, etREAL, { &lowPos1 }, "low position of region of molecule/ion (nm)" },
-        { "-up2", FALSE, etREAL, { &upPos2 }, "up position of region of molecule/ion (nm)" },
-        { "-low2", FALSE, etREAL, { &lowPos2 }, "low position of region of molecule/ion (nm)" },
-        { "-yy", FALSE, etREAL, { &yy }, "y length (nm)" }
+        { "-nbin1", FALSE, etINT, { &nbin1 }, "number of histogram bins" },
+        { "-dim1", FALSE, etINT, { &dim1 }, "axis of the slab: 0 = x, 1 = y, 2 = z" },
+        { "-dim2", FALSE, etINT, { &dim2 }, "axis of the slab: 0 = x, 1 = y, 2 = z" },
+        { "-up1", FALSE, etREAL, { &upPos1 }, "upper bound of the selection slab [nm]" },
+        { "-low1", FALSE, etREAL, { &lowPos1 }, "lower bound of the selection slab [nm]" },
+        { "-up2", FALSE, etREAL, { &upPos2 }, "upper bound of the selection slab [nm]" },
+        { "-low2", FALSE, etREAL, { &lowPos2 }, "lower bound of the selection slab [nm]" },
+        { "-yy", FALSE, etREAL, { &yy }, "box length along y [nm]" }
     };
     hd.fnm = { { efXVG, "-o", "density_slit", ffWRITE } };
     hd.init();

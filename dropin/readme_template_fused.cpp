@@ -17,10 +17,10 @@ gmx_main(temp)
     int  nbin = 100, dim = 2;
     real lowPos = 0, upPos = 30;
     hd.pa = {
-        { "-nbin", FALSE, etINT, { &nbin }, "nbins." },
-        { "-dim", FALSE, etINT, { &dim }, "dim, 0(x), 1(y), 2(z)" },
-        { "-up", FALSE, etREAL, { &upPos }, "up position of region of molecule/ion (nm)" },
-        { "-low", FALSE, etREAL, { &lowPos }, "low position of region of molecule/ion (nm)" }
+        { "-nbin", FALSE, etINT, { &nbin }, "number of histogram bins" },
+        { "-dim", FALSE, etINT, { &dim }, "axis of the slab: 0 = x, 1 = y, 2 = z" },
+        { "-up", FALSE, etREAL, { &upPos }, "upper bound of the selection slab [nm]" },
+        { "-low", FALSE, etREAL, { &lowPos }, "lower bound of the selection slab [nm]" }
     };
     hd.fnm = { { efXVG, "-o", "analysisOutput", ffWRITE } };
     hd.init();
