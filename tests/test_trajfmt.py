@@ -148,10 +148,17 @@ def test_trr_round_trip_exact(stub, tmp_path, monkeypatch):
     # coordinates only: v / f blocks are skipped
     n, _, gx, gv, _, _, _ = read_all(stub, path, K, x.shape[1], TRX_READ_X)
     assert n == K and np.array_equal(gx, x) and not gv.any()
+    # batch reader (coordinates of K frames converted on several threads out of the mapped file), any batch size
+    for batch in (1, 3, 16):
+        bx = np.zeros_like(x); bb = np.zeros((K, 9), np.float32); bt = np.zeros(K, np.float32)
+        assert stub.gmxstub_read_batches(path.encode(), batch, K, _ptr(bx), _ptr(bb), _ptr(bt)) == K
+        assert np.array_equal(bx, x) and np.array_equal(bt, np.arange(K, dtype=np.float32)) and np.array_equal(bb, np.repeat(box, K, axis=0))
     # the FILE* path (no mapping) reads the same frames
     monkeypatch.setenv("GMXSTUB_NO_MMAP", "1")
     n, _, gx, gv, gf, _, _ = read_all(stub, path, K + 2, x.shape[1], TRX_READ_X | TRX_READ_V | TRX_READ_F)
     assert n == K and np.array_equal(gx, x) and np.array_equal(gv, v) and np.array_equal(gf, f)
+    bx = np.zeros_like(x); bb = np.zeros((K, 9), np.float32); bt = np.zeros(K, np.float32)
+    assert stub.gmxstub_read_batches(path.encode(), 3, K, _ptr(bx), _ptr(bb), _ptr(bt)) == K and np.array_equal(bx, x)
     monkeypatch.delenv("GMXSTUB_NO_MMAP")
     # a file without velocities
     path2 = str(tmp_path / "x.trr")
