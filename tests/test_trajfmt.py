@@ -223,13 +223,15 @@ def test_trr_written_elsewhere_double_precision(stub, tmp_path):
     assert [fr["step"] for fr in xtc_classic.read_trr_frames(path)] == [0, 10, 20]
 
 
-def test_reference_program_reads_xtc_like_raw(stub, tmp_path):
-    """The reference's own calc_rdf_region (oracle/_ref) on an XTC file == on the raw file of the quantised coordinates."""
+@pytest.mark.parametrize("select", [[], ["-b", "2", "-e", "7", "-dt", "2"]], ids=["all_frames", "b_e_dt"])
+def test_reference_program_reads_xtc_like_raw(stub, tmp_path, select):
+    """The reference's own calc_rdf_region (oracle/_ref) on an XTC file == on the raw file of the quantised coordinates,
+    also when -b / -e / -dt make the reader skip frames (in the mapped file: header walk without touching the blocks)."""
     if not refprog.have_ref("calc_rdf_region"):
         pytest.skip("oracle/_ref not built")
     import subprocess
     system = synth.water_box(500, 2.5, seed=85, split_atoms=True)
-    K = 3
+    K = 9 if select else 3
     xq = quantise(system.frames(0, K), 1000.0)
     outs = []
     for kind in ("raw", "xtc"):
@@ -244,7 +246,11 @@ def test_reference_program_reads_xtc_like_raw(stub, tmp_path):
         trajio.write_index(str(d / "sys.ndx"), {"OW": system.groups["OW"]})
         env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
         r = subprocess.run([os.path.join(refprog.REFDIR, "calc_rdf_region"), "-f", trj, "-s", str(d / "sys.b2p"), "-n", str(d / "sys.ndx"),
-                            "-o", str(d / "o.xvg")], input="0 0\n", capture_output=True, text=True, env=env, cwd=str(d))
+                            "-o", str(d / "o.xvg")] + select, input="0 0\n", capture_output=True, text=True, env=env, cwd=str(d))
         assert r.returncode == 0, r.stderr[-500:]
         outs.append(refprog.data_lines(str(d / "o.xvg")))
     assert len(outs[0]) > 100 and outs[0] == outs[1]
+    if select:       # and the selection really selected: frames 2, 4, 6 only -> not the all-frames answer of the same file
+        r = subprocess.run([os.path.join(refprog.REFDIR, "calc_rdf_region"), "-f", trj, "-s", str(d / "sys.b2p"), "-n", str(d / "sys.ndx"),
+                            "-o", str(d / "all.xvg")], input="0 0\n", capture_output=True, text=True, env=env, cwd=str(d))
+        assert r.returncode == 0 and refprog.data_lines(str(d / "all.xvg")) != outs[1]
