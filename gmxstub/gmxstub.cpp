@@ -805,7 +805,7 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
         std::vector<const unsigned char*>       src(std::max(max_frames, 1), nullptr);
         std::vector<size_t>                     src_avail(std::max(max_frames, 1), 0);
         std::vector<int>                        bad(std::max(max_frames, 1), 0);
-        int nthreads = std::min<int>(max_frames, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+        int nthreads = std::min<int>(max_frames, std::max(1u, std::min(64u, std::thread::hardware_concurrency())));
         if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(max_frames, std::atoi(e)));
         std::mutex              mu;
         std::condition_variable cv;
@@ -876,7 +876,7 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
             st->nread++;
         }
         const int n = (int)items.size();
-        int nthreads = std::min<int>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+        int nthreads = std::min<int>(n, std::max(1u, std::min(64u, std::thread::hardware_concurrency())));
         if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(n, std::atoi(e)));
         std::atomic<int> next{ 0 };
         auto work = [&]() {
