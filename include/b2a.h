@@ -26,6 +26,16 @@
  *                         100-115 (normalisation); GmxHandle::periodicity (ipp:410-417)
  *   b2a_orient_*       <- src/mofs/calc_orient_mof.cpp:14-63, 120-200
  *   b2a_coord_*        <- src/mofs/calc_pair_dist_bulk.cpp:14-23, 66-100; src/mofs/calc_pair_dist.cpp:80-106
+ *   b2a_region_*       <- src/mofs/calc_density_distribution_in_pore.cpp:47-60; calc_areaDensityDistributionPore.cpp:56-68;
+ *                         calc_numdens_pore.cpp:12-27, 72-80; calc_radius_distribution_in_pore.cpp:45-58;
+ *                         calc_radius_distribution_in_pore_time.cpp:81-107; calc_density_time.cpp:41-60 (per-frame counters)
+ *   b2a_set_group_full <- GmxHandleFull::init (include/itp/gmx_bits/gmx_handle_full.ipp:300-344); its loaders share
+ *                         b2a_centers / b2a_positions / b2a_field_centers (full.ipp:115-250)
+ *   b2a_set_group_wsum <- callers that divide by their own weight sum (e.g. the dipole programs' charge sums)
+ *   b2a_acc_read       <- the post-loop reads of the programs' histograms (`density /= hd.nframe` and friends)
+ * No reference counterpart (infrastructure of the boundary): b2a_create / destroy / sync / stream / version / device_count /
+ * last_error, b2a_pinned_alloc / free (the frame batcher's host buffers), b2a_accumulate / acc_reset / acc_size /
+ * acc_device_ptr (multi-GPU all-reduce), b2a_rdf_tune / rdf_cells / acc_fast / invalidate / timing_* (experiments, validation).
  */
 #ifndef B2A_H
 #define B2A_H
