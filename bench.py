@@ -45,7 +45,7 @@ class Workload:
     (configs[2], the frame-sharded multi-GPU case) is selectable for the scaling runs recorded in profiles/."""
 
     def __init__(self, name):
-        from gmx2020postanalysis_b200 import synth
+        from workloads import synth
         self.name = name
         if name == "c2":
             self.L, self.seed = 12.913, 20200102                   # SURVEY.md 8(d), config C2
@@ -146,7 +146,7 @@ def cpu_reference_sample(wl, n_i, tmpdir, x0):
     threading there) on grp0 = the first n_i molecules of group 0 x grp1 = all of group 1, one frame.  Returns
     (pairs/s, kind, secs)."""
     import refprog
-    from gmx2020postanalysis_b200 import trajio
+    from workloads import trajio
     system, n1 = wl.system, wl.n1
     i0, i1 = wl.gi0["index"], wl.gi1["index"]
     exe = os.path.join(refprog.REFDIR, "calc_rdf_region")
@@ -185,7 +185,7 @@ def cpu_reference_all_cores(wl, n_i, procs, tmpdir, x0):
     its own share of the i-molecules (what a user would do by hand with index groups).  Returns aggregate pairs/s, or None
     where the reference binaries did not travel."""
     import refprog
-    from gmx2020postanalysis_b200 import trajio
+    from workloads import trajio
     if not refprog.have_ref("calc_rdf_region"):
         return None
     system, n1 = wl.system, wl.n1
@@ -276,7 +276,8 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gmx2020postanalysis_b200 import dist as b2d, lib, synth
+    from gmx2020postanalysis_b200 import dist as b2d, lib
+    from workloads import synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,8 +1,8 @@
 // calc_density_time (reference src/mofs/calc_density_time.cpp), ported to the device.
 //
 // Same command line and output file: the number of molecules inside the pore (z slab + cylinder) for every frame.  The per-frame
-// loop (:38-54) becomes one b2aAccumulate() of a region accumulator with per-frame counters per resident batch; the time stamps
-// of the batch come from the batcher.
+// loop (:38-54) becomes one b2aAccumulate() of a region accumulator with per-frame counters per resident batch; the series and its
+// time stamps are fetched once after the loop (b2aSeries), in trajectory order whichever GPU processed a batch.
 #include <itp/gmx>
 
 gmx_main(temp)
@@ -29,13 +29,16 @@ gmx_main(temp)
     const int acc = hd.b2aRegion(spec);
 
     auto ofile = hd.openWrite(hd.get_opt2fn("-o"));
-    std::vector<uint64_t> per;
+    // nothing is read back inside the loop (with several GPUs -- B2A_DEVICES -- that would serialise them): the per-frame counters
+    // stay on the device that computed them and come back after the loop, ordered by frame
     do
     {
         hd.b2aAccumulate(acc);
-        hd.b2aRegionFrames(acc, per);
-        for (int k = 0; k < hd.b2aBatchFrames(); ++k) fmt::print(ofile, "{:8.4f} {:10d}\n", hd.b2aBatchTime(k), (int)per[k]);
     } while (hd.b2aReadNextBatch());
+    std::vector<uint64_t> per;
+    std::vector<float>    times;
+    const size_t          nfr = hd.b2aSeries(acc, per, nullptr, &times);
+    for (size_t k = 0; k < nfr; ++k) fmt::print(ofile, "{:8.4f} {:10d}\n", times[k], (int)per[k]);
     fclose(ofile);
     return 0;
 }

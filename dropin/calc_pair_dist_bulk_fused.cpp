@@ -33,8 +33,8 @@ gmx_main(temp)
     do
     {
         hd.b2aAccumulate(acc);
-        hd.b2aCoordFold(acc, max_count, totPair);   // per-frame tables of this batch, folded in frame order
     } while (hd.b2aReadNextBatch());
+    hd.b2aCoordFoldSeries(acc, max_count, totPair);   // per-frame tables of every frame, folded in frame order after the loop
 
     double totol = 0;
     for (double p : totPair) totol += p;       // :95-99 (absent keys contribute nothing)

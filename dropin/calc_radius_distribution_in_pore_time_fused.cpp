@@ -48,18 +48,19 @@ gmx_main(temp)
     fmt::print(file, "{:8.4f} ", 0.0);
     for (int i = 0; i != nbin; ++i) fmt::print(file, "{:8.5f} ", Cr + i * dr + dr / 2);
     fmt::print(file, "\n");
-    std::vector<uint64_t> per;
     do
     {
         hd.b2aAccumulate(acc);
-        hd.b2aRegionFrames(acc, per);
-        for (int k = 0; k < hd.b2aBatchFrames(); ++k)
-        {
-            fmt::print(file, "{:8.4f} ", hd.b2aBatchTime(k));
-            for (int i = 0; i != nbin; ++i) fmt::print(file, "{:8.5f} ", (double)per[(size_t)k * nbin + i] / volumn[i]);
-            fmt::print(file, "\n");
-        }
     } while (hd.b2aReadNextBatch());
+    std::vector<uint64_t> per;
+    std::vector<float>    times;
+    const size_t          nfr = hd.b2aSeries(acc, per, nullptr, &times);   // every frame, in trajectory order, after the loop
+    for (size_t k = 0; k < nfr; ++k)
+    {
+        fmt::print(file, "{:8.4f} ", times[k]);
+        for (int i = 0; i != nbin; ++i) fmt::print(file, "{:8.5f} ", (double)per[k * nbin + i] / volumn[i]);
+        fmt::print(file, "\n");
+    }
     fclose(file);
     return 0;
 }

@@ -2,8 +2,9 @@
 
 The product is the C-ABI library ``libb2a.so`` (CUDA, sm_100a; ``include/b2a.h``) and the C++ drop-in
 header ``include/itp/gmx``.  This Python package is the thin host-side mirror used by tests and
-``bench.py``: ctypes bindings, the synthetic trajectory generator and file writers.
+``bench.py``: ctypes bindings (``lib``) and the multi-GPU plumbing (``dist``).  Synthetic inputs and file
+writers live in ``workloads/`` (harness).
 """
-from . import synth, trajio  # noqa: F401
+from . import lib  # noqa: F401
 
-__all__ = ["synth", "trajio"]
+__all__ = ["lib", "dist"]

@@ -118,6 +118,16 @@ struct CellSort
 
 enum AccKind { ACC_DENSITY, ACC_RDF, ACC_ORIENT, ACC_COORD, ACC_REGION };
 
+// Per-frame constants computed on the host travel through a small ring of pinned slots: slot s may be rewritten once the
+// upload that last read it has finished (an event per slot, normally long passed), so queueing an accumulation never
+// synchronises the stream and the host can run kFrameRing batches ahead of the device per accumulator.
+constexpr int kFrameRing = 4;
+struct FrameRing
+{
+    cudaEvent_t ev[kFrameRing] = { nullptr, nullptr, nullptr, nullptr };
+    int         next = 0;
+};
+
 struct Acc
 {
     AccKind            kind;
@@ -126,18 +136,31 @@ struct Acc
     b2a_orient_spec    ori{};
     b2a_coord_spec     coord{};
     b2a_region_spec    region{};
-    unsigned long long* d_perframe = nullptr;   // region accumulators with per_frame: [maxK][ncounters] of the last batch
-    int                perframe_frames = 0;
+    unsigned long long* d_perframe = nullptr;   // region accumulators with per_frame: the per-frame log [series_cap][ncounters]
+    int                perframe_frames = 0;     // frames of the last accumulated batch (the tail of the log)
     size_t             ncounters = 0;       // public counters (reference layout size)
     size_t             ndev      = 0;       // device u64 words before the stats block
-    unsigned long long* d_hist   = nullptr; // [ndev + NSLOTS]
+    unsigned long long* d_hist   = nullptr; // [ndev + NSLOTS]: this device's PRIVATE counts
+    // b2a_finalize (b2a_multi.cuh): sum of d_hist over every device of the communicator, valid while merged_epoch == epoch
+    unsigned long long* d_merged = nullptr;
+    uint64_t           epoch = 1, merged_epoch = 0;   // epoch moves with every accumulate / reset
+    // per-frame series (region accumulators with per_frame, coordination numbers): the per-frame tables of EVERY accumulated
+    // batch, appended on the device in accumulation order; `batches` holds (global index of the batch's first frame, frames)
+    size_t             series_cap = 0, series_len = 0;          // frames
+    unsigned*          d_series_numA = nullptr;                 // coord: numA of every logged frame
+    std::vector<std::pair<long long, int>> batches;
+    std::vector<long long>          gathered_idx;               // b2a_finalize across processes: the merged, ordered series
+    std::vector<unsigned long long> gathered;
+    uint64_t                        gathered_epoch = 0;
     // rdf scratch
     int*      d_slab_id = nullptr;
     unsigned* d_slab_cnt = nullptr;   // [maxK][nslab] counts then [maxK][nslab] cursors
     int4*     d_sortedA = nullptr;
     int4*     sortedA_view = nullptr;   // what the next k3_rdf launch reads: d_sortedA (slab sort) or a shared CellSort array
     RdfFrame* d_frames = nullptr;
-    RdfFrame* h_frames = nullptr;     // pinned
+    RdfFrame* h_frames = nullptr;     // pinned, [kFrameRing][maxK]: b2a_accumulate never waits for the device (FrameRing)
+    FrameRing ring;
+    int       alloc_n0 = 0, alloc_n1 = 0;   // molecule counts the per-molecule scratch below was sized for (b2a_*_create)
     int       symmetric = 0, paranoid = 0, cells = -1;   // cells: -1 auto, 0 never, 1 whenever it culls anything
     // cell mode scratch (allocated on first use)
     int*      d_keysA = nullptr; int* d_keysB = nullptr;
@@ -150,9 +173,9 @@ struct Acc
     float2*        d_fmh = nullptr;   // orient: per angle bin {midpoint, shrunk halfwidth} of its cosine interval
     // coord
     int*        d_cnt = nullptr;      // [maxK][n0] pair counts of the last batch
-    unsigned*   d_table = nullptr;    // [maxK][max_count] per-frame histogram of counts of the last batch
+    unsigned*   d_table = nullptr;    // per-frame log [series_cap][max_count]: histogram of counts of every accumulated frame
     CoordFrame* d_cframes = nullptr;
-    CoordFrame* h_cframes = nullptr;  // pinned
+    CoordFrame* h_cframes = nullptr;  // pinned, [kFrameRing][maxK]
     int         table_frames = 0;     // frames of the batch d_table describes
     // orient
     double* d_cosedge = nullptr;
@@ -203,23 +226,55 @@ struct b2a_ctx
     std::vector<Span> spans;
     double       t_ms[8] = { 0 };
     long long    t_n[8]  = { 0 };
+    // ---- multi-GPU (b2a_multi.cuh) ----------------------------------------------------------------------------
+    // A context made by b2a_create_multi is a LEADER: it owns one member context per device and no device resources
+    // of its own; every entry point forwards (to all members, to the member holding the current batch, or to member 0).
+    std::vector<b2a_ctx*> members;
+    int          cur_member = -1;     // leader: member that received the last batch
+    long long    frame_base = 0;      // global index of frame 0 of the current batch (per-frame series are ordered by it)
+    long long    next_frame = 0;      // global index the next submitted batch starts at
+    void*        comm = nullptr;      // ncclComm_t of this device (members and plain contexts), attached by b2a_comm_init / b2a_create_multi
+    int          comm_rank = 0, comm_size = 1, comm_procs = 1;
+    bool         same_device_team = false;   // leader: members share a device (tests on one GPU): merged by a local kernel, NCCL cannot do it
+    bool is_leader() const { return !members.empty(); }
 };
+
+// forwarding of the C ABI on a leader context
+#define TEAM_ALL(c, call)                                                                    \
+    if ((c) && (c)->is_leader())                                                             \
+    {                                                                                        \
+        for (b2a_ctx* m : (c)->members) { if (int rc_ = (call)) return rc_; }                \
+        return B2A_OK;                                                                       \
+    }
+#define TEAM_CUR(c, call)                                                                    \
+    if ((c) && (c)->is_leader())                                                             \
+    {                                                                                        \
+        if ((c)->cur_member < 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet"); \
+        b2a_ctx* m = (c)->members[(c)->cur_member];                                          \
+        return (call);                                                                       \
+    }
+#define TEAM_FIRST(c, call)                                                                  \
+    if ((c) && (c)->is_leader())                                                             \
+    {                                                                                        \
+        b2a_ctx* m = (c)->members[0];                                                        \
+        return (call);                                                                       \
+    }
 
 namespace
 {
 struct Timed   // RAII: records an event pair around a launch sequence when timing is on
 {
-    b2a_ctx* c; int slot; cudaEvent_t a = nullptr, b = nullptr;
-    Timed(b2a_ctx* c_, int slot_) : c(c_), slot(slot_)
+    b2a_ctx* c; int slot; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    Timed(b2a_ctx* c_, int slot_, cudaStream_t on = nullptr) : c(c_), slot(slot_), st(on ? on : c_->stream)
     {
         if (!c->timing) return;
         cudaEventCreate(&a); cudaEventCreate(&b);
-        cudaEventRecord(a, c->stream);
+        cudaEventRecord(a, st);
     }
     ~Timed()
     {
         if (!a) return;
-        cudaEventRecord(b, c->stream);
+        cudaEventRecord(b, st);
         c->spans.push_back({ slot, a, b });
     }
 };
@@ -236,6 +291,9 @@ extern "C" int b2a_device_count(void)
 }
 
 extern "C" void b2a_destroy(b2a_ctx* c);
+static void multi_release(b2a_ctx* c);                    // b2a_multi.cuh: communicator of a context
+static int  team_submit(b2a_ctx* c, int nframes, const float* x, const float* box9);
+static int  team_read(b2a_ctx* c, int id, uint64_t* counts, uint64_t* stats);
 
 extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
 {
@@ -282,19 +340,28 @@ static void free_group(Group& g)
 
 static void free_acc(Acc& a)
 {
+    cudaFree(a.d_merged); cudaFree(a.d_series_numA);
     cudaFree(a.d_hist); cudaFree(a.d_slab_id); cudaFree(a.d_slab_cnt); cudaFree(a.d_sortedA); cudaFree(a.d_frames);
     cudaFree(a.d_cosedge); cudaFree(a.d_fedge); cudaFree(a.d_stab); cudaFree(a.d_lut); cudaFree(a.d_fmh);
     cudaFree(a.d_cnt); cudaFree(a.d_table); cudaFree(a.d_cframes); cudaFree(a.d_perframe);
     if (a.h_cframes) cudaFreeHost(a.h_cframes);
     cudaFree(a.d_keysA); cudaFree(a.d_keysB); cudaFree(a.d_cellA); cudaFree(a.d_cellB); cudaFree(a.d_sortedB);
     if (a.h_frames) cudaFreeHost(a.h_frames);
+    for (auto& e : a.ring.ev) if (e) cudaEventDestroy(e);
 }
 
 extern "C" void b2a_destroy(b2a_ctx* c)
 {
     if (!c) return;
+    if (c->is_leader())
+    {
+        for (b2a_ctx* m : c->members) b2a_destroy(m);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    multi_release(c);
     for (auto& kv : c->groups) free_group(kv.second);
     for (auto& a : c->accs) if (a) free_acc(*a);
     for (auto& cs : c->cell_sorts) { cudaFree(cs->keys); cudaFree(cs->cells); cudaFree(cs->sorted); }
@@ -317,13 +384,18 @@ extern "C" void b2a_destroy(b2a_ctx* c)
 
 extern "C" int b2a_sync(b2a_ctx* c)
 {
+    TEAM_ALL(c, b2a_sync(m));
     if (!c) return fail(B2A_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     return B2A_OK;
 }
 
-extern "C" void* b2a_stream(b2a_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" void* b2a_stream(b2a_ctx* c)
+{
+    if (c && c->is_leader()) return (void*)c->members[0]->stream;   // per-device streams: b2a_member(ctx, i)
+    return c ? (void*)c->stream : nullptr;
+}
 
 extern "C" void* b2a_pinned_alloc(size_t n)
 {
@@ -336,6 +408,7 @@ extern "C" void b2a_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 // ---- groups --------------------------------------------------------------------------------------------------
 extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int napm, const double* mass, const double* charge)
 {
+    TEAM_ALL(c, b2a_set_group(m, grp, index, ngx, napm, mass, charge));
     if (!c || !index || !mass || !charge) return fail(B2A_ERR_ARG, "b2a_set_group: null argument");
     if (grp < 0) return fail(B2A_ERR_ARG, "grp(%d) should not be negative", grp);
     if (napm <= 0 || ngx <= 0 || ngx % napm != 0)
@@ -383,6 +456,7 @@ extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int
 extern "C" int b2a_set_group_full(b2a_ctx* c, int grp, const int* index, int ngx, int nmol, const int* napm, const double* mass,
                                   const double* charge)
 {
+    TEAM_ALL(c, b2a_set_group_full(m, grp, index, ngx, nmol, napm, mass, charge));
     if (!c || !index || !napm || !mass || !charge) return fail(B2A_ERR_ARG, "b2a_set_group_full: null argument");
     if (grp < 0 || ngx <= 0 || nmol <= 0) return fail(B2A_ERR_ARG, "b2a_set_group_full: bad sizes");
     std::vector<int> off(nmol + 1, 0), mol_of(ngx);
@@ -447,6 +521,7 @@ static int get_group(b2a_ctx* c, int grp, Group** out)
 
 extern "C" int b2a_set_group_wsum(b2a_ctx* c, int grp, int com, double wsum)
 {
+    TEAM_ALL(c, b2a_set_group_wsum(m, grp, com, wsum));
     if (!c || com < 0 || com > 3) return fail(B2A_ERR_ARG, "b2a_set_group_wsum: bad argument");
     Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
@@ -458,6 +533,7 @@ extern "C" int b2a_set_group_wsum(b2a_ctx* c, int grp, int com, double wsum)
 
 extern "C" int b2a_group_nmol(b2a_ctx* c, int grp)
 {
+    TEAM_FIRST(c, b2a_group_nmol(m, grp));
     if (!c) return -1;
     auto it = c->groups.find(grp);
     return it == c->groups.end() ? -1 : it->second.nmol;
@@ -467,6 +543,7 @@ extern "C" int b2a_group_nmol(b2a_ctx* c, int grp)
 extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const float* box9)
 {
     if (!c || !x || !box9) return fail(B2A_ERR_ARG, "b2a_submit_batch: null argument");
+    if (c->is_leader()) return team_submit(c, nframes, x, box9);
     if (nframes <= 0 || nframes > c->maxK) return fail(B2A_ERR_ARG, "b2a_submit_batch: nframes %d outside 1..%d", nframes, c->maxK);
     CU(cudaSetDevice(c->device));
     for (int f = 0; f < nframes; ++f)
@@ -509,8 +586,8 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
     {
         // upload on the copy stream (overlaps the kernels of the previous batch, which read the other buffer); kernels
         // launched after this call wait for it through ev_copied.  `x` must stay untouched until then, as before.
-        Timed t(c, 5);
         CU(cudaStreamWaitEvent(c->copy_stream, c->ev_free[b], 0));
+        Timed t(c, 5, c->copy_stream);   // the copies run on the copy stream: that is where the event pair belongs
         CU(cudaMemcpyAsync(c->d_x, x, (size_t)c->natoms * 3 * sizeof(float) * nframes, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaMemcpyAsync(c->d_geom, c->h_geom, sizeof(FrameGeom) * nframes, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->ev_copied[b], c->copy_stream));
@@ -518,10 +595,16 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
     }
     c->nframes = nframes;
     c->serial++;
+    c->frame_base = c->next_frame;
+    c->next_frame += nframes;
     return B2A_OK;
 }
 
-extern "C" int b2a_batch_frames(b2a_ctx* c) { return c ? c->nframes : -1; }
+extern "C" int b2a_batch_frames(b2a_ctx* c)
+{
+    if (c && c->is_leader()) return c->cur_member < 0 ? 0 : c->members[c->cur_member]->nframes;
+    return c ? c->nframes : -1;
+}
 
 // ---- TMA-staged streaming launch (contiguous groups) -----------------------------------------------------------
 static bool stream_block(const Group& g, int* M)
@@ -658,6 +741,7 @@ static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
 
 extern "C" int b2a_centers(b2a_ctx* c, int grp, int com, int frame, double* out)
 {
+    TEAM_CUR(c, b2a_centers(m, grp, com, frame, out));
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_centers: null argument");
     Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
@@ -672,6 +756,7 @@ extern "C" int b2a_centers(b2a_ctx* c, int grp, int com, int frame, double* out)
 
 extern "C" int b2a_centers_batch(b2a_ctx* c, int grp, int com, double* out)
 {
+    TEAM_CUR(c, b2a_centers_batch(m, grp, com, out));
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_centers_batch: null argument");
     Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
@@ -682,8 +767,21 @@ extern "C" int b2a_centers_batch(b2a_ctx* c, int grp, int com, double* out)
     return B2A_OK;
 }
 
+extern "C" int b2a_centers_device(b2a_ctx* c, int grp, int com, const double** dptr)
+{
+    TEAM_CUR(c, b2a_centers_device(m, grp, com, dptr));
+    if (!c || !dptr) return fail(B2A_ERR_ARG, "b2a_centers_device: null argument");
+    Group* g = nullptr;
+    if (int rc = get_group(c, grp, &g)) return rc;
+    CU(cudaSetDevice(c->device));
+    if (int rc = ensure_centers(c, *g, com, false)) return rc;   // queued on the context stream; nothing is copied or waited for
+    *dptr = g->d_cen[com];
+    return B2A_OK;
+}
+
 extern "C" int b2a_positions(b2a_ctx* c, int grp, int frame, double* out)
 {
+    TEAM_CUR(c, b2a_positions(m, grp, frame, out));
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_positions: null argument");
     Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
@@ -718,6 +816,7 @@ extern "C" int b2a_positions(b2a_ctx* c, int grp, int frame, double* out)
 // ---- velocities / forces (reference ipp:201-339): no unwrapping ------------------------------------------------------
 extern "C" int b2a_submit_field(b2a_ctx* c, int field, int nframes, const float* data)
 {
+    TEAM_CUR(c, b2a_submit_field(m, field, nframes, data));
     if (!c || !data) return fail(B2A_ERR_ARG, "b2a_submit_field: null argument");
     if (field != B2A_FIELD_V && field != B2A_FIELD_F) return fail(B2A_ERR_ARG, "b2a_submit_field: field must be B2A_FIELD_V or B2A_FIELD_F");
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
@@ -768,6 +867,7 @@ static int run_field_centers(b2a_ctx* c, int field, Group& g, int com)
 
 extern "C" int b2a_field_centers_batch(b2a_ctx* c, int field, int grp, int com, double* out)
 {
+    TEAM_CUR(c, b2a_field_centers_batch(m, field, grp, com, out));
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_centers_batch: null argument");
     Group* g = nullptr;
     if (int rc = field_ready(c, field, &g, grp)) return rc;
@@ -780,6 +880,7 @@ extern "C" int b2a_field_centers_batch(b2a_ctx* c, int field, int grp, int com, 
 
 extern "C" int b2a_field_centers(b2a_ctx* c, int field, int grp, int com, int frame, double* out)
 {
+    TEAM_CUR(c, b2a_field_centers(m, field, grp, com, frame, out));
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_centers: null argument");
     Group* g = nullptr;
     if (int rc = field_ready(c, field, &g, grp)) return rc;
@@ -793,6 +894,7 @@ extern "C" int b2a_field_centers(b2a_ctx* c, int field, int grp, int com, int fr
 
 extern "C" int b2a_field_values(b2a_ctx* c, int field, int grp, int frame, double* out)
 {
+    TEAM_CUR(c, b2a_field_values(m, field, grp, frame, out));
     if (!c || !out) return fail(B2A_ERR_ARG, "b2a_field_values: null argument");
     Group* g = nullptr;
     if (int rc = field_ready(c, field, &g, grp)) return rc;
@@ -826,6 +928,60 @@ static int new_acc(b2a_ctx* c, std::unique_ptr<Acc> a, int* id)
     return B2A_OK;
 }
 
+// next pinned slot of the per-frame constants (slot index through *slot); waits only if the host is kFrameRing batches ahead
+static int ring_acquire(Acc& a, int* slot)
+{
+    FrameRing& r = a.ring;
+    const int  s = r.next;
+    r.next       = (s + 1) % kFrameRing;
+    if (!r.ev[s]) CU(cudaEventCreateWithFlags(&r.ev[s], cudaEventDisableTiming));
+    else CU(cudaEventSynchronize(r.ev[s]));
+    *slot = s;
+    return B2A_OK;
+}
+
+// Scratch sized at create time must still fit the groups (b2a_set_group may have redefined them since): grow it here
+// rather than let the prep kernels write past the old allocation.
+template <typename T>
+static int regrow(T** p, size_t n)
+{
+    cudaFree(*p);
+    *p = nullptr;
+    CU(cudaMalloc(p, sizeof(T) * n));
+    return B2A_OK;
+}
+
+template <typename T>
+static int grow_log(b2a_ctx* c, T** p, size_t used, size_t n)
+{
+    T* q = nullptr;
+    CU(cudaMalloc(&q, sizeof(T) * n));
+    if (*p && used) CU(cudaMemcpyAsync(q, *p, sizeof(T) * used, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(*p);
+    *p = q;
+    return B2A_OK;
+}
+
+// room for `more` frames at the end of an accumulator's per-frame log; grows geometrically (rare: a stream-ordered copy)
+static int series_reserve(b2a_ctx* c, Acc& a, size_t more)
+{
+    const size_t need = a.series_len + more;
+    if (need <= a.series_cap) return B2A_OK;
+    const size_t cap = std::max(need, std::max<size_t>(2 * a.series_cap, 4 * (size_t)c->maxK));
+    if (a.kind == ACC_REGION)
+    {
+        if (int rc = grow_log(c, &a.d_perframe, a.series_len * a.ndev, cap * a.ndev)) return rc;
+    }
+    else
+    {
+        if (int rc = grow_log(c, &a.d_table, a.series_len * (size_t)a.coord.max_count, cap * (size_t)a.coord.max_count)) return rc;
+        if (int rc = grow_log(c, &a.d_series_numA, a.series_len, cap)) return rc;
+    }
+    a.series_cap = cap;
+    return B2A_OK;
+}
+
 static int get_acc(b2a_ctx* c, int id, Acc** out)
 {
     if (!c) return fail(B2A_ERR_ARG, "null context");
@@ -836,6 +992,7 @@ static int get_acc(b2a_ctx* c, int id, Acc** out)
 
 extern "C" int b2a_density_create(b2a_ctx* c, const b2a_density_spec* s, int* id)
 {
+    TEAM_ALL(c, b2a_density_create(m, s, id));   // created in the same order on every member: same id everywhere
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_density_create: null argument");
     Group* g = nullptr;
     if (int rc = get_group(c, s->grp, &g)) return rc;
@@ -851,6 +1008,7 @@ extern "C" int b2a_density_create(b2a_ctx* c, const b2a_density_spec* s, int* id
 
 extern "C" int b2a_region_create(b2a_ctx* c, const b2a_region_spec* s, int* id)
 {
+    TEAM_ALL(c, b2a_region_create(m, s, id));   // created in the same order on every member: same id everywhere
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_region_create: null argument");
     Group* g = nullptr;
     if (int rc = get_group(c, s->grp, &g)) return rc;
@@ -873,13 +1031,14 @@ extern "C" int b2a_region_create(b2a_ctx* c, const b2a_region_spec* s, int* id)
     if (s->per_frame)
     {
         if (n * (size_t)c->maxK > ((size_t)1 << 28)) return fail(B2A_ERR_UNSUPPORTED, "b2a_region_create: per-frame table of %zu x %d counters", n, c->maxK);
-        CU(cudaMalloc(&a->d_perframe, sizeof(unsigned long long) * n * c->maxK));
+        if (int rc = series_reserve(c, *a, (size_t)c->maxK)) return rc;
     }
     return new_acc(c, std::move(a), id);
 }
 
 extern "C" int b2a_rdf_create(b2a_ctx* c, const b2a_rdf_spec* s, int* id)
 {
+    TEAM_ALL(c, b2a_rdf_create(m, s, id));   // created in the same order on every member: same id everywhere
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_rdf_create: null argument");
     Group *g0 = nullptr, *g1 = nullptr;
     if (int rc = get_group(c, s->grp0, &g0)) return rc;
@@ -899,12 +1058,14 @@ extern "C" int b2a_rdf_create(b2a_ctx* c, const b2a_rdf_spec* s, int* id)
     CU(cudaMalloc(&a->d_slab_cnt, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK));
     CU(cudaMalloc(&a->d_sortedA, sizeof(int4) * (size_t)g0->nmol * c->maxK));
     CU(cudaMalloc(&a->d_frames, sizeof(RdfFrame) * c->maxK));
-    CU(cudaMallocHost(&a->h_frames, sizeof(RdfFrame) * c->maxK));
+    CU(cudaMallocHost(&a->h_frames, sizeof(RdfFrame) * c->maxK * kFrameRing));
+    a->alloc_n0 = g0->nmol; a->alloc_n1 = g1->nmol;
     return new_acc(c, std::move(a), id);
 }
 
 extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
 {
+    TEAM_ALL(c, b2a_rdf_tune(m, id, symmetric, paranoid));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF", id);
@@ -915,6 +1076,7 @@ extern "C" int b2a_rdf_tune(b2a_ctx* c, int id, int symmetric, int paranoid)
 
 extern "C" int b2a_acc_fast(b2a_ctx* c, int id, int mode)
 {
+    TEAM_ALL(c, b2a_acc_fast(m, id, mode));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind == ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is an RDF: use b2a_rdf_tune", id);
@@ -925,6 +1087,7 @@ extern "C" int b2a_acc_fast(b2a_ctx* c, int id, int mode)
 
 extern "C" int b2a_rdf_cells(b2a_ctx* c, int id, int mode)
 {
+    TEAM_ALL(c, b2a_rdf_cells(m, id, mode));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_RDF && a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not an RDF or coordination-number accumulator", id);
@@ -1096,13 +1259,25 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     p.Rm     = (double)s.Rm;
     p.Rbin_d = (double)s.Rbin;
     p.rbin_bits = kMagicBits + (unsigned)s.Rbin;
-    // symmetric evaluation is legal only when both sides are the very same molecules with the same centre kind
-    const bool same = s.com0 == s.com1 && g0->nmol == g1->nmol && g0->napm == g1->napm && g0->h_index == g1->h_index;
+    if (g0->nmol > a.alloc_n0)
+    {   // the group was redefined with more molecules after b2a_rdf_create: the per-molecule scratch must follow
+        CU(cudaStreamSynchronize(c->stream));
+        if (int rc = regrow(&a.d_slab_id, (size_t)g0->nmol * c->maxK)) return rc;
+        if (int rc = regrow(&a.d_sortedA, (size_t)g0->nmol * c->maxK)) return rc;
+        a.alloc_n0 = g0->nmol;
+    }
+    // symmetric evaluation is legal only when both sides are the very same molecules with the same centres: same atoms, same
+    // centre kind, same weights and the same divisor (b2a_set_group_wsum may have overridden one of them)
+    const bool same = s.com0 == s.com1 && (s.grp0 == s.grp1 || (g0->nmol == g1->nmol && g0->napm == g1->napm && !g0->csr && !g1->csr &&
+                                                                g0->h_index == g1->h_index && g0->h_w[s.com0] == g1->h_w[s.com1] &&
+                                                                g0->wsum[s.com0] == g1->wsum[s.com1]));
     p.sym_enabled   = (a.symmetric && same) ? 1 : 0;
 
     // per-frame fast-path constants
     bool cubic = true;
-    CU(cudaStreamSynchronize(c->stream));   // h_frames reuse
+    int  slot  = 0;
+    if (int rc = ring_acquire(a, &slot)) return rc;
+    RdfFrame* const h_frames = a.h_frames + (size_t)slot * c->maxK;
     for (int f = 0; f < c->nframes; ++f)
     {
         const FrameGeom& g = c->h_geom[f];
@@ -1114,7 +1289,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     for (int f = 0; f < c->nframes; ++f)
     {
         const FrameGeom& g    = c->h_geom[f];
-        RdfFrame&        fr   = a.h_frames[f];
+        RdfFrame&        fr   = h_frames[f];
         const double     unit = g.L[0] / 4294967296.0;                  // nm per x fixed unit
         const double     sc   = unit * (double)s.Rbin / (double)s.Rm;   // bins per unit
         float lo = (float)(sc * (1.0 - eps)), hi = (float)(sc * (1.0 + eps));
@@ -1132,7 +1307,8 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         fr.r2max = (float)(r_units * r_units);
         for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
     }
-    CU(cudaMemcpyAsync(a.d_frames, a.h_frames, sizeof(RdfFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(a.d_frames, h_frames, sizeof(RdfFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(a.ring.ev[slot], c->stream));
 
     // Shared histogram: pairs beyond the cut-off are clamped into ONE trash bin (bin Rbin).  Measured on B200
     // (profiles/r01_k3_tuning.md): faster than an oversize histogram -- the ~48 % of lanes beyond Rm hit a single address
@@ -1230,21 +1406,35 @@ static int accumulate_region(b2a_ctx* c, Acc& a)
     for (int b = 0; b < 2; ++b) { d.bdim[b] = s.bdim[b]; d.nb[b] = s.nb[b]; d.blow[b] = (double)s.blow[b]; d.dbin[b] = s.dbin[b]; }
     Timed tm(c, 3);
     dim3  grid((g->nmol + 255) / 256, c->nframes);
-    if (a.d_perframe) CU(cudaMemsetAsync(a.d_perframe, 0, sizeof(unsigned long long) * a.ndev * c->nframes, c->stream));
-    k2g_region<<<grid, 256, 0, c->stream>>>(g->d_cen[s.com], c->nframes, g->nmol, d, c->d_geom, a.d_hist, a.d_hist + a.ndev, a.d_perframe, a.ndev);
+    unsigned long long* pf = nullptr;   // this batch's slice of the per-frame log
+    if (s.per_frame)
+    {
+        if (int rc = series_reserve(c, a, (size_t)c->nframes)) return rc;
+        pf = a.d_perframe + a.series_len * a.ndev;
+        CU(cudaMemsetAsync(pf, 0, sizeof(unsigned long long) * a.ndev * c->nframes, c->stream));
+    }
+    k2g_region<<<grid, 256, 0, c->stream>>>(g->d_cen[s.com], c->nframes, g->nmol, d, c->d_geom, a.d_hist, a.d_hist + a.ndev, pf, a.ndev);
     CU(cudaGetLastError());
+    if (s.per_frame)
+    {
+        a.batches.push_back({ c->frame_base, c->nframes });
+        a.series_len += (size_t)c->nframes;
+    }
     a.perframe_frames = c->nframes;
     return B2A_OK;
 }
 
 extern "C" int b2a_region_read_frames(b2a_ctx* c, int id, unsigned long long* out)
 {
+    TEAM_CUR(c, b2a_region_read_frames(m, id, out));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_REGION || !a->d_perframe) return fail(B2A_ERR_ARG, "accumulator %d keeps no per-frame counters (b2a_region_spec.per_frame)", id);
     if (!out) return fail(B2A_ERR_ARG, "b2a_region_read_frames: null output");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(out, a->d_perframe, sizeof(unsigned long long) * a->ndev * a->perframe_frames, cudaMemcpyDeviceToHost, c->stream));
+    if (a->perframe_frames <= 0 || a->series_len < (size_t)a->perframe_frames) return fail(B2A_ERR_STATE, "nothing accumulated yet");
+    CU(cudaMemcpyAsync(out, a->d_perframe + (a->series_len - a->perframe_frames) * a->ndev, sizeof(unsigned long long) * a->ndev * a->perframe_frames,
+                       cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return B2A_OK;
 }
@@ -1295,6 +1485,7 @@ __global__ void k_add_frames(unsigned long long* stats, unsigned long long n) { 
 
 extern "C" int b2a_accumulate(b2a_ctx* c, int id)
 {
+    TEAM_CUR(c, b2a_accumulate(m, id));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     CU(cudaSetDevice(c->device));
@@ -1311,20 +1502,28 @@ extern "C" int b2a_accumulate(b2a_ctx* c, int id)
     if (rc) return rc;
     k_add_frames<<<1, 1, 0, c->stream>>>(a->d_hist + a->ndev, (unsigned long long)c->nframes);
     CU(cudaGetLastError());
+    a->epoch++;
     return B2A_OK;
 }
 
 extern "C" int b2a_acc_reset(b2a_ctx* c, int id)
 {
+    TEAM_ALL(c, b2a_acc_reset(m, id));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     CU(cudaSetDevice(c->device));
     CU(cudaMemsetAsync(a->d_hist, 0, sizeof(unsigned long long) * (a->ndev + B2A_STAT_NSLOTS), c->stream));
+    a->epoch++;
+    a->series_len = 0;
+    a->batches.clear();
+    a->perframe_frames = a->table_frames = 0;
+    a->gathered.clear(); a->gathered_idx.clear();
     return B2A_OK;
 }
 
 extern "C" int b2a_acc_size(b2a_ctx* c, int id, size_t* n)
 {
+    TEAM_FIRST(c, b2a_acc_size(m, id, n));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (!n) return fail(B2A_ERR_ARG, "null argument");
@@ -1332,8 +1531,19 @@ extern "C" int b2a_acc_size(b2a_ctx* c, int id, size_t* n)
     return B2A_OK;
 }
 
+extern "C" int b2a_acc_public_size(b2a_ctx* c, int id, size_t* n)
+{
+    TEAM_FIRST(c, b2a_acc_public_size(m, id, n));
+    Acc* a = nullptr;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (!n) return fail(B2A_ERR_ARG, "null argument");
+    *n = a->ncounters;
+    return B2A_OK;
+}
+
 extern "C" int b2a_acc_device_ptr(b2a_ctx* c, int id, void** p)
 {
+    TEAM_FIRST(c, b2a_acc_device_ptr(m, id, p));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (!p) return fail(B2A_ERR_ARG, "null argument");
@@ -1343,12 +1553,15 @@ extern "C" int b2a_acc_device_ptr(b2a_ctx* c, int id, void** p)
 
 extern "C" int b2a_acc_read(b2a_ctx* c, int id, uint64_t* counts, uint64_t* stats)
 {
+    if (c && c->is_leader()) return team_read(c, id, counts, stats);   // merges the devices first (b2a_finalize) when needed
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (!counts) return fail(B2A_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
+    // after b2a_finalize (and until the next accumulate / reset) the merged totals are what a read returns
+    const unsigned long long* src = (a->d_merged && a->merged_epoch == a->epoch) ? a->d_merged : a->d_hist;
     std::vector<unsigned long long> h(a->ndev + B2A_STAT_NSLOTS);
-    CU(cudaMemcpyAsync(h.data(), a->d_hist, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h.data(), src, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     unsigned long long* st = h.data() + a->ndev;
     if (a->kind == ACC_RDF)
@@ -1394,6 +1607,7 @@ extern "C" int b2a_rdf_normalise(const uint64_t* counts, int nbin, int Rbin, dou
 // ---- measurement support ---------------------------------------------------------------------------------------
 extern "C" int b2a_invalidate(b2a_ctx* c)
 {
+    TEAM_ALL(c, b2a_invalidate(m));
     if (!c) return fail(B2A_ERR_ARG, "null context");
     c->serial++;
     return B2A_OK;
@@ -1401,6 +1615,7 @@ extern "C" int b2a_invalidate(b2a_ctx* c)
 
 extern "C" int b2a_timing_enable(b2a_ctx* c, int enable)
 {
+    TEAM_ALL(c, b2a_timing_enable(m, enable));
     if (!c) return fail(B2A_ERR_ARG, "null context");
     c->timing = enable != 0;
     return B2A_OK;
@@ -1409,8 +1624,20 @@ extern "C" int b2a_timing_enable(b2a_ctx* c, int enable)
 extern "C" int b2a_timing_read(b2a_ctx* c, double* ms, long long* launches)
 {
     if (!c || !ms || !launches) return fail(B2A_ERR_ARG, "null argument");
+    if (c->is_leader())
+    {   // totals over the devices
+        for (int i = 0; i < 8; ++i) { ms[i] = 0; launches[i] = 0; }
+        for (b2a_ctx* m : c->members)
+        {
+            double t[8]; long long n[8];
+            if (int rc = b2a_timing_read(m, t, n)) return rc;
+            for (int i = 0; i < 8; ++i) { ms[i] += t[i]; launches[i] += n[i]; }
+        }
+        return B2A_OK;
+    }
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
     for (auto& s : c->spans)
     {
         float t = 0.f;
@@ -1427,6 +1654,7 @@ extern "C" int b2a_timing_read(b2a_ctx* c, double* ms, long long* launches)
 // ---- orientation -------------------------------------------------------------------------------------------------
 extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
 {
+    TEAM_ALL(c, b2a_orient_create(m, s, id));   // created in the same order on every member: same id everywhere
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_orient_create: null argument");
     Group* g = nullptr;
     if (int rc = get_group(c, s->grp, &g)) return rc;
@@ -1596,6 +1824,7 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
 // ---- coordination numbers (K5) -------------------------------------------------------------------------------------
 extern "C" int b2a_coord_create(b2a_ctx* c, const b2a_coord_spec* s, int* id)
 {
+    TEAM_ALL(c, b2a_coord_create(m, s, id));   // created in the same order on every member: same id everywhere
     if (!c || !s || !id) return fail(B2A_ERR_ARG, "b2a_coord_create: null argument");
     Group *g0 = nullptr, *g1 = nullptr;
     if (int rc = get_group(c, s->grp0, &g0)) return rc;
@@ -1612,9 +1841,10 @@ extern "C" int b2a_coord_create(b2a_ctx* c, const b2a_coord_spec* s, int* id)
     CU(cudaMalloc(&a->d_slab_cnt, sizeof(unsigned) * 2 * (size_t)c->maxK));
     CU(cudaMalloc(&a->d_sortedA, sizeof(int4) * (size_t)g0->nmol * c->maxK));
     CU(cudaMalloc(&a->d_cnt, sizeof(int) * (size_t)g0->nmol * c->maxK));
-    CU(cudaMalloc(&a->d_table, sizeof(unsigned) * (size_t)s->max_count * c->maxK));
+    if (int rc = series_reserve(c, *a, (size_t)c->maxK)) return rc;
     CU(cudaMalloc(&a->d_cframes, sizeof(CoordFrame) * c->maxK));
-    CU(cudaMallocHost(&a->h_cframes, sizeof(CoordFrame) * c->maxK));
+    CU(cudaMallocHost(&a->h_cframes, sizeof(CoordFrame) * c->maxK * kFrameRing));
+    a->alloc_n0 = g0->nmol; a->alloc_n1 = g1->nmol;
     return new_acc(c, std::move(a), id);
 }
 
@@ -1642,8 +1872,26 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
     if (int rc = ensure_centers(c, *g1, s.com1, true)) return rc;
     const int n0 = g0->nmol, n1 = g1->nmol;
 
+    if (n0 > a.alloc_n0)
+    {   // group 0 redefined with more molecules after b2a_coord_create
+        CU(cudaStreamSynchronize(c->stream));
+        if (int rc = regrow(&a.d_slab_id, (size_t)n0 * c->maxK)) return rc;
+        if (int rc = regrow(&a.d_sortedA, (size_t)n0 * c->maxK)) return rc;
+        if (int rc = regrow(&a.d_cnt, (size_t)n0 * c->maxK)) return rc;
+        if (a.d_keysA) { if (int rc = regrow(&a.d_keysA, (size_t)n0 * c->maxK)) return rc; }
+        a.alloc_n0 = n0;
+    }
+    if (n1 > a.alloc_n1)
+    {
+        CU(cudaStreamSynchronize(c->stream));
+        if (a.d_keysB) { if (int rc = regrow(&a.d_keysB, (size_t)n1 * c->maxK)) return rc; }
+        if (a.d_sortedB) { if (int rc = regrow(&a.d_sortedB, (size_t)n1 * c->maxK)) return rc; }
+        a.alloc_n1 = n1;
+    }
     bool cubic = true;
-    CU(cudaStreamSynchronize(c->stream));   // h_cframes reuse
+    int  slot  = 0;
+    if (int rc = ring_acquire(a, &slot)) return rc;
+    CoordFrame* const h_cframes = a.h_cframes + (size_t)slot * c->maxK;
     for (int f = 0; f < c->nframes; ++f)
         if (c->h_geom[f].L[0] != c->h_geom[f].L[1] || c->h_geom[f].L[0] != c->h_geom[f].L[2]) cubic = false;
     // FP32 error of r^2 (x fixed units^2): 3 I2FP + FMUL/FFMA/FFMA -> 5 * 2^-24 relative (7 * 2^-24 with the two axis-ratio
@@ -1653,7 +1901,7 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
     for (int f = 0; f < c->nframes; ++f)
     {
         const FrameGeom& g  = c->h_geom[f];
-        CoordFrame&      fr = a.h_cframes[f];
+        CoordFrame&      fr = h_cframes[f];
         const double     unit = g.L[0] / 4294967296.0;
         fr.ay = (float)(g.L[1] / g.L[0]);
         fr.az = (float)(g.L[2] / g.L[0]);
@@ -1673,10 +1921,13 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
         fr.t_small = next_up((float)(rs * rs * (1.0 + erel)));
         for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
     }
-    CU(cudaMemcpyAsync(a.d_cframes, a.h_cframes, sizeof(CoordFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(a.d_cframes, h_cframes, sizeof(CoordFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(a.ring.ev[slot], c->stream));
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)c->maxK, c->stream));
     CU(cudaMemsetAsync(a.d_cnt, 0, sizeof(int) * (size_t)n0 * c->nframes, c->stream));
-    CU(cudaMemsetAsync(a.d_table, 0, sizeof(unsigned) * (size_t)s.max_count * c->nframes, c->stream));
+    if (int rc = series_reserve(c, a, (size_t)c->nframes)) return rc;
+    unsigned* const tab = a.d_table + a.series_len * (size_t)s.max_count;   // this batch's slice of the per-frame log
+    CU(cudaMemsetAsync(tab, 0, sizeof(unsigned) * (size_t)s.max_count * c->nframes, c->stream));
 
     CoordSelect sel{};
     sel.dim = s.dim; sel.use_cyl = s.use_cyl; sel.low = (double)s.low; sel.up = (double)s.up;
@@ -1768,23 +2019,28 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
             p.jsplit         = (n1 + p.jchunk - 1) / p.jchunk;
             if (int rc = launch_coord<8, 0>(c, a, *g0, *g1, p, cd, dim3(itiles, p.jsplit, c->nframes), cubic)) return rc;
         }
-        k5_hist<<<grid, 256, sizeof(unsigned) * (s.max_count + 2), c->stream>>>(a.d_cnt, a.d_slab_id, c->nframes, n0, s.max_count, a.d_table, a.d_hist,
+        k5_hist<<<grid, 256, sizeof(unsigned) * (s.max_count + 2), c->stream>>>(a.d_cnt, a.d_slab_id, c->nframes, n0, s.max_count, tab, a.d_hist,
                                                                                  a.d_hist + a.ndev);
         CU(cudaGetLastError());
     }
+    CU(cudaMemcpyAsync(a.d_series_numA + a.series_len, a.d_slab_cnt, sizeof(unsigned) * c->nframes, cudaMemcpyDeviceToDevice, c->stream));
+    a.batches.push_back({ c->frame_base, c->nframes });
+    a.series_len += (size_t)c->nframes;
     a.table_frames = c->nframes;
     return B2A_OK;
 }
 
 extern "C" int b2a_coord_read_frames(b2a_ctx* c, int id, uint32_t* table, uint32_t* numA)
 {
+    TEAM_CUR(c, b2a_coord_read_frames(m, id, table, numA));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not a coordination-number accumulator", id);
     if (!table || !numA) return fail(B2A_ERR_ARG, "null argument");
-    if (a->table_frames <= 0) return fail(B2A_ERR_STATE, "nothing accumulated yet");
+    if (a->table_frames <= 0 || a->series_len < (size_t)a->table_frames) return fail(B2A_ERR_STATE, "nothing accumulated yet");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(table, a->d_table, sizeof(unsigned) * (size_t)a->coord.max_count * a->table_frames, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(table, a->d_table + (a->series_len - a->table_frames) * (size_t)a->coord.max_count,
+                       sizeof(unsigned) * (size_t)a->coord.max_count * a->table_frames, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(numA, a->d_slab_cnt, sizeof(unsigned) * a->table_frames, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return B2A_OK;
@@ -1792,6 +2048,7 @@ extern "C" int b2a_coord_read_frames(b2a_ctx* c, int id, uint32_t* table, uint32
 
 extern "C" int b2a_coord_counts(b2a_ctx* c, int id, int frame, int32_t* count)
 {
+    TEAM_CUR(c, b2a_coord_counts(m, id, frame, count));
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     if (a->kind != ACC_COORD) return fail(B2A_ERR_ARG, "accumulator %d is not a coordination-number accumulator", id);
@@ -1824,3 +2081,5 @@ extern "C" int b2a_coord_fold(const uint32_t* table, const uint32_t* numA, int n
     }
     return B2A_OK;
 }
+
+#include "b2a_multi.cuh"   // multi-GPU: leader contexts, NCCL communicator, b2a_finalize, per-frame series

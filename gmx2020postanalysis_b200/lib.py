@@ -27,6 +27,8 @@ SYMBOLS = [
     "b2a_coord_counts", "b2a_coord_fold", "b2a_accumulate", "b2a_acc_reset", "b2a_acc_size",
     "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_acc_fast", "b2a_invalidate", "b2a_timing_enable",
     "b2a_timing_read",
+    "b2a_create_multi", "b2a_num_devices", "b2a_member", "b2a_current_device", "b2a_finalize", "b2a_comm_unique_id", "b2a_comm_init",
+    "b2a_set_frame_base", "b2a_series_size", "b2a_series_read", "b2a_acc_public_size", "b2a_centers_device",
 ]
 
 
@@ -122,6 +124,19 @@ def load():
         L.b2a_invalidate.argtypes = [_P]
         L.b2a_timing_enable.argtypes = [_P, C.c_int]
         L.b2a_timing_read.argtypes = [_P, _P, _P]
+        L.b2a_create_multi.argtypes = [C.POINTER(_P), C.c_int, _P, C.c_int, C.c_int]
+        L.b2a_num_devices.argtypes = [_P]
+        L.b2a_member.argtypes = [_P, C.c_int]
+        L.b2a_member.restype = _P
+        L.b2a_current_device.argtypes = [_P]
+        L.b2a_finalize.argtypes = [_P]
+        L.b2a_comm_unique_id.argtypes = [_P]
+        L.b2a_comm_init.argtypes = [_P, C.c_int, C.c_int, _P]
+        L.b2a_set_frame_base.argtypes = [_P, C.c_longlong]
+        L.b2a_series_size.argtypes = [_P, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.b2a_series_read.argtypes = [_P, C.c_int, _P, _P]
+        L.b2a_acc_public_size.argtypes = [_P, C.c_int, C.POINTER(C.c_size_t)]
+        L.b2a_centers_device.argtypes = [_P, C.c_int, C.c_int, C.POINTER(_P)]
         _lib = L
     return _lib
 
@@ -150,12 +165,45 @@ def pinned_empty(shape, dtype):
 class Context:
     """One GPU, one stream: owner of the device-resident frame batch, group tables and accumulators."""
 
-    def __init__(self, natoms: int, max_frames: int, device: int = 0):
+    def __init__(self, natoms: int, max_frames: int, device: int = 0, devices=None):
+        """devices: list of CUDA devices -> one context driving all of them (b2a_create_multi): batches are dealt to the
+        devices in turn, read() returns the totals over the devices."""
         self.L = load()
         self._h = _P()
-        check(self.L.b2a_create(C.byref(self._h), device, natoms, max_frames))
+        if devices is None:
+            check(self.L.b2a_create(C.byref(self._h), device, natoms, max_frames))
+            self.devices = [device]
+        else:
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            check(self.L.b2a_create_multi(C.byref(self._h), len(dv), dv.ctypes.data, natoms, max_frames))
+            self.devices, device = [int(d) for d in dv], int(dv[0])
         self.natoms, self.max_frames, self.device = natoms, max_frames, device
         self._keep = []
+
+    # ---- several GPUs / processes ------------------------------------------------------------------------
+    def finalize(self):
+        """The merge: one 64-bit integer all-reduce per accumulator over the devices (and processes) of the communicator."""
+        check(self.L.b2a_finalize(self._h))
+
+    def comm_init(self, nprocs, rank, uid: bytes):
+        assert len(uid) == 128
+        buf = C.create_string_buffer(uid, 128)
+        check(self.L.b2a_comm_init(self._h, nprocs, rank, C.cast(buf, _P)))
+
+    def set_frame_base(self, first_frame):
+        check(self.L.b2a_set_frame_base(self._h, int(first_frame)))
+
+    def current_device(self):
+        return self.L.b2a_current_device(self._h)
+
+    def series(self, acc):
+        """-> (frame_index [n] int64, records [n, words] uint64) ordered by global frame index over all devices."""
+        n, w = C.c_size_t(), C.c_size_t()
+        check(self.L.b2a_series_size(self._h, acc, C.byref(n), C.byref(w)))
+        idx = np.zeros(n.value, dtype=np.int64)
+        out = np.zeros((n.value, w.value), dtype=np.uint64)
+        check(self.L.b2a_series_read(self._h, acc, idx.ctypes.data, out.ctypes.data))
+        return idx, out
 
     def close(self):
         if self._h:
@@ -216,6 +264,12 @@ class Context:
         out = np.empty((3, n), dtype=np.float64)
         check(self.L.b2a_centers(self._h, grp, com, frame, out.ctypes.data))
         return out.T            # [nmol, 3], column-major memory like itp::matd
+
+    def centers_device(self, grp, com=0) -> int:
+        """Queue the centre kernel for the current batch and return the device address of [K][3][nmol] doubles (no copy)."""
+        p = _P()
+        check(self.L.b2a_centers_device(self._h, grp, com, C.byref(p)))
+        return int(p.value or 0)
 
     def centers_batch(self, grp, com=0):
         n, K = max(self.nmol(grp), 0), max(self.L.b2a_batch_frames(self._h), 0)
@@ -361,11 +415,26 @@ class Context:
         check(self.L.b2a_acc_device_ptr(self._h, acc, C.byref(p)))
         return int(p.value)
 
-    def read(self, acc, ncounters):
-        counts = np.zeros(ncounters, dtype=np.uint64)
+    def read(self, acc, ncounters=None):
+        """b2a_acc_read always writes the accumulator's public layout; the buffer is sized from the library, never from the
+        caller (`ncounters`, kept for older call sites, only slices the result)."""
+        full = self._public_size(acc)
+        counts = np.zeros(full, dtype=np.uint64)
         stats = np.zeros(STAT_NSLOTS, dtype=np.uint64)
         check(self.L.b2a_acc_read(self._h, acc, counts.ctypes.data, stats.ctypes.data))
-        return counts, stats
+        return (counts if ncounters is None else counts[:ncounters]), stats
+
+    def _public_size(self, acc):
+        n = C.c_size_t()
+        check(self.L.b2a_acc_public_size(self._h, acc, C.byref(n)))
+        return n.value
+
+
+def comm_unique_id() -> bytes:
+    """128-byte id of a new multi-process communicator (rank 0 calls this and broadcasts it through the launcher's channel)."""
+    buf = C.create_string_buffer(128)
+    check(load().b2a_comm_unique_id(C.cast(buf, _P)))
+    return buf.raw
 
 
 def coord_fold(table, numA, tot=None):

@@ -7,9 +7,12 @@
  * class: include/itp/gmx forwards the loaders to it, and ported programs /
  * bench.py call the fused accumulators.  Everything is extern "C", plain pointers and sizes, status
  * codes instead of gmx_fatal (the C++ wrapper turns them back into gmx_fatal with the reference's
- * messages).  One context = one GPU = one host control thread; calls on a context are not thread-safe,
- * distinct contexts are independent.  All device work is queued on the context's stream; calls that
- * return data to host memory synchronise that stream, everything else is asynchronous.
+ * messages).  One context = one host control thread driving one GPU (b2a_create) or several (b2a_create_multi:
+ * K-frame batches are dealt to the devices in turn, histograms are merged by one NCCL all-reduce in b2a_finalize);
+ * calls on a context are not thread-safe, distinct contexts are independent.  All device work is queued on the
+ * context's stream(s); calls that return data to host memory synchronise, everything else -- b2a_submit_batch and
+ * b2a_accumulate included -- is asynchronous (b2a_submit_batch waits only for the PREVIOUS upload to leave the
+ * caller's buffer; b2a_accumulate only if the host is four batches ahead of the device).
  *
  * Reference interface replaced by each entry point (paths relative to /root/reference):
  *   b2a_set_group      <- GmxHandle::init: get_natom_per_mol / get_mass / get_charge results
@@ -33,8 +36,11 @@
  *                         b2a_centers / b2a_positions / b2a_field_centers (full.ipp:115-250)
  *   b2a_set_group_wsum <- callers that divide by their own weight sum (e.g. the dipole programs' charge sums)
  *   b2a_acc_read       <- the post-loop reads of the programs' histograms (`density /= hd.nframe` and friends)
- * No reference counterpart (infrastructure of the boundary): b2a_create / destroy / sync / stream / version / device_count /
- * last_error, b2a_pinned_alloc / free (the frame batcher's host buffers), b2a_accumulate / acc_reset / acc_size /
+ *   b2a_create_multi / b2a_finalize / b2a_series_* <- the single frame loop of a program (src/general/calc_rdf_region.cpp:68-97) sharded
+ *                         over the GPUs of one box by contiguous frame blocks, and the per-frame outputs
+ *                         (src/mofs/calc_density_time.cpp:41-58; calc_pair_dist_bulk.cpp:89-92) gathered in frame order
+ * No reference counterpart (infrastructure of the boundary): b2a_comm_* (multi-process communicator), b2a_member / num_devices /
+ * current_device / set_frame_base, b2a_create / destroy / sync / stream / version / device_count / last_error, b2a_pinned_alloc / free (the frame batcher's host buffers), b2a_accumulate / acc_reset / acc_size /
  * acc_device_ptr (multi-GPU all-reduce), b2a_rdf_tune / rdf_cells / acc_fast / invalidate / timing_* (experiments, validation).
  */
 #ifndef B2A_H
@@ -72,6 +78,45 @@ int  b2a_create(b2a_ctx** ctx, int device, int natoms, int max_frames);
 void b2a_destroy(b2a_ctx* ctx);
 int  b2a_sync(b2a_ctx* ctx);
 void* b2a_stream(b2a_ctx* ctx);        /* the cudaStream_t all work is queued on */
+
+/* ---- several GPUs behind ONE context -------------------------------------------------------------
+ * ndev member contexts, one per entry of devices[] (NULL = devices 0..ndev-1).  The returned LEADER accepts every call
+ * of this header: groups, accumulator creation / tuning / reset go to all devices; b2a_submit_batch deals the batch (a
+ * contiguous block of frames) to the NEXT device in turn and b2a_accumulate / the loaders act on the device holding the
+ * current batch; b2a_acc_read returns the totals over all devices (it calls b2a_finalize when they are stale).  A program
+ * written as `do { b2a_submit_batch; b2a_accumulate; } while (frames); b2a_acc_read;` therefore runs on N GPUs unchanged
+ * (the drop-in handles create a leader when the environment names several devices: B2A_DEVICES=0,1,2,3 or "all").
+ * The communicator (ncclCommInitAll) is built here, not inside the frame loop.  devices[] may repeat a device (used by
+ * the one-GPU tests: the merge is then a local sum, NCCL cannot place two ranks on one device).                        */
+int  b2a_create_multi(b2a_ctx** ctx, int ndev, const int* devices, int natoms, int max_frames);
+int  b2a_num_devices(b2a_ctx* ctx);              /* 1 for a b2a_create context */
+b2a_ctx* b2a_member(b2a_ctx* ctx, int i);        /* device i's own context (per-device streams, timing); owned by ctx */
+int  b2a_current_device(b2a_ctx* ctx);           /* member index that holds the current batch (-1 before the first) */
+
+/* Merge: ONE all-reduce (64-bit unsigned integer sum, ncclAllReduce over NVLink) per accumulator over its counters and
+ * stats block, across every device of the context and -- after b2a_comm_init -- of every process.  The private counts of
+ * each device stay untouched (the sum lands in a second buffer): accumulation may go on and b2a_finalize may be called
+ * again.  Until the next b2a_accumulate / b2a_acc_reset, b2a_acc_read returns the merged totals (on every process).
+ * Collective: with a multi-process communicator every process must call it.  Also gathers the per-frame series.        */
+int  b2a_finalize(b2a_ctx* ctx);
+
+/* Multi-process (one process per GPU or per group of GPUs, e.g. under torchrun / mpirun): rank 0 obtains an id
+ * (128 bytes), the launcher's own channel broadcasts it, every process joins.  Device i of process p is rank
+ * p * b2a_num_devices + i.                                                                                              */
+int  b2a_comm_unique_id(void* id128);
+int  b2a_comm_init(b2a_ctx* ctx, int nprocs, int proc_rank, const void* id128);
+
+/* Global index of the first frame of the NEXT submitted batch (default: frames submitted so far on this context).
+ * Processes that each read their own block of a trajectory set it so that per-frame series merge in trajectory order. */
+int  b2a_set_frame_base(b2a_ctx* ctx, long long first_frame);
+
+/* Per-frame series of an accumulator (region accumulators with spec.per_frame; coordination numbers): one record per
+ * accumulated frame since creation / reset, ORDERED BY GLOBAL FRAME INDEX over all devices (and, after b2a_finalize,
+ * all processes).  words_per_frame: region = its counters; coordination = max_count table entries (tmpPair) followed by
+ * numA.  frame_index may be NULL.  This is what lets time-series programs (mofs/calc_density_time.cpp:41-58) keep every
+ * device busy: nothing is read back inside the frame loop.                                                             */
+int  b2a_series_size(b2a_ctx* ctx, int acc, size_t* nframes, size_t* words_per_frame);
+int  b2a_series_read(b2a_ctx* ctx, int acc, long long* frame_index, uint64_t* out);
 
 /* pinned host staging for async H2D (optional; pageable memory also works, synchronously) */
 void* b2a_pinned_alloc(size_t nbytes);
@@ -112,6 +157,10 @@ int b2a_batch_frames(b2a_ctx* ctx);
 int b2a_centers(b2a_ctx* ctx, int grp, int com, int frame, double* out);
 /* all frames of the batch at once: out[frame][k][i] */
 int b2a_centers_batch(b2a_ctx* ctx, int grp, int com, double* out);
+/* The same centres left ON THE DEVICE: queues the centre kernel for the whole current batch (asynchronous, cached per batch) and
+ * returns the device address of out[frame][k][i] (valid until the next b2a_submit_batch on this device; consumers order their
+ * work after b2a_stream).  For device-side consumers of e.g. the dipole vectors (com 3) that do not want a D2H copy per frame.   */
+int b2a_centers_device(b2a_ctx* ctx, int grp, int com, const double** dptr);
 /* out: nmol x napm x 3 doubles in itp::boxd memory order: element (i,j)[k] at (i + j*nmol)*3 + k */
 int b2a_positions(b2a_ctx* ctx, int grp, int frame, double* out);
 
@@ -245,6 +294,8 @@ int b2a_acc_reset(b2a_ctx* ctx, int acc);
 /* number of u64 counters (histogram cells) and their device address, for the frame-sharded merge:
  * one all-reduce (sum, 64-bit integer) over [dptr, dptr + ncounters + B2A_STAT_NSLOTS) per accumulator. */
 int b2a_acc_size(b2a_ctx* ctx, int acc, size_t* ncounters);
+/* number of u64 words b2a_acc_read writes into `counts` (the reference layout: rdf nbin*Rbin, orient nbin1*nAngle + nbin1, ...) */
+int b2a_acc_public_size(b2a_ctx* ctx, int acc, size_t* ncounters);
 int b2a_acc_device_ptr(b2a_ctx* ctx, int acc, void** dptr);
 
 /* synchronise and copy out.  counts layouts are the reference's:

@@ -43,15 +43,38 @@ namespace b2a_detail
         {
             if (!ctx_)
             {
-                int dev = 0;
-                if (const char* e = std::getenv("B2A_DEVICE")) dev = std::atoi(e);
-                check(b2a_create(&ctx_, dev, natoms, k_));
+                // B2A_DEVICES=0,1,2,3 (or "all"): one context over several GPUs -- batches are dealt to the devices in turn and the
+                // histograms merged by one NCCL all-reduce when they are read (b2a_create_multi); B2A_DEVICE=n: that one device
+                std::vector<int> devs;
+                if (const char* e = std::getenv("B2A_DEVICES"))
+                {
+                    if (std::strcmp(e, "all") == 0)
+                        for (int d = 0; d < b2a_device_count(); ++d) devs.push_back(d);
+                    else
+                        for (const char* p = e; *p;)
+                        {
+                            char* q = nullptr;
+                            const long v = std::strtol(p, &q, 10);
+                            if (q == p) break;
+                            devs.push_back((int)v);
+                            p = (*q == ',') ? q + 1 : q;
+                        }
+                }
+                if (devs.size() > 1) check(b2a_create_multi(&ctx_, (int)devs.size(), devs.data(), natoms, k_));
+                else
+                {
+                    int dev = devs.empty() ? 0 : devs[0];
+                    if (const char* e = std::getenv("B2A_DEVICE")) dev = std::atoi(e);
+                    check(b2a_create(&ctx_, dev, natoms, k_));
+                }
             }
             return ctx_;
         }
         b2a_ctx* ctx() const { return ctx_; }
         int      frames() const { return n_; }
         float    time_of(int k) const { return btime_[k]; }   // fr->time of frame k of the resident batch
+        // fr->time of every frame handed to the device so far, by global frame index (per-frame series are printed after the loop)
+        const std::vector<float>& all_times() const { return times_all_; }
         int      current() const { return cur_; }
         int      capacity() const { return k_; }
         long     serial() const { return serial_; }
@@ -60,6 +83,8 @@ namespace b2a_detail
         bool start(gmx_output_env_t* oenv, t_trxstatus* status, const t_trxframe& first, t_trxframe* fr)
         {
             oenv_ = oenv; status_ = status; io_ = first; eof_ = false;
+            times_all_.clear();
+            if (ctx_) check(b2a_set_frame_base(ctx_, 0));   // a restarted trajectory counts its frames from 0 again
             natoms_ = io_.natoms;
             const size_t n3 = (size_t)natoms_ * 3;
             for (int p = 0; p < 2; ++p)
@@ -121,6 +146,7 @@ namespace b2a_detail
                 if (n == 0) return false;
                 n_ = n;
                 ++serial_;
+                times_all_.insert(times_all_.end(), btime_.begin(), btime_.begin() + n);
                 check(b2a_submit_batch(ctx(natoms_), n, bx_, bbox_.data()));
                 return true;
             }
@@ -138,6 +164,7 @@ namespace b2a_detail
             if (n == 0) return false;
             n_ = n;
             ++serial_;
+            times_all_.insert(times_all_.end(), btime_.begin(), btime_.begin() + n);
             if (io_.bX) check(b2a_submit_batch(ctx(natoms_), n, bx_, bbox_.data()));
             // velocities / forces (TRR) ride along so that loadVelocity[Center] / loadForce[Center] run on the device too
             if (io_.bX && io_.bV) check(b2a_submit_field(ctx(natoms_), B2A_FIELD_V, n, bv_));
@@ -171,7 +198,7 @@ namespace b2a_detail
         float*             px_[2] = { nullptr, nullptr }, *pv_[2] = { nullptr, nullptr }, *pf_[2] = { nullptr, nullptr };
         float*             bx_ = nullptr, *bv_ = nullptr, *bf_ = nullptr;   // the buffers of the batch being filled / served
         int                flip_ = 0;
-        std::vector<float> bbox_, btime_;
+        std::vector<float> bbox_, btime_, times_all_;
     };
 } // namespace b2a_detail
 } // namespace itp

@@ -63,6 +63,15 @@ namespace itp
         void b2aCoordFold(int acc, int max_count, std::vector<double>& totPair);
         void b2aAccumulate(int acc);                               // whole resident batch, once per batch
         void b2aRead(int acc, std::vector<uint64_t>& counts, uint64_t* stats = nullptr);
+        // Several GPUs (environment B2A_DEVICES=0,1,... or "all"): the frame loop above is unchanged -- batches are dealt to the
+        // devices in turn; b2aRead merges the devices (one NCCL all-reduce).  Programs with per-frame output must not read inside
+        // the loop (that would serialise the devices): they fetch the whole series afterwards, ordered by frame.
+        int  b2aDevices() { return b2a_num_devices(batch_.ctx()); }
+        // per-frame records of a region (spec.per_frame) or coordination accumulator over every frame accumulated so far, in
+        // trajectory order: out[frame][word]; returns the number of frames; times (optional) receives fr->time of each
+        size_t b2aSeries(int acc, std::vector<uint64_t>& out, size_t* words = nullptr, std::vector<float>* times = nullptr);
+        // totPair[k] += tmpPair[k] / numA over the whole series, in frame order (calc_pair_dist_bulk.cpp:89-92)
+        void b2aCoordFoldSeries(int acc, int max_count, std::vector<double>& totPair);
 
     private:
         int  get_natom_per_mol(int grp);

@@ -360,6 +360,38 @@ namespace itp
         b2a_detail::check(b2a_coord_fold(table.data(), numA.data(), nf, max_count, totPair.data()));
     }
 
+    inline size_t GmxHandle::b2aSeries(int acc, std::vector<uint64_t>& out, size_t* words, std::vector<float>* times)
+    {
+        size_t n = 0, w = 0;
+        b2a_detail::check(b2a_series_size(batch_.ctx(), acc, &n, &w));
+        out.assign(n * w, 0);
+        std::vector<long long> idx(n);
+        b2a_detail::check(b2a_series_read(batch_.ctx(), acc, idx.data(), out.data()));
+        if (words) *words = w;
+        if (times)
+        {
+            const std::vector<float>& all = batch_.all_times();
+            times->resize(n);
+            for (size_t f = 0; f < n; ++f) (*times)[f] = (idx[f] >= 0 && (size_t)idx[f] < all.size()) ? all[idx[f]] : 0.f;
+        }
+        return n;
+    }
+
+    inline void GmxHandle::b2aCoordFoldSeries(int acc, int max_count, std::vector<double>& totPair)
+    {
+        std::vector<uint64_t> rec;
+        size_t                w = 0;
+        const size_t          n = b2aSeries(acc, rec, &w);
+        std::vector<uint32_t> table(n * (size_t)max_count), numA(n);
+        for (size_t f = 0; f < n; ++f)
+        {
+            for (int k = 0; k < max_count; ++k) table[f * max_count + k] = (uint32_t)rec[f * w + k];
+            numA[f] = (uint32_t)rec[f * w + max_count];
+        }
+        totPair.resize(max_count, 0.0);
+        b2a_detail::check(b2a_coord_fold(table.data(), numA.data(), (int)n, max_count, totPair.data()));
+    }
+
     inline void GmxHandle::b2aAccumulate(int acc) { b2a_detail::check(b2a_accumulate(batch_.ctx(), acc)); }
 
     inline void GmxHandle::b2aRead(int acc, std::vector<uint64_t>& counts, uint64_t* stats)

@@ -17,7 +17,7 @@ def pytest_configure(config):
 def _built():
     """Make sure the in-tree libraries exist (no-op when they are up to date)."""
     import __graft_entry__ as g
-    need = [os.path.join(ROOT, "gmx2020postanalysis_b200", n) for n in ("libb2a.so", "libb2a_synth.so")]
+    need = [os.path.join(ROOT, "gmx2020postanalysis_b200", "libb2a.so"), os.path.join(ROOT, "workloads", "libsynthgen.so")]
     need.append(os.path.join(ROOT, "oracle", "liboracle.so"))
     if not all(os.path.exists(n) for n in need):
         g.build()

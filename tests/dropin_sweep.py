@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 import refprog
-from gmx2020postanalysis_b200 import synth
+from workloads import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DROPIN = os.path.join(ROOT, "build", "dropin")

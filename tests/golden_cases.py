@@ -3,7 +3,7 @@ answers) and the tests (which ask the oracle / the GPU path).  Inputs are regene
 deterministic synthetic generator, so only the reference's outputs are committed."""
 import numpy as np
 
-from gmx2020postanalysis_b200 import synth
+from workloads import synth
 
 LOADER_FRAME = 2
 

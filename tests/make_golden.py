@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import refprog  # noqa: E402
-from gmx2020postanalysis_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 from oracle import refshim  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")

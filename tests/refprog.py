@@ -7,7 +7,7 @@ import subprocess
 
 import numpy as np
 
-from gmx2020postanalysis_b200 import trajio
+from workloads import synth, trajio
 from oracle import port
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -90,20 +90,7 @@ def oracle_rdf_region(system, nframes, grp0, grp1, nbin=5, low=-100.0, up=100.0,
     return rdf_region_text(port.rdf_normalise(rdf), nbin, Rbin, dim, low, up)
 
 
-def group_info(system, name):
-    """napm / weights for an index group that is a whole species or the oxygen subset of split-atom water."""
-    idx = np.asarray(system.groups[name], dtype=np.int32)
-    for s, off in zip(system.species, system.offsets()):
-        n = s.nmol * s.napm
-        if idx[0] >= off and idx[-1] < off + n:
-            if s.split_atoms:
-                j = int((idx[0] - off) % s.napm)
-                m = np.array([s.mass[j]], np.float64); q = np.array([s.charge[j]], np.float64)
-                return {"index": idx, "napm": 1, "w": {0: m, 1: np.ones(1), 2: q}, "mass": m, "charge": q}
-            assert len(idx) == n, "group must be a whole species"
-            m = s.mass.astype(np.float64); q = s.charge.astype(np.float64)
-            return {"index": idx, "napm": s.napm, "w": {0: m, 1: np.ones(s.napm), 2: q}, "mass": m, "charge": q}
-    raise ValueError(name)
+group_info = synth.group_info      # lives with the synthetic systems; kept under this name for the tests
 
 
 # ---- README template.cpp (README.md:129-176) -----------------------------------------------------------------

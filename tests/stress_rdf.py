@@ -15,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refprog  # noqa: E402
-from gmx2020postanalysis_b200 import lib, synth  # noqa: E402
+from gmx2020postanalysis_b200 import lib  # noqa: E402
+from workloads import synth  # noqa: E402
 
 
 def main(argv=None):

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 import refprog
-from gmx2020postanalysis_b200 import dist, lib, synth, trajio
+from gmx2020postanalysis_b200 import dist, lib
+from workloads import synth, trajio
 from oracle import port
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -72,6 +73,20 @@ def test_synth_is_deterministic_and_wrapped():
     assert not np.array_equal(s.frame(4), a)
     il = synth.ionic_liquid(10, 2.5)
     assert il.natoms == 320 and il.species[0].napm == 25 and il.species[1].napm == 7
+
+
+def test_numpy_generator_is_bit_identical_to_the_compiled_one(monkeypatch):
+    """workloads/synth.py restates synth_gen.c in numpy (what bench.py --impl reference uses, so that the reference arm maps
+    no library of this repo): same hash, same coordinates, for water and for the rejection-sampled quaternions of the blobs."""
+    for mk in (lambda: synth.water_box(700, 2.9, seed=5), lambda: synth.ionic_liquid(40, 3.1, seed=6)):
+        s = mk()
+        a = s.frames(2, 2)
+        monkeypatch.setenv("B2A_SYNTH_NUMPY", "1")
+        assert synth.use_numpy()
+        b = s.frames(2, 2)
+        h = synth.synth_hash(1, 2, 3, 4, 5)
+        monkeypatch.delenv("B2A_SYNTH_NUMPY")
+        assert np.array_equal(a, b) and h == 0x26d9ff6af1517356
 
 
 def test_shard_frames_partition():

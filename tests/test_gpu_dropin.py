@@ -58,10 +58,46 @@ def test_other_fused_ports_match_reference_output(name, exe, batch, tmp_path, mo
     assert got == _golden(name)
 
 
+def _device_env():
+    """B2A_DEVICES values to exercise: members sharing device 0 on a one-GPU box (the dealing, merge and series ordering are the
+    same code; only the NCCL call is replaced by a local sum), plus the real devices where there are several."""
+    from gmx2020postanalysis_b200 import lib
+    n = lib.load().b2a_device_count()
+    return ["0,0,0"] + (["all"] if n >= 2 else [])
+
+
+@pytest.mark.parametrize("devices", _device_env())
+def test_fused_ports_on_several_devices(devices, tmp_path, monkeypatch):
+    """SURVEY 8e behind the C++ handle: the ported programs, unchanged, with B2A_DEVICES naming several devices -- batches dealt
+    round-robin, histograms merged by b2a_finalize inside b2aRead, per-frame series gathered in frame order -- write the very
+    files of the one-device runs (= the reference's)."""
+    monkeypatch.setenv("B2A_DEVICES", devices)
+    monkeypatch.setenv("B2A_BATCH", "2")
+    for name, exe in (("rdf_water_oo", "calc_rdf_region_fused"), ("rdf_il_slabs", "calc_rdf_region_fused"),
+                      ("density_template_c1", "readme_template_fused"), ("orient_water", "calc_orient_mof_fused"),
+                      ("pair_dist_il", "calc_pair_dist_bulk_fused")):
+        case = GC.program_cases()[name]
+        got = refprog.run_program(_dropin(exe), str(tmp_path / name), case["system"](), case["nframes"], case["groups"], case["args"], "out.xvg")
+        assert got == _golden(name), name
+    # per-frame time series: one line per frame, in trajectory order, whichever device processed the frame
+    for name in ("calc_density_time", "calc_radius_distribution_in_pore_time", "calc_pair_dist"):
+        ref_exe, new_exe = os.path.join(refprog.REFDIR, name), os.path.join(DROPIN, name + "_fused")
+        if not (refprog.have_ref(name) and os.path.exists(new_exe)):
+            continue
+        st_ref, ref = SW.run(ref_exe, str(tmp_path / ("ref_" + name)), name)
+        st_new, new = SW.run(new_exe, str(tmp_path / ("new_" + name)), name)
+        assert st_ref == "ok" and st_new == "ok", (name, ref, new)
+        assert sorted(new) == sorted(ref) and all(new[fn] == ref[fn] for fn in ref), name
+    # an unmodified program (compatibility loaders) keeps working on a multi-device context as well
+    case = GC.program_cases()["rdf_water_oo"]
+    got = refprog.run_program(_dropin(case["exe"]), str(tmp_path / "compat"), case["system"](), case["nframes"], case["groups"], case["args"], "out.xvg")
+    assert got == _golden("rdf_water_oo")
+
+
 def test_density_slit_fused_port_matches_reference_build(tmp_path, monkeypatch):
     """general/density_slit_jhl.cpp ported to K2 (both region tests inclusive, second filter dimension, volume normalisation) against
     the reference build of the original on the same trajectory."""
-    from gmx2020postanalysis_b200 import synth
+    from workloads import synth
     exe = "density_slit_jhl"
     if not refprog.have_ref(exe) or not os.path.exists(os.path.join(DROPIN, exe + "_fused")):
         pytest.skip("binaries not built (needs /root/reference at build time)")
@@ -92,7 +128,7 @@ def test_region_fused_ports_match_reference_builds(name, batch, tmp_path, monkey
 
 def test_live_reference_vs_dropin_other_programs(tmp_path):
     """Programs without a golden file: run both builds here and compare (only where oracle/_ref travelled)."""
-    from gmx2020postanalysis_b200 import synth
+    from workloads import synth
     cases = [
         ("density_slit_jhl", synth.water_box(1500, 3.6, seed=71), ["SOL"], 5, []),
         ("calc_pair_dist_bulk", synth.ionic_liquid(150, 3.6, seed=72), ["CAT", "ANI"], 4, []),
@@ -117,7 +153,7 @@ def test_velocity_program_dropin_matches_reference_build(tmp_path, monkeypatch):
     """phaseChange/calc_kineticEnergy.cpp (TRX_READ_V, loadVelocityCenter + loadPositionCenter): the unmodified source
     built against the drop-in header (velocity centres computed on the device) writes the same file as the reference build."""
     import numpy as np
-    from gmx2020postanalysis_b200 import synth
+    from workloads import synth
     exe = "calc_kineticEnergy"
     if not refprog.have_ref(exe) or not os.path.exists(os.path.join(DROPIN, exe)):
         pytest.skip("calc_kineticEnergy binaries not built (needs /root/reference at build time)")
@@ -137,7 +173,7 @@ def test_dropin_reads_xtc_and_trr(batch, tmp_path, monkeypatch):
     import ctypes as C
     import subprocess
     import numpy as np
-    from gmx2020postanalysis_b200 import synth, trajio
+    from workloads import synth, trajio
     import test_trajfmt as TF
     L = C.CDLL(TF.STUB)
     L.gmxstub_write_xtc.argtypes = [C.c_char_p, C.c_int, C.c_int, TF._P, TF._P, C.c_int, TF._P, C.c_float]
@@ -175,7 +211,7 @@ def test_dropin_reads_xtc_and_trr(batch, tmp_path, monkeypatch):
 def test_handle_full_dropin_matches_reference_build(center, tmp_path, monkeypatch):
     """GmxHandleFull (heterogeneous molecule sizes): the same exerciser source built against the reference's own header
     and against the drop-in header dumps identical centres and unwrapped positions (17 significant digits)."""
-    from gmx2020postanalysis_b200 import synth
+    from workloads import synth
     ref_exe, new_exe = os.path.join(refprog.REFDIR, "full_dump"), os.path.join(DROPIN, "full_dump")
     if not (os.path.exists(ref_exe) and os.path.exists(new_exe)):
         pytest.skip("full_dump binaries not built (needs /root/reference at build time)")

@@ -8,7 +8,8 @@ import pytest
 
 import golden_cases as GC
 import refprog
-from gmx2020postanalysis_b200 import lib, synth
+from gmx2020postanalysis_b200 import lib
+from workloads import synth
 from oracle import port
 
 pytestmark = pytest.mark.gpu
@@ -155,11 +156,11 @@ def test_density_template_matches_reference_program_output(gpu_ctx_factory):
 
 
 # ---- A7: RDF -------------------------------------------------------------------------------------------------
-def _rdf_gpu(ctx, system, g0, g1, K, spec, Rm, Rbin, paranoid=0, frames=None):
+def _rdf_gpu(ctx, system, g0, g1, K, spec, Rm, Rbin, paranoid=0, frames=None, symmetric=0):
     _groups(ctx, system, [g0, g1])
     acc = ctx.rdf_create(grp0=0, grp1=1, com0=spec["com"], com1=spec["com"], nbin=spec["nbin"], low=spec["low"], up=spec["up"],
                          dim=spec["dim"], dim2=spec["dim2"], low2=spec["low2"], up2=spec["up2"], Rm=Rm, Rbin=Rbin)
-    ctx.rdf_tune(acc, 0, paranoid)
+    ctx.rdf_tune(acc, symmetric, paranoid)
     ctx.submit(system.frames(0, K) if frames is None else frames, system.box9())
     ctx.accumulate(acc)
     got, st = ctx.read(acc, spec["nbin"] * Rbin)
@@ -177,6 +178,13 @@ _DEF = dict(nbin=5, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0,
     dict(sys=("water", 3000, 4.476), g=("SOL", "SOL"), K=2, com=2, nbin=2, low=0.0, up=4.476, dim=2, Rm=0.9),   # charge centres: NaN/inf centres
     dict(sys=("water", 1500, 3.55), g=("OW", "OW"), K=1, paranoid=1),                                        # every pair through FP64
     dict(sys=("water", 700, 2.8), g=("OW", "OW"), K=2, Rm=0.4),                                              # tiny Rm: clamp-free, large kmax
+    # symmetric evaluation (i < j only, weight 2: what bench.py and the ported calc_rdf_region run) straight against the oracle
+    dict(sys=("water", 4000, 4.93), g=("OW", "OW"), K=2, symmetric=1, sym_runs=True),                        # C2 shape: MODE 1, several i-tiles
+    dict(sys=("water", 1100, 3.2), g=("OW", "OW"), K=3, symmetric=1, sym_runs=True),                         # one full + one ragged i-tile
+    dict(sys=("water", 1500, 3.55), g=("OW", "OW"), K=1, symmetric=1, paranoid=1),                           # every evaluated pair through FP64
+    dict(sys=("water", 3000, 4.476), g=("SOL", "SOL"), K=2, symmetric=1, sym_runs=True, com=0, nbin=1, Rm=0.9),   # molecular centres, cell-binned + symmetric
+    dict(sys=("water", 3000, 4.476), g=("SOL", "SOL"), K=2, symmetric=1, com=0, nbin=3, low=0.0, up=4.476, dim=2),   # several slabs: ineligible, falls through to the full kernel
+    dict(sys=("il", 400, 5.1), g=("CAT", "ANI"), K=2, symmetric=1),                                          # different groups: request ignored
 ])
 def test_rdf_bit_exact(gpu_ctx_factory, case):
     kind, n, L = case["sys"]
@@ -186,12 +194,15 @@ def test_rdf_bit_exact(gpu_ctx_factory, case):
     K = case["K"]
     exp, est, Rm, Rbin = refprog.oracle_rdf_region(system, K, case["g"][0], case["g"][1], return_counts=True, **spec)
     ctx = gpu_ctx_factory(system.natoms, K)
-    got, st = _rdf_gpu(ctx, system, case["g"][0], case["g"][1], K, spec, Rm, Rbin, case.get("paranoid", 0))
+    got, st = _rdf_gpu(ctx, system, case["g"][0], case["g"][1], K, spec, Rm, Rbin, case.get("paranoid", 0), symmetric=case.get("symmetric", 0))
     assert np.array_equal(got, exp)
     assert int(got.sum()) == int(est[0]) and int(st[lib.STAT_DROPPED]) == int(est[1])
     assert int(st[lib.STAT_SELECTED]) == int(est[2]) and int(st[lib.STAT_FRAMES]) == K
-    if case.get("paranoid"):
+    if case.get("paranoid") and not case.get("symmetric"):
         assert int(st[lib.STAT_EXACT]) == n * n * K
+    if case.get("sym_runs"):
+        # the symmetric path really ran: fewer than the N0 * N1 ordered pairs were evaluated
+        assert int(st[lib.STAT_PAIRS]) < n * n * K
 
 
 def test_rdf_matches_reference_program_output(gpu_ctx_factory):
@@ -234,13 +245,15 @@ def test_rdf_edge_fixtures(gpu_ctx_factory):
     ctx = gpu_ctx_factory(n, 1)
     for g in (0, 1):
         ctx.set_group(g, np.arange(n), 1, np.ones(1), np.ones(1))
-    acc = ctx.rdf_create(grp0=0, grp1=1, com0=1, com1=1, nbin=1, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0,
-                         Rm=Rm, Rbin=Rbin)
     ctx.submit(x, box)
-    ctx.accumulate(acc)
-    got, st = ctx.read(acc, Rbin)
-    assert np.array_equal(got.reshape(Rbin, 1), exp)
-    assert int(st[lib.STAT_DROPPED]) == int(est[1])
+    for symmetric in (0, 1):                                  # the full evaluation and the i < j one bench.py runs
+        acc = ctx.rdf_create(grp0=0, grp1=1, com0=1, com1=1, nbin=1, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0,
+                             Rm=Rm, Rbin=Rbin)
+        ctx.rdf_tune(acc, symmetric, 0)
+        ctx.accumulate(acc)
+        got, st = ctx.read(acc, Rbin)
+        assert np.array_equal(got.reshape(Rbin, 1), exp), symmetric
+        assert int(st[lib.STAT_DROPPED]) == int(est[1])
 
 
 def test_rdf_properties_translation_and_transpose(gpu_ctx_factory):
@@ -257,6 +270,37 @@ def test_rdf_properties_translation_and_transpose(gpu_ctx_factory):
     ctx2 = gpu_ctx_factory(system.natoms, K)
     h_ba, _ = _rdf_gpu(ctx2, system, "ANI", "CAT", K, spec, Rm, Rbin)
     assert np.array_equal(h_ab, h_ba) and h_ab.sum() > 0
+    # Translation by box vectors: every atom moved by its own integer multiples of the box lengths.  Minimum-image
+    # distances do not change; with exactly representable shifts (L = 5.5 = 11 * 2^-1, coordinates on a 2^-10 grid) neither do
+    # the float coordinates' fractional positions, so every histogram must be IDENTICAL, bin by bin, in both evaluation modes.
+    L = 5.5
+    system.L = np.array([L, L, L], np.float32)
+    x = system.frames(0, K)
+    x = (np.round(x * 1024.0) / 1024.0).astype(np.float32)               # 2^-10 grid: x + n L is exact in float for |n| <= 3
+    rng = np.random.default_rng(7)
+    shift = rng.integers(-3, 4, size=(1, system.natoms, 3)).astype(np.float32) * np.float32(L)
+    shift[0, system.groups["CAT"][::25]] = 0.0                           # keep some molecules' reference atoms in place
+    xs = (x + shift).astype(np.float32)
+    assert np.array_equal((xs - shift).astype(np.float32), x)
+    Lbox = port.lbox_from_box9(system.box9())
+    Rm = port.rdf_default_rm(Lbox)
+    Rbin = port.rdf_rbin(Rm)
+    out = []
+    for frames in (x, xs):
+        c = gpu_ctx_factory(system.natoms, K)
+        h, _ = _rdf_gpu(c, system, "CAT", "ANI", K, spec, Rm, Rbin, frames=frames)
+        c2 = gpu_ctx_factory(system.natoms, K)
+        hs, _ = _rdf_gpu(c2, system, "ANI", "ANI", K, spec, Rm, Rbin, frames=frames, symmetric=1)
+        out.append((h, hs))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][1].sum() > 0
+    # and the oracle agrees on the translated frames
+    g0, g1 = refprog.group_info(system, "CAT"), refprog.group_info(system, "ANI")
+    exp = np.zeros((Rbin, 1), dtype=np.uint64)
+    for f in range(K):
+        p1 = port.load_position_center(xs[f], g0["index"], g0["napm"], g0["w"][0], Lbox)
+        p2 = port.load_position_center(xs[f], g1["index"], g1["napm"], g1["w"][0], Lbox)
+        port.rdf_accum(p1, p2, Lbox, 1, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, Rbin, exp)
+    assert np.array_equal(out[1][0], exp)
 
 
 @pytest.mark.parametrize("nonzero_box", [(3.0, 4.0, 5.0)])
@@ -302,6 +346,35 @@ def test_rdf_full_size_paranoid_free_properties(gpu_ctx_factory):
     ctx2.accumulate(acc)
     got2, _ = ctx2.read(acc, 5 * Rbin)
     assert np.array_equal(got2.reshape(Rbin, 5), exp)
+
+
+def test_rdf_headline_mode_full_size_against_oracle(gpu_ctx_factory):
+    """EXACTLY the configuration bench.py times (BASELINE config 2 at full size, 8 distinct frames per batch,
+    b2a_rdf_tune(symmetric=1), cells automatic): (i) the symmetric histogram of the batch equals the full (MODE 0) evaluation of
+    the same frames, bin by bin; (ii) the symmetric kernel on one whole frame -- all 72 000 x 72 000 ordered pairs -- is
+    bit-identical to oracle.port.rdf_accum (calc_rdf_region.cpp:73-95) of that frame."""
+    n, L, K = 72000, 12.913, 8
+    system = synth.water_box(n, L, seed=20200102, split_atoms=True)
+    Lbox = port.lbox_from_box9(system.box9())
+    Rm = port.rdf_default_rm(Lbox)
+    Rbin = port.rdf_rbin(Rm)
+    x = system.frames(0, K)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    got_sym, st = _rdf_gpu(ctx, system, "OW", "OW", K, dict(_DEF), Rm, Rbin, frames=x, symmetric=1)
+    assert int(st[lib.STAT_FRAMES]) == K and int(st[lib.STAT_SELECTED]) == n * K
+    assert int(st[lib.STAT_PAIRS]) < 0.52 * n * n * K            # the i < j evaluation really ran (diagonal tiles in full)
+    ctx2 = gpu_ctx_factory(system.natoms, K)
+    got_full, st2 = _rdf_gpu(ctx2, system, "OW", "OW", K, dict(_DEF), Rm, Rbin, frames=x, symmetric=0)
+    assert int(st2[lib.STAT_PAIRS]) == n * n * K
+    assert np.array_equal(got_sym, got_full) and int(st[lib.STAT_DROPPED]) == int(st2[lib.STAT_DROPPED])
+    # one whole frame against the oracle (about 20 s of the host's cores)
+    f = 3
+    o = x[f][0::3].astype(np.float64)
+    exp, est = port.rdf_accum(o, o, Lbox, 5, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, Rbin)
+    ctx3 = gpu_ctx_factory(system.natoms, 1)
+    got1, st1 = _rdf_gpu(ctx3, system, "OW", "OW", 1, dict(_DEF), Rm, Rbin, frames=x[f:f + 1], symmetric=1)
+    assert np.array_equal(got1, exp)
+    assert int(got1.sum()) == int(est[0]) and int(st1[lib.STAT_DROPPED]) == int(est[1])
 
 
 def test_full_size_configs_3_4_5_properties(gpu_ctx_factory):

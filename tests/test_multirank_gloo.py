@@ -1,7 +1,8 @@
 """world_size-2 gloo test of the frame-sharded path on CPU: each rank accumulates its contiguous block of frames
 into private u64 histograms, one all-reduce merges them, and the result is bit-identical to the single-rank
 run (integer sums commute).  On the CPU the per-rank accumulation is played by the oracle; the sharding and the
-merge are the product's (gmx2020postanalysis_b200/dist.py)."""
+hand-over of the communicator id are the product's host plumbing (gmx2020postanalysis_b200/dist.py).  The device
+merge itself (b2a_finalize: ncclAllReduce / ncclAllGather inside libb2a) is covered by tests/test_gpu_multi.py."""
 import os
 import socket
 import sys
@@ -26,7 +27,8 @@ def _worker(rank, world, port_no, nframes, q):
         if p not in sys.path:
             sys.path.insert(0, p)
     import refprog
-    from gmx2020postanalysis_b200 import dist as b2d, synth
+    from gmx2020postanalysis_b200 import dist as b2d
+    from workloads import synth
     from oracle import port
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port_no)
@@ -45,15 +47,19 @@ def _worker(rank, world, port_no, nframes, q):
         port.rdf_accum(p1, p2, Lbox, 2, 0.0, 3.4, 0, 2, -100.0, 100.0, Rm, Rbin, rdf)
     merged = b2d.allreduce_host_counts(rdf.ravel())
     nfr = b2d.allreduce_host_counts(np.array([hi - lo], dtype=np.uint64))
+    # the launcher's other job: carry the 128-byte communicator id from rank 0 to everybody (here a stand-in id: no GPU)
+    uid = b2d.broadcast_id(lambda: bytes(range(128)))
+    ok = np.array([uid == bytes(range(128))], dtype=np.uint64)
+    ok = b2d.allreduce_host_counts(ok)
     if rank == 0:
-        q.put((merged, int(nfr[0]), (lo, hi)))
+        q.put((merged, int(nfr[0]), (lo, hi), int(ok[0])))
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_two_rank_merge_is_bit_identical():
     import refprog
-    from gmx2020postanalysis_b200 import synth
+    from workloads import synth
     nframes, world = 5, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -61,11 +67,11 @@ def test_two_rank_merge_is_bit_identical():
     procs = [ctx.Process(target=_worker, args=(r, world, port_no, nframes, q)) for r in range(world)]
     for p in procs:
         p.start()
-    merged, nfr, block0 = q.get(timeout=120)
+    merged, nfr, block0, id_ok = q.get(timeout=120)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert nfr == nframes and block0 == (0, 2)
+    assert nfr == nframes and block0 == (0, 2) and id_ok == world
     system = synth.ionic_liquid(120, 3.4, seed=41)
     exp, _, _, Rbin = refprog.oracle_rdf_region(system, nframes, "CAT", "ANI", nbin=2, low=0.0, up=3.4, dim=0, dim2=2,
                                                 return_counts=True)

@@ -8,7 +8,7 @@ import pytest
 
 import golden_cases as GC
 import refprog
-from gmx2020postanalysis_b200 import synth
+from workloads import synth
 from oracle import port, refshim
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")

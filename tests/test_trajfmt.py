@@ -15,7 +15,7 @@ import pytest
 
 import refprog
 import xtc_classic
-from gmx2020postanalysis_b200 import synth, trajio
+from workloads import synth, trajio
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 STUB = os.path.join(ROOT, "build", "libgmxstub.so")

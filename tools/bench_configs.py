@@ -15,7 +15,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from gmx2020postanalysis_b200 import lib, synth  # noqa: E402
+from gmx2020postanalysis_b200 import lib  # noqa: E402
+from workloads import synth  # noqa: E402
 
 
 def groups(ctx, system, names):

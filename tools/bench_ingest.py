@@ -20,7 +20,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from gmx2020postanalysis_b200 import synth, trajio  # noqa: E402
+from workloads import synth, trajio  # noqa: E402
 
 _P = C.c_void_p
 

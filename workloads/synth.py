@@ -1,7 +1,9 @@
 """Synthetic systems: SPC/E water boxes and a 25+7-site ionic liquid.
 
-Thin ctypes wrapper over ``libb2a_synth.so`` (include/b2a_synth.h) plus the system definitions
-(templates, masses, charges, molecule/residue tables, index groups) that the reference would read
+Test / bench harness, not product: the generator (``workloads/synth_gen.c`` -> ``libsynthgen.so``, plus a
+bit-identical pure-numpy restatement that needs no compiled code -- ``B2A_SYNTH_NUMPY=1`` or a missing library
+selects it; the reference arm of bench.py uses it so that it maps nothing this repo compiled) and the system
+definitions (templates, masses, charges, molecule/residue tables, index groups) that the reference would read
 from a .tpr/.ndx (reference include/itp/gmx_bits/gmx_handle.ipp:23-34, 419-468).
 """
 from __future__ import annotations
@@ -16,13 +18,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 
 
+LIB_PATH = os.path.join(_HERE, "libsynthgen.so")
+
+
+def use_numpy() -> bool:
+    return bool(int(os.environ.get("B2A_SYNTH_NUMPY", "0") or 0)) or not os.path.exists(LIB_PATH)
+
+
 def _load():
     global _lib
     if _lib is None:
-        path = os.path.join(_HERE, "libb2a_synth.so")
-        if not os.path.exists(path):
-            raise RuntimeError(f"{path} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
-        lib = ctypes.CDLL(path)
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        lib = ctypes.CDLL(LIB_PATH)
         lib.b2a_synth_species.restype = ctypes.c_int
         lib.b2a_synth_species.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
@@ -32,7 +40,71 @@ def _load():
     return _lib
 
 
+# ---- pure-numpy restatement of synth_gen.c (same integer hash, same IEEE double / float operations, no FMA) --------
+_U = np.uint64
+
+
+def _mix64(z):
+    z = (z ^ (z >> _U(30))) * _U(0xbf58476d1ce4e5b9)
+    z = (z ^ (z >> _U(27))) * _U(0x94d049bb133111eb)
+    return z ^ (z >> _U(31))
+
+
+def _hash_np(seed, frame, species, mol, lane):
+    """Vectorised b2a_synth_hash: `mol` and `lane` are uint64 arrays (or scalars), arithmetic wraps mod 2^64."""
+    with np.errstate(over="ignore"):
+        h = _mix64(_U(seed) + _U(0x9e3779b97f4a7c15))
+        h = _mix64(h ^ (_U(frame) * _U(0xd1342543de82ef95) + _U(0x632be59bd9b4e019)))
+        h = _mix64(h ^ (_U(species) * _U(0xa0761d6478bd642f) + _U(0xe7037ed1a0b428db)))
+        h = _mix64(h ^ (np.asarray(mol, _U) * _U(0x8ebc6af09c88c6e3) + _U(0x589965cc75374cc3)))
+        h = _mix64(h ^ (np.asarray(lane, _U) * _U(0x9e3779b97f4a7c15) + _U(0x1d8e4e27c47d124f)))
+    return h
+
+
+def _u01(h):
+    return (h >> _U(40)).astype(np.float64) * (1.0 / 16777216.0)
+
+
+def _species_numpy(seed, frame, species, nmol, tmpl, L, out):
+    mol = np.arange(nmol, dtype=_U)
+    c = np.empty((nmol, 3), np.float32)
+    for k in range(3):
+        c[:, k] = _u01(_hash_np(seed, frame, species, mol, k)).astype(np.float32) * np.float32(L[k])
+    q = np.empty((nmol, 4), np.float64)
+    n2 = np.empty(nmol, np.float64)
+    lane = np.full(nmol, 3, dtype=_U)
+    todo = np.arange(nmol)
+    while todo.size:                                        # rejection from the 4-cube, per molecule
+        acc = np.zeros(todo.size, np.float64)
+        for a in range(4):
+            qa = 2.0 * _u01(_hash_np(seed, frame, species, mol[todo], lane[todo] + _U(a))) - 1.0
+            q[todo, a] = qa
+            acc = acc + qa * qa
+        lane[todo] += _U(4)
+        n2[todo] = acc
+        todo = todo[(acc > 1.0) | (acc < 1e-6)]
+    inv = 1.0 / np.sqrt(n2)
+    w, x, y, z = (q[:, a] * inv for a in range(4))
+    R = [[1.0 - 2.0 * (y * y + z * z), 2.0 * (x * y - w * z), 2.0 * (x * z + w * y)],
+         [2.0 * (x * y + w * z), 1.0 - 2.0 * (x * x + z * z), 2.0 * (y * z - w * x)],
+         [2.0 * (x * z - w * y), 2.0 * (y * z + w * x), 1.0 - 2.0 * (x * x + y * y)]]
+    t = tmpl.astype(np.float64)
+    o = out.reshape(nmol, tmpl.shape[0], 3)
+    for j in range(tmpl.shape[0]):
+        for k in range(3):
+            Lk = np.float32(L[k])
+            p = c[:, k].astype(np.float64) + (R[k][0] * t[j, 0] + R[k][1] * t[j, 1] + R[k][2] * t[j, 2])
+            f = p.astype(np.float32)
+            f = np.where(f < 0, f + Lk, f)
+            f = np.where(f >= Lk, f - Lk, f)
+            f = np.where(f < 0, np.float32(0), f)
+            f = np.where(f >= Lk, np.float32(0), f)
+            o[:, j, k] = f
+
+
 def synth_hash(seed, frame, species, mol, lane) -> int:
+    if use_numpy():
+        return int(_hash_np(seed, frame, species, mol, lane))
     return int(_load().b2a_synth_hash(seed, frame, species, mol, lane))
 
 
@@ -70,14 +142,17 @@ class System:
         return out
 
     def frame(self, f: int, out: np.ndarray | None = None) -> np.ndarray:
-        lib = _load()
         if out is None:
             out = np.empty((self.natoms, 3), dtype=np.float32)
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (self.natoms, 3)
         L = np.ascontiguousarray(self.L, dtype=np.float32)
+        lib = None if use_numpy() else _load()
         for sid, (s, off) in enumerate(zip(self.species, self.offsets())):
             tm = np.ascontiguousarray(s.tmpl, dtype=np.float32)
             view = out[off:off + s.nmol * s.napm]
+            if lib is None:
+                _species_numpy(self.seed, f, sid, s.nmol, tm, L, view)
+                continue
             rc = lib.b2a_synth_species(self.seed, f, sid, s.nmol, s.napm, tm.ctypes.data, L.ctypes.data,
                                        view.ctypes.data)
             if rc != 0:
@@ -114,6 +189,23 @@ class System:
                     mols.append(mols[-1] + s.napm)
         return (np.asarray(m, np.float32), np.asarray(q, np.float32), np.asarray(resind, np.int32),
                 np.asarray(typ, np.int32), names, np.asarray(mols, np.int32))
+
+
+def group_info(system: System, name: str) -> dict:
+    """napm / weights of an index group that is a whole species or the oxygen subset of split-atom water: what
+    GmxHandle::init derives from the topology (get_natom_per_mol / get_mass / get_charge, reference ipp:419-468)."""
+    idx = np.asarray(system.groups[name], dtype=np.int32)
+    for s, off in zip(system.species, system.offsets()):
+        n = s.nmol * s.napm
+        if idx[0] >= off and idx[-1] < off + n:
+            if s.split_atoms:
+                j = int((idx[0] - off) % s.napm)
+                m = np.array([s.mass[j]], np.float64); q = np.array([s.charge[j]], np.float64)
+                return {"index": idx, "napm": 1, "w": {0: m, 1: np.ones(1), 2: q}, "mass": m, "charge": q}
+            assert len(idx) == n, "group must be a whole species"
+            m = s.mass.astype(np.float64); q = s.charge.astype(np.float64)
+            return {"index": idx, "napm": s.napm, "w": {0: m, 1: np.ones(s.napm), 2: q}, "mass": m, "charge": q}
+    raise ValueError(name)
 
 
 # SPC/E: O-H 0.1 nm, H-O-H 109.47 deg (SURVEY 8(d))

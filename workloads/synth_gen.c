@@ -1,5 +1,5 @@
 /* Deterministic synthetic trajectory generator; see include/b2a_synth.h. Build with -ffp-contract=off. */
-#include "b2a_synth.h"
+#include "synth_gen.h"
 
 #include <math.h>
 #include <stddef.h>

@@ -1,5 +1,5 @@
 /*
- * b2a_synth.h -- deterministic synthetic trajectory generator (host, plain C ABI).
+ * synth_gen.h -- deterministic synthetic trajectory generator (host, plain C ABI).
  *
  * the reference ships no data files (*.xtc/*.tpr are git-ignored in the
  * reference, .gitignore:5-17), so every parity test and benchmark runs on synthetic boxes.  The
@@ -10,8 +10,8 @@
  * include/itp/gmx_bits/gmx_handle.ipp:139-143, 183-191).  Only + - * / sqrt in IEEE double without
  * FMA contraction are used, so the output is bit-reproducible across hosts and compilers.
  */
-#ifndef B2A_SYNTH_H
-#define B2A_SYNTH_H
+#ifndef SYNTH_GEN_H
+#define SYNTH_GEN_H
 
 #include <stdint.h>
 
