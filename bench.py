@@ -1,94 +1,185 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark: O-O RDF of the 216k-atom synthetic water box (BASELINE.json configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2a|reference] [--config c2|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b2a|reference] [--config c1|c2|c3|c4|c5] [--no-others]
 
-`--config` selects another BASELINE.json workload for the runs recorded in profiles/ (c3: cation-anion RDF of the 1M-atom ionic
-liquid; c5: all 10 group pairs of the 4M-atom mixed box, cell-binned; use --frames-per-step 2 there); the default c2 is the
-headline the driver measures.
+The printed line is quoted on config 2 (the default; `--config` makes another BASELINE.json workload the headline of a
+manual run).  Unless `--no-others`, the line also carries `other_configs`: configs 1, 3, 4 and 5 pushed through the SAME
+measurement (a few time-boxed steps each): device-resident rate, end-to-end rate, roofline fraction of the dominant kernel,
+the reference's CPU program on the host beside it (N = 1), and a self-check -- so all five named workloads are measured by
+whoever runs this file, at every N.
 
-A "step" is one pass of the whole hot path over one batch of F frames (default 8): centres of both groups
-(K1), slab prep, all-pairs minimum-image histogram (K3).  `value` is measured with the batch already resident
-in HBM (cached intermediates are dropped before every step, so nothing is reused across steps); `e2e` goes
-through the C ABI with HOST buffers: pinned frames -> H2D -> kernels -> D2H of the u64 histogram, every step.
-Frames shard across ranks (one process per GPU, weak scaling: F frames per rank per step); the only collective
-is one all-reduce of the rank-private histograms at the end.  `--impl reference` times the reference's own CPU
-program (oracle/_ref/calc_rdf_region, compiled unmodified) on a bounded i-subset of the same frames.
+A "step" is one pass of the whole hot path over one batch of F frames: centres (K1), slab / cell prep, the pair kernel (K3)
+-- or the density (K2) / orientation (K4) kernel for configs 1 and 4.  Steps cycle through D distinct pinned batches of
+distinct synthetic frames (rank r, batch d: frames (r*D + d)*F ...), so no step sees the frames of the previous one, and the
+default 20 steps x 64 frames cover the 1000 frames config 2 names.
+  * `value`: frames resident in HBM when a step's CUDA-event bracket opens (the upload of step s+1 is queued on the copy
+    stream behind the kernels of step s and is outside every bracket); the sum of the brackets is the time.  L2 is flushed
+    before each bracket.
+  * `e2e`: wall clock of the same loop through the C ABI with HOST buffers: pinned frames -> H2D -> kernels -> D2H of the
+    u64 histogram, every step (double-buffered: the H2D of step s+1 overlaps the kernels of step s).
+  * `check.parity`: after the timed region the accumulated histogram is compared with an independent evaluation of the same
+    frames (config 2: the full N0 x N1 kernel, no symmetry, batch by batch: every timed step is accounted for); at N > 1 the
+    ncclAllReduce inside libb2a (b2a_finalize) is checked against a sum of the rank-private histograms gathered another way.
+Frames shard across ranks (one process per GPU, weak scaling: F frames per rank per step); the only collective of the path
+is the one all-reduce of the private histograms at the end, inside libb2a.  `host_cpp` reports the same workload driven by
+ONE C++ process through the drop-in handle (build/dropin/calc_rdf_region_fused, B2A_DEVICES=0..N-1).
+`--impl reference` times the reference's own CPU program (oracle/_ref, compiled unmodified) on a bounded sample.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for p in (ROOT, os.path.join(ROOT, "tests")):
-    if p not in sys.path:
-        sys.path.insert(0, p)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
-ISSUE_SLOTS_PER_PAIR = 19                           # algorithmic work per evaluated pair
-# dram__bytes_read.sum + dram__bytes_write.sum of one k3_rdf launch, per frame of the launch, from the ncu --set full
-# capture summarised in profiles/r01_k3_ncu.md (the kernel re-reads its 1.15 MB/frame of fixed-point coordinates from L2,
-# not from HBM; nothing is written back but the 26 KB histogram)
-K3_DRAM_BYTES_PER_FRAME = 4.64e6
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+DROPIN = os.path.join(ROOT, "build", "dropin")
+STUBDIR = os.path.join(ROOT, "build")
+
+ISSUE_SLOTS_PER_PAIR = 19          # algorithmic issue slots per evaluated pair (the model `frac` uses)
+# What the hardware counters say about the same kernel (ncu --set full, profiles/r01_k3_ncu.md; re-captured per round):
+# `frac` is a MODEL fraction (19 slots per pair); the kernel really executes K3_INST_PER_PAIR thread-instructions per pair
+# (packed FFMA2 / FMUL2 halve several of the 19) and keeps the issue ports busy K3_ISSUE_ACTIVE of the time.
+K3_NCU = {"issue_active": 0.787, "inst_per_pair": 17.1, "dram_bytes_per_frame": 4.64e6, "source": "profiles/r01_k3_ncu.md"}
+for _f in ("r02_k3_ncu.json",):                  # a later capture replaces the constants (tools/profile_round.sh writes it)
+    _p = os.path.join(ROOT, "profiles", _f)
+    if os.path.exists(_p):
+        try:
+            K3_NCU.update(json.load(open(_p)))
+        except Exception:
+            pass
 
 
+def hbm_peak():
+    """(GB/s, provenance): the measured copy bandwidth of this pool's B200s, else the profiling recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ================================================================================================ workloads
 class Workload:
-    """The RDF job a bench line is quoted on.  `c2` is the headline (BASELINE.json configs[1], what the driver runs); `c3`
-    (configs[2], the frame-sharded multi-GPU case) is selectable for the scaling runs recorded in profiles/."""
+    """One BASELINE.json config: the synthetic system, the device job and how to count it."""
+    kind = "rdf"
 
     def __init__(self, name):
         from workloads import synth
         self.name = name
-        if name == "c2":
-            self.L, self.seed = 12.913, 20200102
-            self.system = synth.water_box(72000, self.L, seed=self.seed, split_atoms=True)
-            self.g0 = self.g1 = "OW"
+        gi = synth.group_info
+        if name == "c1":
+            self.kind = "density"
+            self.system = synth.water_box(3000, 4.476, seed=20200101)
+            self.text = "README template density profile (nbin=100, dim=z, COM), 3k-molecule SPC/E box (9 000 atoms), 100 frames"
+            self.F, self.D = 100, 4
+            self.groups = [gi(self.system, "SOL")]
+        elif name == "c2":
+            self.L = 12.913
+            self.system = synth.water_box(72000, self.L, seed=20200102, split_atoms=True)
             self.text = "O-O RDF, 216k-atom SPC/E water box (72k O, L=12.913 nm, Rm=L/2, Rbin=3228, nbin=5), calc_rdf_region defaults"
-            self.dram_per_frame = K3_DRAM_BYTES_PER_FRAME
+            self.F, self.D = 64, 4
+            self.groups = [gi(self.system, "OW"), gi(self.system, "OW")]
+            self.pairs = [(0, 1)]
+            self.Rm, self.nbin = float(np.float32(np.float32(self.L) / np.float32(2))), 5      # calc_rdf_region.cpp:52-57, :23
         elif name == "c3":
-            self.L, self.seed = 22.1, 20200103
-            self.system = synth.ionic_liquid(31250, self.L, seed=self.seed)
-            self.g0, self.g1 = "CAT", "ANI"
+            self.L = 22.1
+            self.system = synth.ionic_liquid(31250, self.L, seed=20200103)
             self.text = ("cation-anion molecular-COM RDF, 1M-atom ionic liquid (31 250 x (25-site cation + 7-site anion), L=22.1 nm, "
                          "Rm=L/2, Rbin=5525, nbin=5), calc_rdf_region defaults")
-            self.dram_per_frame = None
+            self.F, self.D = 16, 2
+            self.groups = [gi(self.system, "CAT"), gi(self.system, "ANI")]
+            self.pairs = [(0, 1)]
+            self.Rm, self.nbin = float(np.float32(np.float32(self.L) / np.float32(2))), 5
+        elif name == "c4":
+            self.kind = "orient"
+            self.system = synth.water_box(166666, 17.09, seed=20200104)
+            self.text = ("charge-centre dipole vectors + bisector orientation-angle histogram (calc_orient_mof, nAngle=90), "
+                         "166 666 SPC/E = 499 998 atoms")
+            self.F, self.D = 64, 2
+            self.groups = [gi(self.system, "SOL")]
         elif name == "c5":
-            self.L, self.seed = 34.0, 20200105
+            self.L = 34.0
             self.system = synth.mixed_box()
-            self.g0 = self.g1 = "SOL"                              # the CPU sample is taken on the dominant pair
             self.text = ("mixed-species RDF sweep, 4M atoms (1.2M water + 8k cation + 8k anion + 24k cosolvent, L=34 nm), all 10 group "
                          "pairs, Rm=3 nm, Rbin=1500, nbin=1 (cell-binned K3)")
-            self.dram_per_frame = None
-        else:
-            raise SystemExit(f"unknown --config {name}")
-        import refprog
-        self.gi0, self.gi1 = refprog.group_info(self.system, self.g0), refprog.group_info(self.system, self.g1)
-        self.n0 = len(self.gi0["index"]) // self.gi0["napm"]
-        self.n1 = len(self.gi1["index"]) // self.gi1["napm"]
-        self.same = self.g0 == self.g1
-        # the device job: groups to register and the (grp0, grp1) pairs to accumulate
-        if name == "c5":
-            names = ["SOL", "CAT", "ANI", "COS"]
-            self.groups = [refprog.group_info(self.system, n) for n in names]
+            self.F, self.D = 2, 2
+            self.groups = [gi(self.system, n) for n in ("SOL", "CAT", "ANI", "COS")]
             self.pairs = [(a, b) for a in range(4) for b in range(a, 4)]
             self.Rm, self.nbin = 3.0, 1
         else:
-            self.groups = [self.gi0, self.gi1]
-            self.pairs = [(0, 1)]
-            self.Rm, self.nbin = float(np.float32(np.float32(self.L) / np.float32(2))), 5      # calc_rdf_region.cpp:52-57, :23
-        nm = [len(g["index"]) // g["napm"] for g in self.groups]
-        self.pairs_per_frame = float(sum(nm[a] * nm[b] for a, b in self.pairs))                # reference-equivalent ordered pairs
+            raise SystemExit(f"unknown --config {name}")
+        self.natoms = self.system.natoms
+        self.nmol = [len(g["index"]) // g["napm"] for g in self.groups]
+        if self.kind == "rdf":
+            self.Rbin = int(np.float32(self.Rm) / 0.002)                                       # calc_rdf_region.cpp:58
+            self.pairs_per_frame = float(sum(self.nmol[a] * self.nmol[b] for a, b in self.pairs))   # reference-equivalent ordered pairs
+            self.symmetric = 1
+        self.atoms_per_frame = sum(len(g["index"]) for g in self.groups[:1]) if self.kind != "rdf" else None
+
+    # ---- device job ------------------------------------------------------------------------------------------
+    def setup(self, ctx):
+        from gmx2020postanalysis_b200 import lib
+        for g, gi in enumerate(self.groups):
+            ctx.set_group(g, gi["index"], gi["napm"], gi["mass"], gi["charge"])
+        self.accs, self.chk = [], []
+        if self.kind == "rdf":
+            for g0, g1 in self.pairs:
+                a = ctx.rdf_create(grp0=g0, grp1=g1, com0=0, com1=0, nbin=self.nbin, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0,
+                                   up2=100.0, Rm=self.Rm, Rbin=self.Rbin)
+                ctx.rdf_tune(a, self.symmetric, 0)
+                self.accs.append(a)
+            # the independent evaluation the self-check compares with: same spec, full N0 x N1 evaluation, no symmetry, no cells
+            g0, g1 = self.pairs[0]
+            c = ctx.rdf_create(grp0=g0, grp1=g1, com0=0, com1=0, nbin=self.nbin, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0,
+                               up2=100.0, Rm=self.Rm, Rbin=self.Rbin)
+            # (config 3 already runs that kernel -- two different groups, Rm = L/2 -- so there the check re-evaluates EVERY pair in FP64)
+            ctx.rdf_tune(c, 0, 1 if self.name == "c3" else 0)
+            ctx.rdf_cells(c, 0)
+            self.chk = [c]
+        elif self.kind == "density":
+            L = 4.476
+            dbin = float(np.float32(np.float32(L) / np.float32(100)))                         # README.md:127
+            kw = dict(grp=0, com=0, dim=2, low=0.0, up=L, dbin=dbin, nbin=100, upper_inclusive=0, dim2=-1, low2=0.0, up2=0.0)
+            self.accs = [ctx.density_create(**kw)]
+            self.chk = [ctx.density_create(**kw)]
+            ctx.acc_fast(self.chk[0], 0)                                                       # literal FP64 for every molecule
+        elif self.kind == "orient":
+            kw = dict(grp=0, com=0, DIMN=2, low=-1.0, up=100.0, c1=0.0, c2=0.0, dr=100.0, CR=100.0, Cr=0.0, nAngle=90, tp1=1, tp2=2, tp3=3,
+                      DIMNOrient=2, method=1)
+            self.accs = [ctx.orient_create(**kw)]
+            self.chk = [ctx.orient_create(**kw)]
+            ctx.acc_fast(self.chk[0], 0)
+        self.lib = lib
+
+    def step(self, ctx):
+        """One pass of the hot path over the resident batch (nothing cached from a previous step is reused)."""
+        ctx.invalidate()
+        if self.kind == "orient":
+            ctx.centers_device(0, self.lib.COM_DIPOLE)        # the per-molecule dipole vectors, left on the device
+        for a in self.accs:
+            ctx.accumulate(a)
+
+    def read_all(self, ctx, accs=None):
+        out = [ctx.read(a) for a in (self.accs if accs is None else accs)]
+        return [c for c, _ in out], np.sum([st for _, st in out], axis=0)
+
+    def dominant(self):
+        return {"rdf": "k3_rdf", "density": "k2_density", "orient": "k4_orient"}[self.kind]
 
 
-# ------------------------------------------------------------------------------------------------ clocks
+# ================================================================================================ clocks
 class ClockSampler:
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -136,33 +227,40 @@ class ClockSampler:
         if sm:
             busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
             out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
-                       power_w_max=float(max(pw)))
+                       samples_under_load=len(busy), power_w_max=float(max(pw)))
         return out
 
 
-# ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_sample(wl, n_i, tmpdir, x0):
-    """Runs the reference's own calc_rdf_region (oracle/_ref, 1 thread in the pair loop -- the reference has no
-    threading there) on grp0 = the first n_i molecules of group 0 x grp1 = all of group 1, one frame.  Returns
-    (pairs/s, kind, secs)."""
-    import refprog
+# ================================================================================================ CPU baseline
+def _ref_env():
+    return dict(os.environ, LD_LIBRARY_PATH=STUBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="1")
+
+
+def have_ref(prog):
+    return os.path.exists(os.path.join(REFDIR, prog)) and os.path.exists(os.path.join(STUBDIR, "libgmxstub.so"))
+
+
+def _write_inputs(prefix, wl, frames, groups):
     from workloads import trajio
-    system, n1 = wl.system, wl.n1
-    i0, i1 = wl.gi0["index"], wl.gi1["index"]
-    exe = os.path.join(refprog.REFDIR, "calc_rdf_region")
-    if refprog.have_ref("calc_rdf_region"):
+    if not os.path.exists(prefix + ".b2t"):
+        trajio.write_trajectory(prefix + ".b2t", frames, wl.system.box9())
+        trajio.write_topology(prefix + ".b2p", wl.system)
+    trajio.write_index(prefix + ".ndx", groups)
+
+
+def cpu_rdf_sample(wl, n_i, tmpdir, x0, tag="s"):
+    """The reference's own calc_rdf_region (oracle/_ref; its pair loop is single-threaded) on grp0 = the first n_i molecules of
+    group 0 x grp1 = all of group 1, one frame.  Returns (pairs/s, kind, secs)."""
+    g0, g1 = wl.groups[wl.pairs[0][0]], wl.groups[wl.pairs[0][1]]
+    n1 = len(g1["index"]) // g1["napm"]
+    if have_ref("calc_rdf_region"):
         prefix = os.path.join(tmpdir, wl.name)
-        if not os.path.exists(prefix + ".b2t"):
-            trajio.write_trajectory(prefix + ".b2t", x0[None], system.box9())
-            trajio.write_topology(prefix + ".b2p", system)
-        trajio.write_index(prefix + ".ndx", {"G0_sub": i0[:n_i * wl.gi0["napm"]], "G1": i1})
-        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
-                   OMP_NUM_THREADS="1")
-        cmd = [exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", prefix + ".ndx", "-o", prefix + ".xvg"]
+        _write_inputs(prefix, wl, x0[None], {"G0_sub": g0["index"][:n_i * g0["napm"]], "G1": g1["index"]})
+        cmd = [os.path.join(REFDIR, "calc_rdf_region"), "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", prefix + ".ndx", "-o", prefix + tag + ".xvg"]
         if wl.name == "c5":
             cmd += ["-Rm", "3", "-nbin", "1"]
         t = time.perf_counter()
-        r = subprocess.run(cmd, input="0 1\n", capture_output=True, text=True, env=env, cwd=tmpdir)
+        r = subprocess.run(cmd, input="0 1\n", capture_output=True, text=True, env=_ref_env(), cwd=tmpdir)
         dt = time.perf_counter() - t
         if r.returncode != 0:
             raise RuntimeError("reference program failed: " + r.stderr[-500:])
@@ -170,293 +268,547 @@ def cpu_reference_sample(wl, n_i, tmpdir, x0):
     # the reference binary did not travel: time the oracle port instead (single thread)
     from oracle import port
     os.environ["OMP_NUM_THREADS"] = "1"
-    Lbox = port.lbox_from_box9(system.box9())
-    Rm = port.rdf_default_rm(Lbox)
-    p0 = port.load_position_center(x0, wl.gi0["index"][:n_i * wl.gi0["napm"]], wl.gi0["napm"], wl.gi0["w"][0], Lbox)
-    p1 = port.load_position_center(x0, wl.gi1["index"], wl.gi1["napm"], wl.gi1["w"][0], Lbox)
+    Lbox = port.lbox_from_box9(wl.system.box9())
+    p0 = port.load_position_center(x0, g0["index"][:n_i * g0["napm"]], g0["napm"], g0["w"][0], Lbox)
+    p1 = port.load_position_center(x0, g1["index"], g1["napm"], g1["w"][0], Lbox)
     t = time.perf_counter()
-    port.rdf_accum(p0, p1, Lbox, 5, -100.0, 100.0, 0, 2, -100.0, 100.0, Rm, port.rdf_rbin(Rm))
+    port.rdf_accum(p0, p1, Lbox, wl.nbin, -100.0, 100.0, 0, 2, -100.0, 100.0, np.float32(wl.Rm), wl.Rbin)
     dt = time.perf_counter() - t
     return n_i * n1 / dt, "port", dt
 
 
-def cpu_reference_all_cores(wl, n_i, procs, tmpdir, x0):
+def cpu_rdf_all_cores(wl, n_i, procs, tmpdir, x0):
     """The reference has no threading in the pair loop; the most its code can use of a host is one PROCESS per core, each on
-    its own share of the i-molecules (what a user would do by hand with index groups).  Returns aggregate pairs/s, or None
-    where the reference binaries did not travel."""
-    import refprog
+    its own share of the i-molecules.  Returns aggregate pairs/s, or None where the reference binaries did not travel."""
     from workloads import trajio
-    if not refprog.have_ref("calc_rdf_region"):
-        return None
-    system, n1 = wl.system, wl.n1
-    i0, i1, na = wl.gi0["index"], wl.gi1["index"], wl.gi0["napm"]
-    n_i = min(n_i, wl.n0 // procs)
-    exe = os.path.join(refprog.REFDIR, "calc_rdf_region")
+    if not have_ref("calc_rdf_region"):
+        return None, 0
+    g0, g1 = wl.groups[wl.pairs[0][0]], wl.groups[wl.pairs[0][1]]
+    n0, n1, na = len(g0["index"]) // g0["napm"], len(g1["index"]) // g1["napm"], g0["napm"]
+    n_i = min(n_i, n0 // procs)
     prefix = os.path.join(tmpdir, wl.name)
-    if not os.path.exists(prefix + ".b2t"):
-        trajio.write_trajectory(prefix + ".b2t", x0[None], system.box9())
-        trajio.write_topology(prefix + ".b2p", system)
-    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(ROOT, "build") + ":" + os.environ.get("LD_LIBRARY_PATH", ""), OMP_NUM_THREADS="1")
+    _write_inputs(prefix, wl, x0[None], {"G0_sub": g0["index"][:n_i * na], "G1": g1["index"]})
     cmds = []
     for q in range(procs):
         ndx = os.path.join(tmpdir, f"p{q}.ndx")
-        trajio.write_index(ndx, {"G0_sub": i0[q * n_i * na:(q + 1) * n_i * na], "G1": i1})
-        cmds.append([exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", ndx, "-o", os.path.join(tmpdir, f"p{q}.xvg")]
+        trajio.write_index(ndx, {"G0_sub": g0["index"][q * n_i * na:(q + 1) * n_i * na], "G1": g1["index"]})
+        cmds.append([os.path.join(REFDIR, "calc_rdf_region"), "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", ndx, "-o", os.path.join(tmpdir, f"p{q}.xvg")]
                     + (["-Rm", "3", "-nbin", "1"] if wl.name == "c5" else []))
     t = time.perf_counter()
-    ps = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=env, cwd=tmpdir, text=True)
+    ps = [subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=_ref_env(), cwd=tmpdir, text=True)
           for cmd in cmds]
     for pr in ps:
         pr.stdin.write("0 1\n"); pr.stdin.close()
     rcs = [pr.wait() for pr in ps]
     dt = time.perf_counter() - t
     if any(rcs):
-        return None
-    return procs * n_i * n1 / dt
+        return None, 0
+    return procs * n_i * n1 / dt, n_i
+
+
+def cpu_frames_sample(wl, nframes, tmpdir, frames):
+    """Configs 1 and 4: the reference's own program (README template / calc_orient_mof) over `nframes` whole frames, one thread.
+    Returns (frames/s, kind, secs)."""
+    prog, args = (("readme_template", ["-nbin", "100", "-dim", "2", "-low", "0", "-up", "4.476"]) if wl.kind == "density" else
+                  ("calc_orient_mof", ["-NCM", "0", "-dim", "2", "-low", "-1", "-1", "-1", "-up", "100", "100", "100", "-c1", "0", "-c2", "0", "-dr", "100",
+                                       "-CR", "100", "-Cr", "0", "-nA", "90", "-tp1", "1", "-tp2", "2", "-tp3", "3", "-DIMNOrient", "2", "-method", "1"]))
+    if have_ref(prog):
+        prefix = os.path.join(tmpdir, wl.name)
+        _write_inputs(prefix, wl, frames[:nframes], {"SOL": wl.groups[0]["index"]})
+        cmd = [os.path.join(REFDIR, prog), "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", prefix + ".ndx", "-o", prefix + ".xvg"] + args
+        t = time.perf_counter()
+        r = subprocess.run(cmd, input="0\n", capture_output=True, text=True, env=_ref_env(), cwd=tmpdir)
+        dt = time.perf_counter() - t
+        if r.returncode != 0:
+            raise RuntimeError(f"reference program {prog} failed: " + (r.stdout + r.stderr)[-600:])
+        return nframes / dt, "reference", dt
+    from oracle import port
+    os.environ["OMP_NUM_THREADS"] = "1"
+    g = wl.groups[0]
+    Lbox = port.lbox_from_box9(wl.system.box9())
+    t = time.perf_counter()
+    if wl.kind == "density":
+        hist = np.zeros(100, dtype=np.uint64)
+        dbin = float(np.float32(np.float32(4.476) / np.float32(100)))
+        for f in range(nframes):
+            pc = port.load_position_center(frames[f], g["index"], g["napm"], g["w"][0], Lbox)
+            port.density_accum(pc, 2, np.float32(0.0), np.float32(4.476), dbin, 100, hist)
+    else:
+        o = n = None
+        for f in range(nframes):
+            pos = port.load_position(frames[f], g["index"], g["napm"], Lbox)
+            pc = port.load_position_center(frames[f], g["index"], g["napm"], g["w"][0], Lbox)
+            o, n, _ = port.orient_accum(pos, pc, Lbox, 2, np.float32(-1.0), np.float32(100.0), np.float32(0.0), np.float32(0.0), np.float32(100.0),
+                                        np.float32(100.0), np.float32(0.0), 90, 1, 2, 3, 2, 1, o, n)
+    dt = time.perf_counter() - t
+    return nframes / dt, "port", dt
+
+
+def cpu_baseline(wl, tmpdir, frames, rdf_sample):
+    if wl.kind == "rdf":
+        n1 = wl.nmol[wl.pairs[0][1]]
+        n_i = max(1, min(rdf_sample, wl.nmol[wl.pairs[0][0]], int(6.0e8 // n1)))              # ~10 s of one core
+        rate, kind, dt = cpu_rdf_sample(wl, n_i, tmpdir, frames[0], "cb")
+        return {"value": rate, "unit": "pair-distances/s", "cores": 1, "kind": kind,
+                "sample": f"{n_i} of {wl.nmol[wl.pairs[0][0]]} i-molecules x all {n1} j-molecules of one frame ({dt:.1f} s, whole-process wall time)"
+                          + (", dominant group pair SOL-SOL" if wl.name == "c5" else ""),
+                "host_cpus": os.cpu_count(), "frames_per_s": rate / wl.pairs_per_frame}
+    n = min(len(frames), 100 if wl.kind == "density" else 8)
+    rate, kind, dt = cpu_frames_sample(wl, n, tmpdir, frames)
+    return {"value": rate, "unit": "frames/s", "cores": 1, "kind": kind,
+            "sample": f"{n} whole frames ({dt:.2f} s, whole-process wall time incl. start-up and reading the frames)", "host_cpus": os.cpu_count(),
+            "frames_per_s": rate}
 
 
 def run_reference_arm(args):
-    """--impl reference: same metric/config/unit, each step a bounded sample (n_i oxygens x all) of the workload."""
+    """--impl reference: same metric / config / unit, each step a bounded sample of the workload, on the host's cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    os.environ["B2A_SYNTH_NUMPY"] = "1"           # pure-numpy frame generator: this arm maps no library built from this repo's product
     wl = Workload(args.config)
-    system = wl.system
-    x0 = system.frame(0)
-    n_i = max(1, min(args.ref_sample, wl.n0, int(7.2e7 // wl.n1)))      # ~1-2 s of one core per step
+    x0 = wl.system.frames(0, 1)
     rates, kind = [], "reference"
     with tempfile.TemporaryDirectory() as td:
-        for s in range(args.warmup + args.steps):
-            rate, kind, dt = cpu_reference_sample(wl, n_i, td, x0)
-            if s >= args.warmup:
-                rates.append((rate, dt))
-        procs = os.cpu_count() or 1
-        all_cores = cpu_reference_all_cores(wl, n_i, procs, td, x0) if kind == "reference" else None
-    tot_pairs = sum(r * d for r, d in rates)
-    tot_s = sum(d for _, d in rates)
-    value = tot_pairs / tot_s
+        if wl.kind == "rdf":
+            n0, n1 = wl.nmol[wl.pairs[0][0]], wl.nmol[wl.pairs[0][1]]
+            n_i = max(1, min(args.ref_sample, n0, int(7.2e7 // n1)))                           # ~1-2 s of one core per step
+            for s in range(args.warmup + args.steps):
+                rate, kind, dt = cpu_rdf_sample(wl, n_i, td, x0[0])
+                if s >= args.warmup:
+                    rates.append((rate * dt, dt))
+            procs = os.cpu_count() or 1
+            all_cores, n_each = cpu_rdf_all_cores(wl, n_i, procs, td, x0[0]) if kind == "reference" else (None, 0)
+            sample = f"{n_i} of {n0} i-molecules x all {n1} j-molecules of frame 0 per step"
+            unit, per_frame = "pair-distances/s", wl.pairs_per_frame
+            metric = "rdf_pair_distances_per_s"
+        else:
+            nfr = 100 if wl.kind == "density" else 4
+            fr = wl.system.frames(0, nfr)
+            for s in range(args.warmup + args.steps):
+                rate, kind, dt = cpu_frames_sample(wl, nfr, td, fr)
+                if s >= args.warmup:
+                    rates.append((rate * dt, dt))
+            all_cores, sample, unit, per_frame, metric = None, f"{nfr} whole frames per step", "frames/s", 1.0, "frames_per_s"
+    tot_units, tot_s = sum(u for u, _ in rates), sum(d for _, d in rates)
+    value = tot_units / tot_s
     line = {
-        "impl": "reference", "metric": "rdf_pair_distances_per_s", "value": value, "unit": "pair-distances/s",
+        "impl": "reference", "metric": metric, "value": value, "unit": unit,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_s / len(rates),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "frames_per_s": value / wl.pairs_per_frame,
-        "config": {"workload": wl.text, "sample": f"{n_i} of {wl.n0} i-molecules x all {wl.n1} j-molecules of frame 0 per step"},
-        "cpu_baseline": {"value": value, "unit": "pair-distances/s", "cores": 1, "kind": kind,
-                         "sample": f"{n_i} x {wl.n1} ordered pairs per step, {len(rates)} steps, whole-process wall time "
-                                   "(includes reading the frame)", "host_cpus": os.cpu_count()},
-        "e2e": {"value": value, "unit": "pair-distances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "frames_per_s": value / per_frame,
+        "config": {"workload": wl.text, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": 1, "kind": kind,
+                         "sample": f"{sample}, {len(rates)} steps, whole-process wall time (includes reading the frame)", "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     if all_cores:
         # not the reference's own mode of operation (its frame loop is single-threaded): reported beside `value`, never instead
-        line["cpu_all_cores"] = {"value": all_cores, "unit": "pair-distances/s", "processes": procs,
-                                 "sample": f"{procs} concurrent reference processes, {min(n_i, wl.n0 // procs)} x {wl.n1} ordered pairs each, wall time of the slowest"}
+        line["cpu_all_cores"] = {"value": all_cores, "unit": unit, "processes": procs,
+                                 "sample": f"{procs} concurrent reference processes, {n_each} x {n1} ordered pairs each, wall time of the slowest"}
     print(json.dumps(line))
     return 0
 
 
-# ------------------------------------------------------------------------------------------------ B200 arm
+# ================================================================================================ B200 arm
+class Dist:
+    """torch.distributed plumbing of the bench: barriers, max / sum over ranks.  The path's own collective is NOT here (libb2a)."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.cpu_group = None
+        if self.world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.cpu_group = dist.new_group(backend="gloo")        # host-side waits that must not spin on a GPU
+
+    def barrier(self, ctx=None):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.local)
+        if ctx is not None:
+            ctx.sync()
+
+    def cpu_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
+
+    def reduce(self, vals, op):
+        if self.world == 1:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=f"cuda:{self.local}")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(v) for v in t]
+
+    def gather_u64(self, arr):
+        """Every rank's array on rank 0 (a channel independent of libb2a's communicator)."""
+        if self.world == 1:
+            return [arr]
+        t = self.torch.from_numpy(np.ascontiguousarray(arr).view(np.int64).copy()).to(f"cuda:{self.local}")
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.cpu().numpy().view(np.uint64) for o in out]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def measure(wl, D, steps, warmup, with_cpu, rdf_sample, flush):
+    """Runs one workload through the whole measurement; returns the dict the line (or its other_configs entry) is built from."""
+    torch = D.torch
+    from gmx2020postanalysis_b200 import dist as b2d, lib
+    rank, world, local = D.rank, D.world, D.local
+    F, nb = wl.F, wl.D
+    # rank-private, distinct frames in pinned host memory (contiguous frame blocks per rank)
+    batches = []
+    t_gen = time.perf_counter()
+    for d in range(nb):
+        xh = lib.pinned_empty((F, wl.natoms, 3), np.float32)
+        wl.system.frames((rank * nb + d) * F, F, out=xh)
+        batches.append(xh)
+    t_gen = time.perf_counter() - t_gen
+    box = wl.system.box9()
+    ctx = lib.Context(wl.natoms, F, device=local)
+    joined = b2d.comm_init(ctx, device=f"cuda:{local}")       # ncclCommInitRank inside libb2a (id broadcast by torch.distributed)
+    wl.setup(ctx)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
+    pos = {"next": 0, "cur": -1}
+
+    def feed():
+        ctx.submit(batches[pos["next"]], box)
+        pos["cur"] = pos["next"]
+        pos["next"] = (pos["next"] + 1) % nb
+
+    def reset_all():
+        for a in wl.accs + wl.chk:
+            ctx.reset(a)
+
+    # ---- phase 1: device-resident, CUDA events around each step ------------------------------------------------
+    feed()
+    ctx.sync()
+    for _ in range(warmup):
+        wl.step(ctx)
+        feed()
+    ctx.sync()
+    reset_all()
+    ctx.timing_enable(True)
+    ctx.timing_read()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    used = []
+    sampler = ClockSampler(local)
+    sampler.start()
+    D.barrier(ctx)
+    t_wall = time.perf_counter()
+    for s in range(steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()                        # L2 flush between timed iterations (outside the event pair)
+        ev[s][0].record(stream)
+        wl.step(ctx)
+        ev[s][1].record(stream)
+        used.append(pos["cur"])
+        feed()                                   # next step's frames: the upload overlaps this step's kernels (copy stream)
+    D.barrier(ctx)
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    tot_ms = float(sum(a.elapsed_time(b) for a, b in ev))
+    timing = ctx.timing_read()
+    ctx.timing_enable(False)
+    priv_counts, priv_stats = wl.read_all(ctx)                 # this rank's private histograms after the timed steps
+    evaluated_pairs = float(priv_stats[lib.STAT_PAIRS])
+
+    # ---- the path's one collective: merge the rank-private histograms inside libb2a ------------------------------
+    t0 = time.perf_counter()
+    ctx.finalize()
+    ctx.sync()
+    allreduce_ms = 1e3 * (time.perf_counter() - t0)
+    merged_counts, merged_stats = wl.read_all(ctx)
+    mstats = merged_stats.copy()
+    mstats[lib.STAT_FRAMES] = mstats[lib.STAT_FRAMES] // len(wl.accs)      # every accumulator saw every frame
+
+    # ---- self-check ------------------------------------------------------------------------------------------------
+    check = {"frames_merged": int(mstats[lib.STAT_FRAMES]), "counted_merged": int(sum(int(c.sum()) for c in merged_counts)),
+             "fp64_reevaluated": int(mstats[lib.STAT_EXACT]), "dropped_oob": int(mstats[lib.STAT_DROPPED])}
+    problems = []
+    # (a) every timed step against an independent evaluation of the same frames (batch by batch, weighted by how often a batch was used)
+    uses = np.bincount(np.asarray(used, dtype=np.int64), minlength=nb)
+    check_batches = [b for b in range(nb) if uses[b]] if wl.name != "c5" else []
+    if check_batches:
+        expect = np.zeros_like(priv_counts[0])
+        for b in check_batches:
+            ctx.submit(batches[b], box)
+            ctx.reset(wl.chk[0])
+            ctx.accumulate(wl.chk[0])
+            hb, _ = ctx.read(wl.chk[0])
+            expect += hb * np.uint64(uses[b])
+        if not np.array_equal(expect, priv_counts[0]):
+            problems.append("timed histogram differs from the independent evaluation of the same frames")
+        check["independent"] = {"rdf": "every pair re-evaluated in FP64" if wl.name == "c3" else "full N0 x N1 kernel (no symmetry, no cells)", "density": "literal FP64 kernel",
+                                "orient": "literal FP64 kernel"}[wl.kind] + f", {len(check_batches)} batches x {F} frames"
+    elif wl.name == "c5":
+        # 4M atoms: one frame of the dominant pair, cell-binned + symmetric (production) against brute force (about a second)
+        ctx.submit(batches[0][:1], box)
+        for a in (wl.accs[0], wl.chk[0]):
+            ctx.reset(a)
+            ctx.accumulate(a)
+        h_prod, h_brute = ctx.read(wl.accs[0])[0], ctx.read(wl.chk[0])[0]
+        if not np.array_equal(h_prod, h_brute):
+            problems.append("cell-binned histogram differs from brute force")
+        check["independent"] = "brute-force N0 x N1 kernel on one frame of the dominant pair (SOL-SOL)"
+    # (b) the merge: libb2a's all-reduce against the sum of the private histograms gathered over an independent channel
+    if world > 1:
+        flat = np.concatenate([c.ravel() for c in priv_counts] + [priv_stats[[lib.STAT_FRAMES, lib.STAT_PAIRS, lib.STAT_EXACT]]])
+        parts = D.gather_u64(flat)
+        total = np.sum(parts, axis=0)
+        mflat = np.concatenate([c.ravel() for c in merged_counts] + [merged_stats[[lib.STAT_FRAMES, lib.STAT_PAIRS, lib.STAT_EXACT]]])
+        if not np.array_equal(total, mflat):
+            problems.append("merged histogram is not the integer sum of the rank-private ones")
+        check["merge"] = f"ncclAllReduce inside libb2a == sum of {world} private histograms (torch all_gather)"
+    if int(mstats[lib.STAT_FRAMES]) != world * steps * F:
+        problems.append(f"frames_merged {int(mstats[lib.STAT_FRAMES])} != {world * steps * F}")
+    bad = D.reduce([len(problems)], "sum")[0]
+    check["parity"] = "ok" if bad == 0 else ("FAILED: " + "; ".join(problems) if problems else "FAILED on another rank")
+
+    # ---- phase 2: end to end through the C ABI with host buffers ---------------------------------------------------
+    reset_all()
+    e2e_steps = steps
+    pos["next"] = 0
+    feed()
+    for _ in range(2):
+        wl.step(ctx)
+        feed()
+        wl.read_all(ctx)
+    reset_all()
+    D.barrier(ctx)
+    t0 = time.perf_counter()
+    # every step uploads its own frames from pinned memory and reads its own result back; the upload of step s+1 is queued
+    # (double-buffered, on the copy stream) before the host blocks on the result of step s, so it overlaps the kernels of s.
+    # (the first upload of this loop happened just above: the resident batch is consumed by step 0)
+    for s in range(e2e_steps):
+        wl.step(ctx)
+        feed()                                   # H2D of step s+1 from the next pinned batch
+        wl.read_all(ctx)                         # D2H of step s's results (u64 histograms + stats)
+    D.barrier(ctx)
+    e2e_s = time.perf_counter() - t0
+    h2d = F * wl.natoms * 12 + F * 36 + F * 208
+    d2h = sum((ctx.acc_size(a) + lib.STAT_NSLOTS) * 8 for a in wl.accs)
+
+    tot_ms_max, e2e_s_max = D.reduce([tot_ms, e2e_s], "max")
+    evaluated_all = D.reduce([evaluated_pairs], "sum")[0]
+    res = {"wl": wl, "F": F, "steps": steps, "tot_ms": tot_ms, "tot_ms_max": tot_ms_max, "e2e_s_max": e2e_s_max, "timing": timing, "clocks": clocks,
+           "evaluated_pairs": evaluated_pairs, "evaluated_all": evaluated_all, "allreduce_ms": allreduce_ms, "check": check, "h2d": h2d, "d2h": d2h,
+           "gen_s": t_gen, "wall_s": t_wall, "nccl_in_libb2a": bool(joined), "cpu_baseline": None}
+    if with_cpu and rank == 0 and world == 1:
+        with tempfile.TemporaryDirectory() as td:
+            res["cpu_baseline"] = cpu_baseline(wl, td, batches[0], rdf_sample)
+    ctx.close()
+    for xh in batches:
+        lib.pinned_free(xh)
+    return res
+
+
+def roofline_of(res, world):
+    wl, timing, clocks = res["wl"], res["timing"], res["clocks"]
+    kname = wl.dominant()
+    k_ms, k_n = timing[kname]
+    share = k_ms / res["tot_ms"] if res["tot_ms"] else None
+    if wl.kind == "rdf":
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        peak = 148 * 128 * sm_mhz * 1e6                          # FP32 issue ceiling at the SM clock seen in this run
+        pairs_per_launch = res["evaluated_pairs"] / max(k_n, 1)
+        ach = pairs_per_launch * ISSUE_SLOTS_PER_PAIR / (k_ms / max(k_n, 1) * 1e-3) if k_ms > 0 else 0.0
+        rf = {"bound": "fp32_issue", "kernel": kname, "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "Tinst/s",
+              "frac": ach / peak if peak else None,
+              "traffic": K3_NCU["dram_bytes_per_frame"] * res["F"] if wl.name == "c2" else None,
+              "traffic_unit": f"bytes per k3_rdf launch (ncu, {K3_NCU['source']})",
+              "how": f"evaluated pairs per launch x {ISSUE_SLOTS_PER_PAIR} issue slots (BASELINE.md section 4) / mean CUDA-event duration of the "
+                     "k3_rdf launches inside the timed region; peak = 148 SM x 128 lanes x SM clock sampled by nvidia-smi during the timed region. "
+                     "`frac` is this MODEL fraction; `issue_active` and `inst_per_pair` are what ncu measured on the same kernel",
+              "kernel_ms_per_launch": k_ms / max(k_n, 1), "share_of_step": share}
+        if wl.name == "c2":
+            rf.update(issue_active=K3_NCU["issue_active"], inst_per_pair=K3_NCU["inst_per_pair"], ncu_source=K3_NCU["source"])
+        return rf
+    peak, prov = hbm_peak()
+    bytes_per_launch = 12.0 * wl.atoms_per_frame * res["F"]      # one rvec per atom-frame; the histogram stays on chip
+    ach = bytes_per_launch / (k_ms / max(k_n, 1) * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": prov,
+            "traffic": None, "how": "12 B per atom-frame x atoms x frames of one launch / mean CUDA-event duration of that kernel's launches",
+            "kernel_ms_per_launch": k_ms / max(k_n, 1), "share_of_step": share,
+            "note": ("the whole batch is %.1f MB: launch-latency-bound, not bandwidth-bound" % (bytes_per_launch / 1e6)) if bytes_per_launch < 64e6 else None}
+
+
+def entry_of(res, world):
+    """other_configs entry (also the basis of the headline line)."""
+    wl, steps, F = res["wl"], res["steps"], res["F"]
+    frames = world * steps * F
+    fps = frames / (res["tot_ms_max"] * 1e-3)
+    fps_e2e = frames / res["e2e_s_max"]
+    timing = res["timing"]
+    e = {"workload": wl.text, "frames_per_step_per_gpu": F, "steps": steps, "ms_per_step": res["tot_ms_max"] / steps, "frames_per_s": fps,
+         "e2e": {"frames_per_s": fps_e2e, "ms_per_step": 1e3 * res["e2e_s_max"] / steps, "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"]},
+         "roofline": roofline_of(res, world),
+         "kernel_ms_per_step": {k: t / max(steps, 1) for k, (t, n) in timing.items() if n},
+         "check": res["check"], "allreduce_ms": res["allreduce_ms"]}
+    if wl.kind == "rdf":
+        e["pair_distances_per_s"] = fps * wl.pairs_per_frame
+        e["evaluated_pairs_per_s"] = res["evaluated_all"] / (res["tot_ms_max"] * 1e-3)
+        e["e2e"]["pair_distances_per_s"] = fps_e2e * wl.pairs_per_frame
+        e["group_pairs"] = len(wl.accs)
+    else:
+        e["atom_frames_per_s"] = fps * wl.atoms_per_frame
+    if res["cpu_baseline"]:
+        e["cpu_baseline"] = res["cpu_baseline"]
+    return e
+
+
+def host_cpp_block(D, seconds_budget=40.0):
+    """The same workload driven by ONE C++ process through the drop-in handle: build/dropin/calc_rdf_region_fused on a config-2
+    trajectory file, with 1 device and (N > 1) with B2A_DEVICES = 0..N-1 -- batches dealt to the devices by libb2a, histograms
+    merged by b2a_finalize.  Rank 0 runs it while the other ranks wait on the host (their GPUs idle)."""
+    exe = os.path.join(DROPIN, "calc_rdf_region_fused")
+    out = None
+    D.barrier()                                   # every rank's device work is finished; from here the others wait on the host
+    if D.rank == 0 and os.path.exists(exe) and os.path.exists(os.path.join(STUBDIR, "libgmxstub.so")):
+        from workloads import trajio
+        wl = Workload("c2")
+        base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (2 << 30) else None
+        td = tempfile.mkdtemp(prefix="b2a_cpp_", dir=base)
+        try:
+            nfile = 64
+            prefix = os.path.join(td, "c2")
+            trajio.write_trajectory(prefix + ".b2t", wl.system.frames(7000, nfile), wl.system.box9())
+            trajio.write_topology(prefix + ".b2p", wl.system)
+            trajio.write_index(prefix + ".ndx", {"OW": wl.groups[0]["index"]})
+            env = dict(os.environ, LD_LIBRARY_PATH=STUBDIR + ":" + os.path.join(ROOT, "gmx2020postanalysis_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+                env.pop(k, None)
+            out = {"program": "build/dropin/calc_rdf_region_fused (one process, itp::GmxHandle + libb2a)", "trajectory": f"{nfile} distinct frames replayed (raw float format)"}
+            outputs = {}
+            for ndev in sorted({1, D.world}):
+                rep = 8 * ndev                                   # 512 frames per device
+                e2 = dict(env, B2A_BATCH="32", GMXSTUB_REPEAT=str(rep), B2A_DEVICES=",".join(str(d) for d in range(ndev)))
+                t = time.perf_counter()
+                r = subprocess.run([exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", prefix + ".ndx", "-o", prefix + f".{ndev}.xvg"], input="0 0\n",
+                                   capture_output=True, text=True, env=e2, cwd=td, timeout=600)
+                wall = time.perf_counter() - t
+                if r.returncode != 0:
+                    out[f"error_{ndev}"] = (r.stdout + r.stderr)[-400:]
+                    continue
+                loop = [ln for ln in r.stdout.splitlines() if ln.startswith("frame loop")]
+                fps = float(loop[-1].split("=")[1].split()[0]) if loop else None
+                out[f"frames_per_s_{ndev}gpu"] = fps
+                out[f"frames_{ndev}gpu"] = rep * nfile
+                out[f"wall_s_{ndev}gpu"] = wall
+                outputs[ndev] = (rep, [ln for ln in open(prefix + f".{ndev}.xvg") if not ln.startswith("# ")])
+            if len(outputs) == 2:
+                # g(r) is normalised by its own tail mean, so replaying the file more often leaves every printed digit unchanged
+                out["output_identical_1_vs_n"] = outputs[1][1] == outputs[D.world][1]
+                if out.get("frames_per_s_1gpu") and out.get(f"frames_per_s_{D.world}gpu"):
+                    out["speedup"] = out[f"frames_per_s_{D.world}gpu"] / out["frames_per_s_1gpu"]
+        except Exception as ex:                                   # the block is informative; it must not take the bench line down
+            out = {"error": repr(ex)[:300]}
+        finally:
+            shutil.rmtree(td, ignore_errors=True)
+    D.cpu_barrier()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2a", choices=["b2a", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--frames-per-step", type=int, default=0, help="override the workload's batch size")
     ap.add_argument("--ref-sample", type=int, default=1000, help="i-molecules per reference step (~2 s of one core)")
-    ap.add_argument("--cpu-sample", type=int, default=8000, help="i-molecules of the cpu_baseline leg (~15 s of one core)")
+    ap.add_argument("--cpu-sample", type=int, default=8000, help="i-molecules of the cpu_baseline leg (~10 s of one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs block")
+    ap.add_argument("--no-host-cpp", action="store_true", help="skip the one-process C++ run")
+    ap.add_argument("--other-steps", type=int, default=5)
     ap.add_argument("--symmetric", type=int, default=1)
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c5"],
-                    help="c2 = headline (BASELINE configs[1]); c3 = configs[2]; c5 = configs[4] (use --frames-per-step 2)")
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="c2 = headline (BASELINE configs[1]); c1, c3, c4, c5 = configs[0], [2], [3], [4]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
 
-    import torch
-    import torch.distributed as dist
-    from gmx2020postanalysis_b200 import dist as b2d, lib
-    from workloads import synth
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    F = args.frames_per_step
+    D = Dist()
+    torch = D.torch
+    from gmx2020postanalysis_b200 import lib
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{D.local}")   # > 126 MB L2
     wl = Workload(args.config)
-    system, LBOX = wl.system, wl.L
-    natoms = system.natoms
-    # rank-private, distinct frames in pinned host memory (frames shard contiguously across ranks)
-    xh = torch.empty((F, natoms, 3), dtype=torch.float32).pin_memory()
-    system.frames(rank * F, F, out=xh.numpy())
-    xh2 = torch.empty((F, natoms, 3), dtype=torch.float32).pin_memory()      # second host buffer of the end-to-end loop
-    xh2.copy_(xh)
-    box = system.box9()
+    if args.frames_per_step:
+        wl.F = args.frames_per_step
+    if wl.kind == "rdf":
+        wl.symmetric = args.symmetric
+    res = measure(wl, D, args.steps, args.warmup, not args.no_cpu_baseline, args.cpu_sample, flush)
+    head = entry_of(res, D.world)
+    others = {}
+    if not args.no_others:
+        for name in ("c1", "c3", "c4", "c5"):
+            if name == args.config:
+                continue
+            t0 = time.perf_counter()
+            try:
+                o = Workload(name)
+                r = measure(o, D, max(1, min(args.other_steps, 3 if name == "c5" else args.other_steps)), 3, not args.no_cpu_baseline, args.cpu_sample, flush)
+                others[name] = entry_of(r, D.world)
+                others[name]["bench_seconds"] = time.perf_counter() - t0
+            except Exception as ex:
+                if D.world > 1:
+                    raise                                         # a rank that drops out would hang the others: fail loudly
+                others[name] = {"error": repr(ex)[:300]}
+    cpp = None if args.no_host_cpp else host_cpp_block(D)
 
-    ctx = lib.Context(natoms, F, device=local)
-    for g, gi in enumerate(wl.groups):
-        ctx.set_group(g, gi["index"], gi["napm"], gi["mass"], gi["charge"])
-    Rm = wl.Rm
-    Rbin = int(np.float32(Rm) / 0.002)                              # :58
-    nbin = wl.nbin
-    accs = []
-    for g0, g1 in wl.pairs:
-        a_ = ctx.rdf_create(grp0=g0, grp1=g1, com0=0, com1=0, nbin=nbin, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0,
-                            up2=100.0, Rm=Rm, Rbin=Rbin)
-        ctx.rdf_tune(a_, args.symmetric, 0)
-        accs.append(a_)
-    ncounters = nbin * Rbin
-
-    def accumulate_all():
-        for a_ in accs:
-            ctx.accumulate(a_)
-
-    def read_all():
-        out = [ctx.read(a_, ncounters) for a_ in accs]
-        return sum(int(c.sum()) for c, _ in out), np.sum([st for _, st in out], axis=0)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=local)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")   # > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(local)
-        ctx.sync()
-
-    pairs_step = float(F) * wl.pairs_per_frame   # reference-equivalent ordered pairs per rank per step
-
-    # ---- phase 1: device-resident ------------------------------------------------------------------------
-    ctx.submit(xh.numpy(), box)
-    ctx.sync()
-    for _ in range(args.warmup):
-        ctx.invalidate()
-        accumulate_all()
-    ctx.sync()
-    for a_ in accs:
-        ctx.reset(a_)
-    ctx.timing_enable(True)
-    ctx.timing_read()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    sampler.start()
-    barrier()
-    t_wall = time.perf_counter()
-    for s in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()                        # L2 flush between timed iterations (outside the event pair)
-        ev[s][0].record(stream)
-        ctx.invalidate()
-        accumulate_all()
-        ev[s][1].record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    tot_ms = float(sum(step_ms))
-    timing = ctx.timing_read()
-    ctx.timing_enable(False)
-    _, stats_dev = read_all()
-    evaluated_pairs = float(stats_dev[lib.STAT_PAIRS])           # physically evaluated by this rank over the timed steps
-
-    # ---- phase 2: end to end through the C ABI with host buffers -------------------------------------------
-    def reset_all():
-        for a_ in accs:
-            ctx.reset(a_)
-    reset_all()
-    for _ in range(2):
-        ctx.submit(xh.numpy(), box)
-        accumulate_all()
-        read_all()
-    reset_all()
-    barrier()
-    t0 = time.perf_counter()
-    # every step uploads its own frames from pinned memory and reads its own result back; the upload of step s+1 is queued
-    # (double-buffered, on the copy stream) before the host blocks on the result of step s, so it overlaps the kernels of s
-    ctx.submit(xh.numpy(), box)                  # H2D of step 0
-    for s in range(args.steps):
-        accumulate_all()
-        if s + 1 < args.steps:
-            ctx.submit(xh2.numpy(), box)         # H2D of step s+1 (second pinned buffer: ping-pong, as the drop-in batcher does)
-            xh, xh2 = xh2, xh
-        read_all()                               # D2H of step s's results (u64 histograms + stats)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = F * natoms * 12 + F * 36 + F * 72
-    d2h = sum((ctx.acc_size(a_) + lib.STAT_NSLOTS) * 8 for a_ in accs)
-
-    # ---- the single collective: merge rank-private histograms ------------------------------------------------
-    t0 = time.perf_counter()
-    for a_ in accs:
-        b2d.allreduce_accumulator(ctx, a_)
-    allreduce_ms = 1e3 * (time.perf_counter() - t0)
-    merged_sum, mstats = read_all()
-    mstats[lib.STAT_FRAMES] = mstats[lib.STAT_FRAMES] // len(accs)          # every accumulator saw every frame
-
-    # ---- max over ranks -----------------------------------------------------------------------------------------
-    red = torch.tensor([tot_ms, e2e_s, evaluated_pairs], dtype=torch.float64, device=f"cuda:{local}")
-    if world > 1:
-        mx = red.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = red.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        tot_ms_max, e2e_s_max, evaluated_all = float(mx[0]), float(mx[1]), float(sm[2])
-    else:
-        tot_ms_max, e2e_s_max, evaluated_all = tot_ms, e2e_s, evaluated_pairs
-
-    if rank == 0:
-        value = world * args.steps * pairs_step / (tot_ms_max * 1e-3)
-        e2e_value = world * args.steps * pairs_step / e2e_s_max
-        k3_ms, k3_n = timing["k3_rdf"]
-        k1_ms, k1_n = timing["k1_centers"]
-        prep_ms, prep_n = timing["k3_prep"]
-        sm_mhz = clocks.get("sm_mhz") or 1965.0
-        peak_inst = 148 * 128 * sm_mhz * 1e6                        # FP32 issue ceiling at the SM clock seen in this run
-        k3_pairs_per_launch = evaluated_pairs / max(k3_n, 1)
-        achieved_inst = k3_pairs_per_launch * ISSUE_SLOTS_PER_PAIR / (k3_ms / max(k3_n, 1) * 1e-3) if k3_ms > 0 else 0.0
+    if D.rank == 0:
+        clocks, timing = res["clocks"], res["timing"]
+        rdf = wl.kind == "rdf"
+        per_frame = wl.pairs_per_frame if rdf else 1.0
+        launches = int(sum(n for k, (t, n) in timing.items() if k not in ("h2d", "k3_prep")) + 2 * timing["k3_prep"][1] + args.steps * (1 + len(wl.accs)))
         line = {
-            "metric": "rdf_pair_distances_per_s", "value": value, "unit": "pair-distances/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "frames_per_s": value / wl.pairs_per_frame,
-            "evaluated_pairs_per_s": evaluated_all / (tot_ms_max * 1e-3),
-            "config": {"workload": wl.text, "frames_per_step_per_gpu": F, "parallelism": f"frame-sharded x{world}",
-                       "l2": "flushed between timed steps (256 MiB write)", "symmetric_i_lt_j": bool(args.symmetric) and wl.same, "group_pairs": len(accs),
+            "metric": "rdf_pair_distances_per_s" if rdf else "frames_per_s", "value": head["frames_per_s"] * per_frame,
+            "unit": "pair-distances/s" if rdf else "frames/s", "n_gpus": D.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic", "ingest_parity": "unpinned",
+            "frames_per_s": head["frames_per_s"], "frames_timed": D.world * args.steps * wl.F,
+            "config": {"workload": wl.text, "frames_per_step_per_gpu": wl.F, "distinct_batches_per_gpu": wl.D,
+                       "parallelism": f"frame-sharded x{D.world}", "l2": "flushed between timed steps (256 MiB write)",
+                       "frames": "every step consumes the next of the distinct pinned batches (distinct synthetic frames per rank and batch)",
                        "pairs": "value counts reference-equivalent ordered pairs (N0*N1 per frame); roofline counts only evaluated pairs"},
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"), "reasons": clocks.get("reasons", []),
-                       "samples": clocks.get("samples"), "power_w_max": clocks.get("power_w_max")},
-            "e2e": {"value": e2e_value, "unit": "pair-distances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "frames_per_s": e2e_value / wl.pairs_per_frame, "ms_per_step": 1e3 * e2e_s_max / args.steps},
-            "gpu_launches": int(sum(n for k, (t, n) in timing.items() if k in ("k1_centers", "k3_rdf")) + 2 * prep_n + args.steps),
-            "roofline": {"bound": "fp32_issue", "kernel": "k3_rdf", "achieved": achieved_inst / 1e12, "peak": peak_inst / 1e12,
-                         "unit": "Tinst/s", "frac": achieved_inst / peak_inst if peak_inst else None,
-                         "traffic": wl.dram_per_frame * F if wl.dram_per_frame else None, "traffic_unit": "bytes per k3_rdf launch (ncu, profiles/r01_k3_ncu.md)",
-                         "how": f"evaluated pairs per launch x {ISSUE_SLOTS_PER_PAIR} issue slots (BASELINE.md section 4) / mean CUDA-event "
-                                "duration of the k3_rdf launches inside the timed region; peak = 148 SM x 128 lanes x SM clock "
-                                "sampled by nvidia-smi during the timed region",
-                         "kernel_ms_per_launch": k3_ms / max(k3_n, 1), "share_of_step": k3_ms / tot_ms if tot_ms else None},
-            "kernel_ms": {"k1_centers": k1_ms / max(args.steps, 1), "k3_prep": prep_ms / max(args.steps, 1),
-                          "k3_rdf": k3_ms / max(args.steps, 1)},
-            "allreduce_ms": allreduce_ms,
-            "check": {"counted_pairs_merged": int(merged_sum), "fp64_reevaluated": int(mstats[lib.STAT_EXACT]),
-                      "dropped_oob": int(mstats[lib.STAT_DROPPED]), "frames_merged": int(mstats[lib.STAT_FRAMES])},
+                       "samples": clocks.get("samples"), "samples_under_load": clocks.get("samples_under_load"), "power_w_max": clocks.get("power_w_max")},
+            "e2e": {"value": head["e2e"]["frames_per_s"] * per_frame, "unit": "pair-distances/s" if rdf else "frames/s",
+                    "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"], "frames_per_s": head["e2e"]["frames_per_s"],
+                    "ms_per_step": head["e2e"]["ms_per_step"]},
+            "gpu_launches": launches,
+            "roofline": head["roofline"],
+            "kernel_ms": head["kernel_ms_per_step"],
+            "allreduce_ms": res["allreduce_ms"], "collective": "ncclAllReduce(u64, sum) inside libb2a (b2a_finalize)" if res["nccl_in_libb2a"] else "none (one device)",
+            "check": res["check"],
         }
-        if world == 1 and not args.no_cpu_baseline:
-            with tempfile.TemporaryDirectory() as td:
-                n_cpu = max(1, min(args.cpu_sample, wl.n0, int(6.0e8 // wl.n1)))    # ~10 s of one core
-                rate, kind, dt = cpu_reference_sample(wl, n_cpu, td, xh.numpy()[0])
-            line["cpu_baseline"] = {"value": rate, "unit": "pair-distances/s", "cores": 1, "kind": kind,
-                                    "sample": f"{n_cpu} of {wl.n0} i-molecules x all {wl.n1} j-molecules of one frame "
-                                              f"({dt:.1f} s, whole-process wall time)", "host_cpus": os.cpu_count(),
-                                    "frames_per_s": rate / wl.pairs_per_frame}
+        if rdf:
+            line["evaluated_pairs_per_s"] = head["evaluated_pairs_per_s"]
+            line["config"].update(symmetric_i_lt_j=bool(wl.symmetric) and wl.name in ("c2", "c5"), group_pairs=len(wl.accs))
+        if res["cpu_baseline"]:
+            line["cpu_baseline"] = res["cpu_baseline"]
+        if others:
+            line["other_configs"] = others
+        if cpp:
+            line["host_cpp"] = cpp
         print(json.dumps(line))
-    ctx.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
     return 0
 
 

@@ -146,20 +146,27 @@ def check(rc):
         raise B2AError(rc, load().b2a_last_error().decode())
 
 
-_PINNED_KEEPALIVE = []
+_PINNED = {}
 
 
 def pinned_empty(shape, dtype):
     """numpy array over page-locked host memory (cudaMallocHost through the C ABI) for asynchronous H2D copies.
-    The allocation lives until the process exits."""
+    The allocation lives until pinned_free(array) or the end of the process."""
     L = load()
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = L.b2a_pinned_alloc(max(n, 1))
     if not p:
         raise B2AError(2, L.b2a_last_error().decode())
     buf = (C.c_char * max(n, 1)).from_address(p)
-    _PINNED_KEEPALIVE.append(buf)
+    _PINNED[p] = buf
     return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def pinned_free(arr):
+    """Release an array made by pinned_empty (the caller must not touch it, or any view of it, afterwards)."""
+    p = arr.ctypes.data
+    if _PINNED.pop(p, None) is not None:
+        load().b2a_pinned_free(p)
 
 
 class Context:

@@ -20,6 +20,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <unistd.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 
@@ -495,6 +496,9 @@ struct t_trxstatus
      * buffer), and the batch reader's decode threads fault the pages in themselves.  map == nullptr: FILE* path. */
     const unsigned char* map = nullptr;
     size_t  map_size = 0, mpos = 0;
+    int     repeat  = 1;  /* raw format: GMXSTUB_REPEAT=n replays the file n times (benchmarks: a long trajectory without the disk space) */
+    int     pass    = 0;
+    double  t_first = 0, t_last = 0;
     const unsigned char* cur = nullptr; /* coordinate block of the frame xtc_next() delivered last ... */
     size_t  cur_avail = 0;              /* ... and the readable bytes from there on */
 };
@@ -533,9 +537,18 @@ bool time_selected(t_trxstatus* st, double t, bool* past_end)
 /* Reads the next selected frame header (time, box) into hdr[10]; leaves the file positioned at x. */
 bool next_selected(t_trxstatus* st, float hdr[10])
 {
-    while (st->next < st->nframes)
+    for (;;)
     {
+        if (st->next >= st->nframes)
+        {
+            if (st->pass + 1 >= st->repeat || st->nframes <= 0) return false;
+            st->pass++;                                   /* GMXSTUB_REPEAT: back to the first frame, times keep growing */
+            st->next = 0;
+            std::fseek(st->fp, static_cast<long>(sizeof(TrjHeader)), SEEK_SET);
+        }
         if (std::fread(hdr, sizeof(float), 10, st->fp) != 10) return false;
+        if (st->pass == 0) { if (st->next == 0) st->t_first = hdr[0]; st->t_last = hdr[0]; }
+        else hdr[0] += (float)(st->pass * (st->t_last - st->t_first + (st->nframes > 1 ? (st->t_last - st->t_first) / (st->nframes - 1) : 1.0)));
         bool past = false;
         bool sel  = time_selected(st, hdr[0], &past);
         if (past) return false;
@@ -689,6 +702,7 @@ t_trxstatus* open_trx(const char* fn)
     st->natoms  = h.natoms;
     st->nframes = h.nframes;
     st->fflags  = h.flags;
+    if (const char* e = std::getenv("GMXSTUB_REPEAT")) st->repeat = std::max(1, std::atoi(e));
     return st;
 }
 
@@ -905,20 +919,62 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
         st->want = want;
         return got;
     }
-    const size_t rest = frame_floats(st) - 10 - n3;
-    int          got  = 0;
-    while (got < max_frames)
+    /* raw format: walk the (tiny) frame headers sequentially, then fetch the coordinate blocks of the batch with one pread per
+     * frame on several threads -- a single fread stream tops out near 3 GB/s, below what a few GPUs consume */
+    const int          fd = fileno(st->fp);
+    const off_t        fb = static_cast<off_t>(frame_floats(st) * sizeof(float));
+    std::vector<off_t> at;
+    while ((int)at.size() < max_frames)
     {
-        float hdr[10];
-        if (!next_selected(st, hdr)) break;
-        time_out[got] = hdr[0];
-        std::memcpy(box_out + 9 * static_cast<size_t>(got), hdr + 1, 9 * sizeof(float));
-        read_exact(st->fp, x_out + n3 * got, n3, st->fn.c_str());
-        if (rest) std::fseek(st->fp, static_cast<long>(rest * sizeof(float)), SEEK_CUR);
+        /* the same walk as next_selected(), on file offsets: the buffered FILE* would refill megabytes per 40-byte header */
+        if (st->next >= st->nframes)
+        {
+            if (st->pass + 1 >= st->repeat || st->nframes <= 0) break;
+            st->pass++;
+            st->next = 0;
+        }
+        float       hdr[10];
+        const off_t off = static_cast<off_t>(sizeof(TrjHeader)) + static_cast<off_t>(st->next) * fb;
+        if (pread(fd, hdr, sizeof(hdr), off) != (ssize_t)sizeof(hdr)) break;
+        if (st->pass == 0) { if (st->next == 0) st->t_first = hdr[0]; st->t_last = hdr[0]; }
+        else hdr[0] += (float)(st->pass * (st->t_last - st->t_first + (st->nframes > 1 ? (st->t_last - st->t_first) / (st->nframes - 1) : 1.0)));
+        bool       past = false;
+        const bool sel  = time_selected(st, hdr[0], &past);
+        if (past) break;
+        st->next++;
+        if (!sel) continue;
+        if (!st->have_t0) { st->have_t0 = true; st->t0 = hdr[0]; }
+        const int k = (int)at.size();
+        time_out[k] = hdr[0];
+        std::memcpy(box_out + 9 * static_cast<size_t>(k), hdr + 1, 9 * sizeof(float));
+        at.push_back(off + (off_t)sizeof(hdr));
         st->nread++;
-        ++got;
     }
-    return got;
+    std::fseek(st->fp, static_cast<long>(sizeof(TrjHeader) + static_cast<off_t>(st->next) * fb), SEEK_SET);   /* keep the stream in step */
+    const int n  = (int)at.size();
+    int nthreads = std::min<int>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+    if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(n, std::atoi(e)));
+    std::atomic<int> next{ 0 }, bad{ 0 };
+    auto work = [&]() {
+        for (int k = next++; k < n; k = next++)
+        {
+            char*  dst  = reinterpret_cast<char*>(x_out + n3 * k);
+            size_t left = n3 * sizeof(float);
+            off_t  off  = at[k];
+            while (left)
+            {
+                const ssize_t r = pread(fd, dst, left, off);
+                if (r <= 0) { bad = 1; break; }
+                dst += r; off += r; left -= (size_t)r;
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(work);
+    if (n) work();
+    for (auto& th : pool) th.join();
+    if (bad) gmx_fatal(FARGS, "%s: short read", st->fn.c_str());
+    return n;
 }
 
 /* ---- writers for the real formats (tests, tools) --------------------------------------------------------------- */

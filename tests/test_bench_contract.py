@@ -35,17 +35,38 @@ def test_reference_arm_line(config):
         assert d["cpu_all_cores"]["processes"] == (os.cpu_count() or 1) and d["cpu_all_cores"]["value"] > 0
 
 
+@pytest.mark.parametrize("config", ["c1", "c4"])
+def test_reference_arm_line_frame_configs(config):
+    """Configs 1 and 4 have no pair loop: their reference arm times the README template / calc_orient_mof over whole frames."""
+    d = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--config", config], 600)
+    assert BASE_KEYS <= set(d) and d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] == 1
+
+
 @pytest.mark.gpu
 def test_b200_arm_line():
-    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline"], 900)
-    assert BASE_KEYS | {"roofline", "clocks", "frames_per_s", "evaluated_pairs_per_s"} <= set(d)
+    d = _run(["--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--other-steps", "2"], 1500)
+    assert BASE_KEYS | {"roofline", "clocks", "frames_per_s", "evaluated_pairs_per_s", "check", "other_configs", "ingest_parity"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
-    assert d["value"] > 1e12 and d["gpu_launches"] > 0
+    assert d["value"] > 1e12 and d["gpu_launches"] > 0 and d["ingest_parity"] == "unpinned"
+    F = d["config"]["frames_per_step_per_gpu"]
+    assert F * 20 >= 1000 and d["config"]["distinct_batches_per_gpu"] >= 4       # the default 20 steps cover config 2's 1000 frames
     rf = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"} <= set(rf) and 0.3 < rf["frac"] < 1.0
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "issue_active", "inst_per_pair"} <= set(rf) and 0.3 < rf["frac"] < 1.0
     assert abs(rf["achieved"] / rf["peak"] - rf["frac"]) < 1e-9
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] > 8 * 216000 * 12 - 1 and e["d2h_bytes_per_step"] > 0 and 0.5 * d["value"] < e["value"] <= 1.02 * d["value"]
+    assert e["h2d_bytes_per_step"] > F * 216000 * 12 - 1 and e["d2h_bytes_per_step"] > 0 and 0.5 * d["value"] < e["value"] <= 1.02 * d["value"]
     assert d["clocks"]["sm_mhz"] and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    # the histogram really was filled: 72 000^2 - 72 000 ordered pairs per frame, minus those beyond Rm
-    assert d["check"]["frames_merged"] == 3 * 8 and d["check"]["counted_pairs_merged"] > 0.4 * 3 * 8 * 72000 * 72000
+    # the bench checks itself: the timed histogram equals an independent evaluation of the same frames
+    assert d["check"]["parity"] == "ok" and d["check"]["frames_merged"] == 3 * F
+    assert d["check"]["counted_merged"] > 0.4 * 3 * F * 72000 * 72000
+    oc = d["other_configs"]
+    assert sorted(oc) == ["c1", "c3", "c4", "c5"]
+    for name, o in oc.items():
+        assert "error" not in o, (name, o)
+        assert o["check"]["parity"] == "ok", (name, o["check"])
+        assert o["frames_per_s"] > 0 and o["e2e"]["frames_per_s"] > 0 and 0 < o["roofline"]["frac"] < 1.05, name
+        assert o["roofline"]["bound"] == ("hbm" if name in ("c1", "c4") else "fp32_issue")
+    cpp = d.get("host_cpp")
+    if cpp is not None and "error" not in cpp:
+        assert cpp["frames_per_s_1gpu"] > 100
