@@ -99,6 +99,7 @@ struct Group
     double*  d_cen[4]   = { nullptr, nullptr, nullptr, nullptr };
     int4*    d_fix[4]   = { nullptr, nullptr, nullptr, nullptr };
     uint64_t valid[4]   = { 0, 0, 0, 0 };   // batch serial the cache belongs to
+    uint64_t fix_valid[4] = { 0, 0, 0, 0 }; // ... and the fixed-point copy (written only for consumers that read it: K3 / K5)
 };
 
 // One group's molecules counting-sorted by cell (K3 cell mode), shared by every accumulator of the same batch that needs the
@@ -169,6 +170,7 @@ struct Acc
     unsigned  cap_keysA = 0, cap_keysB = 0;
     int       ipt = 0, threads = 0;   // 0 = auto
     int       fast = 1;               // density / orient: 0 literal FP64, 1 FP32 bracket + FP64 queue, 2 validate
+    int       also_com = -1;          // orient: centre kind the streaming kernel materialises on the side (b2a_acc_also_centers)
     unsigned char* d_lut = nullptr;   // orient: cos cell -> first candidate angle bin
     float2*        d_fmh = nullptr;   // orient: per angle bin {midpoint, shrunk halfwidth} of its cosine interval
     // coord
@@ -226,6 +228,7 @@ struct b2a_ctx
     std::vector<Span> spans;
     double       t_ms[8] = { 0 };
     long long    t_n[8]  = { 0 };
+    unsigned long long* d_dbg = nullptr;   // B2A_STREAM_DEBUG: per-block time stamps of the last streaming launch (8 words x 4096 blocks)
     // ---- multi-GPU (b2a_multi.cuh) ----------------------------------------------------------------------------
     // A context made by b2a_create_multi is a LEADER: it owns one member context per device and no device resources
     // of its own; every entry point forwards (to all members, to the member holding the current batch, or to member 0).
@@ -366,7 +369,7 @@ extern "C" void b2a_destroy(b2a_ctx* c)
     for (auto& a : c->accs) if (a) free_acc(*a);
     for (auto& cs : c->cell_sorts) { cudaFree(cs->keys); cudaFree(cs->cells); cudaFree(cs->sorted); }
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    cudaFree(c->d_pos_scratch); cudaFree(c->d_work);
+    cudaFree(c->d_pos_scratch); cudaFree(c->d_work); cudaFree(c->d_dbg);
     cudaFree(c->d_field[1]); cudaFree(c->d_field[2]); cudaFree(c->d_field_cen);
     for (int b = 0; b < 2; ++b)
     {
@@ -657,20 +660,32 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     a.item_frames = 4;
     if (const char* e = getenv("B2A_ITEM_FRAMES")) a.item_frames = std::max(1, atoi(e));
     a.nitems      = a.mblocks * ((c->nframes + a.item_frames - 1) / a.item_frames);
-    if (!c->d_work) CU(cudaMalloc(&c->d_work, sizeof(unsigned)));
+    if (!c->d_work)
+    {   // {next work item, blocks finished}: the last block of a launch puts both back to zero, so no memset precedes a launch
+        CU(cudaMalloc(&c->d_work, 2 * sizeof(unsigned)));
+        CU(cudaMemsetAsync(c->d_work, 0, 2 * sizeof(unsigned), c->stream));
+    }
     a.work = c->d_work;
+    a.dbg = nullptr;
+    if (getenv("B2A_STREAM_DEBUG"))
+    {
+        if (!c->d_dbg) CU(cudaMalloc(&c->d_dbg, sizeof(unsigned long long) * 8 * 4096));
+        CU(cudaMemsetAsync(c->d_dbg, 0, sizeof(unsigned long long) * 8 * 4096, c->stream));
+        a.dbg = c->d_dbg;
+    }
     a.park_ns = 20000u;
     if (const char* e = getenv("B2A_PARK_NS")) a.park_ns = (unsigned)std::max(0, atoi(e));
     constexpr int NS = stream_stages(MODE, VAR);
     size_t smem = (size_t)NS * a.tile_floats * 4 + NS * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
-    if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut : 0);
+    if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut + sizeof(double) * g.napm : 0);
     auto kern = k_stream<MODE, NAPM_T, VAR>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M + 32, smem));
     if (per_sm < 1) return fail(B2A_ERR_UNSUPPORTED, "streaming kernel does not fit on an SM (%zu bytes of shared memory)", smem);
     const int grid = std::min(a.nitems, per_sm * c->sm_count);
-    CU(cudaMemsetAsync(c->d_work, 0, sizeof(unsigned), c->stream));
+    a.cwait_ns = 0u;
+    if (const char* e = getenv("B2A_CWAIT_NS")) a.cwait_ns = (unsigned)std::max(0, atoi(e));
     kern<<<grid, M + 32, smem, c->stream>>>(a);   // M consumer threads (one molecule each) + one producer warp
     CU(cudaGetLastError());
     return B2A_OK;
@@ -707,35 +722,39 @@ static int ensure_centers(b2a_ctx* c, Group& g, int com, bool need_fix)
     if (com < 0 || com > 3) return fail(B2A_ERR_ARG, "com(%d) must be 0 (mass), 1 (geometry), 2 (charge) or 3 (dipole)", com);
     if (c->nframes <= 0) return fail(B2A_ERR_STATE, "no frame batch submitted yet");
     if (!g.d_cen[com]) CU(cudaMalloc(&g.d_cen[com], sizeof(double) * 3 * (size_t)g.nmol * c->maxK));
-    if (!g.d_fix[com]) CU(cudaMalloc(&g.d_fix[com], sizeof(int4) * (size_t)g.nmol * c->maxK));
-    (void)need_fix;
-    if (g.valid[com] == c->serial) return B2A_OK;
+    if (need_fix && !g.d_fix[com]) CU(cudaMalloc(&g.d_fix[com], sizeof(int4) * (size_t)g.nmol * c->maxK));
+    if (g.valid[com] == c->serial && (!need_fix || g.fix_valid[com] == c->serial)) return B2A_OK;
+    // the int4 fixed-point copy (16 B per molecule on top of the 24 B of the doubles) is written only when a pair kernel will read it
+    int4* const fix = need_fix ? g.d_fix[com] : nullptr;
     Timed tm(c, 0);
     if (g.csr)
     {
         dim3 grid((g.nmol + 127) / 128, c->nframes);
         k1_centers_csr<<<grid, 128, 0, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g.d_index, g.d_off, g.nmol, g.d_wfull[com],
-                                                    g.d_div[com], c->d_geom, g.d_cen[com], g.d_fix[com]);
+                                                    g.d_div[com], c->d_geom, g.d_cen[com], fix);
         CU(cudaGetLastError());
         g.valid[com] = c->serial;
+        if (need_fix) g.fix_valid[com] = c->serial;
         return B2A_OK;
     }
     int   M = 0;
     if (stream_block(g, &M))
     {
         StreamArgs a{};
-        a.cen = g.d_cen[com]; a.fix = g.d_fix[com];
+        a.cen = g.d_cen[com]; a.fix = fix;
         if (int rc = launch_stream<0>(c, g, com, M, a, 0)) return rc;
         g.valid[com] = c->serial;
+        if (need_fix) g.fix_valid[com] = c->serial;
         return B2A_OK;
     }
     const int threads = 128;
     dim3      grid((g.nmol + threads - 1) / threads, c->nframes);
     k1_centers<<<grid, threads, sizeof(double) * g.napm, c->stream>>>(
         c->d_x, (size_t)c->natoms * 3, c->nframes, g.d_index, g.nmol, g.napm, g.d_w[com], make_div(g.wsum[com]), c->d_geom,
-        g.d_cen[com], g.d_fix[com]);
+        g.d_cen[com], fix);
     CU(cudaGetLastError());
     g.valid[com] = c->serial;
+    if (need_fix) g.fix_valid[com] = c->serial;
     return B2A_OK;
 }
 
@@ -1082,6 +1101,17 @@ extern "C" int b2a_acc_fast(b2a_ctx* c, int id, int mode)
     if (a->kind == ACC_RDF) return fail(B2A_ERR_ARG, "accumulator %d is an RDF: use b2a_rdf_tune", id);
     if (mode < 0 || mode > 2) return fail(B2A_ERR_ARG, "b2a_acc_fast: mode must be 0 (FP64 only), 1 (FP32 bracket + FP64 queue) or 2 (validate)");
     a->fast = mode;
+    return B2A_OK;
+}
+
+extern "C" int b2a_acc_also_centers(b2a_ctx* c, int id, int com)
+{
+    TEAM_ALL(c, b2a_acc_also_centers(m, id, com));
+    Acc* a = nullptr;
+    if (int rc = get_acc(c, id, &a)) return rc;
+    if (a->kind != ACC_ORIENT) return fail(B2A_ERR_UNSUPPORTED, "b2a_acc_also_centers: accumulator %d is not an orientation accumulator", id);
+    if (com < -1 || com > 3) return fail(B2A_ERR_ARG, "com(%d) must be -1 (off), 0 (mass), 1 (geometry), 2 (charge) or 3 (dipole)", com);
+    a->also_com = com;
     return B2A_OK;
 }
 
@@ -1613,6 +1643,16 @@ extern "C" int b2a_invalidate(b2a_ctx* c)
     return B2A_OK;
 }
 
+// development aid (not in b2a.h): time stamps written by the last streaming launch under B2A_STREAM_DEBUG
+extern "C" int b2a_debug_read(b2a_ctx* c, unsigned long long* out, int nwords)
+{
+    if (!c || !out || !c->d_dbg || nwords > 8 * 4096) return fail(B2A_ERR_STATE, "no debug buffer");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(out, c->d_dbg, sizeof(unsigned long long) * nwords, cudaMemcpyDeviceToHost));
+    return B2A_OK;
+}
+
 extern "C" int b2a_timing_enable(b2a_ctx* c, int enable)
 {
     TEAM_ALL(c, b2a_timing_enable(m, enable));
@@ -1808,6 +1848,15 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
             sa.ori_sign  = s.method == 1 ? -1.f : (d.tp2 == 1 ? 1.f : -1.f);
         }
         if (const char* e = getenv("B2A_ORIENT_VAR")) var = std::min(var, atoi(e));
+        // one pass for two products: the kernel also writes the exact centres of kind also_com (unless this batch has them already)
+        const int  ac    = a.also_com;
+        const bool fused = ac >= 0 && g->valid[ac] != c->serial && !getenv("B2A_NO_FUSE");
+        if (fused)
+        {
+            if (!g->d_cen[ac]) CU(cudaMalloc(&g->d_cen[ac], sizeof(double) * 3 * (size_t)g->nmol * c->maxK));
+            sa.cen = g->d_cen[ac]; sa.w2 = g->d_w[ac]; sa.wsum2 = make_div(g->wsum[ac]);
+        }
+        struct Mark { Group* g; int ac; uint64_t serial; bool on; ~Mark() { if (on) g->valid[ac] = serial; } } mark{ g, ac, c->serial, fused };
         return launch_stream<2>(c, *g, s.com, M, sa, sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 4) & ~1) + sizeof(float2) * (s.nAngle + 2) + sizeof(unsigned) * smem_bins, fast, var);
     }
     const size_t smem       = sizeof(double) * (g->napm + s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins;

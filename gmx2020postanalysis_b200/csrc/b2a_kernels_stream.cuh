@@ -77,9 +77,10 @@ struct StreamArgs
     int              item_frames;    // frames per work item
     int              mblocks;        // molecule blocks (blockDim.x molecules each)
     int              nitems;         // mblocks * ceil(nframes / item_frames)
-    unsigned*        work;           // device counter, zeroed before the launch: next work item to hand out
+    unsigned*        work;           // {next work item to hand out, blocks that have finished}; both zero at launch, re-zeroed by the last block
     int              tile_floats;    // floats reserved per stage (blockDim.x * napm * 3 + 8)
     unsigned         park_ns;        // suspend-time hint of the producer's wait for a free stage (0: plain try_wait loop)
+    unsigned         cwait_ns;       // the same for the consumers' wait for a full stage
     // MODE 0: centres
     double*          cen;
     int4*            fix;
@@ -102,7 +103,28 @@ struct StreamArgs
     int                  rot_shift;  // MODE 2, VAR 1: log2(32 / gcd(3 napm, 32)); 5 = odd stride, no rotation
     int                  ori_reuse;  // MODE 2, VAR 1, three-site molecules: the vector atoms are (reference atom, the other two)
     const float2*        fmh;        // MODE 2: per angle bin {midpoint, halfwidth - table roundings} of its cosine interval
+    // MODE 2 with a fused centre output (b2a_acc_also_centers): the consumer that evaluates a molecule also writes its exact FP64
+    // centre of a second kind (e.g. the dipole vector, com 3) into `cen` -- one pass over the coordinates instead of K1 + K4
+    const double*        w2;         // weights of the fused centre kind (napm doubles), or nullptr
+    DivConst             wsum2;
+    unsigned long long*  dbg;        // optional per-block time stamps (B2A_STREAM_DEBUG; tools/bench_k4.py --timeline): 8 words per block
 };
+
+__device__ __forceinline__ void cp_async4(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 struct StageDesc { int m, f, poff, pad; };   // molecule block, frame, float offset of the block's first atom inside the stage; m < 0: end
 
@@ -146,8 +168,10 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
     unsigned*           shist = reinterpret_cast<unsigned*>(swf + ((napm + 1) & ~1));
     uint2*              fqueue = reinterpret_cast<uint2*>(shist + (MODE != 0 ? ((a.smem_bins + 1) & ~1) : 0));
     unsigned char*      slut   = reinterpret_cast<unsigned char*>(fqueue + (MODE != 0 ? kFastQueue : 0));
+    double*             sw2    = reinterpret_cast<double*>(slut + (MODE == 2 ? kCosLut : 0));   // MODE 2, fused centre output: napm weights
     __shared__ unsigned fq_n;
 
+    if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 0] = gtime();
     const int T = blockDim.x;          // all threads (prologue / epilogue loops)
     const int M = blockDim.x - 32;     // consumer threads
     // molecules per tile.  MODE 2 / VAR 1: two per consumer thread.  MODE 0 / VAR 2: THREE LANES per molecule (one per
@@ -155,26 +179,41 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
     // dimension, and its atoms take 12 * napm bytes of every stage: one thread per molecule leaves an SM with a handful of
     // warps crawling along those chains (napm = 25: 0.19 of HBM peak, tools/bench_hbm_napm.py)
     const int MT = (MODE == 2 && VAR == 1) ? 2 * M : ((MODE == 0 && VAR == 2) ? 10 * (M >> 5) : M);   // (host: launch_stream_t)
-    for (int j = threadIdx.x; j < napm; j += T) { sw[j] = a.w[j]; if (MODE != 0) swf[j] = a.wf[j]; }
-    if (MODE == 2 && a.fp.enabled)
-        for (int j = threadIdx.x; j < kCosLut / 4; j += T) reinterpret_cast<unsigned*>(slut)[j] = reinterpret_cast<const unsigned*>(a.lut)[j];
-    if (threadIdx.x == 0) fq_n = 0;
-    if (MODE == 2)
+    // Prologue.  The consumer threads first ISSUE the copies of the block's tables (weights, edge tables, cos look-up table) as
+    // asynchronous global -> shared copies (cp.async, LDGSTS): nothing waits for them yet.  Then the barriers are armed and the
+    // producer starts the ring; the table copies, issued ahead of the bulk traffic, land while the first stages are in flight,
+    // and the consumers collect them (cp.async.wait_all + a consumer-only named barrier) just before the first stage arrives.
+    if ((int)threadIdx.x < M)
     {
-        for (int j = threadIdx.x; j <= a.ori.nAngle; j += T) sedge[j] = a.cosedge[j];
-        for (int j = threadIdx.x; j < a.ori.nAngle + 3; j += T) fedge[j] = a.fedge[j];   // two -3 sentinels past the last edge
-        for (int j = threadIdx.x; j < a.ori.nAngle + 2; j += T) fmh[j] = a.fmh[j];
-        for (int j = threadIdx.x; j < a.ori.nbin1 + 2; j += T) stab[j] = a.stab[j];
+        for (int j = threadIdx.x; j < napm; j += M) { cp_async8(&sw[j], &a.w[j]); if (MODE != 0) cp_async4(&swf[j], &a.wf[j]); }
+        if (MODE == 2 && a.w2)
+            for (int j = threadIdx.x; j < napm; j += M) cp_async8(&sw2[j], &a.w2[j]);
+        if (MODE == 2 && a.fp.enabled)
+            for (int j = threadIdx.x; j < kCosLut / 4; j += M) cp_async4(reinterpret_cast<unsigned*>(slut) + j, reinterpret_cast<const unsigned*>(a.lut) + j);
+        if (MODE == 2)
+        {
+            for (int j = threadIdx.x; j <= a.ori.nAngle; j += M) cp_async8(&sedge[j], &a.cosedge[j]);
+            for (int j = threadIdx.x; j < a.ori.nAngle + 3; j += M) cp_async4(&fedge[j], &a.fedge[j]);   // two -3 sentinels past the last edge
+            for (int j = threadIdx.x; j < a.ori.nAngle + 2; j += M) cp_async8(&fmh[j], &a.fmh[j]);
+            for (int j = threadIdx.x; j < a.ori.nbin1 + 2; j += M) cp_async8(&stab[j], &a.stab[j]);
+        }
+        if (MODE != 0)
+            for (int b = threadIdx.x; b < a.smem_bins; b += M) shist[b] = 0;
     }
-    const OrientTabs tb{ sedge, fedge, stab };
-    if (MODE != 0)
-        for (int b = threadIdx.x; b < a.smem_bins; b += T) shist[b] = 0;
     if (threadIdx.x == 0)
     {
+        fq_n = 0;
         for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (unsigned)(M >> 5)); }
         mbar_fence_init();
     }
     __syncthreads();
+    if ((int)threadIdx.x < M)
+    {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(M) : "memory");
+    }
+    const OrientTabs tb{ sedge, fedge, stab };
+    if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 1] = gtime();
 
     unsigned   ndrop = 0, nsel = 0, nexact = 0, nbad = 0;
     const bool use_smem = MODE == 1 ? a.smem_bins >= a.den.nbin
@@ -230,8 +269,9 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
         for (unsigned n = 0;; ++n)
         {
             const int s = (int)(n % NS);
-            mbar_wait(&full[s], (n / NS) & 1u);
+            mbar_wait_parked(&full[s], (n / NS) & 1u, a.cwait_ns);
             const StageDesc sd = sdesc[s];
+            if (a.dbg && threadIdx.x == 0 && n == 0) a.dbg[blockIdx.x * 8 + 2] = gtime();   // first stage has landed
             if (sd.m < 0) break;   // the stream is in order: nothing follows the first end marker
             const int f = sd.f;
             const int i = sd.m * MT + (int)threadIdx.x;
@@ -304,6 +344,19 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
                 }
                 else
                 {
+                    if (a.w2)
+                    {   // fused centre output: the same FP64 code as K1 (mol_centers3), on the coordinates already in shared memory
+                        auto put = [&](const float* pm, int im) {
+                            double c0, c1, c2;
+                            mol_centers3<true>(pm, napm, sw2, a.wsum2, g, c0, c1, c2);
+                            double* o = a.cen + (size_t)f * 3 * a.nmol;
+                            o[im]                      = c0;
+                            o[(size_t)a.nmol + im]     = c1;
+                            o[2 * (size_t)a.nmol + im] = c2;
+                        };
+                        if (vA) put(p, i);
+                        if (VAR == 1 && i + M < a.nmol) put(p + (unsigned)M * (unsigned)napm * 3u, i + M);
+                    }
                     auto count = [&](int cz, int ca) {
                         if (cz >= 0)
                         {
@@ -413,9 +466,11 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
             if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);   // this warp is done with stage s
         }
     }
+    if (a.dbg && threadIdx.x == 0) { a.dbg[blockIdx.x * 8 + 3] = gtime(); }   // warp 0 has seen the end of the stream
     if (MODE != 0)
     {
         __syncthreads();
+        if (a.dbg && threadIdx.x == 0) { a.dbg[blockIdx.x * 8 + 4] = gtime(); a.dbg[blockIdx.x * 8 + 7] = fq_n; }
         // undecided molecules: literal FP64 evaluation, read back from global memory (their stage has been refilled)
         const unsigned nq = min(fq_n, (unsigned)kFastQueue);
         for (unsigned e = threadIdx.x; e < nq; e += T)
@@ -451,6 +506,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
             }
         }
         __syncthreads();
+        if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 5] = gtime();   // queue drained
         const int nb = MODE == 1 ? a.den.nbin : a.ori.nbin1 * a.ori.nAngle + a.ori.nbin1;
         if (use_smem)
             for (int b = threadIdx.x; b < nb; b += T)
@@ -469,6 +525,14 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
             if (nexact) atomicAdd(&a.stats[2], (unsigned long long)nexact);
             if (nbad) atomicAdd(&a.stats[7], (unsigned long long)nbad);
         }
+        if (a.dbg && threadIdx.x == 0) a.dbg[blockIdx.x * 8 + 6] = gtime();
+    }
+    // the block that finishes last re-arms the work counter for the next launch (every block has long stopped claiming items:
+    // a block gets here only after its producer saw the end of the item list)
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        if (atomicAdd(a.work + 1, 1u) == gridDim.x - 1u) { a.work[0] = 0u; a.work[1] = 0u; __threadfence(); }
     }
 }
 

@@ -28,7 +28,7 @@ SYMBOLS = [
     "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_acc_fast", "b2a_invalidate", "b2a_timing_enable",
     "b2a_timing_read",
     "b2a_create_multi", "b2a_num_devices", "b2a_member", "b2a_current_device", "b2a_finalize", "b2a_comm_unique_id", "b2a_comm_init",
-    "b2a_set_frame_base", "b2a_series_size", "b2a_series_read", "b2a_acc_public_size", "b2a_centers_device",
+    "b2a_set_frame_base", "b2a_series_size", "b2a_series_read", "b2a_acc_public_size", "b2a_centers_device", "b2a_acc_also_centers",
 ]
 
 
@@ -137,6 +137,7 @@ def load():
         L.b2a_series_read.argtypes = [_P, C.c_int, _P, _P]
         L.b2a_acc_public_size.argtypes = [_P, C.c_int, C.POINTER(C.c_size_t)]
         L.b2a_centers_device.argtypes = [_P, C.c_int, C.c_int, C.POINTER(_P)]
+        L.b2a_acc_also_centers.argtypes = [_P, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -390,6 +391,10 @@ class Context:
     def acc_fast(self, acc, mode):
         """density / orient: 0 literal FP64, 1 FP32 bracket + FP64 queue (default), 2 validate (STAT_MISPROVEN)."""
         check(self.L.b2a_acc_fast(self._h, acc, mode))
+
+    def acc_also_centers(self, acc, com):
+        """orient: the same pass also writes the exact centres of kind `com` (cached for the batch)."""
+        check(self.L.b2a_acc_also_centers(self._h, acc, com))
 
     def invalidate(self):
         """Drop cached centres so the next accumulate redoes the whole path on the resident batch."""

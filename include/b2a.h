@@ -317,6 +317,12 @@ int b2a_rdf_tune(b2a_ctx* ctx, int acc, int symmetric, int paranoid);
  * the HBM roofline); 0 = literal FP64 for every molecule; 2 = validation: both, B2A_STAT_MISPROVEN counts disagreements.
  * The environment variable B2A_FAST overrides the mode.                                                             */
 int b2a_acc_fast(b2a_ctx* ctx, int acc, int mode);
+/* Orientation accumulators: let the same pass over the coordinates also materialise the exact centres of kind `com` of the
+ * accumulator's group (bit-identical to b2a_centers: the reference's loadPositionCenter arithmetic), e.g. the per-molecule dipole
+ * vectors (com 3) beside the orientation histogram (BASELINE config 4: one read of the frame instead of two).  After
+ * b2a_accumulate the centres of the batch are cached: b2a_centers / b2a_centers_batch / b2a_centers_device return them without
+ * another kernel.  com = -1 switches it off.                                                                                 */
+int b2a_acc_also_centers(b2a_ctx* ctx, int acc, int com);
 /* Cell-binned evaluation for cut-offs much shorter than the box (the brute-force loop of calc_rdf_region.cpp:73-95
  * wastes > 99 % of its pairs when Rm = 3 nm in a 34 nm box; pattern and its exactness check in the reference:
  * src/test/nb_cellSearch_anyBoxSize.cpp:194-299).  Counts are identical to the all-pairs evaluation.

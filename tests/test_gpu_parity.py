@@ -465,6 +465,40 @@ def test_orient_bit_exact_and_reference_text(gpu_ctx_factory, name):
     assert refprog.orient_text(o, ncm, kw["nA"]) == open(os.path.join(GOLD, name + ".txt")).read().split("\n")[:-1]
 
 
+@pytest.mark.parametrize("which", ["water", "il"])
+def test_orient_fused_centre_output(gpu_ctx_factory, which):
+    """b2a_acc_also_centers: the orientation pass also materialises the centres of a second kind (config 4: the dipole vectors).
+    The fused centres are bit-identical to b2a_centers of the same kind computed on their own, the histogram is unchanged, and the
+    cache is honoured (no second kernel, fresh values after the next batch)."""
+    if which == "water":
+        system, grp, tp, com2 = synth.water_box(5000, 5.3, seed=20200104), "SOL", (1, 2, 3), lib.COM_DIPOLE
+    else:
+        system, grp, tp, com2 = synth.ionic_liquid(300, 4.0, seed=25), "CAT", (3, 7, 12), lib.COM_CHARGE
+    K = 5
+    kw = dict(grp=0, com=0, DIMN=2, low=0.3, up=3.9, c1=2.0, c2=2.0, dr=0.25, CR=2.0, Cr=0.0, nAngle=90, tp1=tp[0], tp2=tp[1], tp3=tp[2],
+              DIMNOrient=2, method=1)
+    ref = gpu_ctx_factory(system.natoms, K)
+    _groups(ref, system, [grp])
+    a0 = ref.orient_create(**kw)
+    ctx = gpu_ctx_factory(system.natoms, K)
+    _groups(ctx, system, [grp])
+    a1 = ctx.orient_create(**kw)
+    ctx.acc_also_centers(a1, com2)
+    for b in range(2):
+        x = system.frames(K * b, K)
+        ref.submit(x, system.box9()); ref.accumulate(a0)
+        ctx.submit(x, system.box9()); ctx.accumulate(a1)
+        ctx.timing_enable(True); ctx.timing_read()
+        got = ctx.centers_batch(0, com2)                   # served from what the orientation kernel wrote
+        assert ctx.timing_read()["k1_centers"][1] == 0     # ... no centre kernel ran
+        ctx.timing_enable(False)
+        exp = ref.centers_batch(0, com2)
+        assert np.array_equal(got, exp, equal_nan=True) and np.isfinite(got).all()
+    h0, s0 = ref.read(a0)
+    h1, s1 = ctx.read(a1)
+    assert np.array_equal(h0, h1) and h0.sum() > 0 and int(s0[lib.STAT_SELECTED]) == int(s1[lib.STAT_SELECTED])
+
+
 def test_dipole_orientation_config4_shape(gpu_ctx_factory):
     """BASELINE config 4, reduced: charge-centre dipole vectors (guarded) + bisector angle histogram."""
     system = synth.water_box(5000, 5.3, seed=20200104)
