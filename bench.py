@@ -482,6 +482,9 @@ def measure(wl, D, steps, warmup, with_cpu, rdf_sample, flush):
     ctx = lib.Context(wl.natoms, F, device=local)
     joined = b2d.comm_init(ctx, device=f"cuda:{local}")       # ncclCommInitRank inside libb2a (id broadcast by torch.distributed)
     wl.setup(ctx)
+    if joined:
+        ctx.finalize()                           # NCCL connects lazily: the first collective of a communicator pays for it, not the timed one
+        ctx.sync()
     stream = torch.cuda.ExternalStream(ctx.stream, device=local)
     pos = {"next": 0, "cur": -1}
 
@@ -701,8 +704,8 @@ def host_cpp_block(D, seconds_budget=40.0):
             out = {"program": "build/dropin/calc_rdf_region_fused (one process, itp::GmxHandle + libb2a)", "trajectory": f"{nfile} distinct frames replayed (raw float format)"}
             outputs = {}
             for ndev in sorted({1, D.world}):
-                rep = 8 * ndev                                   # 512 frames per device
-                e2 = dict(env, B2A_BATCH="32", GMXSTUB_REPEAT=str(rep), B2A_DEVICES=",".join(str(d) for d in range(ndev)))
+                rep = int(os.environ.get("B2A_CPP_REPEAT", "32")) * ndev        # 2048 frames per device: long enough that ramp-up and drain of the devices do not dominate
+                e2 = dict(env, B2A_BATCH=os.environ.get("B2A_BATCH", "32"), GMXSTUB_REPEAT=str(rep), B2A_DEVICES=",".join(str(d) for d in range(ndev)))
                 t = time.perf_counter()
                 r = subprocess.run([exe, "-f", prefix + ".b2t", "-s", prefix + ".b2p", "-n", prefix + ".ndx", "-o", prefix + f".{ndev}.xvg"], input="0 0\n",
                                    capture_output=True, text=True, env=e2, cwd=td, timeout=600)
@@ -710,6 +713,8 @@ def host_cpp_block(D, seconds_budget=40.0):
                 if r.returncode != 0:
                     out[f"error_{ndev}"] = (r.stdout + r.stderr)[-400:]
                     continue
+                if os.environ.get("B2A_TRACE"):
+                    out[f"trace_{ndev}gpu"] = [ln for ln in r.stderr.splitlines() if ln.startswith("b2a ")]
                 loop = [ln for ln in r.stdout.splitlines() if ln.startswith("frame loop")]
                 fps = float(loop[-1].split("=")[1].split()[0]) if loop else None
                 out[f"frames_per_s_{ndev}gpu"] = fps
@@ -741,6 +746,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the other_configs block")
     ap.add_argument("--no-host-cpp", action="store_true", help="skip the one-process C++ run")
+    ap.add_argument("--host-cpp-only", action="store_true", help="only the one-process C++ run over --gpus devices (no torch, no ranks)")
     ap.add_argument("--other-steps", type=int, default=5)
     ap.add_argument("--symmetric", type=int, default=1)
     ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
@@ -748,6 +754,13 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.host_cpp_only:
+        class _One:
+            rank, world = 0, args.gpus
+            def barrier(self, ctx=None): pass
+            def cpu_barrier(self): pass
+        print(json.dumps({"host_cpp": host_cpp_block(_One())}))
+        return 0
     args.warmup = max(args.warmup, 3)
 
     D = Dist()

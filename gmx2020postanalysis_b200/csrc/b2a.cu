@@ -238,6 +238,8 @@ struct b2a_ctx
     long long    next_frame = 0;      // global index the next submitted batch starts at
     void*        comm = nullptr;      // ncclComm_t of this device (members and plain contexts), attached by b2a_comm_init / b2a_create_multi
     int          comm_rank = 0, comm_size = 1, comm_procs = 1;
+    int          host_buffers = 2;    // leader: host staging buffers the caller cycles through (b2a_set_host_buffers)
+    std::vector<std::pair<int, int>> inflight;   // leader: uploads not yet known to have completed, oldest first: (member, device buffer)
     bool         same_device_team = false;   // leader: members share a device (tests on one GPU): merged by a local kernel, NCCL cannot do it
     bool is_leader() const { return !members.empty(); }
 };

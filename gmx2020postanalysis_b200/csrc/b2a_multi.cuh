@@ -217,15 +217,6 @@ extern "C" int b2a_comm_init(b2a_ctx* c, int nprocs, int proc_rank, const void* 
 // ---- dealing batches to devices -------------------------------------------------------------------------------------------
 static int team_submit(b2a_ctx* c, int nframes, const float* x, const float* box9)
 {
-    // the previous batch went to another device: its upload must have left the caller's pinned buffer before this call returns
-    // (same contract as on one device: callers alternate between two host buffers)
-    if (c->cur_member >= 0)
-    {
-        b2a_ctx* prev = c->members[c->cur_member];
-        CU(cudaSetDevice(prev->device));
-        CU(cudaEventSynchronize(prev->ev_copied[prev->cur]));
-        if (prev->field_pending) { CU(cudaEventSynchronize(prev->ev_field)); prev->field_pending = false; }
-    }
     const int next = (c->cur_member + 1) % (int)c->members.size();
     b2a_ctx*  m    = c->members[next];
     m->next_frame  = c->next_frame;           // global frame index of this block
@@ -235,6 +226,25 @@ static int team_submit(b2a_ctx* c, int nframes, const float* x, const float* box
     c->next_frame += nframes;
     c->nframes = nframes;
     c->serial++;
+    // The caller cycles through `host_buffers` staging buffers: before this call returns, the upload issued host_buffers - 1
+    // submits ago must have left its buffer (with the default of two that is the previous one: the contract of a single device).
+    // With one buffer more than devices the host never waits for a copy, and the uploads of different devices overlap.
+    c->inflight.push_back({ next, m->cur });
+    while ((int)c->inflight.size() > std::max(1, c->host_buffers - 1))
+    {
+        b2a_ctx* o = c->members[c->inflight.front().first];
+        CU(cudaSetDevice(o->device));
+        CU(cudaEventSynchronize(o->ev_copied[c->inflight.front().second]));   // (re-recorded by a later upload at worst: still safe)
+        if (o->field_pending) { CU(cudaEventSynchronize(o->ev_field)); o->field_pending = false; }
+        c->inflight.erase(c->inflight.begin());
+    }
+    return B2A_OK;
+}
+
+extern "C" int b2a_set_host_buffers(b2a_ctx* c, int n)
+{
+    if (!c || n < 2) return fail(B2A_ERR_ARG, "b2a_set_host_buffers: at least two buffers");
+    c->host_buffers = n;
     return B2A_OK;
 }
 

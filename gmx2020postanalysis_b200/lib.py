@@ -28,7 +28,7 @@ SYMBOLS = [
     "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_acc_fast", "b2a_invalidate", "b2a_timing_enable",
     "b2a_timing_read",
     "b2a_create_multi", "b2a_num_devices", "b2a_member", "b2a_current_device", "b2a_finalize", "b2a_comm_unique_id", "b2a_comm_init",
-    "b2a_set_frame_base", "b2a_series_size", "b2a_series_read", "b2a_acc_public_size", "b2a_centers_device", "b2a_acc_also_centers",
+    "b2a_set_frame_base", "b2a_series_size", "b2a_series_read", "b2a_acc_public_size", "b2a_centers_device", "b2a_acc_also_centers", "b2a_set_host_buffers",
 ]
 
 
@@ -138,6 +138,7 @@ def load():
         L.b2a_acc_public_size.argtypes = [_P, C.c_int, C.POINTER(C.c_size_t)]
         L.b2a_centers_device.argtypes = [_P, C.c_int, C.c_int, C.POINTER(_P)]
         L.b2a_acc_also_centers.argtypes = [_P, C.c_int, C.c_int]
+        L.b2a_set_host_buffers.argtypes = [_P, C.c_int]
         _lib = L
     return _lib
 
@@ -197,6 +198,9 @@ class Context:
         assert len(uid) == 128
         buf = C.create_string_buffer(uid, 128)
         check(self.L.b2a_comm_init(self._h, nprocs, rank, C.cast(buf, _P)))
+
+    def set_host_buffers(self, n):
+        check(self.L.b2a_set_host_buffers(self._h, n))
 
     def set_frame_base(self, first_frame):
         check(self.L.b2a_set_frame_base(self._h, int(first_frame)))

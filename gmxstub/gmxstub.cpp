@@ -952,7 +952,7 @@ int gmxstub_read_frames(t_trxstatus* st, int max_frames, float* x_out, float* bo
     }
     std::fseek(st->fp, static_cast<long>(sizeof(TrjHeader) + static_cast<off_t>(st->next) * fb), SEEK_SET);   /* keep the stream in step */
     const int n  = (int)at.size();
-    int nthreads = std::min<int>(n, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+    int nthreads = std::min<int>(n, std::max(1u, std::min(32u, std::thread::hardware_concurrency())));
     if (const char* e = std::getenv("GMXSTUB_DECODE_THREADS")) nthreads = std::max(1, std::min(n, std::atoi(e)));
     std::atomic<int> next{ 0 }, bad{ 0 };
     auto work = [&]() {

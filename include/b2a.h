@@ -93,6 +93,11 @@ int  b2a_num_devices(b2a_ctx* ctx);              /* 1 for a b2a_create context *
 b2a_ctx* b2a_member(b2a_ctx* ctx, int i);        /* device i's own context (per-device streams, timing); owned by ctx */
 int  b2a_current_device(b2a_ctx* ctx);           /* member index that holds the current batch (-1 before the first) */
 
+/* How many host staging buffers the caller cycles through (default 2).  On a multi-device context b2a_submit_batch returns once
+ * the upload issued n - 1 submits ago has left its buffer; with n = devices + 1 the host never waits for a copy and the uploads
+ * of different devices (separate PCIe links) overlap.  A plain context keeps the two-buffer contract whatever n is.            */
+int  b2a_set_host_buffers(b2a_ctx* ctx, int n);
+
 /* Merge: ONE all-reduce (64-bit unsigned integer sum, ncclAllReduce over NVLink) per accumulator over its counters and
  * stats block, across every device of the context and -- after b2a_comm_init -- of every process.  The private counts of
  * each device stay untouched (the sum lands in a second buffer): accumulation may go on and b2a_finalize may be called

@@ -6,6 +6,8 @@
 
 #include <b2a.h>
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -28,8 +30,10 @@ namespace b2a_detail
         }
         ~FrameBatcher()
         {
+            if (std::getenv("B2A_TRACE"))   // where the control thread spent its time (one line on stderr)
+                std::fprintf(stderr, "b2a batcher: %ld batches, host seconds: read/decode %.4f, submit %.4f\n", serial_, t_read_, t_submit_);
             if (ctx_) b2a_destroy(ctx_);
-            for (int p = 0; p < 2; ++p)
+            for (size_t p = 0; p < px_.size(); ++p)
             {
                 if (px_[p]) b2a_pinned_free(px_[p]);
                 if (pv_[p]) b2a_pinned_free(pv_[p]);
@@ -87,7 +91,15 @@ namespace b2a_detail
             if (ctx_) check(b2a_set_frame_base(ctx_, 0));   // a restarted trajectory counts its frames from 0 again
             natoms_ = io_.natoms;
             const size_t n3 = (size_t)natoms_ * 3;
-            for (int p = 0; p < 2; ++p)
+            // staging buffers: two for one device (ping-pong); one more than devices otherwise, so that no submit waits for a copy
+            const int ndev = b2a_num_devices(ctx(natoms_));
+            if (px_.empty())
+            {
+                const size_t nb = ndev > 1 ? (size_t)ndev + 1 : 2;
+                px_.assign(nb, nullptr); pv_.assign(nb, nullptr); pf_.assign(nb, nullptr);
+                if (ndev > 1) check(b2a_set_host_buffers(ctx_, (int)nb));
+            }
+            for (size_t p = 0; p < px_.size(); ++p)
             {
                 if (!px_[p]) px_[p] = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
                 if (io_.bV && !pv_[p]) pv_[p] = static_cast<float*>(b2a_pinned_alloc(n3 * sizeof(float) * k_));
@@ -123,7 +135,7 @@ namespace b2a_detail
         {
             const size_t n3 = (size_t)natoms_ * 3;
             int          n  = 0;
-            flip_ ^= 1;
+            flip_ = (flip_ + 1) % (int)px_.size();
             bx_ = px_[flip_]; bv_ = pv_[flip_]; bf_ = pf_[flip_];
 #ifdef GMXSTUB_BATCH_READ
             // The libgromacs stand-in can hand out K frames per call and decodes XTC frames on K host threads, straight
@@ -137,6 +149,7 @@ namespace b2a_detail
                     btime_[0] = io_.time;
                     n         = 1;
                 }
+                const auto t0 = std::chrono::steady_clock::now();
                 if (!eof_ && n < k_)
                 {
                     const int got = gmxstub_read_frames(status_, k_ - n, bx_ + (size_t)n * n3, bbox_.data() + 9 * (size_t)n, btime_.data() + n);
@@ -147,7 +160,10 @@ namespace b2a_detail
                 n_ = n;
                 ++serial_;
                 times_all_.insert(times_all_.end(), btime_.begin(), btime_.begin() + n);
+                const auto t1 = std::chrono::steady_clock::now();
                 check(b2a_submit_batch(ctx(natoms_), n, bx_, bbox_.data()));
+                t_read_ += std::chrono::duration<double>(t1 - t0).count();
+                t_submit_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
                 return true;
             }
 #endif
@@ -192,13 +208,14 @@ namespace b2a_detail
         int                natoms_ = 0, k_ = 16, n_ = 0, cur_ = 0;
         bool               eof_ = false;
         long               serial_ = 0;
-        // Two pinned staging buffers, used alternately: the asynchronous H2D copy of batch k may still be reading its
+        // Pinned staging buffers, used in turn (two for one device; devices + 1 for a multi-device context, b2a_set_host_buffers): the asynchronous H2D copy of batch k may still be reading its
         // buffer while the host already decodes batch k+1 into the other one; b2a_submit_batch(k+1) waits for the upload of batch k (and for pending field uploads)
         // before it returns, so by the time buffer k%2 is refilled (batch k+2) its copy has completed.
-        float*             px_[2] = { nullptr, nullptr }, *pv_[2] = { nullptr, nullptr }, *pf_[2] = { nullptr, nullptr };
+        std::vector<float*> px_, pv_, pf_;
         float*             bx_ = nullptr, *bv_ = nullptr, *bf_ = nullptr;   // the buffers of the batch being filled / served
         int                flip_ = 0;
         std::vector<float> bbox_, btime_, times_all_;
+        double             t_read_ = 0, t_submit_ = 0;
     };
 } // namespace b2a_detail
 } // namespace itp
