@@ -114,6 +114,8 @@ struct CellSort
     int4*     sorted = nullptr;                      // [maxK][n]
     size_t    cap_n = 0;
     unsigned  cap_keys = 0, nkeys = 0;
+    cudaEvent_t  ready = nullptr;                    // recorded on the stream that built the arrays; other streams wait for it
+    cudaStream_t built_on = nullptr;
     unsigned* starts(int maxK) const { return cells + (size_t)(nkeys + 1) * maxK; }
 };
 
@@ -170,6 +172,13 @@ struct Acc
     unsigned  cap_keysA = 0, cap_keysB = 0;
     int       ipt = 0, threads = 0;   // 0 = auto
     int       fast = 1;               // density / orient: 0 literal FP64, 1 FP32 bracket + FP64 queue, 2 validate
+    // RDF accumulators of a context that holds several of them (a sweep over group pairs) queue their kernels on a stream of their
+    // own, forked from the context stream after the centres and joined before anything that depends on them: the short launches
+    // of small group pairs then run beside the long ones instead of in front of them
+    cudaStream_t side = nullptr;
+    cudaEvent_t  ev_done = nullptr;
+    bool         side_pending = false;
+    cudaStream_t last_stream = nullptr;   // stream the last accumulation was queued on
     int       also_com = -1;          // orient: centre kind the streaming kernel materialises on the side (b2a_acc_also_centers)
     unsigned char* d_lut = nullptr;   // orient: cos cell -> first candidate angle bin
     float2*        d_fmh = nullptr;   // orient: per angle bin {midpoint, shrunk halfwidth} of its cosine interval
@@ -206,6 +215,7 @@ struct b2a_ctx
     cudaEvent_t  ev_free[2]   = { nullptr, nullptr };   // main stream: every kernel launched while b was current has finished
     int          cur = 0;
     cudaEvent_t  ev_field = nullptr;                    // main stream: the last velocity / force upload has finished
+    cudaEvent_t  ev_fork = nullptr;                     // main stream: fork point of an accumulator's side stream
     bool         field_pending = false;
     std::vector<float> h_box;        // [K][9]
     int          nframes = 0;
@@ -285,6 +295,21 @@ struct Timed   // RAII: records an event pair around a launch sequence when timi
 };
 } // namespace
 
+__global__ void k_fetch_words(unsigned* __restrict__ dst, const unsigned* __restrict__ src_pinned, int nwords);
+
+// The context stream waits for every accumulator that has work on a side stream: called before anything that must see (or may
+// overwrite what is read by) that work -- a new batch, an invalidation, a read, a reset, the merge.
+static int join_side(b2a_ctx* c)
+{
+    for (auto& a : c->accs)
+        if (a && a->side_pending)
+        {
+            CU(cudaStreamWaitEvent(c->stream, a->ev_done, 0));
+            a->side_pending = false;
+        }
+    return B2A_OK;
+}
+
 extern "C" const char* b2a_last_error(void) { return g_err.c_str(); }
 extern "C" const char* b2a_version(void) { return "b2a 0.1 (sm_100a)"; }
 
@@ -329,6 +354,7 @@ extern "C" int b2a_create(b2a_ctx** out, int device, int natoms, int max_frames)
         CU(cudaEventCreateWithFlags(&c->ev_free[b], cudaEventDisableTiming));
     }
     CU(cudaEventCreateWithFlags(&c->ev_field, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     c->cur = 0; c->d_x = c->d_xbuf[0]; c->d_geom = c->d_geombuf[0]; c->h_geom = c->h_geombuf[0];
     c->h_box.assign((size_t)max_frames * 9, 0.f);
     *out = c.release();
@@ -353,6 +379,8 @@ static void free_acc(Acc& a)
     cudaFree(a.d_keysA); cudaFree(a.d_keysB); cudaFree(a.d_cellA); cudaFree(a.d_cellB); cudaFree(a.d_sortedB);
     if (a.h_frames) cudaFreeHost(a.h_frames);
     for (auto& e : a.ring.ev) if (e) cudaEventDestroy(e);
+    if (a.side) { cudaStreamSynchronize(a.side); cudaStreamDestroy(a.side); }
+    if (a.ev_done) cudaEventDestroy(a.ev_done);
 }
 
 extern "C" void b2a_destroy(b2a_ctx* c)
@@ -369,7 +397,7 @@ extern "C" void b2a_destroy(b2a_ctx* c)
     multi_release(c);
     for (auto& kv : c->groups) free_group(kv.second);
     for (auto& a : c->accs) if (a) free_acc(*a);
-    for (auto& cs : c->cell_sorts) { cudaFree(cs->keys); cudaFree(cs->cells); cudaFree(cs->sorted); }
+    for (auto& cs : c->cell_sorts) { cudaFree(cs->keys); cudaFree(cs->cells); cudaFree(cs->sorted); if (cs->ready) cudaEventDestroy(cs->ready); }
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_pos_scratch); cudaFree(c->d_work); cudaFree(c->d_dbg);
     cudaFree(c->d_field[1]); cudaFree(c->d_field[2]); cudaFree(c->d_field_cen);
@@ -381,6 +409,7 @@ extern "C" void b2a_destroy(b2a_ctx* c)
         if (c->ev_free[b]) cudaEventDestroy(c->ev_free[b]);
     }
     if (c->ev_field) cudaEventDestroy(c->ev_field);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();   // a context torn down after a failed allocation must not leave a sticky error behind
@@ -392,8 +421,17 @@ extern "C" int b2a_sync(b2a_ctx* c)
     TEAM_ALL(c, b2a_sync(m));
     if (!c) return fail(B2A_ERR_ARG, "null context");
     CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;
     CU(cudaStreamSynchronize(c->stream));
     return B2A_OK;
+}
+
+extern "C" int b2a_join(b2a_ctx* c)
+{
+    TEAM_ALL(c, b2a_join(m));
+    if (!c) return fail(B2A_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    return join_side(c);
 }
 
 extern "C" void* b2a_stream(b2a_ctx* c)
@@ -427,6 +465,7 @@ extern "C" int b2a_set_group(b2a_ctx* c, int grp, const int* index, int ngx, int
     for (int n = 0; n < ngx; ++n)
         if (index[n] < 0 || index[n] >= c->natoms) return fail(B2A_ERR_ARG, "b2a_set_group: atom index %d out of range", index[n]);
     CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;
     CU(cudaStreamSynchronize(c->stream));
     Group& g = c->groups[grp];
     free_group(g);
@@ -482,6 +521,7 @@ extern "C" int b2a_set_group_full(b2a_ctx* c, int grp, const int* index, int ngx
     for (int n = 0; n < ngx; ++n)
         if (index[n] < 0 || index[n] >= c->natoms) return fail(B2A_ERR_ARG, "b2a_set_group_full: atom index %d out of range", index[n]);
     CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;
     CU(cudaStreamSynchronize(c->stream));
     Group& g = c->groups[grp];
     free_group(g);
@@ -530,6 +570,8 @@ extern "C" int b2a_set_group_wsum(b2a_ctx* c, int grp, int com, double wsum)
     if (!c || com < 0 || com > 3) return fail(B2A_ERR_ARG, "b2a_set_group_wsum: bad argument");
     Group* g = nullptr;
     if (int rc = get_group(c, grp, &g)) return rc;
+    CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;
     g->wsum[com]  = wsum;
     g->valid[com] = 0;
     for (auto& e : c->cell_sorts) if (e->grp == grp) e->serial = 0;
@@ -560,6 +602,7 @@ extern "C" int b2a_submit_batch(b2a_ctx* c, int nframes, const float* x, const f
     if (c->field_pending) { CU(cudaEventSynchronize(c->ev_field)); c->field_pending = false; }
     // Everything launched so far read the current buffer; from here on the other one becomes current.  Its last readers
     // (two submits ago) are covered by ev_free, its last upload by ev_copied (which also frees its pinned geometry staging).
+    if (int rc = join_side(c)) return rc;   // side-stream kernels read the current buffer too
     CU(cudaEventRecord(c->ev_free[c->cur], c->stream));
     const int b = c->cur ^ 1;
     CU(cudaEventSynchronize(c->ev_copied[b]));
@@ -1131,20 +1174,24 @@ extern "C" int b2a_rdf_cells(b2a_ctx* c, int id, int mode)
 static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
 static float next_up(float v) { return std::nextafterf(v, INFINITY); }
 
-template <int IPT, int THREADS, bool CUBIC, bool PARANOID, int MODE>
+template <int IPT, int THREADS, bool CUBIC, bool PARANOID, int MODE, bool DBUF = false>
 static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid)
 {
-    auto kern = k3_rdf<IPT, THREADS, true, CUBIC, PARANOID, MODE>;
+    auto kern = k3_rdf<IPT, THREADS, true, CUBIC, PARANOID, MODE, DBUF>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, THREADS, smem, c->stream>>>(a.sortedA_view ? a.sortedA_view : a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
+    kern<<<grid, THREADS, smem, a.last_stream>>>(a.sortedA_view ? a.sortedA_view : a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
                                             a.d_slab_cnt, a.d_frames, p, cd, a.d_hist, a.d_hist + a.ndev);
     CU(cudaGetLastError());
     return B2A_OK;
 }
 
 template <int IPT, int MODE, int TH = 128>
-static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid, bool cubic)
+static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid, bool cubic, bool dbuf = false)
 {
+    if constexpr (MODE != 2)
+        if (dbuf && !a.paranoid)   // double-buffered j-tile (8 KB more shared memory: the caller checked that residency is unchanged)
+            return cubic ? launch_rdf<IPT, TH, true, false, MODE, true>(c, a, g0, g1, p, cd, smem + kTileJ * sizeof(int4), grid)
+                         : launch_rdf<IPT, TH, false, false, MODE, true>(c, a, g0, g1, p, cd, smem + kTileJ * sizeof(int4), grid);
     if (a.paranoid)
         return cubic ? launch_rdf<IPT, TH, true, true, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, true, MODE>(c, a, g0, g1, p, cd, smem, grid);
     return cubic ? launch_rdf<IPT, TH, true, false, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, false, MODE>(c, a, g0, g1, p, cd, smem, grid);
@@ -1225,7 +1272,7 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
 
 // Sorted-by-cell view of one group for the current batch, built on first use and shared afterwards (see CellSort).  `slab` is
 // the accumulator whose slab ids enter the key (its k3_slab_count has been queued), or nullptr for a plain cell sort.
-static int cell_sort(b2a_ctx* c, int grp, Group& g, int com, int bits, const Acc* slab, const RdfDev& p, CellSort** out)
+static int cell_sort(b2a_ctx* c, int grp, Group& g, int com, int bits, const Acc* slab, const RdfDev& p, CellSort** out, cudaStream_t stm)
 {
     const int      n     = g.nmol;
     const unsigned nkeys = (slab ? (unsigned)p.nslab : 1u) << (3 * bits);
@@ -1246,6 +1293,11 @@ static int cell_sort(b2a_ctx* c, int grp, Group& g, int com, int bits, const Acc
         if (slab) { cs->nbin = p.nbin; cs->dim = p.dim; cs->dim2 = p.dim2; cs->low = p.low; cs->up = p.up; cs->low2 = p.low2; cs->up2 = p.up2; }
     }
     *out = cs;
+    if ((size_t)n > cs->cap_n || nkeys > cs->cap_keys)
+    {   // about to replace arrays another stream may still read
+        if (int rc = join_side(c)) return rc;
+        CU(cudaStreamSynchronize(c->stream));
+    }
     if ((size_t)n > cs->cap_n)
     {
         cudaFree(cs->keys); cudaFree(cs->sorted); cs->keys = nullptr; cs->sorted = nullptr; cs->cap_n = 0; cs->serial = 0;
@@ -1259,16 +1311,23 @@ static int cell_sort(b2a_ctx* c, int grp, Group& g, int com, int bits, const Acc
         CU(cudaMalloc(&cs->cells, sizeof(unsigned) * 3 * (size_t)(nkeys + 1) * c->maxK));
         cs->cap_keys = nkeys;
     }
-    if (cs->serial == c->serial && cs->nkeys == nkeys) return B2A_OK;   // built for this batch already
+    if (cs->serial == c->serial && cs->nkeys == nkeys)
+    {   // built for this batch already -- possibly by another accumulator on another stream
+        if (cs->built_on != stm && cs->ready) CU(cudaStreamWaitEvent(stm, cs->ready, 0));
+        return B2A_OK;
+    }
     cs->nkeys = nkeys;
     const size_t sz = (size_t)(nkeys + 1) * c->maxK;
     unsigned *cnt = cs->cells, *st = cs->cells + sz, *cur = cs->cells + 2 * sz;
-    CU(cudaMemsetAsync(cs->cells, 0, sizeof(unsigned) * 3 * sz, c->stream));
+    CU(cudaMemsetAsync(cs->cells, 0, sizeof(unsigned) * 3 * sz, stm));
     dim3 grid((n + 255) / 256, c->nframes);
-    k3_cell_keys<<<grid, 256, 0, c->stream>>>(g.d_fix[com], slab ? slab->d_slab_id : nullptr, c->nframes, n, bits, nkeys, cs->keys, cnt);
-    k3_cell_scan<<<c->nframes, 1024, 0, c->stream>>>(cnt, nkeys, st);
-    k3_cell_scatter<<<grid, 256, 0, c->stream>>>(g.d_fix[com], cs->keys, c->nframes, n, nkeys, st, cur, cs->sorted);
+    k3_cell_keys<<<grid, 256, 0, stm>>>(g.d_fix[com], slab ? slab->d_slab_id : nullptr, c->nframes, n, bits, nkeys, cs->keys, cnt);
+    k3_cell_scan<<<c->nframes, 1024, 0, stm>>>(cnt, nkeys, st);
+    k3_cell_scatter<<<grid, 256, 0, stm>>>(g.d_fix[com], cs->keys, c->nframes, n, nkeys, st, cur, cs->sorted);
     CU(cudaGetLastError());
+    if (!cs->ready) CU(cudaEventCreateWithFlags(&cs->ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(cs->ready, stm));
+    cs->built_on = stm;
     cs->serial = c->serial;
     return B2A_OK;
 }
@@ -1281,6 +1340,30 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     if (int rc = get_group(c, s.grp1, &g1)) return rc;
     if (int rc = ensure_centers(c, *g0, s.com0, true)) return rc;
     if (int rc = ensure_centers(c, *g1, s.com1, true)) return rc;
+    // stream of this accumulation: the context stream, or -- in a context with several RDF accumulators -- the accumulator's own,
+    // forked here (the centres are queued) and joined by join_side()
+    cudaStream_t stm = c->stream;
+    {
+        int nrdf = 0;
+        for (auto& o : c->accs) if (o && o->kind == ACC_RDF) ++nrdf;
+        bool side = nrdf > 1;
+        if (const char* e = getenv("B2A_SIDE_STREAMS")) side = side && atoi(e) != 0;
+        if (side)
+        {
+            if (!a.side) CU(cudaStreamCreateWithFlags(&a.side, cudaStreamNonBlocking));
+            if (!a.ev_done) CU(cudaEventCreateWithFlags(&a.ev_done, cudaEventDisableTiming));
+            CU(cudaEventRecord(c->ev_fork, c->stream));
+            CU(cudaStreamWaitEvent(a.side, c->ev_fork, 0));
+            stm = a.side;
+        }
+    }
+    a.last_stream = stm;
+    struct Done   // whatever happens below, what was queued on the side stream is joined later
+    {
+        Acc& a; cudaStream_t stm; b2a_ctx* c;
+        ~Done() { if (stm != c->stream) { cudaEventRecord(a.ev_done, stm); a.side_pending = true; } }
+    };
+    Done done{ a, stm, c };
 
     RdfDev p{};
     p.n0 = g0->nmol; p.n1 = g1->nmol; p.nbin = s.nbin; p.nslab = s.nbin + 1; p.Rbin = s.Rbin;
@@ -1293,6 +1376,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     p.rbin_bits = kMagicBits + (unsigned)s.Rbin;
     if (g0->nmol > a.alloc_n0)
     {   // the group was redefined with more molecules after b2a_rdf_create: the per-molecule scratch must follow
+        if (a.side) CU(cudaStreamSynchronize(a.side));
         CU(cudaStreamSynchronize(c->stream));
         if (int rc = regrow(&a.d_slab_id, (size_t)g0->nmol * c->maxK)) return rc;
         if (int rc = regrow(&a.d_sortedA, (size_t)g0->nmol * c->maxK)) return rc;
@@ -1339,8 +1423,11 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         fr.r2max = (float)(r_units * r_units);
         for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
     }
-    CU(cudaMemcpyAsync(a.d_frames, h_frames, sizeof(RdfFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(a.ring.ev[slot], c->stream));
+    static_assert(sizeof(RdfFrame) % 4 == 0, "RdfFrame is fetched word by word");
+    k_fetch_words<<<1, 256, 0, stm>>>(reinterpret_cast<unsigned*>(a.d_frames), reinterpret_cast<const unsigned*>(h_frames),
+                                            (int)(sizeof(RdfFrame) / 4) * c->nframes);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(a.ring.ev[slot], stm));
 
     // Shared histogram: pairs beyond the cut-off are clamped into ONE trash bin (bin Rbin).  Measured on B200
     // (profiles/r01_k3_tuning.md): faster than an oversize histogram -- the ~48 % of lanes beyond Rm hit a single address
@@ -1352,19 +1439,19 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
 
     // prep: slab ids and counts
     const int nslab = p.nslab;
-    CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, c->stream));
+    CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, stm));
     int  bits = 0, reach[3] = { 0, 0, 0 };
     const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, kCellIPT * kCellThreads, nullptr, true);
     CellDev cd{};
     {
-        Timed tm(c, 1);
+        Timed tm(c, 1, stm);
         dim3 grid((p.n0 + 255) / 256, c->nframes);
-        k3_slab_count<<<grid, 256, sizeof(unsigned) * nslab, c->stream>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
+        k3_slab_count<<<grid, 256, sizeof(unsigned) * nslab, stm>>>(g0->d_cen[s.com0], c->nframes, p, a.d_slab_id, a.d_slab_cnt);
         CU(cudaGetLastError());
         a.sortedA_view = nullptr;
         if (!cells)
         {
-            k3_slab_scatter<<<grid, 256, sizeof(unsigned) * 3 * nslab, c->stream>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
+            k3_slab_scatter<<<grid, 256, sizeof(unsigned) * 3 * nslab, stm>>>(g0->d_fix[s.com0], a.d_slab_id, c->nframes, p.n0, nslab,
                                                                                  a.d_slab_cnt, a.d_slab_cnt + (size_t)nslab * c->maxK, a.d_sortedA);
             CU(cudaGetLastError());
         }
@@ -1372,8 +1459,8 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         {
             // both groups sorted by cell: shared with the other accumulators of this batch (cell_sort)
             CellSort *sA = nullptr, *sB = nullptr;
-            if (int rc = cell_sort(c, s.grp0, *g0, s.com0, bits, &a, p, &sA)) return rc;
-            if (int rc = cell_sort(c, s.grp1, *g1, s.com1, bits, nullptr, p, &sB)) return rc;
+            if (int rc = cell_sort(c, s.grp0, *g0, s.com0, bits, &a, p, &sA, stm)) return rc;
+            if (int rc = cell_sort(c, s.grp1, *g1, s.com1, bits, nullptr, p, &sB, stm)) return rc;
             const unsigned  nkA = sA->nkeys, nkB = sB->nkeys;
             const unsigned *stA = sA->starts(c->maxK), *stB = sB->starts(c->maxK);
             a.sortedA_view = sA->sorted;
@@ -1382,7 +1469,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         }
     }
 
-    Timed tm(c, 2);
+    Timed tm(c, 2, stm);
     if (cells)
     {
         RdfDev pc = p;
@@ -1393,6 +1480,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         return dispatch_rdf<kCellIPT, 2, kCellThreads>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes), cubic);
     }
     constexpr int TI = 8 * 128;   // TI molecules of one slab per block
+    bool          dbuf = false;
     {
         // full mode: j split so that the grid covers the machine several times
         const int max_tiles = (p.n0 + TI - 1) / TI + std::min(nslab, p.n0);
@@ -1402,14 +1490,37 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         // config 3 (31 i-tiles x 8 frames): 4.4 waves -> 0.75 of FP32 issue, 7 -> 0.78, 10.4 -> 0.79; config 2 full
         // evaluation: 5.4 waves -> 0.85, 10.7 -> 0.87.
         const int resident = std::max(1, std::min(6, (int)((227 * 1024) / (smem + 1024))));   // 80 registers x 128 threads: 6
+        // double-buffered j-tile only where its 8 KB do not cost a resident block
+        dbuf = std::min(6, (int)((227 * 1024) / (smem + kTileJ * sizeof(int4) + 1024))) >= resident;
+        if (const char* e = getenv("B2A_K3_DBUF")) dbuf = atoi(e) != 0;
         int       waves    = 10;
         if (const char* e = getenv("B2A_K3_WAVES")) waves = std::max(1, atoi(e));
         int       jsplit   = std::max(1, (c->sm_count * resident * waves + itiles * c->nframes - 1) / (itiles * c->nframes));
         jsplit             = std::min(jsplit, std::max(1, p.n1 / (2 * kTileJ)));
         p.jchunk           = (p.n1 + jsplit - 1) / jsplit;
         p.jchunk           = ((p.jchunk + kTileJ - 1) / kTileJ) * kTileJ;
+        if (!getenv("B2A_K3_WAVES"))
+        {
+            // Tail model: the grid runs as blocks / slots rounds of `slots` resident blocks, each as long as one block (~ jchunk + a
+            // fixed cost for zeroing and flushing the shared histogram, worth ~100 j); blocks do not finish in lockstep, so the
+            // machine drains over about half a block time, and with very few rounds a nearly empty last round costs a full one.
+            // Among the chunk sizes that give at most 40 rounds take the one with the least total.
+            const double slots = (double)c->sm_count * resident, fixed = 100.0;
+            double       best  = 1e300;
+            int          bestj = p.jchunk;
+            for (int jc = 2 * kTileJ; jc <= std::max(2 * kTileJ, ((p.n1 + kTileJ - 1) / kTileJ) * kTileJ); jc += kTileJ)
+            {
+                const double js     = (double)((p.n1 + jc - 1) / jc);
+                const double exact  = itiles * js * c->nframes / slots;
+                if (exact > 40.0 && jc < p.n1) continue;             // too many tiny blocks
+                const double rounds = std::max(exact + 0.5, exact < 4.0 ? std::ceil(exact) : 0.0);
+                const double cost   = rounds * (jc + fixed);
+                if (cost < best) { best = cost; bestj = jc; }
+            }
+            p.jchunk = bestj;
+        }
         p.jsplit           = (p.n1 + p.jchunk - 1) / p.jchunk;
-        if (int rc = dispatch_rdf<8, 0>(c, a, *g0, *g1, p, cd, smem, dim3(max_tiles, p.jsplit, c->nframes), cubic)) return rc;
+        if (int rc = dispatch_rdf<8, 0>(c, a, *g0, *g1, p, cd, smem, dim3(max_tiles, p.jsplit, c->nframes), cubic, dbuf)) return rc;
     }
     if (p.sym_enabled)
     {
@@ -1420,7 +1531,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         const int T = (p.n0 + TI - 1) / TI;
         long long items = 0;
         for (int t = 0; t < T; ++t) items += 1 + (std::max(0, p.n0 - (t + 1) * TI) + ps.jchunk - 1) / ps.jchunk;
-        if (int rc = dispatch_rdf<8, 1>(c, a, *g0, *g1, ps, cd, smem, dim3((unsigned)items, 1, c->nframes), cubic)) return rc;
+        if (int rc = dispatch_rdf<8, 1>(c, a, *g0, *g1, ps, cd, smem, dim3((unsigned)items, 1, c->nframes), cubic, dbuf)) return rc;
     }
     return B2A_OK;
 }
@@ -1515,6 +1626,15 @@ static int accumulate_coord(b2a_ctx* c, Acc& a);
 
 __global__ void k_add_frames(unsigned long long* stats, unsigned long long n) { stats[0] += n; }
 
+// Per-frame constants travel host -> device through a KERNEL that reads the pinned slot over the bus (pinned memory is mapped into
+// the device's address space), not through cudaMemcpyAsync: a copy would queue on the H2D copy engine BEHIND the upload of the
+// next frame batch (hundreds of MB on the copy stream), and the pair kernel that needs these few hundred bytes would wait for
+// all of it (measured: 3 ms of a 98 ms step on config 2, 7 of 27 ms on config 3).
+__global__ void k_fetch_words(unsigned* __restrict__ dst, const unsigned* __restrict__ src_pinned, int nwords)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += gridDim.x * blockDim.x) dst[i] = src_pinned[i];
+}
+
 extern "C" int b2a_accumulate(b2a_ctx* c, int id)
 {
     TEAM_CUR(c, b2a_accumulate(m, id));
@@ -1532,8 +1652,17 @@ extern "C" int b2a_accumulate(b2a_ctx* c, int id)
         case ACC_REGION: rc = accumulate_region(c, *a); break;
     }
     if (rc) return rc;
-    k_add_frames<<<1, 1, 0, c->stream>>>(a->d_hist + a->ndev, (unsigned long long)c->nframes);
-    CU(cudaGetLastError());
+    if (a->kind == ACC_RDF && a->last_stream && a->last_stream != c->stream)
+    {   // the accumulation went to the accumulator's side stream: the frame counter follows it (before the join event)
+        k_add_frames<<<1, 1, 0, a->last_stream>>>(a->d_hist + a->ndev, (unsigned long long)c->nframes);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(a->ev_done, a->last_stream));
+    }
+    else
+    {
+        k_add_frames<<<1, 1, 0, c->stream>>>(a->d_hist + a->ndev, (unsigned long long)c->nframes);
+        CU(cudaGetLastError());
+    }
     a->epoch++;
     return B2A_OK;
 }
@@ -1544,6 +1673,7 @@ extern "C" int b2a_acc_reset(b2a_ctx* c, int id)
     Acc* a = nullptr;
     if (int rc = get_acc(c, id, &a)) return rc;
     CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;
     CU(cudaMemsetAsync(a->d_hist, 0, sizeof(unsigned long long) * (a->ndev + B2A_STAT_NSLOTS), c->stream));
     a->epoch++;
     a->series_len = 0;
@@ -1590,6 +1720,7 @@ extern "C" int b2a_acc_read(b2a_ctx* c, int id, uint64_t* counts, uint64_t* stat
     if (int rc = get_acc(c, id, &a)) return rc;
     if (!counts) return fail(B2A_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;
     // after b2a_finalize (and until the next accumulate / reset) the merged totals are what a read returns
     const unsigned long long* src = (a->d_merged && a->merged_epoch == a->epoch) ? a->d_merged : a->d_hist;
     std::vector<unsigned long long> h(a->ndev + B2A_STAT_NSLOTS);
@@ -1641,6 +1772,8 @@ extern "C" int b2a_invalidate(b2a_ctx* c)
 {
     TEAM_ALL(c, b2a_invalidate(m));
     if (!c) return fail(B2A_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;   // the centre caches and sorted views about to be rebuilt may still be read
     c->serial++;
     return B2A_OK;
 }
@@ -1678,6 +1811,7 @@ extern "C" int b2a_timing_read(b2a_ctx* c, double* ms, long long* launches)
         return B2A_OK;
     }
     CU(cudaSetDevice(c->device));
+    if (int rc = join_side(c)) return rc;
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaStreamSynchronize(c->copy_stream));
     for (auto& s : c->spans)
@@ -1972,7 +2106,10 @@ static int accumulate_coord(b2a_ctx* c, Acc& a)
         fr.t_small = next_up((float)(rs * rs * (1.0 + erel)));
         for (int k = 0; k < 3; ++k) fr.L[k] = g.L[k];
     }
-    CU(cudaMemcpyAsync(a.d_cframes, h_cframes, sizeof(CoordFrame) * c->nframes, cudaMemcpyHostToDevice, c->stream));
+    static_assert(sizeof(CoordFrame) % 4 == 0, "CoordFrame is fetched word by word");
+    k_fetch_words<<<1, 256, 0, c->stream>>>(reinterpret_cast<unsigned*>(a.d_cframes), reinterpret_cast<const unsigned*>(h_cframes),
+                                            (int)(sizeof(CoordFrame) / 4) * c->nframes);
+    CU(cudaGetLastError());
     CU(cudaEventRecord(a.ring.ev[slot], c->stream));
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)c->maxK, c->stream));
     CU(cudaMemsetAsync(a.d_cnt, 0, sizeof(int) * (size_t)n0 * c->nframes, c->stream));

@@ -46,6 +46,9 @@ constexpr int      kSubJ      = B2A_K3_SUBJ;   // j-iterations between queue dra
 #ifndef B2A_K3_PACKED
 #define B2A_K3_PACKED 1
 #endif
+#ifndef B2A_EXP_NOKMIN
+#define B2A_EXP_NOKMIN 0   // experiment only (WRONG counts in the lowest bins): upper bound of what removing the low-bin test could save
+#endif
 constexpr bool     kPacked    = B2A_K3_PACKED != 0;   // issue the FP32 chain of two pairs as packed f32x2 instructions
 
 struct RdfFrame   // per frame (the box may change frame to frame); host-computed
@@ -353,7 +356,10 @@ struct CellDev   // cell mode parameters (by value)
 //                 columns, restricted to the cells within reach of the tile's own z span
 // (launch bound: 6 resident blocks of the 8 x 128 tile = 80 registers instead of the 96 the compiler takes unconstrained, 36 bytes
 //  of spills: 634.7 -> 652.4 frames/s on config 2; 7 blocks = 72 registers spill into the hot loop: 603.7)
-template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, int MODE>
+// DBUF: the j-tile is double-buffered -- tile t+1 is copied global -> shared asynchronously (cp.async, LDGSTS) while tile t is
+// evaluated, one barrier per tile instead of two.  +1.4 % on config 2 (long j ranges); it costs 8 KB of shared memory, so the
+// host selects it only when the resident-block count is unchanged (profiles/r02_k3_tuning.md: config 3 / 5 lose 2.7 % with it).
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, int MODE, bool DBUF = false>
 __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
                                                   const double* __restrict__ cenA, const double* __restrict__ cenB,
                                                   const unsigned* __restrict__ slab_cnt,
@@ -363,9 +369,11 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
 {
     constexpr int  TI  = IPT * THREADS;
     constexpr bool SYM = MODE == 1;
+    constexpr bool kDbuf = DBUF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    int4*     sj    = reinterpret_cast<int4*>(smem_raw);                                   // kTileJ
-    unsigned* queue = reinterpret_cast<unsigned*>(smem_raw + kTileJ * sizeof(int4));       // kQueueCap
+    int4*     sj    = reinterpret_cast<int4*>(smem_raw);                                   // kTileJ (x 2 when double-buffered)
+    int4*     sjbuf = sj;
+    unsigned* queue = reinterpret_cast<unsigned*>(smem_raw + (kDbuf ? 2 : 1) * kTileJ * sizeof(int4));       // kQueueCap
     unsigned* hist  = queue + kQueueCap + 4;                                               // hist[-1] = trash
     __shared__ unsigned q_count[2];
     __shared__ RdfBlock blk;
@@ -486,12 +494,32 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
     // stream the j-molecules [ja, jb) of B against the i-molecules currently held in registers
     auto process_range = [&](int ja, int jb) {
         const bool partial = tcount < TI;
+        auto prefetch = [&](int4* dst, int jt) {   // kDbuf: asynchronous global -> shared copy of one j-tile (LDGSTS, 16 bytes per thread and request)
+            const int cnt = min(kTileJ, jb - jt);
+            for (int t = threadIdx.x; t < cnt; t += THREADS)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + t)), "l"(B + jt + t) : "memory");
+        };
+        if (kDbuf && ja < jb)
+        {
+            __syncthreads();            // the previous range's last drain may still read the buffer about to be refilled
+            sj = sjbuf;
+            prefetch(sj, ja);
+        }
         for (int jt = ja; jt < jb; jt += kTileJ)
         {
-            __syncthreads();
             const int cnt = min(kTileJ, jb - jt);
-            for (int t = threadIdx.x; t < cnt; t += THREADS) sj[t] = B[jt + t];
-            __syncthreads();
+            if (kDbuf)
+            {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();        // tile jt is visible to everybody; everybody has left tile jt - kTileJ
+                if (jt + kTileJ < jb) prefetch(sj == sjbuf ? sjbuf + kTileJ : sjbuf, jt + kTileJ);   // lands while this tile is evaluated
+            }
+            else
+            {
+                __syncthreads();
+                for (int t = threadIdx.x; t < cnt; t += THREADS) sj[t] = B[jt + t];
+                __syncthreads();
+            }
             for (int js = 0; js < cnt; js += kSubJ, ++sub)
             {
                 const int je = min(cnt, js + kSubJ);
@@ -514,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                                 asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1a * 4u + cb_ok) : "memory");
                                 asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(k1b * 4u + cb_ok) : "memory");
                                 dacc += (k2a - k1a) + (k2b - k1b);
-                                kmin = min(kmin, min(k1a, k1b));
+                                if (!B2A_EXP_NOKMIN) kmin = min(kmin, min(k1a, k1b));
                             }
                         }
                         else
@@ -543,22 +571,42 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                 }
                 else
                 {
-                    // partial tile: lanes beyond tcount add into the trash word only
+                    // partial tile (the last tile of a slab / column): same packed arithmetic; i-slots beyond tcount add into the
+                    // trash word and never raise a candidate
+                    bool okq[IPT];
+#pragma unroll
+                    for (int q = 0; q < IPT; ++q) okq[q] = (int)(threadIdx.x + q * THREADS) < tcount;
 #pragma unroll 1
                     for (int j = js; j < je; ++j)
                     {
                         const int4 pj   = sj[j];
                         unsigned   dacc = 0, kmin = 0xffffffffu;
-#pragma unroll
-                        for (int q = 0; q < IPT; ++q)
+                        if (IPT % 2 == 0 && kPacked)
                         {
-                            const bool ok = (int)(threadIdx.x + q * THREADS) < tcount;
-                            unsigned   k1, k2;
-                            pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
-                            const unsigned addr = ok ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
-                            asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-                            dacc += ok ? (k2 - k1) : 0u;
-                            kmin = ok ? min(kmin, k1) : kmin;
+#pragma unroll
+                            for (int q = 0; q < IPT; q += 2)
+                            {
+                                unsigned k1a, k2a, k1b, k2b;
+                                pair_bins2<CLAMP, CUBIC>(xi[q], yi[q], zi[q], xi[q + 1], yi[q + 1], zi[q + 1], pj, s_lo2, s_hi2, magic2, ay2, az2,
+                                                         r2max, k1a, k2a, k1b, k2b);
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(okq[q] ? (k1a * 4u + cb_ok) : (hist_sa - 4u)) : "memory");
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(okq[q + 1] ? (k1b * 4u + cb_ok) : (hist_sa - 4u)) : "memory");
+                                dacc += (okq[q] ? (k2a - k1a) : 0u) + (okq[q + 1] ? (k2b - k1b) : 0u);
+                                kmin = min(kmin, min(okq[q] ? k1a : 0xffffffffu, okq[q + 1] ? k1b : 0xffffffffu));
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int q = 0; q < IPT; ++q)
+                            {
+                                unsigned k1, k2;
+                                pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
+                                const unsigned addr = okq[q] ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                                dacc += okq[q] ? (k2 - k1) : 0u;
+                                kmin = okq[q] ? min(kmin, k1) : kmin;
+                            }
                         }
                         if (PARANOID || dacc != 0 || kmin <= lowk)
                         {
@@ -584,6 +632,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                 if (threadIdx.x == 0) q_count[(sub + 1) & 1] = 0;   // the other counter was drained one sub-tile ago
                 __syncthreads();
             }
+            if (kDbuf) sj = sj == sjbuf ? sjbuf + kTileJ : sjbuf;
         }
         npairs += (unsigned long long)tcount * (unsigned long long)(jb > ja ? jb - ja : 0);
     };

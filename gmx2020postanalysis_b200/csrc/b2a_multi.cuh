@@ -326,6 +326,11 @@ extern "C" int b2a_finalize(b2a_ctx* c)
     const bool collective = devs[0]->comm != nullptr;
     if (!collective && !c->same_device_team && devs.size() > 1) return fail(B2A_ERR_STATE, "b2a_finalize: no communicator");
     for (b2a_ctx* m : devs)
+    {   // accumulators with work on side streams: the merge is ordered behind them
+        CU(cudaSetDevice(m->device));
+        if (int rc = join_side(m)) return rc;
+    }
+    for (b2a_ctx* m : devs)
         for (auto& a : m->accs)
             if (a && !a->d_merged)
             {

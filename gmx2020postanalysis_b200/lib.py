@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2a.so")
+LIB_PATH = os.environ.get("B2A_LIB") or os.path.join(_HERE, "libb2a.so")   # B2A_LIB: an experimental build (A/B runs)
 _lib = None
 _P = C.c_void_p
 
@@ -28,7 +28,7 @@ SYMBOLS = [
     "b2a_acc_device_ptr", "b2a_acc_read", "b2a_rdf_normalise", "b2a_rdf_tune", "b2a_rdf_cells", "b2a_acc_fast", "b2a_invalidate", "b2a_timing_enable",
     "b2a_timing_read",
     "b2a_create_multi", "b2a_num_devices", "b2a_member", "b2a_current_device", "b2a_finalize", "b2a_comm_unique_id", "b2a_comm_init",
-    "b2a_set_frame_base", "b2a_series_size", "b2a_series_read", "b2a_acc_public_size", "b2a_centers_device", "b2a_acc_also_centers", "b2a_set_host_buffers",
+    "b2a_set_frame_base", "b2a_series_size", "b2a_series_read", "b2a_acc_public_size", "b2a_centers_device", "b2a_acc_also_centers", "b2a_set_host_buffers", "b2a_join",
 ]
 
 
@@ -139,6 +139,7 @@ def load():
         L.b2a_centers_device.argtypes = [_P, C.c_int, C.c_int, C.POINTER(_P)]
         L.b2a_acc_also_centers.argtypes = [_P, C.c_int, C.c_int]
         L.b2a_set_host_buffers.argtypes = [_P, C.c_int]
+        L.b2a_join.argtypes = [_P]
         _lib = L
     return _lib
 
@@ -234,6 +235,10 @@ class Context:
 
     def sync(self):
         check(self.L.b2a_sync(self._h))
+
+    def join(self):
+        """Order the context stream behind the accumulators' internal side streams (asynchronous)."""
+        check(self.L.b2a_join(self._h))
 
     def set_group(self, grp, index, napm, mass, charge):
         idx = np.ascontiguousarray(index, dtype=np.int32)

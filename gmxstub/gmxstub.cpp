@@ -774,9 +774,27 @@ bool deliver(t_trxstatus* st, t_trxframe* fr)
 }
 } // namespace
 
+namespace
+{
+/* statuses handed out and not yet closed: a caller that passes one of them to read_first_frame again (two-pass programs restart
+ * the trajectory that way) gets the old one closed instead of leaked -- file handle and mapping; an uninitialised pointer
+ * (GROMACS callers declare `t_trxstatus* status;`) is simply not found here */
+std::vector<t_trxstatus*>& open_statuses()
+{
+    static std::vector<t_trxstatus*> v;
+    return v;
+}
+} // namespace
+
 bool read_first_frame(const gmx_output_env_t* /*oenv*/, t_trxstatus** status, const char* fn, t_trxframe* fr, int flags)
 {
+    {
+        auto& v = open_statuses();
+        for (size_t k = 0; k < v.size(); ++k)
+            if (status && v[k] == *status) { close_trx(*status); break; }   // close_trx takes it out of the list
+    }
     t_trxstatus* st = open_trx(fn);
+    open_statuses().push_back(st);
     st->want        = flags;
     *status         = st;
     rvec* keep_x = fr->x; rvec* keep_v = fr->v; rvec* keep_f = fr->f;
@@ -796,6 +814,11 @@ bool read_next_frame(const gmx_output_env_t* /*oenv*/, t_trxstatus* status, t_tr
 void close_trx(t_trxstatus* status)
 {
     if (!status) return;
+    {
+        auto& v = open_statuses();
+        for (size_t k = 0; k < v.size(); ++k)
+            if (v[k] == status) { v.erase(v.begin() + (long)k); break; }
+    }
     if (status->map) munmap(const_cast<unsigned char*>(status->map), status->map_size);
     if (status->fp) std::fclose(status->fp);
     delete status;

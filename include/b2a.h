@@ -77,7 +77,13 @@ int         b2a_device_count(void);    /* 0 if no CUDA device is visible */
 int  b2a_create(b2a_ctx** ctx, int device, int natoms, int max_frames);
 void b2a_destroy(b2a_ctx* ctx);
 int  b2a_sync(b2a_ctx* ctx);
-void* b2a_stream(b2a_ctx* ctx);        /* the cudaStream_t all work is queued on */
+void* b2a_stream(b2a_ctx* ctx);        /* the cudaStream_t all work is queued on (but see b2a_join) */
+/* In a context that holds several RDF accumulators (a sweep over group pairs) each of them queues its kernels on an internal
+ * stream of its own, forked from the context stream, so that the short launches of small group pairs run beside the long ones.
+ * b2a_join makes the context stream wait for all of that (asynchronously: nothing blocks on the host).  Every call that
+ * synchronises or starts a new batch implies it (b2a_sync, b2a_acc_read, b2a_acc_reset, b2a_submit_batch, b2a_invalidate,
+ * b2a_finalize); only callers that order their OWN device work after b2a_stream() need to call it.                        */
+int  b2a_join(b2a_ctx* ctx);
 
 /* ---- several GPUs behind ONE context -------------------------------------------------------------
  * ndev member contexts, one per entry of devices[] (NULL = devices 0..ndev-1).  The returned LEADER accepts every call
