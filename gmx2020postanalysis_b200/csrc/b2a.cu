@@ -86,7 +86,7 @@ struct Group
     std::vector<int> h_index;
     // heterogeneous molecule sizes (GmxHandleFull): CSR offsets, per-atom weights, per-molecule totals
     bool      csr = false;
-    int       max_napm = 0;
+    int       max_napm = 0, min_napm = 0;
     int*      d_off = nullptr; int* d_mol_of = nullptr;
     double*   d_wfull[4] = { nullptr, nullptr, nullptr, nullptr };
     DivConst* d_div[4]   = { nullptr, nullptr, nullptr, nullptr };
@@ -527,6 +527,8 @@ extern "C" int b2a_set_group_full(b2a_ctx* c, int grp, const int* index, int ngx
     free_group(g);
     for (auto& e : c->cell_sorts) if (e->grp == grp) e->serial = 0;   // sorted views of the old group are stale
     g.ngx = ngx; g.napm = 0; g.nmol = nmol; g.csr = true; g.max_napm = maxn;
+    g.min_napm = maxn;
+    for (int i = 0; i < nmol; ++i) g.min_napm = std::min(g.min_napm, napm[i]);
     g.h_index.assign(index, index + ngx);
     CU(cudaMalloc(&g.d_index, sizeof(int) * ngx));
     CU(cudaMemcpy(g.d_index, index, sizeof(int) * ngx, cudaMemcpyHostToDevice));
@@ -1499,26 +1501,6 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         jsplit             = std::min(jsplit, std::max(1, p.n1 / (2 * kTileJ)));
         p.jchunk           = (p.n1 + jsplit - 1) / jsplit;
         p.jchunk           = ((p.jchunk + kTileJ - 1) / kTileJ) * kTileJ;
-        if (!getenv("B2A_K3_WAVES"))
-        {
-            // Tail model: the grid runs as blocks / slots rounds of `slots` resident blocks, each as long as one block (~ jchunk + a
-            // fixed cost for zeroing and flushing the shared histogram, worth ~100 j); blocks do not finish in lockstep, so the
-            // machine drains over about half a block time, and with very few rounds a nearly empty last round costs a full one.
-            // Among the chunk sizes that give at most 40 rounds take the one with the least total.
-            const double slots = (double)c->sm_count * resident, fixed = 100.0;
-            double       best  = 1e300;
-            int          bestj = p.jchunk;
-            for (int jc = 2 * kTileJ; jc <= std::max(2 * kTileJ, ((p.n1 + kTileJ - 1) / kTileJ) * kTileJ); jc += kTileJ)
-            {
-                const double js     = (double)((p.n1 + jc - 1) / jc);
-                const double exact  = itiles * js * c->nframes / slots;
-                if (exact > 40.0 && jc < p.n1) continue;             // too many tiny blocks
-                const double rounds = std::max(exact + 0.5, exact < 4.0 ? std::ceil(exact) : 0.0);
-                const double cost   = rounds * (jc + fixed);
-                if (cost < best) { best = cost; bestj = jc; }
-            }
-            p.jchunk = bestj;
-        }
         p.jsplit           = (p.n1 + p.jchunk - 1) / p.jchunk;
         if (int rc = dispatch_rdf<8, 0>(c, a, *g0, *g1, p, cd, smem, dim3(max_tiles, p.jsplit, c->nframes), cubic, dbuf)) return rc;
     }
@@ -1835,9 +1817,10 @@ extern "C" int b2a_orient_create(b2a_ctx* c, const b2a_orient_spec* s, int* id)
     Group* g = nullptr;
     if (int rc = get_group(c, s->grp, &g)) return rc;
     if (s->DIMN < 0 || s->DIMN > 2 || s->DIMNOrient < 0 || s->DIMNOrient > 2) return fail(B2A_ERR_ARG, "orient: dim out of range");
-    if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "orientation histogram on a heterogeneous (GmxHandleFull) group is not implemented");
-    if (s->tp1 < 1 || s->tp2 < 1 || s->tp3 < 1 || s->tp1 > g->napm || s->tp2 > g->napm || s->tp3 > g->napm)
-        return fail(B2A_ERR_ARG, "orient: tp1..3 must lie in 1..napm(%d)", g->napm);
+    // heterogeneous (GmxHandleFull) group: every molecule must own the three vector atoms
+    const int napm_lim = g->csr ? g->min_napm : g->napm;
+    if (s->tp1 < 1 || s->tp2 < 1 || s->tp3 < 1 || s->tp1 > napm_lim || s->tp2 > napm_lim || s->tp3 > napm_lim)
+        return fail(B2A_ERR_ARG, "orient: tp1..3 must lie in 1..napm(%d)", napm_lim);
     if (s->nAngle <= 0 || s->nAngle > 180) return fail(B2A_ERR_ARG, "orient: nAngle must be 1..180 (dAngle = 180 / nAngle is integer division)");
     if (s->method != 1 && s->method != 2) return fail(B2A_ERR_ARG, "orient: method must be 1 or 2");
     if (s->com < 0 || s->com > 3) return fail(B2A_ERR_ARG, "com out of range");
@@ -1944,7 +1927,6 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
     const b2a_orient_spec& s = a.ori;
     Group* g = nullptr;
     if (int rc = get_group(c, s.grp, &g)) return rc;
-    if (g->csr) return fail(B2A_ERR_UNSUPPORTED, "orientation histogram on a heterogeneous (GmxHandleFull) group is not implemented");
     OrientDev d{};
     d.DIMN = s.DIMN; d.nAngle = s.nAngle; d.nbin1 = a.nbin1; d.tp1 = s.tp1 - 1; d.tp2 = s.tp2 - 1; d.tp3 = s.tp3 - 1;
     d.DIMNOrient = s.DIMNOrient; d.method = s.method;
@@ -1954,6 +1936,19 @@ static int accumulate_orient(b2a_ctx* c, Acc& a)
     const size_t hist_words = (size_t)a.nbin1 * s.nAngle + a.nbin1;
     const int    smem_bins  = hist_words <= 24000 ? (int)hist_words : 0;
     int          M = 0;
+    if (g->csr)
+    {
+        // heterogeneous molecule sizes: literal FP64 per molecule with its own atom count, weights and divisor
+        const size_t smem = sizeof(double) * (s.nAngle + 1 + a.nbin1 + 2) + sizeof(float) * ((s.nAngle + 2) & ~1) + sizeof(unsigned) * smem_bins;
+        CU(cudaFuncSetAttribute(k4_orient_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const dim3 blocks((g->nmol + threads - 1) / threads, (c->nframes + kFramesPerBlock - 1) / kFramesPerBlock);
+        Timed      tm(c, 4);
+        k4_orient_csr<<<blocks, threads, smem, c->stream>>>(c->d_x, (size_t)c->natoms * 3, c->nframes, g->d_index, g->d_off, g->nmol, g->d_wfull[s.com],
+                                                            g->d_div[s.com], c->d_geom, d, a.d_cosedge, a.d_fedge, a.d_stab, a.d_hist, a.d_hist + a.ndev,
+                                                            smem_bins);
+        CU(cudaGetLastError());
+        return B2A_OK;
+    }
     if (stream_block(*g, &M))
     {
         Timed      tm(c, 4);

@@ -128,6 +128,63 @@ __device__ __forceinline__ void orient_molecule(const float* p, int napm, const 
     cell_a = meZ + lo * d.nbin1;
 }
 
+// Heterogeneous molecule sizes (GmxHandleFull groups, reference include/itp/gmx_bits/gmx_handle_full.ipp:115-199): the same
+// literal FP64 evaluation per molecule, with the molecule's own atom count, weights (wfull + off[i]) and divisor (div[i]).
+// The reference has no orientation program on GmxHandleFull; this completes the accumulator set for such groups.
+__global__ void __launch_bounds__(256) k4_orient_csr(const float* __restrict__ x, size_t frame_stride, int nframes,
+                                                     const int* __restrict__ index, const int* __restrict__ off, int nmol,
+                                                     const double* __restrict__ wfull, const DivConst* __restrict__ div,
+                                                     const FrameGeom* __restrict__ geom, OrientDev d,
+                                                     const double* __restrict__ cosedge, const float* __restrict__ fedge_g,
+                                                     const double* __restrict__ stab_g,
+                                                     unsigned long long* __restrict__ hist,
+                                                     unsigned long long* __restrict__ stats, int smem_bins)
+{
+    extern __shared__ double sm4c[];
+    double*   sedge = sm4c;                   // nAngle + 1
+    double*   stab  = sedge + d.nAngle + 1;   // nbin1 + 2
+    float*    fedge = reinterpret_cast<float*>(stab + d.nbin1 + 2);   // nAngle + 1 (+1 pad)
+    unsigned* shist = reinterpret_cast<unsigned*>(fedge + ((d.nAngle + 2) & ~1));
+    for (int j = threadIdx.x; j <= d.nAngle; j += blockDim.x) { sedge[j] = cosedge[j]; fedge[j] = fedge_g[j]; }
+    for (int j = threadIdx.x; j < d.nbin1 + 2; j += blockDim.x) stab[j] = stab_g[j];
+    const OrientTabs tb{ sedge, fedge, stab };
+    for (int b = threadIdx.x; b < smem_bins; b += blockDim.x) shist[b] = 0;
+    __syncthreads();
+    const int  ncells   = d.nbin1 * d.nAngle;
+    const bool use_smem = smem_bins >= ncells + d.nbin1;
+    unsigned   ndrop = 0, nsel = 0;
+    const int  i  = blockIdx.x * blockDim.x + threadIdx.x;
+    const int  f0 = blockIdx.y * kFramesPerBlock, f1 = min(nframes, f0 + kFramesPerBlock);
+    if (i < nmol)
+    {
+        const int      o0 = __ldg(off + i), na = __ldg(off + i + 1) - o0;
+        const size_t   moff = (size_t)__ldg(index + o0) * 3;   // atoms are molN + j (full.ipp:187)
+        const DivConst dv = div[i];
+        for (int f = f0; f < f1; ++f)
+        {
+            int cz, ca;
+            const FrameGeom g = geom[f];
+            orient_molecule<false>(x + (size_t)f * frame_stride + moff, na, wfull + o0, dv, g, d, tb, cz, ca, nsel, ndrop);
+            if (cz >= 0) { if (use_smem) atomicAdd(&shist[cz], 1u); else atomicAdd(&hist[cz], 1ull); }
+            if (ca >= 0) { if (use_smem) atomicAdd(&shist[ca], 1u); else atomicAdd(&hist[ca], 1ull); }
+        }
+    }
+    __syncthreads();
+    if (use_smem)
+        for (int b = threadIdx.x; b < ncells + d.nbin1; b += blockDim.x)
+            if (shist[b]) atomicAdd(&hist[b], (unsigned long long)shist[b]);
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        ndrop += __shfl_xor_sync(0xffffffffu, ndrop, o);
+        nsel += __shfl_xor_sync(0xffffffffu, nsel, o);
+    }
+    if ((threadIdx.x & 31) == 0)
+    {
+        if (ndrop) atomicAdd(&stats[1], (unsigned long long)ndrop);
+        if (nsel) atomicAdd(&stats[4], (unsigned long long)nsel);
+    }
+}
+
 // direct-load kernel (index group not contiguous); the TMA-staged variant is k_stream<2>
 __global__ void __launch_bounds__(256) k4_orient(const float* __restrict__ x, size_t frame_stride, int nframes,
                                                  const int* __restrict__ index, int nmol, int napm,

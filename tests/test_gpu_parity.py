@@ -348,6 +348,48 @@ def test_rdf_full_size_paranoid_free_properties(gpu_ctx_factory):
     assert np.array_equal(got2.reshape(Rbin, 5), exp)
 
 
+def test_group_redefined_after_accumulator_creation(gpu_ctx_factory):
+    """A group may be redefined (b2a_set_group) with MORE molecules after accumulators were created on it: the per-molecule
+    scratch sized at create time has to follow (it used to be overrun), symmetric evaluation must notice that the two sides no
+    longer hold the same centres (different weights), and counts stay those of the oracle."""
+    system = synth.water_box(2600, 4.3, seed=65, split_atoms=True)
+    K = 2
+    gi = refprog.group_info(system, "OW")
+    small = gi["index"][:300]
+    ctx = gpu_ctx_factory(system.natoms, K)
+    for g in (0, 1):
+        ctx.set_group(g, small, 1, gi["mass"], gi["charge"])
+    Lbox = port.lbox_from_box9(system.box9())
+    Rm = port.rdf_default_rm(Lbox)
+    Rbin = port.rdf_rbin(Rm)
+    acc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=5, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0, up2=100.0, Rm=Rm, Rbin=Rbin)
+    ctx.rdf_tune(acc, 1, 0)
+    coo = ctx.coord_create(grp0=0, grp1=1, com0=0, com1=0, Rmin=0.5, dim=2, low=-100.0, up=100.0, max_count=64)
+    x = system.frames(0, K)
+    ctx.submit(x, system.box9())
+    ctx.accumulate(acc); ctx.accumulate(coo)
+    ctx.reset(acc); ctx.reset(coo)
+    for g in (0, 1):                                   # now the whole group: 2600 molecules on scratch sized for 300
+        ctx.set_group(g, gi["index"], 1, gi["mass"], gi["charge"])
+    ctx.submit(x, system.box9())
+    ctx.accumulate(acc); ctx.accumulate(coo)
+    got, st = ctx.read(acc)
+    exp, est, _, _ = refprog.oracle_rdf_region(system, K, "OW", "OW", return_counts=True)
+    assert np.array_equal(got.reshape(Rbin, 5), exp) and int(st[lib.STAT_PAIRS]) < 2600 * 2600 * K      # symmetric path, right counts
+    cnt = ctx.coord_counts(coo, 1)
+    o = x[1][0::3].astype(np.float64)
+    ecnt, _ = port.pair_count(o, o, Lbox, refprog.f32(0.5), 2, refprog.f32(-100.0), refprog.f32(100.0))
+    assert np.array_equal(cnt, ecnt)
+    # same atoms, different weights on one side (geometry centre of a one-atom "molecule" is the same point, but the library cannot
+    # know that in general): the symmetric request must be dropped, not mis-applied -- every ordered pair is evaluated
+    ctx.set_group(1, gi["index"], 1, gi["mass"] * 2.0, gi["charge"])
+    ctx.reset(acc)
+    ctx.submit(x, system.box9())
+    ctx.accumulate(acc)
+    got2, st2 = ctx.read(acc)
+    assert np.array_equal(got2.reshape(Rbin, 5), exp) and int(st2[lib.STAT_PAIRS]) == 2600 * 2600 * K
+
+
 def test_rdf_headline_mode_full_size_against_oracle(gpu_ctx_factory):
     """EXACTLY the configuration bench.py times (BASELINE config 2 at full size, 8 distinct frames per batch,
     b2a_rdf_tune(symmetric=1), cells automatic): (i) the symmetric histogram of the batch equals the full (MODE 0) evaluation of
@@ -960,6 +1002,22 @@ def test_handle_full_loaders_and_accumulators(gpu_ctx_factory):
         p2 = port.load_position_center(x[f], gi["index"], 7, gi["w"][0], Lbox)
         port.rdf_accum(p1, p2, Lbox, 2, 0.0, 3.0, 2, 0, -100.0, 100.0, Rm, Rbin, rexp)
     assert np.array_equal(rgot.reshape(Rbin, 2), rexp) and rexp.sum() > 0
-    with pytest.raises(lib.B2AError, match="heterogeneous"):
-        ctx.orient_create(grp=0, com=0, DIMN=2, low=0.0, up=3.0, c1=0.0, c2=0.0, dr=1.0, CR=2.0, Cr=0.0, nAngle=90, tp1=1, tp2=2, tp3=3,
+    # orientation histogram on the heterogeneous group: per molecule its own atom count, weights and total (literal FP64 path),
+    # against the oracle fed with GmxHandleFull's own loaders (padded boxd + per-molecule centres)
+    for method, tp in ((1, (1, 2, 3)), (2, (2, 5, 7))):
+        kw = dict(grp=0, com=0, DIMN=2, low=0.2, up=2.9, c1=1.5, c2=1.5, dr=0.25, CR=2.0, Cr=0.0, nAngle=60, tp1=tp[0], tp2=tp[1], tp3=tp[2],
+                  DIMNOrient=1, method=method)
+        oacc = ctx.orient_create(**kw)
+        ctx.accumulate(oacc)
+        ogot, ost = ctx.read(oacc)
+        eo = en = None
+        for f in range(K):
+            eo, en, _ = port.orient_accum(port.full_load_position(x[f], idx, napm, Lbox), port.full_load_position_center(x[f], idx, napm, m, Lbox), Lbox,
+                                          2, refprog.f32(0.2), refprog.f32(2.9), refprog.f32(1.5), refprog.f32(1.5), refprog.f32(0.25), refprog.f32(2.0),
+                                          refprog.f32(0.0), 60, tp[0], tp[1], tp[2], 1, method, eo, en)
+        nb1 = len(en)
+        assert np.array_equal(ogot[:nb1 * 60].reshape(60, nb1), eo) and np.array_equal(ogot[nb1 * 60:], en) and eo.sum() > 0
+        assert int(ost[lib.STAT_FRAMES]) == K
+    with pytest.raises(lib.B2AError, match="tp1..3 must lie in 1..napm"):      # an atom the smallest molecule does not have
+        ctx.orient_create(grp=0, com=0, DIMN=2, low=0.0, up=3.0, c1=0.0, c2=0.0, dr=1.0, CR=2.0, Cr=0.0, nAngle=90, tp1=1, tp2=2, tp3=int(napm.min()) + 1,
                           DIMNOrient=2, method=1)
