@@ -691,9 +691,11 @@ static FastParams fast_params(const Group& g, int com, int mode)
     return fp;
 }
 
-template <int MODE, int NAPM_T, int VAR = 0>
+template <int MODE, int NAPM_T, int VAR = 0, bool FUSE = false>
 static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode)
 {
+    if constexpr (MODE == 2 && !FUSE)
+        if (a.w2) return launch_stream_t<MODE, NAPM_T, VAR, true>(c, g, com, M, a, extra_smem, fast_mode);   // b2a_acc_also_centers
     a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;
     a.atom0 = g.h_index[0]; a.nmol = g.nmol; a.napm = g.napm;
     a.w = g.d_w[com]; a.wsum = make_div(g.wsum[com]); a.geom = c->d_geom;
@@ -725,7 +727,7 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     constexpr int NS = stream_stages(MODE, VAR);
     size_t smem = (size_t)NS * a.tile_floats * 4 + NS * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
     if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut + sizeof(double) * g.napm : 0);
-    auto kern = k_stream<MODE, NAPM_T, VAR>;
+    auto kern = k_stream<MODE, NAPM_T, VAR, FUSE>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M + 32, smem));

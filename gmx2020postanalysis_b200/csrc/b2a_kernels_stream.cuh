@@ -146,7 +146,9 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 // VAR (MODE 2): 1 = two molecules per consumer thread in packed FP32 (a tile holds 2 x consumer-thread-count molecules):
 // orient_fastNx2() for any molecule, orient_fast3x2() for three-site molecules whose vector atoms are (reference atom, the
 // other two).
-template <int MODE, int NAPM_T, int VAR>
+// FUSE (MODE 2): the instantiation that also writes a second kind of centre (b2a_acc_also_centers); a separate instantiation because
+// the FP64 centre code costs the plain orientation kernel 4 % through register pressure even when it is switched off at run time.
+template <int MODE, int NAPM_T, int VAR, bool FUSE = false>
 __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream(const __grid_constant__ StreamArgs a)
 {
     constexpr int NS = stream_stages(MODE, VAR);   // depth of the TMA ring
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
     if ((int)threadIdx.x < M)
     {
         for (int j = threadIdx.x; j < napm; j += M) { cp_async8(&sw[j], &a.w[j]); if (MODE != 0) cp_async4(&swf[j], &a.wf[j]); }
-        if (MODE == 2 && a.w2)
+        if (MODE == 2 && FUSE)
             for (int j = threadIdx.x; j < napm; j += M) cp_async8(&sw2[j], &a.w2[j]);
         if (MODE == 2 && a.fp.enabled)
             for (int j = threadIdx.x; j < kCosLut / 4; j += M) cp_async4(reinterpret_cast<unsigned*>(slut) + j, reinterpret_cast<const unsigned*>(a.lut) + j);
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
                 }
                 else
                 {
-                    if (a.w2)
+                    if constexpr (FUSE)
                     {   // fused centre output: the same FP64 code as K1 (mol_centers3), on the coordinates already in shared memory
                         auto put = [&](const float* pm, int im) {
                             double c0, c1, c2;
