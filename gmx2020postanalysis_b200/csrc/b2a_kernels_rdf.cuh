@@ -491,6 +491,28 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
     int                sub = 0;   // sub-tile counter: selects the ping-pong queue counter
     unsigned long long npairs = 0, nsel = 0;
 
+    // Candidate queue: entries are (global j << 7 | thread).  A drain re-examines only FULL rounds of THREADS entries -- a partly
+    // filled round costs the same latency (scattered FP64 loads, a dependent FP64 chain) as a full one, and with ~1 candidate per j
+    // the old "drain everything every 256 j" always paid for one (config 2: 257 entries = three rounds for two rounds' worth) -- and
+    // carries the remainder (`carry` entries at the front of the queue, block-uniform) into the next phase.  Entries name j
+    // globally, so they survive the tile they were found in; everything is drained before the i-tile changes and at the end.
+    unsigned carry = 0;
+    auto drain = [&](bool all) {
+        __syncthreads();                                            // every push of the phase that just ended is in the queue
+        const unsigned n   = min(carry + q_count[sub & 1], (unsigned)kQueueCap);
+        const unsigned rem = all ? 0u : (n % (unsigned)THREADS);
+        if (threadIdx.x == 0) q_count[(sub + 1) & 1] = 0;           // the next phase's counter (its last readers passed a barrier long ago)
+        for (unsigned e = rem + threadIdx.x; e < n; e += THREADS)
+        {
+            const unsigned ent = queue[e];
+            const int      jg  = (int)(ent >> 7);
+            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, (int)(ent & 127u), B[jg], jg);
+        }
+        carry = rem;
+        ++sub;
+        __syncthreads();
+    };
+
     // stream the j-molecules [ja, jb) of B against the i-molecules currently held in registers
     auto process_range = [&](int ja, int jb) {
         const bool partial = tcount < TI;
@@ -520,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                 for (int t = threadIdx.x; t < cnt; t += THREADS) sj[t] = B[jt + t];
                 __syncthreads();
             }
-            for (int js = 0; js < cnt; js += kSubJ, ++sub)
+            for (int js = 0; js < cnt; js += kSubJ)
             {
                 const int je = min(cnt, js + kSubJ);
                 unsigned* qc = &q_count[sub & 1];
@@ -559,8 +581,8 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                         }
                         if (PARANOID || dacc != 0 || kmin <= lowk)
                         {
-                            const unsigned slot = atomicAdd(qc, 1u);
-                            if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
+                            const unsigned slot = carry + atomicAdd(qc, 1u);
+                            if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
                             else
                             {
                                 recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
@@ -610,8 +632,8 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                         }
                         if (PARANOID || dacc != 0 || kmin <= lowk)
                         {
-                            const unsigned slot = atomicAdd(qc, 1u);
-                            if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)j << 16) | threadIdx.x;
+                            const unsigned slot = carry + atomicAdd(qc, 1u);
+                            if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
                             else
                             {
                                 recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
@@ -620,17 +642,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                         }
                     }
                 }
-                // drain: every queued (j, thread) candidate is re-examined by whichever thread picks it up
-                __syncthreads();
-                const unsigned n = min(*qc, (unsigned)kQueueCap);
-                for (unsigned e = threadIdx.x; e < n; e += THREADS)
-                {
-                    const unsigned ent = queue[e];
-                    const int      jl  = (int)(ent >> 16);
-                    recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, (int)(ent & 0xffffu), sj[jl], jt + jl);
-                }
-                if (threadIdx.x == 0) q_count[(sub + 1) & 1] = 0;   // the other counter was drained one sub-tile ago
-                __syncthreads();
+                drain(false);
             }
             if (kDbuf) sj = sj == sjbuf ? sjbuf + kTileJ : sjbuf;
         }
@@ -652,6 +664,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
     {
         load_tile();
         process_range(j0, j1);
+        drain(true);
         nsel = SYM ? (weight == 1 ? tcount : 0) : (blockIdx.y == 0 ? tcount : 0);
     }
     else
@@ -665,10 +678,10 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
         for (; tstart < cell_a1; tstart += TI * cny)
         {
             tcount = min(TI, cell_a1 - tstart);
-            __syncthreads();   // previous tile's drain may still read blk.A / blk.tcount
+            drain(true);       // candidates of the previous tile name ITS molecules: re-examine them before blk.A / blk.tcount change
             if (threadIdx.x == 0) { blk.A = sortedA + (size_t)f * p.n0 + tstart; blk.tcount = tcount; }
             load_tile();
-            if (csym && crole == 1) { process_range(tstart, tstart + tcount); continue; }   // the tile against itself
+            if (csym && crole == 1) { process_range(tstart, tstart + tcount); continue; }   // the tile against itself (drained at the next tile / the end)
             nsel += tcount;
             const int jmin = csym ? tstart + tcount : 0;   // symmetric: only sorted positions beyond the tile
             // cells the tile spans along z (cell = top bits of the fixed-point coordinate; the column is sorted by it)
@@ -695,6 +708,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                     else process_range(max(jmin, (int)sb[col + z0]), (int)sb[col + z1 + 1]);
                 }
         }
+        drain(true);
     }
     __syncthreads();
     unsigned long long* gh = ghist + (size_t)slab * p.Rbin;
