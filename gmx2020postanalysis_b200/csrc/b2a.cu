@@ -691,11 +691,17 @@ static FastParams fast_params(const Group& g, int com, int mode)
     return fp;
 }
 
-template <int MODE, int NAPM_T, int VAR = 0, bool FUSE = false>
+template <int MODE, int NAPM_T, int VAR = 0, bool FUSE = false, int SPEC = 0>
 static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArgs a, size_t extra_smem, int fast_mode)
 {
-    if constexpr (MODE == 2 && !FUSE)
+    if constexpr (MODE == 2 && !FUSE && SPEC == 0)
+    {
         if (a.w2) return launch_stream_t<MODE, NAPM_T, VAR, true>(c, g, com, M, a, extra_smem, fast_mode);   // b2a_acc_also_centers
+        // the program's default axes and method (calc_orient_mof.cpp:86-92) on reference-atom vectors: the specialised instantiation
+        if constexpr (NAPM_T == 3 && VAR == 1)
+            if (a.ori_reuse && a.ori.DIMN == 2 && a.ori.DIMNOrient == 2 && a.ori.method == 1 && !getenv("B2A_NO_SPEC"))
+                return launch_stream_t<MODE, NAPM_T, VAR, false, 1>(c, g, com, M, a, extra_smem, fast_mode);
+    }
     a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;
     a.atom0 = g.h_index[0]; a.nmol = g.nmol; a.napm = g.napm;
     a.w = g.d_w[com]; a.wsum = make_div(g.wsum[com]); a.geom = c->d_geom;
@@ -727,7 +733,7 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     constexpr int NS = stream_stages(MODE, VAR);
     size_t smem = (size_t)NS * a.tile_floats * 4 + NS * (sizeof(FrameGeom) + 16 + sizeof(StageDesc)) + sizeof(double) * g.napm + extra_smem;
     if (MODE != 0) smem += sizeof(float) * ((g.napm + 1) & ~1) + sizeof(unsigned) * (a.smem_bins & 1) + sizeof(uint2) * kFastQueue + (MODE == 2 ? kCosLut + sizeof(double) * g.napm : 0);
-    auto kern = k_stream<MODE, NAPM_T, VAR, FUSE>;
+    auto kern = k_stream<MODE, NAPM_T, VAR, FUSE, SPEC>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, M + 32, smem));

@@ -285,6 +285,9 @@ __device__ __forceinline__ void load3x2(Mol3x2& m, const float* pA, const float*
 // ---- the part of the two-molecule bracket that follows the centres and the two vectors -----------------------------------------
 // C: centre components; MU / MD: per-molecule maxima of |offset| and |raw difference| behind the centre (error of the centre);
 // V1, V2: the two vectors up to the sign vsgn; MV / MDV: the maxima behind them (error of the vectors)
+// SPEC = 1: the program's default axes and method (calc_orient_mof.cpp:86-92: DIMN = 2, DIMNOrient = 2, method = 1) as compile-time
+// constants -- the component selects and the cross-product branch fold away; 0: whatever the spec says, at run time.
+template <int SPEC = 0>
 __device__ __forceinline__ void orient_tail_x2(const unsigned long long C[3], unsigned long long MU, unsigned long long MD,
                                                const unsigned long long V1[3], const unsigned long long V2[3], unsigned long long MV,
                                                unsigned long long MDV, bool undA, bool undB, bool validA, bool validB, float vsgn,
@@ -297,15 +300,20 @@ __device__ __forceinline__ void orient_tail_x2(const unsigned long long C[3], un
     const P CM = f2pack(fmaxf(fabsf(c0a), fmaxf(fabsf(c1a), fabsf(c2a))), fmaxf(fabsf(c0b), fmaxf(fabsf(c1b), fabsf(c2b))));
     const P Ec = f2fma(CM, f2bc(fp.e1), f2fma(MD, f2bc(fp.e2), f2mul(MU, f2bc(fp.e3))));      // fast_center_err()
     // slab filter (:158) and radial selection (:160-177); DIMN picks the components
-    const P Cz = d.DIMN == 0 ? C[0] : (d.DIMN == 1 ? C[1] : C[2]);
-    const P Ca = d.DIMN == 0 ? C[1] : C[0], Cb = d.DIMN == 2 ? C[1] : C[2];
+    const int DIMN = SPEC ? 2 : d.DIMN, DIMNOrient = SPEC ? 2 : d.DIMNOrient, method = SPEC ? 1 : d.method;
+    const P Cz = DIMN == 0 ? C[0] : (DIMN == 1 ? C[1] : C[2]);
+    const P Ca = DIMN == 0 ? C[1] : C[0], Cb = DIMN == 2 ? C[1] : C[2];
     bool    outA = false, outB = false;   // proven "not counted"
     {
         const P LO = f2sub(Cz, Ec), HI = f2add(Cz, Ec);
         float   la, lb, ha, hb;
         f2unpack(LO, la, lb); f2unpack(HI, ha, hb);
-        if (!(la > of.low && ha < of.up)) { if (!undA && (ha < of.low || la > of.up)) outA = true; else undA = true; }   // outside, or undecided
-        if (!(lb > of.low && hb < of.up)) { if (!undB && (hb < of.low || lb > of.up)) outB = true; else undB = true; }
+        // inside: proven; definitely outside (and the shifts proven): "not counted"; anything else: undecided.  Written as predicate
+        // algebra (no branches: the two molecules of a thread rarely agree, and a divergent region costs more than the logic)
+        const bool inA = la > of.low && ha < of.up, doA = ha < of.low || la > of.up;
+        const bool inB = lb > of.low && hb < of.up, doB = hb < of.low || lb > of.up;
+        outA = !inA & !undA & doA; undA = undA | (!inA & !doA);
+        outB = !inB & !undB & doB; undB = undB | (!inB & !doB);
     }
     const P Ta = f2sub(Ca, f2bc(of.c1)), Tb = f2sub(Cb, f2bc(of.c2));
     const P S  = f2fma(Ta, Ta, f2mul(Tb, Tb));
@@ -319,8 +327,10 @@ __device__ __forceinline__ void orient_tail_x2(const unsigned long long C[3], un
         const P LO = f2sub(R, ER), HI = f2add(R, ER);
         float   la, lb, ha, hb;
         f2unpack(LO, la, lb); f2unpack(HI, ha, hb);
-        if (!(la > of.cr_lo && ha < of.CR)) { if (!undA && (ha < of.cr_lo || la > of.CR)) outA = true; else undA = true; }
-        if (!(lb > of.cr_lo && hb < of.CR)) { if (!undB && (hb < of.cr_lo || lb > of.CR)) outB = true; else undB = true; }
+        const bool inA = la > of.cr_lo && ha < of.CR, doA = ha < of.cr_lo || la > of.CR;
+        const bool inB = lb > of.cr_lo && hb < of.CR, doB = hb < of.cr_lo || lb > of.CR;
+        outA = outA | (!inA & !undA & doA); undA = undA | (!inA & !doA);
+        outB = outB | (!inB & !undB & doB); undB = undB | (!inB & !doB);
     }
     // radial bin coordinate q = (R - Cr) / dr: proven when its fraction is further than Eq from 0 and 1 and 0 <= q < 2e9
     const P Q  = f2mul(f2sub(R, f2bc(of.Cr)), f2bc(of.inv_dr));
@@ -340,7 +350,7 @@ __device__ __forceinline__ void orient_tail_x2(const unsigned long long C[3], un
     // vecOut up to the sign wsgn; |v^ - v| <= Ev per component
     const P Ev = f2mul(f2add(MDV, MV), f2bc(1.05f * kEps));
     P       VO[3], Evo;
-    if (d.method == 2)
+    if (method == 2)
     {
         VO[0] = f2sub(f2mul(V1[1], V2[2]), f2mul(V1[2], V2[1]));
         VO[1] = f2sub(f2mul(V1[2], V2[0]), f2mul(V1[0], V2[2]));
@@ -359,7 +369,7 @@ __device__ __forceinline__ void orient_tail_x2(const unsigned long long C[3], un
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ria) : "f"(n2a));
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rib) : "f"(n2b));
     const P RI  = f2pack(ria, rib);
-    const P DOT = d.DIMNOrient == 0 ? VO[0] : (d.DIMNOrient == 1 ? VO[1] : VO[2]);
+    const P DOT = DIMNOrient == 0 ? VO[0] : (DIMNOrient == 1 ? VO[1] : VO[2]);
     const P CS  = f2mul(DOT, f2mul(RI, f2bc(vsgn)));
     const P REL = f2mul(Evo, RI);
     const P Ecs = f2fma(REL, f2bc(3.0f), f2bc(10.0f * kEps));   // the float roundings of the edge table are inside fmh[].y
@@ -386,6 +396,7 @@ __device__ __forceinline__ void orient_tail_x2(const unsigned long long C[3], un
 }
 
 // Three-site molecule, vectors from the reference atom to the other two: the vectors ARE the unwrapped offsets (see above).
+template <int SPEC = 0>
 __device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, bool validB, float w1, float w2, float wsgn, const FastParams& fp,
                                                const OrientDev& d, const OrientFast& of, const float* fedge, const float2* fmh,
                                                const unsigned char* lut, int res[2], int meZ[2], int lo[2])
@@ -413,7 +424,7 @@ __device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, boo
     P       C[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) C[k] = f2fma(f2fma(W2, U2[k], f2mul(W1, U1[k])), IW, m.X0[k]);
-    orient_tail_x2(C, MU, MD, U1, U2, MU, MD, undA, undB, validA, validB, wsgn, fp, d, of, fedge, fmh, lut, res, meZ, lo);
+    orient_tail_x2<SPEC>(C, MU, MD, U1, U2, MU, MD, undA, undB, validA, validB, wsgn, fp, d, of, fedge, fmh, lut, res, meZ, lo);
 }
 
 // Any molecule, any three vector atoms, two molecules per thread: the offsets of every atom from the reference atom feed the

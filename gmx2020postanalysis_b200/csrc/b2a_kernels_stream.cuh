@@ -148,7 +148,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 // other two).
 // FUSE (MODE 2): the instantiation that also writes a second kind of centre (b2a_acc_also_centers); a separate instantiation because
 // the FP64 centre code costs the plain orientation kernel 4 % through register pressure even when it is switched off at run time.
-template <int MODE, int NAPM_T, int VAR, bool FUSE = false>
+// SPEC (MODE 2, NAPM_T 3, VAR 1): 1 = calc_orient_mof's default axes and method folded in at compile time (orient_tail_x2<1>).
+template <int MODE, int NAPM_T, int VAR, bool FUSE = false, int SPEC = 0>
 __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream(const __grid_constant__ StreamArgs a)
 {
     constexpr int NS = stream_stages(MODE, VAR);   // depth of the TMA ring
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
                             {
                                 Mol3x2 mol;
                                 load3x2<true>(mol, p, pB, g.fk);
-                                orient_fast3x2(mol, vA, vB, w3a, w3b, w3s, a.fp, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
+                                orient_fast3x2<SPEC>(mol, vA, vB, w3a, w3b, w3s, a.fp, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
                             }
                             else
                                 orient_fastNx2<true>(p, pB, vA, vB, napm, lane_rot, swf, a.fp, g.fk, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
@@ -415,11 +416,15 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
 #pragma unroll
                             for (int l = 0; l < 2; ++l)
                             {
-                                if (res[l] == 0) { undecided(l ? iB : i); continue; }
-                                int cz, ca;
-                                cells(l, cz, ca, nsel, ndrop);
-                                if (cz >= 0) atomicAdd(&shist[cz], 1u);
-                                if (ca >= 0) atomicAdd(&shist[ca], 1u);
+                                if (res[l] == 0) undecided(l ? iB : i);   // rare
+                                // accounting of a proven molecule as in cells(), without branches: two predicated shared atomics
+                                const bool sel = res[l] == 2;
+                                const bool zok = sel & (meZ[l] < a.ori.nbin1);
+                                const bool aok = zok & (lo[l] < a.ori.nAngle);
+                                nsel += sel ? 1u : 0u;
+                                ndrop += ((sel & !zok) | (zok & !aok)) ? 1u : 0u;
+                                if (zok) atomicAdd(&shist[a.ori.nbin1 * a.ori.nAngle + meZ[l]], 1u);
+                                if (aok) atomicAdd(&shist[meZ[l] + lo[l] * a.ori.nbin1], 1u);
                             }
                         }
                         else
