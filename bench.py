@@ -538,6 +538,7 @@ def measure(wl, D, steps, warmup, with_cpu, rdf_sample, flush):
     evaluated_pairs = float(priv_stats[lib.STAT_PAIRS])
 
     # ---- the path's one collective: merge the rank-private histograms inside libb2a ------------------------------
+    D.barrier(ctx)                               # so that the figure below is the collective, not the skew between the ranks' reads
     t0 = time.perf_counter()
     ctx.finalize()
     ctx.sync()
@@ -807,7 +808,18 @@ def main():
         clocks, timing = res["clocks"], res["timing"]
         rdf = wl.kind == "rdf"
         per_frame = wl.pairs_per_frame if rdf else 1.0
-        launches = int(sum(n for k, (t, n) in timing.items() if k not in ("h2d", "k3_prep")) + 2 * timing["k3_prep"][1] + args.steps * (1 + len(wl.accs)))
+        # kernels of libb2a launched inside the timed region, from the launch sequence of one step (profiles/r02_launches.csv shows the
+        # same list for config 2): K1 per group, then per RDF accumulator k_fetch_words + k3_slab_count + k3_slab_scatter + k3_rdf
+        # (full-mode launch, plus the symmetric one when both sides are the same molecules) + k_add_frames; configs 1 / 4: the
+        # streaming kernel + k_add_frames (+ K1 for the dipole vectors).  Cell-binned sweeps (config 5) sort per group on top: there
+        # the count falls back to the number of timed kernel spans.
+        if wl.kind == "rdf" and wl.name != "c5":
+            per_step = len(wl.groups) + len(wl.accs) * (1 + 2 + (2 if (wl.symmetric and wl.name == "c2") else 1) + 1)
+        elif wl.kind == "rdf":
+            per_step = int(sum(n for k, (t, n) in timing.items() if k != "h2d")) // max(args.steps, 1) + len(wl.accs)
+        else:
+            per_step = 2 + (1 if wl.kind == "orient" else 0)
+        launches = per_step * args.steps
         line = {
             "metric": "rdf_pair_distances_per_s" if rdf else "frames_per_s", "value": head["frames_per_s"] * per_frame,
             "unit": "pair-distances/s" if rdf else "frames/s", "n_gpus": D.world,
