@@ -166,10 +166,12 @@ class Workload:
     def step(self, ctx):
         """One pass of the hot path over the resident batch (nothing cached from a previous step is reused)."""
         ctx.invalidate()
-        if self.kind == "orient":
-            ctx.centers_device(0, self.lib.COM_DIPOLE)        # the per-molecule dipole vectors, left on the device
         for a in self.accs:
             ctx.accumulate(a)
+        if self.kind == "orient":
+            # the per-molecule dipole vectors, left on the device.  Queued AFTER the orientation kernel: K1 writes 24 B per molecule
+            # (512 MB per 128-frame batch), and a K4 launched right behind it shares HBM with that write-back (0.60 instead of 0.70 of peak)
+            ctx.centers_device(0, self.lib.COM_DIPOLE)
 
     def read_all(self, ctx, accs=None):
         out = [ctx.read(a) for a in (self.accs if accs is None else accs)]
@@ -527,7 +529,11 @@ def measure(wl, D, steps, warmup, with_cpu, rdf_sample, flush):
         ctx.join()                               # accumulators of a sweep run on streams of their own: the bracket closes behind all of them
         ev[s][1].record(stream)
         used.append(pos["cur"])
-        feed()                                   # next step's frames: the upload overlaps this step's kernels (copy stream)
+        # next step's frames: the upload overlaps this step's kernels (copy stream).  The HBM-bound configs (1 and 4) finish a step
+        # 30x faster than PCIe delivers the next batch: feeding every step would leave the GPU idle (and clocking down) between
+        # brackets, so they take a new batch every fourth step -- their batch is larger than L2 (config 4) or L2 is flushed (config 1)
+        if wl.kind == "rdf" or s % 4 == 3:
+            feed()
     D.barrier(ctx)
     t_wall = time.perf_counter() - t_wall
     clocks = sampler.stop()
