@@ -148,6 +148,13 @@ class Workload:
             ctx.rdf_tune(c, 0, 1 if self.name == "c3" else 0)
             ctx.rdf_cells(c, 0)
             self.chk = [c]
+            if self.name == "c2":
+                # ... and a third one that shares nothing with the FP32 bracket: EVERY pair through the FP64 path (one frame only)
+                c2 = ctx.rdf_create(grp0=g0, grp1=g1, com0=0, com1=0, nbin=self.nbin, low=-100.0, up=100.0, dim=0, dim2=2, low2=-100.0,
+                                    up2=100.0, Rm=self.Rm, Rbin=self.Rbin)
+                ctx.rdf_tune(c2, 0, 1)
+                ctx.rdf_cells(c2, 0)
+                self.chk.append(c2)
         elif self.kind == "density":
             L = 4.476
             dbin = float(np.float32(np.float32(L) / np.float32(100)))                         # README.md:127
@@ -570,6 +577,16 @@ def measure(wl, D, steps, warmup, with_cpu, rdf_sample, flush):
             expect += hb * np.uint64(uses[b])
         if not np.array_equal(expect, priv_counts[0]):
             problems.append("timed histogram differs from the independent evaluation of the same frames")
+        if wl.name == "c2":
+            # the full kernel shares the FP32 bracket with the symmetric one; one frame also goes through the mode that re-evaluates
+            # EVERY pair in FP64 (a kernel that skipped its re-evaluations would pass the comparison above and fail this one)
+            ctx.submit(batches[0][:1], box)
+            for a in (wl.accs[0], wl.chk[1]):
+                ctx.reset(a)
+                ctx.accumulate(a)
+            if not np.array_equal(ctx.read(wl.accs[0])[0], ctx.read(wl.chk[1])[0]):
+                problems.append("symmetric histogram of one frame differs from the all-FP64 evaluation")
+            check["independent_fp64"] = "one frame: symmetric production kernel == every pair re-evaluated in FP64"
         check["independent"] = {"rdf": "every pair re-evaluated in FP64" if wl.name == "c3" else "full N0 x N1 kernel (no symmetry, no cells)", "density": "literal FP64 kernel",
                                 "orient": "literal FP64 kernel"}[wl.kind] + f", {len(check_batches)} batches x {F} frames"
     elif wl.name == "c5":

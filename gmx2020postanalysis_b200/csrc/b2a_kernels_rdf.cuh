@@ -502,6 +502,9 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
         const unsigned n   = min(carry + q_count[sub & 1], (unsigned)kQueueCap);
         const unsigned rem = all ? 0u : (n % (unsigned)THREADS);
         if (threadIdx.x == 0) q_count[(sub + 1) & 1] = 0;           // the next phase's counter (its last readers passed a barrier long ago)
+#ifdef B2A_EXP_NODRAIN   // experiment only (WRONG counts): what the in-kernel re-evaluation of the candidates costs
+        if (false)
+#endif
         for (unsigned e = rem + threadIdx.x; e < n; e += THREADS)
         {
             const unsigned ent = queue[e];
