@@ -697,9 +697,9 @@ static int launch_stream_t(b2a_ctx* c, const Group& g, int com, int M, StreamArg
     if constexpr (MODE == 2 && !FUSE && SPEC == 0)
     {
         if (a.w2) return launch_stream_t<MODE, NAPM_T, VAR, true>(c, g, com, M, a, extra_smem, fast_mode);   // b2a_acc_also_centers
-        // the program's default axes and method (calc_orient_mof.cpp:86-92) on reference-atom vectors: the specialised instantiation
-        if constexpr (NAPM_T == 3 && VAR == 1)
-            if (a.ori_reuse && a.ori.DIMN == 2 && a.ori.DIMNOrient == 2 && a.ori.method == 1 && !getenv("B2A_NO_SPEC"))
+        // the program's default axes and method (calc_orient_mof.cpp:86-92): the specialised instantiation of the two-molecule path
+        if constexpr (VAR == 1)
+            if (a.ori.DIMN == 2 && a.ori.DIMNOrient == 2 && a.ori.method == 1 && !getenv("B2A_NO_SPEC"))
                 return launch_stream_t<MODE, NAPM_T, VAR, false, 1>(c, g, com, M, a, extra_smem, fast_mode);
     }
     a.x = c->d_x; a.frame_stride = (size_t)c->natoms * 3; a.nframes = c->nframes;

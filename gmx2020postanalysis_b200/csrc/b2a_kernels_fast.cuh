@@ -435,7 +435,7 @@ __device__ __forceinline__ void orient_fast3x2(const Mol3x2& m, bool validA, boo
 // order of the atoms, so lane block m = lane / (32 / g), g = gcd(3 napm, 32), starts its walk at atom m: the g lanes that
 // would collide read g different atoms, 3 m words apart, and 3 m mod g is a permutation.  The walk then includes the
 // reference atom itself (offset exactly 0, contributes nothing), so that the wrap-around is a whole molecule = a multiple of g.
-template <bool SMEM>
+template <bool SMEM, int SPEC = 0>
 __device__ __forceinline__ void orient_fastNx2(const float* pA, const float* pB, bool validA, bool validB, int napm, int rot, const float* swf,
                                                const FastParams& fp, const FastPack& fk, const OrientDev& d, const OrientFast& of,
                                                const float* fedge, const float2* fmh, const unsigned char* lut, int res[2], int meZ[2],
@@ -485,7 +485,7 @@ __device__ __forceinline__ void orient_fastNx2(const float* pA, const float* pB,
     }
     const bool undA = !(fmaxf(muA, mvA) < fk.hsmin && fmaxf(mdA, mdvA) <= fk.dmax);
     const bool undB = !(fmaxf(muB, mvB) < fk.hsmin && fmaxf(mdB, mdvB) <= fk.dmax);
-    orient_tail_x2(C, f2pack(muA, muB), f2pack(mdA, mdB), V1, V2, f2pack(mvA, mvB), f2pack(mdvA, mdvB), undA, undB, validA, validB, 1.0f,
+    orient_tail_x2<SPEC>(C, f2pack(muA, muB), f2pack(mdA, mdB), V1, V2, f2pack(mvA, mvB), f2pack(mdvA, mdvB), undA, undB, validA, validB, 1.0f,
                    fp, d, of, fedge, fmh, lut, res, meZ, lo);
 }
 

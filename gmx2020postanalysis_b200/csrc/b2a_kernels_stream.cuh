@@ -148,7 +148,7 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 // other two).
 // FUSE (MODE 2): the instantiation that also writes a second kind of centre (b2a_acc_also_centers); a separate instantiation because
 // the FP64 centre code costs the plain orientation kernel 4 % through register pressure even when it is switched off at run time.
-// SPEC (MODE 2, NAPM_T 3, VAR 1): 1 = calc_orient_mof's default axes and method folded in at compile time (orient_tail_x2<1>).
+// SPEC (MODE 2, VAR 1): 1 = calc_orient_mof's default axes and method folded in at compile time (orient_tail_x2<1>).
 template <int MODE, int NAPM_T, int VAR, bool FUSE = false, int SPEC = 0>
 __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream(const __grid_constant__ StreamArgs a)
 {
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(288, (MODE == 2 && VAR == 1) ? 3 : 1) k_stream
                                 orient_fast3x2<SPEC>(mol, vA, vB, w3a, w3b, w3s, a.fp, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
                             }
                             else
-                                orient_fastNx2<true>(p, pB, vA, vB, napm, lane_rot, swf, a.fp, g.fk, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
+                                orient_fastNx2<true, SPEC>(p, pB, vA, vB, napm, lane_rot, swf, a.fp, g.fk, a.ori, a.of, fedge, fmh, slut, res, meZ, lo);
                         }
                         // accounting of a proven molecule, statement for statement as at the end of orient_molecule(); the host
                         // selects this variant only when the histogram fits in shared memory

@@ -92,6 +92,17 @@ def test_fused_ports_on_several_devices(devices, tmp_path, monkeypatch):
     case = GC.program_cases()["rdf_water_oo"]
     got = refprog.run_program(_dropin(case["exe"]), str(tmp_path / "compat"), case["system"](), case["nframes"], case["groups"], case["args"], "out.xvg")
     assert got == _golden("rdf_water_oo")
+    # ... including the velocity loaders (TRR-like input: the v block of every batch follows its x block to the same device)
+    exe = "calc_kineticEnergy"
+    if refprog.have_ref(exe) and os.path.exists(os.path.join(DROPIN, exe)):
+        import numpy as np
+        from workloads import synth
+        system, nframes = synth.water_box(900, 3.0, seed=75), 7
+        v = np.random.default_rng(76).normal(size=(nframes, system.natoms, 3)).astype(np.float32)
+        args = ["-low1", 0.2, "-up1", 2.7, "-low2", 0.1, "-up2", 2.9]
+        ref = refprog.run_program(os.path.join(refprog.REFDIR, exe), str(tmp_path / "vref"), system, nframes, ["SOL"], args, "o.xvg", velocities=v)
+        got = refprog.run_program(os.path.join(DROPIN, exe), str(tmp_path / "vnew"), system, nframes, ["SOL"], args, "o.xvg", velocities=v)
+        assert len(ref) == nframes + 1 and got == ref
 
 
 def test_density_slit_fused_port_matches_reference_build(tmp_path, monkeypatch):
