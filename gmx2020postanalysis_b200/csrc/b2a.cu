@@ -1479,6 +1479,36 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
             a.sortedA_view = sA->sorted;
             cd.bits = bits; cd.rx = reach[0]; cd.ry = reach[1]; cd.rz = reach[2];
             cd.nkeysA = nkA; cd.nkeysB = nkB; cd.startA = stA; cd.startB = stB; cd.sortedB = sB->sorted;
+            {
+                // per-column z reach: two cells whose index offsets are (dx, dy, dz) have closest points sqrt(sum (max(|d| - 1, 0) cell_k)^2)
+                // apart; a pair can only count if that is below the cut-off (the float-rounded Rm * Rm is below Rm^2 (1 + 1e-6)) plus the
+                // distance the fixed-point rounding can move two centres (cells are cut from the fixed-point coordinates).  Smallest
+                // cells and largest units over the frames of the batch: conservative for every frame.
+                const int nc = 1 << bits;
+                double    cell[3] = { 1e300, 1e300, 1e300 }, unit = 0.0;
+                for (int f = 0; f < c->nframes; ++f)
+                    for (int k = 0; k < 3; ++k)
+                    {
+                        cell[k] = std::min(cell[k], c->h_geom[f].L[k] / nc);
+                        unit    = std::max(unit, c->h_geom[f].L[k] / 4294967296.0);
+                    }
+                const double reff = p.Rm * (1.0 + 1e-6) + 4.0 * std::sqrt(3.0) * unit, r2 = reff * reff;
+                const bool   table = 2 * reach[0] + 1 < nc && 2 * reach[1] + 1 < nc && reach[0] <= 7 && reach[1] <= 7;
+                for (int ix = 0; ix < 15; ++ix)
+                    for (int iy = 0; iy < 15; ++iy)
+                    {
+                        int rz = reach[2];
+                        if (table && ix <= 2 * reach[0] && iy <= 2 * reach[1])
+                        {
+                            const double mx = std::max(std::abs(ix - reach[0]) - 1, 0) * cell[0], my = std::max(std::abs(iy - reach[1]) - 1, 0) * cell[1];
+                            const double left = r2 - mx * mx - my * my;
+                            if (left < 0.0) rz = -1;
+                            else rz = std::min(reach[2], (int)std::floor(std::sqrt(left) / cell[2]) + 1);
+                        }
+                        cd.rzc[ix * 15 + iy] = (signed char)rz;
+                    }
+                cd.use_rzc = (table && !getenv("B2A_NO_RZC")) ? 1 : 0;
+            }
         }
     }
 

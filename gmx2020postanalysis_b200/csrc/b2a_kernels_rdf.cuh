@@ -346,6 +346,12 @@ struct CellDev   // cell mode parameters (by value)
     const unsigned* startA;        // [frame][nkeysA + 1]
     const unsigned* startB;        // [frame][nkeysB + 1]
     const int4*     sortedB;       // [frame][n1]
+    // z reach per neighbour column (dx, dy) = (ix - rx, iy - ry): the cut-off sphere, not its bounding cube.  Cells whose closest
+    // points are further apart than the cut-off (plus the fixed-point slop) hold no countable pair: corner columns need fewer z
+    // layers or none at all (-1).  Symmetric in the signs of dx, dy, dz, as the symmetric evaluation requires.  Host-computed;
+    // all entries = rz when a reach covers its whole axis.
+    signed char     rzc[15 * 15];
+    int             use_rzc;       // 0: reaches above 7 cells (the table does not cover them): every column uses rz
 };
 
 // ---- main kernel ------------------------------------------------------------------------------------------
@@ -690,10 +696,12 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
             // cells the tile spans along z (cell = top bits of the fixed-point coordinate; the column is sorted by it)
             const int4* At  = sortedA + (size_t)f * p.n0 + tstart;
             const int   cza = (int)((unsigned)At[0].z >> zsh), czb = (int)((unsigned)At[tcount - 1].z >> zsh);
-            const int   z0 = cza - cd.rz, z1 = czb + cd.rz;           // inclusive, may leave [0, nc)
             for (int ix = 0; ix < nx; ++ix)
                 for (int iy = 0; iy < ny; ++iy)
                 {
+                    const int rzc = cd.use_rzc ? (int)cd.rzc[ix * 15 + iy] : cd.rz;
+                    if (rzc < 0) continue;                           // the whole column lies outside the cut-off sphere (block-uniform)
+                    const int z0 = cza - rzc, z1 = czb + rzc;        // inclusive, may leave [0, nc)
                     const int      cx  = (ccx - (nx >> 1) + ix + nc) & (nc - 1);
                     const int      cy  = (ccy - (ny >> 1) + iy + nc) & (nc - 1);
                     const unsigned col = ((unsigned)cx << cd.bits | (unsigned)cy) << cd.bits;
