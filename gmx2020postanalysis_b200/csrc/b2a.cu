@@ -3,6 +3,7 @@
 #include "b2a.h"
 
 #include "b2a_kernels_rdf.cuh"
+#include "b2a_kernels_rdf_cell.cuh"
 #include "b2a_kernels_coord.cuh"
 #include "b2a_kernels_stream.cuh"   // pulls in the centre / orientation kernels
 
@@ -1195,6 +1196,18 @@ static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p,
     return B2A_OK;
 }
 
+// cell mode, warp-autonomous tiles (b2a_kernels_rdf_cell.cuh)
+template <bool CUBIC, bool PARANOID>
+static int launch_rdf_cellw(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid)
+{
+    auto kern = k3_rdf_cellw<kCwWarps, CUBIC, PARANOID>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 32 * kCwWarps, smem, a.last_stream>>>(a.sortedA_view ? a.sortedA_view : a.d_sortedA, g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1], a.d_slab_cnt,
+                                                       a.d_frames, p, cd, a.d_hist, a.d_hist + a.ndev);
+    CU(cudaGetLastError());
+    return B2A_OK;
+}
+
 template <int IPT, int MODE, int TH = 128>
 static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid, bool cubic, bool dbuf = false)
 {
@@ -1207,7 +1220,10 @@ static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& 
     return cubic ? launch_rdf<IPT, TH, true, false, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, false, MODE>(c, a, g0, g1, p, cd, smem, grid);
 }
 
-constexpr int kCellIPT = 4, kCellThreads = 64;   // cell mode: 256-molecule tiles (64 threads x 4): half the z span of a 512-molecule tile; measured on config 5: 512 -> 17.7 ms, 256 (128 x 2) -> 13.2, 256 (64 x 4) -> 12.5, 128 (32 x 4) -> 13.5
+#ifndef B2A_CELL_THREADS
+#define B2A_CELL_THREADS 64
+#endif
+constexpr int kCellIPT = 4, kCellThreads = B2A_CELL_THREADS;   // cell mode: 256-molecule tiles (64 threads x 4): half the z span of a 512-molecule tile; measured on config 5: 512 -> 17.7 ms, 256 (128 x 2) -> 13.2, 256 (64 x 4) -> 12.5, 128 (32 x 4) -> 13.5
 
 // Cell grid for r_max << L: cells per dimension 2^bits, reach per dimension from the cut-off plus the fixed-point slop.
 // Returns false when cells would not cull enough to beat the brute-force (possibly symmetric) evaluation.
@@ -1454,7 +1470,8 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     const int nslab = p.nslab;
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, stm));
     int  bits = 0, reach[3] = { 0, 0, 0 };
-    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, kCellIPT * kCellThreads, nullptr, true);
+    const bool block_tiles = getenv("B2A_CELL_BLOCKTILE") != nullptr;   // A/B switch: the 256-molecule block tiles of k3_rdf MODE 2
+    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, block_tiles ? kCellIPT * kCellThreads : kCwTile, nullptr, true);
     CellDev cd{};
     {
         Timed tm(c, 1, stm);
@@ -1508,6 +1525,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
                         cd.rzc[ix * 15 + iy] = (signed char)rz;
                     }
                 cd.use_rzc = (table && !getenv("B2A_NO_RZC")) ? 1 : 0;
+                cd.no_warp_span = getenv("B2A_NO_WSPAN") ? 1 : 0;
             }
         }
     }
@@ -1518,6 +1536,16 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         RdfDev pc = p;
         // one block row per column of i-cells; its tiles are spread over gridDim.y (a block loops if a column is more crowded)
         const double per_col = (double)p.n0 / (double)(1u << (2 * bits));
+        if (!block_tiles)
+        {
+            // every warp owns a 128-molecule tile; rows of kCwWarps tiles
+            const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCwTile * kCwWarps))));
+            const size_t smem_cw = (size_t)kCwWarps * (32 * sizeof(int4) + kCwQueue * sizeof(unsigned)) + 16 + (size_t)pc.kstride * 4;
+            const dim3   grid(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes);
+            if (a.paranoid)
+                return cubic ? launch_rdf_cellw<true, true>(c, a, *g0, *g1, pc, cd, smem_cw, grid) : launch_rdf_cellw<false, true>(c, a, *g0, *g1, pc, cd, smem_cw, grid);
+            return cubic ? launch_rdf_cellw<true, false>(c, a, *g0, *g1, pc, cd, smem_cw, grid) : launch_rdf_cellw<false, false>(c, a, *g0, *g1, pc, cd, smem_cw, grid);
+        }
         const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCellIPT * kCellThreads))));
         // symmetric evaluation doubles the block rows: even = beyond-the-tile part of the j runs, odd = the tile against itself
         return dispatch_rdf<kCellIPT, 2, kCellThreads>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes), cubic);

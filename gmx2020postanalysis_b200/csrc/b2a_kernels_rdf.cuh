@@ -230,9 +230,18 @@ struct RdfBlock   // block-uniform state shared by the hot loop and the cold pat
     unsigned      stats[4];   // exact, moved, dropped, overflow
 };
 
+// Which molecule of the i-tile does register slot q of thread t hold?  Thread-major (all-pairs modes): slot q = the q-th stripe of
+// THREADS molecules.  Warp-major (cell mode): every warp holds 32 * IPT CONSECUTIVE molecules of the (z-sorted) column, so a warp
+// covers a short z span of its own and skips the j cells only the block's other warps can reach.
+template <int IPT, int THREADS, bool WM>
+__device__ __forceinline__ int slot_il(int t, int q)
+{
+    return WM ? ((t >> 5) * (32 * IPT) + q * 32 + (t & 31)) : (t + q * THREADS);
+}
+
 // Re-examine the IPT pairs (thread t's molecules) x (one j): recompute the FP32 bins, and for every pair the
 // FP32 bracket could not decide run the exact FP64 evaluation and move the count if needed.
-template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID>
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, bool WM = false>
 __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
 {
     // phase 1 (converged across the warp): FP32 bins of the thread's IPT pairs, remember the undecided ones
@@ -241,7 +250,7 @@ __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
 #pragma unroll
     for (int q = 0; q < IPT; ++q)
     {
-        const int  il = t + q * THREADS;
+        const int  il = slot_il<IPT, THREADS, WM>(t, q);
         const bool ok = il < b->tcount;
         const int4 a  = ok ? b->A[il] : make_int4(0, 0, 0, 0);
         unsigned   k1, k2;
@@ -260,7 +269,7 @@ __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
 #pragma unroll
         for (int u = 0; u < IPT; ++u) k1 = (u == q) ? k1v[u] : k1;
         const int k1idx = (int)(k1 - kMagicBits);
-        const int iorig = b->A[t + q * THREADS].w;
+        const int iorig = b->A[slot_il<IPT, THREADS, WM>(t, q)].w;
         const int ke    = exact_bin(b->cA, b->cB, b->n0, b->n1, iorig, jorig, b->L0, b->L1, b->L2, b->rm2, b->Rbin_d, b->Rm, b->Rbin);
         atomicAdd(&b->stats[0], 1u);
         if (ke == -2) atomicAdd(&b->stats[2], 1u);
@@ -352,6 +361,7 @@ struct CellDev   // cell mode parameters (by value)
     // all entries = rz when a reach covers its whole axis.
     signed char     rzc[15 * 15];
     int             use_rzc;       // 0: reaches above 7 cells (the table does not cover them): every column uses rz
+    int             no_warp_span;  // experiment switch (B2A_NO_WSPAN): every warp evaluates the whole run of its block
 };
 
 // ---- main kernel ------------------------------------------------------------------------------------------
@@ -365,8 +375,11 @@ struct CellDev   // cell mode parameters (by value)
 // DBUF: the j-tile is double-buffered -- tile t+1 is copied global -> shared asynchronously (cp.async, LDGSTS) while tile t is
 // evaluated, one barrier per tile instead of two.  +1.4 % on config 2 (long j ranges); it costs 8 KB of shared memory, so the
 // host selects it only when the resident-block count is unchanged (profiles/r02_k3_tuning.md: config 3 / 5 lose 2.7 % with it).
+#ifndef B2A_K3_CELL_MINB
+#define B2A_K3_CELL_MINB 10
+#endif
 template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, int MODE, bool DBUF = false>
-__global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
+__global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (MODE == 2 ? B2A_K3_CELL_MINB : 1)) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
                                                   const double* __restrict__ cenA, const double* __restrict__ cenB,
                                                   const unsigned* __restrict__ slab_cnt,
                                                   const RdfFrame* __restrict__ frames, RdfDev p, CellDev cd,
@@ -375,6 +388,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
 {
     constexpr int  TI  = IPT * THREADS;
     constexpr bool SYM = MODE == 1;
+    constexpr bool WM  = MODE == 2;   // warp-major i slots (slot_il)
     constexpr bool kDbuf = DBUF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int4*     sj    = reinterpret_cast<int4*>(smem_raw);                                   // kTileJ (x 2 when double-buffered)
@@ -515,15 +529,16 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
         {
             const unsigned ent = queue[e];
             const int      jg  = (int)(ent >> 7);
-            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, (int)(ent & 127u), B[jg], jg);
+            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID, WM>(&blk, (int)(ent & 127u), B[jg], jg);
         }
         carry = rem;
         ++sub;
         __syncthreads();
     };
 
-    // stream the j-molecules [ja, jb) of B against the i-molecules currently held in registers
-    auto process_range = [&](int ja, int jb) {
+    // stream the j-molecules [ja, jb) of B against the i-molecules currently held in registers; cell mode: this warp evaluates
+    // only [wa, wb) (the part of the run its own molecules can reach) and just keeps the block's barriers for the rest
+    auto process_range = [&](int ja, int jb, int wa, int wb) {
         const bool partial = tcount < TI;
         auto prefetch = [&](int4* dst, int jt) {   // kDbuf: asynchronous global -> shared copy of one j-tile (LDGSTS, 16 bytes per thread and request)
             const int cnt = min(kTileJ, jb - jt);
@@ -555,10 +570,11 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
             {
                 const int je = min(cnt, js + kSubJ);
                 unsigned* qc = &q_count[sub & 1];
+                const int jlo = WM ? max(js, wa - jt) : js, jhi = WM ? min(je, wb - jt) : je;
                 if (!partial)
                 {
 #pragma unroll 2
-                    for (int j = js; j < je; ++j)
+                    for (int j = jlo; j < jhi; ++j)
                     {
                         const int4 pj   = sj[j];
                         unsigned   dacc = 0, kmin = 0xffffffffu;
@@ -594,7 +610,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                             if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
                             else
                             {
-                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
+                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID, WM>(&blk, threadIdx.x, pj, jt + j);
                                 atomicAdd(&blk.stats[3], 1u);
                             }
                         }
@@ -606,9 +622,9 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                     // trash word and never raise a candidate
                     bool okq[IPT];
 #pragma unroll
-                    for (int q = 0; q < IPT; ++q) okq[q] = (int)(threadIdx.x + q * THREADS) < tcount;
+                    for (int q = 0; q < IPT; ++q) okq[q] = slot_il<IPT, THREADS, WM>((int)threadIdx.x, q) < tcount;
 #pragma unroll 1
-                    for (int j = js; j < je; ++j)
+                    for (int j = jlo; j < jhi; ++j)
                     {
                         const int4 pj   = sj[j];
                         unsigned   dacc = 0, kmin = 0xffffffffu;
@@ -645,7 +661,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                             if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
                             else
                             {
-                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
+                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID, WM>(&blk, threadIdx.x, pj, jt + j);
                                 atomicAdd(&blk.stats[3], 1u);
                             }
                         }
@@ -655,7 +671,8 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
             }
             if (kDbuf) sj = sj == sjbuf ? sjbuf + kTileJ : sjbuf;
         }
-        npairs += (unsigned long long)tcount * (unsigned long long)(jb > ja ? jb - ja : 0);
+        if (WM) npairs += (unsigned long long)max(0, min(tcount - (int)(threadIdx.x >> 5) * 32 * IPT, 32 * IPT)) * (unsigned long long)(wb > wa ? wb - wa : 0);
+        else npairs += (unsigned long long)tcount * (unsigned long long)(jb > ja ? jb - ja : 0);
     };
 
     auto load_tile = [&]() {
@@ -663,7 +680,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
 #pragma unroll
         for (int q = 0; q < IPT; ++q)
         {
-            const int  il = threadIdx.x + q * THREADS;
+            const int  il = slot_il<IPT, THREADS, WM>((int)threadIdx.x, q);
             const int4 a  = il < tcount ? A[il] : make_int4(0, 0, 0, 0);
             xi[q] = a.x; yi[q] = a.y; zi[q] = a.z;
         }
@@ -672,7 +689,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
     if (MODE != 2)
     {
         load_tile();
-        process_range(j0, j1);
+        process_range(j0, j1, j0, j1);
         drain(true);
         nsel = SYM ? (weight == 1 ? tcount : 0) : (blockIdx.y == 0 ? tcount : 0);
     }
@@ -690,12 +707,17 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
             drain(true);       // candidates of the previous tile name ITS molecules: re-examine them before blk.A / blk.tcount change
             if (threadIdx.x == 0) { blk.A = sortedA + (size_t)f * p.n0 + tstart; blk.tcount = tcount; }
             load_tile();
-            if (csym && crole == 1) { process_range(tstart, tstart + tcount); continue; }   // the tile against itself (drained at the next tile / the end)
+            if (csym && crole == 1) { process_range(tstart, tstart + tcount, tstart, tstart + tcount); continue; }   // the tile against itself (drained at the next tile / the end)
             nsel += tcount;
             const int jmin = csym ? tstart + tcount : 0;   // symmetric: only sorted positions beyond the tile
             // cells the tile spans along z (cell = top bits of the fixed-point coordinate; the column is sorted by it)
             const int4* At  = sortedA + (size_t)f * p.n0 + tstart;
             const int   cza = (int)((unsigned)At[0].z >> zsh), czb = (int)((unsigned)At[tcount - 1].z >> zsh);
+            // ... and the cells this WARP's molecules span (warp-major slots): it evaluates a j cell only if that cell is within
+            // reach of its own span.  With a 256-molecule tile over ~7 cells and a reach of 3, each warp skips ~3 of the run's 13 cells.
+            const int   wi0 = (int)(threadIdx.x >> 5) * 32 * IPT, wi1 = min(tcount, wi0 + 32 * IPT);
+            const bool  whas = wi0 < tcount && !cd.no_warp_span;
+            const int   cwa = whas ? (int)((unsigned)At[wi0].z >> zsh) : cza, cwb = whas ? (int)((unsigned)At[wi1 - 1].z >> zsh) : czb;
             for (int ix = 0; ix < nx; ++ix)
                 for (int iy = 0; iy < ny; ++iy)
                 {
@@ -705,18 +727,26 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                     const int      cx  = (ccx - (nx >> 1) + ix + nc) & (nc - 1);
                     const int      cy  = (ccy - (ny >> 1) + iy + nc) & (nc - 1);
                     const unsigned col = ((unsigned)cx << cd.bits | (unsigned)cy) << cd.bits;
-                    if (z1 - z0 + 1 >= nc) { process_range(max(jmin, (int)sb[col]), (int)sb[col + nc]); continue; }
-                    if (z0 < 0)
+                    if (z1 - z0 + 1 >= nc)
                     {
-                        process_range(max(jmin, (int)sb[col + z0 + nc]), (int)sb[col + nc]);
-                        process_range(max(jmin, (int)sb[col]), (int)sb[col + z1 + 1]);
+                        const int ja = max(jmin, (int)sb[col]), jb = (int)sb[col + nc];
+                        process_range(ja, jb, ja, jb);
+                        continue;
                     }
-                    else if (z1 >= nc)
-                    {
-                        process_range(max(jmin, (int)sb[col + z0]), (int)sb[col + nc]);
-                        process_range(max(jmin, (int)sb[col]), (int)sb[col + z1 - nc + 1]);
-                    }
-                    else process_range(max(jmin, (int)sb[col + z0]), (int)sb[col + z1 + 1]);
+                    // The run [z0, z1] is shorter than the axis, so every cell of the column has exactly one image in it and the
+                    // warp's own interval [w0, w1] (a sub-interval) selects cells by that image.  A piece = cells [u0, u1] of the
+                    // run that are contiguous in the sorted array, `off` maps the unwrapped index to the stored one.
+                    const int w0 = cwa - rzc, w1 = cwb + rzc;
+                    auto piece = [&](int u0, int u1, int off) {
+                        const int ja = max(jmin, (int)sb[col + u0 + off]), jb = (int)sb[col + u1 + off + 1];
+                        const int a = max(u0, w0), b = min(u1, w1);
+                        int       wa = 0, wb = 0;
+                        if (a <= b) { wa = max(ja, (int)sb[col + a + off]); wb = min(jb, (int)sb[col + b + off + 1]); }
+                        process_range(ja, jb, wa, wb);
+                    };
+                    if (z0 < 0) { piece(z0, -1, nc); piece(0, z1, 0); }
+                    else if (z1 >= nc) { piece(z0, nc - 1, 0); piece(nc, z1, -nc); }
+                    else piece(z0, z1, 0);
                 }
         }
         drain(true);
@@ -734,9 +764,10 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
         if (blk.stats[1]) atomicAdd(&gstats[3], (unsigned long long)blk.stats[1] * (unsigned long long)weight);
         if (blk.stats[2]) atomicAdd(&gstats[1], (unsigned long long)blk.stats[2] * (unsigned long long)weight);
         if (blk.stats[3]) atomicAdd(&gstats[6], (unsigned long long)blk.stats[3]);
-        atomicAdd(&gstats[5], npairs);
+        if (!WM) atomicAdd(&gstats[5], npairs);
         if (nsel) atomicAdd(&gstats[4], nsel);
     }
+    if (WM && (threadIdx.x & 31u) == 0 && npairs) atomicAdd(&gstats[5], npairs);   // cell mode: every warp counted its own pairs
 }
 
 } // namespace b2a
