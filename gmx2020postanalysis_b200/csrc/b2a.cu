@@ -1186,12 +1186,12 @@ static float next_down(float v) { return std::nextafterf(v, -INFINITY); }
 static float next_up(float v) { return std::nextafterf(v, INFINITY); }
 
 template <int IPT, int THREADS, bool CUBIC, bool PARANOID, int MODE, bool DBUF = false>
-static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid)
+static int launch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, dim3 grid)
 {
     auto kern = k3_rdf<IPT, THREADS, true, CUBIC, PARANOID, MODE, DBUF>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, THREADS, smem, a.last_stream>>>(a.sortedA_view ? a.sortedA_view : a.d_sortedA, g1.d_fix[a.rdf.com1], g0.d_cen[a.rdf.com0], g1.d_cen[a.rdf.com1],
-                                            a.d_slab_cnt, a.d_frames, p, cd, a.d_hist, a.d_hist + a.ndev);
+                                            a.d_slab_cnt, a.d_frames, p, a.d_hist, a.d_hist + a.ndev);
     CU(cudaGetLastError());
     return B2A_OK;
 }
@@ -1209,25 +1209,21 @@ static int launch_rdf_cellw(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfD
 }
 
 template <int IPT, int MODE, int TH = 128>
-static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, const CellDev& cd, size_t smem, dim3 grid, bool cubic, bool dbuf = false)
+static int dispatch_rdf(b2a_ctx* c, Acc& a, Group& g0, Group& g1, const RdfDev& p, size_t smem, dim3 grid, bool cubic, bool dbuf = false)
 {
-    if constexpr (MODE != 2)
-        if (dbuf && !a.paranoid)   // double-buffered j-tile (8 KB more shared memory: the caller checked that residency is unchanged)
-            return cubic ? launch_rdf<IPT, TH, true, false, MODE, true>(c, a, g0, g1, p, cd, smem + kTileJ * sizeof(int4), grid)
-                         : launch_rdf<IPT, TH, false, false, MODE, true>(c, a, g0, g1, p, cd, smem + kTileJ * sizeof(int4), grid);
+    if (dbuf && !a.paranoid)   // double-buffered j-tile (8 KB more shared memory: the caller checked that residency is unchanged)
+        return cubic ? launch_rdf<IPT, TH, true, false, MODE, true>(c, a, g0, g1, p, smem + kTileJ * sizeof(int4), grid)
+                     : launch_rdf<IPT, TH, false, false, MODE, true>(c, a, g0, g1, p, smem + kTileJ * sizeof(int4), grid);
     if (a.paranoid)
-        return cubic ? launch_rdf<IPT, TH, true, true, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, true, MODE>(c, a, g0, g1, p, cd, smem, grid);
-    return cubic ? launch_rdf<IPT, TH, true, false, MODE>(c, a, g0, g1, p, cd, smem, grid) : launch_rdf<IPT, TH, false, false, MODE>(c, a, g0, g1, p, cd, smem, grid);
+        return cubic ? launch_rdf<IPT, TH, true, true, MODE>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, false, true, MODE>(c, a, g0, g1, p, smem, grid);
+    return cubic ? launch_rdf<IPT, TH, true, false, MODE>(c, a, g0, g1, p, smem, grid) : launch_rdf<IPT, TH, false, false, MODE>(c, a, g0, g1, p, smem, grid);
 }
 
-#ifndef B2A_CELL_THREADS
-#define B2A_CELL_THREADS 64
-#endif
-constexpr int kCellIPT = 4, kCellThreads = B2A_CELL_THREADS;   // cell mode: 256-molecule tiles (64 threads x 4): half the z span of a 512-molecule tile; measured on config 5: 512 -> 17.7 ms, 256 (128 x 2) -> 13.2, 256 (64 x 4) -> 12.5, 128 (32 x 4) -> 13.5
+constexpr int kCellIPT = 4, kCellThreads = 64;   // k5_coord cell tiles (64 threads x 4); the RDF's cell tiles are kCwTile = 128 molecules per warp
 
 // Cell grid for r_max << L: cells per dimension 2^bits, reach per dimension from the cut-off plus the fixed-point slop.
 // Returns false when cells would not cull enough to beat the brute-force (possibly symmetric) evaluation.
-// `columns`: the caller cuts its i-tiles from whole (cx, cy) columns of cells (k3_rdf MODE 2) instead of giving every cell a
+// `columns`: the caller cuts its i-tiles from whole (cx, cy) columns of cells (k3_rdf_cellw) instead of giving every cell a
 // tile of its own (k5_coord): tiles are always full, so cells may be much finer than a tile, and a tile that spans several
 // cells along z searches the union of their z ranges.
 static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_possible, int* bits, int reach[3], int ti = kCellIPT * kCellThreads,
@@ -1283,7 +1279,7 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
             // one block per tile: a small i side leaves most of the machine idle, where the all-pairs kernel would split j
             const double blocks = std::ceil(col / TI) * (double)nc * nc * c->nframes;
             cost /= std::min(1.0, blocks / (4.0 * c->sm_count));
-            if (sym_possible) cost *= 0.5;   // k3_rdf MODE 2 evaluates eligible frames symmetrically as well
+            if (sym_possible) cost *= 0.5;   // k3_rdf_cellw evaluates eligible frames symmetrically as well
         }
         if (cost < bestc) { bestc = cost; bestb = b; bestr[0] = r[0]; bestr[1] = r[1]; bestr[2] = r[2]; }
     }
@@ -1470,8 +1466,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     const int nslab = p.nslab;
     CU(cudaMemsetAsync(a.d_slab_cnt, 0, sizeof(unsigned) * 2 * (size_t)nslab * c->maxK, stm));
     int  bits = 0, reach[3] = { 0, 0, 0 };
-    const bool block_tiles = getenv("B2A_CELL_BLOCKTILE") != nullptr;   // A/B switch: the 256-molecule block tiles of k3_rdf MODE 2
-    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, block_tiles ? kCellIPT * kCellThreads : kCwTile, nullptr, true);
+    const bool cells = choose_cells(c, a, p, p.sym_enabled != 0, &bits, reach, kCwTile, nullptr, true);
     CellDev cd{};
     {
         Timed tm(c, 1, stm);
@@ -1525,7 +1520,6 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
                         cd.rzc[ix * 15 + iy] = (signed char)rz;
                     }
                 cd.use_rzc = (table && !getenv("B2A_NO_RZC")) ? 1 : 0;
-                cd.no_warp_span = getenv("B2A_NO_WSPAN") ? 1 : 0;
             }
         }
     }
@@ -1534,21 +1528,17 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
     if (cells)
     {
         RdfDev pc = p;
-        // one block row per column of i-cells; its tiles are spread over gridDim.y (a block loops if a column is more crowded)
         const double per_col = (double)p.n0 / (double)(1u << (2 * bits));
-        if (!block_tiles)
-        {
-            // every warp owns a 128-molecule tile; rows of kCwWarps tiles
-            const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCwTile * kCwWarps))));
-            const size_t smem_cw = (size_t)kCwWarps * (32 * sizeof(int4) + kCwQueue * sizeof(unsigned)) + 16 + (size_t)pc.kstride * 4;
-            const dim3   grid(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes);
-            if (a.paranoid)
-                return cubic ? launch_rdf_cellw<true, true>(c, a, *g0, *g1, pc, cd, smem_cw, grid) : launch_rdf_cellw<false, true>(c, a, *g0, *g1, pc, cd, smem_cw, grid);
-            return cubic ? launch_rdf_cellw<true, false>(c, a, *g0, *g1, pc, cd, smem_cw, grid) : launch_rdf_cellw<false, false>(c, a, *g0, *g1, pc, cd, smem_cw, grid);
-        }
-        const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCellIPT * kCellThreads))));
-        // symmetric evaluation doubles the block rows: even = beyond-the-tile part of the j runs, odd = the tile against itself
-        return dispatch_rdf<kCellIPT, 2, kCellThreads>(c, a, *g0, *g1, pc, cd, smem, dim3(cd.nkeysA >> bits, pc.sym_enabled ? 2 * ny : ny, c->nframes), cubic);
+        // every warp owns a 128-molecule tile of its column; rows of kCwWarps tiles, a block loops if a column is more crowded;
+        // symmetric evaluation appends the rows of the tiles against themselves (k3_rdf_cellw)
+        const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCwTile * kCwWarps))));
+        const size_t smem_cw = (size_t)kCwWarps * (32 * sizeof(int4) + kCwQueue * sizeof(unsigned)) + 16 + (size_t)pc.kstride * 4;
+        cd.split = 1;   // measured on config 5: 2 -> -1 %, 3 -> -2 % (the tail of the launch is not a granularity problem)
+        if (const char* e = getenv("B2A_CW_SPLIT")) cd.split = std::max(1, std::min(8, atoi(e)));
+        const dim3   grid(cd.nkeysA >> bits, (pc.sym_enabled ? cd.split + 1 : cd.split) * ny, c->nframes);
+        if (a.paranoid)
+            return cubic ? launch_rdf_cellw<true, true>(c, a, *g0, *g1, pc, cd, smem_cw, grid) : launch_rdf_cellw<false, true>(c, a, *g0, *g1, pc, cd, smem_cw, grid);
+        return cubic ? launch_rdf_cellw<true, false>(c, a, *g0, *g1, pc, cd, smem_cw, grid) : launch_rdf_cellw<false, false>(c, a, *g0, *g1, pc, cd, smem_cw, grid);
     }
     constexpr int TI = 8 * 128;   // TI molecules of one slab per block
     bool          dbuf = false;
@@ -1571,7 +1561,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         p.jchunk           = (p.n1 + jsplit - 1) / jsplit;
         p.jchunk           = ((p.jchunk + kTileJ - 1) / kTileJ) * kTileJ;
         p.jsplit           = (p.n1 + p.jchunk - 1) / p.jchunk;
-        if (int rc = dispatch_rdf<8, 0>(c, a, *g0, *g1, p, cd, smem, dim3(max_tiles, p.jsplit, c->nframes), cubic, dbuf)) return rc;
+        if (int rc = dispatch_rdf<8, 0>(c, a, *g0, *g1, p, smem, dim3(max_tiles, p.jsplit, c->nframes), cubic, dbuf)) return rc;
     }
     if (p.sym_enabled)
     {
@@ -1582,7 +1572,7 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         const int T = (p.n0 + TI - 1) / TI;
         long long items = 0;
         for (int t = 0; t < T; ++t) items += 1 + (std::max(0, p.n0 - (t + 1) * TI) + ps.jchunk - 1) / ps.jchunk;
-        if (int rc = dispatch_rdf<8, 1>(c, a, *g0, *g1, ps, cd, smem, dim3((unsigned)items, 1, c->nframes), cubic, dbuf)) return rc;
+        if (int rc = dispatch_rdf<8, 1>(c, a, *g0, *g1, ps, smem, dim3((unsigned)items, 1, c->nframes), cubic, dbuf)) return rc;
     }
     return B2A_OK;
 }

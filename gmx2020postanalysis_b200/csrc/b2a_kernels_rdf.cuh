@@ -230,18 +230,9 @@ struct RdfBlock   // block-uniform state shared by the hot loop and the cold pat
     unsigned      stats[4];   // exact, moved, dropped, overflow
 };
 
-// Which molecule of the i-tile does register slot q of thread t hold?  Thread-major (all-pairs modes): slot q = the q-th stripe of
-// THREADS molecules.  Warp-major (cell mode): every warp holds 32 * IPT CONSECUTIVE molecules of the (z-sorted) column, so a warp
-// covers a short z span of its own and skips the j cells only the block's other warps can reach.
-template <int IPT, int THREADS, bool WM>
-__device__ __forceinline__ int slot_il(int t, int q)
-{
-    return WM ? ((t >> 5) * (32 * IPT) + q * 32 + (t & 31)) : (t + q * THREADS);
-}
-
 // Re-examine the IPT pairs (thread t's molecules) x (one j): recompute the FP32 bins, and for every pair the
 // FP32 bracket could not decide run the exact FP64 evaluation and move the count if needed.
-template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, bool WM = false>
+template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID>
 __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
 {
     // phase 1 (converged across the warp): FP32 bins of the thread's IPT pairs, remember the undecided ones
@@ -250,7 +241,7 @@ __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
 #pragma unroll
     for (int q = 0; q < IPT; ++q)
     {
-        const int  il = slot_il<IPT, THREADS, WM>(t, q);
+        const int  il = t + q * THREADS;
         const bool ok = il < b->tcount;
         const int4 a  = ok ? b->A[il] : make_int4(0, 0, 0, 0);
         unsigned   k1, k2;
@@ -269,7 +260,7 @@ __device__ __noinline__ void recheck(RdfBlock* b, int t, int4 pj, int jglobal)
 #pragma unroll
         for (int u = 0; u < IPT; ++u) k1 = (u == q) ? k1v[u] : k1;
         const int k1idx = (int)(k1 - kMagicBits);
-        const int iorig = b->A[slot_il<IPT, THREADS, WM>(t, q)].w;
+        const int iorig = b->A[t + q * THREADS].w;
         const int ke    = exact_bin(b->cA, b->cB, b->n0, b->n1, iorig, jorig, b->L0, b->L1, b->L2, b->rm2, b->Rbin_d, b->Rm, b->Rbin);
         atomicAdd(&b->stats[0], 1u);
         if (ke == -2) atomicAdd(&b->stats[2], 1u);
@@ -361,34 +352,29 @@ struct CellDev   // cell mode parameters (by value)
     // all entries = rz when a reach covers its whole axis.
     signed char     rzc[15 * 15];
     int             use_rzc;       // 0: reaches above 7 cells (the table does not cover them): every column uses rz
-    int             no_warp_span;  // experiment switch (B2A_NO_WSPAN): every warp evaluates the whole run of its block
+    int             split;         // k3_rdf_cellw: the neighbour columns of a tile are dealt to this many blocks
 };
 
 // ---- main kernel ------------------------------------------------------------------------------------------
 // MODE 0 (full) : grid x = i-tile (over slabs), y = j-split, z = frame
 // MODE 1 (sym)  : grid x = work item (i-tile, j-chunk beyond the tile | diagonal), z = frame; frames that are not
 //                 eligible (not all molecules in one slab) are skipped here and done by the full kernel, and vice versa
-// MODE 2 (cell) : grid x = (slab, cx, cy) column of i-cells, y = tile of the column, z = frame; j runs over the neighbouring
-//                 columns, restricted to the cells within reach of the tile's own z span
+// (the cell-binned evaluation for r_max << L is a kernel of its own: k3_rdf_cellw in b2a_kernels_rdf_cell.cuh)
 // (launch bound: 6 resident blocks of the 8 x 128 tile = 80 registers instead of the 96 the compiler takes unconstrained, 36 bytes
 //  of spills: 634.7 -> 652.4 frames/s on config 2; 7 blocks = 72 registers spill into the hot loop: 603.7)
 // DBUF: the j-tile is double-buffered -- tile t+1 is copied global -> shared asynchronously (cp.async, LDGSTS) while tile t is
 // evaluated, one barrier per tile instead of two.  +1.4 % on config 2 (long j ranges); it costs 8 KB of shared memory, so the
 // host selects it only when the resident-block count is unchanged (profiles/r02_k3_tuning.md: config 3 / 5 lose 2.7 % with it).
-#ifndef B2A_K3_CELL_MINB
-#define B2A_K3_CELL_MINB 10
-#endif
 template <int IPT, int THREADS, bool CLAMP, bool CUBIC, bool PARANOID, int MODE, bool DBUF = false>
-__global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (MODE == 2 ? B2A_K3_CELL_MINB : 1)) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
+__global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1) k3_rdf(const int4* __restrict__ sortedA, const int4* __restrict__ fixB,
                                                   const double* __restrict__ cenA, const double* __restrict__ cenB,
                                                   const unsigned* __restrict__ slab_cnt,
-                                                  const RdfFrame* __restrict__ frames, RdfDev p, CellDev cd,
+                                                  const RdfFrame* __restrict__ frames, RdfDev p,
                                                   unsigned long long* __restrict__ ghist,
                                                   unsigned long long* __restrict__ gstats)
 {
     constexpr int  TI  = IPT * THREADS;
     constexpr bool SYM = MODE == 1;
-    constexpr bool WM  = MODE == 2;   // warp-major i slots (slot_il)
     constexpr bool kDbuf = DBUF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int4*     sj    = reinterpret_cast<int4*>(smem_raw);                                   // kTileJ (x 2 when double-buffered)
@@ -400,9 +386,6 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
 
     const int f = blockIdx.z;
     int       slab = -1, tstart = 0, tcount = 0, j0 = 0, j1 = 0, weight = 1;
-    int       cell_a0 = 0, cell_a1 = 0, ccx = 0, ccy = 0, crole = 0, cny = 1;
-    bool      csym = false;   // cell mode: this frame is evaluated symmetrically
-    if (MODE != 2)
     {
         // is this frame eligible for symmetric evaluation?  (every molecule passed the filter into ONE slab)
         int sym_slab = -1;
@@ -446,43 +429,9 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
         }
         if (slab < 0 || j1 <= j0) return;   // block-uniform
     }
-    else
-    {
-        // one block per COLUMN of i-cells (fixed slab, cx, cy): the sorted array holds a column's molecules contiguously, in
-        // order of cz, so full tiles of TI molecules are cut from it regardless of how few molecules one cell holds
-        const unsigned  col = blockIdx.x;
-        const unsigned* sa  = cd.startA + (size_t)f * (cd.nkeysA + 1);
-        cell_a0 = (int)sa[col << cd.bits];
-        cell_a1 = (int)sa[(col << cd.bits) + (1u << cd.bits)];
-        const unsigned mask = (1u << cd.bits) - 1u;
-        slab = (int)(col >> (2 * cd.bits));
-        ccy  = (int)(col & mask);
-        ccx  = (int)((col >> cd.bits) & mask);
-        // Symmetric evaluation in cell mode (same molecules on both sides, every molecule of the frame in ONE slab): the j side
-        // is the i side's own sorted array, and a pair of sorted positions t1 < t2 is evaluated once, by the tile that holds
-        // t1, with weight 2 (the neighbourhood relation of cells is symmetric, so t1 lies in the j runs of t2's tile exactly
-        // when t2 lies in the j runs of t1's).  Block rows alternate: even = the part of every j run BEYOND the tile, weight 2;
-        // odd = the tile against itself in full (both orders of every pair, self pairs rejected by the exact path), weight 1.
-        if (p.sym_enabled)
-        {
-            csym = slab_cnt[(size_t)f * p.nslab + slab] == (unsigned)p.n0;
-            crole = (int)(blockIdx.y & 1u);
-            if (crole == 1 && !csym) return;       // nothing to do for a diagonal block of an ineligible frame
-            cny = (int)(gridDim.y >> 1);
-            tstart = cell_a0 + (int)(blockIdx.y >> 1) * TI;
-            if (csym) weight = crole == 0 ? 2 : 1;
-        }
-        else
-        {
-            cny = (int)gridDim.y;
-            tstart = cell_a0 + (int)blockIdx.y * TI;   // the tiles of a column are spread over gridDim.y blocks
-        }
-        if (tstart >= cell_a1) return;             // empty column / no tile left: block-uniform
-        tcount = min(TI, cell_a1 - tstart);
-    }
 
     const RdfFrame fr = frames[f];
-    const int4*    B  = (MODE == 1 || (MODE == 2 && csym)) ? sortedA + (size_t)f * p.n0 : (MODE == 2 ? cd.sortedB + (size_t)f * p.n1 : fixB + (size_t)f * p.n1);
+    const int4*    B  = MODE == 1 ? sortedA + (size_t)f * p.n0 : fixB + (size_t)f * p.n1;
     for (unsigned k = threadIdx.x; k < p.kstride; k += THREADS) hist[(int)k - 1] = 0;
     if (threadIdx.x == 0)
     {
@@ -529,16 +478,15 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
         {
             const unsigned ent = queue[e];
             const int      jg  = (int)(ent >> 7);
-            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID, WM>(&blk, (int)(ent & 127u), B[jg], jg);
+            recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, (int)(ent & 127u), B[jg], jg);
         }
         carry = rem;
         ++sub;
         __syncthreads();
     };
 
-    // stream the j-molecules [ja, jb) of B against the i-molecules currently held in registers; cell mode: this warp evaluates
-    // only [wa, wb) (the part of the run its own molecules can reach) and just keeps the block's barriers for the rest
-    auto process_range = [&](int ja, int jb, int wa, int wb) {
+    // stream the j-molecules [ja, jb) of B against the i-molecules currently held in registers
+    auto process_range = [&](int ja, int jb) {
         const bool partial = tcount < TI;
         auto prefetch = [&](int4* dst, int jt) {   // kDbuf: asynchronous global -> shared copy of one j-tile (LDGSTS, 16 bytes per thread and request)
             const int cnt = min(kTileJ, jb - jt);
@@ -570,11 +518,10 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
             {
                 const int je = min(cnt, js + kSubJ);
                 unsigned* qc = &q_count[sub & 1];
-                const int jlo = WM ? max(js, wa - jt) : js, jhi = WM ? min(je, wb - jt) : je;
                 if (!partial)
                 {
 #pragma unroll 2
-                    for (int j = jlo; j < jhi; ++j)
+                    for (int j = js; j < je; ++j)
                     {
                         const int4 pj   = sj[j];
                         unsigned   dacc = 0, kmin = 0xffffffffu;
@@ -610,7 +557,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
                             if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
                             else
                             {
-                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID, WM>(&blk, threadIdx.x, pj, jt + j);
+                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
                                 atomicAdd(&blk.stats[3], 1u);
                             }
                         }
@@ -622,9 +569,9 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
                     // trash word and never raise a candidate
                     bool okq[IPT];
 #pragma unroll
-                    for (int q = 0; q < IPT; ++q) okq[q] = slot_il<IPT, THREADS, WM>((int)threadIdx.x, q) < tcount;
+                    for (int q = 0; q < IPT; ++q) okq[q] = (int)(threadIdx.x + q * THREADS) < tcount;
 #pragma unroll 1
-                    for (int j = jlo; j < jhi; ++j)
+                    for (int j = js; j < je; ++j)
                     {
                         const int4 pj   = sj[j];
                         unsigned   dacc = 0, kmin = 0xffffffffu;
@@ -661,7 +608,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
                             if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
                             else
                             {
-                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID, WM>(&blk, threadIdx.x, pj, jt + j);
+                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
                                 atomicAdd(&blk.stats[3], 1u);
                             }
                         }
@@ -671,8 +618,7 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
             }
             if (kDbuf) sj = sj == sjbuf ? sjbuf + kTileJ : sjbuf;
         }
-        if (WM) npairs += (unsigned long long)max(0, min(tcount - (int)(threadIdx.x >> 5) * 32 * IPT, 32 * IPT)) * (unsigned long long)(wb > wa ? wb - wa : 0);
-        else npairs += (unsigned long long)tcount * (unsigned long long)(jb > ja ? jb - ja : 0);
+        npairs += (unsigned long long)tcount * (unsigned long long)(jb > ja ? jb - ja : 0);
     };
 
     auto load_tile = [&]() {
@@ -680,77 +626,16 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
 #pragma unroll
         for (int q = 0; q < IPT; ++q)
         {
-            const int  il = slot_il<IPT, THREADS, WM>((int)threadIdx.x, q);
+            const int  il = threadIdx.x + q * THREADS;
             const int4 a  = il < tcount ? A[il] : make_int4(0, 0, 0, 0);
             xi[q] = a.x; yi[q] = a.y; zi[q] = a.z;
         }
     };
 
-    if (MODE != 2)
-    {
-        load_tile();
-        process_range(j0, j1, j0, j1);
-        drain(true);
-        nsel = SYM ? (weight == 1 ? tcount : 0) : (blockIdx.y == 0 ? tcount : 0);
-    }
-    else
-    {
-        const int       nc   = 1 << cd.bits;
-        // j runs: offsets of the j side's sort -- in symmetric frames the i side's own, restricted to its (single) slab
-        const unsigned* sb   = csym ? cd.startA + (size_t)f * (cd.nkeysA + 1) + ((size_t)slab << (3 * cd.bits)) : cd.startB + (size_t)f * (cd.nkeysB + 1);
-        // distinct neighbour columns: if the reach covers the whole axis, visit every cell of that axis once
-        const int nx = min(2 * cd.rx + 1, nc), ny = min(2 * cd.ry + 1, nc);
-        const unsigned  zsh  = 32u - (unsigned)cd.bits;
-        for (; tstart < cell_a1; tstart += TI * cny)
-        {
-            tcount = min(TI, cell_a1 - tstart);
-            drain(true);       // candidates of the previous tile name ITS molecules: re-examine them before blk.A / blk.tcount change
-            if (threadIdx.x == 0) { blk.A = sortedA + (size_t)f * p.n0 + tstart; blk.tcount = tcount; }
-            load_tile();
-            if (csym && crole == 1) { process_range(tstart, tstart + tcount, tstart, tstart + tcount); continue; }   // the tile against itself (drained at the next tile / the end)
-            nsel += tcount;
-            const int jmin = csym ? tstart + tcount : 0;   // symmetric: only sorted positions beyond the tile
-            // cells the tile spans along z (cell = top bits of the fixed-point coordinate; the column is sorted by it)
-            const int4* At  = sortedA + (size_t)f * p.n0 + tstart;
-            const int   cza = (int)((unsigned)At[0].z >> zsh), czb = (int)((unsigned)At[tcount - 1].z >> zsh);
-            // ... and the cells this WARP's molecules span (warp-major slots): it evaluates a j cell only if that cell is within
-            // reach of its own span.  With a 256-molecule tile over ~7 cells and a reach of 3, each warp skips ~3 of the run's 13 cells.
-            const int   wi0 = (int)(threadIdx.x >> 5) * 32 * IPT, wi1 = min(tcount, wi0 + 32 * IPT);
-            const bool  whas = wi0 < tcount && !cd.no_warp_span;
-            const int   cwa = whas ? (int)((unsigned)At[wi0].z >> zsh) : cza, cwb = whas ? (int)((unsigned)At[wi1 - 1].z >> zsh) : czb;
-            for (int ix = 0; ix < nx; ++ix)
-                for (int iy = 0; iy < ny; ++iy)
-                {
-                    const int rzc = cd.use_rzc ? (int)cd.rzc[ix * 15 + iy] : cd.rz;
-                    if (rzc < 0) continue;                           // the whole column lies outside the cut-off sphere (block-uniform)
-                    const int z0 = cza - rzc, z1 = czb + rzc;        // inclusive, may leave [0, nc)
-                    const int      cx  = (ccx - (nx >> 1) + ix + nc) & (nc - 1);
-                    const int      cy  = (ccy - (ny >> 1) + iy + nc) & (nc - 1);
-                    const unsigned col = ((unsigned)cx << cd.bits | (unsigned)cy) << cd.bits;
-                    if (z1 - z0 + 1 >= nc)
-                    {
-                        const int ja = max(jmin, (int)sb[col]), jb = (int)sb[col + nc];
-                        process_range(ja, jb, ja, jb);
-                        continue;
-                    }
-                    // The run [z0, z1] is shorter than the axis, so every cell of the column has exactly one image in it and the
-                    // warp's own interval [w0, w1] (a sub-interval) selects cells by that image.  A piece = cells [u0, u1] of the
-                    // run that are contiguous in the sorted array, `off` maps the unwrapped index to the stored one.
-                    const int w0 = cwa - rzc, w1 = cwb + rzc;
-                    auto piece = [&](int u0, int u1, int off) {
-                        const int ja = max(jmin, (int)sb[col + u0 + off]), jb = (int)sb[col + u1 + off + 1];
-                        const int a = max(u0, w0), b = min(u1, w1);
-                        int       wa = 0, wb = 0;
-                        if (a <= b) { wa = max(ja, (int)sb[col + a + off]); wb = min(jb, (int)sb[col + b + off + 1]); }
-                        process_range(ja, jb, wa, wb);
-                    };
-                    if (z0 < 0) { piece(z0, -1, nc); piece(0, z1, 0); }
-                    else if (z1 >= nc) { piece(z0, nc - 1, 0); piece(nc, z1, -nc); }
-                    else piece(z0, z1, 0);
-                }
-        }
-        drain(true);
-    }
+    load_tile();
+    process_range(j0, j1);
+    drain(true);
+    nsel = SYM ? (weight == 1 ? tcount : 0) : (blockIdx.y == 0 ? tcount : 0);
     __syncthreads();
     unsigned long long* gh = ghist + (size_t)slab * p.Rbin;
     for (int k = threadIdx.x; k < p.Rbin; k += THREADS)
@@ -764,10 +649,9 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : (M
         if (blk.stats[1]) atomicAdd(&gstats[3], (unsigned long long)blk.stats[1] * (unsigned long long)weight);
         if (blk.stats[2]) atomicAdd(&gstats[1], (unsigned long long)blk.stats[2] * (unsigned long long)weight);
         if (blk.stats[3]) atomicAdd(&gstats[6], (unsigned long long)blk.stats[3]);
-        if (!WM) atomicAdd(&gstats[5], npairs);
+        atomicAdd(&gstats[5], npairs);
         if (nsel) atomicAdd(&gstats[4], nsel);
     }
-    if (WM && (threadIdx.x & 31u) == 0 && npairs) atomicAdd(&gstats[5], npairs);   // cell mode: every warp counted its own pairs
 }
 
 } // namespace b2a

@@ -5,11 +5,16 @@
 //   * no block barrier between the first and the last pair: j-molecules are staged 32 at a time in a per-warp shared slot (one
 //     coalesced LDG.128 per lane, the next chunk in flight while this one is evaluated, LDS.128 broadcast per j), candidates go to a
 //     per-warp queue through a ballot (no atomic), and a warp drains its own queue in full rounds of 32;
-//   * a 128-molecule tile spans ~3.5 cells of the column instead of the ~7 of the 256-molecule block tile of k3_rdf MODE 2, so with a
-//     reach of three cells it searches ~9.5 cells of every neighbour column instead of 13 -- and unlike per-warp sub-ranges inside a
-//     block tile (measured: the block's barriers keep the critical path at 13 cells, +3 % only) the saving is not waited away;
+//   * a 128-molecule tile spans ~3.5 cells of the column instead of the ~7 of a 256-molecule block tile (the round-1 design: one
+//     block per tile, j staged per block), so with a reach of three cells it searches ~9.5 cells of every neighbour column instead
+//     of 13 -- and unlike per-warp sub-ranges inside a block tile (measured: the block's barriers keep the critical path at 13
+//     cells, +3 % only) the saving is not waited away;
+//   * several j-iterations share one candidate test (B2A_CW_J2): independent dependency chains in flight, one vote and one branch;
 //   * the warps of a block share only the histogram (zeroed at the start, flushed with the block's weight at the end).
-// Symmetric evaluation, slabs, the per-column z reach table and the role of block rows are those of k3_rdf MODE 2.
+// Symmetric evaluation in cell mode (same molecules on both sides, every molecule of the frame in ONE slab): the j side is the i
+// side's own sorted array, and a pair of sorted positions t1 < t2 is evaluated once, by the tile that holds t1, with weight 2 (the
+// neighbourhood relation of cells is symmetric, so t1 lies in the j runs of t2's tile exactly when t2 lies in the j runs of t1's);
+// the tiles against themselves are separate block rows with weight 1 (both orders of every pair, self pairs rejected by the exact path).
 #pragma once
 
 #include <type_traits>
@@ -21,7 +26,10 @@ namespace b2a
 
 constexpr int kCwIPT   = 4;     // i-molecules per lane
 constexpr int kCwTile  = 32 * kCwIPT;
-constexpr int kCwQueue = 128;   // candidate entries per warp; drained from 96 up, a j-iteration adds at most 32
+#ifndef B2A_CW_J2
+#define B2A_CW_J2 4             // j-iterations per candidate test (measured on config 5: 1 -> 96.9 frames/s, 2 -> 106.0, 3 -> 105.5, 4 -> 107.4)
+#endif
+constexpr int kCwQueue = 96 + 32 * (B2A_CW_J2 > 1 ? B2A_CW_J2 : 1);   // candidate entries per warp; drained from 96 up, a test adds at most 32 per j-iteration
 #ifndef B2A_CW_NW
 #define B2A_CW_NW 2
 #endif
@@ -49,18 +57,24 @@ __global__ void __launch_bounds__(32 * NW, B2A_CW_WARPS_PER_SM / NW)
     unsigned* const wq  = wq_all + warp * kCwQueue;
     RdfBlock* const blk = &wblk[warp];
 
-    // block row -> column of i-cells, role, first tile (as k3_rdf MODE 2, tiles of TW molecules dealt to warps)
+    // block row -> column of i-cells (fixed slab, cx, cy): the sorted array holds a column's molecules contiguously, in order of cz, so
+    // full tiles of TW molecules are cut from it regardless of how few molecules one cell holds; tiles are dealt to warps
     const unsigned  colA = blockIdx.x;
     const unsigned* sa   = cd.startA + (size_t)f * (cd.nkeysA + 1);
     const int       cell_a0 = (int)sa[colA << cd.bits], cell_a1 = (int)sa[(colA << cd.bits) + (1u << cd.bits)];
     const unsigned  cmask = (1u << cd.bits) - 1u;
     const int       slab = (int)(colA >> (2 * cd.bits)), ccy = (int)(colA & cmask), ccx = (int)((colA >> cd.bits) & cmask);
     bool csym = false;
-    int  crole = 0, row = (int)blockIdx.y, nrows = (int)gridDim.y, weight = 1;
+    // block rows: [0, split * nrows) = tile rows x parts of the neighbour-column list; symmetric evaluation appends nrows rows
+    // for the tiles against themselves (light: they fill the tail of the launch)
+    const int split = cd.split;
+    int       crole = 0, row = (int)blockIdx.y, part = 0, weight = 1;
+    int       nrows = p.sym_enabled ? (int)gridDim.y / (split + 1) : (int)gridDim.y / split;
+    if (row >= split * nrows) { crole = 1; row -= split * nrows; }
+    else { part = row % split; row /= split; }
     if (p.sym_enabled)
     {
-        csym  = slab_cnt[(size_t)f * p.nslab + slab] == (unsigned)p.n0;
-        crole = row & 1; row >>= 1; nrows >>= 1;
+        csym = slab_cnt[(size_t)f * p.nslab + slab] == (unsigned)p.n0;
         if (crole == 1 && !csym) return;
         if (csym) weight = crole == 0 ? 2 : 1;
     }
@@ -121,11 +135,7 @@ __global__ void __launch_bounds__(32 * NW, B2A_CW_WARPS_PER_SM / NW)
     auto chunk = [&](auto qn_c, auto part_c, int jc, int cnt) {
         constexpr int  QN   = decltype(qn_c)::value;
         constexpr bool PART = decltype(part_c)::value;
-#pragma unroll 2
-        for (int j = 0; j < cnt; ++j)
-        {
-            const int4 pj   = wsj[j];
-            unsigned   dacc = 0, kmin = 0xffffffffu;
+        auto eval = [&](const int4& pj, unsigned& dacc, unsigned& kmin) {
 #pragma unroll
             for (int q = 0; q < QN; q += 2)
             {
@@ -147,13 +157,52 @@ __global__ void __launch_bounds__(32 * NW, B2A_CW_WARPS_PER_SM / NW)
                     kmin = min(kmin, min(okq[q] ? k1a : 0xffffffffu, okq[q + 1] ? k1b : 0xffffffffu));
                 }
             }
+        };
+        int j = 0;
+#if B2A_CW_J2 > 1
+        // several j per candidate test: independent dependency chains in flight, one vote and one branch for all of them
+        constexpr int JB = B2A_CW_J2;
+#pragma unroll 1
+        for (; j + JB <= cnt; j += JB)
+        {
+            unsigned d[JB], m[JB];
+            bool     cj[JB], any = false;
+#pragma unroll
+            for (int u = 0; u < JB; ++u)
+            {
+                const int4 pj = wsj[j + u];
+                d[u] = 0; m[u] = 0xffffffffu;
+                eval(pj, d[u], m[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < JB; ++u) { cj[u] = PARANOID || d[u] != 0 || m[u] <= lowk; any = any || cj[u]; }
+            if (__ballot_sync(0xffffffffu, any))   // warp-uniform
+            {
+#pragma unroll
+                for (int u = 0; u < JB; ++u)
+                {
+                    const unsigned b = __ballot_sync(0xffffffffu, cj[u]);
+                    if (cj[u]) wq[qn + __popc(b & ltmask)] = ((unsigned)(jc + j + u) << 5) | (unsigned)lane;
+                    qn += __popc(b);
+                }
+                if (qn >= (unsigned)(kCwQueue - 32 * JB)) drain(false);
+            }
+        }
+#else
+#pragma unroll 2
+#endif
+        for (; j < cnt; ++j)
+        {
+            const int4 pj   = wsj[j];
+            unsigned   dacc = 0, kmin = 0xffffffffu;
+            eval(pj, dacc, kmin);
             const bool     cand = PARANOID || dacc != 0 || kmin <= lowk;
             const unsigned m    = __ballot_sync(0xffffffffu, cand);
             if (m)   // warp-uniform
             {
                 if (cand) wq[qn + __popc(m & ltmask)] = ((unsigned)(jc + j) << 5) | (unsigned)lane;
                 qn += __popc(m);
-                if (qn >= (unsigned)(kCwQueue - 32)) drain(false);
+                if (qn >= (unsigned)(kCwQueue - 32 * (B2A_CW_J2 > 1 ? B2A_CW_J2 : 1))) drain(false);
             }
         }
     };
@@ -197,11 +246,11 @@ __global__ void __launch_bounds__(32 * NW, B2A_CW_WARPS_PER_SM / NW)
             const int4 a = okq[q] ? At[il] : make_int4(0, 0, 0, 0);
             xi[q] = a.x; yi[q] = a.y; zi[q] = a.z;
         }
-        if (!diag) nsel += (unsigned long long)tcount;
+        if (!diag && part == 0) nsel += (unsigned long long)tcount;
         const int jmin = (csym && !diag) ? tstart + tcount : 0;   // symmetric: only sorted positions beyond the tile
         const int cza  = (int)((unsigned)At[0].z >> zsh), czb = (int)((unsigned)At[tcount - 1].z >> zsh);
         const int ncol = diag ? 1 : nx * ny;
-        for (int ci = 0; ci < ncol; ++ci)
+        for (int ci = diag ? 0 : part; ci < ncol; ci += diag ? 1 : split)
         {
             int pa[2], pb[2], np = 1;
             if (diag) { pa[0] = tstart; pb[0] = tstart + tcount; }
