@@ -1236,11 +1236,14 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
     const double nmin  = (double)std::min(p.n0, p.n1);
     double       bestc = 1e30;
     int          bestb = -1, bestr[3] = { 0, 0, 0 };
+    int force_bits = 0;   // experiment switch: cells per dimension = 2^B2A_RDF_CELL_BITS for every column-tiled accumulator
+    if (const char* e = getenv("B2A_RDF_CELL_BITS")) force_bits = columns ? atoi(e) : 0;
     for (int b = 2; b <= 7; ++b)
     {
         const int    nc = 1 << b;
         const double m  = nmin / ((double)nc * nc * nc);        // mean molecules per cell
-        if (m < (columns ? 3.0 : (ti >= 512 ? 48.0 : 12.0))) break;
+        if (force_bits && b != force_bits) continue;
+        if (!force_bits && m < (columns ? 0.2 : (ti >= 512 ? 48.0 : 12.0))) break;
         if ((unsigned long long)p.nslab << (3 * b) > (4ull << 20)) break;
         int  r[3];
         bool ok = false;
@@ -1268,14 +1271,29 @@ static bool choose_cells(b2a_ctx* c, const Acc& a, const RdfDev& p, bool sym_pos
         else
         {
             // a tile of TI molecules spans TI / m cells of its column (+1 for the alignment) and searches the union of their z
-            // ranges; every neighbour column costs a fixed ~64 j of tile edges, barriers and queue drains on top
+            // ranges; every neighbour run costs about four j-iterations of set-up (offsets, staging the first chunk) on top, and the
+            // last tile of a column is evaluated on half the register slots when it holds at most TI / 2 molecules.  Calibrated on
+            // config 5 (k3_rdf_cellw, 1.2 M waters x 8 k ions: 8^3 cells 0.44 ms, 16^3 0.32, 32^3 0.33; 8 k x 8 k ions: all pairs
+            // 0.32 ms, 16^3 or 32^3 cells 0.11): sparse groups want cells far finer than one molecule per cell, and then share the
+            // sorted view of the big group with its own pair.
             const double p0    = (double)p.n0 / ((double)nc * nc * nc);
             const double zc    = std::min((double)nc, 2.0 * r[2] + 1.0 + (double)TI / std::max(p0, 1e-9));
             const double col   = p0 * nc;                                  // molecules per i column
-            util               = col / (std::ceil(col / TI) * TI);
+            util               = col / (std::ceil(col / (TI / 2)) * (TI / 2));
             const double jrun  = zc * (double)p.n1 / ((double)nc * nc * nc);   // j molecules per neighbour column
-            frac               = (double)std::min(2 * r[0] + 1, nc) * std::min(2 * r[1] + 1, nc) * zc / ((double)nc * nc * nc);
-            cost               = frac / std::min(1.0, util) * (1.0 + 64.0 / std::max(jrun, 1.0)) * 1.1;
+            // neighbour columns the z reach table keeps (corners outside the cut-off sphere are dropped; first frame's box)
+            double       ncols = 0.0;
+            const int    wx = std::min(2 * r[0] + 1, nc), wy = std::min(2 * r[1] + 1, nc);
+            const bool   sphere = wx < nc && wy < nc && r[0] <= 7 && r[1] <= 7;
+            const double cwx = c->h_geom[0].L[0] / nc, cwy = c->h_geom[0].L[1] / nc;
+            for (int ix = 0; ix < wx; ++ix)
+                for (int iy = 0; iy < wy; ++iy)
+                {
+                    const double mx = std::max(std::abs(ix - wx / 2) - 1, 0) * cwx, my = std::max(std::abs(iy - wy / 2) - 1, 0) * cwy;
+                    if (!sphere || mx * mx + my * my <= p.Rm * p.Rm) ncols += 1.0;
+                }
+            frac               = ncols * zc / ((double)nc * nc * nc);
+            cost               = frac / std::min(1.0, util) * (1.0 + 4.0 / std::max(jrun, 1e-3)) * 1.1;
             // one block per tile: a small i side leaves most of the machine idle, where the all-pairs kernel would split j
             const double blocks = std::ceil(col / TI) * (double)nc * nc * c->nframes;
             cost /= std::min(1.0, blocks / (4.0 * c->sm_count));
