@@ -10,7 +10,8 @@
 //     of 13 -- and unlike per-warp sub-ranges inside a block tile (measured: the block's barriers keep the critical path at 13
 //     cells, +3 % only) the saving is not waited away;
 //   * several j-iterations share one candidate test (B2A_CW_J2): independent dependency chains in flight, one vote and one branch;
-//   * the warps of a block share only the histogram (zeroed at the start, flushed with the block's weight at the end).
+//   * a block is one warp by default (B2A_CW_NW; several warps would share the histogram -- zeroed at the start, flushed with the
+//     block's weight at the end -- and wait for each other there).
 // Symmetric evaluation in cell mode (same molecules on both sides, every molecule of the frame in ONE slab): the j side is the i
 // side's own sorted array, and a pair of sorted positions t1 < t2 is evaluated once, by the tile that holds t1, with weight 2 (the
 // neighbourhood relation of cells is symmetric, so t1 lies in the j runs of t2's tile exactly when t2 lies in the j runs of t1's);
@@ -31,8 +32,8 @@ constexpr int kCwTile  = 32 * kCwIPT;
 #endif
 constexpr int kCwQueue = 96 + 32 * (B2A_CW_J2 > 1 ? B2A_CW_J2 : 1);   // candidate entries per warp; drained from 96 up, a test adds at most 32 per j-iteration
 #ifndef B2A_CW_NW
-#define B2A_CW_NW 2
-#endif
+#define B2A_CW_NW 1              // warps per block (measured on config 5 with four j per test: 1 -> 126.8 frames/s, 2 -> 121.1: a warp whose
+#endif                           // tile is done -- a column's short last tile above all -- frees its slot at once instead of waiting for its sibling)
 #ifndef B2A_CW_WARPS_PER_SM
 #define B2A_CW_WARPS_PER_SM 20   // launch bound: 20 warps per SM = 96 registers
 #endif
