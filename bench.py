@@ -667,7 +667,7 @@ def roofline_of(res, world):
             # overlap; the honest denominator is the whole step (centres and sorting included)
             ach = res["evaluated_pairs"] * ISSUE_SLOTS_PER_PAIR / (res["tot_ms"] * 1e-3)
             share = None
-        rf = {"bound": "fp32_issue", "kernel": kname, "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "Tinst/s",
+        rf = {"bound": "fp32_issue", "kernel": "k3_rdf_cellw" if wl.name == "c5" else kname, "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "Tinst/s",
               "frac": ach / peak if peak else None,
               "traffic": K3_NCU["dram_bytes_per_frame"] * res["F"] if wl.name == "c2" else None,
               "traffic_unit": f"bytes per k3_rdf launch (ncu, {K3_NCU['source']})",
@@ -677,7 +677,7 @@ def roofline_of(res, world):
               "kernel_ms_per_launch": k_ms / max(k_n, 1), "share_of_step": share}
         if concurrent:
             rf["how"] = (f"evaluated pairs of a step x {ISSUE_SLOTS_PER_PAIR} issue slots / CUDA-event duration of the WHOLE step: the {len(wl.accs)} "
-                         "accumulators' k3_rdf launches overlap on their own streams, so no per-launch time exists; centres, cell sorting and slab "
+                         "accumulators' k3_rdf_cellw (cell-binned, one tile per warp) launches overlap on their own streams, so no per-launch time exists; centres, cell sorting and slab "
                          "prep are inside the denominator; peak as for config 2")
             rf["kernel_ms_per_launch"] = None
         if wl.name == "c2":

@@ -19,4 +19,10 @@ ncu --set full --clock-control none --import-source on --kernel-name-base mangle
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-others --no-host-cpp > $out/${tag}_ncu_k3.log 2>&1
 # K4 of the config-4 box, distinct frames
 ncu --set full --clock-control none --import-source on -k regex:k_stream -c 1 -o $out/${tag}_k4 python tools/bench_k4.py --one > $out/${tag}_ncu_k4.log 2>&1
+# config 5: per-pair times of one frame, launch list, full capture of the water-water launch of the cell kernel
+python tools/bench_configs.py --only-c5 > $out/${tag}_c5_pairs.json 2>> $out/${tag}_bench.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $out/${tag}_c5_launches.csv \
+    python tools/bench_configs.py --only-c5 > $out/${tag}_ncu_c5l.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k3_rdf_cellw --launch-skip 0 --launch-count 1 -o $out/${tag}_cellw \
+    python tools/bench_configs.py --only-c5 > $out/${tag}_ncu_cellw.log 2>&1
 ls -la $out | tail -12
