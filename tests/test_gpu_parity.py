@@ -962,6 +962,55 @@ def test_rdf_cells_equal_brute_force_large(gpu_ctx_factory):
         assert int(res[0][1][st]) == int(res[1][1][st]) == int(res[2][1][st])
 
 
+@pytest.mark.parametrize("pair", ["blob-blob", "blob-sparse", "sparse-sparse", "blob-blob-slabs"])
+def test_rdf_cells_inhomogeneous(gpu_ctx_factory, pair):
+    """Cell mode away from the uniform liquid: a dense blob (columns holding twenty times the mean: a warp loops over several tiles;
+    most columns empty), a sparse group (cells far below one molecule each, runs of one or two molecules, last tiles of a few
+    molecules) and their cross pair -- against the oracle (bit-exact) and the all-pairs kernel, symmetric and not."""
+    rng = np.random.default_rng(20201020)
+    L, nA, nB, K = 12.0, 7000, 900, 2
+    f32 = np.float32
+    x = np.empty((K, nA + nB, 3), np.float32)
+    for f in range(K):
+        blob = rng.normal(6.0 + 0.3 * f, 0.55, size=(int(0.7 * nA), 3))
+        x[f, :nA] = np.concatenate([blob, rng.uniform(0.0, L, size=(nA - len(blob), 3))]).astype(np.float32)
+        x[f, nA:] = rng.uniform(-0.2 * L, 1.2 * L, size=(nB, 3)).astype(np.float32)      # some molecules outside the box: wrapped by the centre code
+    box9 = np.array([L, 0, 0, 0, L, 0, 0, 0, L], np.float32)
+    idx = {"blob": np.arange(nA, dtype=np.int32), "sparse": np.arange(nA, nA + nB, dtype=np.int32)}
+    a, b = pair.split("-")[:2]
+    slabs = pair.endswith("slabs")
+    spec = dict(_DEF)
+    if slabs: spec.update(nbin=3, low=2.0, up=10.5, dim=1, dim2=0, low2=1.0, up2=11.0)
+    else: spec.update(nbin=1)
+    Rm = f32(1.1); Rbin = port.rdf_rbin(Rm)
+    Lbox = np.array([L, L, L], np.float64)
+    exp = np.zeros((Rbin, spec["nbin"]), np.uint64)
+    for f in range(K):
+        ca = port.load_position_center(x[f], idx[a], 1, np.ones(1), Lbox)
+        cb = port.load_position_center(x[f], idx[b], 1, np.ones(1), Lbox)
+        h, _ = port.rdf_accum(ca, cb, Lbox, spec["nbin"], spec["low"], spec["up"], spec["dim"], spec["dim2"], spec["low2"], spec["up2"], Rm, Rbin)
+        exp += h.astype(np.uint64)
+    res = {}
+    for cells, sym in ((0, 0), (1, 0), (1, 1)):
+        ctx = gpu_ctx_factory(nA + nB, K)
+        ctx.set_group(0, idx[a], 1, np.ones(1), np.ones(1))
+        ctx.set_group(1, idx[b], 1, np.ones(1), np.ones(1))
+        acc = ctx.rdf_create(grp0=0, grp1=1, com0=0, com1=0, nbin=spec["nbin"], low=spec["low"], up=spec["up"], dim=spec["dim"], dim2=spec["dim2"],
+                             low2=spec["low2"], up2=spec["up2"], Rm=Rm, Rbin=Rbin)
+        ctx.rdf_tune(acc, sym, 0); ctx.rdf_cells(acc, cells)
+        ctx.submit(x, box9)
+        ctx.accumulate(acc)
+        got, st = ctx.read(acc, spec["nbin"] * Rbin)
+        res[(cells, sym)] = (got.reshape(Rbin, spec["nbin"]), st)
+        ctx.close()
+    for key, (got, st) in res.items():
+        assert np.array_equal(got, exp), key
+    n0, n1 = len(idx[a]), len(idx[b])
+    assert int(res[(1, 0)][1][lib.STAT_PAIRS]) < int(res[(0, 0)][1][lib.STAT_PAIRS]) <= n0 * n1 * K
+    if a == b and not slabs:
+        assert int(res[(1, 1)][1][lib.STAT_PAIRS]) < 0.6 * int(res[(1, 0)][1][lib.STAT_PAIRS])   # symmetric: about half the pairs
+
+
 # ---- GmxHandleFull: heterogeneous molecule sizes (SURVEY 8f-3) -----------------------------------------------------
 def test_handle_full_loaders_and_accumulators(gpu_ctx_factory):
     gold = np.load(os.path.join(GOLD, "loaders.npz"))
