@@ -1551,7 +1551,11 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         // symmetric evaluation appends the rows of the tiles against themselves (k3_rdf_cellw)
         const int    ny      = (int)std::min(64.0, std::max(1.0, std::ceil(1.5 * per_col / (kCwTile * kCwWarps))));
         const size_t smem_cw = (size_t)kCwWarps * (32 * sizeof(int4) + kCwQueue * sizeof(unsigned)) + 16 + (size_t)pc.kstride * 4;
-        cd.split = 1;   // measured on config 5: 2 -> -1 %, 3 -> -2 % (the tail of the launch is not a granularity problem)
+        // a tile is one block of one warp, and a launch of a few waves of equal blocks ends in a half-empty wave: deal the
+        // neighbour columns of every tile to two or three blocks while the launch is short (config 5, 6.9 waves per launch:
+        // split 1 / 2 / 3 / 4 -> 126.2 / 128.9 / 128.3 / 126.3 frames/s)
+        const double waves = (double)p.n0 / kCwTile * c->nframes / ((double)c->sm_count * (B2A_CW_WARPS_PER_SM / kCwWarps) * kCwWarps);
+        cd.split = waves >= 12.0 ? 1 : (waves >= 5.0 ? 2 : 3);
         if (const char* e = getenv("B2A_CW_SPLIT")) cd.split = std::max(1, std::min(8, atoi(e)));
         const dim3   grid(cd.nkeysA >> bits, (pc.sym_enabled ? cd.split + 1 : cd.split) * ny, c->nframes);
         if (a.paranoid)
