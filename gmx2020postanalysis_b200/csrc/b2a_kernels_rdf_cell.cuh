@@ -25,7 +25,10 @@
 namespace b2a
 {
 
-constexpr int kCwIPT   = 4;     // i-molecules per lane
+#ifndef B2A_CW_IPT
+#define B2A_CW_IPT 4
+#endif
+constexpr int kCwIPT   = B2A_CW_IPT;     // i-molecules per lane
 constexpr int kCwTile  = 32 * kCwIPT;
 #ifndef B2A_CW_J2
 #define B2A_CW_J2 4             // j-iterations per candidate test (measured on config 5: 1 -> 96.9 frames/s, 2 -> 106.0, 3 -> 105.5, 4 -> 107.4)
@@ -222,8 +225,8 @@ __global__ void __launch_bounds__(32 * NW, B2A_CW_WARPS_PER_SM / NW)
             if (jc + 32 + lane < jb) nxt = B[jc + 32 + lane];   // in flight while this chunk is evaluated
             const int cnt = min(32, jb - jc);
             if (tcount == TW) chunk(std::integral_constant<int, IPT>{}, std::false_type{}, jc, cnt);
-            else if (tcount > TW / 2) chunk(std::integral_constant<int, IPT>{}, std::true_type{}, jc, cnt);
-            else chunk(std::integral_constant<int, IPT / 2>{}, std::true_type{}, jc, cnt);   // at most 64 molecules: two slots per lane
+            else if (IPT < 4 || tcount > TW / 2) chunk(std::integral_constant<int, IPT>{}, std::true_type{}, jc, cnt);
+            else chunk(std::integral_constant<int, (IPT >= 4 ? IPT / 2 : IPT)>{}, std::true_type{}, jc, cnt);   // at most half a tile: half the slots
         }
     };
 
