@@ -107,7 +107,8 @@ class Workload:
             self.system = synth.water_box(166666, 17.09, seed=20200104)
             self.text = ("charge-centre dipole vectors + bisector orientation-angle histogram (calc_orient_mof, nAngle=90), "
                          "166 666 SPC/E = 499 998 atoms")
-            self.F, self.D = 128, 2                           # 768 MB per batch: the per-launch fixed cost (~16 us) is amortised
+            self.F, self.D = 384, 2                           # 2.3 GB per batch: a launch carries ~16 us of start-up, drain and tail (K4 alone:
+                                                              # 0.61 of the HBM peak per 64-frame launch, 0.69 per 128, 0.76 per 256)
             self.groups = [gi(self.system, "SOL")]
         elif name == "c5":
             self.L = 34.0
@@ -177,7 +178,7 @@ class Workload:
             ctx.accumulate(a)
         if self.kind == "orient":
             # the per-molecule dipole vectors, left on the device.  Queued AFTER the orientation kernel: K1 writes 24 B per molecule
-            # (512 MB per 128-frame batch), and a K4 launched right behind it shares HBM with that write-back (0.60 instead of 0.70 of peak)
+            # (4 MB per frame), and a K4 launched right behind it shares HBM with that write-back (0.60 instead of 0.70 of peak)
             ctx.centers_device(0, self.lib.COM_DIPOLE)
 
     def read_all(self, ctx, accs=None):
