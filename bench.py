@@ -683,6 +683,10 @@ def roofline_of(res, world):
             rf["kernel_ms_per_launch"] = None
         if wl.name == "c2":
             rf.update(issue_active=K3_NCU["issue_active"], inst_per_pair=K3_NCU["inst_per_pair"], ncu_source=K3_NCU["source"])
+        elif wl.name == "c5" and "cellw" in K3_NCU:      # the water-water launch of the sweep, captured alone
+            cw = K3_NCU["cellw"]
+            rf.update(issue_active=cw["issue_active"], inst_per_pair=cw["inst_per_pair"], ncu_source=K3_NCU["source"],
+                      traffic=cw["dram_bytes_per_frame"] * res["F"], traffic_unit="bytes per water-water k3_rdf_cellw launch (ncu)")
         return rf
     peak, prov = hbm_peak()
     bytes_per_launch = 12.0 * wl.atoms_per_frame * res["F"]      # one rvec per atom-frame; the histogram stays on chip
