@@ -1569,14 +1569,15 @@ static int accumulate_rdf(b2a_ctx* c, Acc& a)
         const int max_tiles = (p.n0 + TI - 1) / TI + std::min(nslab, p.n0);
         const int itiles    = std::max(1, (p.n0 + TI - 1) / TI);
         // j split: the grid runs in waves of `slots` resident blocks and the under-filled last wave is lost time, so offer
-        // about ten waves, but never chunks below two j tiles (per-block set-up, histogram zeroing and flush).  Measured on
+        // many waves, but never chunks below two j tiles (per-block set-up, histogram zeroing and flush).  Measured on
         // config 3 (31 i-tiles x 8 frames): 4.4 waves -> 0.75 of FP32 issue, 7 -> 0.78, 10.4 -> 0.79; config 2 full
-        // evaluation: 5.4 waves -> 0.85, 10.7 -> 0.87.
+        // evaluation: 5.4 waves -> 0.85, 10.7 -> 0.87; config 3 with 64-frame batches: 10 / 14 / 20 / 30 / 45 / 90 waves ->
+        // 1613 / 1629 / 1633 / 1641 / 1649 / 1649 frames/s (0.814 -> 0.833): shorter blocks also even out the SMs.
         const int resident = std::max(1, std::min(6, (int)((227 * 1024) / (smem + 1024))));   // 80 registers x 128 threads: 6
         // double-buffered j-tile only where its 8 KB do not cost a resident block
         dbuf = std::min(6, (int)((227 * 1024) / (smem + kTileJ * sizeof(int4) + 1024))) >= resident;
         if (const char* e = getenv("B2A_K3_DBUF")) dbuf = atoi(e) != 0;
-        int       waves    = 10;
+        int       waves    = 45;
         if (const char* e = getenv("B2A_K3_WAVES")) waves = std::max(1, atoi(e));
         int       jsplit   = std::max(1, (c->sm_count * resident * waves + itiles * c->nframes - 1) / (itiles * c->nframes));
         jsplit             = std::min(jsplit, std::max(1, p.n1 / (2 * kTileJ)));
