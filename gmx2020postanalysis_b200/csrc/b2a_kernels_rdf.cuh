@@ -25,6 +25,7 @@
 #pragma once
 
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
 
 #include "b2a_packed.cuh"
@@ -565,54 +566,62 @@ __global__ void __launch_bounds__(THREADS, (IPT == 8 && THREADS == 128) ? 6 : 1)
                 }
                 else
                 {
-                    // partial tile (the last tile of a slab / column): same packed arithmetic; i-slots beyond tcount add into the
-                    // trash word and never raise a candidate
-                    bool okq[IPT];
+                    // partial tile (the last tile of a slab): same packed arithmetic; i-slots beyond tcount add into the trash word and
+                    // never raise a candidate.  Full mode evaluates only the register slots that hold molecules: a tile of at most a
+                    // quarter / a half of TI molecules runs on 2 / 4 of the 8 slots (config 3: each of the five slabs ends in a tile of
+                    // ~100 molecules; +1.2 %).  The symmetric mode keeps the single loop: there the extra copies cost config 2 0.5 %.
+                    auto part_loop = [&](auto qn_c) {
+                        constexpr int QN = decltype(qn_c)::value;
+                        bool          okq[QN];
 #pragma unroll
-                    for (int q = 0; q < IPT; ++q) okq[q] = (int)(threadIdx.x + q * THREADS) < tcount;
+                        for (int q = 0; q < QN; ++q) okq[q] = (int)(threadIdx.x + q * THREADS) < tcount;
 #pragma unroll 1
-                    for (int j = js; j < je; ++j)
-                    {
-                        const int4 pj   = sj[j];
-                        unsigned   dacc = 0, kmin = 0xffffffffu;
-                        if (IPT % 2 == 0 && kPacked)
+                        for (int j = js; j < je; ++j)
                         {
-#pragma unroll
-                            for (int q = 0; q < IPT; q += 2)
+                            const int4 pj   = sj[j];
+                            unsigned   dacc = 0, kmin = 0xffffffffu;
+                            if (QN % 2 == 0 && kPacked)
                             {
-                                unsigned k1a, k2a, k1b, k2b;
-                                pair_bins2<CLAMP, CUBIC>(xi[q], yi[q], zi[q], xi[q + 1], yi[q + 1], zi[q + 1], pj, s_lo2, s_hi2, magic2, ay2, az2,
-                                                         r2max, k1a, k2a, k1b, k2b);
-                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(okq[q] ? (k1a * 4u + cb_ok) : (hist_sa - 4u)) : "memory");
-                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(okq[q + 1] ? (k1b * 4u + cb_ok) : (hist_sa - 4u)) : "memory");
-                                dacc += (okq[q] ? (k2a - k1a) : 0u) + (okq[q + 1] ? (k2b - k1b) : 0u);
-                                kmin = min(kmin, min(okq[q] ? k1a : 0xffffffffu, okq[q + 1] ? k1b : 0xffffffffu));
-                            }
-                        }
-                        else
-                        {
 #pragma unroll
-                            for (int q = 0; q < IPT; ++q)
-                            {
-                                unsigned k1, k2;
-                                pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
-                                const unsigned addr = okq[q] ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
-                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
-                                dacc += okq[q] ? (k2 - k1) : 0u;
-                                kmin = okq[q] ? min(kmin, k1) : kmin;
+                                for (int q = 0; q < QN; q += 2)
+                                {
+                                    unsigned k1a, k2a, k1b, k2b;
+                                    pair_bins2<CLAMP, CUBIC>(xi[q], yi[q], zi[q], xi[q + 1], yi[q + 1], zi[q + 1], pj, s_lo2, s_hi2, magic2, ay2, az2,
+                                                             r2max, k1a, k2a, k1b, k2b);
+                                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(okq[q] ? (k1a * 4u + cb_ok) : (hist_sa - 4u)) : "memory");
+                                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(okq[q + 1] ? (k1b * 4u + cb_ok) : (hist_sa - 4u)) : "memory");
+                                    dacc += (okq[q] ? (k2a - k1a) : 0u) + (okq[q + 1] ? (k2b - k1b) : 0u);
+                                    kmin = min(kmin, min(okq[q] ? k1a : 0xffffffffu, okq[q + 1] ? k1b : 0xffffffffu));
+                                }
                             }
-                        }
-                        if (PARANOID || dacc != 0 || kmin <= lowk)
-                        {
-                            const unsigned slot = carry + atomicAdd(qc, 1u);
-                            if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
                             else
                             {
-                                recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
-                                atomicAdd(&blk.stats[3], 1u);
+#pragma unroll
+                                for (int q = 0; q < QN; ++q)
+                                {
+                                    unsigned k1, k2;
+                                    pair_bins<CLAMP, CUBIC>(xi[q], yi[q], zi[q], pj, s_lo, s_hi, ay, az, r2max, k1, k2);
+                                    const unsigned addr = okq[q] ? (k1 * 4u + cb_ok) : (hist_sa - 4u);
+                                    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+                                    dacc += okq[q] ? (k2 - k1) : 0u;
+                                    kmin = okq[q] ? min(kmin, k1) : kmin;
+                                }
+                            }
+                            if (PARANOID || dacc != 0 || kmin <= lowk)
+                            {
+                                const unsigned slot = carry + atomicAdd(qc, 1u);
+                                if (slot < (unsigned)kQueueCap) queue[slot] = ((unsigned)(jt + j) << 7) | threadIdx.x;
+                                else
+                                {
+                                    recheck<IPT, THREADS, CLAMP, CUBIC, PARANOID>(&blk, threadIdx.x, pj, jt + j);
+                                    atomicAdd(&blk.stats[3], 1u);
+                                }
                             }
                         }
-                    }
+                    };
+                    if (MODE == 0 && IPT >= 8 && tcount <= (IPT / 4) * THREADS) part_loop(std::integral_constant<int, (MODE == 0 && IPT >= 8 ? IPT / 4 : IPT)>{});
+                    else if (MODE == 0 && IPT >= 4 && tcount <= (IPT / 2) * THREADS) part_loop(std::integral_constant<int, (MODE == 0 && IPT >= 4 ? IPT / 2 : IPT)>{});
+                    else part_loop(std::integral_constant<int, IPT>{});
                 }
                 drain(false);
             }
